@@ -1,0 +1,203 @@
+/* zsg_b200.h — C ABI of libzsg_b200.so: the ZSGNet per-batch hot path on B200 (sm_100a).
+ *
+ * The reference (TheShadow29/zsgnet-pytorch) has no native code and no FFI; every entry
+ * point below replaces a *library-op call site* of the reference hot path (SURVEY.md 2b /
+ * section 8a).  Each declaration cites the reference lines it stands in for.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless said otherwise;
+ *  - activations are NHWC float32 ("rows" = pixels, channels contiguous);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *    nothing and keeps no global state; the caller owns every buffer;
+ *  - return value: 0 on success, negative ZSG_E* code otherwise; zsg_last_error_string()
+ *    gives the text of the last failure on the calling thread.
+ */
+#ifndef ZSG_B200_H
+#define ZSG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZSG_OK 0
+#define ZSG_EINVAL (-1)   /* bad argument (shape, alignment, null pointer)          */
+#define ZSG_ECUDA (-2)    /* a CUDA runtime error was raised by the launch          */
+#define ZSG_EARCH (-3)    /* device is not sm_100 (tcgen05 path unavailable)        */
+
+typedef void* zsg_stream_t;
+
+const char* zsg_last_error_string(void);
+int zsg_abi_version(void);
+/* 1 if the current device can run the tcgen05 kernels (compute capability 10.x). */
+int zsg_device_supported(void);
+
+/* ----------------------------------------------------------------------------------------
+ * Row table: one 16-byte entry per GEMM row (= output pixel of a conv, or input pixel of a
+ * dgrad).  It makes the implicit-GEMM kernels geometry-agnostic: forward conv, data-gradient
+ * (stride 1 or 2), and the six-level shared head (mdl.py:379-380) are the same kernel.
+ *   base   element offset of this row's image plane (b,0,0,0) inside the input tensor
+ *   y0,x0  input coordinate of filter tap (0,0)
+ *   hin,win input plane size for this row (levels differ inside one launch)
+ *   out    element offset of this row in the output tensor
+ * -------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t base;
+  int16_t y0, x0;
+  int16_t hin, win;
+  int32_t out;
+} zsg_row_t;
+
+/* conv implicit GEMM:  y[row.out + n] = epi( sum_{r,s,c} pro(x[row.base + ((y0+r)/div*win + (x0+s)/div)*cin + c]) * w[n][r][s][c] )
+ * Replaces nn.Conv2d forward and its data-gradient on: torchvision resnet50 convs (mdl.py:149-156),
+ * FPN convs (fpn_resnet.py:157-172), head convs (mdl.py:235-244, 379-380), LSTM input projection
+ * (mdl.py:319).  Arithmetic: 3xTF32 on tcgen05 tensor cores (fp32-accurate), fp32 accumulate in TMEM. */
+typedef struct {
+  const float* x;          /* input activations                                             */
+  const float* w;          /* [cout][r][s][cin] (K-major)                                   */
+  float* y;                /* output                                                        */
+  const zsg_row_t* rows;   /* [m]                                                           */
+  int32_t m, cin, cout, r, s;
+  int32_t in_div;          /* 1: forward / stride-1 dgrad.  2: stride-2 dgrad (tap valid iff even) */
+  const float* in_scale;   /* optional per-input-channel affine applied on load (BatchNorm) */
+  const float* in_shift;
+  int32_t in_relu;         /* ReLU after the affine on load                                 */
+  const float* bias;       /* optional [cout]                                               */
+  int32_t out_relu;
+  const float* residual;   /* optional, indexed like y                                      */
+  int32_t accumulate;      /* y += result instead of y = result                             */
+  int32_t impl;            /* 0 = tcgen05 (product path), 1 = SIMT check kernel (tests only) */
+} zsg_conv_params;
+int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
+
+/* weight gradient: dw[n][r][s][c] += sum_rows dy[row.out + n] * pro(x[gather(row,r,s) + c]).
+ * Replaces the cuDNN wgrad inside loss.backward() (utils.py:412) for every conv above and the
+ * LSTM weight gradients.  dw must be zeroed by the caller (split-K partials are added atomically). */
+typedef struct {
+  const float* x;
+  const float* dy;
+  float* dw;               /* [cout][r][s][cin]                                              */
+  const zsg_row_t* rows;   /* the forward conv's table                                       */
+  int32_t m, cin, cout, r, s;
+  const float* in_scale;
+  const float* in_shift;
+  int32_t in_relu;
+  int32_t split_k;         /* 0 = choose automatically                                       */
+  int32_t impl;
+} zsg_wgrad_params;
+int zsg_conv_wgrad(const zsg_wgrad_params* p, zsg_stream_t stream);
+
+/* w [cout][r][s][cin] -> wt [cin][r][s][cout] with the taps flipped: the dgrad of a conv is the
+ * forward kernel applied to wt. */
+int zsg_weight_transpose_flip(const float* w, float* wt, int cout, int rs_r, int rs_s, int cin, zsg_stream_t stream);
+/* row-wise channel padding copy: dst[n][0:cdst] = src[n][0:csrc] (zero fill / truncate). */
+int zsg_pad_channels(const float* src, float* dst, int64_t n, int csrc, int cdst, zsg_stream_t stream);
+/* NCHW image -> NHWC with 4 channels (4th = 0) for the stem (mdl.py:149). */
+int zsg_nchw_to_nhwc4(const float* img, float* out, int b, int h, int w, zsg_stream_t stream);
+/* column sums: out[c] (+)= sum_rows x[row][c]   (bias gradients of FPN/head convs and LSTM). */
+int zsg_colsum(const float* x, float* out, int64_t rows, int c, int accumulate, zsg_stream_t stream);
+
+/* ---------------------------------- BatchNorm (training) ---------------------------------
+ * torchvision resnet50's 53 BatchNorm2d in train mode (mdl.py:149-156, utils.py:395).      */
+/* sums[0:c] = sum x, sums[c:2c] = sum x^2 (double; must be zeroed by the caller). */
+int zsg_bn_stats(const float* x, double* sums, int64_t rows, int c, zsg_stream_t stream);
+/* mean/invstd/scale/shift from the sums; updates running stats (momentum, unbiased var). */
+int zsg_bn_finalize(const double* sums, int64_t rows, int c, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                    float* scale, float* shift, zsg_stream_t stream);
+/* eval mode: scale/shift from running stats. */
+int zsg_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                       float eps, int c, float* scale, float* shift, zsg_stream_t stream);
+/* y = relu?( x*scale+shift  [+ r*rscale+rshift | + r] ) : the bottleneck tail (bn3 + shortcut + ReLU). */
+int zsg_bn_apply(const float* x, const float* scale, const float* shift, const float* r, const float* rscale,
+                 const float* rshift, int relu, float* y, int64_t rows, int c, zsg_stream_t stream);
+/* backward reduce: dz = dy * mask ; sums[0:c] = sum dz, sums[c:2c] = sum dz*xhat.
+ * mask_mode 0: none; 1: relu mask from (x*scale+shift) > 0; 2: relu mask from act_out > 0 (dz is also
+ * written to dz_out when non-null, for the shortcut path). */
+int zsg_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* invstd, const float* scale,
+                      const float* shift, const float* act_out, int mask_mode, float* dz_out, double* sums,
+                      int64_t rows, int c, zsg_stream_t stream);
+/* dx = gamma*invstd*(dz - s1/rows - xhat*s2/rows); dgamma = s2, dbeta = s1 (written once). */
+int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                     const float* scale, const float* shift, const float* act_out, int mask_mode,
+                     const double* sums, float* dx, float* dgamma, float* dbeta, int64_t rows, int c,
+                     zsg_stream_t stream);
+
+/* ------------------------------ pooling / resampling glue -------------------------------- */
+/* stem: y = maxpool3x3/2,p1( relu(x*scale+shift) )  (mdl.py:150-152). */
+int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const float* shift, float* y, int b, int h, int w,
+                            int c, int ho, int wo, zsg_stream_t stream);
+/* dx (w.r.t. the raw conv output is NOT taken here): da = grad w.r.t. relu(bn(x)) */
+int zsg_maxpool_bn_relu_bwd(const float* x, const float* scale, const float* shift, const float* dy, float* da,
+                            int b, int h, int w, int c, int ho, int wo, zsg_stream_t stream);
+/* dst += nearest_up(src) with host-computed index tables (fpn_resnet.py:161-162,166-167). */
+int zsg_upsample_add(float* dst, const float* src, const int32_t* idx_y, const int32_t* idx_x, int b, int ho,
+                     int wo, int hi, int wi, int c, zsg_stream_t stream);
+/* dsrc += sum over the dst pixels that read each src pixel. */
+int zsg_upsample_add_bwd(const float* ddst, float* dsrc, const int32_t* idx_y, const int32_t* idx_x, int b, int ho,
+                         int wo, int hi, int wi, int c, zsg_stream_t stream);
+/* global average pool (fpn_resnet.py:177) and its gradient (accumulating). */
+int zsg_avgpool_fwd(const float* x, float* y, int b, int hw, int c, zsg_stream_t stream);
+int zsg_avgpool_bwd(const float* dy, float* dx, int b, int hw, int c, zsg_stream_t stream);
+/* dx = (accumulate? dx : 0) + dy * (x > 0) */
+int zsg_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, int accumulate, zsg_stream_t stream);
+int zsg_axpy(const float* x, float* y, float a, int64_t n, zsg_stream_t stream); /* y += a*x */
+
+/* -------------------- language/grid tiling fusion (mdl.py:69-104) ------------------------
+ * fused[b][cell][0:256]=feat, [256:512]=lang[b], [512]=grid_y, [513]=grid_x, [514:cpad]=0, for the six
+ * levels packed level-major: level l occupies rows [b*cells_l + cell] after lvl_row_off[l].            */
+int zsg_fuse_lang_grid(const float* feat, const float* lang, const float* grid_yx, float* fused, int b,
+                       int total_cells, const int32_t* lvl_cells /*[6]*/, int nlvl, int cfeat, int clang, int cpad,
+                       zsg_stream_t stream);
+/* dfeat = dfused[..., 0:256] ; dlang[b][j] = sum_cells dfused[b][cell][256+j] */
+int zsg_unfuse_lang_grid(const float* dfused, float* dfeat, float* dlang, int b, int total_cells,
+                         const int32_t* lvl_cells, int nlvl, int cfeat, int clang, int cpad, zsg_stream_t stream);
+
+/* ---------------------------------- bi-LSTM (mdl.py:296-336) ----------------------------- */
+/* forward direction recurrence over t < len[b]; gx = qvec*W_ih^T precomputed ([B,T,512]).
+ * Saves gate activations / cell / previous-hidden sequences for BPTT.  lang[b][0:128] = h after len[b]. */
+int zsg_lstm_fwd_dir(const float* gx, const float* whh_t /*[128][512]*/, const float* b_ih, const float* b_hh,
+                     const float* h0 /*[B,128] per sample*/, const float* c0, const int32_t* lens, int b, int t,
+                     float* gates /*[B,T,512]*/, float* cs /*[B,T,128]*/, float* hprev /*[B,T,128]*/,
+                     float* lang /*[B,256]*/, zsg_stream_t stream);
+/* reverse direction: ONE step on token len-1 from (h0r,c0r) (mdl.py:326-328 read position len-1). */
+int zsg_lstm_rev_step(const float* qvec /*[B,T,E]*/, const float* wih /*[512][E]*/, const float* whh /*[512][128]*/,
+                      const float* b_ih, const float* b_hh, const float* h0, const float* c0, const int32_t* lens,
+                      int b, int t, int e, float* xlast /*[B,E]*/, float* gates /*[B,512]*/, float* lang /*[B,256]*/,
+                      zsg_stream_t stream);
+/* BPTT of the forward direction: dG [B,T,512] (zero for t>=len). */
+int zsg_lstm_bwd_dir(const float* dlang /*[B,256]*/, const float* whh /*[512][128]*/, const float* gates,
+                     const float* cs, const float* c0, const int32_t* lens, int b, int t, float* dgates,
+                     zsg_stream_t stream);
+int zsg_lstm_rev_step_bwd(const float* dlang, const float* gates /*[B,512]*/, const float* c0, int b,
+                          float* dgates /*[B,512]*/, zsg_stream_t stream);
+
+/* -------------------- anchor match + focal/smooth-L1 loss (loss.py:43-143) ----------------
+ * Fused forward + gradient.  IoU in float64 with the reference's exact op order (anchors.py:90-116),
+ * strict > thr, first-index argmax (bit-exact `pos`/`top1`).  att/reg may be strided views of one packed
+ * [B,A,5] buffer: *_stride are element strides per anchor.
+ * losses[0..2] = loss, cls_ls, box_ls (double); d_att/d_reg are gradients of `loss` (lamb_reg applied).
+ * workspace: zsg_match_loss_workspace_bytes(B).                                                        */
+size_t zsg_match_loss_workspace_bytes(int b);
+int zsg_match_loss(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride, const float* annot,
+                   const double* anchors, int b, int a, double match_thr, float alpha, float gamma, double lamb_reg,
+                   int use_multi, double* losses, float* d_att, int64_t d_att_stride, float* d_reg,
+                   int64_t d_reg_stride, int64_t* top1, uint8_t* pos, void* workspace, size_t ws_bytes,
+                   zsg_stream_t stream);
+
+/* -------------------------- evaluator (evaluator.py:48-117) ------------------------------
+ * best_ids = argmax sigmoid(att) (first index); Acc/MaxPos flags from the decoded box of that / the
+ * IoU-argmax anchor; pred_boxes in pixel x1y1x2y2 (double); metrics[0]=Acc, [1]=MaxPos (float).       */
+int zsg_eval(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride, const float* annot,
+             const double* anchors, const float* img_size /*[B,2] (h,w)*/, int b, int a, double iou_thr,
+             int64_t* best_ids, float* pred_scores, double* pred_boxes, float* metrics, zsg_stream_t stream);
+
+/* ------------------------------ Adam (main_dist.py:50) ----------------------------------- */
+int zsg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+             float eps, int step, float grad_scale, zsg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSG_B200_H */

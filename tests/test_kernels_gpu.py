@@ -1,0 +1,502 @@
+"""GPU parity tests of the individual C-ABI entry points (run on the B200 box with -m gpu).
+
+Checkers: the CPU oracle (oracle/zsg_oracle.py) for matching / loss / metric / LSTM, and plain
+fp32 PyTorch ops (TF32 disabled) for the convolution, BatchNorm and pooling kernels.
+Tolerances: integer/index outputs bit-exact; fp32 outputs 1e-4 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_npz
+
+gpu = pytest.mark.gpu
+pytestmark = gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def zsg():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    import zsg_b200
+    from zsg_b200 import ops, geometry, _lib
+    assert _lib.load().zsg_device_supported() == 1
+    return ops, geometry
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def rel_err(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------- loss / metric
+def run_loss(ops, att, bbx, annot, anchs, packed=False):
+    B, A = att.shape[0], att.shape[1]
+    d = att.device
+    if packed:
+        buf = torch.cat([bbx, att], dim=2).contiguous()          # [B,A,5]: box 0..3, logit 4
+        att_p, reg_p, sa, sr = buf.view(-1)[4:], buf, 5, 5
+        dbuf = torch.empty_like(buf)
+        datt_p, dreg_p = dbuf.view(-1)[4:], dbuf
+    else:
+        att_p, reg_p, sa, sr = att.contiguous(), bbx.contiguous(), 1, 4
+        datt, dreg = torch.empty(B, A, device=d), torch.empty(B, A, 4, device=d)
+        datt_p, dreg_p = datt, dreg
+    losses = torch.empty(3, dtype=torch.float64, device=d)
+    top1 = torch.empty(B, dtype=torch.int64, device=d)
+    pos = torch.empty(B, A, dtype=torch.uint8, device=d)
+    ws = ops.match_loss_workspace(B, d)
+    ops.match_loss(att_p, sa, reg_p, sr, annot, anchs, B, A, 0.6, 0.25, 2.0, 1.0, True, losses, datt_p, sa, dreg_p, sr,
+                   top1, pos, ws)
+    torch.cuda.synchronize()
+    if packed:
+        datt, dreg = dbuf[..., 4], dbuf[..., :4]
+    return losses.cpu(), datt.cpu(), dreg.cpu(), top1.cpu(), pos.cpu().bool()
+
+
+@pytest.mark.parametrize("name", ["rand8", "adv8", "rand3"])
+@pytest.mark.parametrize("packed", [False, True])
+def test_match_loss_vs_oracle_and_golden(zsg, golden_meta, name, packed):
+    ops, _ = zsg
+    from oracle import synth, zsg_oracle as zo
+    c = golden_meta["loss_cases"][name]
+    z = load_npz("loss_" + name)
+    B, seed = c["B"], c["seed"]
+    g = torch.Generator().manual_seed(seed)
+    batch = synth.make_batch(B, seed=seed, adversarial=c["adv"])
+    att = (torch.randn(B, synth.NUM_ANCHORS, 1, generator=g) * 1.5 - 3.0)
+    bbx = (torch.randn(B, synth.NUM_ANCHORS, 4, generator=g) * 0.7)
+    anchs = zo.default_anchors()
+    losses, datt, dreg, top1, pos = run_loss(ops, dev(att), dev(bbx), dev(batch["annot"]), dev(anchs), packed)
+    # bit-exact index work, against the golden dump of the real reference
+    assert np.array_equal(top1.numpy(), z["top1"])
+    assert np.array_equal(pos.nonzero().numpy().astype(np.int32), z["pos_idx"])
+    for i, k in enumerate(("loss", "cls_ls", "box_ls")):
+        assert losses[i].item() == pytest.approx(c[k], rel=RTOL)
+    np.testing.assert_allclose(datt[pos].numpy(), z["datt_pos"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(dreg[pos].numpy(), z["dbbx_pos"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(datt[:, ::97].numpy(), z["datt_stride"], rtol=RTOL, atol=1e-10)
+    assert float(dreg[~pos].abs().sum()) == 0.0
+
+
+def test_match_loss_large_batch_vs_oracle(zsg):
+    ops, _ = zsg
+    from oracle import synth, zsg_oracle as zo
+    B = 64
+    batch = synth.make_batch(B, seed=77, adversarial=True)
+    g = torch.Generator().manual_seed(5)
+    att = (torch.randn(B, synth.NUM_ANCHORS, 1, generator=g) * 2 - 3.0).requires_grad_(True)
+    bbx = (torch.randn(B, synth.NUM_ANCHORS, 4, generator=g)).requires_grad_(True)
+    anchs = zo.default_anchors()
+    ref = zo.zsg_loss(att, bbx, batch["annot"], anchs)
+    ref["loss"].backward()
+    losses, datt, dreg, top1, pos = run_loss(ops, dev(att.detach()), dev(bbx.detach()), dev(batch["annot"]), dev(anchs))
+    assert torch.equal(top1, ref["top1"]) and torch.equal(pos, ref["pos"])
+    for i, k in enumerate(("loss", "cls_ls", "box_ls")):
+        assert losses[i].item() == pytest.approx(ref[k].item(), rel=RTOL)
+    np.testing.assert_allclose(datt.numpy(), att.grad.squeeze(-1).numpy(), rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(dreg.numpy(), bbx.grad.numpy(), rtol=RTOL, atol=1e-10)
+
+
+def test_match_loss_rejects_bad_arguments(zsg):
+    ops, _ = zsg
+    from zsg_b200._lib import ZsgError
+    t = torch.zeros(8, device="cuda")
+    with pytest.raises(ZsgError):
+        ops.match_loss(t, 1, t, 4, t, t.double(), 0, 0, 0.6, 0.25, 2.0, 1.0, True, t.double(), t, 1, t, 4,
+                       t.long(), t.byte(), t.double())
+
+
+@pytest.mark.parametrize("name", ["rand8", "adv8"])
+def test_eval_vs_oracle_and_golden(zsg, golden_meta, name):
+    ops, _ = zsg
+    from oracle import synth, zsg_oracle as zo
+    c = golden_meta["loss_cases"][name]
+    z = load_npz("loss_" + name)
+    B, seed = c["B"], c["seed"]
+    g = torch.Generator().manual_seed(seed)
+    batch = synth.make_batch(B, seed=seed, adversarial=c["adv"])
+    att = (torch.randn(B, synth.NUM_ANCHORS, 1, generator=g) * 1.5 - 3.0)
+    bbx = (torch.randn(B, synth.NUM_ANCHORS, 4, generator=g) * 0.7)
+    anchs = zo.default_anchors()
+    A = synth.NUM_ANCHORS
+    best = torch.empty(B, dtype=torch.int64, device="cuda")
+    scores = torch.empty(B, device="cuda")
+    boxes = torch.empty(B, 4, dtype=torch.float64, device="cuda")
+    metrics = torch.empty(2 + 2 * B, device="cuda")
+    ops.evaluate(dev(att), 1, dev(bbx), 4, dev(batch["annot"]), dev(anchs), dev(batch["img_size"]), B, A, 0.5, best,
+                 scores, boxes, metrics)
+    torch.cuda.synchronize()
+    assert np.array_equal(best.cpu().numpy(), z["best_ids"])
+    assert metrics[0].item() == c["Acc"] and metrics[1].item() == c["MaxPos"]
+    np.testing.assert_allclose(boxes.cpu().numpy(), z["pred_boxes"], rtol=1e-6)
+    np.testing.assert_allclose(scores.cpu().numpy(), z["best"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------- convolution
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def khwc(w):
+    return w.permute(0, 2, 3, 1).contiguous()       # [cout][r][s][cin]
+
+
+CONV_CASES = [
+    # B, cin, H, W, cout, k, stride, pad
+    (2, 64, 19, 19, 64, 1, 1, 0),
+    (2, 64, 19, 19, 256, 3, 1, 1),
+    (3, 128, 20, 18, 128, 3, 2, 1),
+    (2, 256, 10, 10, 512, 1, 2, 0),
+    (2, 4, 61, 61, 64, 7, 2, 3),
+    (2, 256, 5, 5, 45, 3, 1, 1),
+    (5, 300, 4, 1, 512, 1, 1, 0),                   # LSTM input projection shape (K tail: 300 = 9*32+12)
+    (1, 520, 10, 10, 256, 3, 1, 1),                 # head conv0 with padded fusion channels
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_fwd_vs_torch(zsg, case, impl):
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    ref = F.conv2d(x, w, bias, stride=stride, padding=pad)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    y = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
+    op = ops.ConvOp(nhwc(x), khwc(w), y, rows, B * Ho * Wo, cin, cout, k, k, bias=bias, impl=impl)
+    op()
+    torch.cuda.synchronize()
+    assert rel_err(y, nhwc(ref)) < 2e-5
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_prologue_epilogue(zsg, impl):
+    """BatchNorm affine + ReLU on load (zero padding stays zero), bias, residual, ReLU on store."""
+    ops, geo = zsg
+    B, cin, H, W, cout = 2, 64, 13, 11, 128
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / 24).cuda()
+    sc, sh = (torch.rand(cin, generator=g) + 0.5).cuda(), torch.randn(cin, generator=g).cuda() * 0.3
+    res = torch.randn(B, cout, H, W, generator=g).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    a = F.relu(x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    ref = F.relu(F.conv2d(a, w, bias, padding=1) + res)
+    rows = geo.conv_rows(B, H, W, cin, H, W, cout, 1, 1).cuda()
+    y = torch.empty(B, H, W, cout, device="cuda")
+    ops.ConvOp(nhwc(x), khwc(w), y, rows, B * H * W, cin, cout, 3, 3, in_scale=sc, in_shift=sh, in_relu=True, bias=bias,
+               out_relu=True, residual=nhwc(res), impl=impl)()
+    torch.cuda.synchronize()
+    assert rel_err(y, nhwc(ref)) < 2e-5
+
+
+DGRAD_CASES = [(2, 64, 19, 19, 256, 3, 1, 1), (3, 128, 20, 18, 128, 3, 2, 1), (2, 256, 10, 10, 512, 1, 2, 0),
+               (2, 2048, 10, 10, 256, 3, 2, 1), (2, 256, 5, 5, 45, 3, 1, 1), (2, 64, 8, 8, 64, 1, 1, 0)]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_dgrad_vs_torch(zsg, case, impl):
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, cin, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    y = F.conv2d(x, w, None, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    Ho, Wo = y.shape[2], y.shape[3]
+    wk = khwc(w)
+    wt = torch.empty(cin, k, k, cout, device="cuda")
+    ops.weight_transpose_flip(wk, wt, cout, k, k, cin)
+    rows = geo.dgrad_rows(B, H, W, cin, Ho, Wo, cout, k, stride, pad).cuda()
+    dx = torch.empty(B, H, W, cin, device="cuda")
+    ops.ConvOp(nhwc(dy), wt, dx, rows, B * H * W, cout, cin, k, k, in_div=stride, impl=impl)()
+    torch.cuda.synchronize()
+    assert rel_err(dx, nhwc(x.grad)) < 2e-5
+
+
+WGRAD_CASES = [(2, 64, 19, 19, 256, 3, 1, 1), (3, 128, 20, 18, 128, 3, 2, 1), (2, 4, 61, 61, 64, 7, 2, 3),
+               (2, 256, 5, 5, 45, 3, 1, 1), (5, 300, 4, 1, 512, 1, 1, 0), (4, 1024, 19, 19, 256, 1, 1, 0)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_wgrad_vs_torch(zsg, case, impl):
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda().requires_grad_(True)
+    sc, sh = (torch.rand(cin, generator=g) + 0.5).cuda(), torch.randn(cin, generator=g).cuda() * 0.3
+    a = F.relu(x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    y = F.conv2d(a, w, None, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    Ho, Wo = y.shape[2], y.shape[3]
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    dw = torch.zeros(cout, k, k, cin, device="cuda")
+    ops.WgradOp(nhwc(x), nhwc(dy), dw, rows, B * Ho * Wo, cin, cout, k, k, in_scale=sc, in_shift=sh, in_relu=True,
+                impl=impl)()
+    torch.cuda.synchronize()
+    assert rel_err(dw, khwc(w.grad)) < 3e-5
+
+
+def test_conv_multilevel_shared_weights(zsg):
+    """The head applies one weight set to six levels in a single launch (mdl.py:379-380)."""
+    ops, geo = zsg
+    B, c, cout = 2, 64, 45
+    sizes = (7, 4, 2, 1)
+    g = torch.Generator().manual_seed(17)
+    w = (torch.randn(cout, c, 3, 3, generator=g) / 24).cuda()
+    xs = [torch.randn(B, c, s, s, generator=g).cuda() for s in sizes]
+    cells = sum(s * s for s in sizes)
+    xin = torch.cat([nhwc(x).reshape(-1) for x in xs])
+    tabs, in_off, a_off = [], 0, 0
+    A = cells * 9
+    for s in sizes:
+        # output scattered like permute_correctly + cat: [B, A, 5] with anchor-major packing
+        t = geo.conv_rows(B, s, s, c, s, s, cout, 1, 1, in_off=in_off)
+        tabs.append((t, s, a_off))
+        in_off += B * s * s * c
+        a_off += s * s * 9
+    import numpy as np
+    fixed = []
+    for t, s, ao in tabs:
+        arr = t.numpy().view(np.dtype([("base", "<i4"), ("y0", "<i2"), ("x0", "<i2"), ("hin", "<i2"), ("win", "<i2"),
+                                        ("out", "<i4")])).reshape(-1).copy()
+        idx = np.arange(arr.shape[0])
+        b, cell = idx // (s * s), idx % (s * s)
+        arr["out"] = (b * A + ao + cell * 9) * 5
+        fixed.append(torch.from_numpy(arr.view(np.uint8).reshape(-1, 16)))
+    rows = torch.cat(fixed).cuda()
+    out = torch.empty(B, A, 5, device="cuda")
+    ops.ConvOp(xin, khwc(w), out, rows, B * cells, c, cout, 3, 3)()
+    torch.cuda.synchronize()
+    ref = torch.cat([F.conv2d(x, w, None, padding=1).permute(0, 2, 3, 1).reshape(B, -1, 5) for x in xs], dim=1)
+    assert rel_err(out, ref) < 2e-5
+
+
+# ------------------------------------------------------------------------------- BatchNorm etc.
+def test_batchnorm_train_fwd_bwd(zsg):
+    ops, _ = zsg
+    B, C, H, W = 4, 256, 19, 17
+    g = torch.Generator().manual_seed(19)
+    x = (torch.randn(B, C, H, W, generator=g) * 2 + 0.7).cuda().requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda().requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.2).cuda().requires_grad_(True)
+    rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y_ref = F.relu(F.batch_norm(x, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5))
+    dy = torch.randn(y_ref.shape, generator=g).cuda()
+    y_ref.backward(dy)
+    rows = B * H * W
+    xn = nhwc(x.detach())
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    mean, invstd, scale, shift = (torch.empty(C, device="cuda") for _ in range(4))
+    ops.bn_stats(xn, sums, rows, C)
+    ops.bn_finalize(sums, rows, C, gamma.detach(), beta.detach(), 1e-5, 0.1, rm, rv, mean, invstd, scale, shift)
+    y = torch.empty_like(xn)
+    ops.bn_apply(xn, scale, shift, y, rows, C, relu=True)
+    torch.cuda.synchronize()
+    assert rel_err(y, nhwc(y_ref)) < 1e-5
+    assert rel_err(rm, rm_ref) < 1e-5 and rel_err(rv, rv_ref) < 1e-5
+    bsum = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    dyn = nhwc(dy)
+    ops.bn_bwd_reduce(dyn, xn, mean, invstd, bsum, rows, C, mask_mode=1, scale=scale, shift=shift)
+    dx, dgam, dbet = torch.empty_like(xn), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_bwd_apply(dyn, xn, mean, invstd, gamma.detach(), bsum, dx, dgam, dbet, rows, C, mask_mode=1, scale=scale,
+                     shift=shift)
+    torch.cuda.synchronize()
+    assert rel_err(dx, nhwc(x.grad)) < 1e-4
+    assert rel_err(dgam, gamma.grad) < 1e-4 and rel_err(dbet, beta.grad) < 1e-4
+
+
+def test_bottleneck_tail_and_mask_mode2(zsg):
+    ops, _ = zsg
+    rows, C = 1000, 512
+    g = torch.Generator().manual_seed(23)
+    x3, idt = torch.randn(rows, C, generator=g).cuda(), torch.randn(rows, C, generator=g).cuda()
+    sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    sc2, sh2 = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    y = torch.empty_like(x3)
+    ops.bn_apply(x3, sc, sh, y, rows, C, relu=True, r=idt)
+    torch.cuda.synchronize()
+    assert rel_err(y, F.relu(x3 * sc + sh + idt)) < 1e-6
+    ops.bn_apply(x3, sc, sh, y, rows, C, relu=True, r=idt, rscale=sc2, rshift=sh2)
+    torch.cuda.synchronize()
+    ref = F.relu(x3 * sc + sh + idt * sc2 + sh2)
+    assert rel_err(y, ref) < 1e-6
+    dy = torch.randn(rows, C, generator=g).cuda()
+    mean, invstd = torch.randn(C, generator=g).cuda(), (torch.rand(C, generator=g) + 0.5).cuda()
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    dz = torch.empty_like(dy)
+    ops.bn_bwd_reduce(dy, x3, mean, invstd, sums, rows, C, mask_mode=2, act_out=ref, dz_out=dz)
+    torch.cuda.synchronize()
+    dz_ref = dy * (ref > 0)
+    assert torch.equal(dz, dz_ref)
+    assert rel_err(sums[:C], dz_ref.double().sum(0)) < 1e-6
+    assert rel_err(sums[C:], (dz_ref * (x3 - mean) * invstd).double().sum(0)) < 1e-5
+
+
+def test_maxpool_upsample_avgpool(zsg, golden_meta):
+    ops, _ = zsg
+    g = torch.Generator().manual_seed(29)
+    B, C, H, W = 2, 64, 30, 30
+    x = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda() * 0.5
+    a = F.relu(x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    a.retain_grad()
+    y_ref = F.max_pool2d(a, 3, 2, 1)
+    dy = torch.randn(y_ref.shape, generator=g).cuda()
+    y_ref.backward(dy)
+    Ho, Wo = y_ref.shape[2:]
+    y = torch.empty(B, Ho, Wo, C, device="cuda")
+    xn = nhwc(x.detach())
+    ops.maxpool_bn_relu_fwd(xn, sc, sh, y, B, H, W, C, Ho, Wo)
+    da = torch.empty(B, H, W, C, device="cuda")
+    ops.maxpool_bn_relu_bwd(xn, sc, sh, nhwc(dy), da, B, H, W, C, Ho, Wo)
+    torch.cuda.synchronize()
+    assert torch.equal(y, nhwc(y_ref))
+    assert rel_err(da, nhwc(a.grad)) < 1e-6
+    # nearest upsample + add, with the reference's index tables
+    for key, idx in golden_meta["upsample_idx"].items():
+        hi, ho = (int(v) for v in key.split("->"))
+        src = torch.randn(B, 256, hi, hi, generator=g).cuda().requires_grad_(True)
+        dst = torch.randn(B, 256, ho, ho, generator=g).cuda()
+        ref = dst + F.interpolate(src, size=(ho, ho))
+        dref = torch.randn(ref.shape, generator=g).cuda()
+        ref.backward(dref)
+        it = torch.tensor(idx, dtype=torch.int32).cuda()
+        d = nhwc(dst)
+        ops.upsample_add(d, nhwc(src.detach()), it, it, B, ho, ho, hi, hi, 256)
+        dsrc = torch.zeros(B, hi, hi, 256, device="cuda")
+        ops.upsample_add_bwd(nhwc(dref), dsrc, it, it, B, ho, ho, hi, hi, 256)
+        torch.cuda.synchronize()
+        assert rel_err(d, nhwc(ref)) < 1e-6 and rel_err(dsrc, nhwc(src.grad)) < 1e-5
+    p7 = torch.randn(B, 256, 3, 3, generator=g).cuda()
+    out = torch.empty(B, 256, device="cuda")
+    ops.avgpool_fwd(nhwc(p7), out, B, 9, 256)
+    torch.cuda.synchronize()
+    assert rel_err(out, F.adaptive_avg_pool2d(p7, 1).flatten(1)) < 1e-6
+
+
+def test_fuse_unfuse_colsum_pad_adam(zsg):
+    ops, _ = zsg
+    from oracle import zsg_oracle as zo
+    g = torch.Generator().manual_seed(31)
+    B, sizes = 3, (5, 3, 1)
+    cells = [s * s for s in sizes]
+    tot = sum(cells)
+    feats = [torch.randn(B, s * s, 256, generator=g).cuda() for s in sizes]
+    lang = torch.randn(B, 256, generator=g).cuda()
+    grid = torch.cat([zo.make_grid(s, s).view(-1, 2) for s in sizes]).cuda()
+    fused = torch.empty(B * tot, 520, device="cuda")
+    ops.fuse_lang_grid(torch.cat([f.reshape(-1) for f in feats]), lang, grid, fused, B, tot, cells, 256, 256, 520)
+    torch.cuda.synchronize()
+    off, coff = 0, 0
+    for f, n in zip(feats, cells):
+        blk = fused[off:off + B * n].view(B, n, 520)
+        assert torch.equal(blk[..., :256], f)
+        assert torch.equal(blk[..., 256:512], lang[:, None, :].expand(B, n, 256))
+        assert torch.equal(blk[..., 512:514], grid[coff:coff + n][None].expand(B, n, 2))
+        assert float(blk[..., 514:].abs().sum()) == 0
+        off += B * n
+        coff += n
+    dfused = torch.randn(B * tot, 520, generator=g).cuda()
+    dfeat, dlang = torch.empty(B * tot, 256, device="cuda"), torch.empty(B, 256, device="cuda")
+    ops.unfuse_lang_grid(dfused, dfeat, dlang, B, tot, cells, 256, 256, 520)
+    torch.cuda.synchronize()
+    assert torch.equal(dfeat, dfused[:, :256])
+    ref, off = torch.zeros(B, 256, device="cuda"), 0
+    for n in cells:
+        ref += dfused[off:off + B * n].view(B, n, 520)[..., 256:512].sum(1)
+        off += B * n
+    assert rel_err(dlang, ref) < 1e-5
+    x = torch.randn(777, 45, generator=g).cuda()
+    out = torch.empty(45, device="cuda")
+    ops.colsum(x, out, 777, 45)
+    torch.cuda.synchronize()
+    assert rel_err(out, x.sum(0)) < 1e-5
+    src = torch.randn(64 * 49, 3, generator=g).cuda()
+    dst = torch.empty(64 * 49, 4, device="cuda")
+    ops.pad_channels(src, dst, 64 * 49, 3, 4)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, :3], src) and float(dst[:, 3].abs().sum()) == 0
+    img = torch.rand(2, 3, 9, 7, generator=g).cuda()
+    o4 = torch.empty(2, 9, 7, 4, device="cuda")
+    ops.nchw_to_nhwc4(img, o4)
+    torch.cuda.synchronize()
+    assert torch.equal(o4[..., :3], img.permute(0, 2, 3, 1))
+    # Adam, two steps, against torch.optim.Adam(betas=(0.9, 0.99)) (main_dist.py:50)
+    p = torch.randn(10001, generator=g).cuda()
+    p_ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3, betas=(0.9, 0.99))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in (1, 2):
+        gr = torch.randn(10001, generator=g).cuda()
+        p_ref.grad = gr.clone()
+        opt.step()
+        ops.adam(p, gr, m, v, p.numel(), 1e-3, 0.9, 0.99, 1e-8, step)
+    torch.cuda.synchronize()
+    assert rel_err(p, p_ref.detach()) < 1e-5
+
+
+# ------------------------------------------------------------------------------- LSTM
+def test_lstm_recurrences_vs_oracle(zsg):
+    ops, _ = zsg
+    from oracle import synth, zsg_oracle as zo
+    sd = synth.make_state_dict(0)
+    B, T, E, H = 5, 20, 300, 128
+    batch = synth.make_batch(B, seed=41, var_len=True)
+    torch.manual_seed(41)
+    h0, c0 = zo.draw_h0c0(B)
+    keys = [k for k in sd if k.startswith("lstm.")]
+    for k in keys:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    qv = batch["qvec"].clone().requires_grad_(True)
+    ref = zo.lstm_query(sd, qv, batch["qlens"], h0, c0)
+    dl = torch.randn(B, 2 * H, generator=torch.Generator().manual_seed(1))
+    ref.backward(dl)
+    lens = batch["qlens"].int()
+    _, perm = batch["qlens"].sort(0, descending=True)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(B)
+    d = "cuda"
+    gx = (batch["qvec"] @ sd["lstm.weight_ih_l0"].detach().t()).to(d).contiguous()     # the tensor-core part, tested elsewhere
+    gates, cs, hp = torch.empty(B, T, 4 * H, device=d), torch.empty(B, T, H, device=d), torch.empty(B, T, H, device=d)
+    lang = torch.empty(B, 2 * H, device=d)
+    W = {k: sd[k].detach().to(d).contiguous() for k in keys}
+    h0f, c0f, h0r, c0r = (dev(t) for t in (h0[0][inv], c0[0][inv], h0[1][inv], c0[1][inv]))
+    ops.lstm_fwd_dir(gx, W["lstm.weight_hh_l0"].t().contiguous(), W["lstm.bias_ih_l0"], W["lstm.bias_hh_l0"], h0f, c0f,
+                     lens.to(d), B, T, gates, cs, hp, lang)
+    xlast, rg = torch.empty(B, E, device=d), torch.empty(B, 4 * H, device=d)
+    ops.lstm_rev_step(dev(batch["qvec"]), W["lstm.weight_ih_l0_reverse"], W["lstm.weight_hh_l0_reverse"],
+                      W["lstm.bias_ih_l0_reverse"], W["lstm.bias_hh_l0_reverse"], h0r, c0r, lens.to(d), B, T, E, xlast,
+                      rg, lang)
+    torch.cuda.synchronize()
+    assert rel_err(lang, ref.detach()) < 1e-5
+    dg = torch.empty(B, T, 4 * H, device=d)
+    ops.lstm_bwd_dir(dev(dl), W["lstm.weight_hh_l0"], gates, cs, c0f, lens.to(d), B, T, dg)
+    dgr = torch.empty(B, 4 * H, device=d)
+    ops.lstm_rev_step_bwd(dev(dl), rg, c0r, B, dgr)
+    torch.cuda.synchronize()
+    dg2 = dg.view(B * T, 4 * H)
+    assert rel_err(dg2.t() @ dev(batch["qvec"]).view(B * T, E), sd["lstm.weight_ih_l0"].grad) < 1e-4
+    assert rel_err(dg2.t() @ hp.view(B * T, H), sd["lstm.weight_hh_l0"].grad) < 1e-4
+    assert rel_err(dg2.sum(0), sd["lstm.bias_ih_l0"].grad) < 1e-4
+    assert rel_err(dgr.t() @ xlast, sd["lstm.weight_ih_l0_reverse"].grad) < 1e-4
+    assert rel_err(dgr.t() @ h0r, sd["lstm.weight_hh_l0_reverse"].grad) < 1e-4
+    assert rel_err(dgr.sum(0), sd["lstm.bias_hh_l0_reverse"].grad) < 1e-4

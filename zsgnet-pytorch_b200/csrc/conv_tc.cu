@@ -1,0 +1,545 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, accumulators in TMEM).
+//
+// One kernel family serves every dense contraction of the hot path: ResNet-50 / FPN / head
+// convolutions forward, their data gradients (the same kernel over flipped-transposed weights),
+// the LSTM input projection (a 1x1 conv over B*T rows) and, in the wgrad kernel, every weight
+// gradient.  Geometry comes from a 16-byte row table (zsg_row_t), so strides, padding, the
+// stride-2 data gradient and the six-level shared head are data, not code.
+//
+// Arithmetic: fp32 in HBM; each operand tile is split on the fly into a TF32-exact high part
+// and a residual low part, and D += Ah*Bh + Ah*Bl + Al*Bh is issued as three kind::tf32 MMAs
+// (3xTF32): fp32-accurate products, fp32 accumulation in TMEM.  This is what lets the fp32
+// configuration meet the reference's 1e-4 tolerance while still running on the tensor pipe.
+//
+// CTA = 5 warps.  Warps 0-3: producers (im2col gather -> optional BatchNorm affine + ReLU ->
+// hi/lo split -> 128B-swizzled K-major smem tiles), then the epilogue (tcgen05.ld -> bias /
+// residual / ReLU -> global).  Warp 4: TMEM allocation and the single-thread MMA issue loop.
+// Stages are handed over with mbarriers: full[s] (128 producer arrivals after
+// fence.proxy.async), empty[s] and acc_full (tcgen05.commit).
+#include "common.cuh"
+
+namespace zsg {
+
+constexpr int TM = 128;             // tile rows = TMEM lanes
+constexpr int KB = 32;              // fp32 K elements per stage = one 128-byte swizzle row
+constexpr int NPROD = 128;          // producer / epilogue threads
+constexpr int NTHREADS = 160;
+constexpr int A_TILE_BYTES = TM * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("zsg conv: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// TF32-exact high part and fp32 residual (both representable: hi + lo == v exactly).
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
+__device__ __forceinline__ void store_split(uint8_t* tile_hi, uint8_t* tile_lo, int row, int chunk, float4 v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x);
+  split_tf32(v.y, h.y, l.y);
+  split_tf32(v.z, h.z, l.z);
+  split_tf32(v.w, h.w, l.w);
+  const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+  *reinterpret_cast<float4*>(tile_hi + off) = h;
+  *reinterpret_cast<float4*>(tile_lo + off) = l;
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int B_TILE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
+  // after the tiles: row table copy (TM * 16 B), barriers, tmem slot
+  static constexpr int ROWS_OFF = TILES_BYTES;
+  static constexpr int BAR_OFF = ROWS_OFF + TM * 16;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;   // + alignment slack
+};
+
+struct PipeBars {
+  uint32_t full[4], empty[4], acc_full, tmem_slot;
+};
+
+template <int BN>
+__device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int lane) {
+  using S = Smem<BN>;
+  PipeBars pb;
+  const uint32_t bar0 = smem_u32(sm + S::BAR_OFF);
+  for (int i = 0; i < 4; ++i) { pb.full[i] = bar0 + 8 * i; pb.empty[i] = bar0 + 32 + 8 * i; }
+  pb.acc_full = bar0 + 64;
+  pb.tmem_slot = bar0 + 80;
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = 0; i < S::STAGES; ++i) { mbar_init(pb.full[i], NPROD); mbar_init(pb.empty[i], 1); }
+      mbar_init(pb.acc_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(pb.tmem_slot, BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return pb;
+}
+
+// single-thread MMA issue loop over `nkb` K-blocks (3xTF32: hi*hi + hi*lo + lo*hi)
+template <int BN>
+__device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_d, int nkb) {
+  using S = Smem<BN>;
+  constexpr uint32_t idesc = umma_idesc_tf32(BN);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % S::STAGES;
+    mbar_wait(pb.full[s], (kb / S::STAGES) & 1);
+    tc_fence_after();
+    const uint32_t a_hi = smem_u32(sm + s * S::STAGE_BYTES);
+    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+    const uint32_t b_hi = a_lo + A_TILE_BYTES;
+    const uint32_t b_lo = b_hi + S::B_TILE_BYTES;
+#pragma unroll
+    for (int k = 0; k < KB / 8; ++k) {
+      const uint64_t dah = umma_desc_sw128(a_hi + 32 * k), dal = umma_desc_sw128(a_lo + 32 * k);
+      const uint64_t dbh = umma_desc_sw128(b_hi + 32 * k), dbl = umma_desc_sw128(b_lo + 32 * k);
+      umma_tf32(tmem_d, dal, dbh, idesc, (kb | k) != 0);
+      umma_tf32(tmem_d, dah, dbl, idesc, 1);
+      umma_tf32(tmem_d, dah, dbh, idesc, 1);
+    }
+    umma_commit(pb.empty[s]);          // frees the stage when the MMAs above have read it
+  }
+  umma_commit(pb.acc_full);            // accumulator complete
+}
+
+// ============================================================================================
+// forward / data-gradient kernel
+// ============================================================================================
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const zsg_conv_params p) {
+  using S = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * TM;
+  const int K = p.r * p.s * p.cin;
+  const int nkb = (K + KB - 1) / KB;
+
+  int4* rows_s = reinterpret_cast<int4*>(sm + S::ROWS_OFF);
+  if (tid < TM) {
+    int4 e = make_int4(0, 0, 0, 0);                       // hin = win = 0 => every tap out of bounds
+    if (m0 + tid < p.m) e = __ldg(reinterpret_cast<const int4*>(p.rows) + m0 + tid);
+    rows_s[tid] = e;
+  }
+  PipeBars pb = setup_pipeline<BN>(sm, warp, lane);       // contains __syncthreads
+  const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 80);
+
+  if (warp == 4) {
+    if (lane == 0) mma_loop<BN>(sm, pb, tmem_d, nkb);
+    __syncwarp();
+  } else {
+    // ------------------------------ producers ------------------------------
+    const int chunk = tid & 7;           // 16-byte chunk of the 128-byte K row
+    const int rsub = tid >> 3;           // 0..15
+    int c = chunk * 4, tap = 0, tr = 0, ts = 0;
+    while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
+    const int ntap = p.r * p.s;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S::STAGES;
+      mbar_wait(pb.empty[s], ((kb / S::STAGES) & 1) ^ 1);
+      uint8_t* a_hi = sm + s * S::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_TILE_BYTES;
+      uint8_t* b_hi = a_lo + A_TILE_BYTES;
+      uint8_t* b_lo = b_hi + S::B_TILE_BYTES;
+      const bool kvalid = tap < ntap;
+      // ---- A: im2col gather, 8 rows per thread, loads first ----
+      float4 va[8];
+      bool oka[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int4 e = rows_s[it * 16 + rsub];
+        int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+        const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+        bool ok = kvalid;
+        if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
+        ok = ok && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+        oka[it] = ok;
+        va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) va[it] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin + c));
+      }
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.in_scale && kvalid) {
+        sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + c));
+        sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + c));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        float4 v = va[it];
+        if (oka[it]) {
+          if (p.in_scale) {
+            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+            v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+          }
+          if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        }
+        store_split(a_hi, a_lo, it * 16 + rsub, chunk, v);
+      }
+      // ---- B: weights [cout][K], K contiguous ----
+      const int kk = kb * KB + chunk * 4;
+#pragma unroll
+      for (int it = 0; it < BN / 16; ++it) {
+        const int row = it * 16 + rsub;
+        const int n = n0 + row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kvalid && n < p.cout) v = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)n * K + kk));
+        store_split(b_hi, b_lo, row, chunk, v);
+      }
+      fence_proxy_async();
+      mbar_arrive(pb.full[s]);
+      // advance this thread's (tap, channel) by one K block
+      c += KB;
+      while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
+    }
+    // ------------------------------ epilogue ------------------------------
+    mbar_wait(pb.acc_full, 0);
+    tc_fence_after();
+    const int4 e = rows_s[tid];
+    const bool row_ok = (m0 + tid) < p.m;
+    float* yrow = p.y + (int64_t)e.w;
+    const float* rrow = p.residual ? p.residual + (int64_t)e.w : nullptr;
+    const bool vec_ok = ((p.cout & 3) == 0) && ((e.w & 3) == 0);
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t r[32];
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + cb * 32, r);
+      if (!row_ok) continue;
+      const int nb = n0 + cb * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int n = nb + j;
+        if (n >= p.cout) break;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[q] = __uint_as_float(r[j + q]);
+          if (n + q < p.cout) {
+            if (p.bias) v[q] += __ldg(p.bias + n + q);
+            if (rrow) v[q] += rrow[n + q];
+            if (p.accumulate) v[q] += yrow[n + q];
+            if (p.out_relu) v[q] = fmaxf(v[q], 0.f);
+          }
+        }
+        if (vec_ok && n + 3 < p.cout) {
+          *reinterpret_cast<float4*>(yrow + n) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (n + q < p.cout) yrow[n + q] = v[q];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_d, BN);
+}
+
+// ============================================================================================
+// weight-gradient kernel:  D[j = (tap,c)][n] = sum_pix X_gathered[pix][j] * dY[pix][n]
+// ============================================================================================
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const zsg_wgrad_params p, int kb_per_split) {
+  using S = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN;
+  const int j0 = blockIdx.y * TM;
+  const int Kt = p.r * p.s * p.cin;                         // rows of D
+  const int nkb_total = (p.m + KB - 1) / KB;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  int kb_end = kb_begin + kb_per_split;
+  if (kb_end > nkb_total) kb_end = nkb_total;
+  const int nkb = kb_end - kb_begin;                        // >= 1 by construction of the grid
+
+  PipeBars pb = setup_pipeline<BN>(sm, warp, lane);
+  const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 80);
+
+  if (warp == 4) {
+    if (lane == 0) mma_loop<BN>(sm, pb, tmem_d, nkb);
+    __syncwarp();
+  } else {
+    const int j = j0 + tid;                                 // this thread's D row = (tap, channel)
+    const bool jvalid = j < Kt;
+    int tap = 0, c = 0, tr = 0, ts = 0;
+    if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
+    float sc = 1.f, sh = 0.f;
+    if (p.in_scale && jvalid) { sc = __ldg(p.in_scale + c); sh = __ldg(p.in_shift + c); }
+    const int n = n0 + tid;
+    const bool nvalid = tid < BN && n < p.cout;
+    const int4* rows = reinterpret_cast<const int4*>(p.rows);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S::STAGES;
+      mbar_wait(pb.empty[s], ((i / S::STAGES) & 1) ^ 1);
+      uint8_t* a_hi = sm + s * S::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_TILE_BYTES;
+      uint8_t* b_hi = a_lo + A_TILE_BYTES;
+      uint8_t* b_lo = b_hi + S::B_TILE_BYTES;
+      const int pix0 = (kb_begin + i) * KB;
+#pragma unroll 2
+      for (int ch = 0; ch < 8; ++ch) {                       // 8 chunks of 4 pixels
+        float xa[4], yb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pix = pix0 + ch * 4 + q;
+          xa[q] = 0.f;
+          yb[q] = 0.f;
+          if (pix < p.m) {
+            const int4 e = __ldg(rows + pix);                // same address across the warp: broadcast
+            const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+            const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+            if (jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win) {
+              float v = __ldg(p.x + (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin + c);
+              if (p.in_scale) v = fmaf(v, sc, sh);
+              if (p.in_relu) v = fmaxf(v, 0.f);
+              xa[q] = v;
+            }
+            if (nvalid) yb[q] = __ldg(p.dy + (int64_t)e.w + n);
+          }
+        }
+        store_split(a_hi, a_lo, tid, ch, make_float4(xa[0], xa[1], xa[2], xa[3]));
+        if (tid < BN) store_split(b_hi, b_lo, tid, ch, make_float4(yb[0], yb[1], yb[2], yb[3]));
+      }
+      fence_proxy_async();
+      mbar_arrive(pb.full[s]);
+    }
+    // epilogue: lanes own consecutive j => coalesced reductions into dw[n][j]
+    mbar_wait(pb.acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t r[32];
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + cb * 32, r);
+      if (!jvalid) continue;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int nn = n0 + cb * 32 + q;
+        if (nn < p.cout) atomicAdd(p.dw + (int64_t)nn * Kt + j, __uint_as_float(r[q]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_d, BN);
+}
+
+// ============================================================================================
+// SIMT check kernels (tests only): the same gather semantics in plain fp32 FMAs, one thread
+// per output element.  Independent of every tcgen05 / smem-layout assumption above.
+// ============================================================================================
+__global__ void conv_simt_kernel(const zsg_conv_params p) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)p.m * p.cout) return;
+  const int n = (int)(idx % p.cout);
+  const int m = (int)(idx / p.cout);
+  const zsg_row_t e = p.rows[m];
+  const int K = p.r * p.s * p.cin;
+  float acc = 0.f;
+  for (int tr = 0; tr < p.r; ++tr)
+    for (int ts = 0; ts < p.s; ++ts) {
+      int yy = e.y0 + tr, xx = e.x0 + ts;
+      if (p.in_div == 2) {
+        if ((yy | xx) & 1) continue;
+        yy >>= 1;
+        xx >>= 1;
+      }
+      if ((unsigned)yy >= (unsigned)e.hin || (unsigned)xx >= (unsigned)e.win) continue;
+      const float* xp = p.x + (int64_t)e.base + (int64_t)(yy * e.win + xx) * p.cin;
+      const float* wp = p.w + (int64_t)n * K + (tr * p.s + ts) * p.cin;
+      for (int c = 0; c < p.cin; ++c) {
+        float v = xp[c];
+        if (p.in_scale) v = fmaf(v, p.in_scale[c], p.in_shift[c]);
+        if (p.in_relu) v = fmaxf(v, 0.f);
+        acc = fmaf(v, wp[c], acc);
+      }
+    }
+  if (p.bias) acc += p.bias[n];
+  if (p.residual) acc += p.residual[(int64_t)e.out + n];
+  if (p.accumulate) acc += p.y[(int64_t)e.out + n];
+  if (p.out_relu) acc = fmaxf(acc, 0.f);
+  p.y[(int64_t)e.out + n] = acc;
+}
+
+__global__ void wgrad_simt_kernel(const zsg_wgrad_params p) {
+  const int Kt = p.r * p.s * p.cin;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)p.cout * Kt) return;
+  const int j = (int)(idx % Kt);
+  const int n = (int)(idx / Kt);
+  const int tap = j / p.cin, c = j - tap * p.cin, tr = tap / p.s, ts = tap - tr * p.s;
+  float acc = 0.f;
+  for (int m = 0; m < p.m; ++m) {
+    const zsg_row_t e = p.rows[m];
+    const int yy = e.y0 + tr, xx = e.x0 + ts;
+    if ((unsigned)yy >= (unsigned)e.hin || (unsigned)xx >= (unsigned)e.win) continue;
+    float v = p.x[(int64_t)e.base + (int64_t)(yy * e.win + xx) * p.cin + c];
+    if (p.in_scale) v = fmaf(v, p.in_scale[c], p.in_shift[c]);
+    if (p.in_relu) v = fmaxf(v, 0.f);
+    acc = fmaf(v, p.dy[(int64_t)e.out + n], acc);
+  }
+  p.dw[idx] += acc;
+}
+
+template <int BN>
+static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+    attr_done = true;
+  }
+  dim3 grid((p.cout + BN - 1) / BN, (p.m + TM - 1) / TM);
+  conv_tc_kernel<BN><<<grid, NTHREADS, Smem<BN>::TOTAL, st>>>(p);
+  return check_launch("zsg_conv_fwd");
+}
+
+template <int BN>
+static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+    attr_done = true;
+  }
+  const int Kt = p.r * p.s * p.cin;
+  const int tiles = ((p.cout + BN - 1) / BN) * ((Kt + TM - 1) / TM);
+  const int nkb = (p.m + KB - 1) / KB;
+  int split = p.split_k;
+  if (split <= 0) {
+    split = (2 * num_sms() + tiles - 1) / tiles;
+    const int max_split = (nkb + 7) / 8;                    // at least 8 K-blocks per CTA
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+  }
+  if (split > nkb) split = nkb;
+  const int per = (nkb + split - 1) / split;
+  split = (nkb + per - 1) / per;                            // no empty splits
+  dim3 grid((p.cout + BN - 1) / BN, (Kt + TM - 1) / TM, split);
+  wgrad_tc_kernel<BN><<<grid, NTHREADS, Smem<BN>::TOTAL, st>>>(p, per);
+  return check_launch("zsg_conv_wgrad");
+}
+
+}  // namespace zsg
+
+using namespace zsg;
+
+extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
+  ZSG_REQUIRE(pp, "zsg_conv_fwd: null params");
+  const zsg_conv_params& p = *pp;
+  ZSG_REQUIRE(p.x && p.w && p.y && p.rows, "zsg_conv_fwd: null pointer");
+  ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.r > 0 && p.s > 0, "zsg_conv_fwd: empty problem");
+  ZSG_REQUIRE(p.cin > 0 && p.cin % 4 == 0, "zsg_conv_fwd: cin=%d must be a multiple of 4", p.cin);
+  ZSG_REQUIRE(p.in_div == 1 || p.in_div == 2, "zsg_conv_fwd: in_div must be 1 or 2");
+  ZSG_REQUIRE((((uintptr_t)p.x | (uintptr_t)p.w) & 15) == 0, "zsg_conv_fwd: x and w must be 16-byte aligned");
+  ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_fwd: in_scale without in_shift");
+  cudaStream_t st = as_stream(stream);
+  if (p.impl == 1) {
+    const int64_t n = (int64_t)p.m * p.cout;
+    conv_simt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    return check_launch("zsg_conv_fwd(simt)");
+  }
+  if (!zsg_device_supported()) { set_error("zsg_conv_fwd: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
+  return p.cout <= 64 ? launch_conv<64>(p, st) : launch_conv<128>(p, st);
+}
+
+extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
+  ZSG_REQUIRE(pp, "zsg_conv_wgrad: null params");
+  const zsg_wgrad_params& p = *pp;
+  ZSG_REQUIRE(p.x && p.dy && p.dw && p.rows, "zsg_conv_wgrad: null pointer");
+  ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.cin > 0 && p.r > 0 && p.s > 0, "zsg_conv_wgrad: empty problem");
+  ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_wgrad: in_scale without in_shift");
+  cudaStream_t st = as_stream(stream);
+  if (p.impl == 1) {
+    const int64_t n = (int64_t)p.cout * p.r * p.s * p.cin;
+    wgrad_simt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    return check_launch("zsg_conv_wgrad(simt)");
+  }
+  if (!zsg_device_supported()) { set_error("zsg_conv_wgrad: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
+  return p.cout <= 64 ? launch_wgrad<64>(p, st) : launch_wgrad<128>(p, st);
+}

@@ -1,0 +1,684 @@
+// HBM-bound glue of the ZSGNet hot path: BatchNorm (train) statistics / apply / backward,
+// stem max-pool, FPN nearest upsample + add, global average pool, language/grid tiling,
+// bias-gradient column sums, layout helpers and Adam.  All tensors NHWC float32, channel
+// counts multiples of 4 so that every access is a 16-byte vector, channels fastest => coalesced.
+#include <math.h>
+#include "common.cuh"
+
+namespace zsg {
+
+static inline int grid_for(int64_t work_items, int threads, int waves = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 fma4(float4 x, float4 s, float4 b) {
+  return make_float4(fmaf(x.x, s.x, b.x), fmaf(x.y, s.y, b.y), fmaf(x.z, s.z, b.z), fmaf(x.w, s.w, b.w));
+}
+__device__ __forceinline__ float4 relu4(float4 v) {
+  return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-channel reductions over rows.  Block = 256 threads = (256/cols) row lanes x cols float4
+// columns (cols = min(C/4, 256), power of two); grid.y walks column groups when C/4 > 256.
+// Partial sums: fp32 over 8-row chunks, then double; one double atomic per (block, channel).
+// ------------------------------------------------------------------------------------------
+template <int MODE>   // 0: stats (sum x, sum x^2); 1: bn backward (sum dz, sum dz*xhat)
+__global__ void __launch_bounds__(256) channel_reduce_kernel(
+    const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ act_out,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
+    const float* __restrict__ shift, int mask_mode, float* __restrict__ dz_out, double* __restrict__ sums,
+    int64_t rows, int C, int cols) {
+  const int lane_c = threadIdx.x % cols;
+  const int lane_r = threadIdx.x / cols;
+  const int rpb = 256 / cols;
+  const int c = (blockIdx.y * cols + lane_c) * 4;
+  double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  float4 mu = make_float4(0, 0, 0, 0), is = mu, sc = mu, sh = mu;
+  if (MODE == 1) {
+    mu = ld4(mean + c);
+    is = ld4(invstd + c);
+    if (mask_mode == 1) { sc = ld4(scale + c); sh = ld4(shift + c); }
+  }
+  const int64_t stride = (int64_t)gridDim.x * rpb;
+  int64_t r = (int64_t)blockIdx.x * rpb + lane_r;
+  while (r < rows) {
+    float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int it = 0; it < 8 && r < rows; ++it, r += stride) {
+      const size_t off = (size_t)r * C + c;
+      float4 v = ld4(x + off);
+      if (MODE == 0) {
+        f1[0] += v.x; f1[1] += v.y; f1[2] += v.z; f1[3] += v.w;
+        f2[0] = fmaf(v.x, v.x, f2[0]); f2[1] = fmaf(v.y, v.y, f2[1]);
+        f2[2] = fmaf(v.z, v.z, f2[2]); f2[3] = fmaf(v.w, v.w, f2[3]);
+      } else {
+        float4 g = ld4(dy + off);
+        if (mask_mode == 1) {
+          float4 a = fma4(v, sc, sh);
+          g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f;
+          g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+        } else if (mask_mode == 2) {
+          float4 a = ld4(act_out + off);
+          g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f;
+          g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+          if (dz_out) st4(dz_out + off, g);
+        }
+        f1[0] += g.x; f1[1] += g.y; f1[2] += g.z; f1[3] += g.w;
+        f2[0] = fmaf(g.x, (v.x - mu.x) * is.x, f2[0]); f2[1] = fmaf(g.y, (v.y - mu.y) * is.y, f2[1]);
+        f2[2] = fmaf(g.z, (v.z - mu.z) * is.z, f2[2]); f2[3] = fmaf(g.w, (v.w - mu.w) * is.w, f2[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a1[k] += (double)f1[k]; a2[k] += (double)f2[k]; }
+  }
+  __shared__ double sm[2][256][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sm[0][threadIdx.x][k] = a1[k]; sm[1][threadIdx.x][k] = a2[k]; }
+  __syncthreads();
+  if (lane_r == 0) {
+    for (int j = 1; j < rpb; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a1[k] += sm[0][j * cols + lane_c][k]; a2[k] += sm[1][j * cols + lane_c][k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&sums[c + k], a1[k]);
+      atomicAdd(&sums[C + c + k], a2[k]);
+    }
+  }
+}
+
+static int launch_channel_reduce(int mode, const float* x, const float* dy, const float* act_out, const float* mean,
+                                 const float* invstd, const float* scale, const float* shift, int mask_mode,
+                                 float* dz_out, double* sums, int64_t rows, int C, cudaStream_t st) {
+  ZSG_REQUIRE(C % 4 == 0 && C >= 4, "channel reduce: C=%d must be a multiple of 4", C);
+  int c4 = C / 4;
+  int cols = c4 >= 256 ? 256 : c4;
+  ZSG_REQUIRE((cols & (cols - 1)) == 0 && c4 % cols == 0, "channel reduce: C/4=%d must be a power of two", c4);
+  int rpb = 256 / cols;
+  int gy = c4 / cols;
+  int64_t want = (rows + (int64_t)rpb * 16 - 1) / ((int64_t)rpb * 16);
+  int64_t cap = (int64_t)num_sms() * 8 / gy;
+  int gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  dim3 grid(gx, gy);
+  if (mode == 0)
+    channel_reduce_kernel<0><<<grid, 256, 0, st>>>(x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out,
+                                                   sums, rows, C, cols);
+  else
+    channel_reduce_kernel<1><<<grid, 256, 0, st>>>(x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out,
+                                                   sums, rows, C, cols);
+  return check_launch("channel_reduce");
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t rows, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, float* mean, float* invstd, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double n = (double)rows;
+  double m = sums[c] / n;
+  double var = sums[C + c] / n - m * m;
+  if (var < 0.0) var = 0.0;
+  double is = 1.0 / sqrt(var + (double)eps);
+  mean[c] = (float)m;
+  invstd[c] = (float)is;
+  float sc = gamma[c] * (float)is;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  if (running_mean) {
+    double unb = rows > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void bn_eval_affine_kernel(const float* rm, const float* rv, const float* gamma, const float* beta,
+                                      float eps, int C, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float is = 1.0f / sqrtf(rv[c] + eps);
+  float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const float* __restrict__ r,
+                                                       const float* __restrict__ rscale,
+                                                       const float* __restrict__ rshift, int relu,
+                                                       float* __restrict__ y, int64_t n4, int c4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    float4 v = fma4(ld4(x + i * 4), ld4(scale + c), ld4(shift + c));
+    if (r) {
+      float4 q = ld4(r + i * 4);
+      if (rscale) q = fma4(q, ld4(rscale + c), ld4(rshift + c));
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (relu) v = relu4(v);
+    st4(y + i * 4, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ act_out, int mask_mode,
+    const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    int64_t rows, int C) {
+  const int c4 = C / 4;
+  const int64_t n4 = rows * c4;
+  const float inv_n = 1.0f / (float)rows;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)sums[c];
+      if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    float4 g = ld4(dy + i * 4), v = ld4(x + i * 4);
+    if (mask_mode == 1) {
+      float4 a = fma4(v, ld4(scale + c), ld4(shift + c));
+      g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f;
+      g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+    } else if (mask_mode == 2) {
+      float4 a = ld4(act_out + i * 4);
+      g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f;
+      g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+    }
+    const float4 mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c);
+    const float s1[4] = {(float)sums[c] * inv_n, (float)sums[c + 1] * inv_n, (float)sums[c + 2] * inv_n,
+                         (float)sums[c + 3] * inv_n};
+    const float s2[4] = {(float)sums[C + c] * inv_n, (float)sums[C + c + 1] * inv_n, (float)sums[C + c + 2] * inv_n,
+                         (float)sums[C + c + 3] * inv_n};
+    float4 o;
+    o.x = ga.x * is.x * (g.x - s1[0] - (v.x - mu.x) * is.x * s2[0]);
+    o.y = ga.y * is.y * (g.y - s1[1] - (v.y - mu.y) * is.y * s2[1]);
+    o.z = ga.z * is.z * (g.z - s1[2] - (v.z - mu.z) * is.z * s2[2]);
+    o.w = ga.w * is.w * (g.w - s1[3] - (v.w - mu.w) * is.w * s2[3]);
+    st4(dx + i * 4, o);
+  }
+}
+
+// ------------------------------------- stem max-pool ----------------------------------------
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float* __restrict__ y,
+                                                          int B, int H, int W, int C, int Ho, int Wo) {
+  const int c4 = C / 4;
+  const int64_t n = (int64_t)B * Ho * Wo * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    int64_t t = i / c4;
+    const int q = (int)(t % Wo); t /= Wo;
+    const int p = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = 2 * p - 1 + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = 2 * q - 1 + dx;
+        if (xx < 0 || xx >= W) continue;
+        float4 v = relu4(fma4(ld4(x + (((size_t)b * H + yy) * W + xx) * C + c), sc, sh));
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    st4(y + i * 4, m);
+  }
+}
+
+// gather form (deterministic, no atomics): an input pixel receives dy of every window whose FIRST
+// maximum (row-major scan over valid taps, like ATen's max_pool2d) is that pixel.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ dy, float* __restrict__ da, int B,
+                                                          int H, int W, int C, int Ho, int Wo) {
+  const int64_t n = (int64_t)B * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int xx = (int)(t % W); t /= W;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    const float sc = scale[c], sh = shift[c];
+    float acc = 0.f;
+    const int p0 = yy / 2, p1 = (yy + 1) / 2;     // windows p with 2p-1 <= yy <= 2p+1
+    const int q0 = xx / 2, q1 = (xx + 1) / 2;
+    for (int p = p0; p <= p1; ++p) {
+      if (p >= Ho) continue;
+      for (int q = q0; q <= q1; ++q) {
+        if (q >= Wo) continue;
+        float best = -INFINITY;
+        int by = -1, bx = -1;
+        for (int dyy = 0; dyy < 3; ++dyy) {
+          const int y2 = 2 * p - 1 + dyy;
+          if (y2 < 0 || y2 >= H) continue;
+          for (int dxx = 0; dxx < 3; ++dxx) {
+            const int x2 = 2 * q - 1 + dxx;
+            if (x2 < 0 || x2 >= W) continue;
+            const float v = fmaxf(fmaf(x[(((size_t)b * H + y2) * W + x2) * C + c], sc, sh), 0.f);
+            if (v > best) { best = v; by = y2; bx = x2; }
+          }
+        }
+        if (by == yy && bx == xx) acc += dy[(((size_t)b * Ho + p) * Wo + q) * C + c];
+      }
+    }
+    da[i] = acc;
+  }
+}
+
+// --------------------------------- FPN nearest upsample + add --------------------------------
+__global__ void __launch_bounds__(256) upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                           const int32_t* __restrict__ iy, const int32_t* __restrict__ ix,
+                                                           int B, int Ho, int Wo, int Hi, int Wi, int C) {
+  const int c4 = C / 4;
+  const int64_t n = (int64_t)B * Ho * Wo * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    int64_t t = i / c4;
+    const int x = (int)(t % Wo); t /= Wo;
+    const int y = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float4 d = ld4(dst + i * 4);
+    const float4 s = ld4(src + (((size_t)b * Hi + iy[y]) * Wi + ix[x]) * C + c);
+    d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+    st4(dst + i * 4, d);
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample_add_bwd_kernel(const float* __restrict__ ddst, float* __restrict__ dsrc,
+                                                               const int32_t* __restrict__ iy,
+                                                               const int32_t* __restrict__ ix, int B, int Ho, int Wo,
+                                                               int Hi, int Wi, int C) {
+  const int c4 = C / 4;
+  const int64_t n = (int64_t)B * Hi * Wi * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    int64_t t = i / c4;
+    const int xs = (int)(t % Wi); t /= Wi;
+    const int ys = (int)(t % Hi);
+    const int b = (int)(t / Hi);
+    float4 acc = ld4(dsrc + i * 4);
+    for (int y = 0; y < Ho; ++y) {
+      if (iy[y] != ys) continue;
+      for (int x = 0; x < Wo; ++x) {
+        if (ix[x] != xs) continue;
+        const float4 g = ld4(ddst + (((size_t)b * Ho + y) * Wo + x) * C + c);
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      }
+    }
+    st4(dsrc + i * 4, acc);
+  }
+}
+
+__global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int b = i / C, c = i % C;
+  float s = 0.f;
+  for (int k = 0; k < HW; ++k) s += x[((size_t)b * HW + k) * C + c];
+  y[i] = s / (float)HW;
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int HW, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW * C) return;
+  int c = i % C, b = i / (HW * C);
+  dx[i] += dy[b * C + c] / (float)HW;
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                       float* __restrict__ dx, int64_t n4, int accumulate) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 g = ld4(dy + i * 4), v = ld4(x + i * 4);
+    g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f;
+    g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+    if (accumulate) { float4 o = ld4(dx + i * 4); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+    st4(dx + i * 4, g);
+  }
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float a,
+                                                   int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+
+// ------------------------------ language / grid tiling fusion --------------------------------
+struct Levels { int cells[8]; int n; };
+
+__device__ __forceinline__ void locate_row(const Levels& lv, int B, int64_t row, int& lvl, int& b, int& cell,
+                                           int& cell_base) {
+  int64_t off = 0;
+  int cb = 0;
+  lvl = 0;
+  for (int l = 0; l < lv.n; ++l) {
+    const int64_t cnt = (int64_t)B * lv.cells[l];
+    if (row < off + cnt) { lvl = l; break; }
+    off += cnt;
+    cb += lv.cells[l];
+  }
+  const int64_t rr = row - off;
+  b = (int)(rr / lv.cells[lvl]);
+  cell = (int)(rr % lv.cells[lvl]);
+  cell_base = cb;
+}
+
+__global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ feat, const float* __restrict__ lang,
+                                                   const float* __restrict__ grid_yx, float* __restrict__ fused, int B,
+                                                   int total_cells, Levels lv, int cfeat, int clang, int cpad) {
+  const int p4 = cpad / 4;
+  const int64_t n = (int64_t)B * total_cells * p4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % p4) * 4;
+    const int64_t row = i / p4;
+    float4 v;
+    if (c < cfeat) {
+      v = ld4(feat + row * cfeat + c);
+    } else {
+      int lvl, b, cell, cb;
+      locate_row(lv, B, row, lvl, b, cell, cb);
+      if (c < cfeat + clang) {
+        v = ld4(lang + (size_t)b * clang + (c - cfeat));
+      } else if (c == cfeat + clang) {
+        v = make_float4(grid_yx[2 * (cb + cell)], grid_yx[2 * (cb + cell) + 1], 0.f, 0.f);
+      } else {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    st4(fused + i * 4, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) unfuse_feat_kernel(const float* __restrict__ dfused, float* __restrict__ dfeat,
+                                                          int64_t rows, int cfeat, int cpad) {
+  const int f4 = cfeat / 4;
+  const int64_t n = rows * f4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % f4) * 4;
+    const int64_t row = i / f4;
+    st4(dfeat + i * 4, ld4(dfused + row * cpad + c));
+  }
+}
+
+// one block per (sample, level): dlang[b][j] += sum over the level's cells
+__global__ void __launch_bounds__(256) unfuse_lang_kernel(const float* __restrict__ dfused, float* __restrict__ dlang,
+                                                          int B, Levels lv, int cfeat, int clang, int cpad) {
+  const int b = blockIdx.x, l = blockIdx.y;
+  int64_t off = 0;
+  for (int k = 0; k < l; ++k) off += (int64_t)B * lv.cells[k];
+  const float* base = dfused + (off + (int64_t)b * lv.cells[l]) * cpad + cfeat;
+  for (int j = threadIdx.x; j < clang; j += blockDim.x) {
+    float s = 0.f;
+    for (int cell = 0; cell < lv.cells[l]; ++cell) s += base[(size_t)cell * cpad + j];
+    atomicAdd(&dlang[(size_t)b * clang + j], s);
+  }
+}
+
+// ------------------------------------ layout helpers -----------------------------------------
+__global__ void __launch_bounds__(256) weight_transpose_flip_kernel(const float* __restrict__ w, float* __restrict__ wt,
+                                                                    int Cout, int R, int S, int Cin) {
+  const int64_t n = (int64_t)Cout * R * S * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes wt [cin][r][s][cout]
+    const int k = (int)(i % Cout);
+    int64_t t = i / Cout;
+    const int s = (int)(t % S); t /= S;
+    const int r = (int)(t % R);
+    const int c = (int)(t / R);
+    wt[i] = w[(((size_t)k * R + (R - 1 - r)) * S + (S - 1 - s)) * Cin + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           int64_t n, int cs, int cd) {
+  const int64_t tot = n * cd;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cd);
+    const int64_t r = i / cd;
+    dst[i] = c < cs ? src[r * cs + c] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc4_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                            int B, int H, int W) {
+  const int64_t n = (int64_t)B * H * W;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / plane, p = i % plane;
+    const float* s = img + b * 3 * plane + p;
+    st4(out + i * 4, make_float4(s[0], s[plane], s[2 * plane], 0.f));
+  }
+}
+
+// out[c] (+)= sum_rows x[row][c]; block = 32 x 8, each block owns 32 channels and a row slab
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows,
+                                                     int C) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ry; r < rows; r += (int64_t)gridDim.y * 8) s += x[(size_t)r * C + c];
+  sm[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) s += sm[j][threadIdx.x & 31];
+    atomicAdd(&out[c], s);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                   float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                                                   float gscale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace zsg
+
+using namespace zsg;
+
+extern "C" int zsg_bn_stats(const float* x, double* sums, int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && sums && rows > 0, "zsg_bn_stats: bad arguments");
+  return launch_channel_reduce(0, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, sums, rows, c,
+                               as_stream(stream));
+}
+
+extern "C" int zsg_bn_finalize(const double* sums, int64_t rows, int c, const float* gamma, const float* beta,
+                               float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                               float* invstd, float* scale, float* shift, zsg_stream_t stream) {
+  ZSG_REQUIRE(sums && gamma && beta && mean && invstd && scale && shift && rows > 0, "zsg_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, rows, c, gamma, beta, eps, momentum,
+                                                                      running_mean, running_var, mean, invstd, scale,
+                                                                      shift);
+  return check_launch("zsg_bn_finalize");
+}
+
+extern "C" int zsg_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma,
+                                  const float* beta, float eps, int c, float* scale, float* shift,
+                                  zsg_stream_t stream) {
+  ZSG_REQUIRE(running_mean && running_var && gamma && beta && scale && shift, "zsg_bn_eval_affine: null pointer");
+  bn_eval_affine_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(running_mean, running_var, gamma, beta, eps, c,
+                                                                         scale, shift);
+  return check_launch("zsg_bn_eval_affine");
+}
+
+extern "C" int zsg_bn_apply(const float* x, const float* scale, const float* shift, const float* r,
+                            const float* rscale, const float* rshift, int relu, float* y, int64_t rows, int c,
+                            zsg_stream_t stream) {
+  ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_bn_apply: bad arguments");
+  int64_t n4 = rows * (c / 4);
+  bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, n4,
+                                                                     c / 4);
+  return check_launch("zsg_bn_apply");
+}
+
+extern "C" int zsg_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* invstd,
+                                 const float* scale, const float* shift, const float* act_out, int mask_mode,
+                                 float* dz_out, double* sums, int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && x && mean && invstd && sums, "zsg_bn_bwd_reduce: null pointer");
+  ZSG_REQUIRE(mask_mode != 1 || (scale && shift), "zsg_bn_bwd_reduce: mask_mode 1 needs scale/shift");
+  ZSG_REQUIRE(mask_mode != 2 || act_out, "zsg_bn_bwd_reduce: mask_mode 2 needs act_out");
+  return launch_channel_reduce(1, x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out, sums, rows, c,
+                               as_stream(stream));
+}
+
+extern "C" int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* invstd,
+                                const float* gamma, const float* scale, const float* shift, const float* act_out,
+                                int mask_mode, const double* sums, float* dx, float* dgamma, float* dbeta,
+                                int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx && c % 4 == 0, "zsg_bn_bwd_apply: bad arguments");
+  bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
+      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dgamma, dbeta, rows, c);
+  return check_launch("zsg_bn_bwd_apply");
+}
+
+extern "C" int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const float* shift, float* y, int b, int h,
+                                       int w, int c, int ho, int wo, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_maxpool_bn_relu_fwd: bad arguments");
+  maxpool_fwd_kernel<<<grid_for((int64_t)b * ho * wo * (c / 4), 256), 256, 0, as_stream(stream)>>>(x, scale, shift, y,
+                                                                                                    b, h, w, c, ho, wo);
+  return check_launch("zsg_maxpool_bn_relu_fwd");
+}
+
+extern "C" int zsg_maxpool_bn_relu_bwd(const float* x, const float* scale, const float* shift, const float* dy,
+                                       float* da, int b, int h, int w, int c, int ho, int wo, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && scale && shift && dy && da, "zsg_maxpool_bn_relu_bwd: null pointer");
+  maxpool_bwd_kernel<<<grid_for((int64_t)b * h * w * c, 256, 16), 256, 0, as_stream(stream)>>>(x, scale, shift, dy, da,
+                                                                                                b, h, w, c, ho, wo);
+  return check_launch("zsg_maxpool_bn_relu_bwd");
+}
+
+extern "C" int zsg_upsample_add(float* dst, const float* src, const int32_t* idx_y, const int32_t* idx_x, int b,
+                                int ho, int wo, int hi, int wi, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(dst && src && idx_y && idx_x && c % 4 == 0, "zsg_upsample_add: bad arguments");
+  upsample_add_kernel<<<grid_for((int64_t)b * ho * wo * (c / 4), 256), 256, 0, as_stream(stream)>>>(
+      dst, src, idx_y, idx_x, b, ho, wo, hi, wi, c);
+  return check_launch("zsg_upsample_add");
+}
+
+extern "C" int zsg_upsample_add_bwd(const float* ddst, float* dsrc, const int32_t* idx_y, const int32_t* idx_x, int b,
+                                    int ho, int wo, int hi, int wi, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(ddst && dsrc && idx_y && idx_x && c % 4 == 0, "zsg_upsample_add_bwd: bad arguments");
+  upsample_add_bwd_kernel<<<grid_for((int64_t)b * hi * wi * (c / 4), 256), 256, 0, as_stream(stream)>>>(
+      ddst, dsrc, idx_y, idx_x, b, ho, wo, hi, wi, c);
+  return check_launch("zsg_upsample_add_bwd");
+}
+
+extern "C" int zsg_avgpool_fwd(const float* x, float* y, int b, int hw, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && y, "zsg_avgpool_fwd: null pointer");
+  avgpool_fwd_kernel<<<(b * c + 255) / 256, 256, 0, as_stream(stream)>>>(x, y, b, hw, c);
+  return check_launch("zsg_avgpool_fwd");
+}
+extern "C" int zsg_avgpool_bwd(const float* dy, float* dx, int b, int hw, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && dx, "zsg_avgpool_bwd: null pointer");
+  avgpool_bwd_kernel<<<(b * hw * c + 255) / 256, 256, 0, as_stream(stream)>>>(dy, dx, b, hw, c);
+  return check_launch("zsg_avgpool_bwd");
+}
+
+extern "C" int zsg_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, int accumulate,
+                            zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && x && dx && n % 4 == 0, "zsg_relu_bwd: bad arguments");
+  relu_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(dy, x, dx, n / 4, accumulate);
+  return check_launch("zsg_relu_bwd");
+}
+
+extern "C" int zsg_axpy(const float* x, float* y, float a, int64_t n, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && y, "zsg_axpy: null pointer");
+  axpy_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, y, a, n);
+  return check_launch("zsg_axpy");
+}
+
+static int make_levels(const int32_t* lvl_cells, int nlvl, Levels& lv) {
+  ZSG_REQUIRE(lvl_cells && nlvl >= 1 && nlvl <= 8, "levels: nlvl=%d out of range", nlvl);
+  lv.n = nlvl;
+  for (int i = 0; i < 8; ++i) lv.cells[i] = i < nlvl ? lvl_cells[i] : 0;
+  return ZSG_OK;
+}
+
+/* lvl_cells is a HOST array (six ints); everything else is device memory. */
+extern "C" int zsg_fuse_lang_grid(const float* feat, const float* lang, const float* grid_yx, float* fused, int b,
+                                  int total_cells, const int32_t* lvl_cells, int nlvl, int cfeat, int clang, int cpad,
+                                  zsg_stream_t stream) {
+  ZSG_REQUIRE(feat && lang && grid_yx && fused, "zsg_fuse_lang_grid: null pointer");
+  ZSG_REQUIRE(cfeat % 4 == 0 && clang % 4 == 0 && cpad % 4 == 0 && cpad >= cfeat + clang + 2,
+              "zsg_fuse_lang_grid: channel counts must be multiples of 4");
+  Levels lv;
+  if (int rc = make_levels(lvl_cells, nlvl, lv)) return rc;
+  fuse_kernel<<<grid_for((int64_t)b * total_cells * (cpad / 4), 256), 256, 0, as_stream(stream)>>>(
+      feat, lang, grid_yx, fused, b, total_cells, lv, cfeat, clang, cpad);
+  return check_launch("zsg_fuse_lang_grid");
+}
+
+extern "C" int zsg_unfuse_lang_grid(const float* dfused, float* dfeat, float* dlang, int b, int total_cells,
+                                    const int32_t* lvl_cells, int nlvl, int cfeat, int clang, int cpad,
+                                    zsg_stream_t stream) {
+  ZSG_REQUIRE(dfused && dfeat && dlang, "zsg_unfuse_lang_grid: null pointer");
+  Levels lv;
+  if (int rc = make_levels(lvl_cells, nlvl, lv)) return rc;
+  cudaStream_t st = as_stream(stream);
+  unfuse_feat_kernel<<<grid_for((int64_t)b * total_cells * (cfeat / 4), 256), 256, 0, st>>>(
+      dfused, dfeat, (int64_t)b * total_cells, cfeat, cpad);
+  cudaMemsetAsync(dlang, 0, (size_t)b * clang * sizeof(float), st);
+  unfuse_lang_kernel<<<dim3(b, nlvl), 256, 0, st>>>(dfused, dlang, b, lv, cfeat, clang, cpad);
+  return check_launch("zsg_unfuse_lang_grid");
+}
+
+extern "C" int zsg_weight_transpose_flip(const float* w, float* wt, int cout, int rs_r, int rs_s, int cin,
+                                         zsg_stream_t stream) {
+  ZSG_REQUIRE(w && wt, "zsg_weight_transpose_flip: null pointer");
+  weight_transpose_flip_kernel<<<grid_for((int64_t)cout * rs_r * rs_s * cin, 256), 256, 0, as_stream(stream)>>>(
+      w, wt, cout, rs_r, rs_s, cin);
+  return check_launch("zsg_weight_transpose_flip");
+}
+
+extern "C" int zsg_pad_channels(const float* src, float* dst, int64_t n, int csrc, int cdst, zsg_stream_t stream) {
+  ZSG_REQUIRE(src && dst && csrc > 0 && cdst > 0, "zsg_pad_channels: bad arguments");
+  pad_channels_kernel<<<grid_for(n * cdst, 256), 256, 0, as_stream(stream)>>>(src, dst, n, csrc, cdst);
+  return check_launch("zsg_pad_channels");
+}
+
+extern "C" int zsg_nchw_to_nhwc4(const float* img, float* out, int b, int h, int w, zsg_stream_t stream) {
+  ZSG_REQUIRE(img && out, "zsg_nchw_to_nhwc4: null pointer");
+  nchw_to_nhwc4_kernel<<<grid_for((int64_t)b * h * w, 256), 256, 0, as_stream(stream)>>>(img, out, b, h, w);
+  return check_launch("zsg_nchw_to_nhwc4");
+}
+
+extern "C" int zsg_colsum(const float* x, float* out, int64_t rows, int c, int accumulate, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && out && rows > 0 && c > 0, "zsg_colsum: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (!accumulate) cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), st);
+  int gx = (c + 31) / 32;
+  int64_t gy = (rows + 255) / 256;
+  int64_t cap = (int64_t)num_sms() * 8 / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(x, out, rows, c);
+  return check_launch("zsg_colsum");
+}
+
+extern "C" int zsg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, int step, float grad_scale, zsg_stream_t stream) {
+  ZSG_REQUIRE(p && g && m && v && step >= 1, "zsg_adam: bad arguments");
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2,
+                                                                grad_scale);
+  return check_launch("zsg_adam");
+}

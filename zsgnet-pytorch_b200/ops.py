@@ -1,0 +1,174 @@
+"""Tensor-level wrappers over the C ABI (include/zsg_b200.h).  torch supplies device memory and
+streams only; every computation below is a kernel of libzsg_b200.so."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvParams, WgradParams, call, ptr, stream
+
+IMPL_TC, IMPL_SIMT = 0, 1
+
+
+def _f32c(t):
+    assert t.dtype == torch.float32 and t.is_cuda, (t.dtype, t.device)
+    return t
+
+
+class ConvOp:
+    """One implicit-GEMM launch description with its parameter block kept alive (pointers are
+    fixed because the engine's buffers are static)."""
+
+    def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
+                 bias=None, out_relu=False, residual=None, accumulate=False, impl=IMPL_TC):
+        self.keep = (x, w, y, rows, in_scale, in_shift, bias, residual)
+        self.p = ConvParams(ptr(x), ptr(w), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
+                            ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(residual), int(accumulate), impl)
+        self.ref = C.byref(self.p)
+
+    def __call__(self):
+        call("zsg_conv_fwd", self.ref, stream())
+
+
+class WgradOp:
+    def __init__(self, x, dy, dw, rows, m, cin, cout, r, s, in_scale=None, in_shift=None, in_relu=False, split_k=0,
+                 impl=IMPL_TC):
+        self.keep = (x, dy, dw, rows, in_scale, in_shift)
+        self.dw = dw
+        self.p = WgradParams(ptr(x), ptr(dy), ptr(dw), ptr(rows), m, cin, cout, r, s, ptr(in_scale), ptr(in_shift),
+                             int(in_relu), split_k, impl)
+        self.ref = C.byref(self.p)
+
+    def __call__(self):
+        call("zsg_conv_wgrad", self.ref, stream())
+
+
+def weight_transpose_flip(w, wt, cout, r, s, cin):
+    call("zsg_weight_transpose_flip", ptr(w), ptr(wt), cout, r, s, cin, stream())
+
+
+def pad_channels(src, dst, n, csrc, cdst):
+    call("zsg_pad_channels", ptr(src), ptr(dst), n, csrc, cdst, stream())
+
+
+def nchw_to_nhwc4(img, out):
+    b, _, h, w = img.shape
+    call("zsg_nchw_to_nhwc4", ptr(img), ptr(out), b, h, w, stream())
+
+
+def colsum(x, out, rows, c, accumulate=False):
+    call("zsg_colsum", ptr(x), ptr(out), rows, c, int(accumulate), stream())
+
+
+def bn_stats(x, sums, rows, c):
+    call("zsg_bn_stats", ptr(x), ptr(sums), rows, c, stream())
+
+
+def bn_finalize(sums, rows, c, gamma, beta, eps, momentum, rm, rv, mean, invstd, scale, shift):
+    call("zsg_bn_finalize", ptr(sums), rows, c, ptr(gamma), ptr(beta), eps, momentum, ptr(rm), ptr(rv), ptr(mean),
+         ptr(invstd), ptr(scale), ptr(shift), stream())
+
+
+def bn_eval_affine(rm, rv, gamma, beta, eps, c, scale, shift):
+    call("zsg_bn_eval_affine", ptr(rm), ptr(rv), ptr(gamma), ptr(beta), eps, c, ptr(scale), ptr(shift), stream())
+
+
+def bn_apply(x, scale, shift, y, rows, c, relu, r=None, rscale=None, rshift=None):
+    call("zsg_bn_apply", ptr(x), ptr(scale), ptr(shift), ptr(r), ptr(rscale), ptr(rshift), int(relu), ptr(y), rows, c,
+         stream())
+
+
+def bn_bwd_reduce(dy, x, mean, invstd, sums, rows, c, mask_mode=0, scale=None, shift=None, act_out=None, dz_out=None):
+    call("zsg_bn_bwd_reduce", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(act_out), mask_mode,
+         ptr(dz_out), ptr(sums), rows, c, stream())
+
+
+def bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, rows, c, mask_mode=0, scale=None, shift=None,
+                 act_out=None):
+    call("zsg_bn_bwd_apply", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(scale), ptr(shift), ptr(act_out),
+         mask_mode, ptr(sums), ptr(dx), ptr(dgamma), ptr(dbeta), rows, c, stream())
+
+
+def maxpool_bn_relu_fwd(x, scale, shift, y, b, h, w, c, ho, wo):
+    call("zsg_maxpool_bn_relu_fwd", ptr(x), ptr(scale), ptr(shift), ptr(y), b, h, w, c, ho, wo, stream())
+
+
+def maxpool_bn_relu_bwd(x, scale, shift, dy, da, b, h, w, c, ho, wo):
+    call("zsg_maxpool_bn_relu_bwd", ptr(x), ptr(scale), ptr(shift), ptr(dy), ptr(da), b, h, w, c, ho, wo, stream())
+
+
+def upsample_add(dst, src, iy, ix, b, ho, wo, hi, wi, c):
+    call("zsg_upsample_add", ptr(dst), ptr(src), ptr(iy), ptr(ix), b, ho, wo, hi, wi, c, stream())
+
+
+def upsample_add_bwd(ddst, dsrc, iy, ix, b, ho, wo, hi, wi, c):
+    call("zsg_upsample_add_bwd", ptr(ddst), ptr(dsrc), ptr(iy), ptr(ix), b, ho, wo, hi, wi, c, stream())
+
+
+def avgpool_fwd(x, y, b, hw, c):
+    call("zsg_avgpool_fwd", ptr(x), ptr(y), b, hw, c, stream())
+
+
+def avgpool_bwd(dy, dx, b, hw, c):
+    call("zsg_avgpool_bwd", ptr(dy), ptr(dx), b, hw, c, stream())
+
+
+def relu_bwd(dy, x, dx, n, accumulate=False):
+    call("zsg_relu_bwd", ptr(dy), ptr(x), ptr(dx), n, int(accumulate), stream())
+
+
+def axpy(x, y, a, n):
+    call("zsg_axpy", ptr(x), ptr(y), a, n, stream())
+
+
+def _lvl(cells):
+    return (C.c_int32 * len(cells))(*cells)
+
+
+def fuse_lang_grid(feat, lang, grid_yx, fused, b, total_cells, cells, cfeat, clang, cpad):
+    call("zsg_fuse_lang_grid", ptr(feat), ptr(lang), ptr(grid_yx), ptr(fused), b, total_cells, _lvl(cells), len(cells),
+         cfeat, clang, cpad, stream())
+
+
+def unfuse_lang_grid(dfused, dfeat, dlang, b, total_cells, cells, cfeat, clang, cpad):
+    call("zsg_unfuse_lang_grid", ptr(dfused), ptr(dfeat), ptr(dlang), b, total_cells, _lvl(cells), len(cells), cfeat,
+         clang, cpad, stream())
+
+
+def lstm_fwd_dir(gx, whh_t, b_ih, b_hh, h0, c0, lens, b, t, gates, cs, hprev, lang):
+    call("zsg_lstm_fwd_dir", ptr(gx), ptr(whh_t), ptr(b_ih), ptr(b_hh), ptr(h0), ptr(c0), ptr(lens), b, t, ptr(gates),
+         ptr(cs), ptr(hprev), ptr(lang), stream())
+
+
+def lstm_rev_step(qvec, wih, whh, b_ih, b_hh, h0, c0, lens, b, t, e, xlast, gates, lang):
+    call("zsg_lstm_rev_step", ptr(qvec), ptr(wih), ptr(whh), ptr(b_ih), ptr(b_hh), ptr(h0), ptr(c0), ptr(lens), b, t, e,
+         ptr(xlast), ptr(gates), ptr(lang), stream())
+
+
+def lstm_bwd_dir(dlang, whh, gates, cs, c0, lens, b, t, dgates):
+    call("zsg_lstm_bwd_dir", ptr(dlang), ptr(whh), ptr(gates), ptr(cs), ptr(c0), ptr(lens), b, t, ptr(dgates), stream())
+
+
+def lstm_rev_step_bwd(dlang, gates, c0, b, dgates):
+    call("zsg_lstm_rev_step_bwd", ptr(dlang), ptr(gates), ptr(c0), b, ptr(dgates), stream())
+
+
+def match_loss_workspace(b, device):
+    n = _lib.load().zsg_match_loss_workspace_bytes(b)
+    return torch.empty((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+def match_loss(att, att_stride, reg, reg_stride, annot, anchors, b, a, thr, alpha, gamma, lamb, use_multi, losses,
+               d_att, d_att_stride, d_reg, d_reg_stride, top1, pos, ws):
+    call("zsg_match_loss", ptr(att), att_stride, ptr(reg), reg_stride, ptr(annot), ptr(anchors), b, a, thr, alpha,
+         gamma, lamb, int(use_multi), ptr(losses), ptr(d_att), d_att_stride, ptr(d_reg), d_reg_stride, ptr(top1),
+         ptr(pos), ptr(ws), ws.numel() * 8, stream())
+
+
+def evaluate(att, att_stride, reg, reg_stride, annot, anchors, img_size, b, a, thr, best_ids, scores, boxes, metrics):
+    call("zsg_eval", ptr(att), att_stride, ptr(reg), reg_stride, ptr(annot), ptr(anchors), ptr(img_size), b, a, thr,
+         ptr(best_ids), ptr(scores), ptr(boxes), ptr(metrics), stream())
+
+
+def adam(p, g, m, v, n, lr, b1, b2, eps, step, grad_scale=1.0):
+    call("zsg_adam", ptr(p), ptr(g), ptr(m), ptr(v), n, lr, b1, b2, eps, step, grad_scale, stream())
