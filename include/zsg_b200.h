@@ -65,6 +65,8 @@ typedef struct {
   int32_t in_relu;         /* ReLU after the affine on load                                 */
   const float* bias;       /* optional [cout]                                               */
   int32_t out_relu;
+  const float* out_mask;   /* optional, indexed like y: result = 0 where out_mask <= 0 (ReLU backward),
+                              applied after the bias and before residual / accumulate            */
   const float* residual;   /* optional, indexed like y                                      */
   int32_t accumulate;      /* y += result instead of y = result                             */
   int32_t impl;            /* 0 = tcgen05 (product path), 1 = SIMT check kernel (tests only) */
@@ -95,8 +97,12 @@ int zsg_weight_transpose_flip(const float* w, float* wt, int cout, int rs_r, int
 int zsg_pad_channels(const float* src, float* dst, int64_t n, int csrc, int cdst, zsg_stream_t stream);
 /* NCHW image -> NHWC with 4 channels (4th = 0) for the stem (mdl.py:149). */
 int zsg_nchw_to_nhwc4(const float* img, float* out, int b, int h, int w, zsg_stream_t stream);
-/* column sums: out[c] (+)= sum_rows x[row][c]   (bias gradients of FPN/head convs and LSTM). */
-int zsg_colsum(const float* x, float* out, int64_t rows, int c, int accumulate, zsg_stream_t stream);
+/* column sums: out[c] (+)= sum_rows x[row*ld + c]   (bias gradients of FPN/head convs and LSTM). */
+int zsg_colsum(const float* x, float* out, int64_t rows, int c, int ld, int accumulate, zsg_stream_t stream);
+/* dst[i][0:cdst] = src[rows[i].out + 0:csrc] (zero padded): turns the packed [B,A,5] head gradient
+ * (mdl.py:246-254 layout) back into level-major rows for the last head conv's backward. */
+int zsg_gather_rows(const float* src, const zsg_row_t* rows, float* dst, int64_t m, int csrc, int cdst,
+                    zsg_stream_t stream);
 
 /* ---------------------------------- BatchNorm (training) ---------------------------------
  * torchvision resnet50's 53 BatchNorm2d in train mode (mdl.py:149-156, utils.py:395).      */

@@ -32,7 +32,7 @@ def dev(t):
 
 
 def rel_err(a, b):
-    a, b = a.double().flatten(), b.double().flatten()
+    a, b = a.detach().cpu().double().flatten(), b.detach().cpu().double().flatten()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
@@ -221,9 +221,17 @@ def test_conv_dgrad_vs_torch(zsg, case, impl):
     wk = khwc(w)
     wt = torch.empty(cin, k, k, cout, device="cuda")
     ops.weight_transpose_flip(wk, wt, cout, k, k, cin)
-    rows = geo.dgrad_rows(B, H, W, cin, Ho, Wo, cout, k, stride, pad).cuda()
+    dyn = nhwc(dy)
+    cp = (cout + 3) // 4 * 4
+    if cp != cout:                                   # the 45-channel head output: pad to 48 (engine does the same)
+        wtp = torch.empty(cin, k, k, cp, device="cuda")
+        ops.pad_channels(wt, wtp, cin * k * k, cout, cp)
+        dyp = torch.empty(B, Ho, Wo, cp, device="cuda")
+        ops.pad_channels(dyn, dyp, B * Ho * Wo, cout, cp)
+        wt, dyn = wtp, dyp
+    rows = geo.dgrad_rows(B, H, W, cin, Ho, Wo, cp, k, stride, pad).cuda()
     dx = torch.empty(B, H, W, cin, device="cuda")
-    ops.ConvOp(nhwc(dy), wt, dx, rows, B * H * W, cout, cin, k, k, in_div=stride, impl=impl)()
+    ops.ConvOp(dyn, wt, dx, rows, B * H * W, cp, cin, k, k, in_div=stride, impl=impl)()
     torch.cuda.synchronize()
     assert rel_err(dx, nhwc(x.grad)) < 2e-5
 
@@ -369,7 +377,7 @@ def test_maxpool_upsample_avgpool(zsg, golden_meta):
     da = torch.empty(B, H, W, C, device="cuda")
     ops.maxpool_bn_relu_bwd(xn, sc, sh, nhwc(dy), da, B, H, W, C, Ho, Wo)
     torch.cuda.synchronize()
-    assert torch.equal(y, nhwc(y_ref))
+    assert rel_err(y, nhwc(y_ref)) < 1e-6          # fmaf vs mul+add in the affine: not bit-equal
     assert rel_err(da, nhwc(a.grad)) < 1e-6
     # nearest upsample + add, with the reference's index tables
     for key, idx in golden_meta["upsample_idx"].items():
@@ -428,8 +436,13 @@ def test_fuse_unfuse_colsum_pad_adam(zsg):
     x = torch.randn(777, 45, generator=g).cuda()
     out = torch.empty(45, device="cuda")
     ops.colsum(x, out, 777, 45)
+    rt = torch.from_numpy(np.zeros(777 * 4, dtype=np.int32)).view(777, 4)
+    rt[:, 3] = torch.arange(777, dtype=torch.int32).flip(0) * 45
+    gat = torch.empty(777, 48, device="cuda")
+    ops.gather_rows(x, rt.cuda(), gat, 777, 45, 48)
     torch.cuda.synchronize()
     assert rel_err(out, x.sum(0)) < 1e-5
+    assert torch.equal(gat[:, :45], x.flip(0)) and float(gat[:, 45:].abs().sum()) == 0
     src = torch.randn(64 * 49, 3, generator=g).cuda()
     dst = torch.empty(64 * 49, 4, device="cuda")
     ops.pad_channels(src, dst, 64 * 49, 3, 4)

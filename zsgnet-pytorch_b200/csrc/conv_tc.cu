@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const zsg_conv_par
     const bool row_ok = (m0 + tid) < p.m;
     float* yrow = p.y + (int64_t)e.w;
     const float* rrow = p.residual ? p.residual + (int64_t)e.w : nullptr;
+    const float* mrow = p.out_mask ? p.out_mask + (int64_t)e.w : nullptr;
     const bool vec_ok = ((p.cout & 3) == 0) && ((e.w & 3) == 0);
 #pragma unroll 1
     for (int cb = 0; cb < BN / 32; ++cb) {
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const zsg_conv_par
           v[q] = __uint_as_float(r[j + q]);
           if (n + q < p.cout) {
             if (p.bias) v[q] += __ldg(p.bias + n + q);
+            if (mrow && !(mrow[n + q] > 0.f)) v[q] = 0.f;
             if (rrow) v[q] += rrow[n + q];
             if (p.accumulate) v[q] += yrow[n + q];
             if (p.out_relu) v[q] = fmaxf(v[q], 0.f);
@@ -440,6 +442,7 @@ __global__ void conv_simt_kernel(const zsg_conv_params p) {
       }
     }
   if (p.bias) acc += p.bias[n];
+  if (p.out_mask && !(p.out_mask[(int64_t)e.out + n] > 0.f)) acc = 0.f;
   if (p.residual) acc += p.residual[(int64_t)e.out + n];
   if (p.accumulate) acc += p.y[(int64_t)e.out + n];
   if (p.out_relu) acc = fmaxf(acc, 0.f);

@@ -460,18 +460,28 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc4_kernel(const float* __restr
 
 // out[c] (+)= sum_rows x[row][c]; block = 32 x 8, each block owns 32 channels and a row slab
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows,
-                                                     int C) {
+                                                     int C, int ld) {
   __shared__ float sm[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
   float s = 0.f;
   if (c < C)
-    for (int64_t r = (int64_t)blockIdx.y * 8 + ry; r < rows; r += (int64_t)gridDim.y * 8) s += x[(size_t)r * C + c];
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ry; r < rows; r += (int64_t)gridDim.y * 8) s += x[(size_t)r * ld + c];
   sm[ry][threadIdx.x & 31] = s;
   __syncthreads();
   if (ry == 0 && c < C) {
     for (int j = 1; j < 8; ++j) s += sm[j][threadIdx.x & 31];
     atomicAdd(&out[c], s);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const zsg_row_t* __restrict__ rows,
+                                                          float* __restrict__ dst, int64_t m, int cs, int cd) {
+  const int64_t tot = m * cd;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cd);
+    const int64_t r = i / cd;
+    dst[i] = c < cs ? src[(int64_t)rows[r].out + c] : 0.f;
   }
 }
 
@@ -660,8 +670,15 @@ extern "C" int zsg_nchw_to_nhwc4(const float* img, float* out, int b, int h, int
   return check_launch("zsg_nchw_to_nhwc4");
 }
 
-extern "C" int zsg_colsum(const float* x, float* out, int64_t rows, int c, int accumulate, zsg_stream_t stream) {
-  ZSG_REQUIRE(x && out && rows > 0 && c > 0, "zsg_colsum: bad arguments");
+extern "C" int zsg_gather_rows(const float* src, const zsg_row_t* rows, float* dst, int64_t m, int csrc, int cdst,
+                               zsg_stream_t stream) {
+  ZSG_REQUIRE(src && rows && dst && m > 0 && csrc > 0 && cdst > 0, "zsg_gather_rows: bad arguments");
+  gather_rows_kernel<<<grid_for(m * cdst, 256), 256, 0, as_stream(stream)>>>(src, rows, dst, m, csrc, cdst);
+  return check_launch("zsg_gather_rows");
+}
+
+extern "C" int zsg_colsum(const float* x, float* out, int64_t rows, int c, int ld, int accumulate, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && out && rows > 0 && c > 0 && ld >= c, "zsg_colsum: bad arguments");
   cudaStream_t st = as_stream(stream);
   if (!accumulate) cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), st);
   int gx = (c + 31) / 32;
@@ -669,7 +686,7 @@ extern "C" int zsg_colsum(const float* x, float* out, int64_t rows, int c, int a
   int64_t cap = (int64_t)num_sms() * 8 / gx;
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
-  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(x, out, rows, c);
+  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(x, out, rows, c, ld);
   return check_launch("zsg_colsum");
 }
 

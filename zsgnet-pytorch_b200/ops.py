@@ -20,10 +20,11 @@ class ConvOp:
     fixed because the engine's buffers are static)."""
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
-                 bias=None, out_relu=False, residual=None, accumulate=False, impl=IMPL_TC):
-        self.keep = (x, w, y, rows, in_scale, in_shift, bias, residual)
+                 bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC):
+        self.keep = (x, w, y, rows, in_scale, in_shift, bias, out_mask, residual)
         self.p = ConvParams(ptr(x), ptr(w), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
-                            ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(residual), int(accumulate), impl)
+                            ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
+                            impl)
         self.ref = C.byref(self.p)
 
     def __call__(self):
@@ -56,8 +57,12 @@ def nchw_to_nhwc4(img, out):
     call("zsg_nchw_to_nhwc4", ptr(img), ptr(out), b, h, w, stream())
 
 
-def colsum(x, out, rows, c, accumulate=False):
-    call("zsg_colsum", ptr(x), ptr(out), rows, c, int(accumulate), stream())
+def colsum(x, out, rows, c, accumulate=False, ld=None):
+    call("zsg_colsum", ptr(x), ptr(out), rows, c, c if ld is None else ld, int(accumulate), stream())
+
+
+def gather_rows(src, rows, dst, m, csrc, cdst):
+    call("zsg_gather_rows", ptr(src), ptr(rows), ptr(dst), m, csrc, cdst, stream())
 
 
 def bn_stats(x, sums, rows, c):
