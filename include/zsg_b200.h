@@ -149,6 +149,9 @@ int zsg_avgpool_bwd(const float* dy, float* dx, int b, int hw, int c, zsg_stream
 /* dx = (accumulate? dx : 0) + dy * (x > 0) */
 int zsg_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, int accumulate, zsg_stream_t stream);
 int zsg_axpy(const float* x, float* y, float a, int64_t n, zsg_stream_t stream); /* y += a*x */
+/* x[i*stride + 0:width] *= (float)*scale, scale a DEVICE double: applies the incoming autograd gradient
+ * of the scalar loss (utils.py:410-412) without a host synchronisation. */
+int zsg_scale_dev(float* x, int64_t rows, int width, int64_t stride, const double* scale, zsg_stream_t stream);
 
 /* -------------------- language/grid tiling fusion (mdl.py:69-104) ------------------------
  * fused[b][cell][0:256]=feat, [256:512]=lang[b], [512]=grid_y, [513]=grid_x, [514:cpad]=0, for the six

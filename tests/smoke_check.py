@@ -1,0 +1,38 @@
+"""One small training step of the hot path on cuda:0, checked against the CPU oracle
+(used by __graft_entry__.smoke)."""
+import torch
+
+
+def run(B=2, seed=9):
+    import zsg_b200  # noqa: F401
+    from zsg_b200 import mdl, loss, evaluator
+    from oracle import synth, zsg_oracle as zo
+    assert torch.cuda.is_available(), "smoke() needs cuda:0"
+    torch.cuda.set_device(0)
+    cfg = synth.default_cfg()
+    cfg["device"] = "cuda"
+    ratios, scales = synth.ratios_scales(cfg)
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    crit = loss.get_default_loss(ratios, scales, cfg)
+    ev = evaluator.get_default_eval(ratios, scales, cfg)
+    net.load_state_dict(synth.make_state_dict(0), strict=True)
+    net.train()
+    cpu_batch = synth.make_batch(B, seed=seed, var_len=True)
+    batch = {k: v.cuda() for k, v in cpu_batch.items()}
+    torch.manual_seed(seed)
+    out = net(batch)
+    ls = crit(out, batch)
+    ls["loss"].mean().backward()
+    met = ev(out, batch)
+    torch.cuda.synchronize()
+    sd = synth.make_state_dict(0)
+    ols, omet, ograds, _, _ = zo.train_step(sd, cpu_batch, seed=seed, do_adam=False)
+    for k in ("loss", "cls_ls", "box_ls"):
+        a, b = ls[k].item(), ols[k].item()
+        assert abs(a - b) <= 1e-4 * abs(b), (k, a, b)
+    assert torch.equal(crit.last_top1.cpu(), ols["top1"]) and torch.equal(crit.last_pos.cpu().bool(), ols["pos"])
+    assert met["Acc"].item() == omet["Acc"].item()
+    g = net.get_parameter("backbone.encoder.conv1.weight").grad.cpu().double()
+    r = ograds["backbone.encoder.conv1.weight"].double()
+    assert float((g - r).norm() / r.norm()) < 2e-3
+    print(f"smoke: loss {ls['loss'].item():.6f} (oracle {ols['loss'].item():.6f}), Acc {met['Acc'].item()}")

@@ -1,0 +1,78 @@
+"""Host logic of the engine without a GPU: build the launch program on CPU tensors with the C-ABI call
+replaced by a recorder, and check the launch sequence, buffer bookkeeping and gradient-bucket marks."""
+import collections
+
+import pytest
+import torch
+
+
+@pytest.fixture()
+def recorded(monkeypatch):
+    import zsg_b200
+    from zsg_b200 import _lib, ops, engine, spec
+    calls = []
+
+    def fake_call(name, *args):
+        calls.append(name)
+        return 0
+    monkeypatch.setattr(ops, "call", fake_call)
+    monkeypatch.setattr(ops, "stream", lambda: 0)
+    monkeypatch.setattr(ops, "match_loss_workspace", lambda b, d: torch.empty(64, dtype=torch.float64))
+    return calls, engine, spec, ops
+
+
+def test_engine_program_builds_and_runs_on_host(recorded):
+    calls, engine, spec, ops = recorded
+    B, T = 2, 5
+    store = engine.ParamStore(torch.device("cpu"))
+    assert store.used % 64 == 0 and store.total > store.used
+    bufs = {}
+    for name, shp in spec.buffer_specs():
+        bufs[name] = torch.zeros(shp if len(shp) else (), dtype=torch.float32 if len(shp) else torch.long)
+    eng = engine.Engine(store, bufs, B, T, torch.device("cpu"))
+    assert len(eng.bns) == 53                                         # torchvision resnet50 has 53 BatchNorm2d
+    img = torch.rand(B, 3, 300, 300)
+    qvec = torch.randn(B, 4, 300)
+    lens = torch.tensor([4.0, 2.0])
+    inv = torch.tensor([0, 1])
+    eng.set_inputs(img, qvec, lens, inv, torch.randn(2, B, 128), torch.randn(2, B, 128))
+    del calls[:]
+    out = eng.forward(training=True)
+    assert out.shape == (B, spec.NUM_ANCHORS, 5)
+    fwd = collections.Counter(calls)
+    # 53 trunk convs + 8 FPN + 6 head + 1 LSTM projection
+    assert fwd["zsg_conv_fwd"] == 53 + 8 + 6 + 1
+    assert fwd["zsg_bn_stats"] == 53 and fwd["zsg_bn_finalize"] == 53 and fwd["zsg_bn_apply"] == 16
+    assert fwd["zsg_lstm_fwd_dir"] == 1 and fwd["zsg_lstm_rev_step"] == 1 and fwd["zsg_fuse_lang_grid"] == 1
+    del calls[:]
+    eng.forward(training=False)
+    ev = collections.Counter(calls)
+    assert ev["zsg_bn_stats"] == 0 and ev["zsg_bn_eval_affine"] == 53
+    del calls[:]
+    seen = []
+    eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5), on_bucket=lambda lo, hi: seen.append((lo, hi)))
+    bwd = collections.Counter(calls)
+    # every conv has a wgrad (+5 LSTM weight gradients... 4 LSTM matrices), every conv but the stem a dgrad
+    assert bwd["zsg_conv_wgrad"] == 53 + 8 + 6 + 4
+    assert bwd["zsg_conv_fwd"] == 52 + 8 + 6                           # data gradients run through the forward kernel
+    assert bwd["zsg_bn_bwd_reduce"] == 53 and bwd["zsg_bn_bwd_apply"] == 53
+    assert bwd["zsg_weight_transpose_flip"] == 52 + 8 + 6
+    # buckets: contiguous, ordered, covering the used arena exactly once
+    assert seen[0][0] == 0 and seen[-1][1] == store.used
+    for (a, b), (c, d) in zip(seen, seen[1:]):
+        assert b == c and a < b
+    assert len(seen) == 16 + 4
+
+
+def test_param_store_views_follow_reference_shapes(recorded):
+    _, engine, spec, _ = recorded
+    store = engine.ParamStore(torch.device("cpu"))
+    v = store.view("backbone.encoder.layer1.0.conv2.weight")
+    assert v.shape == (64, 64, 3, 3) and v.stride() == (576, 1, 192, 64)      # OIHW view of [O][H][W][I] storage
+    assert store.view("att_reg_box.0.0.weight").shape == (256, 514, 3, 3)
+    g = store.grad_view("lstm.weight_ih_l0")
+    assert g.shape == (512, 300) and g.is_contiguous()
+    # the unused fc sits behind the all-reduce / Adam range
+    assert store.offsets["backbone.encoder.fc.weight"] >= store.used
+    # head parameters come first (their gradients are final first)
+    assert store.offsets["att_reg_box.5.bias"] == 0

@@ -1,0 +1,131 @@
+"""End-to-end parity of the CUDA hot path through the reference-facing API (mdl / loss / evaluator):
+against the golden dumps of the real reference (tests/golden, B=2 and ragged B=3) and against the
+CPU oracle executed live.  Index outputs bit-exact; fp32 losses within 1e-4 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def stack():
+    assert torch.cuda.is_available()
+    import zsg_b200
+    from zsg_b200 import mdl, loss, evaluator
+    from oracle import synth
+    cfg = synth.default_cfg()
+    cfg["device"] = "cuda"
+    ratios, scales = synth.ratios_scales(cfg)
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    crit = loss.get_default_loss(ratios, scales, cfg)
+    ev = evaluator.get_default_eval(ratios, scales, cfg)
+    return net, crit, ev, synth
+
+
+def to_dev(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+def run_step(net, crit, ev, synth, B, seed, var_len, train=True):
+    net.load_state_dict(synth.make_state_dict(0), strict=True)
+    net.train(train)
+    net.zero_grad()
+    batch = to_dev(synth.make_batch(B, seed=seed, var_len=var_len))
+    torch.manual_seed(seed)                          # h0/c0 come from the global CPU RNG (mdl.py:279-294)
+    out = net(batch)
+    ls = crit(out, batch)
+    if train:
+        ls["loss"].mean().backward()
+    met = ev(out, batch)
+    torch.cuda.synchronize()
+    return batch, out, ls, met
+
+
+def test_state_dict_contract(stack):
+    net, _, _, synth = stack
+    sd = net.state_dict()
+    ref = synth.make_state_dict(0)
+    assert set(sd) == set(ref) and len(sd) == 356
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    net.load_state_dict(ref, strict=True)
+    back = net.state_dict()
+    for k in ("backbone.encoder.conv1.weight", "att_reg_box.0.0.weight", "lstm.weight_hh_l0_reverse",
+              "backbone.encoder.layer3.4.bn2.running_var", "backbone.encoder.fc.bias"):
+        assert torch.equal(back[k].cpu(), ref[k]), k
+
+
+@pytest.mark.parametrize("name", ["net2", "net3v"])
+def test_train_step_vs_reference_golden(stack, golden_meta, name):
+    net, crit, ev, synth = stack
+    c = golden_meta["net_cases"][name]
+    z = load_npz(name)
+    batch, out, ls, met = run_step(net, crit, ev, synth, c["B"], c["seed"], c["var_len"])
+    assert out["att_out"].shape == (c["B"], 17460, 1) and out["bbx_out"].shape == (c["B"], 17460, 4)
+    assert out["feat_sizes"].tolist() == [[38, 38], [19, 19], [10, 10], [5, 5], [3, 3], [1, 1]]
+    for k in ("loss", "cls_ls", "box_ls"):
+        assert ls[k].item() == pytest.approx(c[k], rel=RTOL), k
+    assert ls["loss"].dtype == torch.float64 and ls["cls_ls"].dtype == torch.float32
+    assert met["Acc"].item() == c["Acc"] and met["MaxPos"].item() == c["MaxPos"]
+    assert np.array_equal(met["best_ids"].cpu().numpy(), z["best_ids"])
+    att = out["att_out"].detach().squeeze(-1).cpu()
+    np.testing.assert_allclose(att[:, ::53].numpy(), z["att_stride"], rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(out["bbx_out"].detach()[:, ::53].cpu().numpy(), z["bbx_stride"], rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(met["pred_boxes"].cpu().numpy(), z["pred_boxes"], rtol=1e-3, atol=1e-2)
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    for k, ref in c["gnorm"].items():
+        if ref is None:
+            assert grads[k] is None, k
+        else:
+            assert float(grads[k].double().norm()) == pytest.approx(ref, rel=2e-3, abs=1e-7), k
+    for key in z.files:
+        if key.startswith("g:"):
+            np.testing.assert_allclose(grads[key[2:]].cpu().numpy(), z[key], rtol=2e-3, atol=2e-5)
+        elif key.startswith("gs:"):
+            np.testing.assert_allclose(grads[key[3:]].cpu().flatten()[::101].numpy(), z[key], rtol=2e-3, atol=2e-5)
+    sd = net.state_dict()
+    np.testing.assert_allclose(sd["backbone.encoder.bn1.running_mean"].cpu().numpy(), z["bn1_rm"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(sd["backbone.encoder.layer4.2.bn3.running_var"].cpu().numpy(), z["l4_rv"], rtol=1e-4,
+                               atol=1e-6)
+    assert int(sd["backbone.encoder.bn1.num_batches_tracked"]) == 1
+
+
+def test_train_step_vs_live_oracle_b4(stack):
+    net, crit, ev, synth = stack
+    from oracle import zsg_oracle as zo
+    B, seed = 4, 31
+    batch, out, ls, met = run_step(net, crit, ev, synth, B, seed, True)
+    sd = synth.make_state_dict(0)
+    ols, omet, ograds, oout, _ = zo.train_step(sd, synth.make_batch(B, seed=seed, var_len=True), seed=seed, do_adam=False)
+    for k in ("loss", "cls_ls", "box_ls"):
+        assert ls[k].item() == pytest.approx(ols[k].item(), rel=RTOL), k
+    assert torch.equal(crit.last_top1.cpu(), ols["top1"])
+    assert torch.equal(crit.last_pos.cpu().bool(), ols["pos"])
+    assert torch.equal(met["best_ids"].cpu(), omet["idxs_best"])
+    assert met["Acc"].item() == omet["Acc"].item()
+    worst = 0.0
+    for k, g in ograds.items():
+        if g is None:
+            continue
+        mine = net.get_parameter(k).grad.cpu().double()
+        err = float((mine - g.double()).norm() / g.double().norm().clamp_min(1e-12))
+        worst = max(worst, err)
+        assert err < 2e-3, (k, err)
+    print("worst relative gradient error", worst)
+
+
+def test_eval_mode_uses_running_stats(stack):
+    net, crit, ev, synth = stack
+    from oracle import zsg_oracle as zo
+    B, seed = 2, 5
+    batch, out, ls, met = run_step(net, crit, ev, synth, B, seed, False, train=False)
+    sd = synth.make_state_dict(0)
+    torch.manual_seed(seed)
+    oout = zo.zsgnet_forward(sd, synth.make_batch(B, seed=seed), training=False)
+    a, b = out["att_out"].cpu().flatten(), oout["att_out"].flatten()
+    assert float((a - b).abs().max()) < 2e-4 * float(b.abs().max())
+    assert int(net.state_dict()["backbone.encoder.bn1.num_batches_tracked"]) == 0

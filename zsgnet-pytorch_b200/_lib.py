@@ -63,6 +63,7 @@ SIGNATURES = {
     "zsg_avgpool_bwd": [_P, _P, _I, _I, _I, _P],
     "zsg_relu_bwd": [_P, _P, _P, _L, _I, _P],
     "zsg_axpy": [_P, _P, _F, _L, _P],
+    "zsg_scale_dev": [_P, _L, _I, _L, _P, _P],
     "zsg_fuse_lang_grid": [_P, _P, _P, _P, _I, _I, C.POINTER(C.c_int32), _I, _I, _I, _I, _P],
     "zsg_unfuse_lang_grid": [_P, _P, _P, _I, _I, C.POINTER(C.c_int32), _I, _I, _I, _I, _P],
     "zsg_lstm_fwd_dir": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],

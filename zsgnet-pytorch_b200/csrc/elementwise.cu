@@ -351,6 +351,14 @@ __global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ x, 
     y[i] = fmaf(a, x[i], y[i]);
 }
 
+__global__ void __launch_bounds__(256) scale_dev_kernel(float* __restrict__ x, int64_t rows, int width, int64_t stride,
+                                                        const double* __restrict__ scale) {
+  const float s = (float)*scale;
+  const int64_t n = rows * width;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[(i / width) * stride + (i % width)] *= s;
+}
+
 // ------------------------------ language / grid tiling fusion --------------------------------
 struct Levels { int cells[8]; int n; };
 
@@ -613,6 +621,13 @@ extern "C" int zsg_axpy(const float* x, float* y, float a, int64_t n, zsg_stream
   ZSG_REQUIRE(x && y, "zsg_axpy: null pointer");
   axpy_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, y, a, n);
   return check_launch("zsg_axpy");
+}
+
+extern "C" int zsg_scale_dev(float* x, int64_t rows, int width, int64_t stride, const double* scale,
+                             zsg_stream_t stream) {
+  ZSG_REQUIRE(x && scale && rows > 0 && width > 0 && stride >= width, "zsg_scale_dev: bad arguments");
+  scale_dev_kernel<<<grid_for(rows * width, 256), 256, 0, as_stream(stream)>>>(x, rows, width, stride, scale);
+  return check_launch("zsg_scale_dev");
 }
 
 static int make_levels(const int32_t* lvl_cells, int nlvl, Levels& lv) {

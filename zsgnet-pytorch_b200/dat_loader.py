@@ -1,0 +1,90 @@
+"""Batch contract of the reference's code/dat_loader.py (the boundary on the input side).
+
+The reference's loader is CPU work outside the hot path (PIL decode, spaCy vectors; SURVEY.md
+section 2 #8) and is not rebuilt.  What the hot path needs from it is the batch dict
+(dat_loader.py:136-144, 187-196) and `get_data(cfg) -> DataWrap`; this module supplies both over
+a seeded synthetic dataset of the BASELINE shape (300x300 images, 300-d query vectors)."""
+from dataclasses import dataclass
+from typing import Dict, Optional, Union
+
+import torch
+from torch.utils.data import DataLoader, Dataset
+from torch.utils.data.distributed import DistributedSampler
+
+
+@dataclass
+class DataWrap:                                     # utils.py:115-120
+    path: str
+    train_dl: DataLoader
+    valid_dl: DataLoader
+    test_dl: Optional[Union[DataLoader, Dict]] = None
+
+
+class NewDistributedSampler(DistributedSampler):
+    """dat_loader.py:36-65: epoch-seeded permutation, padded to a multiple of the world size, rank slice."""
+
+    def __init__(self, dataset, num_replicas=None, rank=None, shuffle=True):
+        super().__init__(dataset, num_replicas=num_replicas, rank=rank)
+        self.shuffle = shuffle
+
+    def __iter__(self):
+        if self.shuffle:
+            g = torch.Generator()
+            g.manual_seed(self.epoch)
+            indices = torch.randperm(len(self.dataset), generator=g).tolist()
+        else:
+            indices = torch.arange(len(self.dataset)).tolist()
+        indices += indices[: (self.total_size - len(indices))]
+        off = self.num_samples * self.rank
+        return iter(indices[off: off + self.num_samples])
+
+
+class SyntheticImgQuDataset(Dataset):
+    """Items with the keys/dtypes of ImgQuDataset.simple_item_getter (dat_loader.py:136-144)."""
+
+    def __init__(self, n=256, phrase_len=50, img_hw=300, seed=0, min_len=1, max_len=20):
+        self.n, self.phrase_len, self.hw, self.seed, self.min_len, self.max_len = n, phrase_len, img_hw, seed, min_len, max_len
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        g = torch.Generator().manual_seed(self.seed * 1000003 + idx)
+        qlen = int(torch.randint(self.min_len, self.max_len + 1, (1,), generator=g))
+        qvec = torch.zeros(self.phrase_len, 300)
+        qvec[:qlen] = torch.randn(qlen, 300, generator=g)
+        c = torch.rand(2, generator=g) * 1.2 - 0.6
+        s = torch.rand(2, generator=g) * 0.7 + 0.1
+        annot = torch.cat([c - s / 2, c + s / 2]).clamp_(-1, 1)
+        h, w = 480.0, 640.0
+        orig = torch.tensor([(annot[1] + 1) / 2 * w, (annot[0] + 1) / 2 * h, (annot[3] + 1) / 2 * w, (annot[2] + 1) / 2 * h])
+        return {"img": torch.rand(3, self.hw, self.hw, generator=g), "idxs": torch.tensor(idx),
+                "qvec": qvec, "qlens": torch.tensor(qlen), "annot": annot, "orig_annot": orig,
+                "img_size": torch.tensor([h, w])}
+
+
+def collater(batch):
+    """dat_loader.py:187-196: stack, cast everything to float, trim qvec to the batch's longest phrase."""
+    qlens = torch.Tensor([i["qlens"] for i in batch])
+    max_qlen = int(qlens.max().item())
+    out = {k: torch.stack([b[k] for b in batch]).float() for k in batch[0]}
+    out["qvec"] = out["qvec"][:, :max_qlen]
+    return out
+
+
+def get_dataloader(cfg, dataset, is_train):
+    dist = bool(cfg["do_dist"]) if "do_dist" in cfg else False
+    bs = cfg["bs"] if dist else cfg["bs"] * max(1, int(cfg["num_gpus"]) if "num_gpus" in cfg else 1)
+    if dist:
+        sampler = NewDistributedSampler(dataset, shuffle=True)
+    else:
+        sampler = (torch.utils.data.RandomSampler if is_train else torch.utils.data.SequentialSampler)(dataset)
+    return DataLoader(dataset, batch_size=bs, sampler=sampler, drop_last=is_train, num_workers=0, collate_fn=collater)
+
+
+def get_data(cfg):
+    """Same signature as dat_loader.py:230-253, over synthetic data."""
+    n = cfg["synthetic_len"] if "synthetic_len" in cfg else 256
+    trn, val = SyntheticImgQuDataset(n, seed=0), SyntheticImgQuDataset(max(n // 4, 1), seed=1)
+    return DataWrap(path=cfg["tmp_path"] if "tmp_path" in cfg else "./tmp", train_dl=get_dataloader(cfg, trn, True),
+                    valid_dl=get_dataloader(cfg, val, False), test_dl={"test0": get_dataloader(cfg, val, False)})

@@ -1,0 +1,499 @@
+"""Static launch program of the ZSGNet hot path for one (batch, query-length) shape.
+
+The engine owns every activation / gradient buffer (NHWC fp32, allocated once) and two ordered
+lists of launches over the C ABI: `fwd` (mdl.py:338-403 incl. torchvision resnet50 and
+fpn_resnet.py:154-178) and `bwd` (the autograd graph of the same, utils.py:412).  Parameters
+and their gradients live in two flat arenas (ParamStore) laid out in backward-completion order,
+so gradient buckets for the NCCL all-reduce are contiguous slices that become final one after
+the other while the backward is still running.
+"""
+import numpy as np
+import torch
+
+from . import geometry, ops, spec
+from .ops import ConvOp, WgradOp
+
+BN_EPS, BN_MOM = 1e-5, 0.1
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient arenas with named views.
+
+    Conv weights are stored [cout][r][s][cin] (the K-major layout the implicit-GEMM kernels read),
+    exposed to PyTorch as OIHW tensors with channels_last strides, so state_dict keys and shapes
+    match the reference while no repacking is needed at run time."""
+
+    def __init__(self, device):
+        fwd = spec.trainable_specs()
+        order = list(reversed(fwd))                      # backward completes gradients in this order
+        self.names = [n for n, _, _ in order]
+        self.kinds = {n: k for n, _, k in fwd + spec.UNUSED_SPECS}
+        self.shapes = {n: s for n, s, _ in fwd + spec.UNUSED_SPECS}
+        self.offsets, off = {}, 0
+        for n, s, _ in order:
+            self.offsets[n] = off
+            off += _align(int(np.prod(s)))
+        self.used = off                                  # [0, used) takes part in all-reduce and Adam
+        for n, s, _ in spec.UNUSED_SPECS:
+            self.offsets[n] = off
+            off += _align(int(np.prod(s)))
+        self.total = off
+        self.device = device
+        self.param_arena = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad_arena = torch.zeros(self.used, dtype=torch.float32, device=device)
+
+    def numel(self, name):
+        return int(np.prod(self.shapes[name]))
+
+    def flat(self, name, arena=None):
+        arena = self.param_arena if arena is None else arena
+        o = self.offsets[name]
+        return arena[o:o + self.numel(name)]
+
+    def grad_flat(self, name):
+        return self.flat(name, self.grad_arena)
+
+    def view(self, name, arena=None):
+        """Reference-shaped view (OIHW with channels_last strides for 4-D weights)."""
+        s = self.shapes[name]
+        f = self.flat(name, arena)
+        if len(s) == 4:
+            return f.view(s[0], s[2], s[3], s[1]).permute(0, 3, 1, 2)
+        return f.view(s) if len(s) else f.view(())
+
+    def grad_view(self, name):
+        return self.view(name, self.grad_arena)
+
+
+class _BN:
+    def __init__(self, eng, prefix, c, rows):
+        st = eng.store
+        self.c, self.rows, self.prefix = c, rows, prefix
+        self.gamma, self.beta = st.flat(prefix + ".weight"), st.flat(prefix + ".bias")
+        self.dgamma, self.dbeta = st.grad_flat(prefix + ".weight"), st.grad_flat(prefix + ".bias")
+        self.rm, self.rv = eng.buffers[prefix + ".running_mean"], eng.buffers[prefix + ".running_var"]
+        self.nbt = eng.buffers[prefix + ".num_batches_tracked"]
+        self.mean, self.invstd, self.scale, self.shift = (eng.f32(c) for _ in range(4))
+        self.sums, self.bsums = eng.f64(2 * c), eng.f64(2 * c)
+
+
+class Engine:
+    def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC):
+        self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
+        self._rows_cache = {}
+        self._f64_pool, self._f64_used = torch.zeros(1 << 18, dtype=torch.float64, device=device), 0
+        self.bns = []
+        self.fwd_train, self.fwd_eval_bn, self.fwd, self.bwd, self.prep_bwd = [], [], [], [], []
+        self.inp = {}
+        self.nbytes = 0
+        self._build()
+
+    # ------------------------------------------------------------------ allocation helpers
+    def buf(self, *shape, zero=False):
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device=self.device)
+        self.nbytes += t.numel() * 4
+        return t
+
+    def f32(self, n):
+        return torch.zeros(n, dtype=torch.float32, device=self.device)
+
+    def f64(self, n):
+        o = self._f64_used
+        self._f64_used += _align(n, 2)
+        assert self._f64_used <= self._f64_pool.numel()
+        return self._f64_pool[o:o + n]
+
+    def rows(self, kind, *key):
+        k = (kind,) + key
+        if k not in self._rows_cache:
+            fn = geometry.conv_rows if kind == "fwd" else geometry.dgrad_rows
+            self._rows_cache[k] = fn(self.B, *key).to(self.device)
+        return self._rows_cache[k]
+
+    # ------------------------------------------------------------------ layer builders
+    def add_bn(self, prefix, c, rows):
+        bn = _BN(self, prefix, c, rows)
+        self.bns.append(bn)
+        return bn
+
+    def bn_forward(self, bn, x):
+        """train: batch statistics (+ running-stat update); eval: affine from running stats."""
+        def train():
+            ops.bn_stats(x, bn.sums, bn.rows, bn.c)
+            ops.bn_finalize(bn.sums, bn.rows, bn.c, bn.gamma, bn.beta, BN_EPS, BN_MOM, bn.rm, bn.rv, bn.mean,
+                            bn.invstd, bn.scale, bn.shift)
+
+        def evalm():
+            ops.bn_eval_affine(bn.rm, bn.rv, bn.gamma, bn.beta, BN_EPS, bn.c, bn.scale, bn.shift)
+        self.fwd.append(("bn", train, evalm))
+
+    def conv(self, wname, x, hin, win, cin, cout, k, stride, pad, y, pro=None, in_relu=False, bias=None,
+             out_relu=False, w=None):
+        hout, wout = (hin + 2 * pad - k) // stride + 1, (win + 2 * pad - k) // stride + 1
+        rows = self.rows("fwd", hin, win, cin, hout, wout, cout, stride, pad)
+        w = self.store.flat(wname) if w is None else w
+        op = ConvOp(x, w, y, rows, self.B * hout * wout, cin, cout, k, k, in_scale=pro.scale if pro else None,
+                    in_shift=pro.shift if pro else None, in_relu=in_relu, bias=bias, out_relu=out_relu, impl=self.impl)
+        self.fwd.append(("op", op))
+        return dict(wname=wname, x=x, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
+                    hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w)
+
+    def conv_wgrad(self, L, dy, dw=None):
+        dw = self.store.grad_flat(L["wname"]) if dw is None else dw
+        pro = L["pro"]
+        self.bwd.append(WgradOp(L["x"], dy, dw, L["rows"], self.B * L["hout"] * L["wout"], L["cin"], L["cout"], L["k"],
+                                L["k"], in_scale=pro.scale if pro else None, in_shift=pro.shift if pro else None,
+                                in_relu=L["in_relu"], impl=self.impl))
+
+    def conv_dgrad(self, L, dy, dx, out_mask=None, residual=None, accumulate=False):
+        k, cin, cout = L["k"], L["cin"], L["cout"]
+        wt = self.buf(cin * k * k * cout)
+        w = L["w"]
+        self.prep_bwd.append(lambda: ops.weight_transpose_flip(w, wt, cout, k, k, cin))
+        rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, L["stride"], L["pad"])
+        self.bwd.append(ConvOp(dy, wt, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=L["stride"],
+                               out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl))
+
+    def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None):
+        def run():
+            ops.bn_bwd_reduce(dy, x, bn.mean, bn.invstd, bn.bsums, bn.rows, bn.c, mask_mode=mask_mode, scale=bn.scale,
+                              shift=bn.shift, act_out=act_out, dz_out=dz_out)
+            src = dz_out if dz_out is not None else dy
+            mm = 0 if dz_out is not None else mask_mode
+            ops.bn_bwd_apply(src, x, bn.mean, bn.invstd, bn.gamma, bn.bsums, dx, bn.dgamma, bn.dbeta, bn.rows, bn.c,
+                             mask_mode=mm, scale=bn.scale, shift=bn.shift, act_out=act_out)
+        self.bwd.append(run)
+
+    # ------------------------------------------------------------------ the network
+    def _build(self):
+        B, T, st, dev = self.B, self.T, self.store, self.device
+        e = "backbone.encoder."
+        bwd_stages = []                                   # filled in forward order, replayed reversed
+
+        # ---------------- stem: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2 (mdl.py:149-152)
+        img4 = self.buf(B, 300, 300, 4)
+        w1p, dw1p = self.buf(64 * 49 * 4), self.buf(64 * 49 * 4)
+        c1 = self.buf(B * 150 * 150, 64)
+        x0 = self.buf(B * 75 * 75, 64)
+        w1 = st.flat(e + "conv1.weight")
+        self.fwd.append(("fn", lambda: ops.nchw_to_nhwc4(self.inp["img"], img4)))
+        self.fwd.append(("fn", lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, 4)))
+        Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p)
+        bn1 = self.add_bn(e + "bn1", 64, B * 150 * 150)
+        self.bn_forward(bn1, c1)
+        self.fwd.append(("fn", lambda: ops.maxpool_bn_relu_fwd(c1, bn1.scale, bn1.shift, x0, B, 150, 150, 64, 75, 75)))
+        g_x0 = self.buf(B * 75 * 75, 64)
+        da_stem = self.buf(B * 150 * 150, 64)
+        g1 = st.grad_flat(e + "conv1.weight")
+
+        def stem_bwd():
+            self.bwd.append(lambda: ops.maxpool_bn_relu_bwd(c1, bn1.scale, bn1.shift, g_x0, da_stem, B, 150, 150, 64,
+                                                            75, 75))
+            self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1)
+            self.bwd.append(lambda: dw1p.zero_())
+            self.conv_wgrad(Lstem, da_stem, dw=dw1p)
+            self.bwd.append(lambda: ops.pad_channels(dw1p, g1, 64 * 49, 4, 3))
+        bwd_stages.append(stem_bwd)
+
+        # ---------------- bottleneck stages (torchvision resnet50 v1.5)
+        max_o4 = max_ow = max_iw = 0
+        h, cin, inp, g_in = 75, 64, x0, g_x0
+        blocks, stage_out = [], {}
+        for li, (nblk, width, stride) in enumerate(spec.RESNET_LAYERS, start=1):
+            for b in range(nblk):
+                s = stride if b == 0 else 1
+                ho = (h + 2 - 3) // s + 1
+                p = f"{e}layer{li}.{b}."
+                ri, ro = B * h * h, B * ho * ho
+                r1, r2, r3 = self.buf(ri, width), self.buf(ro, width), self.buf(ro, 4 * width)
+                out, g_out = self.buf(ro, 4 * width), self.buf(ro, 4 * width)
+                La = self.conv(p + "conv1.weight", inp, h, h, cin, width, 1, 1, 0, r1)
+                bnA = self.add_bn(p + "bn1", width, ri)
+                self.bn_forward(bnA, r1)
+                Lb = self.conv(p + "conv2.weight", r1, h, h, width, width, 3, s, 1, r2, pro=bnA, in_relu=True)
+                bnB = self.add_bn(p + "bn2", width, ro)
+                self.bn_forward(bnB, r2)
+                Lc = self.conv(p + "conv3.weight", r2, ho, ho, width, 4 * width, 1, 1, 0, r3, pro=bnB, in_relu=True)
+                bnC = self.add_bn(p + "bn3", 4 * width, ro)
+                self.bn_forward(bnC, r3)
+                Ld = bnD = rd = None
+                if b == 0:
+                    rd = self.buf(ro, 4 * width)
+                    Ld = self.conv(p + "downsample.0.weight", inp, h, h, cin, 4 * width, 1, s, 0, rd)
+                    bnD = self.add_bn(p + "downsample.1", 4 * width, ro)
+                    self.bn_forward(bnD, rd)
+
+                def tail(r3=r3, bnC=bnC, rd=rd, bnD=bnD, inp=inp, out=out, ro=ro, c=4 * width):
+                    if rd is not None:
+                        ops.bn_apply(r3, bnC.scale, bnC.shift, out, ro, c, True, r=rd, rscale=bnD.scale, rshift=bnD.shift)
+                    else:
+                        ops.bn_apply(r3, bnC.scale, bnC.shift, out, ro, c, True, r=inp)
+                self.fwd.append(("fn", tail))
+                blocks.append(dict(La=La, Lb=Lb, Lc=Lc, Ld=Ld, bnA=bnA, bnB=bnB, bnC=bnC, bnD=bnD, r1=r1, r2=r2, r3=r3,
+                                   rd=rd, out=out, g_out=g_out, g_in=g_in, ri=ri, ro=ro, width=width,
+                                   acc_in=(b == 0 and li in (3, 4))))   # c3 / c4 also receive FPN gradients
+                max_o4, max_ow, max_iw = max(max_o4, ro * 4 * width), max(max_ow, ro * width), max(max_iw, ri * width)
+                inp, g_in, cin, h = out, g_out, 4 * width, ho
+            stage_out[li] = (inp, g_in, h, cin)
+        sA, sB, sC, sD = self.buf(max_o4), self.buf(max_o4), self.buf(max_ow), self.buf(max_iw)
+
+        def block_bwd(k):
+            def emit():
+                L = blocks[k]
+                ro, ri, w4, w = L["ro"], L["ri"], 4 * L["width"], L["width"]
+                dz, dr3, da2, da1 = sA[:ro * w4], sB[:ro * w4], sC[:ro * w], sD[:ri * w]
+                self.bn_backward(L["bnC"], L["g_out"], L["r3"], dr3, mask_mode=2, act_out=L["out"], dz_out=dz)
+                self.conv_wgrad(L["Lc"], dr3)
+                self.conv_dgrad(L["Lc"], dr3, da2)
+                self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1)
+                self.conv_wgrad(L["Lb"], da2)
+                self.conv_dgrad(L["Lb"], da2, da1)
+                self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1)
+                self.conv_wgrad(L["La"], da1)
+                if L["Ld"] is not None:
+                    drd = sB[:ro * w4]
+                    self.bn_backward(L["bnD"], dz, L["rd"], drd, mask_mode=0)
+                    self.conv_wgrad(L["Ld"], drd)
+                    self.conv_dgrad(L["Ld"], drd, L["g_in"], accumulate=L["acc_in"])
+                    self.conv_dgrad(L["La"], da1, L["g_in"], accumulate=True)
+                else:
+                    self.conv_dgrad(L["La"], da1, L["g_in"], residual=dz, accumulate=L["acc_in"])
+            return emit
+        for k in range(len(blocks)):
+            bwd_stages.append(block_bwd(k))
+
+        # ---------------- FPN (fpn_resnet.py:154-178)
+        c3, g_c3, _, _ = stage_out[2]
+        c4, g_c4, _, _ = stage_out[3]
+        c5, g_c5, _, _ = stage_out[4]
+        lvl_rows = [B * c for c in spec.CELLS]
+        lvl_off = np.concatenate([[0], np.cumsum(lvl_rows)]).tolist()
+        M = B * spec.TOTAL_CELLS
+        feat, dfeat = self.buf(M, 256), self.buf(M, 256)
+        fl = [feat[lvl_off[i]:lvl_off[i + 1]] for i in range(6)]
+        dfl = [dfeat[lvl_off[i]:lvl_off[i + 1]] for i in range(6)]
+        p51, p41, p31 = self.buf(B * 100, 256), self.buf(B * 361, 256), self.buf(B * 1444, 256)
+        dp51, dp41, dp31 = self.buf(B * 100, 256), self.buf(B * 361, 256), self.buf(B * 1444, 256)
+        f = "backbone.fpn."
+        bias = lambda n: st.flat(f + n + ".bias")
+        up = {}
+        for (i, o) in ((10, 19), (19, 38)):
+            idx = [min(int(np.floor(np.float32(d) * np.float32(i / o))), i - 1) for d in range(o)]   # F.interpolate nearest
+            up[(i, o)] = torch.tensor(idx, dtype=torch.int32, device=dev)
+        L51 = self.conv(f + "P5_1.weight", c5, 10, 10, 2048, 256, 1, 1, 0, p51, bias=bias("P5_1"))
+        L52 = self.conv(f + "P5_2.weight", p51, 10, 10, 256, 256, 3, 1, 1, fl[2], bias=bias("P5_2"))
+        L41 = self.conv(f + "P4_1.weight", c4, 19, 19, 1024, 256, 1, 1, 0, p41, bias=bias("P4_1"))
+        self.fwd.append(("fn", lambda: ops.upsample_add(p41, p51, up[(10, 19)], up[(10, 19)], B, 19, 19, 10, 10, 256)))
+        L42 = self.conv(f + "P4_2.weight", p41, 19, 19, 256, 256, 3, 1, 1, fl[1], bias=bias("P4_2"))
+        L31 = self.conv(f + "P3_1.weight", c3, 38, 38, 512, 256, 1, 1, 0, p31, bias=bias("P3_1"))
+        self.fwd.append(("fn", lambda: ops.upsample_add(p31, p41, up[(19, 38)], up[(19, 38)], B, 38, 38, 19, 19, 256)))
+        L32 = self.conv(f + "P3_2.weight", p31, 38, 38, 256, 256, 3, 1, 1, fl[0], bias=bias("P3_2"))
+        L6 = self.conv(f + "P6.weight", c5, 10, 10, 2048, 256, 3, 2, 1, fl[3], bias=bias("P6"))
+        L7 = self.conv(f + "P7_2.weight", fl[3], 5, 5, 256, 256, 3, 2, 1, fl[4], in_relu=True, bias=bias("P7_2"))
+        self.fwd.append(("fn", lambda: ops.avgpool_fwd(fl[4], fl[5], B, 9, 256)))
+
+        def gbias(n, dy, rows):
+            gb = st.grad_flat(f + n + ".bias")
+            self.bwd.append(lambda: ops.colsum(dy, gb, rows, 256))
+
+        def fpn_bwd():
+            self.bwd.append(lambda: ops.avgpool_bwd(dfl[5], dfl[4], B, 9, 256))
+            gbias("P7_2", dfl[4], B * 9); self.conv_wgrad(L7, dfl[4])
+            self.conv_dgrad(L7, dfl[4], dfl[3], out_mask=fl[3], accumulate=True)
+            gbias("P6", dfl[3], B * 25); self.conv_wgrad(L6, dfl[3]); self.conv_dgrad(L6, dfl[3], g_c5)
+            gbias("P3_2", dfl[0], B * 1444); self.conv_wgrad(L32, dfl[0]); self.conv_dgrad(L32, dfl[0], dp31)
+            gbias("P3_1", dp31, B * 1444); self.conv_wgrad(L31, dp31); self.conv_dgrad(L31, dp31, g_c3)
+            gbias("P4_2", dfl[1], B * 361); self.conv_wgrad(L42, dfl[1]); self.conv_dgrad(L42, dfl[1], dp41)
+            self.bwd.append(lambda: ops.upsample_add_bwd(dp31, dp41, up[(19, 38)], up[(19, 38)], B, 38, 38, 19, 19, 256))
+            gbias("P4_1", dp41, B * 361); self.conv_wgrad(L41, dp41); self.conv_dgrad(L41, dp41, g_c4)
+            gbias("P5_2", dfl[2], B * 100); self.conv_wgrad(L52, dfl[2]); self.conv_dgrad(L52, dfl[2], dp51)
+            self.bwd.append(lambda: ops.upsample_add_bwd(dp41, dp51, up[(10, 19)], up[(10, 19)], B, 19, 19, 10, 10, 256))
+            gbias("P5_1", dp51, B * 100); self.conv_wgrad(L51, dp51); self.conv_dgrad(L51, dp51, g_c5, accumulate=True)
+        bwd_stages.append(fpn_bwd)
+
+        # ---------------- bi-LSTM query encoder (mdl.py:296-336)
+        E, Hh, G = 300, 128, 512
+        qv = self.buf(B * T, E, zero=True)
+        lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        h0c0 = self.buf(4, B, Hh, zero=True)              # h0 fwd, c0 fwd, h0 rev, c0 rev (per sample)
+        gx, gates, dgates = self.buf(B * T, G), self.buf(B * T, G, zero=True), self.buf(B * T, G, zero=True)
+        cs, hprev = self.buf(B * T, Hh, zero=True), self.buf(B * T, Hh, zero=True)
+        lang, dlang = self.buf(B, 2 * Hh), self.buf(B, 2 * Hh)
+        xlast, rgates, drgates = self.buf(B, E), self.buf(B, G), self.buf(B, G)
+        whh_t = self.buf(Hh * G)
+        self.qv, self.lens, self.h0c0, self.lang = qv, lens, h0c0, lang
+        P = lambda n: st.flat("lstm." + n)
+        r11 = lambda rows_, cin_, cout_: geometry.conv_rows(rows_, 1, 1, cin_, 1, 1, cout_, 1, 0).to(dev)
+        rows_ih, rows_hh = r11(B * T, E, G), r11(B * T, Hh, G)
+        rows_ihr, rows_hhr = r11(B, E, G), r11(B, Hh, G)
+        self.fwd.append(("op", ConvOp(qv, P("weight_ih_l0"), gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl)))
+        self.fwd.append(("fn", lambda: ops.weight_transpose_flip(P("weight_hh_l0"), whh_t, G, 1, 1, Hh)))
+        self.fwd.append(("fn", lambda: ops.lstm_fwd_dir(gx, whh_t, P("bias_ih_l0"), P("bias_hh_l0"), h0c0[0], h0c0[1],
+                                                        lens, B, T, gates, cs, hprev, lang)))
+        self.fwd.append(("fn", lambda: ops.lstm_rev_step(qv, P("weight_ih_l0_reverse"), P("weight_hh_l0_reverse"),
+                                                         P("bias_ih_l0_reverse"), P("bias_hh_l0_reverse"), h0c0[2],
+                                                         h0c0[3], lens, B, T, E, xlast, rgates, lang)))
+        Gd = lambda n: st.grad_flat("lstm." + n)
+
+        def lstm_bwd():
+            self.bwd.append(lambda: ops.lstm_bwd_dir(dlang, P("weight_hh_l0"), gates, cs, h0c0[1], lens, B, T, dgates))
+            self.bwd.append(WgradOp(qv, dgates, Gd("weight_ih_l0"), rows_ih, B * T, E, G, 1, 1, impl=self.impl))
+            self.bwd.append(WgradOp(hprev, dgates, Gd("weight_hh_l0"), rows_hh, B * T, Hh, G, 1, 1, impl=self.impl))
+            self.bwd.append(lambda: ops.colsum(dgates, Gd("bias_ih_l0"), B * T, G))
+            self.bwd.append(lambda: Gd("bias_hh_l0").copy_(Gd("bias_ih_l0")))
+            self.bwd.append(lambda: ops.lstm_rev_step_bwd(dlang, rgates, h0c0[3], B, drgates))
+            self.bwd.append(WgradOp(xlast, drgates, Gd("weight_ih_l0_reverse"), rows_ihr, B, E, G, 1, 1, impl=self.impl))
+            self.bwd.append(WgradOp(h0c0[2], drgates, Gd("weight_hh_l0_reverse"), rows_hhr, B, Hh, G, 1, 1,
+                                    impl=self.impl))
+            self.bwd.append(lambda: ops.colsum(drgates, Gd("bias_ih_l0_reverse"), B, G))
+            self.bwd.append(lambda: Gd("bias_hh_l0_reverse").copy_(Gd("bias_ih_l0_reverse")))
+        bwd_stages.append(lstm_bwd)
+
+        # ---------------- fusion + shared six-level head (mdl.py:69-104, 235-254, 379-382)
+        CP, A = spec.FUSED_CP, spec.NUM_ANCHORS
+        from .anchors import cell_grid
+        grid = torch.cat([cell_grid(s, s).view(-1, 2) for s in spec.LEVEL_SIZES]).to(dev).contiguous()
+        fused, dfused = self.buf(M, CP), self.buf(M, CP)
+        hs = [self.buf(M, 256) for _ in range(5)]
+        dhs = [self.buf(M, 256) for _ in range(5)]
+        out = self.buf(B, A, 5)
+        dy5 = self.buf(M, 48)
+        self.out = out
+        w0, w0p, dw0p = st.flat("att_reg_box.0.0.weight"), self.buf(256 * 9 * CP), self.buf(256 * 9 * CP)
+        cells = list(spec.CELLS)
+        self.fwd.append(("fn", lambda: ops.fuse_lang_grid(feat, lang, grid, fused, B, spec.TOTAL_CELLS, cells, 256, 256, CP)))
+        self.fwd.append(("fn", lambda: ops.pad_channels(w0, w0p, 256 * 9, spec.FUSED_C, CP)))
+
+        def head_rows(kind, cin, cout, scatter=False):
+            tabs, a_off = [], 0
+            for li, s in enumerate(spec.LEVEL_SIZES):
+                fn = geometry.conv_rows if kind == "fwd" else geometry.dgrad_rows
+                args = (B, s, s, cin, s, s, cout, 1, 1) if kind == "fwd" else (B, s, s, cin, s, s, cout, 3, 1, 1)
+                if kind == "fwd":
+                    t = fn(*args, in_off=lvl_off[li] * cin, out_off=lvl_off[li] * cout)
+                else:
+                    t = fn(*args, dy_off=lvl_off[li] * cout, dx_off=lvl_off[li] * cin)
+                if scatter:                                  # permute_correctly + cat: [B, A, 5]
+                    arr = t.numpy().view(geometry.ROW_DTYPE).reshape(-1).copy()
+                    i = np.arange(arr.shape[0])
+                    arr["out"] = ((i // (s * s)) * A + a_off + (i % (s * s)) * 9) * 5
+                    t = torch.from_numpy(arr.view(np.uint8).reshape(-1, 16))
+                tabs.append(t)
+                a_off += s * s * 9
+            return torch.cat(tabs).contiguous().to(dev)
+        hb = lambda i: st.flat(f"att_reg_box.{i}.0.bias")
+        rows_f520, rows_f256 = head_rows("fwd", CP, 256), head_rows("fwd", 256, 256)
+        rows_last, rows_f48 = head_rows("fwd", 256, 45, scatter=True), head_rows("fwd", 256, 48)
+        rows_d520, rows_d256, rows_d48 = head_rows("dgrad", CP, 256), head_rows("dgrad", 256, 256), head_rows("dgrad", 256, 48)
+        self.fwd.append(("op", ConvOp(fused, w0p, hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
+                                      impl=self.impl)))
+        for i in range(1, 5):
+            self.fwd.append(("op", ConvOp(hs[i - 1], st.flat(f"att_reg_box.{i}.0.weight"), hs[i], rows_f256, M, 256, 256,
+                                          3, 3, bias=hb(i), out_relu=True, impl=self.impl)))
+        w5 = st.flat("att_reg_box.5.weight")
+        self.fwd.append(("op", ConvOp(hs[4], w5, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
+                                      impl=self.impl)))
+        self.d_out = self.buf(B, A, 5)
+        wt5, wt5p = self.buf(256 * 9 * 45), self.buf(256 * 9 * 48)
+        wts = [self.buf(256 * 9 * 256) for _ in range(5)]
+        wt0 = self.buf(CP * 9 * 256)
+        tmp48 = self.buf(48)
+
+        def head_bwd():
+            d_out = self.d_out
+            self.prep_bwd.append(lambda: ops.weight_transpose_flip(w5, wt5, 45, 3, 3, 256))
+            self.prep_bwd.append(lambda: ops.pad_channels(wt5, wt5p, 256 * 9, 45, 48))
+            self.bwd.append(lambda: ops.gather_rows(d_out, rows_last, dy5, M, 45, 48))
+            self.bwd.append(lambda: ops.colsum(dy5, tmp48, M, 48))
+            self.bwd.append(lambda: st.grad_flat("att_reg_box.5.bias").copy_(tmp48[:45]))
+            self.bwd.append(WgradOp(hs[4], dy5, st.grad_flat("att_reg_box.5.weight"), rows_f48, M, 256, 45, 3, 3,
+                                    impl=self.impl))
+            self.bwd.append(ConvOp(dy5, wt5p, dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl))
+            for i in range(4, 0, -1):
+                wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i]
+                self.prep_bwd.append(lambda wi=wi, wti=wti: ops.weight_transpose_flip(wi, wti, 256, 3, 3, 256))
+                gb = st.grad_flat(f"att_reg_box.{i}.0.bias")
+                self.bwd.append(lambda i=i, gb=gb: ops.colsum(dhs[i], gb, M, 256))
+                self.bwd.append(WgradOp(hs[i - 1], dhs[i], st.grad_flat(f"att_reg_box.{i}.0.weight"), rows_f256, M, 256,
+                                        256, 3, 3, impl=self.impl))
+                self.bwd.append(ConvOp(dhs[i], wti, dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
+                                       impl=self.impl))
+            self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
+            gb0 = st.grad_flat("att_reg_box.0.0.bias")
+            self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
+            self.bwd.append(lambda: dw0p.zero_())
+            self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl))
+            g0 = st.grad_flat("att_reg_box.0.0.weight")
+            self.bwd.append(lambda: ops.pad_channels(dw0p, g0, 256 * 9, CP, spec.FUSED_C))
+            self.bwd.append(ConvOp(dhs[0], wt0, dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl))
+            self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
+        bwd_stages.append(head_bwd)
+
+        # backward = stages in reverse forward order; gradient-ready marks for the bucketed all-reduce
+        self.bucket_marks = []                            # (index into self.bwd after which arena[lo:hi] is final)
+        names_by_stage = self._stage_param_names(len(blocks))
+        for stage, names in zip(reversed(bwd_stages), reversed(names_by_stage)):
+            stage()
+            lo = min(st.offsets[n] for n in names)
+            hi = max(st.offsets[n] + _align(st.numel(n)) for n in names)
+            self.bucket_marks.append((len(self.bwd), lo, hi))
+
+    def _stage_param_names(self, nblocks):
+        """Parameter names per backward stage, in forward order (stem, blocks..., fpn, lstm, head)."""
+        e = "backbone.encoder."
+        names = [[e + "conv1.weight", e + "bn1.weight", e + "bn1.bias"]]
+        for li, (nblk, _, _) in enumerate(spec.RESNET_LAYERS, start=1):
+            for b in range(nblk):
+                p = f"{e}layer{li}.{b}."
+                names.append([n for n, _, _ in spec.trainable_specs() if n.startswith(p)])
+        names.append([n for n, _, _ in spec.trainable_specs() if n.startswith("backbone.fpn.")])
+        names.append([n for n, _, _ in spec.trainable_specs() if n.startswith("lstm.")])
+        names.append([n for n, _, _ in spec.trainable_specs() if n.startswith("att_reg_box.")])
+        assert len(names) == nblocks + 4
+        return names
+
+    # ------------------------------------------------------------------ execution
+    def set_inputs(self, img, qvec, lens_cpu, inv_perm_cpu, h0, c0):
+        """img [B,3,300,300] device; qvec [B,T',300] device; lens/inv_perm on the host; h0,c0 [2,B,128] on
+        the host in SORTED-row order (mdl.py:307-319), re-ordered here to per-sample order."""
+        B, T = self.B, self.T
+        assert img.shape == (B, 3, 300, 300) and img.is_contiguous(), img.shape
+        self.inp["img"] = img
+        Tq = qvec.shape[1]
+        self.qv.view(B, T, 300)[:, :Tq].copy_(qvec)
+        self.lens.copy_(lens_cpu.to(torch.int32), non_blocking=True)
+        hc = torch.stack([h0[0][inv_perm_cpu], c0[0][inv_perm_cpu], h0[1][inv_perm_cpu], c0[1][inv_perm_cpu]])
+        self.h0c0.copy_(hc, non_blocking=True)
+
+    def forward(self, training=True):
+        if training:
+            self._f64_pool[:self._f64_used].zero_()
+        for item in self.fwd:
+            if item[0] == "op":
+                item[1]()
+            elif item[0] == "fn":
+                item[1]()
+            else:
+                (item[1] if training else item[2])()
+        if training:
+            for bn in self.bns:
+                pass                                      # num_batches_tracked is bumped in one op below
+        return self.out
+
+    def backward(self, d_out=None, on_bucket=None):
+        """d_out: [B,A,5] gradient of the packed head output (copied into the static buffer unless it already
+        is self.d_out).  on_bucket(lo, hi) is called as soon as grad_arena[lo:hi] is final."""
+        if d_out is not None and d_out.data_ptr() != self.d_out.data_ptr():
+            self.d_out.copy_(d_out)
+        self.store.grad_arena.zero_()
+        for fn in self.prep_bwd:
+            fn()
+        marks = {m[0]: m for m in self.bucket_marks}
+        for i, op in enumerate(self.bwd, start=1):
+            op()
+            if on_bucket is not None and i in marks:
+                on_bucket(marks[i][1], marks[i][2])

@@ -4,10 +4,12 @@ import numpy as np
 import torch
 
 
+ROW_DTYPE = np.dtype([("base", "<i4"), ("y0", "<i2"), ("x0", "<i2"), ("hin", "<i2"), ("win", "<i2"), ("out", "<i4")])
+
+
 def _pack(base, y0, x0, hin, win, out):
     n = base.shape[0]
-    arr = np.zeros(n, dtype=[("base", "<i4"), ("y0", "<i2"), ("x0", "<i2"), ("hin", "<i2"), ("win", "<i2"),
-                             ("out", "<i4")])
+    arr = np.zeros(n, dtype=ROW_DTYPE)
     arr["base"], arr["y0"], arr["x0"], arr["hin"], arr["win"], arr["out"] = base, y0, x0, hin, win, out
     assert arr.itemsize == 16
     return torch.from_numpy(arr.view(np.uint8).reshape(n, 16).copy())

@@ -1,0 +1,94 @@
+"""Drop-in for the reference's code/loss.py: `get_default_loss(ratios, scales, cfg)` -> module with
+`.loss_keys == ['loss', 'cls_ls', 'box_ls']` and `forward(out, inp) -> dict` (loss.py:43-143).
+
+One fused CUDA pass (zsg_match_loss) does the anchor matching (float64 IoU, bit-exact positives and
+argmax), focal BCE, smooth-L1 and both gradients; it replaces ~25 ATen launches, the 1.22 GB
+`torch.eye` of loss.py:79 and its three host synchronisations."""
+from typing import Dict
+
+import torch
+from torch import nn
+
+from . import ops, spec
+from .anchors import create_anchors
+
+
+def _packed_base(att, bbx):
+    """If att_out / bbx_out are the [..., 4:] / [..., :4] views of one contiguous [B,A,5] buffer (what
+    zsg_b200.mdl.ZSGNet returns, like mdl.py:381-382), return the element strides (5, 5)."""
+    if att.dim() == 3 and bbx.dim() == 3 and att.stride() == bbx.stride() == (att.shape[1] * 5, 5, 1) \
+            and att.data_ptr() == bbx.data_ptr() + 16:
+        return True
+    return False
+
+
+class _MatchLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, att, bbx, annot, mod):
+        B, A = att.shape[0], att.shape[1]
+        dev = att.device
+        packed = _packed_base(att, bbx)
+        if not packed:
+            att, bbx = att.contiguous(), bbx.contiguous()
+        sa, sr = (5, 5) if packed else (1, 4)
+        if packed:
+            dbuf = torch.empty(B, A, 5, device=dev)
+            d_att, d_reg = dbuf[..., 4:], dbuf[..., :4]
+        else:
+            d_att, d_reg = torch.empty(B, A, 1, device=dev), torch.empty(B, A, 4, device=dev)
+        losses = torch.empty(3, dtype=torch.float64, device=dev)
+        top1 = torch.empty(B, dtype=torch.int64, device=dev)
+        pos = torch.empty(B, A, dtype=torch.uint8, device=dev)
+        ws = ops.match_loss_workspace(B, dev)
+        ops.match_loss(att, sa, bbx, sr, annot, mod.anchs, B, A, float(mod.match_thr), float(mod.alpha),
+                       float(mod.gamma), float(mod.lamb_reg), bool(mod.use_multi), losses, d_att, sa, d_reg, sr, top1,
+                       pos, ws)
+        mod.last_top1, mod.last_pos = top1, pos
+        ctx.save_for_backward(d_att, d_reg)
+        ctx.lamb = float(mod.lamb_reg)
+        ctx.mark_non_differentiable(top1, pos)
+        # dtypes as in the reference: loss/box float64, cls float32
+        return losses[0], losses[1].float(), losses[2], top1, pos
+
+    @staticmethod
+    def backward(ctx, g_loss, g_cls, g_box, _g1, _g2):
+        d_att, d_reg = ctx.saved_tensors
+        # d_att = d cls / d att, d_reg = lamb * d box / d reg (both as gradients of `loss`)
+        s_att = g_loss.double() + g_cls.double()
+        s_reg = g_loss.double() + (g_box.double() / ctx.lamb if ctx.lamb != 0 else 0.0)
+        ops.scale_dev(d_att, s_att)
+        ops.scale_dev(d_reg, s_reg)
+        return d_att, d_reg, None, None
+
+
+class ZSGLoss(nn.Module):
+    def __init__(self, ratios, scales, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.ratios, self.scales = ratios, scales
+        self.alpha, self.gamma = cfg["alpha"], cfg["gamma"]
+        self.use_focal, self.use_softmax, self.use_multi = cfg["use_focal"], cfg["use_softmax"], cfg["use_multi"]
+        self.lamb_reg = cfg["lamb_reg"]
+        self.match_thr = cfg["matching_threshold"]
+        if not self.use_focal or self.use_softmax:
+            raise NotImplementedError("zsg_b200 loss covers the paper configuration: use_focal=true, use_softmax=false")
+        self.loss_keys = ["loss", "cls_ls", "box_ls"]
+        self.anchs = None
+        self.last_top1 = self.last_pos = None
+
+    def get_anchors(self, feat_sizes, device):
+        sizes = [(int(h), int(w)) for h, w in feat_sizes.tolist()]
+        return create_anchors(sizes, self.ratios, self.scales, flatten=True, device=device)
+
+    def forward(self, out: Dict[str, torch.Tensor], inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        att, bbx = out["att_out"], out["bbx_out"]
+        if self.anchs is None:                      # loss.py:66-72: built once, sizes are fixed
+            self.anchs = self.get_anchors(out["feat_sizes"][:len(spec.LEVEL_SIZES)].cpu(), att.device)
+        assert att.shape[1] == self.anchs.shape[0], "anchor count does not match the head output"
+        annot = inp["annot"].contiguous().float()
+        loss, cls, box, _, _ = _MatchLossFn.apply(att, bbx, annot, self)
+        return {"loss": loss, "cls_ls": cls, "box_ls": box}
+
+
+def get_default_loss(ratios, scales, cfg):
+    return ZSGLoss(ratios, scales, cfg)

@@ -126,6 +126,15 @@ def axpy(x, y, a, n):
     call("zsg_axpy", ptr(x), ptr(y), a, n, stream())
 
 
+def scale_dev(x, scale):
+    """x: [..., width] view whose rows are `stride` elements apart (last dim contiguous); scale: device double."""
+    width = x.shape[-1]
+    stride = x.stride(-2) if x.dim() > 1 else width
+    rows = x.numel() // width
+    scale = scale.reshape(1).contiguous()
+    call("zsg_scale_dev", ptr(x), rows, width, stride, ptr(scale), stream())
+
+
 def _lvl(cells):
     return (C.c_int32 * len(cells))(*cells)
 
