@@ -134,7 +134,7 @@ def match(annot, anchs, thr=0.6):
     iou = iou_gt_vs_anchors(annot, anchs)
     top1 = iou.max(1)[1]
     pos = iou > thr
-    pos[torch.arange(annot.shape[0]), top1] = True
+    pos[torch.arange(annot.shape[0], device=annot.device), top1] = True
     return pos, top1, iou
 
 
@@ -144,7 +144,7 @@ def zsg_loss(att_out, bbx_out, annot, anchs, cfg=None):
     pos, top1, _ = match(annot, anchs, cfg["matching_threshold"])
     if not cfg["use_multi"]:
         pos = torch.zeros_like(pos)
-        pos[torch.arange(annot.shape[0]), top1] = True
+        pos[torch.arange(annot.shape[0], device=annot.device), top1] = True
     tgt = gt_reg_targets(anchs, annot)
     box_l = F.smooth_l1_loss(bbx_out.double(), tgt, reduction="none")       # f32 vs f64 -> f64
     posf = pos.float()
@@ -174,7 +174,7 @@ def evaluate(att_out, bbx_out, annot, img_size, anchs, cfg=None):
     score, best = torch.sigmoid(att_out).squeeze(-1).max(1)
     top1 = iou_gt_vs_anchors(annot, anchs).max(1)[1]
     boxes = decode_boxes(anchs, bbx_out)                                     # [B,A,4] f64
-    ar = torch.arange(B)
+    ar = torch.arange(B, device=annot.device)
     thr = cfg["acc_iou_threshold"]
     maxpos = (iou_pairwise_diag(boxes[ar, top1], annot) >= thr).float().mean()
     pb = boxes[ar, best]
@@ -289,7 +289,7 @@ def lstm_query_batched(sd, qvec, qlens, h0, c0):
     lens = qlens.long()
     _, perm = qlens.sort(0, descending=True)
     inv = torch.empty_like(perm)
-    inv[perm] = torch.arange(B)
+    inv[perm] = torch.arange(B, device=perm.device)
     h, c = h0[0][inv], c0[0][inv]                                 # sample b uses sorted row inv[b]
     gx = qvec @ sd["lstm.weight_ih_l0"].t() + sd["lstm.bias_ih_l0"] + sd["lstm.bias_hh_l0"]
     for t in range(int(lens.max())):
@@ -299,7 +299,7 @@ def lstm_query_batched(sd, qvec, qlens, h0, c0):
         h2 = o * c2.tanh()
         live = (t < lens).unsqueeze(1)
         c, h = torch.where(live, c2, c), torch.where(live, h2, h)
-    xl = qvec[torch.arange(B), lens - 1]
+    xl = qvec[torch.arange(B, device=lens.device), lens - 1]
     hr, cr = h0[1][inv], c0[1][inv]
     g = (xl @ sd["lstm.weight_ih_l0_reverse"].t() + sd["lstm.bias_ih_l0_reverse"]
          + hr @ sd["lstm.weight_hh_l0_reverse"].t() + sd["lstm.bias_hh_l0_reverse"])
@@ -316,7 +316,7 @@ def fuse_and_head(sd, feats, lang):
     B = lang.shape[0]
     for x in feats:
         H, W = x.shape[2], x.shape[3]
-        grid = make_grid(H, W).permute(2, 0, 1).unsqueeze(0).expand(B, 2, H, W)
+        grid = make_grid(H, W).to(x.device).permute(2, 0, 1).unsqueeze(0).expand(B, 2, H, W)
         we = lang.view(B, -1, 1, 1).expand(B, lang.shape[1], H, W)
         y = torch.cat([x, we, grid], dim=1)
         for i in range(5):
@@ -340,6 +340,7 @@ def zsgnet_forward(sd, batch, training=True, h0c0=None, batched_lstm=True, retur
     max_qlen = int(qlens.max().item())
     qvec = qvec[:, :max_qlen].contiguous()
     h0, c0 = h0c0 if h0c0 is not None else draw_h0c0(img.shape[0])
+    h0, c0 = h0.to(img.device), c0.to(img.device)          # drawn on the CPU, then moved (mdl.py:291-292)
     lang = (lstm_query_batched if batched_lstm else lstm_query)(sd, qvec, qlens, h0, c0)
     bn = BNState(sd, training)
     c3, c4, c5 = resnet50_c3c4c5(sd, img, bn)
@@ -376,7 +377,7 @@ def train_step(sd, batch, opt_state=None, lr=1e-4, seed=None, do_adam=True):
     for k in keys:
         sd[k] = sd[k].detach().requires_grad_(True)
     out = zsgnet_forward(sd, batch, training=True)
-    anchs = default_anchors()
+    anchs = default_anchors().to(batch["img"].device)
     ls = zsg_loss(out["att_out"], out["bbx_out"], batch["annot"], anchs)
     ls["loss"].mean().backward()
     grads = {k: sd[k].grad for k in keys}

@@ -1,0 +1,75 @@
+"""Data-parallel gradient exchange (the path's only collective; main_dist.py:36-40).
+
+One process per GPU.  Parameters and gradients live in flat arenas ordered by backward completion,
+so a gradient bucket is a contiguous slice: as soon as the engine reports a slice final, it is
+all-reduced with NCCL (NVLink 5 / NVSwitch) on a side stream while the backward continues.  The 1/N
+averaging is folded into the Adam kernel (grad_scale), so no extra pass touches the gradients.
+BatchNorm statistics stay per rank, like the reference's non-synchronised BatchNorm."""
+import torch
+import torch.distributed as dist
+
+
+class GradReducer:
+    def __init__(self, store, min_bucket_elems=4 << 20, group=None):
+        self.store, self.group = store, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.min_bucket = min_bucket_elems
+        self.comm_stream = torch.cuda.Stream() if (self.world > 1 and store.grad_arena.is_cuda) else None
+        self._lo = None
+        self._works = []
+        self.bytes_reduced = 0
+        self.calls = 0
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world
+
+    def on_bucket(self, lo, hi):
+        """Engine callback: grad_arena[lo:hi] is final (called in increasing arena order)."""
+        if self.world == 1:
+            return
+        if self._lo is None:
+            self._lo = lo
+        if hi - self._lo >= self.min_bucket or hi >= self.store.used:
+            self._launch(self._lo, hi)
+            self._lo = None
+
+    def _launch(self, lo, hi):
+        buf = self.store.grad_arena[lo:hi]
+        self.bytes_reduced += buf.numel() * 4
+        self.calls += 1
+        if self.comm_stream is None:                      # gloo / CPU tests
+            self._works.append(dist.all_reduce(buf, group=self.group, async_op=True))
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(buf, group=self.group)        # NCCL: enqueued on comm_stream, overlaps the backward
+
+    def finish(self):
+        """Make the compute stream wait for every outstanding all-reduce (call before the optimiser)."""
+        if self.world == 1:
+            return
+        if self._lo is not None:
+            self._launch(self._lo, self.store.used)
+            self._lo = None
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def broadcast_state(self, net):
+        """Rank 0's parameters and BatchNorm buffers to every rank (DDP does this at construction)."""
+        if self.world == 1:
+            return
+        dist.broadcast(self.store.param_arena, 0, group=self.group)
+        dist.broadcast(net._bn_f, 0, group=self.group)
+        dist.broadcast(net._bn_n, 0, group=self.group)
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard of a global batch: rank r takes [r*B, (r+1)*B)."""
+    per = n_items // world
+    return rank * per, (rank + 1) * per

@@ -398,6 +398,8 @@ class Engine:
         self.fwd.append(("op", ConvOp(hs[4], w5, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
                                       impl=self.impl)))
         self.d_out = self.buf(B, A, 5)
+        self.dbg = dict(x0=x0, c1=c1, c3=c3, c4=c4, c5=c5, feat=feat, lang=lang, hs=hs, fused=fused, lvl_off=lvl_off,
+                        blocks=blocks)
         wt5, wt5p = self.buf(256 * 9 * 45), self.buf(256 * 9 * 48)
         wts = [self.buf(256 * 9 * 256) for _ in range(5)]
         wt0 = self.buf(CP * 9 * 256)

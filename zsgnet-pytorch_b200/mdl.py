@@ -91,6 +91,8 @@ class ZSGNet(nn.Module):
         self.cfg = cfg
         self.n_anchors = n_anchors
         dev = torch.device(device if device is not None else "cuda")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.store = ParamStore(dev)
         self.param_names = [n for n, _, _ in spec.trainable_specs()]
         for n in self.param_names + [u[0] for u in spec.UNUSED_SPECS]:
