@@ -106,8 +106,14 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per C-ABI call (memsets not counted); used for bench.py's gpu_launches claim
+KERNELS_PER_CALL = {"zsg_match_loss": 4, "zsg_eval": 2, "zsg_unfuse_lang_grid": 2}
+LAUNCH_COUNT = [0]
+
+
 def call(name, *args):
     lib = load()
+    LAUNCH_COUNT[0] += KERNELS_PER_CALL.get(name, 1)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise ZsgError(f"{name} failed ({rc}): {lib.zsg_last_error_string().decode()}")

@@ -63,6 +63,21 @@ class SyntheticImgQuDataset(Dataset):
                 "img_size": torch.tensor([h, w])}
 
 
+def synthetic_batch(B, seed=0, T=20, img_hw=300, pin=False):
+    """A whole batch at once with the collater's keys/dtypes (BASELINE shape: 300x300, qlen = T)."""
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(B, 2, generator=g) * 1.2 - 0.6
+    s = torch.rand(B, 2, generator=g) * 0.7 + 0.1
+    annot = torch.cat([c - s / 2, c + s / 2], dim=1).clamp_(-1, 1)
+    hw = torch.tensor([[480.0, 640.0]]).repeat(B, 1)
+    orig = torch.stack([(annot[:, 1] + 1) / 2 * 640, (annot[:, 0] + 1) / 2 * 480, (annot[:, 3] + 1) / 2 * 640,
+                        (annot[:, 2] + 1) / 2 * 480], dim=1)
+    out = {"img": torch.rand(B, 3, img_hw, img_hw, generator=g), "idxs": torch.arange(B).float(),
+           "qvec": torch.randn(B, T, 300, generator=g), "qlens": torch.full((B,), float(T)), "annot": annot,
+           "orig_annot": orig, "img_size": hw}
+    return {k: v.pin_memory() for k, v in out.items()} if pin else out
+
+
 def collater(batch):
     """dat_loader.py:187-196: stack, cast everything to float, trim qvec to the batch's longest phrase."""
     qlens = torch.Tensor([i["qlens"] for i in batch])

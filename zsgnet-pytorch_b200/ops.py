@@ -8,6 +8,30 @@ from . import _lib
 from ._lib import ConvParams, WgradParams, call, ptr, stream
 
 IMPL_TC, IMPL_SIMT = 0, 1
+PROFILER = None          # set by bench.py: per-launch CUDA-event timing of the implicit-GEMM kernels
+
+
+class LaunchProfiler:
+    """CUDA events around every implicit-GEMM launch on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.records = []                # (kernel, flops, start_event, end_event)
+
+    def timed(self, op, entry):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        call(entry, op.ref, stream())
+        b.record()
+        self.records.append((op.kernel, op.flops, a, b))
+
+    def summary(self):
+        out = {}
+        for k, f, a, b in self.records:
+            d = out.setdefault(k, dict(launches=0, flops=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += f
+            d["ms"] += a.elapsed_time(b)
+        return out
 
 
 def _f32c(t):
@@ -26,8 +50,12 @@ class ConvOp:
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
                             impl)
         self.ref = C.byref(self.p)
+        self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
+        self.kernel = "conv_tc_kernel"
 
     def __call__(self):
+        if PROFILER is not None:
+            return PROFILER.timed(self, "zsg_conv_fwd")
         call("zsg_conv_fwd", self.ref, stream())
 
 
@@ -39,8 +67,12 @@ class WgradOp:
         self.p = WgradParams(ptr(x), ptr(dy), ptr(dw), ptr(rows), m, cin, cout, r, s, ptr(in_scale), ptr(in_shift),
                              int(in_relu), split_k, impl)
         self.ref = C.byref(self.p)
+        self.flops = 2.0 * m * cout * r * s * cin
+        self.kernel = "wgrad_tc_kernel"
 
     def __call__(self):
+        if PROFILER is not None:
+            return PROFILER.timed(self, "zsg_conv_wgrad")
         call("zsg_conv_wgrad", self.ref, stream())
 
 
