@@ -56,6 +56,8 @@ typedef struct {
 typedef struct {
   const float* x;          /* input activations                                             */
   const float* w;          /* [cout][r][s][cin] (K-major)                                   */
+  const float* w_lo;       /* optional: if set, `w` holds the TF32-exact high parts and w_lo the fp32 remainders
+                              (zsg_split_tf32) and the weight operand is fetched by TMA instead of gathered */
   float* y;                /* output                                                        */
   const zsg_row_t* rows;   /* [m]                                                           */
   int32_t m, cin, cout, r, s;
@@ -93,6 +95,8 @@ int zsg_conv_wgrad(const zsg_wgrad_params* p, zsg_stream_t stream);
 /* w [cout][r][s][cin] -> wt [cin][r][s][cout] with the taps flipped: the dgrad of a conv is the
  * forward kernel applied to wt. */
 int zsg_weight_transpose_flip(const float* w, float* wt, int cout, int rs_r, int rs_s, int cin, zsg_stream_t stream);
+/* hi[i] = w[i] with the 13 low mantissa bits cleared (exactly representable in TF32), lo[i] = w[i] - hi[i]. */
+int zsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, zsg_stream_t stream);
 /* row-wise channel padding copy: dst[n][0:cdst] = src[n][0:csrc] (zero fill / truncate). */
 int zsg_pad_channels(const float* src, float* dst, int64_t n, int csrc, int cdst, zsg_stream_t stream);
 /* NCHW image -> NHWC with 4 channels (4th = 0) for the stem (mdl.py:149). */

@@ -43,6 +43,7 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     # 53 trunk convs + 8 FPN + 6 head + 1 LSTM projection
     assert fwd["zsg_conv_fwd"] == 53 + 8 + 6 + 1
     assert fwd["zsg_bn_stats"] == 53 and fwd["zsg_bn_finalize"] == 53 and fwd["zsg_bn_apply"] == 16
+    assert fwd["zsg_split_tf32"] == 2 and fwd["zsg_pad_channels"] == 2
     assert fwd["zsg_lstm_fwd_dir"] == 1 and fwd["zsg_lstm_rev_step"] == 1 and fwd["zsg_fuse_lang_grid"] == 1
     del calls[:]
     eng.forward(training=False)
@@ -56,7 +57,7 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     assert bwd["zsg_conv_wgrad"] == 53 + 8 + 6 + 4
     assert bwd["zsg_conv_fwd"] == 52 + 8 + 6                           # data gradients run through the forward kernel
     assert bwd["zsg_bn_bwd_reduce"] == 53 and bwd["zsg_bn_bwd_apply"] == 53
-    assert bwd["zsg_weight_transpose_flip"] == 52 + 8 + 6
+    assert bwd["zsg_weight_transpose_flip"] == 52 + 8 + 6 and bwd["zsg_split_tf32"] == 1
     # buckets: contiguous, ordered, covering the used arena exactly once
     assert seen[0][0] == 0 and seen[-1][1] == store.used
     for (a, b), (c, d) in zip(seen, seen[1:]):

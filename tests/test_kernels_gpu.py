@@ -181,6 +181,30 @@ def test_conv_fwd_vs_torch(zsg, case, impl):
     assert rel_err(y, nhwc(ref)) < 2e-5
 
 
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_tma_weights(zsg, case):
+    """Weights pre-split into TF32 hi/lo images and fetched by TMA (the path the engine uses)."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(hash(case) % 1000 + 1)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    ref = F.conv2d(x, w, bias, stride=stride, padding=pad)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    wk = khwc(w)
+    hi, lo = torch.empty_like(wk), torch.empty_like(wk)
+    ops.split_tf32(wk, hi, lo, wk.numel())
+    torch.cuda.synchronize()
+    assert torch.equal(hi + lo, wk) and int((hi.view(torch.int32) & 0x1FFF).abs().sum()) == 0
+    for impl in (0, 1):
+        y = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
+        ops.ConvOp(nhwc(x), hi, y, rows, B * Ho * Wo, cin, cout, k, k, bias=bias, impl=impl, w_lo=lo)()
+        torch.cuda.synchronize()
+        assert rel_err(y, nhwc(ref)) < 2e-5, impl
+
+
 @pytest.mark.parametrize("impl", [0, 1])
 def test_conv_prologue_epilogue(zsg, impl):
     """BatchNorm affine + ReLU on load (zero padding stays zero), bias, residual, ReLU on store."""
@@ -260,6 +284,27 @@ def test_conv_wgrad_vs_torch(zsg, case, impl):
                 impl=impl)()
     torch.cuda.synchronize()
     assert rel_err(dw, khwc(w.grad)) < 3e-5
+
+
+def test_wgrad_mn_major_descriptor_probe(zsg):
+    """Reports which LBO/SBO reading of the MN-major smem descriptor is right (impl 0 = product, 7 = swapped)."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k = 2, 256, 12, 12, 256, 3
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / 48).cuda().requires_grad_(True)
+    y = F.conv2d(x, w, None, padding=1)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    rows = geo.conv_rows(B, H, W, cin, H, W, cout, 1, 1).cuda()
+    errs = {}
+    for impl in (0, 7):
+        dw = torch.zeros(cout, k, k, cin, device="cuda")
+        ops.WgradOp(nhwc(x), nhwc(dy), dw, rows, B * H * W, cin, cout, k, k, impl=impl)()
+        torch.cuda.synchronize()
+        errs[impl] = rel_err(dw, khwc(w.grad))
+    print("MN-major descriptor probe: rel err product layout %.3e, swapped LBO/SBO %.3e" % (errs[0], errs[7]))
+    assert errs[0] < 3e-5, errs
 
 
 def test_conv_multilevel_shared_weights(zsg):

@@ -21,7 +21,7 @@ class RowT(C.Structure):
 
 
 class ConvParams(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("y", C.c_void_p), ("rows", C.c_void_p),
+    _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("w_lo", C.c_void_p), ("y", C.c_void_p), ("rows", C.c_void_p),
                 ("m", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
                 ("in_div", C.c_int32), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
@@ -46,6 +46,7 @@ SIGNATURES = {
     "zsg_conv_wgrad": [C.POINTER(WgradParams), _P],
     "zsg_weight_transpose_flip": [_P, _P, _I, _I, _I, _I, _P],
     "zsg_pad_channels": [_P, _P, _L, _I, _I, _P],
+    "zsg_split_tf32": [_P, _P, _P, _L, _P],
     "zsg_nchw_to_nhwc4": [_P, _P, _I, _I, _I, _P],
     "zsg_colsum": [_P, _P, _L, _I, _I, _I, _P],
     "zsg_gather_rows": [_P, _P, _P, _L, _I, _I, _P],

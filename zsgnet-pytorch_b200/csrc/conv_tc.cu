@@ -15,6 +15,8 @@
 // K-major smem tiles.  Stages are handed over with mbarriers: full[s] (128 producer arrivals after
 // fence.proxy.async), empty[s] / acc_full[a] (tcgen05.commit), acc_empty[a] (256 drain arrivals).
 // Warp roles and the chunked-promotion scheme are described above setup_pipeline().
+#include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace zsg {
@@ -75,8 +77,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n, bool mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -90,6 +93,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -102,6 +119,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- TMA (cp.async.bulk.tensor) for the weight operand --------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
 }
 
 // TF32-exact high part and fp32 residual (both representable: hi + lo == v exactly).
@@ -153,26 +181,28 @@ struct Smem {
   static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
 };
 
-struct PipeBars {
-  uint32_t full[4], empty[4], acc_full[2], acc_empty[2], tmem_slot;
+struct PipeBars {                      // mbarrier addresses are computed, never indexed from memory
+  uint32_t bar0;
+  __device__ __forceinline__ uint32_t full(int s) const { return bar0 + 8 * s; }
+  __device__ __forceinline__ uint32_t empty(int s) const { return bar0 + 32 + 8 * s; }
+  __device__ __forceinline__ uint32_t acc_full(int a) const { return bar0 + 64 + 8 * a; }
+  __device__ __forceinline__ uint32_t acc_empty(int a) const { return bar0 + 80 + 8 * a; }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return bar0 + 96; }
 };
 
 template <int BN>
-__device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int lane) {
+__device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int lane, int full_count = NPROD) {
   using S = Smem<BN>;
   PipeBars pb;
-  const uint32_t bar0 = smem_u32(sm + S::BAR_OFF);
-  for (int i = 0; i < 4; ++i) { pb.full[i] = bar0 + 8 * i; pb.empty[i] = bar0 + 32 + 8 * i; }
-  for (int i = 0; i < 2; ++i) { pb.acc_full[i] = bar0 + 64 + 8 * i; pb.acc_empty[i] = bar0 + 80 + 8 * i; }
-  pb.tmem_slot = bar0 + 96;
+  pb.bar0 = smem_u32(sm + S::BAR_OFF);
   if (warp == MMA_WARP) {
     if (lane == 0) {
-      for (int i = 0; i < S::STAGES; ++i) { mbar_init(pb.full[i], NPROD); mbar_init(pb.empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(pb.acc_full[i], 1); mbar_init(pb.acc_empty[i], NDRAIN); }
+      for (int i = 0; i < S::STAGES; ++i) { mbar_init(pb.full(i), full_count); mbar_init(pb.empty(i), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(pb.acc_full(i), 1); mbar_init(pb.acc_empty(i), NDRAIN); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(pb.tmem_slot, S::TMEM_COLS);
+    tmem_alloc(pb.tmem_slot(), S::TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -180,36 +210,53 @@ __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int la
   return pb;
 }
 
-// single-thread MMA issue loop (3xTF32: lo*hi + hi*lo + hi*hi), one TMEM accumulator per chunk
-template <int BN>
-__device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb) {
+// MMA issue loop (3xTF32: lo*hi + hi*lo + hi*hi), one TMEM accumulator per chunk.  The whole warp runs the
+// loop so that descriptors and addresses live in uniform registers; only the tcgen05 instructions are
+// predicated on one elected lane (a single divergent thread makes the compiler wrap every UTCHMMA in an
+// ELECT / R2UR.BROADCAST loop, which costs more than the 64-cycle tf32 MMA itself).
+// MN_MAJOR (weight-gradient kernel): both operands are stored as they lie in memory, [pixel][channel].  For 32-bit
+// operands the only MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1): atoms of
+// 4 pixel rows x 128 B (32 channels) in which the 32-byte granule g of row r is stored at granule g ^ r (byte-address
+// bits [5,7) ^= bits [7,9)).  Tile = [channel atom][pixel group of 4][4][128 B]: LBO = 4096 B between channel atoms, SBO = 512 B
+// between pixel groups; one MMA (K = 8) consumes two pixel groups (1024 B).
+template <int BN, bool MN_MAJOR = false>
+__device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb,
+                                         bool swap_lbo_sbo = false) {
   using S = Smem<BN>;
-  constexpr uint32_t idesc = umma_idesc_tf32(BN);
+  constexpr uint32_t idesc = umma_idesc_tf32(BN, MN_MAJOR);
+  const uint32_t tiles0 = smem_u32(sm);
+  const uint64_t lbo = MN_MAJOR ? (swap_lbo_sbo ? 32ull : 256ull) : 1ull;
+  const uint64_t sbo = MN_MAJOR ? (swap_lbo_sbo ? 256ull : 32ull) : 64ull;
+  const uint64_t desc_hi = (lbo << 16) | (sbo << 32) | (1ull << 46) | ((MN_MAJOR ? 1ull : 2ull) << 61);
+  constexpr uint32_t kstep = MN_MAJOR ? 64u : 2u;          // descriptor start-address advance per MMA (16 B units)
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % S::STAGES;
     const int chunk = kb / CHUNK_KB;
     const bool first = (kb % CHUNK_KB) == 0;
     const uint32_t tmem_d = tmem_base + (uint32_t)(chunk & 1) * BN;
     if (first) {                                          // the drain warps must have emptied this accumulator
-      mbar_wait(pb.acc_empty[chunk & 1], ((chunk >> 1) & 1) ^ 1);
+      mbar_wait(pb.acc_empty(chunk & 1), ((chunk >> 1) & 1) ^ 1);
       tc_fence_after();
     }
-    mbar_wait(pb.full[s], (kb / S::STAGES) & 1);
+    mbar_wait(pb.full(s), (kb / S::STAGES) & 1);
     tc_fence_after();
-    const uint32_t a_hi = smem_u32(sm + s * S::STAGE_BYTES);
-    const uint32_t a_lo = a_hi + A_TILE_BYTES;
-    const uint32_t b_hi = a_lo + A_TILE_BYTES;
-    const uint32_t b_lo = b_hi + S::B_TILE_BYTES;
+    const uint32_t a_hi = (tiles0 + s * S::STAGE_BYTES) >> 4;
+    const uint32_t a_lo = a_hi + (A_TILE_BYTES >> 4);
+    const uint32_t b_hi = a_lo + (A_TILE_BYTES >> 4);
+    const uint32_t b_lo = b_hi + (S::B_TILE_BYTES >> 4);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < KB / 8; ++k) {
-      const uint64_t dah = umma_desc_sw128(a_hi + 32 * k), dal = umma_desc_sw128(a_lo + 32 * k);
-      const uint64_t dbh = umma_desc_sw128(b_hi + 32 * k), dbl = umma_desc_sw128(b_lo + 32 * k);
-      umma_tf32(tmem_d, dal, dbh, idesc, (first && k == 0) ? 0u : 1u);
-      umma_tf32(tmem_d, dah, dbl, idesc, 1);
-      umma_tf32(tmem_d, dah, dbh, idesc, 1);
+      for (int k = 0; k < KB / 8; ++k) {
+        const uint64_t dah = desc_hi | (uint64_t)((a_hi + kstep * k) & 0x3FFFu), dal = desc_hi | (uint64_t)((a_lo + kstep * k) & 0x3FFFu);
+        const uint64_t dbh = desc_hi | (uint64_t)((b_hi + kstep * k) & 0x3FFFu), dbl = desc_hi | (uint64_t)((b_lo + kstep * k) & 0x3FFFu);
+        umma_tf32(tmem_d, dal, dbh, idesc, (first && k == 0) ? 0u : 1u);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1);
+        umma_tf32(tmem_d, dah, dbh, idesc, 1);
+      }
+      umma_commit(pb.empty(s));                           // frees the stage once the MMAs above have read it
+      if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(pb.acc_full(chunk & 1));
     }
-    umma_commit(pb.empty[s]);                             // frees the stage once the MMAs above have read it
-    if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(pb.acc_full[chunk & 1]);
+    __syncwarp();
   }
 }
 
@@ -221,26 +268,28 @@ __device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_bas
   for (int i = 0; i < BN / 2; ++i) acc[i] = 0.f;
   const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
   for (int c = 0; c < nchunks; ++c) {
-    mbar_wait(pb.acc_full[c & 1], (c >> 1) & 1);
+    mbar_wait(pb.acc_full(c & 1), (c >> 1) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(c & 1) * BN + half * (BN / 2);
 #pragma unroll
-    for (int cb = 0; cb < BN / 64; ++cb) {
-      uint32_t r[32];
-      tmem_ld32(taddr + cb * 32, r);
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t r[16];
+      tmem_ld16(taddr + cb * 16, r);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cb * 32 + j] += __uint_as_float(r[j]);
+      for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += __uint_as_float(r[j]);
     }
     tc_fence_before();
-    mbar_arrive(pb.acc_empty[c & 1]);
+    mbar_arrive(pb.acc_empty(c & 1));
   }
 }
 
 // ============================================================================================
 // forward / data-gradient kernel
 // ============================================================================================
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_params p) {
+template <int BN, bool TMA_W>
+__global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_params p,
+                                                               const __grid_constant__ CUtensorMap tm_hi,
+                                                               const __grid_constant__ CUtensorMap tm_lo) {
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -256,72 +305,100 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
     if (m0 + tid < p.m) e = __ldg(reinterpret_cast<const int4*>(p.rows) + m0 + tid);
     rows_s[tid] = e;
   }
-  PipeBars pb = setup_pipeline<BN>(sm, warp, lane);       // contains __syncthreads
+  PipeBars pb = setup_pipeline<BN>(sm, warp, lane, TMA_W ? NPROD + 1 : NPROD);   // contains __syncthreads
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 96);
 
   if (warp == MMA_WARP) {
-    if (lane == 0) mma_loop<BN>(sm, pb, tmem_base, nkb);
-    __syncwarp();
+    mma_loop<BN>(sm, pb, tmem_base, nkb);
   } else if (warp < DRAIN_WARP0) {
     // ------------------------------ producers ------------------------------
+    // Thread (rsub, chunk) owns the 16-byte chunk `chunk` of rows rsub, rsub+16, ... of every K block of its
+    // group.  Its filter tap changes only every cin/32 K blocks, so the bounds check and the pixel offset of
+    // its 8 rows are cached per tap; the swizzled smem offset is a compile-time function of (it, rsub, chunk).
     const int group = warp >> 2;
     const int t = tid & 127;
-    const int chunk = t & 7;             // 16-byte chunk of the 128-byte K row
-    const int rsub = t >> 3;             // 0..15
+    const int chunk = t & 7;
+    const int rsub = t >> 3;
+    const int soff = rsub * 128 + ((chunk ^ (rsub & 7)) << 4);      // + it * 2048 (16 rows x 128 B)
     int c = chunk * 4 + group * KB, tap = 0, tr = 0, ts = 0;
     while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
     const int ntap = p.r * p.s;
+    int cached_tap = -1;
+    int off[8];                                                     // element offset of the tap's pixel, -1 = padding
     for (int kb = group; kb < nkb; kb += NGROUP) {
       const int s = kb % S::STAGES;
-      mbar_wait(pb.empty[s], ((kb / S::STAGES) & 1) ^ 1);
-      uint8_t* a_hi = sm + s * S::STAGE_BYTES;
-      uint8_t* a_lo = a_hi + A_TILE_BYTES;
-      uint8_t* b_hi = a_lo + A_TILE_BYTES;
-      uint8_t* b_lo = b_hi + S::B_TILE_BYTES;
       const bool kvalid = tap < ntap;
-      const int kk = kb * KB + chunk * 4;
-      // ---- issue every load of this K block first: 8 im2col rows (A) and BN/16 weight rows (B) ----
-      float4 va[8], vb[BN / 16];
-      bool oka[8];
+      if (tap != cached_tap) {
+        cached_tap = tap;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int4 e = rows_s[it * 16 + rsub];
+          int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+          const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+          bool ok = kvalid;
+          if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
+          ok = ok && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          off[it] = ok ? e.x + (yy * win + xx) * p.cin : -1;
+        }
+      }
+      // issue the gather loads before waiting for the stage: they only need registers
+      // (p.impl >= 2 are timing ablations used by tools/ablate_conv.py: 2 = no gather loads, 3 = also no smem
+      //  stores, 4 = also no proxy fence, 5 = everything but the proxy fence; results are garbage then)
+      float4 va[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const int4 e = rows_s[it * 16 + rsub];
-        int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
-        const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-        bool ok = kvalid;
-        if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
-        ok = ok && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
-        oka[it] = ok;
         va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) va[it] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin + c));
+        if (off[it] >= 0 && (p.impl < 2 || p.impl == 5))
+          va[it] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)off[it] + c));
       }
+      float4 vb[TMA_W ? 1 : BN / 16];
+      if (!TMA_W) {
+        const int kk = kb * KB + chunk * 4;
 #pragma unroll
-      for (int it = 0; it < BN / 16; ++it) {
-        const int n = n0 + it * 16 + rsub;
-        vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kvalid && n < p.cout) vb[it] = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)n * K + kk));
+        for (int it = 0; it < BN / 16; ++it) {
+          const int n = n0 + it * 16 + rsub;
+          vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kvalid && n < p.cout) vb[it] = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)n * K + kk));
+        }
       }
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.in_scale && kvalid) {
         sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + c));
         sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + c));
       }
+      mbar_wait(pb.empty(s), ((kb / S::STAGES) & 1) ^ 1);
+      uint8_t* a_hi = sm + s * S::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_TILE_BYTES;
+      uint8_t* b_hi = a_lo + A_TILE_BYTES;
+      uint8_t* b_lo = b_hi + S::B_TILE_BYTES;
+      if (TMA_W && t == 0 && p.impl != 6) {                         // weights: two TMA tiles, no register pass
+        mbar_arrive_expect_tx(pb.full(s), 2 * S::B_TILE_BYTES);
+        tma_load_2d(smem_u32(b_hi), &tm_hi, kb * KB, n0, pb.full(s));
+        tma_load_2d(smem_u32(b_lo), &tm_lo, kb * KB, n0, pb.full(s));
+      }
+      if (TMA_W && t == 0 && p.impl == 6) mbar_arrive(pb.full(s));   // ablation 6: no weight TMA
+      if (p.impl != 3 && p.impl != 4)
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         float4 v = va[it];
-        if (oka[it]) {
+        if (off[it] >= 0) {
           if (p.in_scale) {
             v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
             v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
           }
           if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         }
-        store_split(a_hi, a_lo, it * 16 + rsub, chunk, v);
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<float4*>(a_hi + soff + it * 2048) = h;
+        *reinterpret_cast<float4*>(a_lo + soff + it * 2048) = l;
       }
+      if (!TMA_W) {
 #pragma unroll
-      for (int it = 0; it < BN / 16; ++it) store_split(b_hi, b_lo, it * 16 + rsub, chunk, vb[it]);
-      fence_proxy_async();
-      mbar_arrive(pb.full[s]);
+        for (int it = 0; it < BN / 16; ++it) store_split(b_hi, b_lo, it * 16 + rsub, chunk, vb[it]);
+      }
+      if (p.impl != 4 && p.impl != 5) fence_proxy_async();
+      mbar_arrive(pb.full(s));
       // advance this thread's (tap, channel) by NGROUP K blocks
       c += NGROUP * KB;
       while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
@@ -374,6 +451,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
 
 // ============================================================================================
 // weight-gradient kernel:  D[j = (tap,c)][n] = sum_pix X_gathered[pix][j] * dY[pix][n]
+// Both operands are read as they lie in memory (pixel rows, channels contiguous) with 128-bit coalesced loads
+// and stored MN-major; no transposition anywhere.
 // ============================================================================================
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_params p, int kb_per_split) {
@@ -394,74 +473,99 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 96);
 
   if (warp == MMA_WARP) {
-    if (lane == 0) mma_loop<BN>(sm, pb, tmem_base, nkb);
-    __syncwarp();
+    mma_loop<BN, true>(sm, pb, tmem_base, nkb, p.impl == 7);
   } else if (warp < DRAIN_WARP0) {
     const int group = warp >> 2;
     const int t = tid & 127;
-    const int j = j0 + t;                                   // this thread's D row = (tap, channel)
+    const int mc = t & 31;                                  // 16-byte chunk (4 channels) of the 128-channel tile row
+    const int ps = t >> 5;                                  // pixel sub-index 0..3
+    const int atom_off = (mc >> 3) * 4096;                  // channel atom
+    const int cj = mc & 7;
+    // A side: this thread's 4 channels j..j+3 of D's row index = (tap, c)
+    const int j = j0 + mc * 4;
     const bool jvalid = j < Kt;
     int tap = 0, c = 0, tr = 0, ts = 0;
     if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
-    float sc = 1.f, sh = 0.f;
-    if (p.in_scale && jvalid) { sc = __ldg(p.in_scale + c); sh = __ldg(p.in_shift + c); }
-    const int n = n0 + t;
-    const bool nvalid = t < BN && n < p.cout;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.in_scale && jvalid) {
+      sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + c));
+      sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + c));
+    }
+    // B side: 4 output channels n..n+3
+    const int n = n0 + mc * 4;
+    const bool bthread = mc * 4 < BN;
     const int4* rows = reinterpret_cast<const int4*>(p.rows);
     int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 64;       // [2][32] entries per group
     int it = 0;
     for (int i = group; i < nkb; i += NGROUP, ++it) {
       const int s = i % S::STAGES;
       const int pix0 = (kb_begin + i) * KB;
-      // stage the 32 row entries of this K block in smem (one global load instead of 32 per thread)
       int4* eb = ent + (it & 1) * 32;
-      if (t < 32) {
-        int4 e = make_int4(0, 0, 0, 0);
+      if (t < 32) {                                          // stage this K block's 32 row entries
+        int4 e = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
         if (pix0 + t < p.m) e = __ldg(rows + pix0 + t);
         eb[t] = e;
       }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
-      mbar_wait(pb.empty[s], ((i / S::STAGES) & 1) ^ 1);
       uint8_t* a_hi = sm + s * S::STAGE_BYTES;
       uint8_t* a_lo = a_hi + A_TILE_BYTES;
       uint8_t* b_hi = a_lo + A_TILE_BYTES;
       uint8_t* b_lo = b_hi + S::B_TILE_BYTES;
+      bool waited = false;
 #pragma unroll
-      for (int hp = 0; hp < 2; ++hp) {                       // two halves of 16 pixels: 32 loads in flight
-        float xa[16], yb[16];
+      for (int hp = 0; hp < 2; ++hp) {                       // 2 x (4 pixels of A + 4 pixels of B) in flight
+        float4 xa[4], yb[4];
+        bool oka[4];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int4 e = eb[hp * 16 + q];
-          const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
-          const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;     // hin = 0 past the last pixel
-          const bool ok = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
-          xa[q] = 0.f;
-          yb[q] = 0.f;
-          if (ok) xa[q] = __ldg(p.x + (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin + c);
-          if (nvalid && hin > 0) yb[q] = __ldg(p.dy + (int64_t)e.w + n);
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int4 e = eb[hp * 16 + q];
+        for (int q = 0; q < 4; ++q) {
+          const int pixel = (hp * 4 + q) * 4 + ps;           // 0..31 within the K block
+          const int4 e = eb[pixel];
           const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
           const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-          const bool ok = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
-          if (ok) {
-            float v = xa[q];
-            if (p.in_scale) v = fmaf(v, sc, sh);
-            if (p.in_relu) v = fmaxf(v, 0.f);
-            xa[q] = v;
+          oka[q] = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          xa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          yb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (oka[q]) xa[q] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin + c));
+          if (bthread && hin > 0 && n < p.cout) {
+            const float* src = p.dy + (int64_t)e.w + n;
+            if (((e.w & 3) == 0) && n + 3 < p.cout) {
+              yb[q] = __ldg(reinterpret_cast<const float4*>(src));
+            } else {                                         // ragged channel count (45): scalar, bounded
+              yb[q].x = __ldg(src);
+              if (n + 1 < p.cout) yb[q].y = __ldg(src + 1);
+              if (n + 2 < p.cout) yb[q].z = __ldg(src + 2);
+              if (n + 3 < p.cout) yb[q].w = __ldg(src + 3);
+            }
           }
         }
+        if (!waited) { mbar_wait(pb.empty(s), ((i / S::STAGES) & 1) ^ 1); waited = true; }
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          store_split(a_hi, a_lo, t, hp * 4 + ch, make_float4(xa[ch * 4], xa[ch * 4 + 1], xa[ch * 4 + 2], xa[ch * 4 + 3]));
-          if (t < BN)
-            store_split(b_hi, b_lo, t, hp * 4 + ch, make_float4(yb[ch * 4], yb[ch * 4 + 1], yb[ch * 4 + 2], yb[ch * 4 + 3]));
+        for (int q = 0; q < 4; ++q) {
+          const int pixel = (hp * 4 + q) * 4 + ps;
+          const int r4 = pixel & 3;
+          const int off = atom_off + (pixel >> 2) * 512 + r4 * 128 + ((((cj >> 1) ^ r4) << 1) | (cj & 1)) * 16;
+          float4 v = xa[q];
+          if (oka[q]) {
+            if (p.in_scale) {
+              v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+              v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+            }
+            if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          }
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+          *reinterpret_cast<float4*>(a_hi + off) = h;
+          *reinterpret_cast<float4*>(a_lo + off) = l;
+          if (bthread) {
+            const float4 w = yb[q];
+            split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
+            *reinterpret_cast<float4*>(b_hi + off) = h;
+            *reinterpret_cast<float4*>(b_lo + off) = l;
+          }
         }
       }
       fence_proxy_async();
-      mbar_arrive(pb.full[s]);
+      mbar_arrive(pb.full(s));
     }
   } else {
     // drain + epilogue: lanes own consecutive j => coalesced reductions into dw[n][j]
@@ -510,7 +614,7 @@ __global__ void conv_simt_kernel(const zsg_conv_params p) {
         float v = xp[c];
         if (p.in_scale) v = fmaf(v, p.in_scale[c], p.in_shift[c]);
         if (p.in_relu) v = fmaxf(v, 0.f);
-        acc = fmaf(v, wp[c], acc);
+        acc = fmaf(v, p.w_lo ? wp[c] + p.w_lo[(int64_t)n * K + (tr * p.s + ts) * p.cin + c] : wp[c], acc);
       }
     }
   if (p.bias) acc += p.bias[n];
@@ -541,16 +645,55 @@ __global__ void wgrad_simt_kernel(const zsg_wgrad_params p) {
   p.dw[idx] += acc;
 }
 
-template <int BN>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// weights [cout][K] fp32, K contiguous: box = 32 K elements (128 B, swizzle 128B) x BN rows; OOB reads give 0
+static int make_weight_map(CUtensorMap* map, const float* w, int cout, int K, int bn) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ZSG_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for cout=%d K=%d", (int)r, cout, K); return ZSG_ECUDA; }
+  return ZSG_OK;
+}
+
+template <int BN, bool TMA_W>
 static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, TMA_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Smem<BN>::TOTAL);
     if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
   }
+  CUtensorMap tm_hi, tm_lo;
+  memset(&tm_hi, 0, sizeof(tm_hi));
+  memset(&tm_lo, 0, sizeof(tm_lo));
+  if (TMA_W) {
+    const int K = p.r * p.s * p.cin;
+    if (int rc = make_weight_map(&tm_hi, p.w, p.cout, K, BN)) return rc;
+    if (int rc = make_weight_map(&tm_lo, p.w_lo, p.cout, K, BN)) return rc;
+  }
   dim3 grid((p.cout + BN - 1) / BN, (p.m + TM - 1) / TM);
-  conv_tc_kernel<BN><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p);
+  conv_tc_kernel<BN, TMA_W><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
   return check_launch("zsg_conv_fwd");
 }
 
@@ -600,7 +743,11 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
     return check_launch("zsg_conv_fwd(simt)");
   }
   if (!zsg_device_supported()) { set_error("zsg_conv_fwd: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
-  return p.cout <= 64 ? launch_conv<64>(p, st) : launch_conv<128>(p, st);
+  if (p.w_lo) {
+    ZSG_REQUIRE(((uintptr_t)p.w_lo & 15) == 0, "zsg_conv_fwd: w_lo must be 16-byte aligned");
+    return p.cout <= 64 ? launch_conv<64, true>(p, st) : launch_conv<128, true>(p, st);
+  }
+  return p.cout <= 64 ? launch_conv<64, false>(p, st) : launch_conv<128, false>(p, st);
 }
 
 extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
@@ -608,6 +755,7 @@ extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
   const zsg_wgrad_params& p = *pp;
   ZSG_REQUIRE(p.x && p.dy && p.dw && p.rows, "zsg_conv_wgrad: null pointer");
   ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.cin > 0 && p.r > 0 && p.s > 0, "zsg_conv_wgrad: empty problem");
+  ZSG_REQUIRE(p.impl == 1 || p.cin % 4 == 0, "zsg_conv_wgrad: cin=%d must be a multiple of 4", p.cin);
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_wgrad: in_scale without in_shift");
   cudaStream_t st = as_stream(stream);
   if (p.impl == 1) {

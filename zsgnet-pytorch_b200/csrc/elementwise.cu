@@ -445,6 +445,16 @@ __global__ void __launch_bounds__(256) weight_transpose_flip_kernel(const float*
   }
 }
 
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi,
+                                                         float* __restrict__ lo, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
 __global__ void __launch_bounds__(256) pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                            int64_t n, int cs, int cd) {
   const int64_t tot = n * cd;
@@ -671,6 +681,12 @@ extern "C" int zsg_weight_transpose_flip(const float* w, float* wt, int cout, in
   weight_transpose_flip_kernel<<<grid_for((int64_t)cout * rs_r * rs_s * cin, 256), 256, 0, as_stream(stream)>>>(
       w, wt, cout, rs_r, rs_s, cin);
   return check_launch("zsg_weight_transpose_flip");
+}
+
+extern "C" int zsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, zsg_stream_t stream) {
+  ZSG_REQUIRE(w && hi && lo && n > 0, "zsg_split_tf32: bad arguments");
+  split_tf32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, hi, lo, n);
+  return check_launch("zsg_split_tf32");
 }
 
 extern "C" int zsg_pad_channels(const float* src, float* dst, int64_t n, int csrc, int cdst, zsg_stream_t stream) {

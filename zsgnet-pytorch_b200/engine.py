@@ -90,6 +90,14 @@ class Engine:
         self.fwd_train, self.fwd_eval_bn, self.fwd, self.bwd, self.prep_bwd = [], [], [], [], []
         self.inp = {}
         self.nbytes = 0
+        # TF32 hi/lo images of the weights (the kernels fetch them by TMA): the whole parameter arena is split by
+        # one launch per forward; transformed weights (padded / transposed-flipped) live in one pool that is split
+        # by one launch per forward (region F) and one per backward (region B)
+        self.arena_hi, self.arena_lo = self.buf(store.total), self.buf(store.total)
+        self.pool_n = 44 << 20
+        self.pool, self.pool_hi, self.pool_lo = self.buf(self.pool_n), self.buf(self.pool_n), self.buf(self.pool_n)
+        self._pool_used, self._pool_f_end = 0, None
+        self.prep_fwd = []
         self._build()
 
     # ------------------------------------------------------------------ allocation helpers
@@ -106,6 +114,17 @@ class Engine:
         self._f64_used += _align(n, 2)
         assert self._f64_used <= self._f64_pool.numel()
         return self._f64_pool[o:o + n]
+
+    def pool_alloc(self, n):
+        """(w, hi, lo) views of n floats from the transformed-weight pool."""
+        o = self._pool_used
+        self._pool_used += _align(n)
+        assert self._pool_used <= self.pool_n, "transformed-weight pool too small"
+        return self.pool[o:o + n], self.pool_hi[o:o + n], self.pool_lo[o:o + n]
+
+    def arena_split_views(self, wname):
+        o, n = self.store.offsets[wname], self.store.numel(wname)
+        return self.arena_hi[o:o + n], self.arena_lo[o:o + n]
 
     def rows(self, kind, *key):
         k = (kind,) + key
@@ -135,12 +154,17 @@ class Engine:
              out_relu=False, w=None):
         hout, wout = (hin + 2 * pad - k) // stride + 1, (win + 2 * pad - k) // stride + 1
         rows = self.rows("fwd", hin, win, cin, hout, wout, cout, stride, pad)
-        w = self.store.flat(wname) if w is None else w
-        op = ConvOp(x, w, y, rows, self.B * hout * wout, cin, cout, k, k, in_scale=pro.scale if pro else None,
-                    in_shift=pro.shift if pro else None, in_relu=in_relu, bias=bias, out_relu=out_relu, impl=self.impl)
+        if w is None:
+            w = self.store.flat(wname)
+            w_hi, w_lo = self.arena_split_views(wname)
+        else:
+            w, w_hi, w_lo = w                                # a (w, hi, lo) triple from the pool
+        op = ConvOp(x, w_hi, y, rows, self.B * hout * wout, cin, cout, k, k, in_scale=pro.scale if pro else None,
+                    in_shift=pro.shift if pro else None, in_relu=in_relu, bias=bias, out_relu=out_relu, impl=self.impl,
+                    w_lo=w_lo)
         self.fwd.append(("op", op))
         return dict(wname=wname, x=x, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
-                    hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w)
+                    hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w)   # w: fp32 weights (for dgrad prep)
 
     def conv_wgrad(self, L, dy, dw=None):
         dw = self.store.grad_flat(L["wname"]) if dw is None else dw
@@ -151,12 +175,13 @@ class Engine:
 
     def conv_dgrad(self, L, dy, dx, out_mask=None, residual=None, accumulate=False):
         k, cin, cout = L["k"], L["cin"], L["cout"]
-        wt = self.buf(cin * k * k * cout)
+        wt, wt_hi, wt_lo = self.pool_alloc(cin * k * k * cout)
         w = L["w"]
         self.prep_bwd.append(lambda: ops.weight_transpose_flip(w, wt, cout, k, k, cin))
         rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, L["stride"], L["pad"])
-        self.bwd.append(ConvOp(dy, wt, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=L["stride"],
-                               out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl))
+        self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=L["stride"],
+                               out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl,
+                               w_lo=wt_lo))
 
     def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None):
         def run():
@@ -176,13 +201,16 @@ class Engine:
 
         # ---------------- stem: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2 (mdl.py:149-152)
         img4 = self.buf(B, 300, 300, 4)
-        w1p, dw1p = self.buf(64 * 49 * 4), self.buf(64 * 49 * 4)
+        w1p_t = self.pool_alloc(64 * 49 * 4)
+        w1p, dw1p = w1p_t[0], self.buf(64 * 49 * 4)
         c1 = self.buf(B * 150 * 150, 64)
         x0 = self.buf(B * 75 * 75, 64)
         w1 = st.flat(e + "conv1.weight")
         self.fwd.append(("fn", lambda: ops.nchw_to_nhwc4(self.inp["img"], img4)))
-        self.fwd.append(("fn", lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, 4)))
-        Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p)
+        self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, 4))
+        w0p_t = self.pool_alloc(256 * 9 * spec.FUSED_CP)
+        self._pool_f_end = self._pool_used                    # region F (forward-time transformed weights) ends here
+        Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p_t)
         bn1 = self.add_bn(e + "bn1", 64, B * 150 * 150)
         self.bn_forward(bn1, c1)
         self.fwd.append(("fn", lambda: ops.maxpool_bn_relu_fwd(c1, bn1.scale, bn1.shift, x0, B, 150, 150, 64, 75, 75)))
@@ -330,7 +358,8 @@ class Engine:
         r11 = lambda rows_, cin_, cout_: geometry.conv_rows(rows_, 1, 1, cin_, 1, 1, cout_, 1, 0).to(dev)
         rows_ih, rows_hh = r11(B * T, E, G), r11(B * T, Hh, G)
         rows_ihr, rows_hhr = r11(B, E, G), r11(B, Hh, G)
-        self.fwd.append(("op", ConvOp(qv, P("weight_ih_l0"), gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl)))
+        wih_hi, wih_lo = self.arena_split_views("lstm.weight_ih_l0")
+        self.fwd.append(("op", ConvOp(qv, wih_hi, gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl, w_lo=wih_lo)))
         self.fwd.append(("fn", lambda: ops.weight_transpose_flip(P("weight_hh_l0"), whh_t, G, 1, 1, Hh)))
         self.fwd.append(("fn", lambda: ops.lstm_fwd_dir(gx, whh_t, P("bias_ih_l0"), P("bias_hh_l0"), h0c0[0], h0c0[1],
                                                         lens, B, T, gates, cs, hprev, lang)))
@@ -363,10 +392,10 @@ class Engine:
         out = self.buf(B, A, 5)
         dy5 = self.buf(M, 48)
         self.out = out
-        w0, w0p, dw0p = st.flat("att_reg_box.0.0.weight"), self.buf(256 * 9 * CP), self.buf(256 * 9 * CP)
+        w0, w0p, dw0p = st.flat("att_reg_box.0.0.weight"), w0p_t[0], self.buf(256 * 9 * CP)
         cells = list(spec.CELLS)
         self.fwd.append(("fn", lambda: ops.fuse_lang_grid(feat, lang, grid, fused, B, spec.TOTAL_CELLS, cells, 256, 256, CP)))
-        self.fwd.append(("fn", lambda: ops.pad_channels(w0, w0p, 256 * 9, spec.FUSED_C, CP)))
+        self.prep_fwd.append(lambda: ops.pad_channels(w0, w0p, 256 * 9, spec.FUSED_C, CP))
 
         def head_rows(kind, cin, cout, scatter=False):
             tabs, a_off = [], 0
@@ -389,20 +418,25 @@ class Engine:
         rows_f520, rows_f256 = head_rows("fwd", CP, 256), head_rows("fwd", 256, 256)
         rows_last, rows_f48 = head_rows("fwd", 256, 45, scatter=True), head_rows("fwd", 256, 48)
         rows_d520, rows_d256, rows_d48 = head_rows("dgrad", CP, 256), head_rows("dgrad", 256, 256), head_rows("dgrad", 256, 48)
-        self.fwd.append(("op", ConvOp(fused, w0p, hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
-                                      impl=self.impl)))
+        self.fwd.append(("op", ConvOp(fused, w0p_t[1], hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
+                                      impl=self.impl, w_lo=w0p_t[2])))
         for i in range(1, 5):
-            self.fwd.append(("op", ConvOp(hs[i - 1], st.flat(f"att_reg_box.{i}.0.weight"), hs[i], rows_f256, M, 256, 256,
-                                          3, 3, bias=hb(i), out_relu=True, impl=self.impl)))
+            wh, wl = self.arena_split_views(f"att_reg_box.{i}.0.weight")
+            self.fwd.append(("op", ConvOp(hs[i - 1], wh, hs[i], rows_f256, M, 256, 256, 3, 3, bias=hb(i), out_relu=True,
+                                          impl=self.impl, w_lo=wl)))
         w5 = st.flat("att_reg_box.5.weight")
-        self.fwd.append(("op", ConvOp(hs[4], w5, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
-                                      impl=self.impl)))
+        w5h, w5l = self.arena_split_views("att_reg_box.5.weight")
+        self.fwd.append(("op", ConvOp(hs[4], w5h, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
+                                      impl=self.impl, w_lo=w5l)))
         self.d_out = self.buf(B, A, 5)
         self.dbg = dict(x0=x0, c1=c1, c3=c3, c4=c4, c5=c5, feat=feat, lang=lang, hs=hs, fused=fused, lvl_off=lvl_off,
                         blocks=blocks)
-        wt5, wt5p = self.buf(256 * 9 * 45), self.buf(256 * 9 * 48)
-        wts = [self.buf(256 * 9 * 256) for _ in range(5)]
-        wt0 = self.buf(CP * 9 * 256)
+        wt5 = self.buf(256 * 9 * 45)
+        wt5p_t = self.pool_alloc(256 * 9 * 48)
+        wt5p = wt5p_t[0]
+        wts = [self.pool_alloc(256 * 9 * 256) for _ in range(5)]
+        wt0_t = self.pool_alloc(CP * 9 * 256)
+        wt0 = wt0_t[0]
         tmp48 = self.buf(48)
 
         def head_bwd():
@@ -414,16 +448,17 @@ class Engine:
             self.bwd.append(lambda: st.grad_flat("att_reg_box.5.bias").copy_(tmp48[:45]))
             self.bwd.append(WgradOp(hs[4], dy5, st.grad_flat("att_reg_box.5.weight"), rows_f48, M, 256, 45, 3, 3,
                                     impl=self.impl))
-            self.bwd.append(ConvOp(dy5, wt5p, dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl))
+            self.bwd.append(ConvOp(dy5, wt5p_t[1], dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl,
+                                   w_lo=wt5p_t[2]))
             for i in range(4, 0, -1):
-                wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i]
+                wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i][0]
                 self.prep_bwd.append(lambda wi=wi, wti=wti: ops.weight_transpose_flip(wi, wti, 256, 3, 3, 256))
                 gb = st.grad_flat(f"att_reg_box.{i}.0.bias")
                 self.bwd.append(lambda i=i, gb=gb: ops.colsum(dhs[i], gb, M, 256))
                 self.bwd.append(WgradOp(hs[i - 1], dhs[i], st.grad_flat(f"att_reg_box.{i}.0.weight"), rows_f256, M, 256,
                                         256, 3, 3, impl=self.impl))
-                self.bwd.append(ConvOp(dhs[i], wti, dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
-                                       impl=self.impl))
+                self.bwd.append(ConvOp(dhs[i], wts[i][1], dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
+                                       impl=self.impl, w_lo=wts[i][2]))
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
             gb0 = st.grad_flat("att_reg_box.0.0.bias")
             self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
@@ -431,7 +466,7 @@ class Engine:
             self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl))
             g0 = st.grad_flat("att_reg_box.0.0.weight")
             self.bwd.append(lambda: ops.pad_channels(dw0p, g0, 256 * 9, CP, spec.FUSED_C))
-            self.bwd.append(ConvOp(dhs[0], wt0, dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl))
+            self.bwd.append(ConvOp(dhs[0], wt0_t[1], dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0_t[2]))
             self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
         bwd_stages.append(head_bwd)
 
@@ -474,6 +509,11 @@ class Engine:
     def forward(self, training=True):
         if training:
             self._f64_pool[:self._f64_used].zero_()
+        for fn in self.prep_fwd:
+            fn()
+        ops.split_tf32(self.store.param_arena, self.arena_hi, self.arena_lo, self.store.total)
+        fe = self._pool_f_end
+        ops.split_tf32(self.pool, self.pool_hi, self.pool_lo, fe)
         for item in self.fwd:
             if item[0] == "op":
                 item[1]()
@@ -494,6 +534,8 @@ class Engine:
         self.store.grad_arena.zero_()
         for fn in self.prep_bwd:
             fn()
+        fe, pu = self._pool_f_end, self._pool_used
+        ops.split_tf32(self.pool[fe:pu], self.pool_hi[fe:pu], self.pool_lo[fe:pu], pu - fe)
         marks = {m[0]: m for m in self.bucket_marks}
         for i, op in enumerate(self.bwd, start=1):
             op()

@@ -44,9 +44,9 @@ class ConvOp:
     fixed because the engine's buffers are static)."""
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
-                 bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC):
-        self.keep = (x, w, y, rows, in_scale, in_shift, bias, out_mask, residual)
-        self.p = ConvParams(ptr(x), ptr(w), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
+                 bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None):
+        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual)
+        self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
                             impl)
         self.ref = C.byref(self.p)
@@ -78,6 +78,10 @@ class WgradOp:
 
 def weight_transpose_flip(w, wt, cout, r, s, cin):
     call("zsg_weight_transpose_flip", ptr(w), ptr(wt), cout, r, s, cin, stream())
+
+
+def split_tf32(w, hi, lo, n):
+    call("zsg_split_tf32", ptr(w), ptr(hi), ptr(lo), n, stream())
 
 
 def pad_channels(src, dst, n, csrc, cdst):
