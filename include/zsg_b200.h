@@ -135,12 +135,13 @@ int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const f
                      zsg_stream_t stream);
 
 /* ------------------------------ pooling / resampling glue -------------------------------- */
-/* stem: y = maxpool3x3/2,p1( relu(x*scale+shift) )  (mdl.py:150-152). */
-int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const float* shift, float* y, int b, int h, int w,
-                            int c, int ho, int wo, zsg_stream_t stream);
-/* dx (w.r.t. the raw conv output is NOT taken here): da = grad w.r.t. relu(bn(x)) */
-int zsg_maxpool_bn_relu_bwd(const float* x, const float* scale, const float* shift, const float* dy, float* da,
-                            int b, int h, int w, int c, int ho, int wo, zsg_stream_t stream);
+/* stem: y = maxpool3x3/2,p1( relu(x*scale+shift) )  (mdl.py:150-152).  argmax (optional, same shape as y, one
+ * byte per element) records the winning tap dy*3+dx (first maximum in scan order, as ATen does). */
+int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const float* shift, float* y, uint8_t* argmax, int b,
+                            int h, int w, int c, int ho, int wo, zsg_stream_t stream);
+/* da = gradient w.r.t. relu(bn(x)) (the max-pool input), gathered through the recorded argmax codes. */
+int zsg_maxpool_bn_relu_bwd(const uint8_t* argmax, const float* dy, float* da, int b, int h, int w, int c, int ho,
+                            int wo, zsg_stream_t stream);
 /* dst += nearest_up(src) with host-computed index tables (fpn_resnet.py:161-162,166-167). */
 int zsg_upsample_add(float* dst, const float* src, const int32_t* idx_y, const int32_t* idx_x, int b, int ho,
                      int wo, int hi, int wi, int c, zsg_stream_t stream);

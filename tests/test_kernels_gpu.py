@@ -418,9 +418,10 @@ def test_maxpool_upsample_avgpool(zsg, golden_meta):
     Ho, Wo = y_ref.shape[2:]
     y = torch.empty(B, Ho, Wo, C, device="cuda")
     xn = nhwc(x.detach())
-    ops.maxpool_bn_relu_fwd(xn, sc, sh, y, B, H, W, C, Ho, Wo)
+    arg = torch.empty(B, Ho, Wo, C, dtype=torch.uint8, device="cuda")
+    ops.maxpool_bn_relu_fwd(xn, sc, sh, y, arg, B, H, W, C, Ho, Wo)
     da = torch.empty(B, H, W, C, device="cuda")
-    ops.maxpool_bn_relu_bwd(xn, sc, sh, nhwc(dy), da, B, H, W, C, Ho, Wo)
+    ops.maxpool_bn_relu_bwd(arg, nhwc(dy), da, B, H, W, C, Ho, Wo)
     torch.cuda.synchronize()
     assert rel_err(y, nhwc(y_ref)) < 1e-6          # fmaf vs mul+add in the affine: not bit-equal
     assert rel_err(da, nhwc(a.grad)) < 1e-6

@@ -176,8 +176,10 @@ struct Smem {
   static constexpr int STAGES = BN >= 128 ? 3 : 4;
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
   static constexpr int ROWS_OFF = TILES_BYTES;              // TM row entries (fwd) / 2 groups x 2 x 32 (wgrad)
-  static constexpr int BAR_OFF = ROWS_OFF + TM * 16;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;        // + alignment slack
+  static constexpr int BAR_OFF = ROWS_OFF + NGROUP * TM * 16;
+  static constexpr int EPI_OFF = BAR_OFF + 256;             // epilogue staging: 8 warps x 32 rows x 20 floats
+  static constexpr int EPI_WARP_BYTES = 32 * 20 * 4;
+  static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_BYTES + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
 };
 
@@ -220,8 +222,8 @@ __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int la
 // bits [5,7) ^= bits [7,9)).  Tile = [channel atom][pixel group of 4][4][128 B]: LBO = 4096 B between channel atoms, SBO = 512 B
 // between pixel groups; one MMA (K = 8) consumes two pixel groups (1024 B).
 template <int BN, bool MN_MAJOR = false>
-__device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb,
-                                         bool swap_lbo_sbo = false) {
+__device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb, int& gkb,
+                                         int& gchunk, bool swap_lbo_sbo = false) {
   using S = Smem<BN>;
   constexpr uint32_t idesc = umma_idesc_tf32(BN, MN_MAJOR);
   const uint32_t tiles0 = smem_u32(sm);
@@ -229,16 +231,18 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
   const uint64_t sbo = MN_MAJOR ? (swap_lbo_sbo ? 256ull : 32ull) : 64ull;
   const uint64_t desc_hi = (lbo << 16) | (sbo << 32) | (1ull << 46) | ((MN_MAJOR ? 1ull : 2ull) << 61);
   constexpr uint32_t kstep = MN_MAJOR ? 64u : 2u;          // descriptor start-address advance per MMA (16 B units)
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % S::STAGES;
-    const int chunk = kb / CHUNK_KB;
+  // gkb / gchunk count K blocks / chunks over ALL tiles of this CTA: they index the smem ring and the two TMEM
+  // accumulators and give the mbarrier phases; a chunk never spans two tiles.
+  for (int kb = 0; kb < nkb; ++kb, ++gkb) {
+    const int s = gkb % S::STAGES;
+    const int chunk = gchunk;
     const bool first = (kb % CHUNK_KB) == 0;
     const uint32_t tmem_d = tmem_base + (uint32_t)(chunk & 1) * BN;
     if (first) {                                          // the drain warps must have emptied this accumulator
       mbar_wait(pb.acc_empty(chunk & 1), ((chunk >> 1) & 1) ^ 1);
       tc_fence_after();
     }
-    mbar_wait(pb.full(s), (kb / S::STAGES) & 1);
+    mbar_wait(pb.full(s), (gkb / S::STAGES) & 1);
     tc_fence_after();
     const uint32_t a_hi = (tiles0 + s * S::STAGE_BYTES) >> 4;
     const uint32_t a_lo = a_hi + (A_TILE_BYTES >> 4);
@@ -257,17 +261,19 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
       if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(pb.acc_full(chunk & 1));
     }
     __syncwarp();
+    if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) ++gchunk;
   }
 }
 
 // drain warps: promote every finished TMEM chunk into fp32 registers (round-to-nearest adds)
 template <int BN>
 __device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_base, int nkb, int quadrant, int half,
-                                           float (&acc)[BN / 2]) {
+                                           float (&acc)[BN / 2], int& gchunk) {
 #pragma unroll
   for (int i = 0; i < BN / 2; ++i) acc[i] = 0.f;
   const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int cc = 0; cc < nchunks; ++cc, ++gchunk) {
+    const int c = gchunk;
     mbar_wait(pb.acc_full(c & 1), (c >> 1) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(c & 1) * BN + half * (BN / 2);
@@ -290,26 +296,25 @@ template <int BN, bool TMA_W>
 __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_params p,
                                                                const __grid_constant__ CUtensorMap tm_hi,
                                                                const __grid_constant__ CUtensorMap tm_lo) {
+  // Persistent: one CTA per SM walks the output tiles (n fastest, so the CTAs that share im2col rows run at the
+  // same time and hit L2).  TMEM and the mbarriers are set up once; the smem ring, the two TMEM accumulators and
+  // all barrier phases run on counters that continue across tiles, so the epilogue of tile i overlaps the gathers
+  // and MMAs of tile i+1.
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * TM;
   const int K = p.r * p.s * p.cin;
   const int nkb = (K + KB - 1) / KB;
+  const int tiles_n = (p.cout + BN - 1) / BN;
+  const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
 
-  int4* rows_s = reinterpret_cast<int4*>(sm + S::ROWS_OFF);
-  if (tid < TM) {
-    int4 e = make_int4(0, 0, 0, 0);                       // hin = win = 0 => every tap out of bounds
-    if (m0 + tid < p.m) e = __ldg(reinterpret_cast<const int4*>(p.rows) + m0 + tid);
-    rows_s[tid] = e;
-  }
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane, TMA_W ? NPROD + 1 : NPROD);   // contains __syncthreads
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 96);
 
   if (warp == MMA_WARP) {
-    mma_loop<BN>(sm, pb, tmem_base, nkb);
+    int gkb = 0, gchunk = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) mma_loop<BN>(sm, pb, tmem_base, nkb, gkb, gchunk);
   } else if (warp < DRAIN_WARP0) {
     // ------------------------------ producers ------------------------------
     // Thread (rsub, chunk) owns the 16-byte chunk `chunk` of rows rsub, rsub+16, ... of every K block of its
@@ -320,125 +325,174 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
     const int chunk = t & 7;
     const int rsub = t >> 3;
     const int soff = rsub * 128 + ((chunk ^ (rsub & 7)) << 4);      // + it * 2048 (16 rows x 128 B)
-    int c = chunk * 4 + group * KB, tap = 0, tr = 0, ts = 0;
-    while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
     const int ntap = p.r * p.s;
-    int cached_tap = -1;
-    int off[8];                                                     // element offset of the tap's pixel, -1 = padding
-    for (int kb = group; kb < nkb; kb += NGROUP) {
-      const int s = kb % S::STAGES;
-      const bool kvalid = tap < ntap;
-      if (tap != cached_tap) {
-        cached_tap = tap;
+    int4* rows_g = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * TM;      // this group's copy of the row table
+    int gkb0 = 0;                                                   // global index of the tile's first K block
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, gkb0 += nkb) {
+      const int n0 = (tile % tiles_n) * BN;
+      const int m0 = (tile / tiles_n) * TM;
+      {
+        int4 e = make_int4(0, 0, 0, 0);                   // hin = win = 0 => every tap out of bounds
+        if (m0 + t < p.m) e = __ldg(reinterpret_cast<const int4*>(p.rows) + m0 + t);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");   // previous tile's reads are done
+        rows_g[t] = e;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      }
+      const int kb_first = (group - gkb0) & 1;            // K blocks with (gkb0 + kb) % NGROUP == group
+      int c = chunk * 4 + kb_first * KB, tap = 0, tr = 0, ts = 0;
+      while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
+      int cached_tap = -1;
+      int off[8];                                         // element offset of the tap's pixel, -1 = padding
+      for (int kb = kb_first; kb < nkb; kb += NGROUP) {
+        const int gk = gkb0 + kb;
+        const int s = gk % S::STAGES;
+        const bool kvalid = tap < ntap;
+        if (tap != cached_tap) {
+          cached_tap = tap;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int4 e = rows_g[it * 16 + rsub];
+            int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+            const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+            bool ok = kvalid;
+            if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
+            ok = ok && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+            off[it] = ok ? e.x + (yy * win + xx) * p.cin : -1;
+          }
+        }
+        // issue the gather loads before waiting for the stage: they only need registers
+        // (p.impl >= 2 are timing ablations used by tools/ablate_conv.py: 2 = no gather loads, 3 = also no smem
+        //  stores, 4 = also no proxy fence, 5 = everything but the proxy fence; results are garbage then)
+        float4 va[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int4 e = rows_s[it * 16 + rsub];
-          int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
-          const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-          bool ok = kvalid;
-          if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
-          ok = ok && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
-          off[it] = ok ? e.x + (yy * win + xx) * p.cin : -1;
+          va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (off[it] >= 0 && (p.impl < 2 || p.impl == 5))
+            va[it] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)off[it] + c));
         }
-      }
-      // issue the gather loads before waiting for the stage: they only need registers
-      // (p.impl >= 2 are timing ablations used by tools/ablate_conv.py: 2 = no gather loads, 3 = also no smem
-      //  stores, 4 = also no proxy fence, 5 = everything but the proxy fence; results are garbage then)
-      float4 va[8];
+        float4 vb[TMA_W ? 1 : BN / 16];
+        if (!TMA_W) {
+          const int kk = kb * KB + chunk * 4;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (off[it] >= 0 && (p.impl < 2 || p.impl == 5))
-          va[it] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)off[it] + c));
-      }
-      float4 vb[TMA_W ? 1 : BN / 16];
-      if (!TMA_W) {
-        const int kk = kb * KB + chunk * 4;
-#pragma unroll
-        for (int it = 0; it < BN / 16; ++it) {
-          const int n = n0 + it * 16 + rsub;
-          vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kvalid && n < p.cout) vb[it] = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)n * K + kk));
-        }
-      }
-      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.in_scale && kvalid) {
-        sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + c));
-        sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + c));
-      }
-      mbar_wait(pb.empty(s), ((kb / S::STAGES) & 1) ^ 1);
-      uint8_t* a_hi = sm + s * S::STAGE_BYTES;
-      uint8_t* a_lo = a_hi + A_TILE_BYTES;
-      uint8_t* b_hi = a_lo + A_TILE_BYTES;
-      uint8_t* b_lo = b_hi + S::B_TILE_BYTES;
-      if (TMA_W && t == 0 && p.impl != 6) {                         // weights: two TMA tiles, no register pass
-        mbar_arrive_expect_tx(pb.full(s), 2 * S::B_TILE_BYTES);
-        tma_load_2d(smem_u32(b_hi), &tm_hi, kb * KB, n0, pb.full(s));
-        tma_load_2d(smem_u32(b_lo), &tm_lo, kb * KB, n0, pb.full(s));
-      }
-      if (TMA_W && t == 0 && p.impl == 6) mbar_arrive(pb.full(s));   // ablation 6: no weight TMA
-      if (p.impl != 3 && p.impl != 4)
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        float4 v = va[it];
-        if (off[it] >= 0) {
-          if (p.in_scale) {
-            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-            v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+          for (int it = 0; it < BN / 16; ++it) {
+            const int n = n0 + it * 16 + rsub;
+            vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kvalid && n < p.cout) vb[it] = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)n * K + kk));
           }
-          if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         }
-        float4 h, l;
-        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-        *reinterpret_cast<float4*>(a_hi + soff + it * 2048) = h;
-        *reinterpret_cast<float4*>(a_lo + soff + it * 2048) = l;
-      }
-      if (!TMA_W) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.in_scale && kvalid) {
+          sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + c));
+          sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + c));
+        }
+        mbar_wait(pb.empty(s), ((gk / S::STAGES) & 1) ^ 1);
+        uint8_t* a_hi = sm + s * S::STAGE_BYTES;
+        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+        uint8_t* b_hi = a_lo + A_TILE_BYTES;
+        uint8_t* b_lo = b_hi + S::B_TILE_BYTES;
+        if (TMA_W && t == 0 && p.impl != 6) {             // weights: two TMA tiles, no register pass
+          mbar_arrive_expect_tx(pb.full(s), 2 * S::B_TILE_BYTES);
+          tma_load_2d(smem_u32(b_hi), &tm_hi, kb * KB, n0, pb.full(s));
+          tma_load_2d(smem_u32(b_lo), &tm_lo, kb * KB, n0, pb.full(s));
+        }
+        if (TMA_W && t == 0 && p.impl == 6) mbar_arrive(pb.full(s));   // ablation 6: no weight TMA
+        if (p.impl != 3 && p.impl != 4)
 #pragma unroll
-        for (int it = 0; it < BN / 16; ++it) store_split(b_hi, b_lo, it * 16 + rsub, chunk, vb[it]);
+        for (int it = 0; it < 8; ++it) {
+          float4 v = va[it];
+          if (off[it] >= 0) {
+            if (p.in_scale) {
+              v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+              v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+            }
+            if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          }
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+          *reinterpret_cast<float4*>(a_hi + soff + it * 2048) = h;
+          *reinterpret_cast<float4*>(a_lo + soff + it * 2048) = l;
+        }
+        if (!TMA_W) {
+#pragma unroll
+          for (int it = 0; it < BN / 16; ++it) store_split(b_hi, b_lo, it * 16 + rsub, chunk, vb[it]);
+        }
+        if (p.impl != 4 && p.impl != 5) fence_proxy_async();
+        mbar_arrive(pb.full(s));
+        // advance this thread's (tap, channel) by NGROUP K blocks
+        c += NGROUP * KB;
+        while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
       }
-      if (p.impl != 4 && p.impl != 5) fence_proxy_async();
-      mbar_arrive(pb.full(s));
-      // advance this thread's (tap, channel) by NGROUP K blocks
-      c += NGROUP * KB;
-      while (c >= p.cin) { c -= p.cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
     }
   } else {
     // ------------------------------ drain + epilogue ------------------------------
     const int dw = warp - DRAIN_WARP0;
     const int quadrant = dw & 3, half = dw >> 2;
-    float acc[BN / 2];
-    drain_loop<BN>(pb, tmem_base, nkb, quadrant, half, acc);
     const int row = quadrant * 32 + lane;
-    if (m0 + row < p.m) {
-      const int4 e = rows_s[row];
-      float* yrow = p.y + (int64_t)e.w;
-      const float* rrow = p.residual ? p.residual + (int64_t)e.w : nullptr;
-      const float* mrow = p.out_mask ? p.out_mask + (int64_t)e.w : nullptr;
-      const bool vec_ok = ((p.cout & 3) == 0) && ((e.w & 3) == 0);
-      const int nb = n0 + half * (BN / 2);
+    int gchunk = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % tiles_n) * BN;
+      const int m0 = (tile / tiles_n) * TM;
+      int out_off = 0;
+      const bool row_ok = m0 + row < p.m;
+      if (row_ok) out_off = __ldg(&p.rows[m0 + row].out);          // prefetched under the drain
+      float acc[BN / 2];
+      drain_loop<BN>(pb, tmem_base, nkb, quadrant, half, acc, gchunk);
+      // Epilogue through a per-warp smem slab: a thread owns one row of the accumulator, but global memory wants
+      // lanes along channels.  16 columns at a time are transposed through smem (row stride 20 floats keeps the
+      // 128-bit accesses conflict-free); then 4 lanes cover one row's 64 B and a warp instruction touches 8 rows
+      // with full 32-byte sectors, for the store and for the residual / mask / accumulate reads alike.
+      float* stg = reinterpret_cast<float*>(sm + S::EPI_OFF + dw * S::EPI_WARP_BYTES);
+      const int rsel = lane >> 2, c4 = (lane & 3) * 4;
 #pragma unroll
-      for (int j = 0; j < BN / 2; j += 4) {
-        const int n = nb + j;
-        if (n < p.cout) {
-          float v[4];
+      for (int slab = 0; slab < BN / 32; ++slab) {
+        __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            v[q] = acc[j + q];
-            if (n + q < p.cout) {
-              if (p.bias) v[q] += __ldg(p.bias + n + q);
-              if (mrow && !(mrow[n + q] > 0.f)) v[q] = 0.f;
-              if (rrow) v[q] += rrow[n + q];
-              if (p.accumulate) v[q] += yrow[n + q];
-              if (p.out_relu) v[q] = fmaxf(v[q], 0.f);
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * 20 + j) =
+              make_float4(acc[slab * 16 + j], acc[slab * 16 + j + 1], acc[slab * 16 + j + 2], acc[slab * 16 + j + 3]);
+        __syncwarp();
+        const int n = n0 + half * (BN / 2) + slab * 16 + c4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && n < p.cout) {
+          if (n + 3 < p.cout) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          else { bias4.x = __ldg(p.bias + n); if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1); if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2); }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + rsel;
+          const int off_r = __shfl_sync(0xffffffffu, out_off, r);
+          const bool ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r) != 0;
+          if (!ok_r || n >= p.cout) continue;
+          float4 v4 = *reinterpret_cast<const float4*>(stg + r * 20 + c4);
+          float v[4] = {v4.x + bias4.x, v4.y + bias4.y, v4.z + bias4.z, v4.w + bias4.w};
+          float* yrow = p.y + (int64_t)off_r + n;
+          const bool vec = ((p.cout & 3) == 0) && ((off_r & 3) == 0) && (n + 3 < p.cout);
+          if (vec) {
+            if (p.out_mask) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(p.out_mask + (int64_t)off_r + n));
+              if (!(m.x > 0.f)) v[0] = 0.f; if (!(m.y > 0.f)) v[1] = 0.f; if (!(m.z > 0.f)) v[2] = 0.f; if (!(m.w > 0.f)) v[3] = 0.f;
             }
-          }
-          if (vec_ok && n + 3 < p.cout) {
-            *reinterpret_cast<float4*>(yrow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.residual) {
+              const float4 q = *reinterpret_cast<const float4*>(p.residual + (int64_t)off_r + n);
+              v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+            }
+            if (p.accumulate) {
+              const float4 q = *reinterpret_cast<const float4*>(yrow);
+              v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+            }
+            if (p.out_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+            *reinterpret_cast<float4*>(yrow) = make_float4(v[0], v[1], v[2], v[3]);
           } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (n + q < p.cout) yrow[n + q] = v[q];
+            for (int q = 0; q < 4; ++q) {
+              if (n + q >= p.cout) break;
+              float u = v[q];
+              if (p.out_mask && !(p.out_mask[(int64_t)off_r + n + q] > 0.f)) u = 0.f;
+              if (p.residual) u += p.residual[(int64_t)off_r + n + q];
+              if (p.accumulate) u += yrow[q];
+              if (p.out_relu) u = fmaxf(u, 0.f);
+              yrow[q] = u;
+            }
           }
         }
       }
@@ -473,7 +527,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 96);
 
   if (warp == MMA_WARP) {
-    mma_loop<BN, true>(sm, pb, tmem_base, nkb, p.impl == 7);
+    int gkb = 0, gchunk = 0;
+    mma_loop<BN, true>(sm, pb, tmem_base, nkb, gkb, gchunk, p.impl == 7);
   } else if (warp < DRAIN_WARP0) {
     const int group = warp >> 2;
     const int t = tid & 127;
@@ -572,7 +627,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
     const int dw = warp - DRAIN_WARP0;
     const int quadrant = dw & 3, half = dw >> 2;
     float acc[BN / 2];
-    drain_loop<BN>(pb, tmem_base, nkb, quadrant, half, acc);
+    int gchunk = 0;
+    drain_loop<BN>(pb, tmem_base, nkb, quadrant, half, acc, gchunk);
     const int j = j0 + quadrant * 32 + lane;
     if (j < Kt) {
 #pragma unroll
@@ -692,7 +748,8 @@ static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
     if (int rc = make_weight_map(&tm_hi, p.w, p.cout, K, BN)) return rc;
     if (int rc = make_weight_map(&tm_lo, p.w_lo, p.cout, K, BN)) return rc;
   }
-  dim3 grid((p.cout + BN - 1) / BN, (p.m + TM - 1) / TM);
+  const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
   conv_tc_kernel<BN, TMA_W><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
   return check_launch("zsg_conv_fwd");
 }

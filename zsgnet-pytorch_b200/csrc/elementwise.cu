@@ -48,35 +48,48 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
   }
   const int64_t stride = (int64_t)gridDim.x * rpb;
   int64_t r = (int64_t)blockIdx.x * rpb + lane_r;
+  constexpr int U = 4;                                   // rows in flight per thread (memory-level parallelism)
   while (r < rows) {
+    float4 v[U], g[U], a[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * stride;
+      ok[u] = rr < rows;
+      const size_t off = (size_t)(ok[u] ? rr : r) * C + c;
+      v[u] = ld4(x + off);
+      if (MODE == 1) {
+        g[u] = ld4(dy + off);
+        if (mask_mode == 2) a[u] = ld4(act_out + off);
+      }
+    }
     float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
-#pragma unroll 4
-    for (int it = 0; it < 8 && r < rows; ++it, r += stride) {
-      const size_t off = (size_t)r * C + c;
-      float4 v = ld4(x + off);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
       if (MODE == 0) {
-        f1[0] += v.x; f1[1] += v.y; f1[2] += v.z; f1[3] += v.w;
-        f2[0] = fmaf(v.x, v.x, f2[0]); f2[1] = fmaf(v.y, v.y, f2[1]);
-        f2[2] = fmaf(v.z, v.z, f2[2]); f2[3] = fmaf(v.w, v.w, f2[3]);
+        f1[0] += v[u].x; f1[1] += v[u].y; f1[2] += v[u].z; f1[3] += v[u].w;
+        f2[0] = fmaf(v[u].x, v[u].x, f2[0]); f2[1] = fmaf(v[u].y, v[u].y, f2[1]);
+        f2[2] = fmaf(v[u].z, v[u].z, f2[2]); f2[3] = fmaf(v[u].w, v[u].w, f2[3]);
       } else {
-        float4 g = ld4(dy + off);
+        float4 gg = g[u];
         if (mask_mode == 1) {
-          float4 a = fma4(v, sc, sh);
-          g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f;
-          g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+          const float4 t = fma4(v[u], sc, sh);
+          gg.x = t.x > 0.f ? gg.x : 0.f; gg.y = t.y > 0.f ? gg.y : 0.f;
+          gg.z = t.z > 0.f ? gg.z : 0.f; gg.w = t.w > 0.f ? gg.w : 0.f;
         } else if (mask_mode == 2) {
-          float4 a = ld4(act_out + off);
-          g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f;
-          g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
-          if (dz_out) st4(dz_out + off, g);
+          gg.x = a[u].x > 0.f ? gg.x : 0.f; gg.y = a[u].y > 0.f ? gg.y : 0.f;
+          gg.z = a[u].z > 0.f ? gg.z : 0.f; gg.w = a[u].w > 0.f ? gg.w : 0.f;
+          if (dz_out) st4(dz_out + (size_t)(r + u * stride) * C + c, gg);
         }
-        f1[0] += g.x; f1[1] += g.y; f1[2] += g.z; f1[3] += g.w;
-        f2[0] = fmaf(g.x, (v.x - mu.x) * is.x, f2[0]); f2[1] = fmaf(g.y, (v.y - mu.y) * is.y, f2[1]);
-        f2[2] = fmaf(g.z, (v.z - mu.z) * is.z, f2[2]); f2[3] = fmaf(g.w, (v.w - mu.w) * is.w, f2[3]);
+        f1[0] += gg.x; f1[1] += gg.y; f1[2] += gg.z; f1[3] += gg.w;
+        f2[0] = fmaf(gg.x, (v[u].x - mu.x) * is.x, f2[0]); f2[1] = fmaf(gg.y, (v[u].y - mu.y) * is.y, f2[1]);
+        f2[2] = fmaf(gg.z, (v[u].z - mu.z) * is.z, f2[2]); f2[3] = fmaf(gg.w, (v[u].w - mu.w) * is.w, f2[3]);
       }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { a1[k] += (double)f1[k]; a2[k] += (double)f2[k]; }
+    r += U * stride;
   }
   __shared__ double sm[2][256][4];
 #pragma unroll
@@ -103,7 +116,7 @@ static int launch_channel_reduce(int mode, const float* x, const float* dy, cons
   ZSG_REQUIRE((cols & (cols - 1)) == 0 && c4 % cols == 0, "channel reduce: C/4=%d must be a power of two", c4);
   int rpb = 256 / cols;
   int gy = c4 / cols;
-  int64_t want = (rows + (int64_t)rpb * 16 - 1) / ((int64_t)rpb * 16);
+  int64_t want = (rows + (int64_t)rpb * 8 - 1) / ((int64_t)rpb * 8);
   int64_t cap = (int64_t)num_sms() * 8 / gy;
   int gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   dim3 grid(gx, gy);
@@ -208,9 +221,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 }
 
 // ------------------------------------- stem max-pool ----------------------------------------
+// forward also records, per output element, which tap of the 3x3 window won (first maximum in row-major scan
+// order over the valid taps, like ATen's max_pool2d): code = dy*3 + dx.  Backward is then a pure gather.
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, float* __restrict__ y,
-                                                          int B, int H, int W, int C, int Ho, int Wo) {
+                                                          uint8_t* __restrict__ argmax, int B, int H, int W, int C,
+                                                          int Ho, int Wo) {
   const int c4 = C / 4;
   const int64_t n = (int64_t)B * Ho * Wo * c4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -221,57 +237,54 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
     const int b = (int)(t / Ho);
     const float4 sc = ld4(scale + c), sh = ld4(shift + c);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    uchar4 code = make_uchar4(0, 0, 0, 0);
     for (int dy = 0; dy < 3; ++dy) {
       const int yy = 2 * p - 1 + dy;
       if (yy < 0 || yy >= H) continue;
       for (int dx = 0; dx < 3; ++dx) {
         const int xx = 2 * q - 1 + dx;
         if (xx < 0 || xx >= W) continue;
-        float4 v = relu4(fma4(ld4(x + (((size_t)b * H + yy) * W + xx) * C + c), sc, sh));
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        const float4 v = relu4(fma4(ld4(x + (((size_t)b * H + yy) * W + xx) * C + c), sc, sh));
+        const unsigned char k = (unsigned char)(dy * 3 + dx);
+        if (v.x > m.x) { m.x = v.x; code.x = k; }
+        if (v.y > m.y) { m.y = v.y; code.y = k; }
+        if (v.z > m.z) { m.z = v.z; code.z = k; }
+        if (v.w > m.w) { m.w = v.w; code.w = k; }
       }
     }
     st4(y + i * 4, m);
+    if (argmax) *reinterpret_cast<uchar4*>(argmax + i * 4) = code;
   }
 }
 
-// gather form (deterministic, no atomics): an input pixel receives dy of every window whose FIRST
-// maximum (row-major scan over valid taps, like ATen's max_pool2d) is that pixel.
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift,
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restrict__ argmax,
                                                           const float* __restrict__ dy, float* __restrict__ da, int B,
                                                           int H, int W, int C, int Ho, int Wo) {
-  const int64_t n = (int64_t)B * H * W * C;
+  const int c4 = C / 4;
+  const int64_t n = (int64_t)B * H * W * c4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    int64_t t = i / C;
+    const int c = (int)(i % c4) * 4;
+    int64_t t = i / c4;
     const int xx = (int)(t % W); t /= W;
     const int yy = (int)(t % H);
     const int b = (int)(t / H);
-    const float sc = scale[c], sh = shift[c];
-    float acc = 0.f;
-    const int p0 = yy / 2, p1 = (yy + 1) / 2;     // windows p with 2p-1 <= yy <= 2p+1
-    const int q0 = xx / 2, q1 = (xx + 1) / 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int p0 = yy / 2, p1 = (yy + 1) / 2, q0 = xx / 2, q1 = (xx + 1) / 2;     // windows containing (yy, xx)
     for (int p = p0; p <= p1; ++p) {
       if (p >= Ho) continue;
       for (int q = q0; q <= q1; ++q) {
         if (q >= Wo) continue;
-        float best = -INFINITY;
-        int by = -1, bx = -1;
-        for (int dyy = 0; dyy < 3; ++dyy) {
-          const int y2 = 2 * p - 1 + dyy;
-          if (y2 < 0 || y2 >= H) continue;
-          for (int dxx = 0; dxx < 3; ++dxx) {
-            const int x2 = 2 * q - 1 + dxx;
-            if (x2 < 0 || x2 >= W) continue;
-            const float v = fmaxf(fmaf(x[(((size_t)b * H + y2) * W + x2) * C + c], sc, sh), 0.f);
-            if (v > best) { best = v; by = y2; bx = x2; }
-          }
-        }
-        if (by == yy && bx == xx) acc += dy[(((size_t)b * Ho + p) * Wo + q) * C + c];
+        const unsigned char k = (unsigned char)((yy - (2 * p - 1)) * 3 + (xx - (2 * q - 1)));
+        const size_t o = (((size_t)b * Ho + p) * Wo + q) * C + c;
+        const uchar4 code = *reinterpret_cast<const uchar4*>(argmax + o);
+        const float4 g = ld4(dy + o);
+        if (code.x == k) acc.x += g.x;
+        if (code.y == k) acc.y += g.y;
+        if (code.z == k) acc.z += g.z;
+        if (code.w == k) acc.w += g.w;
       }
     }
-    da[i] = acc;
+    st4(da + i * 4, acc);
   }
 }
 
@@ -577,19 +590,20 @@ extern "C" int zsg_bn_bwd_apply(const float* dy, const float* x, const float* me
   return check_launch("zsg_bn_bwd_apply");
 }
 
-extern "C" int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const float* shift, float* y, int b, int h,
-                                       int w, int c, int ho, int wo, zsg_stream_t stream) {
+extern "C" int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const float* shift, float* y,
+                                       uint8_t* argmax, int b, int h, int w, int c, int ho, int wo,
+                                       zsg_stream_t stream) {
   ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_maxpool_bn_relu_fwd: bad arguments");
-  maxpool_fwd_kernel<<<grid_for((int64_t)b * ho * wo * (c / 4), 256), 256, 0, as_stream(stream)>>>(x, scale, shift, y,
-                                                                                                    b, h, w, c, ho, wo);
+  maxpool_fwd_kernel<<<grid_for((int64_t)b * ho * wo * (c / 4), 256), 256, 0, as_stream(stream)>>>(
+      x, scale, shift, y, argmax, b, h, w, c, ho, wo);
   return check_launch("zsg_maxpool_bn_relu_fwd");
 }
 
-extern "C" int zsg_maxpool_bn_relu_bwd(const float* x, const float* scale, const float* shift, const float* dy,
-                                       float* da, int b, int h, int w, int c, int ho, int wo, zsg_stream_t stream) {
-  ZSG_REQUIRE(x && scale && shift && dy && da, "zsg_maxpool_bn_relu_bwd: null pointer");
-  maxpool_bwd_kernel<<<grid_for((int64_t)b * h * w * c, 256, 16), 256, 0, as_stream(stream)>>>(x, scale, shift, dy, da,
-                                                                                                b, h, w, c, ho, wo);
+extern "C" int zsg_maxpool_bn_relu_bwd(const uint8_t* argmax, const float* dy, float* da, int b, int h, int w, int c,
+                                       int ho, int wo, zsg_stream_t stream) {
+  ZSG_REQUIRE(argmax && dy && da && c % 4 == 0, "zsg_maxpool_bn_relu_bwd: bad arguments");
+  maxpool_bwd_kernel<<<grid_for((int64_t)b * h * w * (c / 4), 256, 16), 256, 0, as_stream(stream)>>>(argmax, dy, da, b,
+                                                                                                      h, w, c, ho, wo);
   return check_launch("zsg_maxpool_bn_relu_bwd");
 }
 

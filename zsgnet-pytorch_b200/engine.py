@@ -213,14 +213,15 @@ class Engine:
         Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p_t)
         bn1 = self.add_bn(e + "bn1", 64, B * 150 * 150)
         self.bn_forward(bn1, c1)
-        self.fwd.append(("fn", lambda: ops.maxpool_bn_relu_fwd(c1, bn1.scale, bn1.shift, x0, B, 150, 150, 64, 75, 75)))
+        pool_arg = torch.empty(B * 75 * 75 * 64, dtype=torch.uint8, device=dev)
+        self.fwd.append(("fn", lambda: ops.maxpool_bn_relu_fwd(c1, bn1.scale, bn1.shift, x0, pool_arg, B, 150, 150, 64, 75,
+                                                               75)))
         g_x0 = self.buf(B * 75 * 75, 64)
         da_stem = self.buf(B * 150 * 150, 64)
         g1 = st.grad_flat(e + "conv1.weight")
 
         def stem_bwd():
-            self.bwd.append(lambda: ops.maxpool_bn_relu_bwd(c1, bn1.scale, bn1.shift, g_x0, da_stem, B, 150, 150, 64,
-                                                            75, 75))
+            self.bwd.append(lambda: ops.maxpool_bn_relu_bwd(pool_arg, g_x0, da_stem, B, 150, 150, 64, 75, 75))
             self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1)
             self.bwd.append(lambda: dw1p.zero_())
             self.conv_wgrad(Lstem, da_stem, dw=dw1p)

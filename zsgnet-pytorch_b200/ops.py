@@ -130,12 +130,12 @@ def bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, rows, c, m
          mask_mode, ptr(sums), ptr(dx), ptr(dgamma), ptr(dbeta), rows, c, stream())
 
 
-def maxpool_bn_relu_fwd(x, scale, shift, y, b, h, w, c, ho, wo):
-    call("zsg_maxpool_bn_relu_fwd", ptr(x), ptr(scale), ptr(shift), ptr(y), b, h, w, c, ho, wo, stream())
+def maxpool_bn_relu_fwd(x, scale, shift, y, argmax, b, h, w, c, ho, wo):
+    call("zsg_maxpool_bn_relu_fwd", ptr(x), ptr(scale), ptr(shift), ptr(y), ptr(argmax), b, h, w, c, ho, wo, stream())
 
 
-def maxpool_bn_relu_bwd(x, scale, shift, dy, da, b, h, w, c, ho, wo):
-    call("zsg_maxpool_bn_relu_bwd", ptr(x), ptr(scale), ptr(shift), ptr(dy), ptr(da), b, h, w, c, ho, wo, stream())
+def maxpool_bn_relu_bwd(argmax, dy, da, b, h, w, c, ho, wo):
+    call("zsg_maxpool_bn_relu_bwd", ptr(argmax), ptr(dy), ptr(da), b, h, w, c, ho, wo, stream())
 
 
 def upsample_add(dst, src, iy, ix, b, ho, wo, hi, wi, c):
