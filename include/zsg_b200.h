@@ -74,6 +74,9 @@ typedef struct {
   int32_t impl;            /* 0 = tcgen05 (product path), 1 = SIMT check kernel (tests only) */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
+/* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
+ * K blocks to buf[nblocks * 16] (device memory); buf = NULL switches tracing off. */
+int zsg_debug_set_conv_trace(unsigned int* buf, int nblocks);
 
 /* weight gradient: dw[n][r][s][c] += sum_rows dy[row.out + n] * pro(x[gather(row,r,s) + c]).
  * Replaces the cuDNN wgrad inside loss.backward() (utils.py:412) for every conv above and the

@@ -1,3 +1,6 @@
+"""Timing ablations of conv_tc_kernel (diagnostics; results are garbage when a part is switched off).
+impl = 8 + bits: 1 = no producers (MMA warp does not wait for `full`), 2 = drain warps skip tcgen05.ld, 4 = MMA warp
+does not wait for acc_empty."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,9 +16,8 @@ def run(B, cin, H, cout, k, label):
     y = torch.empty(B, H, H, cout, device="cuda")
     M = B * H * H
     fl = 2.0 * M * cout * k * k * cin
-    names = {0: "normal", 2: "no gather loads", 3: "no loads, no STS", 4: "no loads/STS/fence", 5: "normal w/o proxy fence",
-             6: "no weight TMA"}
-    for impl in (0, 2, 3, 4, 5, 6):
+    names = {0: "normal", 9: "no producers", 11: "no producers, no drain", 10: "no drain"}
+    for impl in names:
         op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, impl=impl, w_lo=lo)
         for _ in range(2): op()
         torch.cuda.synchronize()
@@ -24,7 +26,7 @@ def run(B, cin, H, cout, k, label):
         for _ in range(5): op()
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 5
-        print(f"{label:28s} {names[impl]:26s} {ms:7.3f} ms  {fl/ms/1e9:7.1f} TF/s")
+        print(f"{label:28s} {names[impl]:30s} {ms:7.3f} ms  {fl/ms/1e9:7.1f} TF/s", flush=True)
 
 run(64, 256, 44, 256, 3, "3x3 256->256 M=123904")
 run(64, 64, 75, 256, 1, "1x1 64->256 M=360000")

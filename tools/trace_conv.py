@@ -1,0 +1,43 @@
+"""Pipeline timeline of conv_tc_kernel (diagnostics): CTA 0 stamps clock64 at the hand-overs of its first K blocks.
+events: 0 producer before empty-wait, 1 after empty-wait, 2 after the STS loop, 3 after arrive(full);
+        8 issuer before full-wait, 9 after full-wait, 10 after token-wait, 11 after issue+commit."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import zsg_b200
+from zsg_b200 import ops, geometry, _lib
+
+def run(B, cin, H, cout, k, label, nblk=120, pro=False):
+    x = torch.randn(B, H, H, cin, device="cuda")
+    w = torch.randn(cout, k, k, cin, device="cuda") * 0.05
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    ops.split_tf32(w, hi, lo, w.numel())
+    rows = geometry.conv_rows(B, H, H, cin, H, H, cout, 1, k // 2).cuda()
+    y = torch.empty(B, H, H, cout, device="cuda")
+    M = B * H * H
+    sc = torch.rand(cin, device="cuda") + 0.5 if pro else None
+    sh = torch.randn(cin, device="cuda") if pro else None
+    op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, in_scale=sc, in_shift=sh, in_relu=pro)
+    for _ in range(2): op()
+    torch.cuda.synchronize()
+    buf = torch.zeros(nblk * 16, dtype=torch.int32, device="cuda")
+    _lib.call("zsg_debug_set_conv_trace", buf.data_ptr(), nblk)
+    op()
+    torch.cuda.synchronize()
+    _lib.call("zsg_debug_set_conv_trace", None, 0)
+    t = buf.cpu().numpy().astype(np.int64).reshape(nblk, 16) & 0xFFFFFFFF
+    t0 = t[0, 0]
+    t = (t - t0) & 0xFFFFFFFF
+    print(f"--- {label}: cycles relative to the first producer stamp; gk | P:top emptyOK stsDone arrived | I:top fullOK tokOK issued | issue-to-issue")
+    prev = None
+    for g in range(40, min(nblk, 76)):
+        r = t[g]
+        d = (r[11] - prev) if prev is not None else 0
+        prev = r[11]
+        print(f"{g:4d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | {r[8]:7d} {r[9]:7d} {r[10]:7d} {r[11]:7d} | {d:5d}   emptywait {r[1]-r[0]:5d} sts {r[2]-r[1]:5d}  fullwait {r[9]-r[8]:5d} tok {r[10]-r[9]:4d} issue {r[11]-r[10]:4d}  full->arrive lag {r[9]-r[3]:5d}")
+    per = (t[100, 11] - t[20, 11]) / 80.0
+    print(f"average issue period over K blocks 20..100: {per:.0f} cycles (floor 768)")
+
+run(64, 256, 44, 256, 3, "3x3 256->256 no prologue")
+run(64, 256, 44, 256, 3, "3x3 256->256 BN+ReLU prologue", pro=True)

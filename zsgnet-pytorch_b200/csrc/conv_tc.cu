@@ -46,14 +46,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("zsg conv: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
+      printf("zsg conv: mbarrier wait timed out (block %d,%d,%d thread %d, wait site %d, parity %u)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, tag, parity);
       __trap();
     }
   }
@@ -149,11 +149,11 @@ __device__ __forceinline__ void store_split(uint8_t* tile_hi, uint8_t* tile_lo, 
 }
 
 // --------------------------------------------------------------------------------------------
-// CTA layout (17 warps):
+// CTA layout (18 warps):
 //   warps 0-3, 4-7   two producer groups; group g fills the stages of K-blocks kb == g (mod 2), so
 //                    twice as many gather loads are in flight and neither group waits on the other
 //   warps 8-15       drain + epilogue: quadrant (warp & 3) = TMEM lanes, (warp - 8) >> 2 = column half
-//   warp 16          TMEM allocation + single-thread MMA issue
+//   warps 16, 17     MMA issue, one elected thread each, taking turns K block by K block (16 also owns TMEM)
 //
 // Chunked promotion: the tensor core adds every MMA into the fp32 TMEM accumulator with truncation,
 // which biases long reductions toward zero (measured -1.4e-5 relative at K = 2304).  So TMEM only
@@ -163,11 +163,12 @@ __device__ __forceinline__ void store_split(uint8_t* tile_hi, uint8_t* tile_lo, 
 // result in registers.
 // --------------------------------------------------------------------------------------------
 constexpr int NGROUP = 2;            // producer groups
-constexpr int CHUNK_KB = 4;          // K-blocks accumulated in TMEM before promotion (128 fp32 K elements)
+constexpr int CHUNK_KB = 8;          // K-blocks per chunk: each of the two issuers accumulates its (up to) 4 in its own TMEM
+                                     // accumulator before the drain warps promote both into fp32 registers
 constexpr int NDRAIN = 256;          // drain / epilogue threads
 constexpr int DRAIN_WARP0 = 8;
-constexpr int MMA_WARP = 16;
-constexpr int NTHREADS2 = 17 * 32;
+constexpr int MMA_WARP = 16;           // issuer warps: 16 and 17 (TMEM is allocated / freed by 16)
+constexpr int NTHREADS2 = 18 * 32;
 
 template <int BN>
 struct Smem {
@@ -180,7 +181,7 @@ struct Smem {
   static constexpr int EPI_OFF = BAR_OFF + 256;             // epilogue staging: 8 warps x 32 rows x 20 floats
   static constexpr int EPI_WARP_BYTES = 32 * 20 * 4;
   static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_BYTES + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
+  static constexpr int TMEM_COLS = 4 * BN;                  // (chunk parity) x (issuer) accumulators
 };
 
 struct PipeBars {                      // mbarrier addresses are computed, never indexed from memory
@@ -188,9 +189,18 @@ struct PipeBars {                      // mbarrier addresses are computed, never
   __device__ __forceinline__ uint32_t full(int s) const { return bar0 + 8 * s; }
   __device__ __forceinline__ uint32_t empty(int s) const { return bar0 + 32 + 8 * s; }
   __device__ __forceinline__ uint32_t acc_full(int a) const { return bar0 + 64 + 8 * a; }
-  __device__ __forceinline__ uint32_t acc_empty(int a) const { return bar0 + 80 + 8 * a; }
-  __device__ __forceinline__ uint32_t tmem_slot() const { return bar0 + 96; }
+  __device__ __forceinline__ uint32_t acc_empty(int a) const { return bar0 + 96 + 8 * a; }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return bar0 + 128; }
+  __device__ __forceinline__ uint32_t token(uint32_t w) const { return bar0 + 136 + 8 * w; }
 };
+
+// Diagnostics (tools/trace_conv.py): when a trace buffer is registered, CTA 0 records clock timestamps of the
+// pipeline hand-overs of its first K blocks: trace[gk * 16 + event].
+__device__ unsigned int* g_trace = nullptr;
+__device__ int g_trace_blocks = 0;
+__device__ __forceinline__ void trace(int gk, int ev) {
+  if (g_trace != nullptr && blockIdx.x == 0 && gk < g_trace_blocks) g_trace[gk * 16 + ev] = (unsigned int)clock64();
+}
 
 template <int BN>
 __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int lane, int full_count = NPROD) {
@@ -200,7 +210,8 @@ __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int la
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < S::STAGES; ++i) { mbar_init(pb.full(i), full_count); mbar_init(pb.empty(i), 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(pb.acc_full(i), 1); mbar_init(pb.acc_empty(i), NDRAIN); }
+      for (int i = 0; i < 4; ++i) { mbar_init(pb.acc_full(i), 1); mbar_init(pb.acc_empty(i), NDRAIN); }
+      for (int i = 0; i < 2; ++i) mbar_init(pb.token(i), 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -212,88 +223,247 @@ __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int la
   return pb;
 }
 
-// MMA issue loop (3xTF32: lo*hi + hi*lo + hi*hi), one TMEM accumulator per chunk.  The whole warp runs the
-// loop so that descriptors and addresses live in uniform registers; only the tcgen05 instructions are
-// predicated on one elected lane (a single divergent thread makes the compiler wrap every UTCHMMA in an
-// ELECT / R2UR.BROADCAST loop, which costs more than the 64-cycle tf32 MMA itself).
+// MMA issue (3xTF32: lo*hi + hi*lo + hi*hi), one TMEM accumulator per chunk.
+//
+// The tensor pipe only queues about two MMAs (measured: every UTCHMMA of a K block stalls equally on issue, and
+// the pipe idled 42 % of the time while this warp spent ~700 cycles per K block outside the MMA issue stall), so
+// everything this warp executes between the last MMA of one K block and the first of the next is exposed.  Hence:
+// ring position and phases are running counters (no division), the four descriptors of a stage differ from one
+// base word by constants, and the twelve MMAs of a K block are issued from ONE asm block whose only other
+// instructions are the 32-bit adds that advance the descriptor start addresses.
+//
 // MN_MAJOR (weight-gradient kernel): both operands are stored as they lie in memory, [pixel][channel].  For 32-bit
 // operands the only MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1): atoms of
 // 4 pixel rows x 128 B (32 channels) in which the 32-byte granule g of row r is stored at granule g ^ r (byte-address
 // bits [5,7) ^= bits [7,9)).  Tile = [channel atom][pixel group of 4][4][128 B]: LBO = 4096 B between channel atoms, SBO = 512 B
 // between pixel groups; one MMA (K = 8) consumes two pixel groups (1024 B).
-template <int BN, bool MN_MAJOR = false>
-__device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb, int& gkb,
-                                         int& gchunk, bool swap_lbo_sbo = false) {
-  using S = Smem<BN>;
+// Two issuing warps.  Measured on B200 (tools/micro/mma_pingpong.cu): the tensor pipe queues only about two MMAs, so
+// with ONE issuing thread every instruction between the last MMA of a K block and the first of the next (barrier
+// waits, fences, descriptor set-up: ~50 SASS instructions) is exposed -- a single issuer with that much work per
+// 12 MMAs reaches 71 % of the 64-cycle/MMA floor, two issuers reach 100 %.  So warps 16 and 17 each elect one
+// thread; thread w owns the K blocks with (global index) % 2 == w and accumulates them into ITS OWN TMEM
+// accumulator (chunk parity x issuer = 4 accumulators), so the two never touch the same accumulator or stage and
+// results do not depend on how the pipe interleaves the tail of one K block with the head of the next (with a
+// shared accumulator that made the fp32 sums differ from run to run).  They still take turns through a token
+// (mbarrier) so that only one thread issues at a time: issuing from both concurrently hung the pipe now and then.
+struct Issuer {
+  uint32_t w;                // 0 / 1
+  uint32_t stage;            // ring position of my next K block
+  uint32_t phase;            // parity of full[stage] for my next K block
+  uint32_t tokens = 0;       // tokens consumed so far (parity of my token barrier)
+  uint32_t g = 0;            // global K-block index over all tiles of this CTA
+  uint32_t chunk = 0;        // global chunk index (selects the accumulator pair and its parity)
+};
+
+template <int BN, bool MN_MAJOR>
+__device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_hi_lo, uint32_t desc_hi, uint32_t acc_first) {
   constexpr uint32_t idesc = umma_idesc_tf32(BN, MN_MAJOR);
-  const uint32_t tiles0 = smem_u32(sm);
-  const uint64_t lbo = MN_MAJOR ? (swap_lbo_sbo ? 32ull : 256ull) : 1ull;
-  const uint64_t sbo = MN_MAJOR ? (swap_lbo_sbo ? 256ull : 32ull) : 64ull;
-  const uint64_t desc_hi = (lbo << 16) | (sbo << 32) | (1ull << 46) | ((MN_MAJOR ? 1ull : 2ull) << 61);
-  constexpr uint32_t kstep = MN_MAJOR ? 64u : 2u;          // descriptor start-address advance per MMA (16 B units)
-  // gkb / gchunk count K blocks / chunks over ALL tiles of this CTA: they index the smem ring and the two TMEM
-  // accumulators and give the mbarrier phases; a chunk never spans two tiles.
-  for (int kb = 0; kb < nkb; ++kb, ++gkb) {
-    const int s = gkb % S::STAGES;
-    const int chunk = gchunk;
-    const bool first = (kb % CHUNK_KB) == 0;
-    const uint32_t tmem_d = tmem_base + (uint32_t)(chunk & 1) * BN;
-    if (first) {                                          // the drain warps must have emptied this accumulator
-      mbar_wait(pb.acc_empty(chunk & 1), ((chunk >> 1) & 1) ^ 1);
+  constexpr uint32_t A16 = A_TILE_BYTES >> 4, B16 = (BN * 128) >> 4, KSTEP = MN_MAJOR ? 64u : 2u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b32 a0, a1, b0, b1;\n\t"
+      ".reg .b64 dah, dal, dbh, dbl;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b32 a0, %1;\n\t"
+      "add.u32 a1, a0, %5;\n\t"
+      "add.u32 b0, a1, %5;\n\t"
+      "add.u32 b1, b0, %6;\n\t"
+      "mov.b64 dah, {a0, %2};\n\tmov.b64 dal, {a1, %2};\n\tmov.b64 dbh, {b0, %2};\n\tmov.b64 dbl, {b1, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dal, dbh, %4, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbl, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbh, %4, pt;\n\t"
+      "add.u32 a0, a0, %7;\n\tadd.u32 a1, a1, %7;\n\tadd.u32 b0, b0, %7;\n\tadd.u32 b1, b1, %7;\n\t"
+      "mov.b64 dah, {a0, %2};\n\tmov.b64 dal, {a1, %2};\n\tmov.b64 dbh, {b0, %2};\n\tmov.b64 dbl, {b1, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dal, dbh, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbl, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbh, %4, pt;\n\t"
+      "add.u32 a0, a0, %7;\n\tadd.u32 a1, a1, %7;\n\tadd.u32 b0, b0, %7;\n\tadd.u32 b1, b1, %7;\n\t"
+      "mov.b64 dah, {a0, %2};\n\tmov.b64 dal, {a1, %2};\n\tmov.b64 dbh, {b0, %2};\n\tmov.b64 dbl, {b1, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dal, dbh, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbl, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbh, %4, pt;\n\t"
+      "add.u32 a0, a0, %7;\n\tadd.u32 a1, a1, %7;\n\tadd.u32 b0, b0, %7;\n\tadd.u32 b1, b1, %7;\n\t"
+      "mov.b64 dah, {a0, %2};\n\tmov.b64 dal, {a1, %2};\n\tmov.b64 dbh, {b0, %2};\n\tmov.b64 dbl, {b1, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dal, dbh, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbl, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], dah, dbh, %4, pt;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(a_hi_lo), "r"(desc_hi), "r"(acc_first), "n"(idesc), "n"(A16), "n"(B16), "n"(KSTEP)
+      : "memory");
+}
+
+template <int BN>
+__device__ __forceinline__ Issuer issuer_init(uint32_t w) {
+  Issuer is;
+  is.w = w;
+  is.stage = w % Smem<BN>::STAGES;
+  is.phase = 0;
+  return is;
+}
+
+// Executed by the elected thread of issuer warp `is.w` for the K blocks of one tile (both issuers walk all K blocks
+// to keep the chunk bookkeeping, each acts on its own).  A chunk never spans two tiles.
+template <int BN, bool MN_MAJOR = false>
+__device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb, Issuer& is,
+                                         bool swap_lbo_sbo = false, int ablate = 0) {
+  using S = Smem<BN>;
+  const uint32_t lbo = MN_MAJOR ? (swap_lbo_sbo ? 32u : 256u) : 1u;
+  const uint32_t sbo = MN_MAJOR ? (swap_lbo_sbo ? 256u : 32u) : 64u;
+  const uint32_t desc_hi = sbo | (1u << 14) | ((MN_MAJOR ? 1u : 2u) << 29);          // bits 32..63 of the descriptor
+  const uint32_t lo0 = ((smem_u32(sm) >> 4) & 0x3FFFu) | (lbo << 16);                // a_hi tile of stage 0
+  uint32_t mine = 0;                                        // my K blocks so far in the current chunk
+  for (int kb = 0; kb < nkb; ++kb, ++is.g) {
+    const uint32_t acc = (is.chunk & 1u) * 2u + is.w;
+    if ((is.g & 1u) == is.w) {
+      if (mine == 0) mbar_wait(pb.acc_empty(acc), ((is.chunk >> 1) & 1u) ^ 1u, 100 + is.g);      // drained two chunks ago
+      trace(is.g, 8);
+      if (!(ablate & 1)) mbar_wait(pb.full(is.stage), is.phase, 1000 + is.g);     // ablate bit 0 (diagnostics): producers are off
+      trace(is.g, 9);
+      if (is.g > 0) { mbar_wait(pb.token(is.w), is.tokens & 1u, 4000 + is.g); ++is.tokens; }      // my turn
+      trace(is.g, 10);
       tc_fence_after();
+      issue_kblock<BN, MN_MAJOR>(tmem_base + acc * BN, lo0 + is.stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi,
+                                 mine == 0 ? 0u : 1u);
+      tc_fence_before();
+      mbar_arrive(pb.token(is.w ^ 1u));                     // the other issuer may go
+      umma_commit(pb.empty(is.stage));                      // frees the stage once the MMAs above have read it
+      trace(is.g, 11);
+      ++mine;
+      is.stage += 2;
+      if (is.stage >= (uint32_t)S::STAGES) { is.stage -= S::STAGES; is.phase ^= 1u; }
     }
-    mbar_wait(pb.full(s), (gkb / S::STAGES) & 1);
-    tc_fence_after();
-    const uint32_t a_hi = (tiles0 + s * S::STAGE_BYTES) >> 4;
-    const uint32_t a_lo = a_hi + (A_TILE_BYTES >> 4);
-    const uint32_t b_hi = a_lo + (A_TILE_BYTES >> 4);
-    const uint32_t b_lo = b_hi + (S::B_TILE_BYTES >> 4);
-    if (elect_one()) {
-#pragma unroll
-      for (int k = 0; k < KB / 8; ++k) {
-        const uint64_t dah = desc_hi | (uint64_t)((a_hi + kstep * k) & 0x3FFFu), dal = desc_hi | (uint64_t)((a_lo + kstep * k) & 0x3FFFu);
-        const uint64_t dbh = desc_hi | (uint64_t)((b_hi + kstep * k) & 0x3FFFu), dbl = desc_hi | (uint64_t)((b_lo + kstep * k) & 0x3FFFu);
-        umma_tf32(tmem_d, dal, dbh, idesc, (first && k == 0) ? 0u : 1u);
-        umma_tf32(tmem_d, dah, dbl, idesc, 1);
-        umma_tf32(tmem_d, dah, dbh, idesc, 1);
-      }
-      umma_commit(pb.empty(s));                           // frees the stage once the MMAs above have read it
-      if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(pb.acc_full(chunk & 1));
+    if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) {   // chunk closed: my part of it (possibly empty) is complete
+      umma_commit(pb.acc_full(acc));
+      ++is.chunk;
+      mine = 0;
     }
-    __syncwarp();
-    if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1) ++gchunk;
   }
 }
 
-// drain warps: promote every finished TMEM chunk into fp32 registers (round-to-nearest adds)
+// drain warps: promote every finished TMEM chunk into fp32 registers (round-to-nearest adds), issuer 0's part first.
+// gkb0 = global index of the tile's first K block (decides which issuer owns which K block of the chunk).
 template <int BN>
-__device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_base, int nkb, int quadrant, int half,
-                                           float (&acc)[BN / 2], int& gchunk) {
+__device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_base, int nkb, int gkb0, int quadrant, int half,
+                                           float (&acc)[BN / 2], int& gchunk, int ablate = 0) {
 #pragma unroll
   for (int i = 0; i < BN / 2; ++i) acc[i] = 0.f;
   const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
   for (int cc = 0; cc < nchunks; ++cc, ++gchunk) {
     const int c = gchunk;
-    mbar_wait(pb.acc_full(c & 1), (c >> 1) & 1);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(c & 1) * BN + half * (BN / 2);
+    const int k0 = cc * CHUNK_KB;
+    const int n = (nkb - k0 < CHUNK_KB) ? nkb - k0 : CHUNK_KB;
+    const int first_owner = (gkb0 + k0) & 1;
 #pragma unroll
-    for (int cb = 0; cb < BN / 32; ++cb) {
-      uint32_t r[16];
-      tmem_ld16(taddr + cb * 16, r);
+    for (int w = 0; w < 2; ++w) {
+      const int a = (c & 1) * 2 + w;
+      const int count = (w == first_owner) ? (n + 1) / 2 : n / 2;      // K blocks issuer w put into its accumulator
+      mbar_wait(pb.acc_full(a), (c >> 1) & 1, 2000 + c * 2 + w);
+      tc_fence_after();
+      if (count > 0 && !(ablate & 2)) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)a * BN + half * (BN / 2);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += __uint_as_float(r[j]);
+        for (int cb = 0; cb < BN / 32; ++cb) {
+          uint32_t r[16];
+          tmem_ld16(taddr + cb * 16, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += __uint_as_float(r[j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(pb.acc_empty(a));
     }
-    tc_fence_before();
-    mbar_arrive(pb.acc_empty(c & 1));
+  }
+}
+
+// drain + epilogue warps of the forward / data-gradient kernels
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t* sm, const PipeBars& pb, uint32_t tmem_base,
+                                              int warp, int lane, int nkb, int tiles_n, int total_tiles, int ablate = 0) {
+  using S = Smem<BN>;
+  // ------------------------------ drain + epilogue ------------------------------
+  const int dw = warp - DRAIN_WARP0;
+  const int quadrant = dw & 3, half = dw >> 2;
+  const int row = quadrant * 32 + lane;
+  int gchunk = 0, gkb0 = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n0 = (tile % tiles_n) * BN;
+    const int m0 = (tile / tiles_n) * TM;
+    int out_off = 0;
+    const bool row_ok = m0 + row < p.m;
+    if (row_ok) out_off = __ldg(&p.rows[m0 + row].out);          // prefetched under the drain
+    float acc[BN / 2];
+    drain_loop<BN>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
+    gkb0 += nkb;
+    // Epilogue through a per-warp smem slab: a thread owns one row of the accumulator, but global memory wants
+    // lanes along channels.  16 columns at a time are transposed through smem (row stride 20 floats keeps the
+    // 128-bit accesses conflict-free); then 4 lanes cover one row's 64 B and a warp instruction touches 8 rows
+    // with full 32-byte sectors, for the store and for the residual / mask / accumulate reads alike.
+    float* stg = reinterpret_cast<float*>(sm + S::EPI_OFF + dw * S::EPI_WARP_BYTES);
+    const int rsel = lane >> 2, c4 = (lane & 3) * 4;
+#pragma unroll
+    for (int slab = 0; slab < BN / 32; ++slab) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * 20 + j) =
+            make_float4(acc[slab * 16 + j], acc[slab * 16 + j + 1], acc[slab * 16 + j + 2], acc[slab * 16 + j + 3]);
+      __syncwarp();
+      const int n = n0 + half * (BN / 2) + slab * 16 + c4;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias && n < p.cout) {
+        if (n + 3 < p.cout) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        else { bias4.x = __ldg(p.bias + n); if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1); if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2); }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + rsel;
+        const int off_r = __shfl_sync(0xffffffffu, out_off, r);
+        const bool ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r) != 0;
+        if (!ok_r || n >= p.cout) continue;
+        float4 v4 = *reinterpret_cast<const float4*>(stg + r * 20 + c4);
+        float v[4] = {v4.x + bias4.x, v4.y + bias4.y, v4.z + bias4.z, v4.w + bias4.w};
+        float* yrow = p.y + (int64_t)off_r + n;
+        const bool vec = ((p.cout & 3) == 0) && ((off_r & 3) == 0) && (n + 3 < p.cout);
+        if (vec) {
+          if (p.out_mask) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(p.out_mask + (int64_t)off_r + n));
+            if (!(m.x > 0.f)) v[0] = 0.f; if (!(m.y > 0.f)) v[1] = 0.f; if (!(m.z > 0.f)) v[2] = 0.f; if (!(m.w > 0.f)) v[3] = 0.f;
+          }
+          if (p.residual) {
+            const float4 q = *reinterpret_cast<const float4*>(p.residual + (int64_t)off_r + n);
+            v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+          }
+          if (p.accumulate) {
+            const float4 q = *reinterpret_cast<const float4*>(yrow);
+            v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+          }
+          if (p.out_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+          *reinterpret_cast<float4*>(yrow) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (n + q >= p.cout) break;
+            float u = v[q];
+            if (p.out_mask && !(p.out_mask[(int64_t)off_r + n + q] > 0.f)) u = 0.f;
+            if (p.residual) u += p.residual[(int64_t)off_r + n + q];
+            if (p.accumulate) u += yrow[q];
+            if (p.out_relu) u = fmaxf(u, 0.f);
+            yrow[q] = u;
+          }
+        }
+      }
+    }
   }
 }
 
 // ============================================================================================
-// forward / data-gradient kernel
+// forward / data-gradient kernel, generic variant: weights gathered through registers (p.w_lo == NULL) and every
+// option decided at run time.  The product path (pre-split weights, TMA) is conv_tc_kernel below.
 // ============================================================================================
 template <int BN, bool TMA_W>
-__global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_params p,
+__global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_generic_kernel(const zsg_conv_params p,
                                                                const __grid_constant__ CUtensorMap tm_hi,
                                                                const __grid_constant__ CUtensorMap tm_lo) {
   // Persistent: one CTA per SM walks the output tiles (n fastest, so the CTAs that share im2col rows run at the
@@ -310,11 +480,14 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
   const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
 
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane, TMA_W ? NPROD + 1 : NPROD);   // contains __syncthreads
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
 
-  if (warp == MMA_WARP) {
-    int gkb = 0, gchunk = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) mma_loop<BN>(sm, pb, tmem_base, nkb, gkb, gchunk);
+  if (warp >= MMA_WARP) {
+    if (elect_one()) {
+      Issuer is = issuer_init<BN>(warp - MMA_WARP);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) mma_loop<BN>(sm, pb, tmem_base, nkb, is);
+    }
+    __syncwarp();
   } else if (warp < DRAIN_WARP0) {
     // ------------------------------ producers ------------------------------
     // Thread (rsub, chunk) owns the 16-byte chunk `chunk` of rows rsub, rsub+16, ... of every K block of its
@@ -424,79 +597,211 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
       }
     }
   } else {
-    // ------------------------------ drain + epilogue ------------------------------
-    const int dw = warp - DRAIN_WARP0;
-    const int quadrant = dw & 3, half = dw >> 2;
-    const int row = quadrant * 32 + lane;
-    int gchunk = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    conv_epilogue<BN>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ============================================================================================
+// forward / data-gradient kernel, product variant.
+//
+// Same tiling, barriers, MMA and drain code as above; the producers are written for instruction count, because
+// ncu showed them issue-bound (about 440 SASS instructions per thread per K block, the MMA warp idle a fifth of
+// the time waiting for `full`):  the prologue (PRO bit 1 = BatchNorm affine, bit 0 = ReLU) is a template
+// parameter; gather loads, the affine and the zero-padding rule are predicated instructions instead of
+// branches; one IMAD.WIDE forms each address; the affine and the hi/lo subtraction use packed f32x2 math;
+// weights always arrive by TMA; one elected lane per producer warp arrives on `full`.
+// ============================================================================================
+__device__ __forceinline__ float4 ldg128_pred(const float* ptr, int off) {     // zeros when off < 0
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %5, 0;\n\t"
+      "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(ptr + off), "r"(off));
+  return v;
+}
+// v = v * sc + sh where off >= 0 (padding rows stay exactly zero)
+__device__ __forceinline__ void affine4_pred(float4& v, const float4& sc, const float4& sh, int off) {
+  asm("{\n\t.reg .pred q;\n\t.reg .b64 a, b, c;\n\tsetp.ge.s32 q, %12, 0;\n\t"
+      "mov.b64 a, {%0, %1};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%8, %9};\n\t"
+      "@q fma.rn.f32x2 a, a, b, c;\n\tmov.b64 {%0, %1}, a;\n\t"
+      "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%6, %7};\n\tmov.b64 c, {%10, %11};\n\t"
+      "@q fma.rn.f32x2 a, a, b, c;\n\tmov.b64 {%2, %3}, a;\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "f"(sc.x), "f"(sc.y), "f"(sc.z), "f"(sc.w), "f"(sh.x), "f"(sh.y), "f"(sh.z), "f"(sh.w), "r"(off));
+}
+__device__ __forceinline__ void affine4(float4& v, const float4& sc, const float4& sh) {
+  asm("{\n\t.reg .b64 a, b, c;\n\t"
+      "mov.b64 a, {%0, %1};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%8, %9};\n\t"
+      "fma.rn.f32x2 a, a, b, c;\n\tmov.b64 {%0, %1}, a;\n\t"
+      "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%6, %7};\n\tmov.b64 c, {%10, %11};\n\t"
+      "fma.rn.f32x2 a, a, b, c;\n\tmov.b64 {%2, %3}, a;\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "f"(sc.x), "f"(sc.y), "f"(sc.z), "f"(sc.w), "f"(sh.x), "f"(sh.y), "f"(sh.z), "f"(sh.w));
+}
+__device__ __forceinline__ void sts128(uint32_t dst, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  asm("{\n\t.reg .b64 a, b;\n\t"
+      "mov.b64 a, {%4, %5};\n\tmov.b64 b, {%8, %9};\n\tsub.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t"
+      "mov.b64 a, {%6, %7};\n\tmov.b64 b, {%10, %11};\n\tsub.rn.f32x2 a, a, b;\n\tmov.b64 {%2, %3}, a;\n\t}"
+      : "=f"(l.x), "=f"(l.y), "=f"(l.z), "=f"(l.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w));
+}
+
+constexpr int FULL_COUNT_TMA = NPROD / 32 + 1;
+     // one elected arrive per producer warp + the expect_tx arrive
+
+template <int BN, int PRO>
+__global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_params p,
+                                                               const __grid_constant__ CUtensorMap tm_hi,
+                                                               const __grid_constant__ CUtensorMap tm_lo) {
+  using S = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.r * p.s * p.cin;
+  const int nkb = (K + KB - 1) / KB;
+  const int tiles_n = (p.cout + BN - 1) / BN;
+  const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
+
+  const int ablate = p.impl >= 8 ? p.impl - 8 : 0;     // diagnostics (tools/ablate_conv.py): 1 = no producers, 2 = no TMEM drain, 4 = no acc_empty wait
+  PipeBars pb = setup_pipeline<BN>(sm, warp, lane, FULL_COUNT_TMA);   // contains __syncthreads
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+
+  if (warp >= MMA_WARP) {
+    if (elect_one()) {
+      Issuer is = issuer_init<BN>(warp - MMA_WARP);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) mma_loop<BN>(sm, pb, tmem_base, nkb, is, false, ablate);
+    }
+    __syncwarp();
+  } else if (warp < DRAIN_WARP0 && !(ablate & 1)) {
+    // ------------------------------ producers ------------------------------
+    const int group = warp >> 2;
+    const int t = tid & 127;
+    const int chunk = t & 7;
+    const int rsub = t >> 3;
+    const uint32_t soff = rsub * 128 + ((chunk ^ (rsub & 7)) << 4);      // + it * 2048 (16 rows x 128 B)
+    const int ntap = p.r * p.s;
+    const int cin = p.cin;
+    int4* rows_g = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * TM;      // this group's copy of the row table
+    const uint32_t tiles0 = smem_u32(sm);
+    int gkb0 = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, gkb0 += nkb) {
       const int n0 = (tile % tiles_n) * BN;
       const int m0 = (tile / tiles_n) * TM;
-      int out_off = 0;
-      const bool row_ok = m0 + row < p.m;
-      if (row_ok) out_off = __ldg(&p.rows[m0 + row].out);          // prefetched under the drain
-      float acc[BN / 2];
-      drain_loop<BN>(pb, tmem_base, nkb, quadrant, half, acc, gchunk);
-      // Epilogue through a per-warp smem slab: a thread owns one row of the accumulator, but global memory wants
-      // lanes along channels.  16 columns at a time are transposed through smem (row stride 20 floats keeps the
-      // 128-bit accesses conflict-free); then 4 lanes cover one row's 64 B and a warp instruction touches 8 rows
-      // with full 32-byte sectors, for the store and for the residual / mask / accumulate reads alike.
-      float* stg = reinterpret_cast<float*>(sm + S::EPI_OFF + dw * S::EPI_WARP_BYTES);
-      const int rsel = lane >> 2, c4 = (lane & 3) * 4;
+      {
+        int4 e = make_int4(0, 0, 0, 0);                   // hin = win = 0 => every tap out of bounds
+        if (m0 + t < p.m) e = __ldg(reinterpret_cast<const int4*>(p.rows) + m0 + t);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");   // previous tile's reads are done
+        rows_g[t] = e;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      }
+      const int kb_first = (group - gkb0) & 1;            // K blocks with (gkb0 + kb) % NGROUP == group
+      // (c, tap, tr, ts, off[], mask) always describe the block whose gather loads are issued NEXT.  The loads of
+      // block i + NGROUP are issued row by row while block i is converted, into the registers block i just freed:
+      // a whole iteration ahead, so their latency never sits between `empty` and `full`.
+      int c = chunk * 4 + kb_first * KB, tap = 0, tr = 0, ts = 0;
+      while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
+      int cached_tap = -1;
+      int off[8];                                         // element offset of the tap's pixel, -1 = padding
+      uint32_t mask = 0;                                  // bit it = row it is a real pixel at the cached tap
+      auto retap = [&]() {
+        cached_tap = tap;
+        const bool kvalid = tap < ntap;
+        mask = 0;
 #pragma unroll
-      for (int slab = 0; slab < BN / 32; ++slab) {
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * 20 + j) =
-              make_float4(acc[slab * 16 + j], acc[slab * 16 + j + 1], acc[slab * 16 + j + 2], acc[slab * 16 + j + 3]);
-        __syncwarp();
-        const int n = n0 + half * (BN / 2) + slab * 16 + c4;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && n < p.cout) {
-          if (n + 3 < p.cout) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          else { bias4.x = __ldg(p.bias + n); if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1); if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2); }
+        for (int it = 0; it < 8; ++it) {
+          const int4 e = rows_g[it * 16 + rsub];
+          int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+          const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+          bool ok = kvalid;
+          if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
+          ok = ok && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          off[it] = ok ? e.x + (yy * win + xx) * cin : -1;
+          mask |= ok ? (1u << it) : 0u;
         }
+      };
+      float4 va[8];
+      if (kb_first < nkb) {                               // prologue: loads of this group's first block of the tile
+        retap();
+        const float* xb = p.x + c;
+        asm("" : "+l"(xb));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 8 + rsel;
-          const int off_r = __shfl_sync(0xffffffffu, out_off, r);
-          const bool ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r) != 0;
-          if (!ok_r || n >= p.cout) continue;
-          float4 v4 = *reinterpret_cast<const float4*>(stg + r * 20 + c4);
-          float v[4] = {v4.x + bias4.x, v4.y + bias4.y, v4.z + bias4.z, v4.w + bias4.w};
-          float* yrow = p.y + (int64_t)off_r + n;
-          const bool vec = ((p.cout & 3) == 0) && ((off_r & 3) == 0) && (n + 3 < p.cout);
-          if (vec) {
-            if (p.out_mask) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(p.out_mask + (int64_t)off_r + n));
-              if (!(m.x > 0.f)) v[0] = 0.f; if (!(m.y > 0.f)) v[1] = 0.f; if (!(m.z > 0.f)) v[2] = 0.f; if (!(m.w > 0.f)) v[3] = 0.f;
-            }
-            if (p.residual) {
-              const float4 q = *reinterpret_cast<const float4*>(p.residual + (int64_t)off_r + n);
-              v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
-            }
-            if (p.accumulate) {
-              const float4 q = *reinterpret_cast<const float4*>(yrow);
-              v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
-            }
-            if (p.out_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-            *reinterpret_cast<float4*>(yrow) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
+        for (int it = 0; it < 8; ++it) va[it] = ldg128_pred(xb, off[it]);
+      }
+      for (int kb = kb_first; kb < nkb; kb += NGROUP) {
+        const int gk = gkb0 + kb;
+        const int s = gk % S::STAGES;
+        const uint32_t cur_mask = mask;                   // validity of the rows held in va[]
+        float4 sc, sh;
+        if (PRO & 2) {
+          sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + c));
+          sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + c));
+        }
+        // advance (tap, channel) to this group's next block and prepare its addresses
+        const bool has_next = kb + NGROUP < nkb;
+        c += NGROUP * KB;
+        while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
+        if (has_next && tap != cached_tap) retap();
+        const float* xb = p.x + c;
+        asm("" : "+l"(xb));                                // keep xb a 64-bit base: each address is one IMAD.WIDE
+        if (t == 0) trace(gk, 0);
+        mbar_wait(pb.empty(s), ((gk / S::STAGES) & 1) ^ 1, 3000 + gk);
+        if (t == 0) trace(gk, 1);
+        const uint32_t a_hi = tiles0 + s * S::STAGE_BYTES;
+        if ((t >> 5) == 0) {                               // weights: two TMA tiles, no register pass
+          if (elect_one()) {
+            mbar_arrive_expect_tx(pb.full(s), 2 * S::B_TILE_BYTES);
+            tma_load_2d(a_hi + 2 * A_TILE_BYTES, &tm_hi, kb * KB, n0, pb.full(s));
+            tma_load_2d(a_hi + 2 * A_TILE_BYTES + S::B_TILE_BYTES, &tm_lo, kb * KB, n0, pb.full(s));
+          }
+          __syncwarp();
+        }
+        const bool cur_full = cur_mask == 0xFFu, next_full = mask == 0xFFu;
+        if (cur_full && next_full && has_next) {           // interior: no per-row predicates anywhere
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (n + q >= p.cout) break;
-              float u = v[q];
-              if (p.out_mask && !(p.out_mask[(int64_t)off_r + n + q] > 0.f)) u = 0.f;
-              if (p.residual) u += p.residual[(int64_t)off_r + n + q];
-              if (p.accumulate) u += yrow[q];
-              if (p.out_relu) u = fmaxf(u, 0.f);
-              yrow[q] = u;
-            }
+          for (int it = 0; it < 8; ++it) {
+            float4 v = va[it];
+            va[it] = __ldg(reinterpret_cast<const float4*>(xb + off[it]));
+            if (PRO & 2) affine4(v, sc, sh);
+            if (PRO & 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            float4 h, l;
+            split4(v, h, l);
+            sts128(a_hi + soff + it * 2048, h);
+            sts128(a_hi + soff + it * 2048 + A_TILE_BYTES, l);
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float4 v = va[it];
+            if (has_next) va[it] = ldg128_pred(xb, off[it]);
+            if (PRO & 2) affine4_pred(v, sc, sh, (cur_mask >> it) & 1u ? 0 : -1);
+            if (PRO & 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            float4 h, l;
+            split4(v, h, l);
+            sts128(a_hi + soff + it * 2048, h);
+            sts128(a_hi + soff + it * 2048 + A_TILE_BYTES, l);
           }
         }
+        if (t == 0) trace(gk, 2);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pb.full(s));
+        if (t == 0) trace(gk, 3);
       }
     }
+  } else if (warp >= DRAIN_WARP0) {
+    conv_epilogue<BN>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
   }
   tc_fence_before();
   __syncthreads();
@@ -524,11 +829,14 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
   const int nkb = kb_end - kb_begin;                        // >= 1 by construction of the grid
 
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane);
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
 
-  if (warp == MMA_WARP) {
-    int gkb = 0, gchunk = 0;
-    mma_loop<BN, true>(sm, pb, tmem_base, nkb, gkb, gchunk, p.impl == 7);
+  if (warp >= MMA_WARP) {
+    if (elect_one()) {
+      Issuer is = issuer_init<BN>(warp - MMA_WARP);
+      mma_loop<BN, true>(sm, pb, tmem_base, nkb, is, p.impl == 7);
+    }
+    __syncwarp();
   } else if (warp < DRAIN_WARP0) {
     const int group = warp >> 2;
     const int t = tid & 127;
@@ -628,7 +936,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
     const int quadrant = dw & 3, half = dw >> 2;
     float acc[BN / 2];
     int gchunk = 0;
-    drain_loop<BN>(pb, tmem_base, nkb, quadrant, half, acc, gchunk);
+    drain_loop<BN>(pb, tmem_base, nkb, 0, quadrant, half, acc, gchunk);
     const int j = j0 + quadrant * 32 + lane;
     if (j < Kt) {
 #pragma unroll
@@ -731,11 +1039,11 @@ static int make_weight_map(CUtensorMap* map, const float* w, int cout, int K, in
   return ZSG_OK;
 }
 
-template <int BN, bool TMA_W>
-static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
+template <int BN>
+static int launch_conv_generic(const zsg_conv_params& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, TMA_W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_generic_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Smem<BN>::TOTAL);
     if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
@@ -743,15 +1051,38 @@ static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
   CUtensorMap tm_hi, tm_lo;
   memset(&tm_hi, 0, sizeof(tm_hi));
   memset(&tm_lo, 0, sizeof(tm_lo));
-  if (TMA_W) {
-    const int K = p.r * p.s * p.cin;
-    if (int rc = make_weight_map(&tm_hi, p.w, p.cout, K, BN)) return rc;
-    if (int rc = make_weight_map(&tm_lo, p.w_lo, p.cout, K, BN)) return rc;
-  }
   const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_kernel<BN, TMA_W><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
+  conv_tc_generic_kernel<BN, false><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
   return check_launch("zsg_conv_fwd");
+}
+
+template <int BN, int PRO>
+static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+    attr_done = true;
+  }
+  CUtensorMap tm_hi, tm_lo;
+  const int K = p.r * p.s * p.cin;
+  if (int rc = make_weight_map(&tm_hi, p.w, p.cout, K, BN)) return rc;
+  if (int rc = make_weight_map(&tm_lo, p.w_lo, p.cout, K, BN)) return rc;
+  const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
+  conv_tc_kernel<BN, PRO><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
+  return check_launch("zsg_conv_fwd");
+}
+
+template <int BN>
+static int launch_conv_pro(const zsg_conv_params& p, cudaStream_t st) {
+  switch ((p.in_scale ? 2 : 0) | (p.in_relu ? 1 : 0)) {
+    case 0: return launch_conv<BN, 0>(p, st);
+    case 1: return launch_conv<BN, 1>(p, st);
+    case 2: return launch_conv<BN, 2>(p, st);
+    default: return launch_conv<BN, 3>(p, st);
+  }
 }
 
 template <int BN>
@@ -784,6 +1115,13 @@ static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
 
 using namespace zsg;
 
+extern "C" int zsg_debug_set_conv_trace(unsigned int* buf, int nblocks) {
+  cudaError_t e = cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_trace_blocks, &nblocks, sizeof(nblocks));
+  if (e != cudaSuccess) { set_error("zsg_debug_set_conv_trace: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+  return ZSG_OK;
+}
+
 extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(pp, "zsg_conv_fwd: null params");
   const zsg_conv_params& p = *pp;
@@ -802,9 +1140,9 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   if (!zsg_device_supported()) { set_error("zsg_conv_fwd: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
   if (p.w_lo) {
     ZSG_REQUIRE(((uintptr_t)p.w_lo & 15) == 0, "zsg_conv_fwd: w_lo must be 16-byte aligned");
-    return p.cout <= 64 ? launch_conv<64, true>(p, st) : launch_conv<128, true>(p, st);
+    return p.cout <= 64 ? launch_conv_pro<64>(p, st) : launch_conv_pro<128>(p, st);
   }
-  return p.cout <= 64 ? launch_conv<64, false>(p, st) : launch_conv<128, false>(p, st);
+  return p.cout <= 64 ? launch_conv_generic<64>(p, st) : launch_conv_generic<128>(p, st);
 }
 
 extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
