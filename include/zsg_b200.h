@@ -72,6 +72,9 @@ typedef struct {
   const float* residual;   /* optional, indexed like y                                      */
   int32_t accumulate;      /* y += result instead of y = result                             */
   int32_t impl;            /* 0 = tcgen05 (product path), 1 = SIMT check kernel (tests only) */
+  const float* x_lo;       /* optional (needs w_lo, no in_scale / in_relu): fp32 remainders of x after TF32 truncation
+                              (zsg_split_act), same indexing as x.  The input operand then goes global -> shared by
+                              cp.async with no register pass: the tensor core reads x itself as the TF32 high part */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
@@ -92,12 +95,19 @@ typedef struct {
   int32_t in_relu;
   int32_t split_k;         /* 0 = choose automatically                                       */
   int32_t impl;
+  const float* x_lo;       /* optional pair (both or none; no in_scale / in_relu): TF32 remainders of x and dy      */
+  const float* dy_lo;      /* (zsg_split_act); operands then go global -> shared by cp.async                         */
 } zsg_wgrad_params;
 int zsg_conv_wgrad(const zsg_wgrad_params* p, zsg_stream_t stream);
 
 /* w [cout][r][s][cin] -> wt [cin][r][s][cout] with the taps flipped: the dgrad of a conv is the
  * forward kernel applied to wt. */
 int zsg_weight_transpose_flip(const float* w, float* wt, int cout, int rs_r, int rs_s, int cin, zsg_stream_t stream);
+/* Operand preparation for the cp.async GEMM paths: z = relu?(x * scale[c] + shift[c]) (z may be NULL when there is
+ * no affine / ReLU: the tensor is its own high part) and lo = z - trunc_tf32(z).  x is [rows, c], c % 4 == 0.
+ * Replaces the on-the-fly split inside the conv kernels for every conv of the path (mdl.py / fpn_resnet.py). */
+int zsg_split_act(const float* x, const float* scale, const float* shift, int relu, float* z, float* lo, int64_t rows,
+                  int c, zsg_stream_t stream);
 /* hi[i] = w[i] with the 13 low mantissa bits cleared (exactly representable in TF32), lo[i] = w[i] - hi[i]. */
 int zsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, zsg_stream_t stream);
 /* row-wise channel padding copy: dst[n][0:cdst] = src[n][0:csrc] (zero fill / truncate). */

@@ -70,14 +70,16 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int issuers, int work
   const uint32_t stage16 = (64 * 1024) >> 4;
   long long t0 = clock64();
   uint32_t sink = 0;
-  if (warp < issuers) {
+  const int nissue = issuers == 3 ? 2 : issuers;
+  if (warp < nissue) {
     if (elect_one()) {
       // thread `warp` issues groups g = warp, warp + issuers, ...; group g uses smem stage g % 3; accumulator zeroed at g == 0 only
-      for (int g = warp; g < iters; g += issuers) {
+      for (int g = warp; g < iters; g += nissue) {
         sink = busy(sink + g, work);                                  // "prologue": barrier checks, descriptors ...
         const uint32_t base16 = (smem_u32(sm) >> 4) + (g % 3) * stage16 + (sink & 0);
         if (issuers == 2 && g > 0) mbar_wait(smem_u32(&tok[warp]), ((g - 1) >> 1) & 1);      // my turn?
-        group12(tmem, base16, desc_hi, idesc, g ? 1u : 0u);
+        if (issuers == 3) group12(tmem + 128 * warp, base16, desc_hi, idesc, g >= 2 ? 1u : 0u);
+        else group12(tmem, base16, desc_hi, idesc, g ? 1u : 0u);
         if (issuers == 2) mbar_arrive(smem_u32(&tok[warp ^ 1]));                              // hand over
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done[warp])) : "memory");
@@ -95,7 +97,10 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int issuers, int work
     uint32_t r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(tmem) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (blockIdx.x == 0 && lane == 5) result[0] = __uint_as_float(r);
+    uint32_t r2;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r2) : "r"(tmem + 128) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (blockIdx.x == 0 && lane == 5) result[0] = __uint_as_float(r) + (issuers == 3 ? __uint_as_float(r2) : 0.f);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -122,6 +127,8 @@ int main() {
   for (int work : {0, 20, 50, 100}) {
     run("single issuer", 1, work);
     run("ping-pong", 2, work);
+    run("two free-running", 3, work);
   }
+  for (int rep = 0; rep < 20; ++rep) run("two free-running long", 3, 37 + rep, 200000);
   return 0;
 }

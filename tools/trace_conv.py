@@ -8,7 +8,7 @@ import torch
 import zsg_b200
 from zsg_b200 import ops, geometry, _lib
 
-def run(B, cin, H, cout, k, label, nblk=120, pro=False):
+def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False):
     x = torch.randn(B, H, H, cin, device="cuda")
     w = torch.randn(cout, k, k, cin, device="cuda") * 0.05
     hi, lo = torch.empty_like(w), torch.empty_like(w)
@@ -18,7 +18,12 @@ def run(B, cin, H, cout, k, label, nblk=120, pro=False):
     M = B * H * H
     sc = torch.rand(cin, device="cuda") + 0.5 if pro else None
     sh = torch.randn(cin, device="cuda") if pro else None
-    op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, in_scale=sc, in_shift=sh, in_relu=pro)
+    if use_async:
+        x_lo = torch.empty_like(x)
+        ops.split_act(x, x_lo, M, cin)
+        op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, x_lo=x_lo)
+    else:
+        op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, in_scale=sc, in_shift=sh, in_relu=pro)
     for _ in range(2): op()
     torch.cuda.synchronize()
     buf = torch.zeros(nblk * 16, dtype=torch.int32, device="cuda")
@@ -39,5 +44,8 @@ def run(B, cin, H, cout, k, label, nblk=120, pro=False):
     per = (t[100, 11] - t[20, 11]) / 80.0
     print(f"average issue period over K blocks 20..100: {per:.0f} cycles (floor 768)")
 
-run(64, 256, 44, 256, 3, "3x3 256->256 no prologue")
-run(64, 256, 44, 256, 3, "3x3 256->256 BN+ReLU prologue", pro=True)
+if "async" in sys.argv:
+    run(64, 256, 44, 256, 3, "3x3 256->256 cp.async path", use_async=True)
+else:
+    run(64, 256, 44, 256, 3, "3x3 256->256 no prologue")
+    run(64, 256, 44, 256, 3, "3x3 256->256 BN+ReLU prologue", pro=True)

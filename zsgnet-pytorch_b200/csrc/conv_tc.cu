@@ -199,7 +199,9 @@ struct PipeBars {                      // mbarrier addresses are computed, never
 __device__ unsigned int* g_trace = nullptr;
 __device__ int g_trace_blocks = 0;
 __device__ __forceinline__ void trace(int gk, int ev) {
+#ifdef ZSG_TRACE                       // build.py --trace; the stamps cost ~30 cycles each even when no buffer is registered
   if (g_trace != nullptr && blockIdx.x == 0 && gk < g_trace_blocks) g_trace[gk * 16 + ev] = (unsigned int)clock64();
+#endif
 }
 
 template <int BN>
@@ -321,13 +323,16 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
       trace(is.g, 8);
       if (!(ablate & 1)) mbar_wait(pb.full(is.stage), is.phase, 1000 + is.g);     // ablate bit 0 (diagnostics): producers are off
       trace(is.g, 9);
-      if (is.g > 0) { mbar_wait(pb.token(is.w), is.tokens & 1u, 4000 + is.g); ++is.tokens; }      // my turn
+      fence_proxy_async();                                  // cp.async-filled tiles (generic proxy) -> tensor core (async proxy)
+      if (is.g > 0 && !(ablate & 8)) { mbar_wait(pb.token(is.w), is.tokens & 1u, 4000 + is.g); ++is.tokens; }      // my turn
       trace(is.g, 10);
       tc_fence_after();
       issue_kblock<BN, MN_MAJOR>(tmem_base + acc * BN, lo0 + is.stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi,
                                  mine == 0 ? 0u : 1u);
-      tc_fence_before();
-      mbar_arrive(pb.token(is.w ^ 1u));                     // the other issuer may go
+      if (!(ablate & 8)) {
+        tc_fence_before();
+        mbar_arrive(pb.token(is.w ^ 1u));                   // the other issuer may go
+      }
       umma_commit(pb.empty(is.stage));                      // frees the stage once the MMAs above have read it
       trace(is.g, 11);
       ++mine;
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
   const int tiles_n = (p.cout + BN - 1) / BN;
   const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
 
-  const int ablate = p.impl >= 8 ? p.impl - 8 : 0;     // diagnostics (tools/ablate_conv.py): 1 = no producers, 2 = no TMEM drain, 4 = no acc_empty wait
+  const int ablate = p.impl >= 8 ? p.impl - 8 : 0;     // diagnostics (tools/ablate_conv.py): 1 = no producers, 2 = no TMEM drain, 8 = issuers without token
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane, FULL_COUNT_TMA);   // contains __syncthreads
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
 
@@ -798,6 +803,129 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
         __syncwarp();
         if (lane == 0) mbar_arrive(pb.full(s));
         if (t == 0) trace(gk, 3);
+      }
+    }
+  } else if (warp >= DRAIN_WARP0) {
+    conv_epilogue<BN>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ============================================================================================
+// forward / data-gradient kernel, pre-split input operand (p.x_lo != NULL).
+//
+// The input tensor comes with its TF32 remainders (zsg_split_act): the tensor core reads a raw fp32 word as its
+// TF32 truncation, so `x` itself is the high-part tile and `x_lo` the low-part tile, and both go global -> shared
+// with cp.async (16 B per request, zero-filled for padding taps) -- no register pass, no arithmetic.  Measured
+// before this existed: the register-path producers (gather, affine, split, 16 STS.128 per thread and K block) took
+// 1000-2700 cycles per K block and group against a 768-cycle MMA floor.
+// ============================================================================================
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_conv_params p,
+                                                                     const __grid_constant__ CUtensorMap tm_hi,
+                                                                     const __grid_constant__ CUtensorMap tm_lo) {
+  using S = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.r * p.s * p.cin;
+  const int nkb = (K + KB - 1) / KB;
+  const int tiles_n = (p.cout + BN - 1) / BN;
+  const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
+  const int ablate = p.impl >= 8 ? p.impl - 8 : 0;
+  PipeBars pb = setup_pipeline<BN>(sm, warp, lane, NPROD + 1);   // 128 cp.async completions + the expect_tx arrive
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+
+  if (warp >= MMA_WARP) {
+    if (elect_one()) {
+      Issuer is = issuer_init<BN>(warp - MMA_WARP);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) mma_loop<BN>(sm, pb, tmem_base, nkb, is, false, ablate);
+    }
+    __syncwarp();
+  } else if (warp < DRAIN_WARP0 && !(ablate & 1)) {
+    // ------------------------------ producers ------------------------------
+    const int group = warp >> 2;
+    const int t = tid & 127;
+    const int chunk = t & 7;
+    const int rsub = t >> 3;
+    const uint32_t soff = rsub * 128 + ((chunk ^ (rsub & 7)) << 4);      // + it * 2048 (16 rows x 128 B)
+    const int ntap = p.r * p.s;
+    const int cin = p.cin;
+    int4* rows_g = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * TM;      // this group's copy of the row table
+    const uint32_t tiles0 = smem_u32(sm);
+    int gkb0 = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, gkb0 += nkb) {
+      const int n0 = (tile % tiles_n) * BN;
+      const int m0 = (tile / tiles_n) * TM;
+      {
+        int4 e = make_int4(0, 0, 0, 0);                   // hin = win = 0 => every tap out of bounds
+        if (m0 + t < p.m) e = __ldg(reinterpret_cast<const int4*>(p.rows) + m0 + t);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");   // previous tile's reads are done
+        rows_g[t] = e;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      }
+      const int kb_first = (group - gkb0) & 1;            // K blocks with (gkb0 + kb) % NGROUP == group
+      int c = chunk * 4 + kb_first * KB, tap = 0, tr = 0, ts = 0;
+      while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
+      int cached_tap = -1;
+      int off[8];                                         // element offset of the tap's pixel, -1 = padding
+      for (int kb = kb_first; kb < nkb; kb += NGROUP) {
+        const int gk = gkb0 + kb;
+        const int s = gk % S::STAGES;
+        if (tap != cached_tap) {
+          cached_tap = tap;
+          const bool kvalid = tap < ntap;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int4 e = rows_g[it * 16 + rsub];
+            int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+            const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+            bool ok = kvalid;
+            if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
+            ok = ok && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+            off[it] = ok ? e.x + (yy * win + xx) * cin : -1;
+          }
+        }
+        const float* xh = p.x + c;
+        const float* xl = p.x_lo + c;
+        asm("" : "+l"(xh));
+        asm("" : "+l"(xl));
+        if (t == 0) trace(gk, 0);
+        mbar_wait(pb.empty(s), ((gk / S::STAGES) & 1) ^ 1, 3000 + gk);
+        if (t == 0) trace(gk, 1);
+        const uint32_t a_hi = tiles0 + s * S::STAGE_BYTES;
+        if ((t >> 5) == 0) {                               // weights: two TMA tiles
+          if (elect_one()) {
+            mbar_arrive_expect_tx(pb.full(s), 2 * S::B_TILE_BYTES);
+            tma_load_2d(a_hi + 2 * A_TILE_BYTES, &tm_hi, kb * KB, n0, pb.full(s));
+            tma_load_2d(a_hi + 2 * A_TILE_BYTES + S::B_TILE_BYTES, &tm_lo, kb * KB, n0, pb.full(s));
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const bool ok = off[it] >= 0;
+          const int o = ok ? off[it] : 0;
+          const uint32_t nbytes = ok ? 16u : 0u;           // 0 source bytes = 16 bytes of zeros (padding)
+          const uint32_t dst = a_hi + soff + it * 2048;
+          cp_async16(dst, xh + o, nbytes);
+          cp_async16(dst + A_TILE_BYTES, xl + o, nbytes);
+        }
+        // arrive on `full` when this thread's copies have landed; the thread itself moves on to its next K block.
+        // (The copies are generic-proxy writes: the issuer runs fence.proxy.async after its wait on `full`.)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
+        if (t == 0) trace(gk, 3);
+        c += NGROUP * KB;
+        while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
       }
     }
   } else if (warp >= DRAIN_WARP0) {
@@ -952,6 +1080,129 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
 }
 
 // ============================================================================================
+// weight-gradient kernel, pre-split operands (p.x_lo and p.dy_lo given): same tiling, layouts and epilogue as
+// wgrad_tc_kernel, but both operands and their TF32 remainders go global -> shared with cp.async (no register
+// pass: the register-path producers ran ~850 SASS instructions per thread and K block), completion is signalled
+// straight to `full` by cp.async.mbarrier.arrive, and the row entries of the next K block are fetched while the
+// current one is in flight.
+// ============================================================================================
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_wgrad_params p, int kb_per_split) {
+  using S = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN;
+  const int j0 = blockIdx.y * TM;
+  const int Kt = p.r * p.s * p.cin;                         // rows of D
+  const int nkb_total = (p.m + KB - 1) / KB;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  int kb_end = kb_begin + kb_per_split;
+  if (kb_end > nkb_total) kb_end = nkb_total;
+  const int nkb = kb_end - kb_begin;                        // >= 1 by construction of the grid
+
+  PipeBars pb = setup_pipeline<BN>(sm, warp, lane, NPROD);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+
+  if (warp >= MMA_WARP) {
+    if (elect_one()) {
+      Issuer is = issuer_init<BN>(warp - MMA_WARP);
+      mma_loop<BN, true>(sm, pb, tmem_base, nkb, is);
+    }
+    __syncwarp();
+  } else if (warp < DRAIN_WARP0) {
+    const int group = warp >> 2;
+    const int t = tid & 127;
+    const int mc = t & 31;                                  // 16-byte chunk (4 channels) of the 128-channel tile row
+    const int ps = t >> 5;                                  // pixel sub-index 0..3
+    const uint32_t atom_off = (mc >> 3) * 4096;             // channel atom
+    const int cj = mc & 7;
+    // A side: this thread's 4 channels j..j+3 of D's row index = (tap, c)
+    const int j = j0 + mc * 4;
+    const bool jvalid = j < Kt;
+    int tap = 0, c = 0, tr = 0, ts = 0;
+    if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
+    // B side: 4 output channels n..n+3 (ragged channel counts: only the valid bytes are copied, the rest is zero)
+    const int n = n0 + mc * 4;
+    const bool bthread = mc * 4 < BN && n < p.cout;
+    const uint32_t bbytes = bthread ? (p.cout - n >= 4 ? 16u : 4u * (uint32_t)(p.cout - n)) : 0u;
+    const float* xh = p.x + c;
+    const float* xl = p.x_lo + c;
+    const float* yh = p.dy + (bthread ? n : 0);
+    const float* yl = p.dy_lo + (bthread ? n : 0);
+    const int4* rows = reinterpret_cast<const int4*>(p.rows);
+    int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 64;       // [2][32] entries per group
+    const uint32_t tiles0 = smem_u32(sm);
+    // prologue: entries of this group's first K block
+    if (group < nkb) {
+      if (t < 32) {
+        int4 e = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
+        const int pix = (kb_begin + group) * KB + t;
+        if (pix < p.m) e = __ldg(rows + pix);
+        ent[t] = e;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+    }
+    int it = 0;
+    for (int i = group; i < nkb; i += NGROUP, ++it) {
+      const int s = i % S::STAGES;
+      const int4* eb = ent + (it & 1) * 32;
+      int4 e_next = make_int4(0, 0, 0, 0);                   // entries of my next K block: in flight during this one
+      const bool has_next = i + NGROUP < nkb;
+      if (has_next && t < 32) {
+        const int pix = (kb_begin + i + NGROUP) * KB + t;
+        if (pix < p.m) e_next = __ldg(rows + pix);
+      }
+      mbar_wait(pb.empty(s), ((i / S::STAGES) & 1) ^ 1, 5000 + i);
+      const uint32_t a_hi = tiles0 + s * S::STAGE_BYTES;
+      const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int pixel = q * 4 + ps;                        // 0..31 within the K block
+        const int4 e = eb[pixel];
+        const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+        const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+        const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+        const int r4 = pixel & 3;
+        const uint32_t off = atom_off + (pixel >> 2) * 512 + r4 * 128 + ((((cj >> 1) ^ r4) << 1) | (cj & 1)) * 16;
+        const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
+        cp_async16(a_hi + off, xh + ao, oka ? 16u : 0u);
+        cp_async16(a_hi + A_TILE_BYTES + off, xl + ao, oka ? 16u : 0u);
+        if (mc * 4 < BN) {
+          const bool okb = hin > 0;
+          const int64_t bo = okb ? (int64_t)e.w : 0;
+          cp_async16(b_hi + off, yh + bo, okb ? bbytes : 0u);
+          cp_async16(b_hi + S::B_TILE_BYTES + off, yl + bo, okb ? bbytes : 0u);
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
+      if (has_next) {
+        if (t < 32) ent[((it + 1) & 1) * 32 + t] = e_next;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      }
+    }
+  } else {
+    // drain + epilogue: lanes own consecutive j => coalesced reductions into dw[n][j]
+    const int dw = warp - DRAIN_WARP0;
+    const int quadrant = dw & 3, half = dw >> 2;
+    float acc[BN / 2];
+    int gchunk = 0;
+    drain_loop<BN>(pb, tmem_base, nkb, 0, quadrant, half, acc, gchunk);
+    const int j = j0 + quadrant * 32 + lane;
+    if (j < Kt) {
+#pragma unroll
+      for (int q = 0; q < BN / 2; ++q) {
+        const int nn = n0 + half * (BN / 2) + q;
+        if (nn < p.cout) atomicAdd(p.dw + (int64_t)nn * Kt + j, acc[q]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ============================================================================================
 // SIMT check kernels (tests only): the same gather semantics in plain fp32 FMAs, one thread
 // per output element.  Independent of every tcgen05 / smem-layout assumption above.
 // ============================================================================================
@@ -1076,6 +1327,24 @@ static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
 }
 
 template <int BN>
+static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+    attr_done = true;
+  }
+  CUtensorMap tm_hi, tm_lo;
+  const int K = p.r * p.s * p.cin;
+  if (int rc = make_weight_map(&tm_hi, p.w, p.cout, K, BN)) return rc;
+  if (int rc = make_weight_map(&tm_lo, p.w_lo, p.cout, K, BN)) return rc;
+  const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
+  conv_tc_async_kernel<BN><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
+  return check_launch("zsg_conv_fwd");
+}
+
+template <int BN>
 static int launch_conv_pro(const zsg_conv_params& p, cudaStream_t st) {
   switch ((p.in_scale ? 2 : 0) | (p.in_relu ? 1 : 0)) {
     case 0: return launch_conv<BN, 0>(p, st);
@@ -1085,11 +1354,12 @@ static int launch_conv_pro(const zsg_conv_params& p, cudaStream_t st) {
   }
 }
 
-template <int BN>
+template <int BN, bool ASYNC>
 static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
   static bool attr_done = false;
+  auto kern = ASYNC ? wgrad_tc_async_kernel<BN> : wgrad_tc_kernel<BN>;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
     if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
   }
@@ -1107,7 +1377,7 @@ static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
   const int per = (nkb + split - 1) / split;
   split = (nkb + per - 1) / per;                            // no empty splits
   dim3 grid((p.cout + BN - 1) / BN, (Kt + TM - 1) / TM, split);
-  wgrad_tc_kernel<BN><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per);
+  kern<<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per);
   return check_launch("zsg_conv_wgrad");
 }
 
@@ -1138,6 +1408,12 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
     return check_launch("zsg_conv_fwd(simt)");
   }
   if (!zsg_device_supported()) { set_error("zsg_conv_fwd: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
+  if (p.x_lo) {
+    ZSG_REQUIRE(p.w_lo, "zsg_conv_fwd: x_lo needs pre-split weights (w_lo)");
+    ZSG_REQUIRE(!p.in_scale && !p.in_relu, "zsg_conv_fwd: x_lo excludes the on-load affine / ReLU (apply them in zsg_split_act)");
+    ZSG_REQUIRE((((uintptr_t)p.x_lo | (uintptr_t)p.w_lo) & 15) == 0, "zsg_conv_fwd: x_lo and w_lo must be 16-byte aligned");
+    return p.cout <= 64 ? launch_conv_async<64>(p, st) : launch_conv_async<128>(p, st);
+  }
   if (p.w_lo) {
     ZSG_REQUIRE(((uintptr_t)p.w_lo & 15) == 0, "zsg_conv_fwd: w_lo must be 16-byte aligned");
     return p.cout <= 64 ? launch_conv_pro<64>(p, st) : launch_conv_pro<128>(p, st);
@@ -1159,5 +1435,13 @@ extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
     return check_launch("zsg_conv_wgrad(simt)");
   }
   if (!zsg_device_supported()) { set_error("zsg_conv_wgrad: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
-  return p.cout <= 64 ? launch_wgrad<64>(p, st) : launch_wgrad<128>(p, st);
+  if (p.x_lo || p.dy_lo) {
+    ZSG_REQUIRE(p.x_lo && p.dy_lo, "zsg_conv_wgrad: x_lo and dy_lo go together");
+    ZSG_REQUIRE(!p.in_scale && !p.in_relu, "zsg_conv_wgrad: pre-split operands exclude the on-load affine / ReLU");
+    ZSG_REQUIRE(p.cin % 4 == 0, "zsg_conv_wgrad: cin must be a multiple of 4");
+    ZSG_REQUIRE((((uintptr_t)p.x | (uintptr_t)p.x_lo | (uintptr_t)p.dy | (uintptr_t)p.dy_lo) & 15) == 0,
+                "zsg_conv_wgrad: operands must be 16-byte aligned");
+    return p.cout <= 64 ? launch_wgrad<64, true>(p, st) : launch_wgrad<128, true>(p, st);
+  }
+  return p.cout <= 64 ? launch_wgrad<64, false>(p, st) : launch_wgrad<128, false>(p, st);
 }

@@ -179,6 +179,27 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   }
 }
 
+// operand preparation for the cp.async GEMM paths: z = relu?(x * scale + shift), lo = z - trunc_tf32(z)
+__global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int relu, float* __restrict__ z,
+                                                        float* __restrict__ lo, int64_t n4, int c4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = ld4(x + i * 4);
+    if (scale) {
+      const int c = (int)(i % c4) * 4;
+      v = fma4(v, ld4(scale + c), ld4(shift + c));
+    }
+    if (relu) v = relu4(v);
+    if (z) st4(z + i * 4, v);
+    float4 l;
+    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    st4(lo + i * 4, l);
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
@@ -568,6 +589,17 @@ extern "C" int zsg_bn_apply(const float* x, const float* scale, const float* shi
   bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, n4,
                                                                      c / 4);
   return check_launch("zsg_bn_apply");
+}
+
+extern "C" int zsg_split_act(const float* x, const float* scale, const float* shift, int relu, float* z, float* lo,
+                             int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && lo && c > 0 && c % 4 == 0, "zsg_split_act: bad arguments");
+  ZSG_REQUIRE(!scale == !shift, "zsg_split_act: scale and shift go together");
+  ZSG_REQUIRE(z || (!scale && !relu), "zsg_split_act: a prologue needs an output tensor z");
+  if (rows <= 0) return ZSG_OK;
+  const int64_t n4 = rows * (c / 4);
+  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, z, lo, n4, c / 4);
+  return check_launch("zsg_split_act");
 }
 
 extern "C" int zsg_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* invstd,

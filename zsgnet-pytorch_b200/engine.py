@@ -85,6 +85,7 @@ class Engine:
     def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC):
         self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
         self._rows_cache = {}
+        self._operand_cache, self._bwd_lo = {}, {}
         self._f64_pool, self._f64_used = torch.zeros(1 << 18, dtype=torch.float64, device=device), 0
         self.bns = []
         self.fwd_train, self.fwd_eval_bn, self.fwd, self.bwd, self.prep_bwd = [], [], [], [], []
@@ -126,6 +127,35 @@ class Engine:
         o, n = self.store.offsets[wname], self.store.numel(wname)
         return self.arena_hi[o:o + n], self.arena_lo[o:o + n]
 
+    # ------------------------------------------------------------------ GEMM operand images
+    # Every tensor that feeds an implicit GEMM is given its TF32 remainder image (`lo`) by one elementwise pass
+    # (zsg_split_act); when the consumer needs a BatchNorm affine / ReLU on load, the same pass materialises
+    # z = relu(x * scale + shift).  The GEMM kernels then move (z, lo) global -> shared with cp.async, no register
+    # pass (csrc/conv_tc.cu: conv_tc_async_kernel, wgrad_tc_async_kernel).
+    def fwd_operand(self, x, nrows, c, pro=None, relu=False):
+        """(z, lo) of a forward conv input; the split launch is appended to the forward program once per tensor."""
+        key = (x.data_ptr(), nrows, c, id(pro), bool(relu))
+        if key not in self._operand_cache:
+            need_z = pro is not None or relu
+            z = self.buf(nrows, c) if need_z else x
+            lo = self.buf(nrows, c)
+            sc, sh = (pro.scale, pro.shift) if pro is not None else (None, None)
+            self.fwd.append(("fn", lambda: ops.split_act(x, lo, nrows, c, scale=sc, shift=sh, relu=relu,
+                                                         z=z if need_z else None)))
+            self._operand_cache[key] = (z, lo)
+        return self._operand_cache[key]
+
+    def bwd_operand(self, dy, nrows, c):
+        """lo image of a gradient tensor; appends the split launch to the backward program (call it right after
+        the kernel that produced dy -- scratch buffers are reused, so nothing is cached across calls)."""
+        n = nrows * c
+        key = dy.data_ptr()
+        if key not in self._bwd_lo or self._bwd_lo[key].numel() < n:
+            self._bwd_lo[key] = self.buf(n)
+        lo = self._bwd_lo[key][:n]
+        self.bwd.append(lambda: ops.split_act(dy, lo, nrows, c))
+        return lo
+
     def rows(self, kind, *key):
         k = (kind,) + key
         if k not in self._rows_cache:
@@ -159,21 +189,23 @@ class Engine:
             w_hi, w_lo = self.arena_split_views(wname)
         else:
             w, w_hi, w_lo = w                                # a (w, hi, lo) triple from the pool
-        op = ConvOp(x, w_hi, y, rows, self.B * hout * wout, cin, cout, k, k, in_scale=pro.scale if pro else None,
-                    in_shift=pro.shift if pro else None, in_relu=in_relu, bias=bias, out_relu=out_relu, impl=self.impl,
-                    w_lo=w_lo)
+        xz, x_lo = self.fwd_operand(x, self.B * hin * win, cin, pro=pro, relu=in_relu)
+        op = ConvOp(xz, w_hi, y, rows, self.B * hout * wout, cin, cout, k, k, bias=bias, out_relu=out_relu, impl=self.impl,
+                    w_lo=w_lo, x_lo=x_lo)
         self.fwd.append(("op", op))
-        return dict(wname=wname, x=x, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
+        return dict(wname=wname, x=x, xz=xz, x_lo=x_lo, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
                     hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w)   # w: fp32 weights (for dgrad prep)
 
-    def conv_wgrad(self, L, dy, dw=None):
+    def conv_wgrad(self, L, dy, dy_lo, dw=None):
         dw = self.store.grad_flat(L["wname"]) if dw is None else dw
-        pro = L["pro"]
-        self.bwd.append(WgradOp(L["x"], dy, dw, L["rows"], self.B * L["hout"] * L["wout"], L["cin"], L["cout"], L["k"],
-                                L["k"], in_scale=pro.scale if pro else None, in_shift=pro.shift if pro else None,
-                                in_relu=L["in_relu"], impl=self.impl))
+        self.bwd.append(WgradOp(L["xz"], dy, dw, L["rows"], self.B * L["hout"] * L["wout"], L["cin"], L["cout"], L["k"],
+                                L["k"], impl=self.impl, x_lo=L["x_lo"], dy_lo=dy_lo))
 
-    def conv_dgrad(self, L, dy, dx, out_mask=None, residual=None, accumulate=False):
+    def grad_operand(self, L, dy):
+        """lo image of the output gradient of conv L (shared by its wgrad and dgrad)."""
+        return self.bwd_operand(dy, self.B * L["hout"] * L["wout"], L["cout"])
+
+    def conv_dgrad(self, L, dy, dy_lo, dx, out_mask=None, residual=None, accumulate=False):
         k, cin, cout = L["k"], L["cin"], L["cout"]
         wt, wt_hi, wt_lo = self.pool_alloc(cin * k * k * cout)
         w = L["w"]
@@ -181,7 +213,7 @@ class Engine:
         rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, L["stride"], L["pad"])
         self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=L["stride"],
                                out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl,
-                               w_lo=wt_lo))
+                               w_lo=wt_lo, x_lo=dy_lo))
 
     def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None):
         def run():
@@ -224,7 +256,7 @@ class Engine:
             self.bwd.append(lambda: ops.maxpool_bn_relu_bwd(pool_arg, g_x0, da_stem, B, 150, 150, 64, 75, 75))
             self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1)
             self.bwd.append(lambda: dw1p.zero_())
-            self.conv_wgrad(Lstem, da_stem, dw=dw1p)
+            self.conv_wgrad(Lstem, da_stem, self.grad_operand(Lstem, da_stem), dw=dw1p)
             self.bwd.append(lambda: ops.pad_channels(dw1p, g1, 64 * 49, 4, 3))
         bwd_stages.append(stem_bwd)
 
@@ -276,21 +308,25 @@ class Engine:
                 ro, ri, w4, w = L["ro"], L["ri"], 4 * L["width"], L["width"]
                 dz, dr3, da2, da1 = sA[:ro * w4], sB[:ro * w4], sC[:ro * w], sD[:ri * w]
                 self.bn_backward(L["bnC"], L["g_out"], L["r3"], dr3, mask_mode=2, act_out=L["out"], dz_out=dz)
-                self.conv_wgrad(L["Lc"], dr3)
-                self.conv_dgrad(L["Lc"], dr3, da2)
+                lo3 = self.grad_operand(L["Lc"], dr3)
+                self.conv_wgrad(L["Lc"], dr3, lo3)
+                self.conv_dgrad(L["Lc"], dr3, lo3, da2)
                 self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1)
-                self.conv_wgrad(L["Lb"], da2)
-                self.conv_dgrad(L["Lb"], da2, da1)
+                lo2 = self.grad_operand(L["Lb"], da2)
+                self.conv_wgrad(L["Lb"], da2, lo2)
+                self.conv_dgrad(L["Lb"], da2, lo2, da1)
                 self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1)
-                self.conv_wgrad(L["La"], da1)
+                lo1 = self.grad_operand(L["La"], da1)
+                self.conv_wgrad(L["La"], da1, lo1)
                 if L["Ld"] is not None:
                     drd = sB[:ro * w4]
                     self.bn_backward(L["bnD"], dz, L["rd"], drd, mask_mode=0)
-                    self.conv_wgrad(L["Ld"], drd)
-                    self.conv_dgrad(L["Ld"], drd, L["g_in"], accumulate=L["acc_in"])
-                    self.conv_dgrad(L["La"], da1, L["g_in"], accumulate=True)
+                    lod = self.grad_operand(L["Ld"], drd)
+                    self.conv_wgrad(L["Ld"], drd, lod)
+                    self.conv_dgrad(L["Ld"], drd, lod, L["g_in"], accumulate=L["acc_in"])
+                    self.conv_dgrad(L["La"], da1, lo1, L["g_in"], accumulate=True)
                 else:
-                    self.conv_dgrad(L["La"], da1, L["g_in"], residual=dz, accumulate=L["acc_in"])
+                    self.conv_dgrad(L["La"], da1, lo1, L["g_in"], residual=dz, accumulate=L["acc_in"])
             return emit
         for k in range(len(blocks)):
             bwd_stages.append(block_bwd(k))
@@ -330,18 +366,22 @@ class Engine:
             self.bwd.append(lambda: ops.colsum(dy, gb, rows, 256))
 
         def fpn_bwd():
+            def layer(name, L, dy, rows_, dx, **kw):
+                gbias(name, dy, rows_)
+                lo = self.grad_operand(L, dy)
+                self.conv_wgrad(L, dy, lo)
+                self.conv_dgrad(L, dy, lo, dx, **kw)
             self.bwd.append(lambda: ops.avgpool_bwd(dfl[5], dfl[4], B, 9, 256))
-            gbias("P7_2", dfl[4], B * 9); self.conv_wgrad(L7, dfl[4])
-            self.conv_dgrad(L7, dfl[4], dfl[3], out_mask=fl[3], accumulate=True)
-            gbias("P6", dfl[3], B * 25); self.conv_wgrad(L6, dfl[3]); self.conv_dgrad(L6, dfl[3], g_c5)
-            gbias("P3_2", dfl[0], B * 1444); self.conv_wgrad(L32, dfl[0]); self.conv_dgrad(L32, dfl[0], dp31)
-            gbias("P3_1", dp31, B * 1444); self.conv_wgrad(L31, dp31); self.conv_dgrad(L31, dp31, g_c3)
-            gbias("P4_2", dfl[1], B * 361); self.conv_wgrad(L42, dfl[1]); self.conv_dgrad(L42, dfl[1], dp41)
+            layer("P7_2", L7, dfl[4], B * 9, dfl[3], out_mask=fl[3], accumulate=True)
+            layer("P6", L6, dfl[3], B * 25, g_c5)
+            layer("P3_2", L32, dfl[0], B * 1444, dp31)
+            layer("P3_1", L31, dp31, B * 1444, g_c3)
+            layer("P4_2", L42, dfl[1], B * 361, dp41)
             self.bwd.append(lambda: ops.upsample_add_bwd(dp31, dp41, up[(19, 38)], up[(19, 38)], B, 38, 38, 19, 19, 256))
-            gbias("P4_1", dp41, B * 361); self.conv_wgrad(L41, dp41); self.conv_dgrad(L41, dp41, g_c4)
-            gbias("P5_2", dfl[2], B * 100); self.conv_wgrad(L52, dfl[2]); self.conv_dgrad(L52, dfl[2], dp51)
+            layer("P4_1", L41, dp41, B * 361, g_c4)
+            layer("P5_2", L52, dfl[2], B * 100, dp51)
             self.bwd.append(lambda: ops.upsample_add_bwd(dp41, dp51, up[(10, 19)], up[(10, 19)], B, 19, 19, 10, 10, 256))
-            gbias("P5_1", dp51, B * 100); self.conv_wgrad(L51, dp51); self.conv_dgrad(L51, dp51, g_c5, accumulate=True)
+            layer("P5_1", L51, dp51, B * 100, g_c5, accumulate=True)
         bwd_stages.append(fpn_bwd)
 
         # ---------------- bi-LSTM query encoder (mdl.py:296-336)
@@ -360,7 +400,8 @@ class Engine:
         rows_ih, rows_hh = r11(B * T, E, G), r11(B * T, Hh, G)
         rows_ihr, rows_hhr = r11(B, E, G), r11(B, Hh, G)
         wih_hi, wih_lo = self.arena_split_views("lstm.weight_ih_l0")
-        self.fwd.append(("op", ConvOp(qv, wih_hi, gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl, w_lo=wih_lo)))
+        _, qv_lo = self.fwd_operand(qv, B * T, E)
+        self.fwd.append(("op", ConvOp(qv, wih_hi, gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl, w_lo=wih_lo, x_lo=qv_lo)))
         self.fwd.append(("fn", lambda: ops.weight_transpose_flip(P("weight_hh_l0"), whh_t, G, 1, 1, Hh)))
         self.fwd.append(("fn", lambda: ops.lstm_fwd_dir(gx, whh_t, P("bias_ih_l0"), P("bias_hh_l0"), h0c0[0], h0c0[1],
                                                         lens, B, T, gates, cs, hprev, lang)))
@@ -419,16 +460,20 @@ class Engine:
         rows_f520, rows_f256 = head_rows("fwd", CP, 256), head_rows("fwd", 256, 256)
         rows_last, rows_f48 = head_rows("fwd", 256, 45, scatter=True), head_rows("fwd", 256, 48)
         rows_d520, rows_d256, rows_d48 = head_rows("dgrad", CP, 256), head_rows("dgrad", 256, 256), head_rows("dgrad", 256, 48)
+        _, fused_lo = self.fwd_operand(fused, M, CP)
         self.fwd.append(("op", ConvOp(fused, w0p_t[1], hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
-                                      impl=self.impl, w_lo=w0p_t[2])))
+                                      impl=self.impl, w_lo=w0p_t[2], x_lo=fused_lo)))
+        hs_lo = []
         for i in range(1, 5):
             wh, wl = self.arena_split_views(f"att_reg_box.{i}.0.weight")
+            hs_lo.append(self.fwd_operand(hs[i - 1], M, 256)[1])
             self.fwd.append(("op", ConvOp(hs[i - 1], wh, hs[i], rows_f256, M, 256, 256, 3, 3, bias=hb(i), out_relu=True,
-                                          impl=self.impl, w_lo=wl)))
+                                          impl=self.impl, w_lo=wl, x_lo=hs_lo[-1])))
+        hs_lo.append(self.fwd_operand(hs[4], M, 256)[1])
         w5 = st.flat("att_reg_box.5.weight")
         w5h, w5l = self.arena_split_views("att_reg_box.5.weight")
         self.fwd.append(("op", ConvOp(hs[4], w5h, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
-                                      impl=self.impl, w_lo=w5l)))
+                                      impl=self.impl, w_lo=w5l, x_lo=hs_lo[4])))
         self.d_out = self.buf(B, A, 5)
         self.dbg = dict(x0=x0, c1=c1, c3=c3, c4=c4, c5=c5, feat=feat, lang=lang, hs=hs, fused=fused, lvl_off=lvl_off,
                         blocks=blocks)
@@ -447,27 +492,31 @@ class Engine:
             self.bwd.append(lambda: ops.gather_rows(d_out, rows_last, dy5, M, 45, 48))
             self.bwd.append(lambda: ops.colsum(dy5, tmp48, M, 48))
             self.bwd.append(lambda: st.grad_flat("att_reg_box.5.bias").copy_(tmp48[:45]))
+            dy5_lo = self.bwd_operand(dy5, M, 48)
             self.bwd.append(WgradOp(hs[4], dy5, st.grad_flat("att_reg_box.5.weight"), rows_f48, M, 256, 45, 3, 3,
-                                    impl=self.impl))
+                                    impl=self.impl, x_lo=hs_lo[4], dy_lo=dy5_lo))
             self.bwd.append(ConvOp(dy5, wt5p_t[1], dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl,
-                                   w_lo=wt5p_t[2]))
+                                   w_lo=wt5p_t[2], x_lo=dy5_lo))
             for i in range(4, 0, -1):
                 wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i][0]
                 self.prep_bwd.append(lambda wi=wi, wti=wti: ops.weight_transpose_flip(wi, wti, 256, 3, 3, 256))
                 gb = st.grad_flat(f"att_reg_box.{i}.0.bias")
                 self.bwd.append(lambda i=i, gb=gb: ops.colsum(dhs[i], gb, M, 256))
+                dlo = self.bwd_operand(dhs[i], M, 256)
                 self.bwd.append(WgradOp(hs[i - 1], dhs[i], st.grad_flat(f"att_reg_box.{i}.0.weight"), rows_f256, M, 256,
-                                        256, 3, 3, impl=self.impl))
+                                        256, 3, 3, impl=self.impl, x_lo=hs_lo[i - 1], dy_lo=dlo))
                 self.bwd.append(ConvOp(dhs[i], wts[i][1], dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
-                                       impl=self.impl, w_lo=wts[i][2]))
+                                       impl=self.impl, w_lo=wts[i][2], x_lo=dlo))
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
             gb0 = st.grad_flat("att_reg_box.0.0.bias")
             self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
             self.bwd.append(lambda: dw0p.zero_())
-            self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl))
+            d0lo = self.bwd_operand(dhs[0], M, 256)
+            self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl, x_lo=fused_lo, dy_lo=d0lo))
             g0 = st.grad_flat("att_reg_box.0.0.weight")
             self.bwd.append(lambda: ops.pad_channels(dw0p, g0, 256 * 9, CP, spec.FUSED_C))
-            self.bwd.append(ConvOp(dhs[0], wt0_t[1], dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0_t[2]))
+            self.bwd.append(ConvOp(dhs[0], wt0_t[1], dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0_t[2],
+                                   x_lo=d0lo))
             self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
         bwd_stages.append(head_bwd)
 

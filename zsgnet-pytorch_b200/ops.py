@@ -44,11 +44,12 @@ class ConvOp:
     fixed because the engine's buffers are static)."""
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
-                 bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None):
-        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual)
+                 bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
+                 x_lo=None):
+        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo)
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl)
+                            impl, ptr(x_lo))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
         self.kernel = "conv_tc_kernel"
@@ -61,11 +62,11 @@ class ConvOp:
 
 class WgradOp:
     def __init__(self, x, dy, dw, rows, m, cin, cout, r, s, in_scale=None, in_shift=None, in_relu=False, split_k=0,
-                 impl=IMPL_TC):
-        self.keep = (x, dy, dw, rows, in_scale, in_shift)
+                 impl=IMPL_TC, x_lo=None, dy_lo=None):
+        self.keep = (x, dy, dw, rows, in_scale, in_shift, x_lo, dy_lo)
         self.dw = dw
         self.p = WgradParams(ptr(x), ptr(dy), ptr(dw), ptr(rows), m, cin, cout, r, s, ptr(in_scale), ptr(in_shift),
-                             int(in_relu), split_k, impl)
+                             int(in_relu), split_k, impl, ptr(x_lo), ptr(dy_lo))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin
         self.kernel = "wgrad_tc_kernel"
@@ -78,6 +79,11 @@ class WgradOp:
 
 def weight_transpose_flip(w, wt, cout, r, s, cin):
     call("zsg_weight_transpose_flip", ptr(w), ptr(wt), cout, r, s, cin, stream())
+
+
+def split_act(x, lo, rows, c, scale=None, shift=None, relu=False, z=None):
+    """lo = remainder of (z or x) after TF32 truncation; z = relu?(x * scale + shift) when a prologue is given."""
+    call("zsg_split_act", ptr(x), ptr(scale), ptr(shift), int(relu), ptr(z), ptr(lo), rows, c, stream())
 
 
 def split_tf32(w, hi, lo, n):
