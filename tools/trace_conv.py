@@ -8,7 +8,7 @@ import torch
 import zsg_b200
 from zsg_b200 import ops, geometry, _lib
 
-def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False):
+def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False, impl=0):
     x = torch.randn(B, H, H, cin, device="cuda")
     w = torch.randn(cout, k, k, cin, device="cuda") * 0.05
     hi, lo = torch.empty_like(w), torch.empty_like(w)
@@ -21,7 +21,7 @@ def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False):
     if use_async:
         x_lo = torch.empty_like(x)
         ops.split_act(x, x_lo, M, cin)
-        op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, x_lo=x_lo)
+        op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, x_lo=x_lo, impl=impl)
     else:
         op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, in_scale=sc, in_shift=sh, in_relu=pro)
     for _ in range(2): op()
@@ -41,10 +41,19 @@ def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False):
         d = (r[11] - prev) if prev is not None else 0
         prev = r[11]
         print(f"{g:4d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | {r[8]:7d} {r[9]:7d} {r[10]:7d} {r[11]:7d} | {d:5d}   emptywait {r[1]-r[0]:5d} sts {r[2]-r[1]:5d}  fullwait {r[9]-r[8]:5d} tok {r[10]-r[9]:4d} issue {r[11]-r[10]:4d}  full->arrive lag {r[9]-r[3]:5d}")
+    print("drain warp 8: tile-first-gk | before acc_full wait, after TMEM drain, after epilogue stores | drain  epilogue  tile period")
+    prevd = None
+    for g in range(40, min(nblk, 76)):
+        r = t[g]
+        if r[12] == 0 and r[13] == 0: continue
+        print(f"{g:4d} | {r[12]:8d} {r[13]:8d} {r[14]:8d} | {r[13]-r[12]:6d} {r[14]-r[13]:6d} {(r[12]-prevd) if prevd is not None else 0:6d}")
+        prevd = r[12]
     per = (t[100, 11] - t[20, 11]) / 80.0
     print(f"average issue period over K blocks 20..100: {per:.0f} cycles (floor 768)")
 
-if "async" in sys.argv:
+if "small" in sys.argv:
+    run(64, 64, 75, 256, 1, "1x1 64->256 M=360000 cp.async path", use_async=True, impl=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+elif "async" in sys.argv:
     run(64, 256, 44, 256, 3, "3x3 256->256 cp.async path", use_async=True)
 else:
     run(64, 256, 44, 256, 3, "3x3 256->256 no prologue")

@@ -45,12 +45,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.  Waiting warps back off with
+// nanosleep: 18 warps share 4 schedulers and up to 10 of them wait at any time; spinning on try_wait took the issue
+// slots of the warps that had work (the epilogue of a tile ran at 10 cycles per instruction).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
     if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
       printf("zsg conv: mbarrier wait timed out (block %d,%d,%d thread %d, wait site %d, parity %u)\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, tag, parity);
@@ -382,6 +385,22 @@ __device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_bas
   }
 }
 
+// ragged rows (channel count or row offset not a multiple of 4: the [B, A, 5] head output): scalar, out of line
+__device__ __noinline__ void epilogue_store_ragged(const zsg_conv_params& p, int off_r, int n, float4 v4) {
+  const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  float* yrow = p.y + (int64_t)off_r + n;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    if (n + q >= p.cout) break;
+    float u = v[q];
+    if (p.out_mask && !(p.out_mask[(int64_t)off_r + n + q] > 0.f)) u = 0.f;
+    if (p.residual) u += p.residual[(int64_t)off_r + n + q];
+    if (p.accumulate) u += yrow[q];
+    if (p.out_relu) u = fmaxf(u, 0.f);
+    yrow[q] = u;
+  }
+}
+
 // drain + epilogue warps of the forward / data-gradient kernels
 template <int BN>
 __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t* sm, const PipeBars& pb, uint32_t tmem_base,
@@ -399,7 +418,10 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
     const bool row_ok = m0 + row < p.m;
     if (row_ok) out_off = __ldg(&p.rows[m0 + row].out);          // prefetched under the drain
     float acc[BN / 2];
+    if (dw == 0 && lane == 0) trace(gkb0, 12);
     drain_loop<BN>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
+    if (dw == 0 && lane == 0) trace(gkb0, 13);
+    const int gkb_tile = gkb0;
     gkb0 += nkb;
     // Epilogue through a per-warp smem slab: a thread owns one row of the accumulator, but global memory wants
     // lanes along channels.  16 columns at a time are transposed through smem (row stride 20 floats keeps the
@@ -421,45 +443,40 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         if (n + 3 < p.cout) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
         else { bias4.x = __ldg(p.bias + n); if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1); if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2); }
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
+#pragma unroll 1                                    // (fully unrolled, the epilogue alone was > 100 KB of code and ran
+      for (int i = 0; i < 4; ++i) {                       //  out of the instruction cache: 8.5 k cycles per 64 KB tile)
         const int r = i * 8 + rsel;
         const int off_r = __shfl_sync(0xffffffffu, out_off, r);
         const bool ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r) != 0;
         if (!ok_r || n >= p.cout) continue;
         float4 v4 = *reinterpret_cast<const float4*>(stg + r * 20 + c4);
-        float v[4] = {v4.x + bias4.x, v4.y + bias4.y, v4.z + bias4.z, v4.w + bias4.w};
+        v4.x += bias4.x; v4.y += bias4.y; v4.z += bias4.z; v4.w += bias4.w;
         float* yrow = p.y + (int64_t)off_r + n;
         const bool vec = ((p.cout & 3) == 0) && ((off_r & 3) == 0) && (n + 3 < p.cout);
         if (vec) {
           if (p.out_mask) {
             const float4 m = __ldg(reinterpret_cast<const float4*>(p.out_mask + (int64_t)off_r + n));
-            if (!(m.x > 0.f)) v[0] = 0.f; if (!(m.y > 0.f)) v[1] = 0.f; if (!(m.z > 0.f)) v[2] = 0.f; if (!(m.w > 0.f)) v[3] = 0.f;
+            if (!(m.x > 0.f)) v4.x = 0.f;
+            if (!(m.y > 0.f)) v4.y = 0.f;
+            if (!(m.z > 0.f)) v4.z = 0.f;
+            if (!(m.w > 0.f)) v4.w = 0.f;
           }
           if (p.residual) {
             const float4 q = *reinterpret_cast<const float4*>(p.residual + (int64_t)off_r + n);
-            v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+            v4.x += q.x; v4.y += q.y; v4.z += q.z; v4.w += q.w;
           }
           if (p.accumulate) {
             const float4 q = *reinterpret_cast<const float4*>(yrow);
-            v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+            v4.x += q.x; v4.y += q.y; v4.z += q.z; v4.w += q.w;
           }
-          if (p.out_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-          *reinterpret_cast<float4*>(yrow) = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.out_relu) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
+          if (!(ablate & 16)) *reinterpret_cast<float4*>(yrow) = v4;
         } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (n + q >= p.cout) break;
-            float u = v[q];
-            if (p.out_mask && !(p.out_mask[(int64_t)off_r + n + q] > 0.f)) u = 0.f;
-            if (p.residual) u += p.residual[(int64_t)off_r + n + q];
-            if (p.accumulate) u += yrow[q];
-            if (p.out_relu) u = fmaxf(u, 0.f);
-            yrow[q] = u;
-          }
+          epilogue_store_ragged(p, off_r, n, v4);
         }
       }
     }
+    if (dw == 0 && lane == 0) trace(gkb_tile, 14);
   }
 }
 
@@ -664,6 +681,13 @@ __device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
 }
 
 constexpr int FULL_COUNT_TMA = NPROD / 32 + 1;
+
+// Register re-balancing (cp.async kernels): the producers only form addresses, the drain warps hold 64 accumulators
+// per thread plus the epilogue's state.  The carve-out leaves ~6 KB of L1, so a spilled register costs an L2 round
+// trip: with the launch-time 96 registers the epilogue loop reloaded two spilled values per iteration and took
+// 7.5 k cycles per tile; producers give registers up, drain warps take them.
+__device__ __forceinline__ void regs_release_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 64;"); }
+__device__ __forceinline__ void regs_take_drain() { asm volatile("setmaxnreg.inc.sync.aligned.u32 128;"); }
      // one elected arrive per producer warp + the expect_tx arrive
 
 template <int BN, int PRO>
@@ -851,8 +875,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) mma_loop<BN>(sm, pb, tmem_base, nkb, is, false, ablate);
     }
     __syncwarp();
-  } else if (warp < DRAIN_WARP0 && !(ablate & 1)) {
+  } else if (warp < DRAIN_WARP0) {
     // ------------------------------ producers ------------------------------
+    regs_release_producer();
+    if (!(ablate & 1)) {
     const int group = warp >> 2;
     const int t = tid & 127;
     const int chunk = t & 7;
@@ -928,7 +954,9 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
         while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
       }
     }
+    }
   } else if (warp >= DRAIN_WARP0) {
+    regs_take_drain();
     conv_epilogue<BN>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
   }
   tc_fence_before();
@@ -1111,6 +1139,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
     }
     __syncwarp();
   } else if (warp < DRAIN_WARP0) {
+    regs_release_producer();
     const int group = warp >> 2;
     const int t = tid & 127;
     const int mc = t & 31;                                  // 16-byte chunk (4 channels) of the 128-channel tile row
@@ -1183,6 +1212,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
     }
   } else {
     // drain + epilogue: lanes own consecutive j => coalesced reductions into dw[n][j]
+    regs_take_drain();
     const int dw = warp - DRAIN_WARP0;
     const int quadrant = dw & 3, half = dw >> 2;
     float acc[BN / 2];
