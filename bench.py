@@ -211,12 +211,18 @@ def main():
     dom = max(ksum, key=lambda k: ksum[k]["ms"])
     d = ksum[dom]
     achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+    traffic = None                                    # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
     roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tflops"], "traffic": None, "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
+            "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
             "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
             "share_of_step": d["ms"] / args.steps / ms_step,
-            "note": "fp32 path = 3xTF32: 3 kind::tf32 MMAs per algorithmic product, TF32 issues at half the bf16 rate, "
-                    "so the ceiling of this arithmetic is peak/6"}
+            "note": "fp32 path = 3xTF32: 3 kind::tf32 MMAs per algorithmic product; measured on this B200 a 128x128x8 "
+                    "kind::tf32 MMA takes 64 cycles = 4096 FLOP/cycle/SM (tools/micro/mma_bench.cu), so the ceiling of this "
+                    "arithmetic is 148 SMs x 4096 x clock / 3 = 373 TFLOP/s at 1.845 GHz, i.e. 0.27 of the bf16 peak used here"}
     kernels = {k: {"tflops": v["flops"] / (v["ms"] / 1e3) / 1e12, "ms_per_step": v["ms"] / args.steps,
                    "launches_per_step": v["launches"] / args.steps} for k, v in ksum.items()}
     step_tflops = value / world * FLOP_PER_PAIR_TRAIN / 1e12

@@ -97,6 +97,8 @@ typedef struct {
   int32_t impl;
   const float* x_lo;       /* optional pair (both or none; no in_scale / in_relu): TF32 remainders of x and dy      */
   const float* dy_lo;      /* (zsg_split_act); operands then go global -> shared by cp.async                         */
+  int32_t dy_pitch;        /* > 0: rows[i].out == i * dy_pitch for every row (dy is a plain [m, dy_pitch] matrix, true for
+                              every forward table of the path): dy / dy_lo are then fetched by TMA.  0: unknown        */
 } zsg_wgrad_params;
 int zsg_conv_wgrad(const zsg_wgrad_params* p, zsg_stream_t stream);
 

@@ -14,6 +14,16 @@ rows = geometry.conv_rows(B, H, H, cin, H, H, cout, 1, k // 2).cuda()
 y = torch.empty(B, H, H, cout, device="cuda")
 sc = torch.rand(cin, device="cuda") + 0.5 if pro else None
 sh = torch.randn(cin, device="cuda") if pro else None
-op = ops.ConvOp(x, hi, y, rows, B * H * H, cin, cout, k, k, w_lo=lo, in_scale=sc, in_shift=sh, in_relu=pro)
-for _ in range(3): op()
+if "async" in sys.argv:
+    x_lo = torch.empty_like(x)
+    ops.split_act(x, x_lo, B * H * H, cin)
+    op = ops.ConvOp(x, hi, y, rows, B * H * H, cin, cout, k, k, w_lo=lo, x_lo=x_lo)
+    dy = torch.randn(B, H, H, cout, device="cuda"); dy_lo = torch.empty_like(dy)
+    ops.split_act(dy, dy_lo, B * H * H, cout)
+    dw = torch.zeros(cout, k, k, cin, device="cuda")
+    wop = ops.WgradOp(x, dy, dw, rows, B * H * H, cin, cout, k, k, x_lo=x_lo, dy_lo=dy_lo)
+    for _ in range(3): op(); wop()
+else:
+    op = ops.ConvOp(x, hi, y, rows, B * H * H, cin, cout, k, k, w_lo=lo, in_scale=sc, in_shift=sh, in_relu=pro)
+    for _ in range(3): op()
 torch.cuda.synchronize()

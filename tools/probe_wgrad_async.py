@@ -20,8 +20,11 @@ def run(B, cin, H, cout, k, stride=1, pitch=None, reps=5):
     dw1 = torch.zeros(cout, k, k, cin, device="cuda"); dw2 = torch.zeros_like(dw1)
     op1 = ops.WgradOp(x, dy, dw1, rows, M, cin, cout, k, k)
     op2 = ops.WgradOp(x, dy, dw2, rows, M, cin, cout, k, k, x_lo=x_lo, dy_lo=dy_lo)
-    op1(); op2()
+    dw3 = torch.zeros_like(dw1)
+    op3 = ops.WgradOp(x, dy, dw3, rows, M, cin, cout, k, k, x_lo=x_lo, dy_lo=dy_lo, dy_pitch=pitch)
+    op1(); op2(); op3()
     torch.cuda.synchronize()
+    d12 = float((dw1 - dw2).abs().max() / dw1.abs().max()); d13 = float((dw1 - dw3).abs().max() / dw1.abs().max())
     ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (cout, cin, k, k), dy[..., :cout].permute(0, 3, 1, 2).double(),
                                       stride=stride, padding=k // 2).permute(0, 2, 3, 1) if M * cout * cin * k * k < 3e12 else None
     e = lambda a: float((a.double() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()) if ref is not None else float("nan")
@@ -34,9 +37,9 @@ def run(B, cin, H, cout, k, stride=1, pitch=None, reps=5):
         for _ in range(reps): f()
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
-    t1, t2 = timeit(op1, dw1), timeit(op2, dw2)
-    print(f"B={B} cin={cin} H={H} cout={cout} k={k} s={stride}: rel err register {e(dw1):.2e} async {e(dw2):.2e} | "
-          f"register {t1:.3f} ms {fl/t1/1e9:6.1f} TF/s | async {t2:.3f} ms {fl/t2/1e9:6.1f} TF/s", flush=True)
+    t1, t2, t3 = timeit(op1, dw1), timeit(op2, dw2), timeit(op3, dw3)
+    print(f"B={B} cin={cin} H={H} cout={cout} k={k} s={stride}: max rel diff vs register: cp.async {d12:.1e} tma-dy {d13:.1e} | "
+          f"register {t1:.3f} ms {fl/t1/1e9:6.1f} TF/s | cp.async {t2:.3f} ms {fl/t2/1e9:6.1f} | tma-dy {t3:.3f} ms {fl/t3/1e9:6.1f} TF/s", flush=True)
 
 run(2, 64, 19, 256, 3)
 run(3, 128, 20, 128, 3, stride=2)

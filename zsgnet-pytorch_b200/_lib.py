@@ -32,7 +32,7 @@ class WgradParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p), ("rows", C.c_void_p),
                 ("m", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
                 ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32), ("split_k", C.c_int32),
-                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dy_lo", C.c_void_p)]
+                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int32)]
 
 
 _P, _I, _L, _F, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t

@@ -1114,8 +1114,13 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
 // straight to `full` by cp.async.mbarrier.arrive, and the row entries of the next K block are fetched while the
 // current one is in flight.
 // ============================================================================================
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_wgrad_params p, int kb_per_split) {
+// TMA_DY: dy / dy_lo are plain [m, dy_pitch] matrices (always true for the rows of a forward table): the B tile is
+// fetched by TMA (four 32-pixel x 32-channel boxes per image, SWIZZLE_128B_ATOM_32B = the MN-major operand layout),
+// which halves the cp.async instruction stream -- ncu showed the LSU, not the tensor pipe, pacing this kernel.
+template <int BN, bool TMA_DY>
+__global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_wgrad_params p, int kb_per_split,
+                                                                      const __grid_constant__ CUtensorMap tm_dy,
+                                                                      const __grid_constant__ CUtensorMap tm_dy_lo) {
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -1129,7 +1134,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
   if (kb_end > nkb_total) kb_end = nkb_total;
   const int nkb = kb_end - kb_begin;                        // >= 1 by construction of the grid
 
-  PipeBars pb = setup_pipeline<BN>(sm, warp, lane, NPROD);
+  PipeBars pb = setup_pipeline<BN>(sm, warp, lane, TMA_DY ? NPROD + 1 : NPROD);
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
 
   if (warp >= MMA_WARP) {
@@ -1162,6 +1167,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
     const int4* rows = reinterpret_cast<const int4*>(p.rows);
     int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 64;       // [2][32] entries per group
     const uint32_t tiles0 = smem_u32(sm);
+    const int tap0 = __shfl_sync(0xffffffffu, tap, 0);        // (outside the &&: every lane must take part)
+    const bool warp_uniform = __all_sync(0xffffffffu, jvalid && tap == tap0) != 0;
     // prologue: entries of this group's first K block
     if (group < nkb) {
       if (t < 32) {
@@ -1185,23 +1192,59 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
       mbar_wait(pb.empty(s), ((i / S::STAGES) & 1) ^ 1, 5000 + i);
       const uint32_t a_hi = tiles0 + s * S::STAGE_BYTES;
       const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+      if (TMA_DY && (t >> 5) == 0) {
+        if (elect_one()) {
+          const int pix0 = (kb_begin + i) * KB;
+          mbar_arrive_expect_tx(pb.full(s), 2 * S::B_TILE_BYTES);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int pixel = q * 4 + ps;                        // 0..31 within the K block
-        const int4 e = eb[pixel];
+          for (int atom = 0; atom < BN / 32; ++atom) {
+            tma_load_2d(b_hi + atom * 4096, &tm_dy, n0 + atom * 32, pix0, pb.full(s));
+            tma_load_2d(b_hi + S::B_TILE_BYTES + atom * 4096, &tm_dy_lo, n0 + atom * 32, pix0, pb.full(s));
+          }
+        }
+        __syncwarp();
+      }
+      if (warp_uniform) {
+        // one tap for the whole warp: lane q decodes pixel q * 4 + ps once, the offsets are broadcast
+        const int4 e = eb[(lane & 7) * 4 + ps];
         const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
         const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-        const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
-        const int r4 = pixel & 3;
-        const uint32_t off = atom_off + (pixel >> 2) * 512 + r4 * 128 + ((((cj >> 1) ^ r4) << 1) | (cj & 1)) * 16;
-        const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
-        cp_async16(a_hi + off, xh + ao, oka ? 16u : 0u);
-        cp_async16(a_hi + A_TILE_BYTES + off, xl + ao, oka ? 16u : 0u);
-        if (mc * 4 < BN) {
-          const bool okb = hin > 0;
-          const int64_t bo = okb ? (int64_t)e.w : 0;
-          cp_async16(b_hi + off, yh + bo, okb ? bbytes : 0u);
-          cp_async16(b_hi + S::B_TILE_BYTES + off, yl + bo, okb ? bbytes : 0u);
+        const bool oka = (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+        const int my_ao = oka ? e.x + (yy * win + xx) * p.cin : -1;
+        const int my_bo = hin > 0 ? e.w : -1;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int ao = __shfl_sync(0xffffffffu, my_ao, q), bo = __shfl_sync(0xffffffffu, my_bo, q);
+          const int pixel = q * 4 + ps;
+          const int r4 = ps;                                 // pixel & 3
+          const uint32_t off = atom_off + q * 512 + r4 * 128 + ((((cj >> 1) ^ r4) << 1) | (cj & 1)) * 16;
+          (void)pixel;
+          cp_async16(a_hi + off, xh + (ao < 0 ? 0 : ao), ao < 0 ? 0u : 16u);
+          cp_async16(a_hi + A_TILE_BYTES + off, xl + (ao < 0 ? 0 : ao), ao < 0 ? 0u : 16u);
+          if (!TMA_DY && mc * 4 < BN) {
+            cp_async16(b_hi + off, yh + (bo < 0 ? 0 : bo), bo < 0 ? 0u : bbytes);
+            cp_async16(b_hi + S::B_TILE_BYTES + off, yl + (bo < 0 ? 0 : bo), bo < 0 ? 0u : bbytes);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int pixel = q * 4 + ps;                      // 0..31 within the K block
+          const int4 e = eb[pixel];
+          const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+          const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+          const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          const int r4 = pixel & 3;
+          const uint32_t off = atom_off + (pixel >> 2) * 512 + r4 * 128 + ((((cj >> 1) ^ r4) << 1) | (cj & 1)) * 16;
+          const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
+          cp_async16(a_hi + off, xh + ao, oka ? 16u : 0u);
+          cp_async16(a_hi + A_TILE_BYTES + off, xl + ao, oka ? 16u : 0u);
+          if (!TMA_DY && mc * 4 < BN) {
+            const bool okb = hin > 0;
+            const int64_t bo = okb ? (int64_t)e.w : 0;
+            cp_async16(b_hi + off, yh + bo, okb ? bbytes : 0u);
+            cp_async16(b_hi + S::B_TILE_BYTES + off, yl + bo, okb ? bbytes : 0u);
+          }
         }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
@@ -1384,30 +1427,65 @@ static int launch_conv_pro(const zsg_conv_params& p, cudaStream_t st) {
   }
 }
 
-template <int BN, bool ASYNC>
+// dy [m][pitch] fp32: box = 32 channels (128 B) x 32 pixels, 32-byte-atom 128 B swizzle (MN-major tf32 operand layout)
+static int make_dy_map(CUtensorMap* map, const float* dy, int m, int pitch) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ZSG_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)m};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)KB};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dy), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for dy m=%d pitch=%d", (int)r, m, pitch); return ZSG_ECUDA; }
+  return ZSG_OK;
+}
+
+template <int BN, int MODE>          // MODE 0 = register path, 1 = cp.async operands, 2 = cp.async x + TMA dy
 static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
   static bool attr_done = false;
-  auto kern = ASYNC ? wgrad_tc_async_kernel<BN> : wgrad_tc_kernel<BN>;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    cudaError_t e = MODE == 0 ? cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL)
+                  : MODE == 1 ? cudaFuncSetAttribute(wgrad_tc_async_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL)
+                              : cudaFuncSetAttribute(wgrad_tc_async_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
     if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
+  }
+  CUtensorMap tm_dy, tm_dy_lo;
+  memset(&tm_dy, 0, sizeof(tm_dy));
+  memset(&tm_dy_lo, 0, sizeof(tm_dy_lo));
+  if (MODE == 2) {
+    if (int rc = make_dy_map(&tm_dy, p.dy, p.m, p.dy_pitch)) return rc;
+    if (int rc = make_dy_map(&tm_dy_lo, p.dy_lo, p.m, p.dy_pitch)) return rc;
   }
   const int Kt = p.r * p.s * p.cin;
   const int tiles = ((p.cout + BN - 1) / BN) * ((Kt + TM - 1) / TM);
   const int nkb = (p.m + KB - 1) / KB;
   int split = p.split_k;
   if (split <= 0) {
-    split = (2 * num_sms() + tiles - 1) / tiles;
-    const int max_split = (nkb + 7) / 8;                    // at least 8 K-blocks per CTA
-    if (split > max_split) split = max_split;
-    if (split < 1) split = 1;
+    // split-K factor: minimise (waves of CTAs) x (K blocks per CTA + fixed per-CTA cost), so that the grid fills whole
+    // waves of the SMs (a 2.2-wave grid costs 3 waves) while every CTA keeps at least 8 K blocks
+    const int sms = num_sms();
+    const int max_split = nkb >= 16 ? nkb / 8 : 1;
+    const int fixed = 24;                                   // pipeline fill + atomic epilogue, in K-block times
+    long best_cost = -1;
+    split = 1;
+    for (int sk = 1; sk <= max_split && sk <= 256; ++sk) {
+      const int per_cta = (nkb + sk - 1) / sk;
+      const int ctas = tiles * ((nkb + per_cta - 1) / per_cta);
+      const long waves = (ctas + sms - 1) / sms;
+      const long cost = waves * (per_cta + fixed);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; split = sk; }
+    }
   }
   if (split > nkb) split = nkb;
   const int per = (nkb + split - 1) / split;
   split = (nkb + per - 1) / per;                            // no empty splits
   dim3 grid((p.cout + BN - 1) / BN, (Kt + TM - 1) / TM, split);
-  kern<<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per);
+  if (MODE == 0) wgrad_tc_kernel<BN><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per);
+  else if (MODE == 1) wgrad_tc_async_kernel<BN, false><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per, tm_dy, tm_dy_lo);
+  else wgrad_tc_async_kernel<BN, true><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per, tm_dy, tm_dy_lo);
   return check_launch("zsg_conv_wgrad");
 }
 
@@ -1471,7 +1549,11 @@ extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
     ZSG_REQUIRE(p.cin % 4 == 0, "zsg_conv_wgrad: cin must be a multiple of 4");
     ZSG_REQUIRE((((uintptr_t)p.x | (uintptr_t)p.x_lo | (uintptr_t)p.dy | (uintptr_t)p.dy_lo) & 15) == 0,
                 "zsg_conv_wgrad: operands must be 16-byte aligned");
-    return p.cout <= 64 ? launch_wgrad<64, true>(p, st) : launch_wgrad<128, true>(p, st);
+    if (p.dy_pitch > 0) {
+      ZSG_REQUIRE(p.dy_pitch >= p.cout && p.dy_pitch % 4 == 0, "zsg_conv_wgrad: dy_pitch must be >= cout and a multiple of 4");
+      return p.cout <= 64 ? launch_wgrad<64, 2>(p, st) : launch_wgrad<128, 2>(p, st);
+    }
+    return p.cout <= 64 ? launch_wgrad<64, 1>(p, st) : launch_wgrad<128, 1>(p, st);
   }
-  return p.cout <= 64 ? launch_wgrad<64, false>(p, st) : launch_wgrad<128, false>(p, st);
+  return p.cout <= 64 ? launch_wgrad<64, 0>(p, st) : launch_wgrad<128, 0>(p, st);
 }

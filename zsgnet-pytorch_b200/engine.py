@@ -199,7 +199,7 @@ class Engine:
     def conv_wgrad(self, L, dy, dy_lo, dw=None):
         dw = self.store.grad_flat(L["wname"]) if dw is None else dw
         self.bwd.append(WgradOp(L["xz"], dy, dw, L["rows"], self.B * L["hout"] * L["wout"], L["cin"], L["cout"], L["k"],
-                                L["k"], impl=self.impl, x_lo=L["x_lo"], dy_lo=dy_lo))
+                                L["k"], impl=self.impl, x_lo=L["x_lo"], dy_lo=dy_lo, dy_pitch=L["cout"]))
 
     def grad_operand(self, L, dy):
         """lo image of the output gradient of conv L (shared by its wgrad and dgrad)."""
@@ -494,7 +494,7 @@ class Engine:
             self.bwd.append(lambda: st.grad_flat("att_reg_box.5.bias").copy_(tmp48[:45]))
             dy5_lo = self.bwd_operand(dy5, M, 48)
             self.bwd.append(WgradOp(hs[4], dy5, st.grad_flat("att_reg_box.5.weight"), rows_f48, M, 256, 45, 3, 3,
-                                    impl=self.impl, x_lo=hs_lo[4], dy_lo=dy5_lo))
+                                    impl=self.impl, x_lo=hs_lo[4], dy_lo=dy5_lo, dy_pitch=48))
             self.bwd.append(ConvOp(dy5, wt5p_t[1], dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl,
                                    w_lo=wt5p_t[2], x_lo=dy5_lo))
             for i in range(4, 0, -1):
@@ -504,7 +504,7 @@ class Engine:
                 self.bwd.append(lambda i=i, gb=gb: ops.colsum(dhs[i], gb, M, 256))
                 dlo = self.bwd_operand(dhs[i], M, 256)
                 self.bwd.append(WgradOp(hs[i - 1], dhs[i], st.grad_flat(f"att_reg_box.{i}.0.weight"), rows_f256, M, 256,
-                                        256, 3, 3, impl=self.impl, x_lo=hs_lo[i - 1], dy_lo=dlo))
+                                        256, 3, 3, impl=self.impl, x_lo=hs_lo[i - 1], dy_lo=dlo, dy_pitch=256))
                 self.bwd.append(ConvOp(dhs[i], wts[i][1], dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
                                        impl=self.impl, w_lo=wts[i][2], x_lo=dlo))
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
@@ -512,7 +512,8 @@ class Engine:
             self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
             self.bwd.append(lambda: dw0p.zero_())
             d0lo = self.bwd_operand(dhs[0], M, 256)
-            self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl, x_lo=fused_lo, dy_lo=d0lo))
+            self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl, x_lo=fused_lo, dy_lo=d0lo,
+                                    dy_pitch=256))
             g0 = st.grad_flat("att_reg_box.0.0.weight")
             self.bwd.append(lambda: ops.pad_channels(dw0p, g0, 256 * 9, CP, spec.FUSED_C))
             self.bwd.append(ConvOp(dhs[0], wt0_t[1], dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0_t[2],

@@ -52,7 +52,7 @@ class ConvOp:
                             impl, ptr(x_lo))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
-        self.kernel = "conv_tc_kernel"
+        self.kernel = "conv_tc_async_kernel" if x_lo is not None else ("conv_tc_kernel" if w_lo is not None else "conv_tc_generic_kernel")
 
     def __call__(self):
         if PROFILER is not None:
@@ -62,14 +62,14 @@ class ConvOp:
 
 class WgradOp:
     def __init__(self, x, dy, dw, rows, m, cin, cout, r, s, in_scale=None, in_shift=None, in_relu=False, split_k=0,
-                 impl=IMPL_TC, x_lo=None, dy_lo=None):
+                 impl=IMPL_TC, x_lo=None, dy_lo=None, dy_pitch=0):
         self.keep = (x, dy, dw, rows, in_scale, in_shift, x_lo, dy_lo)
         self.dw = dw
         self.p = WgradParams(ptr(x), ptr(dy), ptr(dw), ptr(rows), m, cin, cout, r, s, ptr(in_scale), ptr(in_shift),
-                             int(in_relu), split_k, impl, ptr(x_lo), ptr(dy_lo))
+                             int(in_relu), split_k, impl, ptr(x_lo), ptr(dy_lo), dy_pitch)
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin
-        self.kernel = "wgrad_tc_kernel"
+        self.kernel = "wgrad_tc_async_kernel" if x_lo is not None else "wgrad_tc_kernel"
 
     def __call__(self):
         if PROFILER is not None:
