@@ -559,3 +559,122 @@ def test_lstm_recurrences_vs_oracle(zsg):
     assert rel_err(dgr.t() @ xlast, sd["lstm.weight_ih_l0_reverse"].grad) < 1e-4
     assert rel_err(dgr.t() @ h0r, sd["lstm.weight_hh_l0_reverse"].grad) < 1e-4
     assert rel_err(dgr.sum(0), sd["lstm.bias_hh_l0_reverse"].grad) < 1e-4
+
+
+# ------------------------------------------------------------------ operand images (cp.async / TMA GEMM paths)
+def test_split_act_images(zsg):
+    """z = relu(x*scale+shift) with the same fmaf as the in-kernel prologue; lo = z - trunc_tf32(z), exactly."""
+    ops, _ = zsg
+    g = torch.Generator().manual_seed(5)
+    rows, c = 1237, 72
+    x = torch.randn(rows, c, generator=g).cuda()
+    sc, sh = (torch.rand(c, generator=g) + 0.5).cuda(), torch.randn(c, generator=g).cuda()
+    z, lo = torch.empty_like(x), torch.empty_like(x)
+    ops.split_act(x, lo, rows, c, scale=sc, shift=sh, relu=True, z=z)
+    lo0 = torch.empty_like(x)
+    ops.split_act(x, lo0, rows, c)
+    torch.cuda.synchronize()
+    zr = torch.relu(torch.addcmul(sh, x, sc))                       # single-rounding fma on the GPU as well
+    assert float((z - zr).abs().max()) <= 1.2e-7 * float(zr.abs().max())
+    hi = (z.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(hi + lo, z) and torch.equal(lo, z - hi)
+    hi0 = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(lo0, x - hi0)
+
+
+@pytest.mark.parametrize("case", CONV_CASES + [(2, 128, 9, 9, 128, 3, 2, 1)])
+@pytest.mark.parametrize("pro", [False, True])
+def test_conv_async_equals_register_path(zsg, case, pro):
+    """The cp.async kernel (tensor + remainder image) must reproduce the register-path kernel bit for bit and meet
+    the same tolerance against torch."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(hash(case) % 1000 + 7)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    sc, sh = (torch.rand(cin, generator=g) + 0.5).cuda(), torch.randn(cin, generator=g).cuda() * 0.3
+    a = F.relu(x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)) if pro else x
+    ref = F.conv2d(a, w, bias, stride=stride, padding=pad)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    wk = khwc(w)
+    hi, lo = torch.empty_like(wk), torch.empty_like(wk)
+    ops.split_tf32(wk, hi, lo, wk.numel())
+    xn = nhwc(x)
+    y1 = torch.full((B, Ho, Wo, cout), float("nan"), device="cuda")
+    y2 = torch.full_like(y1, float("nan"))
+    ops.ConvOp(xn, hi, y1, rows, B * Ho * Wo, cin, cout, k, k, bias=bias, w_lo=lo, in_scale=sc if pro else None,
+               in_shift=sh if pro else None, in_relu=pro)()
+    z, x_lo = (torch.empty_like(xn) if pro else None), torch.empty_like(xn)
+    ops.split_act(xn, x_lo, B * H * W, cin, scale=sc if pro else None, shift=sh if pro else None, relu=pro, z=z)
+    ops.ConvOp(z if pro else xn, hi, y2, rows, B * Ho * Wo, cin, cout, k, k, bias=bias, w_lo=lo, x_lo=x_lo)()
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    assert rel_err(y2, nhwc(ref)) < 2e-5
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_conv_dgrad_async_vs_torch(zsg, case):
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, cin, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    y = F.conv2d(x, w, None, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    Ho, Wo = y.shape[2], y.shape[3]
+    wt = torch.empty(cin, k, k, cout, device="cuda")
+    ops.weight_transpose_flip(khwc(w), wt, cout, k, k, cin)
+    dyn = nhwc(dy)
+    cp = (cout + 3) // 4 * 4
+    if cp != cout:
+        wtp = torch.empty(cin, k, k, cp, device="cuda")
+        ops.pad_channels(wt, wtp, cin * k * k, cout, cp)
+        dyp = torch.empty(B, Ho, Wo, cp, device="cuda")
+        ops.pad_channels(dyn, dyp, B * Ho * Wo, cout, cp)
+        wt, dyn = wtp, dyp
+    hi, lo = torch.empty_like(wt), torch.empty_like(wt)
+    ops.split_tf32(wt, hi, lo, wt.numel())
+    dy_lo = torch.empty_like(dyn)
+    ops.split_act(dyn, dy_lo, B * Ho * Wo, cp)
+    rows = geo.dgrad_rows(B, H, W, cin, Ho, Wo, cp, k, stride, pad).cuda()
+    res = torch.randn(B, H, W, cin, generator=g).cuda()
+    mask = torch.randn(B, H, W, cin, generator=g).cuda()
+    dx = torch.empty(B, H, W, cin, device="cuda")
+    ops.ConvOp(dyn, hi, dx, rows, B * H * W, cp, cin, k, k, in_div=stride, w_lo=lo, x_lo=dy_lo, out_mask=mask, residual=res)()
+    torch.cuda.synchronize()
+    want = nhwc(x.grad) * (mask > 0) + res
+    assert rel_err(dx, want) < 2e-5
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES + [(2, 520, 10, 10, 256, 3, 1, 1), (2, 264, 7, 9, 128, 1, 1, 0)])
+@pytest.mark.parametrize("tma_dy", [False, True])
+def test_conv_wgrad_async_vs_torch(zsg, case, tma_dy):
+    """cp.async weight-gradient kernel (x, dy with remainder images; dy optionally by TMA) against torch, including
+    channel counts whose 128-wide tiles straddle filter taps and the ragged 45-channel head output (pitch 48)."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(19)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda().requires_grad_(True)
+    y = F.conv2d(x, w, None, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    Ho, Wo = y.shape[2], y.shape[3]
+    pitch = (cout + 3) // 4 * 4
+    dyn = nhwc(dy)
+    if pitch != cout:
+        dyp = torch.empty(B, Ho, Wo, pitch, device="cuda")
+        ops.pad_channels(dyn, dyp, B * Ho * Wo, cout, pitch)
+        dyn = dyp
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, pitch, stride, pad).cuda()
+    xn = nhwc(x)
+    x_lo, dy_lo = torch.empty_like(xn), torch.empty_like(dyn)
+    ops.split_act(xn, x_lo, B * H * W, cin)
+    ops.split_act(dyn, dy_lo, B * Ho * Wo, pitch)
+    dw = torch.zeros(cout, k, k, cin, device="cuda")
+    ops.WgradOp(xn, dyn, dw, rows, B * Ho * Wo, cin, cout, k, k, x_lo=x_lo, dy_lo=dy_lo, dy_pitch=pitch if tma_dy else 0)()
+    torch.cuda.synchronize()
+    assert rel_err(dw, khwc(w.grad)) < 3e-5
