@@ -134,19 +134,21 @@ int zsg_bn_finalize(const double* sums, int64_t rows, int c, const float* gamma,
 /* eval mode: scale/shift from running stats. */
 int zsg_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
                        float eps, int c, float* scale, float* shift, zsg_stream_t stream);
-/* y = relu?( x*scale+shift  [+ r*rscale+rshift | + r] ) : the bottleneck tail (bn3 + shortcut + ReLU). */
+/* y = relu?( x*scale+shift  [+ r*rscale+rshift | + r] ) : the bottleneck tail (bn3 + shortcut + ReLU).
+ * y_lo (optional): TF32 remainder image of y for the GEMMs that read it (see zsg_split_act). */
 int zsg_bn_apply(const float* x, const float* scale, const float* shift, const float* r, const float* rscale,
-                 const float* rshift, int relu, float* y, int64_t rows, int c, zsg_stream_t stream);
+                 const float* rshift, int relu, float* y, float* y_lo, int64_t rows, int c, zsg_stream_t stream);
 /* backward reduce: dz = dy * mask ; sums[0:c] = sum dz, sums[c:2c] = sum dz*xhat.
  * mask_mode 0: none; 1: relu mask from (x*scale+shift) > 0; 2: relu mask from act_out > 0 (dz is also
  * written to dz_out when non-null, for the shortcut path). */
 int zsg_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* invstd, const float* scale,
                       const float* shift, const float* act_out, int mask_mode, float* dz_out, double* sums,
                       int64_t rows, int c, zsg_stream_t stream);
-/* dx = gamma*invstd*(dz - s1/rows - xhat*s2/rows); dgamma = s2, dbeta = s1 (written once). */
+/* dx = gamma*invstd*(dz - s1/rows - xhat*s2/rows); dgamma = s2, dbeta = s1 (written once).
+ * dx_lo (optional): TF32 remainder image of dx for the data- and weight-gradient GEMMs that read it. */
 int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                      const float* scale, const float* shift, const float* act_out, int mask_mode,
-                     const double* sums, float* dx, float* dgamma, float* dbeta, int64_t rows, int c,
+                     const double* sums, float* dx, float* dx_lo, float* dgamma, float* dbeta, int64_t rows, int c,
                      zsg_stream_t stream);
 
 /* ------------------------------ pooling / resampling glue -------------------------------- */

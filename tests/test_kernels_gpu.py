@@ -678,3 +678,24 @@ def test_conv_wgrad_async_vs_torch(zsg, case, tma_dy):
     ops.WgradOp(xn, dyn, dw, rows, B * Ho * Wo, cin, cout, k, k, x_lo=x_lo, dy_lo=dy_lo, dy_pitch=pitch if tma_dy else 0)()
     torch.cuda.synchronize()
     assert rel_err(dw, khwc(w.grad)) < 3e-5
+
+
+def test_bn_kernels_write_operand_images(zsg):
+    """bn_apply / bn_bwd_apply optionally emit the TF32 remainder image of their output (same values as zsg_split_act)."""
+    ops, _ = zsg
+    g = torch.Generator().manual_seed(23)
+    rows, C = 777, 64
+    x, r, dy = (torch.randn(rows, C, generator=g).cuda() for _ in range(3))
+    sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    y, y_lo, ref_lo = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    ops.bn_apply(x, sc, sh, y, rows, C, relu=True, r=r, y_lo=y_lo)
+    ops.split_act(y, ref_lo, rows, C)
+    torch.cuda.synchronize()
+    assert torch.equal(y_lo, ref_lo)
+    mean, invstd, gamma = torch.randn(C, generator=g).cuda(), (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    sums = torch.randn(2 * C, generator=g).double().cuda()
+    dx, dx_lo, dg, db = torch.empty_like(x), torch.empty_like(x), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx, dg, db, rows, C, dx_lo=dx_lo)
+    ops.split_act(dx, ref_lo, rows, C)
+    torch.cuda.synchronize()
+    assert torch.equal(dx_lo, ref_lo)

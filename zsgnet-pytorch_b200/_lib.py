@@ -55,9 +55,9 @@ SIGNATURES = {
     "zsg_bn_stats": [_P, _P, _L, _I, _P],
     "zsg_bn_finalize": [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "zsg_bn_eval_affine": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
-    "zsg_bn_apply": [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P],
+    "zsg_bn_apply": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
     "zsg_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
-    "zsg_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _I, _P],
+    "zsg_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P],
     "zsg_maxpool_bn_relu_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "zsg_maxpool_bn_relu_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "zsg_upsample_add": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

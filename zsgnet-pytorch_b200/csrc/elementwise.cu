@@ -23,6 +23,14 @@ __device__ __forceinline__ float4 fma4(float4 x, float4 s, float4 b) {
 __device__ __forceinline__ float4 relu4(float4 v) {
   return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
 }
+__device__ __forceinline__ float4 tf32_lo4(float4 v) {          // remainder after TF32 truncation (operand image)
+  float4 l;
+  l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  return l;
+}
 
 // ------------------------------------------------------------------------------------------
 // Per-channel reductions over rows.  Block = 256 threads = (256/cols) row lanes x cols float4
@@ -165,7 +173,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ shift, const float* __restrict__ r,
                                                        const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, int relu,
-                                                       float* __restrict__ y, int64_t n4, int c4) {
+                                                       float* __restrict__ y, float* __restrict__ y_lo, int64_t n4,
+                                                       int c4) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
     float4 v = fma4(ld4(x + i * 4), ld4(scale + c), ld4(shift + c));
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     }
     if (relu) v = relu4(v);
     st4(y + i * 4, v);
+    if (y_lo) st4(y_lo + i * 4, tf32_lo4(v));
   }
 }
 
@@ -191,12 +201,7 @@ __global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict_
     }
     if (relu) v = relu4(v);
     if (z) st4(z + i * 4, v);
-    float4 l;
-    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    st4(lo + i * 4, l);
+    st4(lo + i * 4, tf32_lo4(v));
   }
 }
 
@@ -204,8 +209,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ act_out, int mask_mode,
-    const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    int64_t rows, int C) {
+    const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dx_lo, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, int64_t rows, int C) {
   const int c4 = C / 4;
   const int64_t n4 = rows * c4;
   const float inv_n = 1.0f / (float)rows;
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     o.z = ga.z * is.z * (g.z - s1[2] - (v.z - mu.z) * is.z * s2[2]);
     o.w = ga.w * is.w * (g.w - s1[3] - (v.w - mu.w) * is.w * s2[3]);
     st4(dx + i * 4, o);
+    if (dx_lo) st4(dx_lo + i * 4, tf32_lo4(o));
   }
 }
 
@@ -582,12 +588,12 @@ extern "C" int zsg_bn_eval_affine(const float* running_mean, const float* runnin
 }
 
 extern "C" int zsg_bn_apply(const float* x, const float* scale, const float* shift, const float* r,
-                            const float* rscale, const float* rshift, int relu, float* y, int64_t rows, int c,
-                            zsg_stream_t stream) {
+                            const float* rscale, const float* rshift, int relu, float* y, float* y_lo, int64_t rows,
+                            int c, zsg_stream_t stream) {
   ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_bn_apply: bad arguments");
   int64_t n4 = rows * (c / 4);
-  bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, n4,
-                                                                     c / 4);
+  bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, y_lo,
+                                                                     n4, c / 4);
   return check_launch("zsg_bn_apply");
 }
 
@@ -614,11 +620,11 @@ extern "C" int zsg_bn_bwd_reduce(const float* dy, const float* x, const float* m
 
 extern "C" int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* invstd,
                                 const float* gamma, const float* scale, const float* shift, const float* act_out,
-                                int mask_mode, const double* sums, float* dx, float* dgamma, float* dbeta,
-                                int64_t rows, int c, zsg_stream_t stream) {
+                                int mask_mode, const double* sums, float* dx, float* dx_lo, float* dgamma,
+                                float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
   ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx && c % 4 == 0, "zsg_bn_bwd_apply: bad arguments");
   bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
-      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dgamma, dbeta, rows, c);
+      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dx_lo, dgamma, dbeta, rows, c);
   return check_launch("zsg_bn_bwd_apply");
 }
 

@@ -145,14 +145,18 @@ class Engine:
             self._operand_cache[key] = (z, lo)
         return self._operand_cache[key]
 
-    def bwd_operand(self, dy, nrows, c):
-        """lo image of a gradient tensor; appends the split launch to the backward program (call it right after
-        the kernel that produced dy -- scratch buffers are reused, so nothing is cached across calls)."""
+    def bwd_lo_buffer(self, dy, nrows, c):
+        """Storage for the lo image of a gradient tensor (one per scratch buffer, sized for its largest user)."""
         n = nrows * c
         key = dy.data_ptr()
         if key not in self._bwd_lo or self._bwd_lo[key].numel() < n:
             self._bwd_lo[key] = self.buf(n)
-        lo = self._bwd_lo[key][:n]
+        return self._bwd_lo[key][:n]
+
+    def bwd_operand(self, dy, nrows, c):
+        """lo image of a gradient tensor; appends the split launch to the backward program (call it right after
+        the kernel that produced dy -- scratch buffers are reused, so nothing is cached across calls)."""
+        lo = self.bwd_lo_buffer(dy, nrows, c)
         self.bwd.append(lambda: ops.split_act(dy, lo, nrows, c))
         return lo
 
@@ -215,15 +219,19 @@ class Engine:
                                out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl,
                                w_lo=wt_lo, x_lo=dy_lo))
 
-    def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None):
+    def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True):
+        """BatchNorm backward; returns the lo image of dx (written by the same kernel) for the GEMMs that follow."""
+        dx_lo = self.bwd_lo_buffer(dx, bn.rows, bn.c) if want_lo else None
+
         def run():
             ops.bn_bwd_reduce(dy, x, bn.mean, bn.invstd, bn.bsums, bn.rows, bn.c, mask_mode=mask_mode, scale=bn.scale,
                               shift=bn.shift, act_out=act_out, dz_out=dz_out)
             src = dz_out if dz_out is not None else dy
             mm = 0 if dz_out is not None else mask_mode
             ops.bn_bwd_apply(src, x, bn.mean, bn.invstd, bn.gamma, bn.bsums, dx, bn.dgamma, bn.dbeta, bn.rows, bn.c,
-                             mask_mode=mm, scale=bn.scale, shift=bn.shift, act_out=act_out)
+                             mask_mode=mm, scale=bn.scale, shift=bn.shift, act_out=act_out, dx_lo=dx_lo)
         self.bwd.append(run)
+        return dx_lo
 
     # ------------------------------------------------------------------ the network
     def _build(self):
@@ -254,9 +262,9 @@ class Engine:
 
         def stem_bwd():
             self.bwd.append(lambda: ops.maxpool_bn_relu_bwd(pool_arg, g_x0, da_stem, B, 150, 150, 64, 75, 75))
-            self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1)
+            lo_stem = self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1)
             self.bwd.append(lambda: dw1p.zero_())
-            self.conv_wgrad(Lstem, da_stem, self.grad_operand(Lstem, da_stem), dw=dw1p)
+            self.conv_wgrad(Lstem, da_stem, lo_stem, dw=dw1p)
             self.bwd.append(lambda: ops.pad_channels(dw1p, g1, 64 * 49, 4, 3))
         bwd_stages.append(stem_bwd)
 
@@ -288,11 +296,15 @@ class Engine:
                     bnD = self.add_bn(p + "downsample.1", 4 * width, ro)
                     self.bn_forward(bnD, rd)
 
-                def tail(r3=r3, bnC=bnC, rd=rd, bnD=bnD, inp=inp, out=out, ro=ro, c=4 * width):
+                out_lo = self.buf(ro, 4 * width)              # operand image of the block output, written by the tail
+                self._operand_cache[(out.data_ptr(), ro, 4 * width, id(None), False)] = (out, out_lo)
+
+                def tail(r3=r3, bnC=bnC, rd=rd, bnD=bnD, inp=inp, out=out, ro=ro, c=4 * width, out_lo=out_lo):
                     if rd is not None:
-                        ops.bn_apply(r3, bnC.scale, bnC.shift, out, ro, c, True, r=rd, rscale=bnD.scale, rshift=bnD.shift)
+                        ops.bn_apply(r3, bnC.scale, bnC.shift, out, ro, c, True, r=rd, rscale=bnD.scale, rshift=bnD.shift,
+                                     y_lo=out_lo)
                     else:
-                        ops.bn_apply(r3, bnC.scale, bnC.shift, out, ro, c, True, r=inp)
+                        ops.bn_apply(r3, bnC.scale, bnC.shift, out, ro, c, True, r=inp, y_lo=out_lo)
                 self.fwd.append(("fn", tail))
                 blocks.append(dict(La=La, Lb=Lb, Lc=Lc, Ld=Ld, bnA=bnA, bnB=bnB, bnC=bnC, bnD=bnD, r1=r1, r2=r2, r3=r3,
                                    rd=rd, out=out, g_out=g_out, g_in=g_in, ri=ri, ro=ro, width=width,
@@ -307,21 +319,17 @@ class Engine:
                 L = blocks[k]
                 ro, ri, w4, w = L["ro"], L["ri"], 4 * L["width"], L["width"]
                 dz, dr3, da2, da1 = sA[:ro * w4], sB[:ro * w4], sC[:ro * w], sD[:ri * w]
-                self.bn_backward(L["bnC"], L["g_out"], L["r3"], dr3, mask_mode=2, act_out=L["out"], dz_out=dz)
-                lo3 = self.grad_operand(L["Lc"], dr3)
+                lo3 = self.bn_backward(L["bnC"], L["g_out"], L["r3"], dr3, mask_mode=2, act_out=L["out"], dz_out=dz)
                 self.conv_wgrad(L["Lc"], dr3, lo3)
                 self.conv_dgrad(L["Lc"], dr3, lo3, da2)
-                self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1)
-                lo2 = self.grad_operand(L["Lb"], da2)
+                lo2 = self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1)
                 self.conv_wgrad(L["Lb"], da2, lo2)
                 self.conv_dgrad(L["Lb"], da2, lo2, da1)
-                self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1)
-                lo1 = self.grad_operand(L["La"], da1)
+                lo1 = self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1)
                 self.conv_wgrad(L["La"], da1, lo1)
                 if L["Ld"] is not None:
                     drd = sB[:ro * w4]
-                    self.bn_backward(L["bnD"], dz, L["rd"], drd, mask_mode=0)
-                    lod = self.grad_operand(L["Ld"], drd)
+                    lod = self.bn_backward(L["bnD"], dz, L["rd"], drd, mask_mode=0)
                     self.conv_wgrad(L["Ld"], drd, lod)
                     self.conv_dgrad(L["Ld"], drd, lod, L["g_in"], accumulate=L["acc_in"])
                     self.conv_dgrad(L["La"], da1, lo1, L["g_in"], accumulate=True)

@@ -120,9 +120,9 @@ def bn_eval_affine(rm, rv, gamma, beta, eps, c, scale, shift):
     call("zsg_bn_eval_affine", ptr(rm), ptr(rv), ptr(gamma), ptr(beta), eps, c, ptr(scale), ptr(shift), stream())
 
 
-def bn_apply(x, scale, shift, y, rows, c, relu, r=None, rscale=None, rshift=None):
-    call("zsg_bn_apply", ptr(x), ptr(scale), ptr(shift), ptr(r), ptr(rscale), ptr(rshift), int(relu), ptr(y), rows, c,
-         stream())
+def bn_apply(x, scale, shift, y, rows, c, relu, r=None, rscale=None, rshift=None, y_lo=None):
+    call("zsg_bn_apply", ptr(x), ptr(scale), ptr(shift), ptr(r), ptr(rscale), ptr(rshift), int(relu), ptr(y), ptr(y_lo),
+         rows, c, stream())
 
 
 def bn_bwd_reduce(dy, x, mean, invstd, sums, rows, c, mask_mode=0, scale=None, shift=None, act_out=None, dz_out=None):
@@ -131,9 +131,9 @@ def bn_bwd_reduce(dy, x, mean, invstd, sums, rows, c, mask_mode=0, scale=None, s
 
 
 def bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, rows, c, mask_mode=0, scale=None, shift=None,
-                 act_out=None):
+                 act_out=None, dx_lo=None):
     call("zsg_bn_bwd_apply", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(scale), ptr(shift), ptr(act_out),
-         mask_mode, ptr(sums), ptr(dx), ptr(dgamma), ptr(dbeta), rows, c, stream())
+         mask_mode, ptr(sums), ptr(dx), ptr(dx_lo), ptr(dgamma), ptr(dbeta), rows, c, stream())
 
 
 def maxpool_bn_relu_fwd(x, scale, shift, y, argmax, b, h, w, c, ho, wo):
