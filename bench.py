@@ -188,22 +188,36 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    prof = ops.LaunchProfiler()
-    ops.PROFILER = prof
     launches0 = _lib.LAUNCH_COUNT[0]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    loss_ev = []
     ev0.record()
     for i in range(args.steps):
         fused.step(resident[i % nres])
     ev1.record()
     barrier()
-    ops.PROFILER = None
     launches = _lib.LAUNCH_COUNT[0] - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
+
+    # per-kernel durations for the roofline: CUDA events around every implicit-GEMM launch, on the launching stream, in
+    # `psteps` further steps of the same loop.  In the product step weight gradients run on a side stream next to the
+    # data gradients (their intervals overlap and cannot be attributed), so for this pass they are put back in line.
+    eng0 = net.engine_for(B, 20)
+    overlap0, eng0.overlap_wgrad = eng0.overlap_wgrad, False
+    prof = ops.LaunchProfiler()
+    ops.PROFILER = prof
+    psteps = min(args.steps, 5)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(psteps):
+        fused.step(resident[i % nres])
+    p1.record()
+    barrier()
+    ops.PROFILER = None
+    eng0.overlap_wgrad = overlap0
+    ms_step_inline = p0.elapsed_time(p1) / psteps
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
     pk = peaks()
@@ -218,13 +232,14 @@ def main():
             traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
     roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
-            "launches_per_step": d["launches"] / args.steps, "avg_launch_ms": d["ms"] / d["launches"],
-            "share_of_step": d["ms"] / args.steps / ms_step,
+            "launches_per_step": d["launches"] / psteps, "avg_launch_ms": d["ms"] / d["launches"],
+            "share_of_step": d["ms"] / psteps / ms_step_inline, "timed_in": f"{psteps} steps after the timed region, weight "
+            f"gradients in line ({ms_step_inline:.2f} ms/step; the product step overlaps them with the data gradients)",
             "note": "fp32 path = 3xTF32: 3 kind::tf32 MMAs per algorithmic product; measured on this B200 a 128x128x8 "
                     "kind::tf32 MMA takes 64 cycles = 4096 FLOP/cycle/SM (tools/micro/mma_bench.cu), so the ceiling of this "
                     "arithmetic is 148 SMs x 4096 x clock / 3 = 373 TFLOP/s at 1.845 GHz, i.e. 0.27 of the bf16 peak used here"}
-    kernels = {k: {"tflops": v["flops"] / (v["ms"] / 1e3) / 1e12, "ms_per_step": v["ms"] / args.steps,
-                   "launches_per_step": v["launches"] / args.steps} for k, v in ksum.items()}
+    kernels = {k: {"tflops": v["flops"] / (v["ms"] / 1e3) / 1e12, "ms_per_step": v["ms"] / psteps,
+                   "launches_per_step": v["launches"] / psteps} for k, v in ksum.items()}
     step_tflops = value / world * FLOP_PER_PAIR_TRAIN / 1e12
 
     # HBM-bound side: the fused match + loss + gradient pass, timed alone with CUDA events
@@ -300,8 +315,8 @@ def main():
                 "roofline": roof, "roofline_hbm": roof_hbm, "kernels": kernels,
                 "step_tensor_tflops_per_gpu": step_tflops, "step_tensor_frac_of_peak": step_tflops / pk["tflops"],
                 "cpu_baseline": cpu,
-                "allreduce": {"bytes_per_step": reducer.bytes_reduced / max(1, args.steps + args.warmup + (0 if args.no_e2e else args.steps + 3)),
-                              "buckets_per_step": reducer.calls / max(1, args.steps + args.warmup + (0 if args.no_e2e else args.steps + 3))}}
+                "allreduce": {"bytes_per_step": reducer.bytes_reduced / max(1, args.steps + args.warmup + psteps + (0 if args.no_e2e else args.steps + 3)),
+                              "buckets_per_step": reducer.calls / max(1, args.steps + args.warmup + psteps + (0 if args.no_e2e else args.steps + 3))}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -86,6 +86,8 @@ class Engine:
         self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
         self._rows_cache = {}
         self._operand_cache, self._bwd_lo = {}, {}
+        self._side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
+        self.overlap_wgrad = self._side_stream is not None
         self._f64_pool, self._f64_used = torch.zeros(1 << 18, dtype=torch.float64, device=device), 0
         self.bns = []
         self.fwd_train, self.fwd_eval_bn, self.fwd, self.bwd, self.prep_bwd = [], [], [], [], []
@@ -596,7 +598,37 @@ class Engine:
         fe, pu = self._pool_f_end, self._pool_used
         ops.split_tf32(self.pool[fe:pu], self.pool_hi[fe:pu], self.pool_lo[fe:pu], pu - fe)
         marks = {m[0]: m for m in self.bucket_marks}
+        # Weight gradients run on a side stream next to the data gradient(s) that follow them: the two only share
+        # read-only inputs, and the tail of one persistent kernel (partial last wave) is filled by the other.
+        # Any other launch first waits for the outstanding weight gradient (its dy scratch may be overwritten).
+        if not self.overlap_wgrad:
+            for i, op in enumerate(self.bwd, start=1):
+                op()
+                if on_bucket is not None and i in marks:
+                    on_bucket(marks[i][1], marks[i][2])
+            return
+        main = torch.cuda.current_stream()
+        side = self._side_stream
+        pending = None
         for i, op in enumerate(self.bwd, start=1):
-            op()
-            if on_bucket is not None and i in marks:
-                on_bucket(marks[i][1], marks[i][2])
+            if isinstance(op, WgradOp):
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    op()
+                pending = torch.cuda.Event()
+                pending.record(side)
+            else:
+                if pending is not None and not isinstance(op, ConvOp):
+                    main.wait_event(pending)
+                    pending = None
+                op()
+            if i in marks:
+                if pending is not None:
+                    main.wait_event(pending)
+                    pending = None
+                if on_bucket is not None:
+                    on_bucket(marks[i][1], marks[i][2])
+        if pending is not None:
+            main.wait_event(pending)
