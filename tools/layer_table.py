@@ -20,6 +20,8 @@ batch["qlens_cpu"] = batch["qlens"].cpu()
 for _ in range(2):
     fs.step(batch)
 torch.cuda.synchronize()
+eng = net.engine_for(B, 20)
+eng.overlap_wgrad = False          # weight gradients in line, so that per-launch intervals do not overlap
 prof = ops.LaunchProfiler(); ops.PROFILER = prof
 fs.step(batch)
 torch.cuda.synchronize()

@@ -212,14 +212,41 @@ class Engine:
         return self.bwd_operand(dy, self.B * L["hout"] * L["wout"], L["cout"])
 
     def conv_dgrad(self, L, dy, dy_lo, dx, out_mask=None, residual=None, accumulate=False):
-        k, cin, cout = L["k"], L["cin"], L["cout"]
+        k, cin, cout, stride = L["k"], L["cin"], L["cout"], L["stride"]
         wt, wt_hi, wt_lo = self.pool_alloc(cin * k * k * cout)
         w = L["w"]
         self.prep_bwd.append(lambda: ops.weight_transpose_flip(w, wt, cout, k, k, cin))
-        rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, L["stride"], L["pad"])
-        self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=L["stride"],
-                               out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl,
-                               w_lo=wt_lo, x_lo=dy_lo))
+        epi = dict(out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl)
+        if stride == 2 and k == 3 and L["pad"] == 1:
+            # four parity classes of input pixels, each a dense 1- or 2-tap conv over dy (geometry.dgrad_rows_s2_class):
+            # a quarter of the MMA work of the zero-stuffed formulation
+            wt4 = wt.view(cin, 3, 3, cout)
+            for ey in (0, 1):
+                for ex in (0, 1):
+                    sr, sc_ = (slice(1, 2), slice(0, 3, 2))[ey], (slice(1, 2), slice(0, 3, 2))[ex]
+                    kr, ks = 1 + ey, 1 + ex
+                    wc, wc_hi, wc_lo = self.pool_alloc(cin * kr * ks * cout)
+                    self.prep_bwd.append(lambda wc=wc, sr=sr, sc_=sc_, kr=kr, ks=ks:
+                                         wc.view(cin, kr, ks, cout).copy_(wt4[:, sr, sc_, :]))
+                    key = ("dgrad_s2", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, ey, ex)
+                    if key not in self._rows_cache:
+                        self._rows_cache[key] = geometry.dgrad_rows_s2_class(self.B, L["hin"], L["win"], cin, L["hout"],
+                                                                             L["wout"], cout, ey, ex).to(self.device)
+                    rows = self._rows_cache[key]
+                    self.bwd.append(ConvOp(dy, wc_hi, dx, rows, rows.shape[0], cout, cin, kr, ks, w_lo=wc_lo, x_lo=dy_lo, **epi))
+            return
+        if stride == 2 and k == 1 and L["pad"] == 0 and accumulate and out_mask is None and residual is None:
+            # only the even pixels receive anything: one row per dy pixel, accumulated into the already written dx
+            key = ("dgrad_1x1_s2", L["hin"], L["win"], cin, L["hout"], L["wout"], cout)
+            if key not in self._rows_cache:
+                self._rows_cache[key] = geometry.dgrad_rows_1x1_s2(self.B, L["hin"], L["win"], cin, L["hout"], L["wout"],
+                                                                   cout).to(self.device)
+            rows = self._rows_cache[key]
+            self.bwd.append(ConvOp(dy, wt_hi, dx, rows, rows.shape[0], cout, cin, 1, 1, w_lo=wt_lo, x_lo=dy_lo, **epi))
+            return
+        rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, stride, L["pad"])
+        self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=stride,
+                               w_lo=wt_lo, x_lo=dy_lo, **epi))
 
     def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True):
         """BatchNorm backward; returns the lo image of dx (written by the same kernel) for the GEMMs that follow."""
@@ -333,8 +360,8 @@ class Engine:
                     drd = sB[:ro * w4]
                     lod = self.bn_backward(L["bnD"], dz, L["rd"], drd, mask_mode=0)
                     self.conv_wgrad(L["Ld"], drd, lod)
-                    self.conv_dgrad(L["Ld"], drd, lod, L["g_in"], accumulate=L["acc_in"])
-                    self.conv_dgrad(L["La"], da1, lo1, L["g_in"], accumulate=True)
+                    self.conv_dgrad(L["La"], da1, lo1, L["g_in"], accumulate=L["acc_in"])      # writes every pixel
+                    self.conv_dgrad(L["Ld"], drd, lod, L["g_in"], accumulate=True)            # stride 2: even pixels only
                 else:
                     self.conv_dgrad(L["La"], da1, lo1, L["g_in"], residual=dz, accumulate=L["acc_in"])
             return emit

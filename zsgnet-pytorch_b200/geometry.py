@@ -39,5 +39,30 @@ def dgrad_rows(B, hin, win, cin, hout, wout, cout, R, stride, pad, dy_off=0, dx_
     return _pack(base, y + off, x + off, np.full(n, hout), np.full(n, wout), out)
 
 
+def dgrad_rows_s2_class(B, hin, win, cin, hout, wout, cout, ey, ex, dy_off=0, dx_off=0):
+    """Data gradient of a 3x3 / stride 2 / pad 1 conv, restricted to the input pixels (y, x) = (2i + ey, 2j + ex).
+    For one parity class only the filter rows r with (y + 1 - r) even contribute (r = 1 for ey = 0; r = 2, 0 for
+    ey = 1, reading dY rows i, i + 1), so the class is a small stride-1 conv over dY with 1 or 2 taps per axis and
+    no zero-stuffed taps at all (in_div = 1).  Rows are (b, i, j); `out` scatters to the class's pixels of dX."""
+    ni, nj = (hin - ey + 1) // 2, (win - ex + 1) // 2
+    b, i, j = np.meshgrid(np.arange(B), np.arange(ni), np.arange(nj), indexing="ij")
+    b, i, j = b.ravel(), i.ravel(), j.ravel()
+    base = dy_off + b * (hout * wout * cout)
+    out = dx_off + ((b * hin + 2 * i + ey) * win + 2 * j + ex) * cin
+    n = b.shape[0]
+    return _pack(base, i, j, np.full(n, hout), np.full(n, wout), out)
+
+
+def dgrad_rows_1x1_s2(B, hin, win, cin, hout, wout, cout, dy_off=0, dx_off=0):
+    """Data gradient of a 1x1 / stride 2 conv: only the even input pixels receive anything, one row per dY pixel
+    (b, p, q) scattering to dX pixel (2p, 2q); the caller accumulates into a dX that is already written."""
+    b, p, q = np.meshgrid(np.arange(B), np.arange(hout), np.arange(wout), indexing="ij")
+    b, p, q = b.ravel(), p.ravel(), q.ravel()
+    base = dy_off + b * (hout * wout * cout)
+    out = dx_off + ((b * hin + 2 * p) * win + 2 * q) * cin
+    n = b.shape[0]
+    return _pack(base, p, q, np.full(n, hout), np.full(n, wout), out)
+
+
 def concat_rows(tables):
     return torch.cat(tables, dim=0).contiguous()
