@@ -78,6 +78,43 @@ def synthetic_batch(B, seed=0, T=20, img_hw=300, pin=False):
     return {k: v.pin_memory() for k, v in out.items()} if pin else out
 
 
+class DevicePrefetcher:
+    """Wraps an iterable of host batches (pinned memory) and yields device batches, copying batch i + 1 on a side
+    stream while batch i is being used -- what `Learner.train_epoch`'s `batch[k].to(device)` (utils.py:405-406) does,
+    taken off the critical path.  The consumer's stream waits on the copy's event, and the tensors are recorded on it
+    so the allocator does not recycle them early."""
+
+    def __init__(self, batches, device):
+        self.it, self.device = iter(batches), torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.next = self._fetch()
+
+    def _fetch(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(self.stream):
+            dev = {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        dev, ev = self.next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for v in dev.values():
+            v.record_stream(cur)
+        self.next = self._fetch()
+        return dev
+
+
 def collater(batch):
     """dat_loader.py:187-196: stack, cast everything to float, trim qvec to the batch's longest phrase."""
     qlens = torch.Tensor([i["qlens"] for i in batch])
