@@ -6,14 +6,21 @@
 // gradient.  Geometry comes from a 16-byte row table (zsg_row_t), so strides, padding, the
 // stride-2 data gradient and the six-level shared head are data, not code.
 //
-// Arithmetic: fp32 in HBM; each operand tile is split on the fly into a TF32-exact high part
-// and a residual low part, and D += Ah*Bh + Ah*Bl + Al*Bh is issued as three kind::tf32 MMAs
-// (3xTF32): fp32-accurate products, fp32 accumulation in TMEM.  This is what lets the fp32
-// configuration meet the reference's 1e-4 tolerance while still running on the tensor pipe.
+// Arithmetic: fp32 in HBM; D += Ah*Bh + Ah*Bl + Al*Bh is issued as three kind::tf32 MMAs (3xTF32): fp32-accurate
+// products, fp32 accumulation in TMEM, promoted to registers every few K blocks.  This is what lets the fp32
+// configuration meet the reference's 1e-4 tolerance while still running on the tensor pipe.  The tensor core
+// reads a raw fp32 word as its TF32 truncation, so a tensor is its own high part; the low part is a second
+// image (lo = v - trunc(v)).
 //
-// Producers: im2col gather -> optional BatchNorm affine + ReLU -> hi/lo split -> 128B-swizzled
-// K-major smem tiles.  Stages are handed over with mbarriers: full[s] (128 producer arrivals after
-// fence.proxy.async), empty[s] / acc_full[a] (tcgen05.commit), acc_empty[a] (256 drain arrivals).
+// Kernels in this file (all share the tiling, the barrier protocol, the two MMA-issuer warps and the drain):
+//   conv_tc_async_kernel<BN>          product path: input + remainder image by cp.async, weight images by TMA
+//   wgrad_tc_async_kernel<BN,TMA_DY>  product path: x images by cp.async, dy images by TMA (or cp.async)
+//   conv_tc_kernel<BN,PRO>            register path: gather -> BatchNorm affine / ReLU -> split in registers -> smem
+//   conv_tc_generic_kernel<BN>        register path with weights gathered as well (no pre-split weight images)
+//   wgrad_tc_kernel<BN>               register path of the weight gradient
+//   conv_simt_kernel / wgrad_simt_kernel   plain-FMA check kernels (tests only)
+// Stages are handed over with mbarriers: full[s] (producer arrivals / cp.async completions / TMA bytes),
+// empty[s] and acc_full[a] (tcgen05.commit), acc_empty[a] (256 drain arrivals), token[w] (issuer hand-over).
 // Warp roles and the chunked-promotion scheme are described above setup_pipeline().
 #include <cuda.h>
 #include <string.h>

@@ -437,6 +437,7 @@ class Engine:
         rows_ih, rows_hh = r11(B * T, E, G), r11(B * T, Hh, G)
         rows_ihr, rows_hhr = r11(B, E, G), r11(B, Hh, G)
         wih_hi, wih_lo = self.arena_split_views("lstm.weight_ih_l0")
+        lstm_first = len(self.fwd)                           # forward items [lstm_first, lstm_end) = the query encoder
         _, qv_lo = self.fwd_operand(qv, B * T, E)
         self.fwd.append(("op", ConvOp(qv, wih_hi, gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl, w_lo=wih_lo, x_lo=qv_lo)))
         self.fwd.append(("fn", lambda: ops.weight_transpose_flip(P("weight_hh_l0"), whh_t, G, 1, 1, Hh)))
@@ -445,6 +446,7 @@ class Engine:
         self.fwd.append(("fn", lambda: ops.lstm_rev_step(qv, P("weight_ih_l0_reverse"), P("weight_hh_l0_reverse"),
                                                          P("bias_ih_l0_reverse"), P("bias_hh_l0_reverse"), h0c0[2],
                                                          h0c0[3], lens, B, T, E, xlast, rgates, lang)))
+        self._lstm_items = (lstm_first, len(self.fwd))
         Gd = lambda n: st.grad_flat("lstm." + n)
 
         def lstm_bwd():
@@ -602,13 +604,32 @@ class Engine:
         ops.split_tf32(self.store.param_arena, self.arena_hi, self.arena_lo, self.store.total)
         fe = self._pool_f_end
         ops.split_tf32(self.pool, self.pool_hi, self.pool_lo, fe)
-        for item in self.fwd:
-            if item[0] == "op":
-                item[1]()
-            elif item[0] == "fn":
-                item[1]()
-            else:
+        def run(item):
+            if item[0] == "bn":
                 (item[1] if training else item[2])()
+            else:
+                item[1]()
+
+        lo, hi = self._lstm_items
+        side = self._side_stream
+        if side is not None:
+            # the query encoder (20 sequential LSTM steps, latency-bound) only depends on the inputs: it runs on the side
+            # stream under the image trunk and is joined before the language vector is tiled into the head input
+            main = torch.cuda.current_stream()
+            start = torch.cuda.Event()
+            start.record(main)
+            side.wait_event(start)
+            with torch.cuda.stream(side):
+                for item in self.fwd[lo:hi]:
+                    run(item)
+            done = torch.cuda.Event()
+            done.record(side)
+        for i, item in enumerate(self.fwd):
+            if lo <= i < hi and side is not None:
+                continue
+            if i == hi and side is not None:
+                main.wait_event(done)
+            run(item)
         if training:
             for bn in self.bns:
                 pass                                      # num_batches_tracked is bumped in one op below
