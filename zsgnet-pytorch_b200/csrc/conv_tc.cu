@@ -392,18 +392,21 @@ __device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_bas
   }
 }
 
-// ragged rows (channel count or row offset not a multiple of 4: the [B, A, 5] head output): scalar, out of line
-__device__ __noinline__ void epilogue_store_ragged(const zsg_conv_params& p, int off_r, int n, float4 v4) {
+// ragged rows (channel count or row offset not a multiple of 4: the [B, A, 5] head output): scalar, out of line.
+// (Arguments by value: a reference to the kernel parameter block forces a local-memory copy of it, and with ~6 KB of
+// L1 left every read of that copy is an L2 round trip.)
+__device__ __noinline__ void epilogue_store_ragged(float* y, const float* out_mask, const float* residual, int accumulate,
+                                                   int out_relu, int cout, int off_r, int n, float4 v4) {
   const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-  float* yrow = p.y + (int64_t)off_r + n;
+  float* yrow = y + (int64_t)off_r + n;
 #pragma unroll 1
   for (int q = 0; q < 4; ++q) {
-    if (n + q >= p.cout) break;
+    if (n + q >= cout) break;
     float u = v[q];
-    if (p.out_mask && !(p.out_mask[(int64_t)off_r + n + q] > 0.f)) u = 0.f;
-    if (p.residual) u += p.residual[(int64_t)off_r + n + q];
-    if (p.accumulate) u += yrow[q];
-    if (p.out_relu) u = fmaxf(u, 0.f);
+    if (out_mask && !(out_mask[(int64_t)off_r + n + q] > 0.f)) u = 0.f;
+    if (residual) u += residual[(int64_t)off_r + n + q];
+    if (accumulate) u += yrow[q];
+    if (out_relu) u = fmaxf(u, 0.f);
     yrow[q] = u;
   }
 }
@@ -450,36 +453,53 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         if (n + 3 < p.cout) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
         else { bias4.x = __ldg(p.bias + n); if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1); if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2); }
       }
-#pragma unroll 1                                    // (fully unrolled, the epilogue alone was > 100 KB of code and ran
-      for (int i = 0; i < 4; ++i) {                       //  out of the instruction cache: 8.5 k cycles per 64 KB tile)
-        const int r = i * 8 + rsel;
-        const int off_r = __shfl_sync(0xffffffffu, out_off, r);
-        const bool ok_r = __shfl_sync(0xffffffffu, (int)row_ok, r) != 0;
-        if (!ok_r || n >= p.cout) continue;
-        float4 v4 = *reinterpret_cast<const float4*>(stg + r * 20 + c4);
-        v4.x += bias4.x; v4.y += bias4.y; v4.z += bias4.z; v4.w += bias4.w;
-        float* yrow = p.y + (int64_t)off_r + n;
-        const bool vec = ((p.cout & 3) == 0) && ((off_r & 3) == 0) && (n + 3 < p.cout);
+      // Two rows per pass, one operand array at a time (mask, residual, accumulate read) through ONE pair of
+      // temporaries: the two loads of a pair are in flight together, which halves the exposed load latencies of the
+      // short-K data gradients (row by row they cost ~800 cycles each).  Loop, not unrolled: inlined four times with
+      // the ragged path the epilogue was > 100 KB of code and ran out of the instruction cache.
+#pragma unroll 1
+      for (int ih = 0; ih < 2; ++ih) {
+        const int r0 = (ih * 2) * 8 + rsel, r1 = r0 + 8;
+        const int o0 = __shfl_sync(0xffffffffu, out_off, r0), o1 = __shfl_sync(0xffffffffu, out_off, r1);
+        const bool k0 = __shfl_sync(0xffffffffu, (int)row_ok, r0) != 0 && n < p.cout;
+        const bool k1 = __shfl_sync(0xffffffffu, (int)row_ok, r1) != 0 && n < p.cout;
+        float4 v0 = *reinterpret_cast<const float4*>(stg + r0 * 20 + c4);
+        float4 v1 = *reinterpret_cast<const float4*>(stg + r1 * 20 + c4);
+        v0.x += bias4.x; v0.y += bias4.y; v0.z += bias4.z; v0.w += bias4.w;
+        v1.x += bias4.x; v1.y += bias4.y; v1.z += bias4.z; v1.w += bias4.w;
+        const bool vec = ((p.cout & 3) == 0) && (((o0 | o1) & 3) == 0) && (n + 3 < p.cout);
         if (vec) {
+          const int64_t a0 = (int64_t)o0 + n, a1 = (int64_t)o1 + n;
+          float4 q0, q1;
           if (p.out_mask) {
-            const float4 m = __ldg(reinterpret_cast<const float4*>(p.out_mask + (int64_t)off_r + n));
-            if (!(m.x > 0.f)) v4.x = 0.f;
-            if (!(m.y > 0.f)) v4.y = 0.f;
-            if (!(m.z > 0.f)) v4.z = 0.f;
-            if (!(m.w > 0.f)) v4.w = 0.f;
+            if (k0) q0 = __ldg(reinterpret_cast<const float4*>(p.out_mask + a0));
+            if (k1) q1 = __ldg(reinterpret_cast<const float4*>(p.out_mask + a1));
+            if (k0) { if (!(q0.x > 0.f)) v0.x = 0.f; if (!(q0.y > 0.f)) v0.y = 0.f; if (!(q0.z > 0.f)) v0.z = 0.f; if (!(q0.w > 0.f)) v0.w = 0.f; }
+            if (k1) { if (!(q1.x > 0.f)) v1.x = 0.f; if (!(q1.y > 0.f)) v1.y = 0.f; if (!(q1.z > 0.f)) v1.z = 0.f; if (!(q1.w > 0.f)) v1.w = 0.f; }
           }
           if (p.residual) {
-            const float4 q = *reinterpret_cast<const float4*>(p.residual + (int64_t)off_r + n);
-            v4.x += q.x; v4.y += q.y; v4.z += q.z; v4.w += q.w;
+            if (k0) q0 = *reinterpret_cast<const float4*>(p.residual + a0);
+            if (k1) q1 = *reinterpret_cast<const float4*>(p.residual + a1);
+            if (k0) { v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w; }
+            if (k1) { v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w; }
           }
           if (p.accumulate) {
-            const float4 q = *reinterpret_cast<const float4*>(yrow);
-            v4.x += q.x; v4.y += q.y; v4.z += q.z; v4.w += q.w;
+            if (k0) q0 = *reinterpret_cast<const float4*>(p.y + a0);
+            if (k1) q1 = *reinterpret_cast<const float4*>(p.y + a1);
+            if (k0) { v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w; }
+            if (k1) { v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w; }
           }
-          if (p.out_relu) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
-          if (!(ablate & 16)) *reinterpret_cast<float4*>(yrow) = v4;
+          if (p.out_relu) {
+            v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v0.z = fmaxf(v0.z, 0.f); v0.w = fmaxf(v0.w, 0.f);
+            v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); v1.z = fmaxf(v1.z, 0.f); v1.w = fmaxf(v1.w, 0.f);
+          }
+          if (!(ablate & 16)) {
+            if (k0) *reinterpret_cast<float4*>(p.y + a0) = v0;
+            if (k1) *reinterpret_cast<float4*>(p.y + a1) = v1;
+          }
         } else {
-          epilogue_store_ragged(p, off_r, n, v4);
+          if (k0) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o0, n, v0);
+          if (k1) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o1, n, v1);
         }
       }
     }
@@ -692,9 +712,10 @@ constexpr int FULL_COUNT_TMA = NPROD / 32 + 1;
 // Register re-balancing (cp.async kernels): the producers only form addresses, the drain warps hold 64 accumulators
 // per thread plus the epilogue's state.  The carve-out leaves ~6 KB of L1, so a spilled register costs an L2 round
 // trip: with the launch-time 96 registers the epilogue loop reloaded two spilled values per iteration and took
-// 7.5 k cycles per tile; producers give registers up, drain warps take them.
-__device__ __forceinline__ void regs_release_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 64;"); }
-__device__ __forceinline__ void regs_take_drain() { asm volatile("setmaxnreg.inc.sync.aligned.u32 128;"); }
+// 7.5 k cycles per tile; producers give registers up (96 -> 56), drain warps take exactly what was freed (96 -> 136): setmaxnreg.inc draws
+// from the CTA's own pool, a larger request never returns.
+__device__ __forceinline__ void regs_release_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); }
+__device__ __forceinline__ void regs_take_drain() { asm volatile("setmaxnreg.inc.sync.aligned.u32 136;"); }
      // one elected arrive per producer warp + the expect_tx arrive
 
 template <int BN, int PRO>
