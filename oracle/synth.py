@@ -108,13 +108,64 @@ def param_specs():
     return specs
 
 
-def make_state_dict(seed=0):
+VGG_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, "C", 512, 512, 512, "M", 512, 512, 512)   # ssd_vgg.py:174-177
+# extras (ssd_vgg.py:140-154, cfg at 179-182): (cin, cout, kernel, stride, pad); ReLU after each (ssd_vgg.py:92-93)
+VGG_EXTRAS = ((1024, 256, 1, 1, 0), (256, 512, 3, 2, 1), (512, 128, 1, 1, 0), (128, 256, 3, 2, 1),
+              (256, 128, 1, 1, 0), (128, 256, 3, 1, 0), (256, 128, 1, 1, 0), (128, 256, 3, 1, 0))
+VGG_MBOX = (4, 6, 6, 6, 4, 4)                                                                    # ssd_vgg.py:183-186
+
+
+def vgg_layers():
+    """ssd_vgg.py:111-133 as a flat list aligned with the `vgg` ModuleList indices:
+    ("conv", cin, cout, k, pad, dil) | ("relu",) | ("pool", k, stride, pad, ceil)."""
+    out, cin = [], 3
+    for v in VGG_CFG:
+        if v == "M":
+            out.append(("pool", 2, 2, 0, False))
+        elif v == "C":
+            out.append(("pool", 2, 2, 0, True))
+        else:
+            out += [("conv", cin, v, 3, 1, 1), ("relu",)]
+            cin = v
+    out += [("pool", 3, 1, 1, False), ("conv", 512, 1024, 3, 6, 6), ("relu",), ("conv", 1024, 1024, 1, 0, 1), ("relu",)]
+    return out
+
+
+def vgg_param_specs():
+    """(key, shape, kind) of ZSGNet over SSDBackBone (mdl.py:162-168, ssd_vgg.py:31-52): vgg.*, fproj1-3,
+    extras.*, the unused loc.* / conf.* multibox heads (built at ssd_vgg.py:157-171, never called), then the
+    shared head and the LSTM as in param_specs()."""
+    specs = []
+    e = "backbone.encoder."
+
+    def conv(name, cin, cout, k):
+        specs.append((name + ".weight", (cout, cin, k, k), "conv"))
+        specs.append((name + ".bias", (cout,), "bias"))
+    for i, L in enumerate(vgg_layers()):
+        if L[0] == "conv":
+            conv(f"{e}vgg.{i}", L[1], L[2], L[3])
+    conv(e + "fproj1", 512, 256, 1)
+    conv(e + "fproj2", 1024, 256, 1)
+    conv(e + "fproj3", 512, 256, 1)
+    for i, (cin, cout, k, _, _) in enumerate(VGG_EXTRAS):
+        conv(f"{e}extras.{i}", cin, cout, k)
+    src_ch = (512, 1024, 512, 256, 256, 256)
+    for i, (c, nb) in enumerate(zip(src_ch, VGG_MBOX)):
+        conv(f"{e}loc.{i}", c, nb * 4, 3)
+    for i, (c, nb) in enumerate(zip(src_ch, VGG_MBOX)):
+        conv(f"{e}conf.{i}", c, nb * 21, 3)
+    specs += [s for s in param_specs() if s[0].startswith(("att_reg_box.", "lstm."))]
+    return specs
+
+
+def make_state_dict(seed=0, model="retina"):
     """Deterministic random-init weights with the reference's names and shapes.
     Distributions mimic the PyTorch defaults in scale; BN affine parameters are
     randomised (not 1/0) so that parity tests exercise them."""
     sd = {}
-    for i, (key, shape, kind) in enumerate(param_specs()):
-        g = torch.Generator().manual_seed(seed * 100003 + i)
+    specs, base = (param_specs(), 0) if model == "retina" else (vgg_param_specs(), 50000)
+    for i, (key, shape, kind) in enumerate(specs):
+        g = torch.Generator().manual_seed(seed * 100003 + base + i)
         if kind == "conv":
             fan_in = shape[1] * shape[2] * shape[3]
             t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in) * 0.8
@@ -143,9 +194,9 @@ def make_state_dict(seed=0):
     return sd
 
 
-def default_cfg():
+def default_cfg(model="retina"):
     """The hot-path keys of configs/cfg.json:1-43 (only those the path reads)."""
-    return {"do_norm": False, "use_same_atb": True, "mdl_to_use": "retina",
+    return {"do_norm": False, "use_same_atb": True, "mdl_to_use": model,
             "resize_img": [300, 300], "use_multi": True, "use_focal": True,
             "use_softmax": False, "alpha": 0.25, "gamma": 2, "emb_dim": 300,
             "matching_threshold": 0.6, "use_bidirectional": True, "lstm_dim": 128,

@@ -249,6 +249,37 @@ def fpn(sd, c3, c4, c5):
     return [p3, p4, p5, p6, p7, p8]
 
 
+def ssd_vgg_feats(sd, img):
+    """SSDBackBone.encode_feats (mdl.py:162-168) = SSD.forward (ssd_vgg.py:54-102) for a 300x300 input:
+    VGG-16 up to relu(conv4_3) (vgg[0:23]) -> x / ||x||_2 over channels (ssd_vgg.py:80; no eps, no learned
+    scale) = source 0; the rest of VGG with pool5 (3x3/1), the dilated conv6 and conv7 = source 1; eight extra
+    convs, ReLU after each, every second one a source (92-95); fproj1..3 (1x1 to 256) on the first three
+    sources, the last three are used as they are (97-98).  Sizes 38, 19, 10, 5, 3, 1."""
+    e = "backbone.encoder."
+
+    def run(x, lo, hi):
+        for i, L in enumerate(synth.vgg_layers()):
+            if not lo <= i < hi:
+                continue
+            if L[0] == "conv":
+                x = F.conv2d(x, sd[f"{e}vgg.{i}.weight"], sd[f"{e}vgg.{i}.bias"], padding=L[4], dilation=L[5])
+            elif L[0] == "relu":
+                x = F.relu(x)
+            else:
+                x = F.max_pool2d(x, L[1], L[2], L[3], ceil_mode=L[4])
+        return x
+    x = run(img, 0, 23)
+    sources = [x / x.norm(dim=1, keepdim=True)]
+    x = run(x, 23, len(synth.vgg_layers()))
+    sources.append(x)
+    for i, (_, _, _, stride, pad) in enumerate(synth.VGG_EXTRAS):
+        x = F.relu(F.conv2d(x, sd[f"{e}extras.{i}.weight"], sd[f"{e}extras.{i}.bias"], stride=stride, padding=pad))
+        if i % 2 == 1:
+            sources.append(x)
+    proj = [F.conv2d(sources[j], sd[f"{e}fproj{j + 1}.weight"], sd[f"{e}fproj{j + 1}.bias"]) for j in range(3)]
+    return proj + sources[3:]
+
+
 def lstm_query(sd, qvec, qlens, h0, c0):
     """mdl.py:296-336.  One-layer bi-LSTM (gate order i,f,g,o; two bias vectors).  The
     returned vector for sample b is lstm_out[len_b-1, b, :]: the forward direction after
@@ -335,16 +366,20 @@ def draw_h0c0(B):
 
 
 def zsgnet_forward(sd, batch, training=True, h0c0=None, batched_lstm=True, return_inter=False):
-    """mdl.py:338-403."""
+    """mdl.py:338-403.  The trunk is chosen by the keys present: SSD-VGG (mdl.py:413-418) or ResNet-50+FPN."""
     img, qvec, qlens = batch["img"], batch["qvec"], batch["qlens"]
     max_qlen = int(qlens.max().item())
     qvec = qvec[:, :max_qlen].contiguous()
     h0, c0 = h0c0 if h0c0 is not None else draw_h0c0(img.shape[0])
     h0, c0 = h0.to(img.device), c0.to(img.device)          # drawn on the CPU, then moved (mdl.py:291-292)
     lang = (lstm_query_batched if batched_lstm else lstm_query)(sd, qvec, qlens, h0, c0)
-    bn = BNState(sd, training)
-    c3, c4, c5 = resnet50_c3c4c5(sd, img, bn)
-    feats = fpn(sd, c3, c4, c5)
+    c3 = c4 = c5 = None
+    if "backbone.encoder.vgg.0.weight" in sd:
+        feats = ssd_vgg_feats(sd, img)
+    else:
+        bn = BNState(sd, training)
+        c3, c4, c5 = resnet50_c3c4c5(sd, img, bn)
+        feats = fpn(sd, c3, c4, c5)
     att, bbx = fuse_and_head(sd, feats, lang)
     out = {"att_out": att, "bbx_out": bbx,
            "feat_sizes": torch.tensor([[f.shape[2], f.shape[3]] for f in feats]),

@@ -67,9 +67,70 @@ def import_reference():
     return anchors, loss, evaluator, mdl, cfg
 
 
+def vgg_cases(synth, anchors, loss, evaluator, mdl, cfg, out_dir):
+    """Config 5's trunk: ZSGNet over SSDBackBone(build_ssd('train')) (mdl.py:413-418, minus the torch.load of
+    ./weights/vgg16_reducedfc.pth, which is absent: SURVEY.md section 8(c) step 7), seeded weights of
+    synth.make_state_dict(0, 'ssd_vgg')."""
+    import ssd_vgg
+    ratios, scales = synth.ratios_scales()
+    cpu = torch.device("cpu")
+    cfg.mdl_to_use = "ssd_vgg"
+    encoder = ssd_vgg.build_ssd("train", cfg=cfg)
+    net = mdl.ZSGNet(mdl.SSDBackBone(encoder, cfg), 9, cfg=cfg)
+    crit = loss.get_default_loss(ratios, scales, cfg)
+    crit.get_anchors = partial(anchors.create_anchors, ratios=ratios, scales=scales, flatten=True, device=cpu)
+    ev = evaluator.get_default_eval(ratios, scales, cfg)
+    ev.get_anchors = partial(anchors.create_anchors, ratios=ratios, scales=scales, flatten=True, device=cpu)
+    full = {}
+    for name, B, seed, var_len in (("vgg2", 2, 31, False), ("vgg3v", 3, 32, True)):
+        print("load_state_dict:", net.load_state_dict(synth.make_state_dict(0, "ssd_vgg"), strict=True))
+        net.train()
+        net.zero_grad()
+        crit.anchs = None
+        ev.anchs = None
+        batch = synth.make_batch(B, seed=seed, var_len=var_len)
+        torch.manual_seed(seed)
+        out = net(batch)
+        ls = crit(out, batch)
+        ls["loss"].mean().backward()
+        with torch.no_grad():
+            met = ev(out, batch)
+        grads = {k: p.grad for k, p in net.named_parameters()}
+        gnorm = {k: (float(g.double().norm()) if g is not None else None) for k, g in grads.items()}
+        e = "backbone.encoder."
+        arrs = dict(
+            att_stride=out["att_out"].detach().squeeze(-1)[:, ::53].numpy(),
+            bbx_stride=out["bbx_out"].detach()[:, ::53].numpy(),
+            best_ids=torch.sigmoid(out["att_out"].detach()).squeeze(-1).max(1)[1].numpy(),
+            pred_boxes=met["pred_boxes"].numpy(), pred_scores=met["pred_scores"].numpy())
+        for k in (e + "vgg.0.bias", e + "vgg.21.bias", e + "vgg.31.bias", e + "fproj1.bias", e + "extras.7.bias",
+                  "att_reg_box.5.bias", "lstm.bias_ih_l0"):
+            arrs["g:" + k] = grads[k].numpy()
+        for k in (e + "vgg.0.weight", e + "vgg.14.weight", e + "vgg.21.weight", e + "vgg.28.weight", e + "vgg.31.weight",
+                  e + "vgg.33.weight", e + "fproj1.weight", e + "fproj2.weight", e + "fproj3.weight",
+                  e + "extras.1.weight", e + "extras.5.weight", e + "extras.6.weight", "att_reg_box.0.0.weight"):
+            arrs["gs:" + k] = grads[k].flatten()[::101].numpy()
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), **arrs)
+        full[name] = dict(B=B, seed=seed, var_len=var_len, loss=ls["loss"].item(), cls_ls=ls["cls_ls"].item(),
+                          box_ls=ls["box_ls"].item(), Acc=met["Acc"].item(), MaxPos=met["MaxPos"].item(),
+                          gnorm=gnorm)
+        print(name, full[name]["loss"], full[name]["cls_ls"], full[name]["box_ls"])
+    return full
+
+
 def main():
     from oracle import synth
     anchors, loss, evaluator, mdl, cfg = import_reference()
+    if "vgg" in sys.argv[1:]:                      # add the SSD-VGG cases to an existing meta.json
+        torch.set_num_threads(8)
+        out_dir = os.path.join(REPO, "tests", "golden")
+        with open(os.path.join(out_dir, "meta.json")) as f:
+            meta = json.load(f)
+        meta["vgg_cases"] = vgg_cases(synth, anchors, loss, evaluator, mdl, cfg, out_dir)
+        with open(os.path.join(out_dir, "meta.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+        print("done (vgg)")
+        return
     torch.set_num_threads(8)
     ratios, scales = synth.ratios_scales()
     cpu = torch.device("cpu")
@@ -177,6 +238,7 @@ def main():
         idx = torch.nn.functional.interpolate(src, size=(o, o))[0, 0, :, 0].long().tolist()
         up[f"{i}->{o}"] = idx
     meta["upsample_idx"] = up
+    meta["vgg_cases"] = vgg_cases(synth, anchors, loss, evaluator, mdl, cfg, out_dir)
     meta["torch"] = torch.__version__
     with open(os.path.join(out_dir, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1)

@@ -75,6 +75,33 @@ def test_full_network_vs_reference(name, golden_meta):
     np.testing.assert_allclose(sd["backbone.encoder.layer4.2.bn3.running_var"].numpy(), z["l4_rv"], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["vgg2", "vgg3v"])
+def test_ssd_vgg_network_vs_reference(name, golden_meta):
+    """a-8: ZSGNet over the SSD-VGG trunk (ssd_vgg.py:54-102), restatement vs the reference's own modules."""
+    c = golden_meta["vgg_cases"][name]
+    z = load_npz(name)
+    sd = synth.make_state_dict(0, "ssd_vgg")
+    batch = synth.make_batch(c["B"], seed=c["seed"], var_len=c["var_len"])
+    ls, met, grads, out, _ = zo.train_step(sd, batch, seed=c["seed"], do_adam=False)
+    for k in ("loss", "cls_ls", "box_ls"):
+        assert ls[k].item() == pytest.approx(c[k], rel=RTOL)
+    assert met["Acc"].item() == c["Acc"] and met["MaxPos"].item() == c["MaxPos"]
+    att = out["att_out"].detach().squeeze(-1)
+    np.testing.assert_allclose(att[:, ::53].numpy(), z["att_stride"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(out["bbx_out"].detach()[:, ::53].numpy(), z["bbx_stride"], rtol=1e-3, atol=1e-4)
+    assert np.array_equal(met["idxs_best"].numpy(), z["best_ids"])
+    for k, ref in c["gnorm"].items():
+        if ref is None:                                        # loc.* / conf.*: built, never called
+            assert grads[k] is None or float(grads[k].abs().sum()) == 0.0, k
+        else:
+            assert float(grads[k].double().norm()) == pytest.approx(ref, rel=2e-3, abs=1e-7), k
+    for key in z.files:
+        if key.startswith("g:"):
+            np.testing.assert_allclose(grads[key[2:]].numpy(), z[key], rtol=2e-3, atol=1e-6)
+        elif key.startswith("gs:"):
+            np.testing.assert_allclose(grads[key[3:]].flatten()[::101].numpy(), z[key], rtol=2e-3, atol=1e-6)
+
+
 def test_loop_and_batched_lstm_agree():
     sd = synth.make_state_dict(0)
     batch = synth.make_batch(5, seed=3, var_len=True)
