@@ -49,7 +49,7 @@ typedef struct {
   int32_t out;
 } zsg_row_t;
 
-/* conv implicit GEMM:  y[row.out + n] = epi( sum_{r,s,c} pro(x[row.base + ((y0+r)/div*win + (x0+s)/div)*cin + c]) * w[n][r][s][c] )
+/* conv implicit GEMM:  y[row.out + n] = epi( sum_{r,s,c} pro(x[row.base + ((y0+r*dil)/div*win + (x0+s*dil)/div)*cin + c]) * w[n][r][s][c] )
  * Replaces nn.Conv2d forward and its data-gradient on: torchvision resnet50 convs (mdl.py:149-156),
  * FPN convs (fpn_resnet.py:157-172), head convs (mdl.py:235-244, 379-380), LSTM input projection
  * (mdl.py:319).  Arithmetic: 3xTF32 on tcgen05 tensor cores (fp32-accurate), fp32 accumulate in TMEM. */
@@ -75,6 +75,8 @@ typedef struct {
   const float* x_lo;       /* optional (needs w_lo, no in_scale / in_relu): fp32 remainders of x after TF32 truncation
                               (zsg_split_act), same indexing as x.  The input operand then goes global -> shared by
                               cp.async with no register pass: the tensor core reads x itself as the TF32 high part */
+  int32_t dil;             /* tap spacing: tap (r,s) reads (y0 + r*dil, x0 + s*dil); 0 means 1.  6 for the SSD conv6
+                              (ssd_vgg.py:129) and its data gradient                                              */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
@@ -99,6 +101,7 @@ typedef struct {
   const float* dy_lo;      /* (zsg_split_act); operands then go global -> shared by cp.async                         */
   int32_t dy_pitch;        /* > 0: rows[i].out == i * dy_pitch for every row (dy is a plain [m, dy_pitch] matrix, true for
                               every forward table of the path): dy / dy_lo are then fetched by TMA.  0: unknown        */
+  int32_t dil;             /* tap spacing as in zsg_conv_params (0 means 1)                                             */
 } zsg_wgrad_params;
 int zsg_conv_wgrad(const zsg_wgrad_params* p, zsg_stream_t stream);
 
@@ -168,6 +171,21 @@ int zsg_upsample_add_bwd(const float* ddst, float* dsrc, const int32_t* idx_y, c
 /* global average pool (fpn_resnet.py:177) and its gradient (accumulating). */
 int zsg_avgpool_fwd(const float* x, float* y, int b, int hw, int c, zsg_stream_t stream);
 int zsg_avgpool_bwd(const float* dy, float* dx, int b, int hw, int c, zsg_stream_t stream);
+/* SSD-VGG trunk glue (config 5; ssd_vgg.py).
+ * Generic NHWC max-pool: window k, stride, symmetric pad; (ho, wo) chosen by the caller (floor or ceil mode:
+ * nn.MaxPool2d(2,2), MaxPool2d(2,2,ceil_mode=True), MaxPool2d(3,1,1) at ssd_vgg.py:115-118,127).  argmax (one byte per
+ * output element) records the winning tap dy*k+dx, first maximum in scan order as ATen does. */
+int zsg_maxpool_fwd(const float* x, float* y, uint8_t* argmax, int b, int h, int w, int c, int k, int stride, int pad,
+                    int ho, int wo, zsg_stream_t stream);
+/* dx = gradient w.r.t. the pool input, gathered through the codes; mask (optional, indexed like dx: the pool's
+ * input, a ReLU output): dx = 0 where mask <= 0, i.e. the ReLU backward of vgg[k-1] folded in. */
+int zsg_maxpool_bwd(const uint8_t* argmax, const float* dy, const float* mask, float* dx, int b, int h, int w, int c,
+                    int k, int stride, int pad, int ho, int wo, zsg_stream_t stream);
+/* y[row] = x[row] / ||x[row]||_2 over the c channels (ssd_vgg.py:80: no eps, no learned scale); norm[row] is kept. */
+int zsg_l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int c, zsg_stream_t stream);
+/* dx (+)= dy / n - x * sum_c(dy * x) / n^3, zeroed where x <= 0 when mask_relu (x is the output of vgg[22]). */
+int zsg_l2norm_bwd(const float* dy, const float* x, const float* norm, float* dx, int64_t rows, int c, int accumulate,
+                   int mask_relu, zsg_stream_t stream);
 /* dx = (accumulate? dx : 0) + dy * (x > 0) */
 int zsg_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, int accumulate, zsg_stream_t stream);
 int zsg_axpy(const float* x, float* y, float a, int64_t n, zsg_stream_t stream); /* y += a*x */

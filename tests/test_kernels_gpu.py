@@ -699,3 +699,103 @@ def test_bn_kernels_write_operand_images(zsg):
     ops.split_act(dx, ref_lo, rows, C)
     torch.cuda.synchronize()
     assert torch.equal(dx_lo, ref_lo)
+
+
+# ------------------------------------------------------------------------------- SSD-VGG trunk glue (a-8)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_dilated_conv_fwd_dgrad_wgrad(zsg, impl):
+    """ssd_vgg.py:129: conv6 = 3x3, dilation 6, padding 6 (19x19 stays 19x19); forward, data and weight gradient
+    against torch; impl 0 = the cp.async tcgen05 path, 1 = SIMT check kernels."""
+    ops, geo = zsg
+    B, cin, H, cout, k, pad, dil = 2, 64, 19, 128, 3, 6, 6
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(B, cin, H, H, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda().requires_grad_(True)
+    bias = torch.randn(cout, generator=g).cuda()
+    y = F.conv2d(x, w, bias, padding=pad, dilation=dil)
+    assert y.shape[2] == H
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    M = B * H * H
+    xn, dyn, wk = nhwc(x.detach()), nhwc(dy), khwc(w.detach())
+    rows = geo.conv_rows(B, H, H, cin, H, H, cout, 1, pad).cuda()
+    hi, lo = torch.empty_like(wk), torch.empty_like(wk)
+    ops.split_tf32(wk, hi, lo, wk.numel())
+    x_lo, dy_lo = torch.empty_like(xn), torch.empty_like(dyn)
+    ops.split_act(xn, x_lo, M, cin)
+    ops.split_act(dyn, dy_lo, M, cout)
+    yk = torch.empty(B, H, H, cout, device="cuda")
+    if impl == 0:
+        ops.ConvOp(xn, hi, yk, rows, M, cin, cout, k, k, bias=bias, w_lo=lo, x_lo=x_lo, dil=dil)()
+    else:
+        ops.ConvOp(xn, wk, yk, rows, M, cin, cout, k, k, bias=bias, impl=1, dil=dil)()
+    wt = torch.empty(cin, k, k, cout, device="cuda")
+    ops.weight_transpose_flip(wk, wt, cout, k, k, cin)
+    thi, tlo = torch.empty_like(wt), torch.empty_like(wt)
+    ops.split_tf32(wt, thi, tlo, wt.numel())
+    drows = geo.dgrad_rows(B, H, H, cin, H, H, cout, k, 1, pad, dil=dil).cuda()
+    dx = torch.empty(B, H, H, cin, device="cuda")
+    if impl == 0:
+        ops.ConvOp(dyn, thi, dx, drows, M, cout, cin, k, k, w_lo=tlo, x_lo=dy_lo, dil=dil)()
+    else:
+        ops.ConvOp(dyn, wt, dx, drows, M, cout, cin, k, k, impl=1, dil=dil)()
+    dw = torch.zeros(cout, k, k, cin, device="cuda")
+    if impl == 0:
+        ops.WgradOp(xn, dyn, dw, rows, M, cin, cout, k, k, x_lo=x_lo, dy_lo=dy_lo, dy_pitch=cout, dil=dil)()
+    else:
+        ops.WgradOp(xn, dyn, dw, rows, M, cin, cout, k, k, impl=1, dil=dil)()
+    torch.cuda.synchronize()
+    assert rel_err(yk, nhwc(y)) < 2e-5
+    assert rel_err(dx, nhwc(x.grad)) < 2e-5
+    assert rel_err(dw, khwc(w.grad)) < 3e-5
+
+
+@pytest.mark.parametrize("case", [(2, 8, 10, 10, 2, 2, 0, False), (2, 12, 7, 9, 2, 2, 0, True), (2, 8, 75, 75, 2, 2, 0, True),
+                                  (3, 16, 19, 19, 3, 1, 1, False), (1, 4, 5, 6, 3, 2, 1, False)])
+def test_generic_maxpool_fwd_bwd(zsg, case):
+    """ssd_vgg.py:115-118,127: MaxPool2d(2,2), MaxPool2d(2,2,ceil_mode=True), MaxPool2d(3,1,1) on ReLU outputs (exact
+    zeros make ties: the first maximum in scan order must win, like ATen), backward with the ReLU mask folded in."""
+    ops, _ = zsg
+    B, C, H, W, k, stride, pad, ceil = case
+    g = torch.Generator().manual_seed(43)
+    pre = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    a = F.relu(pre)
+    y = F.max_pool2d(a, k, stride, pad, ceil_mode=ceil)
+    Ho, Wo = y.shape[2], y.shape[3]
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    an = nhwc(a.detach())
+    yk = torch.empty(B, Ho, Wo, C, device="cuda")
+    arg = torch.empty(B * Ho * Wo * C, dtype=torch.uint8, device="cuda")
+    ops.maxpool_fwd(an, yk, arg, B, H, W, C, k, stride, pad, Ho, Wo)
+    dx = torch.full((B, H, W, C), float("nan"), device="cuda")
+    ops.maxpool_bwd(arg, nhwc(dy), dx, B, H, W, C, k, stride, pad, Ho, Wo, mask=an)
+    torch.cuda.synchronize()
+    assert torch.equal(yk, nhwc(y))
+    assert torch.equal(dx, nhwc(pre.grad))
+
+
+def test_l2norm_fwd_bwd(zsg):
+    """ssd_vgg.py:80: s = x / x.norm(dim=1, keepdim=True) on relu(conv4_3) and its autograd (ReLU mask folded in,
+    accumulated onto the gradient that arrives through the other consumer of x)."""
+    ops, _ = zsg
+    B, C, H = 2, 512, 9
+    g = torch.Generator().manual_seed(45)
+    pre = torch.randn(B, C, H, H, generator=g).cuda().requires_grad_(True)
+    x = F.relu(pre)
+    s = x / x.norm(dim=1, keepdim=True)
+    ds = torch.randn(s.shape, generator=g).cuda()
+    s.backward(ds)
+    xn = nhwc(x.detach())
+    rows = B * H * H
+    y, norm = torch.empty_like(xn), torch.empty(rows, device="cuda")
+    ops.l2norm_fwd(xn, y, norm, rows, C)
+    other = torch.randn(B, H, H, C, generator=g).cuda()
+    dx = other.clone()
+    ops.l2norm_bwd(nhwc(ds), xn, norm, dx, rows, C, accumulate=True, mask_relu=True)
+    dx2 = torch.empty_like(dx)
+    ops.l2norm_bwd(nhwc(ds), xn, norm, dx2, rows, C)
+    torch.cuda.synchronize()
+    assert rel_err(y, nhwc(s)) < 1e-6
+    assert rel_err(dx - other, nhwc(pre.grad)) < 2e-5
+    assert rel_err(dx2 * (xn > 0), nhwc(pre.grad)) < 2e-5

@@ -25,14 +25,14 @@ class ConvParams(C.Structure):
                 ("m", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
                 ("in_div", C.c_int32), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
-                ("impl", C.c_int32), ("x_lo", C.c_void_p)]
+                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32)]
 
 
 class WgradParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p), ("rows", C.c_void_p),
                 ("m", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
                 ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32), ("split_k", C.c_int32),
-                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int32)]
+                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int32), ("dil", C.c_int32)]
 
 
 _P, _I, _L, _F, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
@@ -64,6 +64,10 @@ SIGNATURES = {
     "zsg_upsample_add_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "zsg_avgpool_fwd": [_P, _P, _I, _I, _I, _P],
     "zsg_avgpool_bwd": [_P, _P, _I, _I, _I, _P],
+    "zsg_maxpool_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "zsg_maxpool_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "zsg_l2norm_fwd": [_P, _P, _P, _L, _I, _P],
+    "zsg_l2norm_bwd": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "zsg_relu_bwd": [_P, _P, _P, _L, _I, _P],
     "zsg_axpy": [_P, _P, _F, _L, _P],
     "zsg_scale_dev": [_P, _L, _I, _L, _P, _P],

@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_generic_kernel(const zsg
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int4 e = rows_g[it * 16 + rsub];
-            int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+            int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
             const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
             bool ok = kvalid;
             if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int4 e = rows_g[it * 16 + rsub];
-          int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+          int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
           const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
           bool ok = kvalid;
           if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
@@ -941,7 +941,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int4 e = rows_g[it * 16 + rsub];
-            int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+            int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
             const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
             bool ok = kvalid;
             if (p.in_div == 2) { ok = ok && (((yy | xx) & 1) == 0); yy >>= 1; xx >>= 1; }
@@ -1067,7 +1067,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
         for (int q = 0; q < 4; ++q) {
           const int pixel = (hp * 4 + q) * 4 + ps;           // 0..31 within the K block
           const int4 e = eb[pixel];
-          const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+          const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
           const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
           oka[q] = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
           xa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1235,7 +1235,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
       if (warp_uniform) {
         // one tap for the whole warp: lane q decodes pixel q * 4 + ps once, the offsets are broadcast
         const int4 e = eb[(lane & 7) * 4 + ps];
-        const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+        const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
         const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
         const bool oka = (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
         const int my_ao = oka ? e.x + (yy * win + xx) * p.cin : -1;
@@ -1259,7 +1259,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
         for (int q = 0; q < 8; ++q) {
           const int pixel = q * 4 + ps;                      // 0..31 within the K block
           const int4 e = eb[pixel];
-          const int yy = (int)(short)(e.y & 0xFFFF) + tr, xx = (e.y >> 16) + ts;
+          const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
           const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
           const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
           const int r4 = pixel & 3;
@@ -1317,7 +1317,7 @@ __global__ void conv_simt_kernel(const zsg_conv_params p) {
   float acc = 0.f;
   for (int tr = 0; tr < p.r; ++tr)
     for (int ts = 0; ts < p.s; ++ts) {
-      int yy = e.y0 + tr, xx = e.x0 + ts;
+      int yy = e.y0 + tr * p.dil, xx = e.x0 + ts * p.dil;
       if (p.in_div == 2) {
         if ((yy | xx) & 1) continue;
         yy >>= 1;
@@ -1351,7 +1351,7 @@ __global__ void wgrad_simt_kernel(const zsg_wgrad_params p) {
   float acc = 0.f;
   for (int m = 0; m < p.m; ++m) {
     const zsg_row_t e = p.rows[m];
-    const int yy = e.y0 + tr, xx = e.x0 + ts;
+    const int yy = e.y0 + tr * p.dil, xx = e.x0 + ts * p.dil;
     if ((unsigned)yy >= (unsigned)e.hin || (unsigned)xx >= (unsigned)e.win) continue;
     float v = p.x[(int64_t)e.base + (int64_t)(yy * e.win + xx) * p.cin + c];
     if (p.in_scale) v = fmaf(v, p.in_scale[c], p.in_shift[c]);
@@ -1530,7 +1530,9 @@ extern "C" int zsg_debug_set_conv_trace(unsigned int* buf, int nblocks) {
 
 extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(pp, "zsg_conv_fwd: null params");
-  const zsg_conv_params& p = *pp;
+  zsg_conv_params p = *pp;
+  ZSG_REQUIRE(p.dil >= 0 && p.dil <= 64, "zsg_conv_fwd: dil=%d out of range", p.dil);
+  if (p.dil == 0) p.dil = 1;
   ZSG_REQUIRE(p.x && p.w && p.y && p.rows, "zsg_conv_fwd: null pointer");
   ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.r > 0 && p.s > 0, "zsg_conv_fwd: empty problem");
   ZSG_REQUIRE(p.cin > 0 && p.cin % 4 == 0, "zsg_conv_fwd: cin=%d must be a multiple of 4", p.cin);
@@ -1559,7 +1561,9 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
 
 extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(pp, "zsg_conv_wgrad: null params");
-  const zsg_wgrad_params& p = *pp;
+  zsg_wgrad_params p = *pp;
+  ZSG_REQUIRE(p.dil >= 0 && p.dil <= 64, "zsg_conv_wgrad: dil=%d out of range", p.dil);
+  if (p.dil == 0) p.dil = 1;
   ZSG_REQUIRE(p.x && p.dy && p.dw && p.rows, "zsg_conv_wgrad: null pointer");
   ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.cin > 0 && p.r > 0 && p.s > 0, "zsg_conv_wgrad: empty problem");
   ZSG_REQUIRE(p.impl == 1 || p.cin % 4 == 0, "zsg_conv_wgrad: cin=%d must be a multiple of 4", p.cin);

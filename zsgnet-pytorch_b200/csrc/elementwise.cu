@@ -333,6 +333,144 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restr
   }
 }
 
+// ----------------------------- SSD-VGG trunk glue (ssd_vgg.py) -------------------------------
+// Generic max-pool (k x k window, stride, symmetric padding, output size given by the caller so that floor and
+// ceil mode are the same kernel).  The code of the winning tap (first maximum in row-major scan order over the
+// taps inside the image, as ATen's max_pool2d) is recorded per element; the backward is a gather over the
+// windows that contain an input pixel, optionally masked by the ReLU that feeds the pool.
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       uint8_t* __restrict__ argmax, int B, int H, int W, int C, int K,
+                                                       int S, int P, int Ho, int Wo) {
+  const int c4 = C / 4;
+  const int64_t n = (int64_t)B * Ho * Wo * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    int64_t t = i / c4;
+    const int q = (int)(t % Wo); t /= Wo;
+    const int p = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    uchar4 code = make_uchar4(255, 255, 255, 255);
+    for (int dy = 0; dy < K; ++dy) {
+      const int yy = p * S - P + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < K; ++dx) {
+        const int xx = q * S - P + dx;
+        if (xx < 0 || xx >= W) continue;
+        const float4 v = ld4(x + (((size_t)b * H + yy) * W + xx) * C + c);
+        const unsigned char k = (unsigned char)(dy * K + dx);
+        if (v.x > m.x || code.x == 255) { m.x = v.x; code.x = k; }
+        if (v.y > m.y || code.y == 255) { m.y = v.y; code.y = k; }
+        if (v.z > m.z || code.z == 255) { m.z = v.z; code.z = k; }
+        if (v.w > m.w || code.w == 255) { m.w = v.w; code.w = k; }
+      }
+    }
+    st4(y + i * 4, m);
+    if (argmax) *reinterpret_cast<uchar4*>(argmax + i * 4) = code;
+  }
+}
+
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const uint8_t* __restrict__ argmax, const float* __restrict__ dy,
+                                                       const float* __restrict__ mask, float* __restrict__ dx, int B,
+                                                       int H, int W, int C, int K, int S, int P, int Ho, int Wo) {
+  const int c4 = C / 4;
+  const int64_t n = (int64_t)B * H * W * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    int64_t t = i / c4;
+    const int xx = (int)(t % W); t /= W;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // windows p with p*S - P <= yy <= p*S - P + K - 1
+    int p0 = yy + P - K + 1; p0 = p0 <= 0 ? 0 : (p0 + S - 1) / S;
+    int q0 = xx + P - K + 1; q0 = q0 <= 0 ? 0 : (q0 + S - 1) / S;
+    const int p1 = min((yy + P) / S, Ho - 1), q1 = min((xx + P) / S, Wo - 1);
+    for (int p = p0; p <= p1; ++p)
+      for (int q = q0; q <= q1; ++q) {
+        const unsigned char k = (unsigned char)((yy - (p * S - P)) * K + (xx - (q * S - P)));
+        const size_t o = (((size_t)b * Ho + p) * Wo + q) * C + c;
+        const uchar4 code = *reinterpret_cast<const uchar4*>(argmax + o);
+        const float4 g = ld4(dy + o);
+        if (code.x == k) acc.x += g.x;
+        if (code.y == k) acc.y += g.y;
+        if (code.z == k) acc.z += g.z;
+        if (code.w == k) acc.w += g.w;
+      }
+    if (mask) {
+      const float4 v = ld4(mask + i * 4);
+      if (!(v.x > 0.f)) acc.x = 0.f;
+      if (!(v.y > 0.f)) acc.y = 0.f;
+      if (!(v.z > 0.f)) acc.z = 0.f;
+      if (!(v.w > 0.f)) acc.w = 0.f;
+    }
+    st4(dx + i * 4, acc);
+  }
+}
+
+// s = x / ||x||_2 over channels (ssd_vgg.py:80): one warp per pixel row, the row stays in registers between the
+// reduction and the division (C <= 1024).  The norm is kept for the backward.
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                         float* __restrict__ norm, int64_t rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarp) {
+    float4 v[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      v[j] = c < C ? ld4(x + r * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
+    const float nrm = sqrtf(warp_sum(ss));
+    if (lane == 0) norm[r] = nrm;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) st4(y + r * C + c, make_float4(v[j].x / nrm, v[j].y / nrm, v[j].z / nrm, v[j].w / nrm));
+    }
+  }
+}
+
+// dx (+)= [x > 0] * (dy / n - x * sum_c(dy * x) / n^3): the autograd of x / x.norm(dim=1, keepdim=True), with the
+// ReLU that produced x (vgg[22]) folded in when mask_relu is set.
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ norm, float* __restrict__ dx,
+                                                         int64_t rows, int C, int accumulate, int mask_relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarp) {
+    float4 v[8], g[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      v[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) { v[j] = ld4(x + r * C + c); g[j] = ld4(dy + r * C + c); }
+      dot += v[j].x * g[j].x + v[j].y * g[j].y + v[j].z * g[j].z + v[j].w * g[j].w;
+    }
+    dot = warp_sum(dot);
+    const float n = norm[r];
+    const float k = dot / (n * n * n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c >= C) continue;
+      float4 o = make_float4(g[j].x / n - v[j].x * k, g[j].y / n - v[j].y * k, g[j].z / n - v[j].z * k,
+                             g[j].w / n - v[j].w * k);
+      if (mask_relu) {
+        if (!(v[j].x > 0.f)) o.x = 0.f;
+        if (!(v[j].y > 0.f)) o.y = 0.f;
+        if (!(v[j].z > 0.f)) o.z = 0.f;
+        if (!(v[j].w > 0.f)) o.w = 0.f;
+      }
+      if (accumulate) { const float4 a = ld4(dx + r * C + c); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+      st4(dx + r * C + c, o);
+    }
+  }
+}
+
 // --------------------------------- FPN nearest upsample + add --------------------------------
 __global__ void __launch_bounds__(256) upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                            const int32_t* __restrict__ iy, const int32_t* __restrict__ ix,
@@ -688,6 +826,38 @@ extern "C" int zsg_avgpool_bwd(const float* dy, float* dx, int b, int hw, int c,
   ZSG_REQUIRE(dy && dx, "zsg_avgpool_bwd: null pointer");
   avgpool_bwd_kernel<<<(b * hw * c + 255) / 256, 256, 0, as_stream(stream)>>>(dy, dx, b, hw, c);
   return check_launch("zsg_avgpool_bwd");
+}
+
+extern "C" int zsg_maxpool_fwd(const float* x, float* y, uint8_t* argmax, int b, int h, int w, int c, int k, int stride,
+                               int pad, int ho, int wo, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && y && c % 4 == 0 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "zsg_maxpool_fwd: bad arguments");
+  ZSG_REQUIRE(ho >= 1 && wo >= 1 && (ho - 1) * stride - pad < h && (wo - 1) * stride - pad < w,
+              "zsg_maxpool_fwd: a window starts outside the image");
+  pool_fwd_kernel<<<grid_for((int64_t)b * ho * wo * (c / 4), 256), 256, 0, as_stream(stream)>>>(x, y, argmax, b, h, w, c, k,
+                                                                                                 stride, pad, ho, wo);
+  return check_launch("zsg_maxpool_fwd");
+}
+
+extern "C" int zsg_maxpool_bwd(const uint8_t* argmax, const float* dy, const float* mask, float* dx, int b, int h, int w,
+                               int c, int k, int stride, int pad, int ho, int wo, zsg_stream_t stream) {
+  ZSG_REQUIRE(argmax && dy && dx && c % 4 == 0 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k,
+              "zsg_maxpool_bwd: bad arguments");
+  pool_bwd_kernel<<<grid_for((int64_t)b * h * w * (c / 4), 256, 16), 256, 0, as_stream(stream)>>>(argmax, dy, mask, dx, b, h,
+                                                                                                   w, c, k, stride, pad, ho, wo);
+  return check_launch("zsg_maxpool_bwd");
+}
+
+extern "C" int zsg_l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && y && norm && rows > 0 && c > 0 && c % 4 == 0 && c <= 1024, "zsg_l2norm_fwd: bad arguments (c <= 1024, c % 4 == 0)");
+  l2norm_fwd_kernel<<<grid_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(x, y, norm, rows, c);
+  return check_launch("zsg_l2norm_fwd");
+}
+
+extern "C" int zsg_l2norm_bwd(const float* dy, const float* x, const float* norm, float* dx, int64_t rows, int c,
+                              int accumulate, int mask_relu, zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && x && norm && dx && rows > 0 && c > 0 && c % 4 == 0 && c <= 1024, "zsg_l2norm_bwd: bad arguments");
+  l2norm_bwd_kernel<<<grid_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(dy, x, norm, dx, rows, c, accumulate, mask_relu);
+  return check_launch("zsg_l2norm_bwd");
 }
 
 extern "C" int zsg_relu_bwd(const float* dy, const float* x, float* dx, int64_t n, int accumulate,

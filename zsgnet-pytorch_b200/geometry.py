@@ -27,15 +27,16 @@ def conv_rows(B, hin, win, cin, hout, wout, cout, stride, pad, in_off=0, out_off
     return _pack(base, p * stride - pad, q * stride - pad, np.full(n, hin), np.full(n, win), out)
 
 
-def dgrad_rows(B, hin, win, cin, hout, wout, cout, R, stride, pad, dy_off=0, dx_off=0):
+def dgrad_rows(B, hin, win, cin, hout, wout, cout, R, stride, pad, dy_off=0, dx_off=0, dil=1):
     """Data gradient of the conv above: one row per INPUT pixel (b, y, x); the gathered tensor is dY
-    (plane hout x wout, cout channels).  Used with flipped-transposed weights, in_div = stride."""
+    (plane hout x wout, cout channels).  Used with flipped-transposed weights, in_div = stride, and the
+    forward conv's tap spacing `dil` (flipped tap r' reads dY at y + pad - (R-1)*dil + r'*dil)."""
     b, y, x = np.meshgrid(np.arange(B), np.arange(hin), np.arange(win), indexing="ij")
     b, y, x = b.ravel(), y.ravel(), x.ravel()
     base = dy_off + b * (hout * wout * cout)
     out = dx_off + ((b * hin + y) * win + x) * cin
     n = b.shape[0]
-    off = pad - (R - 1)
+    off = pad - (R - 1) * dil
     return _pack(base, y + off, x + off, np.full(n, hout), np.full(n, wout), out)
 
 

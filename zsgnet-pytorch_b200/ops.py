@@ -45,11 +45,11 @@ class ConvOp:
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
-                 x_lo=None):
+                 x_lo=None, dil=1):
         self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo)
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl, ptr(x_lo))
+                            impl, ptr(x_lo), dil)
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
         self.kernel = "conv_tc_async_kernel" if x_lo is not None else ("conv_tc_kernel" if w_lo is not None else "conv_tc_generic_kernel")
@@ -62,11 +62,11 @@ class ConvOp:
 
 class WgradOp:
     def __init__(self, x, dy, dw, rows, m, cin, cout, r, s, in_scale=None, in_shift=None, in_relu=False, split_k=0,
-                 impl=IMPL_TC, x_lo=None, dy_lo=None, dy_pitch=0):
+                 impl=IMPL_TC, x_lo=None, dy_lo=None, dy_pitch=0, dil=1):
         self.keep = (x, dy, dw, rows, in_scale, in_shift, x_lo, dy_lo)
         self.dw = dw
         self.p = WgradParams(ptr(x), ptr(dy), ptr(dw), ptr(rows), m, cin, cout, r, s, ptr(in_scale), ptr(in_shift),
-                             int(in_relu), split_k, impl, ptr(x_lo), ptr(dy_lo), dy_pitch)
+                             int(in_relu), split_k, impl, ptr(x_lo), ptr(dy_lo), dy_pitch, dil)
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin
         self.kernel = "wgrad_tc_async_kernel" if x_lo is not None else "wgrad_tc_kernel"
@@ -158,6 +158,22 @@ def avgpool_fwd(x, y, b, hw, c):
 
 def avgpool_bwd(dy, dx, b, hw, c):
     call("zsg_avgpool_bwd", ptr(dy), ptr(dx), b, hw, c, stream())
+
+
+def maxpool_fwd(x, y, argmax, b, h, w, c, k, stride, pad, ho, wo):
+    call("zsg_maxpool_fwd", ptr(x), ptr(y), ptr(argmax), b, h, w, c, k, stride, pad, ho, wo, stream())
+
+
+def maxpool_bwd(argmax, dy, dx, b, h, w, c, k, stride, pad, ho, wo, mask=None):
+    call("zsg_maxpool_bwd", ptr(argmax), ptr(dy), ptr(mask), ptr(dx), b, h, w, c, k, stride, pad, ho, wo, stream())
+
+
+def l2norm_fwd(x, y, norm, rows, c):
+    call("zsg_l2norm_fwd", ptr(x), ptr(y), ptr(norm), rows, c, stream())
+
+
+def l2norm_bwd(dy, x, norm, dx, rows, c, accumulate=False, mask_relu=False):
+    call("zsg_l2norm_bwd", ptr(dy), ptr(x), ptr(norm), ptr(dx), rows, c, int(accumulate), int(mask_relu), stream())
 
 
 def relu_bwd(dy, x, dx, n, accumulate=False):
