@@ -78,13 +78,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(bs, steps, warmup, seed=1234):
+def cpu_oracle_rate(bs, steps, warmup, seed=1234, model="retina"):
     """pairs/s of the oracle port (the reference's arithmetic, PyTorch CPU fp32/fp64) on all host threads."""
     import torch
     from oracle import synth, zsg_oracle as zo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = synth.make_state_dict(0)
+    sd = synth.make_state_dict(0, model)
     state = {}
     times = []
     for i in range(warmup + steps):
@@ -102,7 +102,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     sample_bs = 8
-    rate, cores, sec = cpu_oracle_rate(sample_bs, args.steps, args.warmup)
+    set_model(args.model)
+    rate, cores, sec = cpu_oracle_rate(sample_bs, args.steps, args.warmup, model=args.model)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -118,6 +119,15 @@ def run_reference(args, rank, world):
 WORKLOAD = "refclef config, bs=64 per GPU, ResNet-50+FPN, qlen=20, 300x300 synthetic images+queries, fp32 (BASELINE configs[1])"
 
 
+def set_model(model):
+    """--model ssd_vgg: the trunk of BASELINE configs[4] (SSD-VGG16) in fp32 on this arm's batch; not the headline."""
+    global WORKLOAD, FLOP_PER_PAIR_TRAIN
+    if model == "ssd_vgg":
+        WORKLOAD = ("vg_split config, SSD-VGG backbone (ssd_vgg.py), qlen=20, 300x300 synthetic images+queries, fp32 "
+                    "(trunk of BASELINE configs[4]; per-GPU batch as given)")
+        FLOP_PER_PAIR_TRAIN = 225.0e9   # SURVEY.md 8(d): SSD-VGG model 75.0 GFLOP forward, x3 for training
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -125,6 +135,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="zsg", choices=["zsg", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--model", default="retina", choices=["retina", "ssd_vgg"],
+                    help="image trunk (cfg mdl_to_use); the headline workload is retina")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -146,7 +158,8 @@ def main():
     import numpy as np
 
     B = args.batch
-    cfg = {"do_norm": False, "use_same_atb": True, "mdl_to_use": "retina", "resize_img": [300, 300], "use_multi": True,
+    set_model(args.model)
+    cfg = {"do_norm": False, "use_same_atb": True, "mdl_to_use": args.model, "resize_img": [300, 300], "use_multi": True,
            "use_focal": True, "use_softmax": False, "alpha": 0.25, "gamma": 2, "emb_dim": 300,
            "matching_threshold": 0.6, "use_bidirectional": True, "lstm_dim": 128, "lamb_reg": 1,
            "acc_iou_threshold": 0.5, "use_lang": True, "use_img": True, "device": f"cuda:{local_rank}"}
@@ -303,7 +316,7 @@ def main():
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, sec = cpu_oracle_rate(16, 2, 1)
+        rate, cores, sec = cpu_oracle_rate(16, 2, 1, model=args.model)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"2 timed steps (+1 warm-up) of bs=16 from the same synthetic distribution, {sec:.1f} s/step: forward, "
                          "loss, backward, Adam, metric in PyTorch CPU (the reference's arithmetic) on all host threads"}

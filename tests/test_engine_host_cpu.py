@@ -67,6 +67,37 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     assert len(seen) == 16 + 4
 
 
+def test_ssd_vgg_program_builds_and_runs_on_host(recorded):
+    """a-8 (config 5): launch program of the SSD-VGG trunk (ssd_vgg.py:54-102) + shared head."""
+    calls, engine, spec, ops = recorded
+    B, T = 1, 4
+    store = engine.ParamStore(torch.device("cpu"), "ssd_vgg")
+    assert store.offsets["backbone.encoder.loc.0.weight"] >= store.used          # unused multibox heads: no all-reduce / Adam
+    eng = engine.Engine(store, {}, B, T, torch.device("cpu"))
+    assert len(eng.bns) == 0
+    eng.set_inputs(torch.rand(B, 3, 300, 300), torch.randn(B, 4, 300), torch.tensor([4.0]), torch.tensor([0]),
+                   torch.randn(2, B, 128), torch.randn(2, B, 128))
+    del calls[:]
+    out = eng.forward(training=True)
+    assert out.shape == (B, spec.NUM_ANCHORS, 5)
+    fwd = collections.Counter(calls)
+    # 15 VGG convs + 8 extras + 3 fproj + 6 head + 1 LSTM projection
+    assert fwd["zsg_conv_fwd"] == 15 + 8 + 3 + 6 + 1
+    assert fwd["zsg_maxpool_fwd"] == 5 and fwd["zsg_l2norm_fwd"] == 1 and fwd["zsg_bn_stats"] == 0
+    del calls[:]
+    seen = []
+    eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5), on_bucket=lambda lo, hi: seen.append((lo, hi)))
+    bwd = collections.Counter(calls)
+    assert bwd["zsg_conv_wgrad"] == 15 + 8 + 3 + 6 + 4
+    # every conv but vgg.0 has a data gradient; extras.1 / extras.3 (3x3, stride 2) take 4 parity-class launches each
+    assert bwd["zsg_conv_fwd"] == 14 + 8 + 3 + 6 + 2 * 3
+    assert bwd["zsg_maxpool_bwd"] == 5 and bwd["zsg_l2norm_bwd"] == 1 and bwd["zsg_relu_bwd"] == 3
+    assert seen[0][0] == 0 and seen[-1][1] == store.used
+    for (a, b), (c, d) in zip(seen, seen[1:]):
+        assert b == c and a < b
+    assert len(seen) == 6 + 2 + 2                                              # VGG segments, extras, fproj, lstm, head
+
+
 def test_param_store_views_follow_reference_shapes(recorded):
     _, engine, spec, _ = recorded
     store = engine.ParamStore(torch.device("cpu"))

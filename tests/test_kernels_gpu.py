@@ -649,7 +649,8 @@ def test_conv_dgrad_async_vs_torch(zsg, case):
     assert rel_err(dx, want) < 2e-5
 
 
-@pytest.mark.parametrize("case", WGRAD_CASES + [(2, 520, 10, 10, 256, 3, 1, 1), (2, 264, 7, 9, 128, 1, 1, 0)])
+@pytest.mark.parametrize("case", WGRAD_CASES + [(2, 520, 10, 10, 256, 3, 1, 1), (2, 264, 7, 9, 128, 1, 1, 0),
+                                               (2, 512, 19, 19, 512, 3, 1, 1), (2, 1024, 19, 19, 256, 1, 1, 0)])
 @pytest.mark.parametrize("tma_dy", [False, True])
 def test_conv_wgrad_async_vs_torch(zsg, case, tma_dy):
     """cp.async weight-gradient kernel (x, dy with remainder images; dy optionally by TMA) against torch, including

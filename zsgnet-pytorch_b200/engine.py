@@ -27,18 +27,21 @@ class ParamStore:
     exposed to PyTorch as OIHW tensors with channels_last strides, so state_dict keys and shapes
     match the reference while no repacking is needed at run time."""
 
-    def __init__(self, device):
-        fwd = spec.trainable_specs()
+    def __init__(self, device, model="retina"):
+        assert model in spec.MODELS, model
+        self.model = model
+        fwd = spec.trainable_specs(model)
+        unused = spec.unused_specs(model)
         order = list(reversed(fwd))                      # backward completes gradients in this order
         self.names = [n for n, _, _ in order]
-        self.kinds = {n: k for n, _, k in fwd + spec.UNUSED_SPECS}
-        self.shapes = {n: s for n, s, _ in fwd + spec.UNUSED_SPECS}
+        self.kinds = {n: k for n, _, k in fwd + unused}
+        self.shapes = {n: s for n, s, _ in fwd + unused}
         self.offsets, off = {}, 0
         for n, s, _ in order:
             self.offsets[n] = off
             off += _align(int(np.prod(s)))
         self.used = off                                  # [0, used) takes part in all-reduce and Adam
-        for n, s, _ in spec.UNUSED_SPECS:
+        for n, s, _ in unused:
             self.offsets[n] = off
             off += _align(int(np.prod(s)))
         self.total = off
@@ -84,6 +87,7 @@ class _BN:
 class Engine:
     def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC):
         self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
+        self.model = store.model
         self._rows_cache = {}
         self._operand_cache, self._bwd_lo = {}, {}
         self._side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
@@ -165,8 +169,10 @@ class Engine:
     def rows(self, kind, *key):
         k = (kind,) + key
         if k not in self._rows_cache:
-            fn = geometry.conv_rows if kind == "fwd" else geometry.dgrad_rows
-            self._rows_cache[k] = fn(self.B, *key).to(self.device)
+            if kind == "fwd":
+                self._rows_cache[k] = geometry.conv_rows(self.B, *key).to(self.device)
+            else:                                            # key = (..., k, stride, pad, dil)
+                self._rows_cache[k] = geometry.dgrad_rows(self.B, *key[:-1], dil=key[-1]).to(self.device)
         return self._rows_cache[k]
 
     # ------------------------------------------------------------------ layer builders
@@ -187,8 +193,9 @@ class Engine:
         self.fwd.append(("bn", train, evalm))
 
     def conv(self, wname, x, hin, win, cin, cout, k, stride, pad, y, pro=None, in_relu=False, bias=None,
-             out_relu=False, w=None):
-        hout, wout = (hin + 2 * pad - k) // stride + 1, (win + 2 * pad - k) // stride + 1
+             out_relu=False, w=None, dil=1):
+        span = dil * (k - 1) + 1
+        hout, wout = (hin + 2 * pad - span) // stride + 1, (win + 2 * pad - span) // stride + 1
         rows = self.rows("fwd", hin, win, cin, hout, wout, cout, stride, pad)
         if w is None:
             w = self.store.flat(wname)
@@ -197,15 +204,15 @@ class Engine:
             w, w_hi, w_lo = w                                # a (w, hi, lo) triple from the pool
         xz, x_lo = self.fwd_operand(x, self.B * hin * win, cin, pro=pro, relu=in_relu)
         op = ConvOp(xz, w_hi, y, rows, self.B * hout * wout, cin, cout, k, k, bias=bias, out_relu=out_relu, impl=self.impl,
-                    w_lo=w_lo, x_lo=x_lo)
+                    w_lo=w_lo, x_lo=x_lo, dil=dil)
         self.fwd.append(("op", op))
         return dict(wname=wname, x=x, xz=xz, x_lo=x_lo, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
-                    hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w)   # w: fp32 weights (for dgrad prep)
+                    hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w, dil=dil)   # w: fp32 weights (dgrad prep)
 
     def conv_wgrad(self, L, dy, dy_lo, dw=None):
         dw = self.store.grad_flat(L["wname"]) if dw is None else dw
         self.bwd.append(WgradOp(L["xz"], dy, dw, L["rows"], self.B * L["hout"] * L["wout"], L["cin"], L["cout"], L["k"],
-                                L["k"], impl=self.impl, x_lo=L["x_lo"], dy_lo=dy_lo, dy_pitch=L["cout"]))
+                                L["k"], impl=self.impl, x_lo=L["x_lo"], dy_lo=dy_lo, dy_pitch=L["cout"], dil=L["dil"]))
 
     def grad_operand(self, L, dy):
         """lo image of the output gradient of conv L (shared by its wgrad and dgrad)."""
@@ -244,9 +251,9 @@ class Engine:
             rows = self._rows_cache[key]
             self.bwd.append(ConvOp(dy, wt_hi, dx, rows, rows.shape[0], cout, cin, 1, 1, w_lo=wt_lo, x_lo=dy_lo, **epi))
             return
-        rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, stride, L["pad"])
+        rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, stride, L["pad"], L["dil"])
         self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=stride,
-                               w_lo=wt_lo, x_lo=dy_lo, **epi))
+                               w_lo=wt_lo, x_lo=dy_lo, dil=L["dil"], **epi))
 
     def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True):
         """BatchNorm backward; returns the lo image of dx (written by the same kernel) for the GEMMs that follow."""
@@ -265,8 +272,41 @@ class Engine:
     # ------------------------------------------------------------------ the network
     def _build(self):
         B, T, st, dev = self.B, self.T, self.store, self.device
+        bwd_stages, stage_names = [], []                  # filled in forward order, replayed reversed
+        # the six feature levels (38, 19, 10, 5, 3, 1 cells a side) live level-major in one [M, 256] matrix, so that
+        # the shared head runs over all of them in one launch per layer
+        lvl_rows = [B * c for c in spec.CELLS]
+        lvl_off = np.concatenate([[0], np.cumsum(lvl_rows)]).tolist()
+        M = B * spec.TOTAL_CELLS
+        feat, dfeat = self.buf(M, 256), self.buf(M, 256)
+        fl = [feat[lvl_off[i]:lvl_off[i + 1]] for i in range(6)]
+        dfl = [dfeat[lvl_off[i]:lvl_off[i + 1]] for i in range(6)]
+        trunk = self._build_resnet_fpn if self.model == "retina" else self._build_ssd_vgg
+        dbg = trunk(bwd_stages, stage_names, fl, dfl)
+        w0p_t = self._w0p_t
+        specs = spec.trainable_specs(self.model)
+        stage_names.append([n for n, _, _ in specs if n.startswith("lstm.")])
+        stage_names.append([n for n, _, _ in specs if n.startswith("att_reg_box.")])
+        self._build_lstm_head(bwd_stages, feat, dfeat, lvl_off, M, w0p_t, dbg)
+
+        # backward = stages in reverse forward order; gradient-ready marks for the bucketed all-reduce
+        self.bucket_marks = []                            # (index into self.bwd after which arena[lo:hi] is final)
+        assert len(stage_names) == len(bwd_stages)
+        for stage, names in zip(reversed(bwd_stages), reversed(stage_names)):
+            stage()
+            lo = min(st.offsets[n] for n in names)
+            hi = max(st.offsets[n] + _align(st.numel(n)) for n in names)
+            self.bucket_marks.append((len(self.bwd), lo, hi))
+
+    def _alloc_head_w0p(self):
+        """Padded first head weight: the last forward-time entry of the transformed-weight pool (region F)."""
+        self._w0p_t = self.pool_alloc(256 * 9 * spec.FUSED_CP)
+        self._pool_f_end = self._pool_used
+
+    def _build_resnet_fpn(self, bwd_stages, stage_names, fl, dfl):
+        """mdl_to_use='retina': torchvision resnet50 trunk (mdl.py:148-156) + FPN (fpn_resnet.py:154-178)."""
+        B, T, st, dev = self.B, self.T, self.store, self.device
         e = "backbone.encoder."
-        bwd_stages = []                                   # filled in forward order, replayed reversed
 
         # ---------------- stem: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2 (mdl.py:149-152)
         img4 = self.buf(B, 300, 300, 4)
@@ -277,8 +317,7 @@ class Engine:
         w1 = st.flat(e + "conv1.weight")
         self.fwd.append(("fn", lambda: ops.nchw_to_nhwc4(self.inp["img"], img4)))
         self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, 4))
-        w0p_t = self.pool_alloc(256 * 9 * spec.FUSED_CP)
-        self._pool_f_end = self._pool_used                    # region F (forward-time transformed weights) ends here
+        self._alloc_head_w0p()                                # region F (forward-time transformed weights) ends here
         Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p_t)
         bn1 = self.add_bn(e + "bn1", 64, B * 150 * 150)
         self.bn_forward(bn1, c1)
@@ -372,12 +411,6 @@ class Engine:
         c3, g_c3, _, _ = stage_out[2]
         c4, g_c4, _, _ = stage_out[3]
         c5, g_c5, _, _ = stage_out[4]
-        lvl_rows = [B * c for c in spec.CELLS]
-        lvl_off = np.concatenate([[0], np.cumsum(lvl_rows)]).tolist()
-        M = B * spec.TOTAL_CELLS
-        feat, dfeat = self.buf(M, 256), self.buf(M, 256)
-        fl = [feat[lvl_off[i]:lvl_off[i + 1]] for i in range(6)]
-        dfl = [dfeat[lvl_off[i]:lvl_off[i + 1]] for i in range(6)]
         p51, p41, p31 = self.buf(B * 100, 256), self.buf(B * 361, 256), self.buf(B * 1444, 256)
         dp51, dp41, dp31 = self.buf(B * 100, 256), self.buf(B * 361, 256), self.buf(B * 1444, 256)
         f = "backbone.fpn."
@@ -420,6 +453,141 @@ class Engine:
             self.bwd.append(lambda: ops.upsample_add_bwd(dp41, dp51, up[(10, 19)], up[(10, 19)], B, 19, 19, 10, 10, 256))
             layer("P5_1", L51, dp51, B * 100, g_c5, accumulate=True)
         bwd_stages.append(fpn_bwd)
+        stage_names += self._stage_param_names(len(blocks))
+        return dict(x0=x0, c1=c1, c3=c3, c4=c4, c5=c5, blocks=blocks)
+
+    def _build_ssd_vgg(self, bwd_stages, stage_names, fl, dfl):
+        """mdl_to_use='ssd_vgg' (config 5): SSDBackBone.encode_feats (mdl.py:162-168) = SSD.forward (ssd_vgg.py:54-102).
+        Every conv is conv + bias + ReLU in one launch (no BatchNorm); the gradient buffer `g` of a conv holds the
+        gradient w.r.t. its PRE-ReLU output: the data gradient of the next conv is masked by this conv's activation in
+        its epilogue (out_mask), the max-pool backward masks by its input.  Where an activation has two consumers
+        (conv4_3, conv7, extras.1/3/5) the second data gradient accumulates onto the first."""
+        B, st, dev = self.B, self.store, self.device
+        e = "backbone.encoder."
+        bias = lambda n: st.flat(n + ".bias")
+
+        def conv_bwd(rec):
+            """bias / weight / data gradient of one conv whose `g` is final."""
+            L, g = rec["L"], rec["g"]
+            gb = st.grad_flat(rec["name"] + ".bias")
+            self.bwd.append(lambda: ops.colsum(g, gb, rec["rows"], L["cout"]))
+            lo = self.grad_operand(L, g)
+            if rec.get("dw") is not None:                     # first conv: padded input channels
+                dwp, gw = rec["dw"], st.grad_flat(rec["name"] + ".weight")
+                self.bwd.append(lambda: dwp.zero_())
+                self.conv_wgrad(L, g, lo, dw=dwp)
+                self.bwd.append(lambda: ops.pad_channels(dwp, gw, L["cout"] * L["k"] * L["k"], 4, 3))
+            else:
+                self.conv_wgrad(L, g, lo)
+            if rec["dx"] is not None:
+                self.conv_dgrad(L, g, lo, rec["dx"], out_mask=rec["dx_mask"], accumulate=rec.get("dx_acc", False))
+
+        # ---------------- VGG-16 with pool5 / dilated conv6 / conv7 (ssd_vgg.py:76-85, 111-133)
+        img4 = self.buf(B, 300, 300, 4)
+        w1 = st.flat(e + "vgg.0.weight")
+        w1p_t = self.pool_alloc(64 * 9 * 4)
+        self.fwd.append(("fn", lambda: ops.nchw_to_nhwc4(self.inp["img"], img4)))
+        self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p_t[0], 64 * 9, 3, 4))
+        self._alloc_head_w0p()
+        x, gx, h, cin, x_is_relu = img4, None, 300, 4, False
+        segments, seg = [], []
+        src = {}
+        for i, Lr in enumerate(spec.vgg_layers()):
+            if Lr[0] == "conv":
+                _, _, co, k, pad, dil = Lr
+                name = f"{e}vgg.{i}"
+                y, gy = self.buf(B * h * h, co), self.buf(B * h * h, co)
+                L = self.conv(name + ".weight", x, h, h, cin, co, k, 1, pad, y, bias=bias(name), out_relu=True, dil=dil,
+                              w=w1p_t if i == 0 else None)
+                assert L["hout"] == h
+                seg.append(("conv", dict(L=L, name=name, g=gy, rows=B * h * h, dx=gx, dx_mask=x if x_is_relu else None,
+                                         dw=self.buf(64 * 9 * 4) if i == 0 else None)))
+                x, gx, cin, x_is_relu = y, gy, co, True
+                if i == 21:                                   # relu(conv4_3): source 0 = x / ||x||_2 -> fproj1 (ssd_vgg.py:80, 97)
+                    n38 = B * h * h
+                    x38, s38, nrm38, ds38 = y, self.buf(n38, co), self.buf(n38), self.buf(n38, co)
+                    self.fwd.append(("fn", lambda: ops.l2norm_fwd(x38, s38, nrm38, n38, 512)))
+                    Lf1 = self.conv(e + "fproj1.weight", s38, h, h, co, 256, 1, 1, 0, fl[0], bias=bias(e + "fproj1"))
+                    seg.append(("l2norm", dict(dy=ds38, x=x38, norm=nrm38, dx=gy, rows=n38, c=co)))
+                    src[1] = dict(L=Lf1, name=e + "fproj1", g=dfl[0], rows=n38, dx=ds38, dx_mask=None)
+            elif Lr[0] == "pool":
+                _, k, s_, pad, ceil = Lr
+                span = h + 2 * pad - k
+                ho = (-(-span // s_) if ceil else span // s_) + 1
+                if ceil and (ho - 1) * s_ >= h + pad:
+                    ho -= 1
+                y, gy = self.buf(B * ho * ho, cin), self.buf(B * ho * ho, cin)
+                arg = torch.empty(B * ho * ho * cin, dtype=torch.uint8, device=dev)
+                geom = (B, h, h, cin, k, s_, pad, ho, ho)
+                self.fwd.append(("fn", lambda x=x, y=y, arg=arg, geom=geom: ops.maxpool_fwd(x, y, arg, *geom)))
+                seg.append(("pool", dict(arg=arg, dy=gy, dx=gx, mask=x, geom=geom)))
+                segments.append(seg)
+                seg = []
+                x, gx, h, x_is_relu = y, gy, ho, False
+        segments.append(seg)
+        assert h == 19 and cin == 1024
+        x19, g19 = x, gx
+        Lf2 = self.conv(e + "fproj2.weight", x19, 19, 19, 1024, 256, 1, 1, 0, fl[1], bias=bias(e + "fproj2"))
+        src[2] = dict(L=Lf2, name=e + "fproj2", g=dfl[1], rows=B * 361, dx=g19, dx_mask=x19)
+
+        # ---------------- extras: ReLU after each, every second one is a source (ssd_vgg.py:92-95)
+        level_of = {3: 3, 5: 4, 7: 5}                         # extras.3/5/7 ARE the features of levels 3..5 (ssd_vgg.py:97-98)
+        xe, ge, he = x19, g19, 19
+        ext = []
+        for i, (ci, co, k, s_, pad) in enumerate(spec.VGG_EXTRAS):
+            ho = (he + 2 * pad - k) // s_ + 1
+            if i in level_of:
+                y, gy = fl[level_of[i]], dfl[level_of[i]]
+                assert ho == spec.LEVEL_SIZES[level_of[i]] and co == 256
+            else:
+                y, gy = self.buf(B * ho * ho, co), self.buf(B * ho * ho, co)
+            name = f"{e}extras.{i}"
+            L = self.conv(name + ".weight", xe, he, he, ci, co, k, s_, pad, y, bias=bias(name), out_relu=True)
+            # even extras read an activation that has a second consumer (conv7 -> fproj2, extras.1 -> fproj3, a level
+            # -> the head) whose gradient is already in the buffer
+            ext.append(dict(L=L, name=name, g=gy, rows=B * ho * ho, dx=ge, dx_mask=xe, dx_acc=(i % 2 == 0), y=y))
+            if i == 1:
+                Lf3 = self.conv(e + "fproj3.weight", y, ho, ho, co, 256, 1, 1, 0, fl[2], bias=bias(e + "fproj3"))
+                src[3] = dict(L=Lf3, name=e + "fproj3", g=dfl[2], rows=B * ho * ho, dx=gy, dx_mask=y)
+            xe, ge, he = y, gy, ho
+        assert he == 1
+
+        # ---------------- backward stages, forward order: VGG segments, extras, fproj
+        def seg_bwd(seg):
+            def emit():
+                for kind, r in reversed(seg):
+                    if kind == "conv":
+                        conv_bwd(r)
+                    elif kind == "pool":
+                        self.bwd.append(lambda r=r: ops.maxpool_bwd(r["arg"], r["dy"], r["dx"], *r["geom"], mask=r["mask"]))
+                    else:                                     # second consumer of relu(conv4_3): accumulates onto the pool's
+                        self.bwd.append(lambda r=r: ops.l2norm_bwd(r["dy"], r["x"], r["norm"], r["dx"], r["rows"], r["c"],
+                                                                   accumulate=True, mask_relu=True))
+            return emit
+        specs = spec.trainable_specs("ssd_vgg")
+        for seg in segments:
+            bwd_stages.append(seg_bwd(seg))
+            convs = tuple(r["name"] + "." for kind, r in seg if kind == "conv")
+            stage_names.append([n for n, _, _ in specs if n.startswith(convs)])
+
+        def extras_bwd():
+            for lvl in (3, 4, 5):                             # gradient w.r.t. the level (from the head) -> pre-ReLU
+                n = dfl[lvl].numel()
+                self.bwd.append(lambda lvl=lvl, n=n: ops.relu_bwd(dfl[lvl], fl[lvl], dfl[lvl], n))
+            for r in reversed(ext):
+                conv_bwd(r)
+        bwd_stages.append(extras_bwd)
+        stage_names.append([n for n, _, _ in specs if n.startswith(e + "extras.")])
+
+        def fproj_bwd():
+            for j in (3, 2, 1):
+                conv_bwd(src[j])
+        bwd_stages.append(fproj_bwd)
+        stage_names.append([n for n, _, _ in specs if n.startswith(e + "fproj")])
+        return dict(x38=x38, s38=s38, x19=x19, ext=ext, segments=segments)
+
+    def _build_lstm_head(self, bwd_stages, feat, dfeat, lvl_off, M, w0p_t, dbg):
+        B, T, st, dev = self.B, self.T, self.store, self.device
 
         # ---------------- bi-LSTM query encoder (mdl.py:296-336)
         E, Hh, G = 300, 128, 512
@@ -514,8 +682,7 @@ class Engine:
         self.fwd.append(("op", ConvOp(hs[4], w5h, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
                                       impl=self.impl, w_lo=w5l, x_lo=hs_lo[4])))
         self.d_out = self.buf(B, A, 5)
-        self.dbg = dict(x0=x0, c1=c1, c3=c3, c4=c4, c5=c5, feat=feat, lang=lang, hs=hs, fused=fused, lvl_off=lvl_off,
-                        blocks=blocks)
+        self.dbg = dict(feat=feat, lang=lang, hs=hs, fused=fused, lvl_off=lvl_off, **dbg)
         wt5 = self.buf(256 * 9 * 45)
         wt5p_t = self.pool_alloc(256 * 9 * 48)
         wt5p = wt5p_t[0]
@@ -560,17 +727,8 @@ class Engine:
             self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
         bwd_stages.append(head_bwd)
 
-        # backward = stages in reverse forward order; gradient-ready marks for the bucketed all-reduce
-        self.bucket_marks = []                            # (index into self.bwd after which arena[lo:hi] is final)
-        names_by_stage = self._stage_param_names(len(blocks))
-        for stage, names in zip(reversed(bwd_stages), reversed(names_by_stage)):
-            stage()
-            lo = min(st.offsets[n] for n in names)
-            hi = max(st.offsets[n] + _align(st.numel(n)) for n in names)
-            self.bucket_marks.append((len(self.bwd), lo, hi))
-
     def _stage_param_names(self, nblocks):
-        """Parameter names per backward stage, in forward order (stem, blocks..., fpn, lstm, head)."""
+        """Parameter names per backward stage of the ResNet-50 + FPN trunk, in forward order (stem, blocks..., fpn)."""
         e = "backbone.encoder."
         names = [[e + "conv1.weight", e + "bn1.weight", e + "bn1.bias"]]
         for li, (nblk, _, _) in enumerate(spec.RESNET_LAYERS, start=1):
@@ -578,9 +736,7 @@ class Engine:
                 p = f"{e}layer{li}.{b}."
                 names.append([n for n, _, _ in spec.trainable_specs() if n.startswith(p)])
         names.append([n for n, _, _ in spec.trainable_specs() if n.startswith("backbone.fpn.")])
-        names.append([n for n, _, _ in spec.trainable_specs() if n.startswith("lstm.")])
-        names.append([n for n, _, _ in spec.trainable_specs() if n.startswith("att_reg_box.")])
-        assert len(names) == nblocks + 4
+        assert len(names) == nblocks + 2
         return names
 
     # ------------------------------------------------------------------ execution

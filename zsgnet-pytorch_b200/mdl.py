@@ -59,8 +59,9 @@ class _ZSGNetFn(torch.autograd.Function):
 
 
 class ZSGNet(nn.Module):
-    """ResNet-50 + FPN image encoder, bi-LSTM query encoder, language/grid tiling fusion and the
-    shared six-level convolutional head of ZSGNet (mdl.py:171-403), on B200."""
+    """Image encoder (cfg['mdl_to_use']: 'retina' = ResNet-50 + FPN, mdl.py:138-159; 'ssd_vgg' = SSD-VGG16,
+    mdl.py:162-168 + ssd_vgg.py), bi-LSTM query encoder, language/grid tiling fusion and the shared six-level
+    convolutional head of ZSGNet (mdl.py:171-403), on B200."""
 
     def __init__(self, backbone=None, n_anchors=9, final_bias=0.0, cfg=None, device=None):
         super().__init__()
@@ -72,8 +73,9 @@ class ZSGNet(nn.Module):
         cfg = cfg if cfg is not None else {}
         get = lambda k, d: (cfg[k] if k in cfg else d)
         unsupported = []
-        if get("mdl_to_use", "retina") != "retina":
-            unsupported.append("mdl_to_use=%r (only 'retina' = ResNet-50+FPN is built)" % get("mdl_to_use", None))
+        self.model = get("mdl_to_use", "retina")
+        if self.model not in spec.MODELS:
+            unsupported.append("mdl_to_use=%r (built: 'retina' = ResNet-50+FPN, 'ssd_vgg' = SSD-VGG16)" % self.model)
         if list(get("resize_img", [300, 300])) != [300, 300]:
             unsupported.append("resize_img != [300, 300]")
         if get("do_norm", False):
@@ -93,12 +95,12 @@ class ZSGNet(nn.Module):
         dev = torch.device(device if device is not None else "cuda")
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-        self.store = ParamStore(dev)
-        self.param_names = [n for n, _, _ in spec.trainable_specs()]
-        for n in self.param_names + [u[0] for u in spec.UNUSED_SPECS]:
+        self.store = ParamStore(dev, self.model)
+        self.param_names = [n for n, _, _ in spec.trainable_specs(self.model)]
+        for n in self.param_names + [u[0] for u in spec.unused_specs(self.model)]:
             _attach(self, n, nn.Parameter(self.store.view(n)), True)
         # BatchNorm buffers: float stats in one tensor, counters in another (views keep the reference names)
-        bspecs = spec.buffer_specs()
+        bspecs = spec.buffer_specs(self.model)
         nf = sum(s[0] for _, s in bspecs if len(s))
         self._bn_f = torch.zeros(nf, device=dev)
         self._bn_n = torch.zeros(sum(1 for _, s in bspecs if not len(s)), dtype=torch.long, device=dev)
@@ -122,13 +124,14 @@ class ZSGNet(nn.Module):
     @torch.no_grad()
     def reset_parameters(self):
         """PyTorch-default initialisers (the reference applies none of its own, mdl.py:20-41,227-228;
-        torchvision's resnet50 uses kaiming_normal(fan_out) for convs).  The ImageNet weights the
-        reference downloads (mdl.py:411) are loaded with load_state_dict when available."""
+        torchvision's resnet50 uses kaiming_normal(fan_out) for convs; ssd_vgg.py's convs keep nn.Conv2d's default).
+        The ImageNet weights the reference downloads (mdl.py:411) or reads from ./weights/vgg16_reducedfc.pth
+        (mdl.py:415-416) are loaded with load_state_dict when available."""
         st = self.store
-        for name, shape, kind in spec.trainable_specs() + spec.UNUSED_SPECS:
+        for name, shape, kind in spec.trainable_specs(self.model) + spec.unused_specs(self.model):
             v = st.view(name)
             if kind == "conv":
-                if name.startswith("backbone.encoder."):
+                if name.startswith("backbone.encoder.") and self.model == "retina":
                     nn.init.kaiming_normal_(v, mode="fan_out", nonlinearity="relu")
                 else:
                     nn.init.kaiming_uniform_(v, a=math.sqrt(5))

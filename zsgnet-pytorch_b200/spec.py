@@ -1,6 +1,6 @@
-"""Static description of the ZSGNet (ResNet-50 + FPN) parameter set: names and shapes are the
-reference's state_dict contract (mdl.py:171-229, fpn_resnet.py:108-152,
-torchvision resnet50), listed in FORWARD execution order."""
+"""Static description of the ZSGNet parameter sets: names and shapes are the reference's state_dict
+contract (mdl.py:171-229, fpn_resnet.py:108-152, torchvision resnet50 for
+mdl_to_use='retina'; ssd_vgg.py:31-52,111-171 for 'ssd_vgg'), listed in FORWARD execution order."""
 
 RESNET_LAYERS = ((3, 64, 1), (4, 128, 2), (6, 256, 2), (3, 512, 2))     # blocks, width, stride
 LEVEL_SIZES = (38, 19, 10, 5, 3, 1)                                     # P3..P8 at 300x300
@@ -20,8 +20,79 @@ def bn_buffers(prefix, c):
     return [(prefix + ".running_mean", (c,)), (prefix + ".running_var", (c,)), (prefix + ".num_batches_tracked", ())]
 
 
-def trainable_specs():
+MODELS = ("retina", "ssd_vgg")
+
+# ssd_vgg.py:174-177 (base['300']), 179-182 (extras['300']), 183-186 (mbox['300'])
+VGG_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, "C", 512, 512, 512, "M", 512, 512, 512)
+VGG_EXTRAS = ((1024, 256, 1, 1, 0), (256, 512, 3, 2, 1), (512, 128, 1, 1, 0), (128, 256, 3, 2, 1),     # cin, cout, k, stride, pad
+              (256, 128, 1, 1, 0), (128, 256, 3, 1, 0), (256, 128, 1, 1, 0), (128, 256, 3, 1, 0))
+VGG_MBOX = (4, 6, 6, 6, 4, 4)
+
+
+def vgg_layers():
+    """The `vgg` ModuleList (ssd_vgg.py:111-133), index-aligned: ("conv", cin, cout, k, pad, dil) | ("relu",) |
+    ("pool", k, stride, pad, ceil_mode)."""
+    out, cin = [], 3
+    for v in VGG_CFG:
+        if v in ("M", "C"):
+            out.append(("pool", 2, 2, 0, v == "C"))
+        else:
+            out += [("conv", cin, v, 3, 1, 1), ("relu",)]
+            cin = v
+    out += [("pool", 3, 1, 1, False), ("conv", 512, 1024, 3, 6, 6), ("relu",), ("conv", 1024, 1024, 1, 0, 1), ("relu",)]
+    return out
+
+
+def _head_lstm_specs():
+    out = []
+    for sfx in ("", "_reverse"):
+        out.append((f"lstm.weight_ih_l0{sfx}", (512, 300), "lstm"))
+        out.append((f"lstm.weight_hh_l0{sfx}", (512, 128), "lstm"))
+        out.append((f"lstm.bias_ih_l0{sfx}", (512,), "lstm"))
+        out.append((f"lstm.bias_hh_l0{sfx}", (512,), "lstm"))
+    out.append(("att_reg_box.0.0.weight", (256, FUSED_C, 3, 3), "conv"))
+    out.append(("att_reg_box.0.0.bias", (256,), "bias"))
+    for i in range(1, 5):
+        out.append((f"att_reg_box.{i}.0.weight", (256, 256, 3, 3), "conv"))
+        out.append((f"att_reg_box.{i}.0.bias", (256,), "bias"))
+    out.append(("att_reg_box.5.weight", (45, 256, 3, 3), "conv"))
+    out.append(("att_reg_box.5.bias", (45,), "final_bias"))
+    return out
+
+
+def _conv_bias(name, cin, cout, k):
+    return [(name + ".weight", (cout, cin, k, k), "conv"), (name + ".bias", (cout,), "bias")]
+
+
+def vgg_trainable_specs():
+    """SSD-VGG model in forward order: vgg.*, extras.*, fproj1..3 (their gradients are the first of the trunk to
+    complete in the backward), LSTM, head."""
+    e = "backbone.encoder."
+    out = []
+    for i, L in enumerate(vgg_layers()):
+        if L[0] == "conv":
+            out += _conv_bias(f"{e}vgg.{i}", L[1], L[2], L[3])
+    for i, (cin, cout, k, _, _) in enumerate(VGG_EXTRAS):
+        out += _conv_bias(f"{e}extras.{i}", cin, cout, k)
+    for j, cin in enumerate((512, 1024, 512), start=1):
+        out += _conv_bias(f"{e}fproj{j}", cin, 256, 1)
+    return out + _head_lstm_specs()
+
+
+def vgg_unused_specs():
+    """loc.* / conf.*: the multibox heads SSD builds (ssd_vgg.py:157-171, 21 classes) and ZSGNet never calls."""
+    e = "backbone.encoder."
+    out = []
+    for kind, mult in (("loc", 4), ("conf", 21)):
+        for i, (c, nb) in enumerate(zip((512, 1024, 512, 256, 256, 256), VGG_MBOX)):
+            out += _conv_bias(f"{e}{kind}.{i}", c, nb * mult, 3)
+    return out
+
+
+def trainable_specs(model="retina"):
     """[(name, shape, kind)] in forward order; `fc` (unused by the path, mdl.py:149-156) comes last."""
+    if model == "ssd_vgg":
+        return vgg_trainable_specs()
     out = []
     e = "backbone.encoder."
     out.append((e + "conv1.weight", (64, 3, 7, 7), "conv"))
@@ -63,8 +134,14 @@ def trainable_specs():
 UNUSED_SPECS = [("backbone.encoder.fc.weight", (1000, 2048), "lin"), ("backbone.encoder.fc.bias", (1000,), "bias")]
 
 
-def buffer_specs():
+def unused_specs(model="retina"):
+    return vgg_unused_specs() if model == "ssd_vgg" else list(UNUSED_SPECS)
+
+
+def buffer_specs(model="retina"):
     out = []
+    if model == "ssd_vgg":
+        return out                                   # no BatchNorm anywhere (vgg(..., batch_norm=False))
     e = "backbone.encoder."
     out += bn_buffers(e + "bn1", 64)
     for li, (nblk, width, _) in enumerate(RESNET_LAYERS, start=1):
