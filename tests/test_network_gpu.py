@@ -307,3 +307,61 @@ def test_ssd_vgg_train_step_vs_reference_golden(vgg_stack, golden_meta, name):
     for k, v in worst.items():
         assert v < (1e-4 if k.startswith(tight) else 5e-2), (k, v)
     assert float(np.median(list(worst.values()))) < 1e-3, worst
+
+
+# ------------------------------------------------------------------------------- f-3: checkpoints in the reference's format
+def test_checkpoint_round_trip_reference_format(stack, tmp_path):
+    """utils.py:440-497: {model_state_dict, optimizer_state_dict, scheduler_state_dict, num_it, num_epoch, cfgtxt,
+    best_met}.  The optimizer state must load into a stock torch.optim.Adam (the reference's optimiser) and resuming
+    from the file must continue like the original (restored state bit for bit; the next step up to the fp32 atomics of
+    the split-K weight gradients, whose summation order varies from run to run)."""
+    net, crit, ev, synth = stack
+    from zsg_b200 import checkpoint, mdl, optim
+    net.load_state_dict(synth.make_state_dict(0), strict=True)
+    net.train()
+    opt = optim.FusedAdam(net.parameters(), lr=1e-4, net=net)
+
+    def one_step(n, o, seed):
+        batch = to_dev(synth.make_batch(2, seed=seed))
+        torch.manual_seed(seed)
+        o.zero_grad()
+        crit(n(batch), batch)["loss"].mean().backward()
+        o.step()
+    one_step(net, opt, 1)
+    one_step(net, opt, 2)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.1, patience=2)
+    path = tmp_path / "ck.pth"
+    checkpoint.save_model_dict(path, net, opt, sched, num_it=2, num_epoch=1, best_met=0.5, cfg=synth.default_cfg(),
+                               ddp_prefix=True)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "num_it", "num_epoch", "cfgtxt",
+                       "best_met"}
+    assert all(k.startswith("module.") for k in ck["model_state_dict"])
+    w = ck["model_state_dict"]["module.backbone.encoder.layer1.0.conv2.weight"]
+    assert w.shape == (64, 64, 3, 3) and w.is_contiguous()
+    # reference side: a stock Adam over same-shaped parameters accepts the optimizer state
+    ref_params = [torch.nn.Parameter(p.detach().cpu().clone()) for p in net.parameters()]
+    adam = torch.optim.Adam(ref_params, lr=1e-4, betas=(0.9, 0.99))
+    adam.load_state_dict(ck["optimizer_state_dict"])
+    assert int(adam.state[ref_params[0]]["step"]) == 2
+    assert adam.state[ref_params[0]]["exp_avg"].shape == ref_params[0].shape
+    # resume into a fresh net + optimizer, then one more identical step on both
+    cfg = synth.default_cfg()
+    cfg["device"] = "cuda"
+    net2 = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    net2.train()
+    opt2 = optim.FusedAdam(net2.parameters(), lr=3e-3, net=net2)
+    info = checkpoint.load_model_dict(path, net2, opt2)
+    assert info == {"num_it": 2, "num_epoch": 1, "best_met": 0.5}
+    used = net.store.used
+    assert opt2.t == 2 and opt2.param_groups[0]["lr"] == 1e-4
+    assert torch.equal(net2.store.param_arena, net.store.param_arena)
+    assert torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v)
+    for k, v in net.state_dict().items():
+        assert torch.equal(net2.state_dict()[k], v), k
+    one_step(net, opt, 3)
+    one_step(net2, opt2, 3)
+    torch.cuda.synchronize()
+    d = (net2.store.param_arena[:used] - net.store.param_arena[:used]).abs()
+    # an Adam update is at most lr = 1e-4 per element; a wrong moment / step count / lr would move every element by O(lr)
+    assert float(d.mean()) < 1e-7 and float(d.max()) <= 2.5e-4, (float(d.mean()), float(d.max()))
