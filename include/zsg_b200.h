@@ -77,6 +77,11 @@ typedef struct {
                               cp.async with no register pass: the tensor core reads x itself as the TF32 high part */
   int32_t dil;             /* tap spacing: tap (r,s) reads (y0 + r*dil, x0 + s*dil); 0 means 1.  6 for the SSD conv6
                               (ssd_vgg.py:129) and its data gradient                                              */
+  float* stats;            /* optional (plain outputs only: no bias / ReLU / mask / residual / accumulate): BatchNorm
+                              statistics of y as a by-product of the epilogue.  [ceil(m/128)*4][2][cout] floats: for every
+                              32-row group of the output, the column sums and the column sums of squares.
+                              zsg_bn_stats_partials turns them into the sums zsg_bn_finalize reads, without
+                              re-reading y (replaces zsg_bn_stats for the 53 convs that feed a BatchNorm)             */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
@@ -130,6 +135,8 @@ int zsg_gather_rows(const float* src, const zsg_row_t* rows, float* dst, int64_t
  * torchvision resnet50's 53 BatchNorm2d in train mode (mdl.py:149-156, utils.py:395).      */
 /* sums[0:c] = sum x, sums[c:2c] = sum x^2 (double; must be zeroed by the caller). */
 int zsg_bn_stats(const float* x, double* sums, int64_t rows, int c, zsg_stream_t stream);
+/* the same sums from the per-row-group partials a conv wrote (zsg_conv_params.stats): parts = ceil(m/128)*4. */
+int zsg_bn_stats_partials(const float* partials, int64_t parts, int c, double* sums, zsg_stream_t stream);
 /* mean/invstd/scale/shift from the sums; updates running stats (momentum, unbiased var). */
 int zsg_bn_finalize(const double* sums, int64_t rows, int c, const float* gamma, const float* beta, float eps,
                     float momentum, float* running_mean, float* running_var, float* mean, float* invstd,

@@ -800,3 +800,42 @@ def test_l2norm_fwd_bwd(zsg):
     assert rel_err(y, nhwc(s)) < 1e-6
     assert rel_err(dx - other, nhwc(pre.grad)) < 2e-5
     assert rel_err(dx2 * (xn > 0), nhwc(pre.grad)) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(2, 64, 19, 19, 256, 3, 1, 1), (3, 128, 20, 18, 64, 1, 1, 0), (2, 4, 61, 61, 64, 7, 2, 3),
+                                  (5, 256, 7, 9, 520, 1, 1, 0)])
+def test_conv_epilogue_batchnorm_statistics(zsg, case):
+    """zsg_conv_params.stats: per-32-row-group column sums / sums of squares written by the conv epilogue, reduced by
+    zsg_bn_stats_partials, must equal zsg_bn_stats over the stored output (and torch's mean / biased variance)."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(B, cin, H, W, generator=g).cuda() + 0.3
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    ref = F.conv2d(x, w, None, stride=stride, padding=pad)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    M = B * Ho * Wo
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    wk, xn = khwc(w), nhwc(x)
+    hi, lo, x_lo = torch.empty_like(wk), torch.empty_like(wk), torch.empty_like(xn)
+    ops.split_tf32(wk, hi, lo, wk.numel())
+    ops.split_act(xn, x_lo, B * H * W, cin)
+    parts = (M + 127) // 128 * 4
+    part = torch.full((parts, 2, cout), float("nan"), device="cuda")
+    y = torch.empty(B, Ho, Wo, cout, device="cuda")
+    ops.ConvOp(xn, hi, y, rows, M, cin, cout, k, k, w_lo=lo, x_lo=x_lo, stats=part)()
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    ops.bn_stats_partials(part, parts, cout, sums)
+    direct = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    pow2 = (cout // 4) & (cout // 4 - 1) == 0                  # zsg_bn_stats wants C/4 to be a power of two
+    if pow2:
+        ops.bn_stats(y, direct, M, cout)
+    torch.cuda.synchronize()
+    assert not torch.isnan(part).any()
+    assert rel_err(y, nhwc(ref)) < 2e-5
+    # sums of ~M terms of either sign: absolute tolerance = fp32 rounding of the 32-row partials (values are O(1))
+    if pow2:
+        np.testing.assert_allclose(sums.cpu().numpy(), direct.cpu().numpy(), rtol=2e-6, atol=1e-7 * M)
+    y2 = y.view(M, cout).double()
+    np.testing.assert_allclose((sums[:cout] / M).cpu().numpy(), y2.mean(0).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose((sums[cout:] / M).cpu().numpy(), (y2 * y2).mean(0).cpu().numpy(), rtol=1e-5, atol=1e-7)

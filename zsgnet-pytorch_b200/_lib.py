@@ -25,7 +25,7 @@ class ConvParams(C.Structure):
                 ("m", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
                 ("in_div", C.c_int32), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
-                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32)]
+                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32), ("stats", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
@@ -53,6 +53,7 @@ SIGNATURES = {
     "zsg_colsum": [_P, _P, _L, _I, _I, _I, _P],
     "zsg_gather_rows": [_P, _P, _P, _L, _I, _I, _P],
     "zsg_bn_stats": [_P, _P, _L, _I, _P],
+    "zsg_bn_stats_partials": [_P, _L, _I, _P, _P],
     "zsg_bn_finalize": [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "zsg_bn_eval_affine": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
     "zsg_bn_apply": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],

@@ -447,6 +447,25 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         *reinterpret_cast<float4*>(stg + lane * 20 + j) =
             make_float4(acc[slab * 16 + j], acc[slab * 16 + j + 1], acc[slab * 16 + j + 2], acc[slab * 16 + j + 3]);
       __syncwarp();
+      if (p.stats) {
+        // BatchNorm statistics of this warp's 32 rows x 16 columns while they sit in the slab: lane = (row half,
+        // column); the two halves walk rows 20 (or 4) apart, which puts them on different banks (row stride 20 floats).
+        // Rows past p.m hold zeros (their A rows were zero-filled), so they add nothing.
+        const int col = lane & 15, hsel = lane >> 4;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int rr = hsel ? 16 + ((r + 4) & 15) : r;
+          const float v = stg[rr * 20 + col];
+          s1 += v;
+          s2 = fmaf(v, v, s2);
+        }
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+        const int ncol = n0 + half * (BN / 2) + slab * 16 + col;
+        if (ncol < p.cout)
+          p.stats[((int64_t)((m0 / TM) * 4 + quadrant) * 2 + hsel) * p.cout + ncol] = hsel ? s2 : s1;
+      }
       const int n = n0 + half * (BN / 2) + slab * 16 + c4;
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias && n < p.cout) {
@@ -1539,6 +1558,8 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(p.in_div == 1 || p.in_div == 2, "zsg_conv_fwd: in_div must be 1 or 2");
   ZSG_REQUIRE((((uintptr_t)p.x | (uintptr_t)p.w) & 15) == 0, "zsg_conv_fwd: x and w must be 16-byte aligned");
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_fwd: in_scale without in_shift");
+  ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.accumulate && p.impl != 1),
+              "zsg_conv_fwd: stats needs a plain output (no bias / ReLU / mask / residual / accumulate) on the tcgen05 path");
   cudaStream_t st = as_stream(stream);
   if (p.impl == 1) {
     const int64_t n = (int64_t)p.m * p.cout;

@@ -265,6 +265,32 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   }
 }
 
+// Column sums of the [parts][2][C] partial statistics a conv epilogue wrote (zsg_conv_params.stats) into the double
+// sums of bn_finalize.  Block = 8 part-lanes x 32 channels; grid.y strides over the parts; one double atomic per
+// (block, channel, moment), like channel_reduce_kernel.
+__global__ void __launch_bounds__(256) bn_partials_kernel(const float* __restrict__ partials, int64_t parts, int C,
+                                                          double* __restrict__ sums) {
+  __shared__ double sh[2][8][32];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int64_t p = (int64_t)blockIdx.y * 8 + pl; p < parts; p += (int64_t)gridDim.y * 8) {
+      a += (double)partials[(p * 2) * C + c];
+      b += (double)partials[(p * 2 + 1) * C + c];
+    }
+  }
+  sh[0][pl][cl] = a;
+  sh[1][pl][cl] = b;
+  __syncthreads();
+  if (pl < 2 && c < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[pl][i][cl];
+    atomicAdd(sums + pl * C + c, t);
+  }
+}
+
 // ------------------------------------- stem max-pool ----------------------------------------
 // forward also records, per output element, which tap of the 3x3 window won (first maximum in row-major scan
 // order over the valid taps, like ATen's max_pool2d): code = dy*3 + dx.  Backward is then a pure gather.
@@ -722,6 +748,16 @@ extern "C" int zsg_bn_stats(const float* x, double* sums, int64_t rows, int c, z
   ZSG_REQUIRE(x && sums && rows > 0, "zsg_bn_stats: bad arguments");
   return launch_channel_reduce(0, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, sums, rows, c,
                                as_stream(stream));
+}
+
+extern "C" int zsg_bn_stats_partials(const float* partials, int64_t parts, int c, double* sums, zsg_stream_t stream) {
+  ZSG_REQUIRE(partials && sums && parts > 0 && c > 0, "zsg_bn_stats_partials: bad arguments");
+  const int gx = (c + 31) / 32;
+  int64_t gy = (parts + 63) / 64;                         // >= 8 parts per part-lane
+  const int64_t cap = (int64_t)num_sms() * 4 / gx + 1;
+  if (gy > cap) gy = cap;
+  bn_partials_kernel<<<dim3(gx, (unsigned)gy), 256, 0, as_stream(stream)>>>(partials, parts, c, sums);
+  return check_launch("zsg_bn_stats_partials");
 }
 
 extern "C" int zsg_bn_finalize(const double* sums, int64_t rows, int c, const float* gamma, const float* beta,

@@ -181,10 +181,16 @@ class Engine:
         self.bns.append(bn)
         return bn
 
-    def bn_forward(self, bn, x):
-        """train: batch statistics (+ running-stat update); eval: affine from running stats."""
+    def bn_forward(self, bn, x, L=None):
+        """train: batch statistics (+ running-stat update); eval: affine from running stats.  L = the conv that wrote x
+        with statistics partials in its epilogue (conv(..., stats=True)): x is then not read again."""
+        part = L.get("stats") if L is not None else None
+
         def train():
-            ops.bn_stats(x, bn.sums, bn.rows, bn.c)
+            if part is not None:
+                ops.bn_stats_partials(part[0], part[1], bn.c, bn.sums)
+            else:
+                ops.bn_stats(x, bn.sums, bn.rows, bn.c)
             ops.bn_finalize(bn.sums, bn.rows, bn.c, bn.gamma, bn.beta, BN_EPS, BN_MOM, bn.rm, bn.rv, bn.mean,
                             bn.invstd, bn.scale, bn.shift)
 
@@ -193,7 +199,7 @@ class Engine:
         self.fwd.append(("bn", train, evalm))
 
     def conv(self, wname, x, hin, win, cin, cout, k, stride, pad, y, pro=None, in_relu=False, bias=None,
-             out_relu=False, w=None, dil=1):
+             out_relu=False, w=None, dil=1, stats=False):
         span = dil * (k - 1) + 1
         hout, wout = (hin + 2 * pad - span) // stride + 1, (win + 2 * pad - span) // stride + 1
         rows = self.rows("fwd", hin, win, cin, hout, wout, cout, stride, pad)
@@ -203,10 +209,15 @@ class Engine:
         else:
             w, w_hi, w_lo = w                                # a (w, hi, lo) triple from the pool
         xz, x_lo = self.fwd_operand(x, self.B * hin * win, cin, pro=pro, relu=in_relu)
+        part = None
+        if stats:                                            # BatchNorm statistics as a by-product of the epilogue
+            parts = (self.B * hout * wout + 127) // 128 * 4
+            assert parts * 2 * cout <= self._stats_scratch.numel()
+            part = (self._stats_scratch, parts)
         op = ConvOp(xz, w_hi, y, rows, self.B * hout * wout, cin, cout, k, k, bias=bias, out_relu=out_relu, impl=self.impl,
-                    w_lo=w_lo, x_lo=x_lo, dil=dil)
+                    w_lo=w_lo, x_lo=x_lo, dil=dil, stats=part[0] if part else None)
         self.fwd.append(("op", op))
-        return dict(wname=wname, x=x, xz=xz, x_lo=x_lo, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
+        return dict(stats=part, wname=wname, x=x, xz=xz, x_lo=x_lo, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
                     hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w, dil=dil)   # w: fp32 weights (dgrad prep)
 
     def conv_wgrad(self, L, dy, dy_lo, dw=None):
@@ -308,6 +319,12 @@ class Engine:
         B, T, st, dev = self.B, self.T, self.store, self.device
         e = "backbone.encoder."
 
+        # scratch for the per-32-row statistics partials of one conv (the conv and its BatchNorm finalize run back to
+        # back on the main stream, so one buffer serves all 53)
+        nparts = lambda m: (m + 127) // 128 * 4
+        self._stats_scratch = self.buf(2 * max(nparts(B * 22500) * 64, nparts(B * 5625) * 256, nparts(B * 1444) * 512,
+                                               nparts(B * 361) * 1024, nparts(B * 100) * 2048))
+
         # ---------------- stem: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2 (mdl.py:149-152)
         img4 = self.buf(B, 300, 300, 4)
         w1p_t = self.pool_alloc(64 * 49 * 4)
@@ -318,9 +335,9 @@ class Engine:
         self.fwd.append(("fn", lambda: ops.nchw_to_nhwc4(self.inp["img"], img4)))
         self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, 4))
         self._alloc_head_w0p()                                # region F (forward-time transformed weights) ends here
-        Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p_t)
+        Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p_t, stats=True)
         bn1 = self.add_bn(e + "bn1", 64, B * 150 * 150)
-        self.bn_forward(bn1, c1)
+        self.bn_forward(bn1, c1, Lstem)
         pool_arg = torch.empty(B * 75 * 75 * 64, dtype=torch.uint8, device=dev)
         self.fwd.append(("fn", lambda: ops.maxpool_bn_relu_fwd(c1, bn1.scale, bn1.shift, x0, pool_arg, B, 150, 150, 64, 75,
                                                                75)))
@@ -348,21 +365,21 @@ class Engine:
                 ri, ro = B * h * h, B * ho * ho
                 r1, r2, r3 = self.buf(ri, width), self.buf(ro, width), self.buf(ro, 4 * width)
                 out, g_out = self.buf(ro, 4 * width), self.buf(ro, 4 * width)
-                La = self.conv(p + "conv1.weight", inp, h, h, cin, width, 1, 1, 0, r1)
+                La = self.conv(p + "conv1.weight", inp, h, h, cin, width, 1, 1, 0, r1, stats=True)
                 bnA = self.add_bn(p + "bn1", width, ri)
-                self.bn_forward(bnA, r1)
-                Lb = self.conv(p + "conv2.weight", r1, h, h, width, width, 3, s, 1, r2, pro=bnA, in_relu=True)
+                self.bn_forward(bnA, r1, La)
+                Lb = self.conv(p + "conv2.weight", r1, h, h, width, width, 3, s, 1, r2, pro=bnA, in_relu=True, stats=True)
                 bnB = self.add_bn(p + "bn2", width, ro)
-                self.bn_forward(bnB, r2)
-                Lc = self.conv(p + "conv3.weight", r2, ho, ho, width, 4 * width, 1, 1, 0, r3, pro=bnB, in_relu=True)
+                self.bn_forward(bnB, r2, Lb)
+                Lc = self.conv(p + "conv3.weight", r2, ho, ho, width, 4 * width, 1, 1, 0, r3, pro=bnB, in_relu=True, stats=True)
                 bnC = self.add_bn(p + "bn3", 4 * width, ro)
-                self.bn_forward(bnC, r3)
+                self.bn_forward(bnC, r3, Lc)
                 Ld = bnD = rd = None
                 if b == 0:
                     rd = self.buf(ro, 4 * width)
-                    Ld = self.conv(p + "downsample.0.weight", inp, h, h, cin, 4 * width, 1, s, 0, rd)
+                    Ld = self.conv(p + "downsample.0.weight", inp, h, h, cin, 4 * width, 1, s, 0, rd, stats=True)
                     bnD = self.add_bn(p + "downsample.1", 4 * width, ro)
-                    self.bn_forward(bnD, rd)
+                    self.bn_forward(bnD, rd, Ld)
 
                 out_lo = self.buf(ro, 4 * width)              # operand image of the block output, written by the tail
                 self._operand_cache[(out.data_ptr(), ro, 4 * width, id(None), False)] = (out, out_lo)

@@ -45,11 +45,11 @@ class ConvOp:
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
-                 x_lo=None, dil=1):
-        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo)
+                 x_lo=None, dil=1, stats=None):
+        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats)
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl, ptr(x_lo), dil)
+                            impl, ptr(x_lo), dil, ptr(stats))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
         self.kernel = "conv_tc_async_kernel" if x_lo is not None else ("conv_tc_kernel" if w_lo is not None else "conv_tc_generic_kernel")
@@ -109,6 +109,10 @@ def gather_rows(src, rows, dst, m, csrc, cdst):
 
 def bn_stats(x, sums, rows, c):
     call("zsg_bn_stats", ptr(x), ptr(sums), rows, c, stream())
+
+
+def bn_stats_partials(partials, parts, c, sums):
+    call("zsg_bn_stats_partials", ptr(partials), parts, c, ptr(sums), stream())
 
 
 def bn_finalize(sums, rows, c, gamma, beta, eps, momentum, rm, rv, mean, invstd, scale, shift):
