@@ -36,6 +36,10 @@ def run(B, cin, H, cout, k, label):
     ms = a.elapsed_time(b) / 5
     print(f"{label:28s} {'torch fill_ of y':24s} {ms:7.3f} ms  {4.0*M*cout/ms/1e6:7.0f} GB/s", flush=True)
 
-run(64, 64, 75, 256, 1, "1x1 64->256 M=360000")
-run(64, 128, 38, 512, 1, "1x1 128->512 M=92416")
-run(64, 256, 75, 64, 1, "1x1 256->64 M=360000")
+if len(sys.argv) > 1:
+    run(64, 64, 75, 64, 1, "1x1 64->64 M=360000")
+    run(64, 64, 75, 64, 3, "3x3 64->64 M=360000")
+else:
+    run(64, 64, 75, 256, 1, "1x1 64->256 M=360000")
+    run(64, 128, 38, 512, 1, "1x1 128->512 M=92416")
+    run(64, 256, 75, 64, 1, "1x1 256->64 M=360000")

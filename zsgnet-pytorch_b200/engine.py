@@ -92,6 +92,7 @@ class Engine:
         self._operand_cache, self._bwd_lo = {}, {}
         self._side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
         self.overlap_wgrad = self._side_stream is not None
+        self.overlap_lstm = self._side_stream is not None
         self._f64_pool, self._f64_used = torch.zeros(1 << 18, dtype=torch.float64, device=device), 0
         self.bns = []
         self.fwd_train, self.fwd_eval_bn, self.fwd, self.bwd, self.prep_bwd = [], [], [], [], []
@@ -784,7 +785,7 @@ class Engine:
                 item[1]()
 
         lo, hi = self._lstm_items
-        side = self._side_stream
+        side = self._side_stream if self.overlap_lstm else None
         if side is not None:
             # the query encoder (20 sequential LSTM steps, latency-bound) only depends on the inputs: it runs on the side
             # stream under the image trunk and is joined before the language vector is tiled into the head input
