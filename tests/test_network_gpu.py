@@ -365,3 +365,46 @@ def test_checkpoint_round_trip_reference_format(stack, tmp_path):
     d = (net2.store.param_arena[:used] - net.store.param_arena[:used]).abs()
     # an Adam update is at most lr = 1e-4 per element; a wrong moment / step count / lr would move every element by O(lr)
     assert float(d.mean()) < 1e-7 and float(d.max()) <= 2.5e-4, (float(d.mean()), float(d.max()))
+
+
+# ------------------------------------------------------------------------------- edge cases of the input contract
+@pytest.mark.parametrize("B,lens", [(1, [1.0]), (2, [50.0, 7.0]), (3, [1.0, 20.0, 1.0])])
+def test_extreme_batch_and_phrase_lengths_vs_live_oracle(stack, B, lens):
+    """Smallest batch (one pair: BatchNorm statistics over a single image), one-token phrases (the reverse LSTM direction
+    and the forward one see the same single token) and the loader's maximum phrase length of 50 (dat_loader.py:86)."""
+    net, crit, ev, synth = stack
+    from oracle import zsg_oracle as zo
+    T = int(max(lens))
+    batch = synth.make_batch(B, seed=91, T=T)
+    batch["qlens"] = torch.tensor(lens)
+    net.load_state_dict(synth.make_state_dict(0), strict=True)
+    net.train()
+    net.zero_grad()
+    torch.manual_seed(5)
+    out = net(to_dev(batch))
+    ls = crit(out, to_dev(batch))
+    ls["loss"].mean().backward()
+    met = ev(out, to_dev(batch))
+    torch.cuda.synchronize()
+    sd = synth.make_state_dict(0)
+    ols, omet, ograds, oout, _ = zo.train_step(sd, batch, seed=5, do_adam=False)
+    assert out["att_out"].shape == (B, 17460, 1)
+    for k in ("loss", "cls_ls", "box_ls"):
+        assert ls[k].item() == pytest.approx(ols[k].item(), rel=RTOL), k
+    assert torch.equal(crit.last_top1.cpu(), ols["top1"]) and torch.equal(crit.last_pos.cpu().bool(), ols["pos"])
+    assert torch.equal(met["best_ids"].cpu(), omet["idxs_best"]) and met["Acc"].item() == omet["Acc"].item()
+    # the language path is exact arithmetic-wise (no BatchNorm in it): its gradients must agree tightly
+    for k in ("lstm.weight_ih_l0_reverse", "lstm.bias_hh_l0"):
+        g, r = net.get_parameter(k).grad.cpu().double(), ograds[k].double()
+        assert float((g - r).norm() / r.norm().clamp_min(1e-30)) < 5e-2, k
+
+
+def test_inputs_are_validated_not_silently_accepted(stack):
+    net, crit, ev, synth = stack
+    batch = synth.make_batch(2, seed=3)
+    with pytest.raises(RuntimeError):
+        net(batch)                                        # host tensors: there is no CPU path
+    bad = to_dev(batch)
+    bad["img"] = bad["img"][:, :, :256, :256].contiguous()
+    with pytest.raises((AssertionError, RuntimeError, NotImplementedError)):
+        net(bad)                                          # only 300x300 is built (resize_img)
