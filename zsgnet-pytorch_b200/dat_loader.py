@@ -1,12 +1,22 @@
 """Batch contract of the reference's code/dat_loader.py (the boundary on the input side).
 
-The reference's loader is CPU work outside the hot path (PIL decode, spaCy vectors; SURVEY.md
-section 2 #8) and is not rebuilt.  What the hot path needs from it is the batch dict
-(dat_loader.py:136-144, 187-196) and `get_data(cfg) -> DataWrap`; this module supplies both over
-a seeded synthetic dataset of the BASELINE shape (300x300 images, 300-d query vectors)."""
+What the hot path needs from the loader is the batch dict (dat_loader.py:136-144, 187-196) and
+`get_data(cfg) -> DataWrap`.  This module supplies both
+  * over a seeded synthetic dataset of the BASELINE shape (300x300 images, 300-d query vectors), and
+  * over the reference's on-disk format: the annotation CSV `img_id,bbox,query`
+    (DATA_PREP_README.md:10-11) read like ImgQuDataset (dat_loader.py:66-185), images decoded and resized with PIL
+    as there.  The word vectors are the one thing the reference takes from a package that is not in this image
+    (spaCy en_core_web_md, dat_loader.py:23): ImgQuDataset takes an `embed(text) -> [n_tokens, 300]` callable
+    and falls back to spaCy only when it is importable.
+The prediction file of Learner.validate / update_prediction_file (utils.py:377-381, 500-509) is written by
+`prediction_records` / `write_prediction_file`."""
+import ast
+import pickle
 from dataclasses import dataclass
+from pathlib import Path
 from typing import Dict, Optional, Union
 
+import numpy as np
 import torch
 from torch.utils.data import DataLoader, Dataset
 from torch.utils.data.distributed import DistributedSampler
@@ -61,6 +71,82 @@ class SyntheticImgQuDataset(Dataset):
         return {"img": torch.rand(3, self.hw, self.hw, generator=g), "idxs": torch.tensor(idx),
                 "qvec": qvec, "qlens": torch.tensor(qlen), "annot": annot, "orig_annot": orig,
                 "img_size": torch.tensor([h, w])}
+
+
+class ImgQuDataset(Dataset):
+    """dat_loader.py:66-185.  One item per CSV row: the image resized to cfg.resize_img and scaled to [0,1] (no mean /
+    std normalisation, 89-90), the phrase padded with ' PD' tokens to 50 vectors (107-114), the box turned from pixel
+    x1y1x2y2 into y1x1y2x2 in [-1,1] (119-128).  Keys and dtypes are the reference's (136-144)."""
+
+    def __init__(self, cfg, csv_file, ds_name, split_type="train", embed=None):
+        self.cfg, self.ann_file, self.ds_name, self.split_type = cfg, csv_file, ds_name, split_type
+        self.image_data = self._read_annotations(csv_file)
+        self.img_dir = Path(cfg["ds_info"][ds_name]["img_dir"])
+        self.phrase_len = 50
+        self.embed = embed if embed is not None else _spacy_embedder()
+
+    def __len__(self):
+        return len(self.image_data)
+
+    def _read_annotations(self, csv_file):
+        """dat_loader.py:163-185: bbox is a python-literal list [x1,y1,x2,y2]; query is a string or a python-literal
+        list of strings (decided on the first row); flickr30k image names get a .jpg suffix."""
+        import pandas as pd
+        df = pd.read_csv(csv_file)
+        df["bbox"] = df.bbox.apply(ast.literal_eval)
+        if str(df["query"].iloc[0])[0] == "[":
+            df["query"] = df["query"].apply(ast.literal_eval)
+        names = df.img_id.apply(lambda x: f"{x}.jpg") if self.ds_name == "flickr30k" else df.img_id
+        return [(n, b[0], b[1], b[2], b[3], q) for n, b, q in zip(names, df.bbox, df["query"])]
+
+    def load_annotations(self, idx):
+        img_file, x1, y1, x2, y2, queries = self.image_data[idx]
+        q = str(np.random.choice(queries)) if isinstance(queries, list) else queries
+        assert isinstance(q, str)
+        return self.img_dir / f"{img_file}", np.array([x1, y1, x2, y2]), q.replace("_", " ")
+
+    def __getitem__(self, idx):
+        import PIL.Image
+        img_file, annot, q = self.load_annotations(idx)
+        img = PIL.Image.open(img_file).convert("RGB")
+        h, w = img.height, img.width
+        q = q.strip()
+        qlen = len(self.embed(q))
+        if qlen == 0:
+            raise NotImplementedError("empty query")                 # dat_loader.py:103-105
+        vecs = np.asarray(self.embed(q + " PD" * (self.phrase_len - qlen)), dtype=np.float32)[: self.phrase_len]
+        img = img.resize((self.cfg["resize_img"][0], self.cfg["resize_img"][1]))
+        t = np.array([annot[1] / h, annot[0] / w, annot[3] / h, annot[2] / w])
+        px = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255)
+        return {"img": px, "idxs": torch.tensor(idx).long(), "qvec": torch.from_numpy(vecs), "qlens": torch.tensor(qlen),
+                "annot": torch.from_numpy(2 * t - 1).float(), "orig_annot": torch.tensor(annot).float(),
+                "img_size": torch.tensor([h, w])}
+
+
+def _spacy_embedder():
+    try:
+        import spacy
+        nlp = spacy.load("en_core_web_md")                         # dat_loader.py:23
+    except Exception as e:                                           # not in this image
+        raise RuntimeError("ImgQuDataset needs word vectors: pass embed=callable(text) -> [n_tokens, 300] "
+                           "(spaCy en_core_web_md, the reference's source, is not importable here)") from e
+    return lambda text: np.array([t.vector for t in nlp(str(text))])
+
+
+def prediction_records(metric):
+    """The per-sample prediction dicts Learner.validate collects (utils.py:377-383): metric = Evaluator output."""
+    ids, boxes, scores = metric["idxs"].tolist(), metric["pred_boxes"].tolist(), metric["pred_scores"].tolist()
+    return [{"id": i, "pred_boxes": b, "pred_scores": s} for i, b, s in zip(ids, boxes, scores)]
+
+
+def write_prediction_file(predictions, pred_file, rank=0, distributed=False):
+    """utils.py:500-509: a pickled list of {'id','pred_boxes','pred_scores'}; one file per rank under DDP
+    ('<rank>_<name>'), which eval_script.py:4-8 reads back."""
+    pred_file = Path(pred_file)
+    target = pred_file.parent / f"{rank}_{pred_file.name}" if distributed else pred_file
+    with target.open("wb") as f:
+        pickle.dump(predictions, f)
+    return target
 
 
 def synthetic_batch(B, seed=0, T=20, img_hw=300, pin=False):
@@ -134,8 +220,17 @@ def get_dataloader(cfg, dataset, is_train):
     return DataLoader(dataset, batch_size=bs, sampler=sampler, drop_last=is_train, num_workers=0, collate_fn=collater)
 
 
-def get_data(cfg):
-    """Same signature as dat_loader.py:230-253, over synthetic data."""
+def get_data(cfg, embed=None):
+    """Same signature as dat_loader.py:230-253.  With cfg.ds_to_use / cfg.ds_info set, the reference's CSV datasets
+    (train / valid / test); otherwise synthetic data of the BASELINE shape."""
+    if "ds_to_use" in cfg and "ds_info" in cfg and cfg["ds_to_use"] in cfg["ds_info"]:
+        name = cfg["ds_to_use"]
+        info = cfg["ds_info"][name]
+        ds = {k: ImgQuDataset(cfg, info[f"{k}_csv_file"], name, split_type="train" if k == "trn" else "valid", embed=embed)
+              for k in ("trn", "val", "test")}
+        return DataWrap(path=cfg["tmp_path"] if "tmp_path" in cfg else "./tmp",
+                        train_dl=get_dataloader(cfg, ds["trn"], True), valid_dl=get_dataloader(cfg, ds["val"], False),
+                        test_dl={"test0": get_dataloader(cfg, ds["test"], False)})
     n = cfg["synthetic_len"] if "synthetic_len" in cfg else 256
     trn, val = SyntheticImgQuDataset(n, seed=0), SyntheticImgQuDataset(max(n // 4, 1), seed=1)
     return DataWrap(path=cfg["tmp_path"] if "tmp_path" in cfg else "./tmp", train_dl=get_dataloader(cfg, trn, True),
