@@ -439,6 +439,27 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
     // with full 32-byte sectors, for the store and for the residual / mask / accumulate reads alike.
     float* stg = reinterpret_cast<float*>(sm + S::EPI_OFF + dw * S::EPI_WARP_BYTES);
     const int rsel = lane >> 2, c4 = (lane & 3) * 4;
+    // Plain stores (every conv that feeds a BatchNorm, the plain data gradients): the row offsets of the four rows
+    // this lane stores are fetched once per tile and the per-slab work is four LDS.128 + four STG.128, against ~100
+    // instructions per pass of the generic path below (653 per warp and tile in the ncu source view).  Worth 1 % of
+    // the training step; the store-heavy 1x1 64->256 conv itself did not move (0.172 -> 0.168 ms), so its limit is
+    // not the epilogue's instruction count.
+    const bool plain = !p.bias && !p.out_mask && !p.residual && !p.accumulate && !p.out_relu && (p.cout & 3) == 0 &&
+                       !(ablate & 16);
+    int64_t po[4];
+    bool pk[4];
+    bool use_plain = false;
+    if (plain) {
+      bool al = true;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int o = __shfl_sync(0xffffffffu, out_off, i * 8 + rsel);
+        pk[i] = __shfl_sync(0xffffffffu, (int)row_ok, i * 8 + rsel) != 0;
+        po[i] = (int64_t)o + n0 + half * (BN / 2) + c4;
+        al = al && (o & 3) == 0;
+      }
+      use_plain = __all_sync(0xffffffffu, al);             // unaligned row offsets: leave the tile to the generic path
+    }
 #pragma unroll
     for (int slab = 0; slab < BN / 32; ++slab) {
       __syncwarp();
@@ -467,6 +488,16 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
           p.stats[((int64_t)((m0 / TM) * 4 + quadrant) * 2 + hsel) * p.cout + ncol] = hsel ? s2 : s1;
       }
       const int n = n0 + half * (BN / 2) + slab * 16 + c4;
+      if (use_plain) {
+        if (n < p.cout) {                                   // cout % 4 == 0: the whole float4 is inside
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + (i * 8 + rsel) * 20 + c4);
+            if (pk[i]) *reinterpret_cast<float4*>(p.y + po[i] + slab * 16) = v;
+          }
+        }
+        continue;
+      }
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias && n < p.cout) {
         if (n + 3 < p.cout) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -730,9 +761,10 @@ constexpr int FULL_COUNT_TMA = NPROD / 32 + 1;
 
 // Register re-balancing (cp.async kernels): the producers only form addresses, the drain warps hold 64 accumulators
 // per thread plus the epilogue's state.  The carve-out leaves ~6 KB of L1, so a spilled register costs an L2 round
-// trip: with the launch-time 96 registers the epilogue loop reloaded two spilled values per iteration and took
-// 7.5 k cycles per tile; producers give registers up (96 -> 56), drain warps take exactly what was freed (96 -> 136): setmaxnreg.inc draws
-// from the CTA's own pool, a larger request never returns.
+// trip (two spilled values in the epilogue loop cost 7.5 k cycles per tile).  Launch-time count: 96 -- registers are
+// allocated per 4 warps, so the 18 warps pay for 20 and 20 x 32 x 96 = 61440 is the most that fits (a build with
+// __maxnreg__(112) fails to launch: "too many resources").  Producers give up 96 -> 56, drain warps take exactly what
+// was freed, 96 -> 136: setmaxnreg.inc draws only from what the CTA's own warps released, a larger request never returns.
 __device__ __forceinline__ void regs_release_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); }
 __device__ __forceinline__ void regs_take_drain() { asm volatile("setmaxnreg.inc.sync.aligned.u32 136;"); }
      // one elected arrive per producer warp + the expect_tx arrive

@@ -638,17 +638,30 @@ __global__ void __launch_bounds__(256) unfuse_feat_kernel(const float* __restric
   }
 }
 
-// one block per (sample, level): dlang[b][j] += sum over the level's cells
+// one block per (sample, level, chunk of 64 cells): dlang[b][j] += sum over the chunk's cells (four rows in flight per
+// thread; one block per whole level walked 1444 cells with a single load in flight: 181 us for 139 MB)
+constexpr int UNFUSE_CHUNK = 64;
 __global__ void __launch_bounds__(256) unfuse_lang_kernel(const float* __restrict__ dfused, float* __restrict__ dlang,
                                                           int B, Levels lv, int cfeat, int clang, int cpad) {
   const int b = blockIdx.x, l = blockIdx.y;
+  const int c0 = blockIdx.z * UNFUSE_CHUNK;
+  const int ncell = lv.cells[l];
+  if (c0 >= ncell) return;
+  const int c1 = min(c0 + UNFUSE_CHUNK, ncell);
   int64_t off = 0;
   for (int k = 0; k < l; ++k) off += (int64_t)B * lv.cells[k];
-  const float* base = dfused + (off + (int64_t)b * lv.cells[l]) * cpad + cfeat;
+  const float* base = dfused + (off + (int64_t)b * ncell) * cpad + cfeat;
   for (int j = threadIdx.x; j < clang; j += blockDim.x) {
-    float s = 0.f;
-    for (int cell = 0; cell < lv.cells[l]; ++cell) s += base[(size_t)cell * cpad + j];
-    atomicAdd(&dlang[(size_t)b * clang + j], s);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int cell = c0;
+    for (; cell + 3 < c1; cell += 4) {
+      s0 += base[(size_t)cell * cpad + j];
+      s1 += base[(size_t)(cell + 1) * cpad + j];
+      s2 += base[(size_t)(cell + 2) * cpad + j];
+      s3 += base[(size_t)(cell + 3) * cpad + j];
+    }
+    for (; cell < c1; ++cell) s0 += base[(size_t)cell * cpad + j];
+    atomicAdd(&dlang[(size_t)b * clang + j], (s0 + s1) + (s2 + s3));
   }
 }
 
@@ -947,7 +960,10 @@ extern "C" int zsg_unfuse_lang_grid(const float* dfused, float* dfeat, float* dl
   unfuse_feat_kernel<<<grid_for((int64_t)b * total_cells * (cfeat / 4), 256), 256, 0, st>>>(
       dfused, dfeat, (int64_t)b * total_cells, cfeat, cpad);
   cudaMemsetAsync(dlang, 0, (size_t)b * clang * sizeof(float), st);
-  unfuse_lang_kernel<<<dim3(b, nlvl), 256, 0, st>>>(dfused, dlang, b, lv, cfeat, clang, cpad);
+  int max_cells = 1;
+  for (int i = 0; i < nlvl; ++i) max_cells = lv.cells[i] > max_cells ? lv.cells[i] : max_cells;
+  unfuse_lang_kernel<<<dim3(b, nlvl, (max_cells + UNFUSE_CHUNK - 1) / UNFUSE_CHUNK), 256, 0, st>>>(dfused, dlang, b, lv, cfeat,
+                                                                                                  clang, cpad);
   return check_launch("zsg_unfuse_lang_grid");
 }
 
