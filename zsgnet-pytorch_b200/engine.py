@@ -804,10 +804,7 @@ class Engine:
             if i == hi and side is not None:
                 main.wait_event(done)
             run(item)
-        if training:
-            for bn in self.bns:
-                pass                                      # num_batches_tracked is bumped in one op below
-        return self.out
+        return self.out                                   # num_batches_tracked is bumped by the caller (one op for all)
 
     def backward(self, d_out=None, on_bucket=None):
         """d_out: [B,A,5] gradient of the packed head output (copied into the static buffer unless it already
