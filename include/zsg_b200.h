@@ -113,6 +113,15 @@ int zsg_conv_wgrad(const zsg_wgrad_params* p, zsg_stream_t stream);
 /* w [cout][r][s][cin] -> wt [cin][r][s][cout] with the taps flipped: the dgrad of a conv is the
  * forward kernel applied to wt. */
 int zsg_weight_transpose_flip(const float* w, float* wt, int cout, int rs_r, int rs_s, int cin, zsg_stream_t stream);
+/* The same for n weight tensors in ONE launch (the backward needs ~64 of them per step and each alone is a
+ * launch-latency-bound 8 us kernel): entry e transposes src_base[src .. ) -> dst_base[dst .. ); `begin` is the
+ * running element count (begin[0] = 0, ascending), total = sum of cout*r*s*cin.  descs lives in device memory. */
+typedef struct {
+  int64_t src, dst, begin;
+  int32_t cout, r, s, cin;
+} zsg_wtf_desc;
+int zsg_weight_transpose_flip_batched(const float* src_base, float* dst_base, const zsg_wtf_desc* descs, int n,
+                                      int64_t total, zsg_stream_t stream);
 /* Operand preparation for the cp.async GEMM paths: z = relu?(x * scale[c] + shift[c]) (z may be NULL when there is
  * no affine / ReLU: the tensor is its own high part) and lo = z - trunc_tf32(z).  x is [rows, c], c % 4 == 0.
  * Replaces the on-the-fly split inside the conv kernels for every conv of the path (mdl.py / fpn_resnet.py). */

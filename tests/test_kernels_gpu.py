@@ -839,3 +839,24 @@ def test_conv_epilogue_batchnorm_statistics(zsg, case):
     y2 = y.view(M, cout).double()
     np.testing.assert_allclose((sums[:cout] / M).cpu().numpy(), y2.mean(0).cpu().numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose((sums[cout:] / M).cpu().numpy(), (y2 * y2).mean(0).cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_batched_weight_transpose_flip(zsg):
+    """One launch for many conv weights must equal the per-tensor kernel (which is checked against torch above)."""
+    ops, _ = zsg
+    g = torch.Generator().manual_seed(61)
+    shapes = [(64, 1, 64), (256, 3, 128), (45 + 3, 3, 256), (8, 7, 4), (512, 1, 2048)]     # cout, k, cin
+    src = torch.randn(sum(co * k * k * ci for co, k, ci in shapes) + 64, generator=g).cuda()
+    dst = torch.full_like(src, float("nan"))
+    want = torch.full_like(src, float("nan"))
+    entries, off = [], 0
+    for co, k, ci in shapes:
+        n = co * k * k * ci
+        entries.append((off, off, co, k, k, ci))
+        ops.weight_transpose_flip(src[off:off + n], want[off:off + n], co, k, k, ci)
+        off += n
+    tab, total = ops.wtf_table(entries, "cuda")
+    assert total == off
+    ops.weight_transpose_flip_batched(src, dst, tab, len(entries), total)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:off], want[:off]) and torch.isnan(dst[off:]).all()

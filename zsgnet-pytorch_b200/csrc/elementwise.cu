@@ -680,6 +680,27 @@ __global__ void __launch_bounds__(256) weight_transpose_flip_kernel(const float*
   }
 }
 
+__global__ void __launch_bounds__(256) weight_transpose_flip_batched_kernel(const float* __restrict__ src,
+                                                                            float* __restrict__ dst,
+                                                                            const zsg_wtf_desc* __restrict__ descs, int n,
+                                                                            int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;                                // last entry with begin <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (descs[mid].begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const zsg_wtf_desc d = descs[lo];
+    const int64_t j = i - d.begin;                         // index into wt [cin][r][s][cout]
+    const int k = (int)(j % d.cout);
+    int64_t t = j / d.cout;
+    const int s_ = (int)(t % d.s); t /= d.s;
+    const int r_ = (int)(t % d.r);
+    const int c = (int)(t / d.r);
+    dst[d.dst + j] = src[d.src + (((int64_t)k * d.r + (d.r - 1 - r_)) * d.s + (d.s - 1 - s_)) * d.cin + c];
+  }
+}
+
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi,
                                                          float* __restrict__ lo, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -973,6 +994,13 @@ extern "C" int zsg_weight_transpose_flip(const float* w, float* wt, int cout, in
   weight_transpose_flip_kernel<<<grid_for((int64_t)cout * rs_r * rs_s * cin, 256), 256, 0, as_stream(stream)>>>(
       w, wt, cout, rs_r, rs_s, cin);
   return check_launch("zsg_weight_transpose_flip");
+}
+
+extern "C" int zsg_weight_transpose_flip_batched(const float* src_base, float* dst_base, const zsg_wtf_desc* descs, int n,
+                                                 int64_t total, zsg_stream_t stream) {
+  ZSG_REQUIRE(src_base && dst_base && descs && n > 0 && total > 0, "zsg_weight_transpose_flip_batched: bad arguments");
+  weight_transpose_flip_batched_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src_base, dst_base, descs, n, total);
+  return check_launch("zsg_weight_transpose_flip_batched");
 }
 
 extern "C" int zsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, zsg_stream_t stream) {

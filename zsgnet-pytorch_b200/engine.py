@@ -105,6 +105,7 @@ class Engine:
         self.pool_n = 44 << 20
         self.pool, self.pool_hi, self.pool_lo = self.buf(self.pool_n), self.buf(self.pool_n), self.buf(self.pool_n)
         self._pool_used, self._pool_f_end = 0, None
+        self._wtf = []
         self.prep_fwd = []
         self._build()
 
@@ -234,7 +235,7 @@ class Engine:
         k, cin, cout, stride = L["k"], L["cin"], L["cout"], L["stride"]
         wt, wt_hi, wt_lo = self.pool_alloc(cin * k * k * cout)
         w = L["w"]
-        self.prep_bwd.append(lambda: ops.weight_transpose_flip(w, wt, cout, k, k, cin))
+        self.queue_transpose(w, wt, cout, k, cin)
         epi = dict(out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl)
         if stride == 2 and k == 3 and L["pad"] == 1:
             # four parity classes of input pixels, each a dense 1- or 2-tap conv over dy (geometry.dgrad_rows_s2_class):
@@ -266,6 +267,16 @@ class Engine:
         rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, stride, L["pad"], L["dil"])
         self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=stride,
                                w_lo=wt_lo, x_lo=dy_lo, dil=L["dil"], **epi))
+
+    def queue_transpose(self, w, wt, cout, k, cin):
+        """Flipped-transposed copy of a conv weight for its data gradient.  Copies from the parameter arena into the
+        transformed-weight pool are collected into ONE launch per backward (zsg_weight_transpose_flip_batched)."""
+        a = self.store.param_arena
+        so, do = (w.data_ptr() - a.data_ptr()) // 4, (wt.data_ptr() - self.pool.data_ptr()) // 4
+        if 0 <= so < a.numel() and 0 <= do < self.pool_n:
+            self._wtf.append((so, do, cout, k, k, cin))
+        else:
+            self.prep_bwd.append(lambda: ops.weight_transpose_flip(w, wt, cout, k, k, cin))
 
     def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True):
         """BatchNorm backward; returns the lo image of dx (written by the same kernel) for the GEMMs that follow."""
@@ -309,6 +320,10 @@ class Engine:
             lo = min(st.offsets[n] for n in names)
             hi = max(st.offsets[n] + _align(st.numel(n)) for n in names)
             self.bucket_marks.append((len(self.bwd), lo, hi))
+        if self._wtf:                                     # first: the stride-2 class slices are cut from these copies
+            tab, total = ops.wtf_table(self._wtf, dev)
+            n, arena, pool = len(self._wtf), st.param_arena, self.pool
+            self.prep_bwd.insert(0, lambda: ops.weight_transpose_flip_batched(arena, pool, tab, n, total))
 
     def _alloc_head_w0p(self):
         """Padded first head weight: the last forward-time entry of the transformed-weight pool (region F)."""
@@ -723,7 +738,7 @@ class Engine:
                                    w_lo=wt5p_t[2], x_lo=dy5_lo))
             for i in range(4, 0, -1):
                 wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i][0]
-                self.prep_bwd.append(lambda wi=wi, wti=wti: ops.weight_transpose_flip(wi, wti, 256, 3, 3, 256))
+                self.queue_transpose(wi, wti, 256, 3, 256)
                 gb = st.grad_flat(f"att_reg_box.{i}.0.bias")
                 self.bwd.append(lambda i=i, gb=gb: ops.colsum(dhs[i], gb, M, 256))
                 dlo = self.bwd_operand(dhs[i], M, 256)

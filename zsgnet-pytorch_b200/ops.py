@@ -2,6 +2,7 @@
 streams only; every computation below is a kernel of libzsg_b200.so."""
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -79,6 +80,24 @@ class WgradOp:
 
 def weight_transpose_flip(w, wt, cout, r, s, cin):
     call("zsg_weight_transpose_flip", ptr(w), ptr(wt), cout, r, s, cin, stream())
+
+
+WTF_DESC = np.dtype([("src", "<i8"), ("dst", "<i8"), ("begin", "<i8"), ("cout", "<i4"), ("r", "<i4"), ("s", "<i4"), ("cin", "<i4")])
+
+
+def wtf_table(entries, device):
+    """Device table for weight_transpose_flip_batched from [(src_off, dst_off, cout, r, s, cin)] (element offsets)."""
+    arr = np.zeros(len(entries), dtype=WTF_DESC)
+    begin = 0
+    for i, (so, do, cout, r, s, cin) in enumerate(entries):
+        arr[i] = (so, do, begin, cout, r, s, cin)
+        begin += cout * r * s * cin
+    assert arr.itemsize == 40
+    return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(device), begin
+
+
+def weight_transpose_flip_batched(src_base, dst_base, table, n, total):
+    call("zsg_weight_transpose_flip_batched", ptr(src_base), ptr(dst_base), ptr(table), n, total, stream())
 
 
 def split_act(x, lo, rows, c, scale=None, shift=None, relu=False, z=None):
