@@ -146,6 +146,12 @@ int zsg_gather_rows(const float* src, const zsg_row_t* rows, float* dst, int64_t
 int zsg_bn_stats(const float* x, double* sums, int64_t rows, int c, zsg_stream_t stream);
 /* the same sums from the per-row-group partials a conv wrote (zsg_conv_params.stats): parts = ceil(m/128)*4. */
 int zsg_bn_stats_partials(const float* partials, int64_t parts, int c, double* sums, zsg_stream_t stream);
+/* zsg_bn_stats_partials + zsg_bn_finalize in one launch: the last block of a channel group to finish (ticket counter)
+ * finalizes it.  sums: 2c doubles, zeroed by the caller; tickets: 64 ints, zero before the first use, left zero. */
+int zsg_bn_finalize_partials(const float* partials, int64_t parts, int64_t rows, int c, const float* gamma,
+                             const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                             float* mean, float* invstd, float* scale, float* shift, double* sums, int* tickets,
+                             zsg_stream_t stream);
 /* mean/invstd/scale/shift from the sums; updates running stats (momentum, unbiased var). */
 int zsg_bn_finalize(const double* sums, int64_t rows, int c, const float* gamma, const float* beta, float eps,
                     float momentum, float* running_mean, float* running_var, float* mean, float* invstd,

@@ -43,14 +43,14 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     # 53 trunk convs + 8 FPN + 6 head + 1 LSTM projection
     assert fwd["zsg_conv_fwd"] == 53 + 8 + 6 + 1
     # BatchNorm statistics come out of the conv epilogues (per-row-group partials), not from a pass over the activations
-    assert fwd["zsg_bn_stats"] == 0 and fwd["zsg_bn_stats_partials"] == 53
-    assert fwd["zsg_bn_finalize"] == 53 and fwd["zsg_bn_apply"] == 16
+    assert fwd["zsg_bn_stats"] == 0 and fwd["zsg_bn_finalize_partials"] == 53
+    assert fwd["zsg_bn_finalize"] == 0 and fwd["zsg_bn_apply"] == 16
     assert fwd["zsg_split_tf32"] == 2 and fwd["zsg_pad_channels"] == 2
     assert fwd["zsg_lstm_fwd_dir"] == 1 and fwd["zsg_lstm_rev_step"] == 1 and fwd["zsg_fuse_lang_grid"] == 1
     del calls[:]
     eng.forward(training=False)
     ev = collections.Counter(calls)
-    assert ev["zsg_bn_stats_partials"] == 0 and ev["zsg_bn_eval_affine"] == 53
+    assert ev["zsg_bn_finalize_partials"] == 0 and ev["zsg_bn_eval_affine"] == 53
     del calls[:]
     seen = []
     eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5), on_bucket=lambda lo, hi: seen.append((lo, hi)))

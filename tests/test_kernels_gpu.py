@@ -830,7 +830,25 @@ def test_conv_epilogue_batchnorm_statistics(zsg, case):
     pow2 = (cout // 4) & (cout // 4 - 1) == 0                  # zsg_bn_stats wants C/4 to be a power of two
     if pow2:
         ops.bn_stats(y, direct, M, cout)
+    # fused reduce + finalize (ticket counter) against the two-launch path, twice to check the counter resets
+    gamma, beta = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+    tickets = torch.zeros(64, dtype=torch.int32, device="cuda")
+    outs = []
+    for _ in range(2):
+        s2_ = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+        rm, rv = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+        o = [torch.empty(cout, device="cuda") for _ in range(4)]
+        ops.bn_finalize_partials(part, parts, M, cout, gamma, beta, 1e-5, 0.1, rm, rv, *o, s2_, tickets)
+        outs.append(o + [rm, rv])
+    s3_ = sums.clone()
+    rm0, rv0 = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    o0 = [torch.empty(cout, device="cuda") for _ in range(4)]
+    ops.bn_finalize(s3_, M, cout, gamma, beta, 1e-5, 0.1, rm0, rv0, *o0)
     torch.cuda.synchronize()
+    assert int(tickets.abs().sum()) == 0
+    for o in outs:
+        for a, b in zip(o, o0 + [rm0, rv0]):
+            np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-6)
     assert not torch.isnan(part).any()
     assert rel_err(y, nhwc(ref)) < 2e-5
     # sums of ~M terms of either sign: absolute tolerance = fp32 rounding of the 32-row partials (values are O(1))

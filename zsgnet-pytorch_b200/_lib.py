@@ -55,6 +55,7 @@ SIGNATURES = {
     "zsg_gather_rows": [_P, _P, _P, _L, _I, _I, _P],
     "zsg_bn_stats": [_P, _P, _L, _I, _P],
     "zsg_bn_stats_partials": [_P, _L, _I, _P, _P],
+    "zsg_bn_finalize_partials": [_P, _L, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "zsg_bn_finalize": [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "zsg_bn_eval_affine": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
     "zsg_bn_apply": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],

@@ -269,8 +269,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 // sums of bn_finalize.  Block = 8 part-lanes x 32 channels; grid.y strides over the parts; one double atomic per
 // (block, channel, moment), like channel_reduce_kernel.
 __global__ void __launch_bounds__(256) bn_partials_kernel(const float* __restrict__ partials, int64_t parts, int C,
-                                                          double* __restrict__ sums) {
+                                                          double* __restrict__ sums, int64_t rows,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, float momentum, float* running_mean,
+                                                          float* running_var, float* mean, float* invstd, float* scale,
+                                                          float* shift, int* __restrict__ tickets) {
   __shared__ double sh[2][8][32];
+  __shared__ int last;
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double a = 0.0, b = 0.0;
@@ -288,6 +293,32 @@ __global__ void __launch_bounds__(256) bn_partials_kernel(const float* __restric
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sh[pl][i][cl];
     atomicAdd(sums + pl * C + c, t);
+  }
+  if (!tickets) return;
+  // fused finalize: the last block of this channel group to arrive (ticket counter, as in the threadfence-reduction
+  // pattern) turns the completed sums into mean / invstd / scale / shift and the running statistics.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&tickets[blockIdx.x], 1) == (int)gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0;           // ready for the next BatchNorm on this stream
+  if (threadIdx.x < 32 && c < C) {
+    const double n = (double)rows;
+    const double m = __ldcg(sums + c) / n;
+    double var = __ldcg(sums + C + c) / n - m * m;
+    if (var < 0.0) var = 0.0;
+    const double is = 1.0 / sqrt(var + (double)eps);
+    mean[c] = (float)m;
+    invstd[c] = (float)is;
+    const float sc = gamma[c] * (float)is;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)m * sc;
+    if (running_mean) {
+      const double unb = rows > 1 ? var * n / (n - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
   }
 }
 
@@ -790,8 +821,27 @@ extern "C" int zsg_bn_stats_partials(const float* partials, int64_t parts, int c
   int64_t gy = (parts + 63) / 64;                         // >= 8 parts per part-lane
   const int64_t cap = (int64_t)num_sms() * 4 / gx + 1;
   if (gy > cap) gy = cap;
-  bn_partials_kernel<<<dim3(gx, (unsigned)gy), 256, 0, as_stream(stream)>>>(partials, parts, c, sums);
+  bn_partials_kernel<<<dim3(gx, (unsigned)gy), 256, 0, as_stream(stream)>>>(partials, parts, c, sums, 0, nullptr, nullptr, 0.f,
+                                                                            0.f, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                            nullptr, nullptr);
   return check_launch("zsg_bn_stats_partials");
+}
+
+extern "C" int zsg_bn_finalize_partials(const float* partials, int64_t parts, int64_t rows, int c, const float* gamma,
+                                        const float* beta, float eps, float momentum, float* running_mean,
+                                        float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                                        double* sums, int* tickets, zsg_stream_t stream) {
+  ZSG_REQUIRE(partials && sums && tickets && gamma && beta && mean && invstd && scale && shift && parts > 0 && rows > 0 &&
+                  c > 0 && c <= 32 * 64,
+              "zsg_bn_finalize_partials: bad arguments (c <= 2048, tickets = 64 zeroed ints)");
+  const int gx = (c + 31) / 32;
+  int64_t gy = (parts + 63) / 64;
+  const int64_t cap = (int64_t)num_sms() * 4 / gx + 1;
+  if (gy > cap) gy = cap;
+  bn_partials_kernel<<<dim3(gx, (unsigned)gy), 256, 0, as_stream(stream)>>>(partials, parts, c, sums, rows, gamma, beta, eps,
+                                                                            momentum, running_mean, running_var, mean, invstd,
+                                                                            scale, shift, tickets);
+  return check_launch("zsg_bn_finalize_partials");
 }
 
 extern "C" int zsg_bn_finalize(const double* sums, int64_t rows, int c, const float* gamma, const float* beta,

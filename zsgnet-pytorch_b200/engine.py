@@ -106,6 +106,7 @@ class Engine:
         self.pool, self.pool_hi, self.pool_lo = self.buf(self.pool_n), self.buf(self.pool_n), self.buf(self.pool_n)
         self._pool_used, self._pool_f_end = 0, None
         self._wtf = []
+        self._bn_tickets = torch.zeros(64, dtype=torch.int32, device=device)
         self.prep_fwd = []
         self._build()
 
@@ -189,10 +190,11 @@ class Engine:
         part = L.get("stats") if L is not None else None
 
         def train():
-            if part is not None:
-                ops.bn_stats_partials(part[0], part[1], bn.c, bn.sums)
-            else:
-                ops.bn_stats(x, bn.sums, bn.rows, bn.c)
+            if part is not None:                              # reduce the epilogue's partials and finalize, one launch
+                ops.bn_finalize_partials(part[0], part[1], bn.rows, bn.c, bn.gamma, bn.beta, BN_EPS, BN_MOM, bn.rm, bn.rv,
+                                         bn.mean, bn.invstd, bn.scale, bn.shift, bn.sums, self._bn_tickets)
+                return
+            ops.bn_stats(x, bn.sums, bn.rows, bn.c)
             ops.bn_finalize(bn.sums, bn.rows, bn.c, bn.gamma, bn.beta, BN_EPS, BN_MOM, bn.rm, bn.rv, bn.mean,
                             bn.invstd, bn.scale, bn.shift)
 

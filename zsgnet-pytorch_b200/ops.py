@@ -134,6 +134,12 @@ def bn_stats_partials(partials, parts, c, sums):
     call("zsg_bn_stats_partials", ptr(partials), parts, c, ptr(sums), stream())
 
 
+def bn_finalize_partials(partials, parts, rows, c, gamma, beta, eps, momentum, rm, rv, mean, invstd, scale, shift, sums,
+                         tickets):
+    call("zsg_bn_finalize_partials", ptr(partials), parts, rows, c, ptr(gamma), ptr(beta), eps, momentum, ptr(rm), ptr(rv),
+         ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(sums), ptr(tickets), stream())
+
+
 def bn_finalize(sums, rows, c, gamma, beta, eps, momentum, rm, rv, mean, invstd, scale, shift):
     call("zsg_bn_finalize", ptr(sums), rows, c, ptr(gamma), ptr(beta), eps, momentum, ptr(rm), ptr(rv), ptr(mean),
          ptr(invstd), ptr(scale), ptr(shift), stream())
