@@ -86,3 +86,47 @@ def test_even_pixel_scatter_for_1x1_stride2():
     t = geometry.dgrad_rows_1x1_s2(B, H, W, cin, Ho, Wo, cout)
     emulate(dy, wt, t, cout, cin, 1, 1, dx, accumulate=True)
     assert np.allclose(dx, g + want, atol=1e-12)
+
+
+def test_ssd_vgg_layer_geometry_matches_torch_modules():
+    """spec.vgg_layers() / VGG_EXTRAS against torch's own shape arithmetic for ssd_vgg.py:111-154 (300x300 input):
+    pool ceil mode, the dilated conv6, the unpadded 3x3 extras; the six sources must be 38, 19, 10, 5, 3, 1."""
+    import torch
+    import torch.nn as nn
+    from zsg_b200 import spec
+    x = torch.zeros(1, 3, 300, 300)
+    sizes = []
+    for i, L in enumerate(spec.vgg_layers()):
+        if L[0] == "conv":
+            x = nn.Conv2d(L[1], L[2], L[3], padding=L[4], dilation=L[5])(x)
+        elif L[0] == "pool":
+            x = nn.MaxPool2d(L[1], L[2], L[3], ceil_mode=L[4])(x)
+        if i == 22:
+            sizes.append(x.shape[-1])
+    sizes.append(x.shape[-1])
+    assert x.shape[1] == 1024
+    for i, (ci, co, k, s, p) in enumerate(spec.VGG_EXTRAS):
+        assert x.shape[1] == ci
+        x = nn.Conv2d(ci, co, k, stride=s, padding=p)(x)
+        if i % 2 == 1:
+            sizes.append(x.shape[-1])
+    assert tuple(sizes) == spec.LEVEL_SIZES
+    names = [n for n, _, _ in spec.trainable_specs("ssd_vgg")]
+    assert len(names) == len(set(names)) and names[0] == "backbone.encoder.vgg.0.weight"
+    assert not set(names) & {n for n, _, _ in spec.unused_specs("ssd_vgg")}
+
+
+def test_dilated_dgrad_rows_mirror_forward_taps():
+    """Data-gradient table of a dilated conv: flipped tap r' of input pixel y reads dY at y + pad - (R-1-r')*dil, i.e. the
+    output pixels whose forward tap (R-1-r') touched y."""
+    import numpy as np
+    from zsg_b200 import geometry
+    B, H, C, R, pad, dil = 1, 19, 8, 3, 6, 6
+    t = geometry.dgrad_rows(B, H, H, C, H, H, C, R, 1, pad, dil=dil).numpy().view(geometry.ROW_DTYPE).reshape(-1)
+    y, x = 7, 11
+    e = t[y * H + x]
+    for r in range(R):
+        p = e["y0"] + r * dil                       # dY row read by flipped tap r
+        fwd_tap = R - 1 - r
+        assert p * 1 - pad + fwd_tap * dil == y     # forward: output p reads input p - pad + tap*dil
+    assert e["x0"] == x + pad - (R - 1) * dil and e["out"] == (y * H + x) * C

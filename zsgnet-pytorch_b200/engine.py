@@ -790,6 +790,7 @@ class Engine:
     def forward(self, training=True):
         if training:
             self._f64_pool[:self._f64_used].zero_()
+            self._bn_tickets.zero_()                      # self-resetting, but a step aborted mid-kernel must not poison the next
         for fn in self.prep_fwd:
             fn()
         ops.split_tf32(self.store.param_arena, self.arena_hi, self.arena_lo, self.store.total)
