@@ -1,10 +1,11 @@
 // Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, accumulators in TMEM).
 //
-// One kernel family serves every dense contraction of the hot path: ResNet-50 / FPN / head
+// One kernel family serves every dense contraction of the hot path: ResNet-50 / FPN / SSD-VGG / head
 // convolutions forward, their data gradients (the same kernel over flipped-transposed weights),
 // the LSTM input projection (a 1x1 conv over B*T rows) and, in the wgrad kernel, every weight
-// gradient.  Geometry comes from a 16-byte row table (zsg_row_t), so strides, padding, the
-// stride-2 data gradient and the six-level shared head are data, not code.
+// gradient.  Geometry comes from a 16-byte row table (zsg_row_t) plus a tap spacing, so strides, padding,
+// dilation, the stride-2 data gradient and the six-level shared head are data, not code.  The epilogue can
+// emit the BatchNorm statistics of its output (zsg_conv_params.stats) so that y is not read again for them.
 //
 // Arithmetic: fp32 in HBM; D += Ah*Bh + Ah*Bl + Al*Bh is issued as three kind::tf32 MMAs (3xTF32): fp32-accurate
 // products, fp32 accumulation in TMEM, promoted to registers every few K blocks.  This is what lets the fp32
