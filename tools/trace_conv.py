@@ -1,5 +1,6 @@
 """Pipeline timeline of conv_tc_kernel (diagnostics): CTA 0 stamps clock64 at the hand-overs of its first K blocks.
 events: 0 producer before empty-wait, 1 after empty-wait, 2 after the STS loop, 3 after arrive(full);
+        4 producer tile top, 5 first group barrier passed, 6 row table in smem (cp.async kernel only);
         8 issuer before full-wait, 9 after full-wait, 10 after token-wait, 11 after issue+commit."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -41,6 +42,13 @@ def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False, impl=0)
         d = (r[11] - prev) if prev is not None else 0
         prev = r[11]
         print(f"{g:4d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | {r[8]:7d} {r[9]:7d} {r[10]:7d} {r[11]:7d} | {d:5d}   emptywait {r[1]-r[0]:5d} sts {r[2]-r[1]:5d}  fullwait {r[9]-r[8]:5d} tok {r[10]-r[9]:4d} issue {r[11]-r[10]:4d}  full->arrive lag {r[9]-r[3]:5d}")
+    if t[40:64, 4].any():
+        print("producer per-tile prologue (cp.async kernel): gk | tile top | first barrier, row table in smem, tap offsets | "
+              "previous arrive of this group -> this top")
+        for g in range(42, min(nblk, 64)):
+            r = t[g]
+            if r[4] == 0: continue
+            print(f"{g:4d} | {r[4]:8d} | bar1 {r[5]-r[4]:6d}  rows {r[6]-r[5]:6d}  retap {r[0]-r[6]:6d} | {r[4]-t[g-2][3]:6d}")
     print("drain warp 8: tile-first-gk | before acc_full wait, after TMEM drain, after epilogue stores | drain  epilogue  tile period")
     prevd = None
     for g in range(40, min(nblk, 76)):

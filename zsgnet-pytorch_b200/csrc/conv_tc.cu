@@ -972,13 +972,16 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, gkb0 += nkb) {
       const int n0 = (tile % tiles_n) * BN;
       const int m0 = (tile / tiles_n) * TM;
+      if (t == 0) trace(gkb0 + ((group - gkb0) & 1), 4);  // tile top (stamps exist in the build.py --trace build only)
       {
         int4 e = make_int4(0, 0, 0, 0);                   // hin = win = 0 => every tap out of bounds
         if (m0 + t < p.m) e = __ldg(reinterpret_cast<const int4*>(p.rows) + m0 + t);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");   // previous tile's reads are done
+        if (t == 0) trace(gkb0 + ((group - gkb0) & 1), 5);  // first group barrier passed
         rows_g[t] = e;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
       }
+      if (t == 0) trace(gkb0 + ((group - gkb0) & 1), 6);  // row table of the tile is in shared memory
       const int kb_first = (group - gkb0) & 1;            // K blocks with (gkb0 + kb) % NGROUP == group
       int c = chunk * 4 + kb_first * KB, tap = 0, tr = 0, ts = 0;
       while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
