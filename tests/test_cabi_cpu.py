@@ -48,3 +48,24 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libzsg_b200.so")
     with pytest.raises(_lib.ZsgError):
         _lib.load()
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of the parameter blocks as a C compiler sees include/zsg_b200.h (gcc, plain C: the header must
+    stay C-clean) against the ctypes mirrors in _lib.py and the numpy table layouts."""
+    import subprocess
+    from zsg_b200 import _lib, geometry, ops
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "zsg_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(zsg_row_t), sizeof(zsg_conv_params), '
+                   'offsetof(zsg_conv_params, x_lo), offsetof(zsg_conv_params, dil), offsetof(zsg_conv_params, stats), '
+                   'sizeof(zsg_wgrad_params), offsetof(zsg_wgrad_params, dy_pitch), offsetof(zsg_wgrad_params, dil), '
+                   'sizeof(zsg_wtf_desc)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    C, W = _lib.ConvParams, _lib.WgradParams
+    want = [ctypes.sizeof(_lib.RowT), ctypes.sizeof(C), C.x_lo.offset, C.dil.offset, C.stats.offset, ctypes.sizeof(W),
+            W.dy_pitch.offset, W.dil.offset, ops.WTF_DESC.itemsize]
+    assert got == want, (got, want)
+    assert geometry.ROW_DTYPE.itemsize == got[0]
