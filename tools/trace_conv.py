@@ -8,6 +8,7 @@ import numpy as np
 import torch
 import zsg_b200
 from zsg_b200 import ops, geometry, _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libzsg_b200_trace.so")   # python zsgnet-pytorch_b200/build.py --trace
 
 def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False, impl=0):
     x = torch.randn(B, H, H, cin, device="cuda")

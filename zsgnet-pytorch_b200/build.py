@@ -1,5 +1,7 @@
 """In-tree build of libzsg_b200.so (nvcc, sm_100a only).  No JIT cache: the .so ships with the repo
-snapshot to the GPU box.  Usage: python zsgnet-pytorch_b200/build.py [--force]"""
+snapshot to the GPU box.  Usage: python zsgnet-pytorch_b200/build.py [--force] [-v] [--trace]
+--trace builds the diagnostics variant (-DZSG_TRACE: clock stamps in the conv kernels) as libzsg_b200_trace.so and
+leaves the product library alone; tools/trace_conv.py loads it."""
 import os
 import subprocess
 import sys
@@ -7,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzsg_b200.so")
+TRACE_LIB = os.path.join(HERE, "libzsg_b200_trace.so")
 SOURCES = ["api.cu", "match_loss.cu", "elementwise.cu", "lstm.cu", "conv_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
@@ -28,7 +31,7 @@ def build(force=False, verbose=False, trace=False):
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".trace.o" if trace else ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -42,8 +45,9 @@ def build(force=False, verbose=False, trace=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    out = TRACE_LIB if trace else LIB
+    subprocess.check_call([nvcc, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
 
 
 if __name__ == "__main__":
