@@ -18,18 +18,18 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_q):
+def _worker(rank, world, port, out_q, model="retina"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import zsg_b200  # noqa: F401
     from zsg_b200 import ddp, engine, spec
-    store = engine.ParamStore(torch.device("cpu"))
+    store = engine.ParamStore(torch.device("cpu"), model)
     g = torch.Generator().manual_seed(100 + rank)
     store.grad_arena.copy_(torch.randn(store.used, generator=g))
     mine = store.grad_arena.clone()
     red = ddp.GradReducer(store, min_bucket_elems=2 << 20)
     # replay the engine's bucket marks: stage ranges in arena order
-    names = [n for n, _, _ in reversed(spec.trainable_specs())]
+    names = [n for n, _, _ in reversed(spec.trainable_specs(model))]
     marks, lo = [], 0
     for i, n in enumerate(names):
         hi = store.offsets[n] + engine._align(store.numel(n))
@@ -48,11 +48,12 @@ def _worker(rank, world, port, out_q):
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_two_ranks_gloo():
+@pytest.mark.parametrize("model", ["retina", "ssd_vgg"])
+def test_bucketed_allreduce_two_ranks_gloo(model):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, model)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in procs)
