@@ -82,6 +82,10 @@ typedef struct {
                               32-row group of the output, the column sums and the column sums of squares.
                               zsg_bn_stats_partials turns them into the sums zsg_bn_finalize reads, without
                               re-reading y (replaces zsg_bn_stats for the 53 convs that feed a BatchNorm)             */
+  const uint16_t* x_bf16;  /* optional pair (both or none; cin % 8 == 0; no in_scale / in_relu): bfloat16 images of the input   */
+  const uint16_t* w_bf16;  /* (indexed like x, zsg_cast_bf16) and of the weights [cout][r][s][cin].  Selects the bf16 operand  */
+                           /* path of BASELINE configs 3-5 ("bf16 tensor-core convs"): one kind::f16 MMA per product, fp32      */
+                           /* accumulation, fp32 epilogue and output; x / w / x_lo / w_lo are not read then (may be NULL)      */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
@@ -107,6 +111,8 @@ typedef struct {
   int32_t dy_pitch;        /* > 0: rows[i].out == i * dy_pitch for every row (dy is a plain [m, dy_pitch] matrix, true for
                               every forward table of the path): dy / dy_lo are then fetched by TMA.  0: unknown        */
   int32_t dil;             /* tap spacing as in zsg_conv_params (0 means 1)                                             */
+  const uint16_t* x_bf16;  /* optional pair (both or none; cin % 8 == 0, dy_pitch > 0 and % 8 == 0): bfloat16 images of x and */
+  const uint16_t* dy_bf16; /* dy (zsg_cast_bf16); bf16 operand path as in zsg_conv_params, dw stays fp32 (atomic split-K)      */
 } zsg_wgrad_params;
 int zsg_conv_wgrad(const zsg_wgrad_params* p, zsg_stream_t stream);
 
@@ -127,6 +133,10 @@ int zsg_weight_transpose_flip_batched(const float* src_base, float* dst_base, co
  * Replaces the on-the-fly split inside the conv kernels for every conv of the path (mdl.py / fpn_resnet.py). */
 int zsg_split_act(const float* x, const float* scale, const float* shift, int relu, float* z, float* lo, int64_t rows,
                   int c, zsg_stream_t stream);
+/* bf16 operand image for the bf16 GEMM path (configs 3-5): out = bf16_rn( relu?(x * scale[c] + shift[c]) ), x [rows, c],
+ * c % 4 == 0; scale / shift may be NULL.  With rows = n / 4, c = 4 it is the plain cast of a flat array (weights). */
+int zsg_cast_bf16(const float* x, const float* scale, const float* shift, int relu, uint16_t* out, int64_t rows, int c,
+                  zsg_stream_t stream);
 /* hi[i] = w[i] with the 13 low mantissa bits cleared (exactly representable in TF32), lo[i] = w[i] - hi[i]. */
 int zsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, zsg_stream_t stream);
 /* row-wise channel padding copy: dst[n][0:cdst] = src[n][0:csrc] (zero fill / truncate). */
@@ -163,6 +173,9 @@ int zsg_bn_eval_affine(const float* running_mean, const float* running_var, cons
  * y_lo (optional): TF32 remainder image of y for the GEMMs that read it (see zsg_split_act). */
 int zsg_bn_apply(const float* x, const float* scale, const float* shift, const float* r, const float* rscale,
                  const float* rshift, int relu, float* y, float* y_lo, int64_t rows, int c, zsg_stream_t stream);
+/* zsg_bn_apply that also writes the bf16 image of y (y_bf16, required) instead of a TF32 remainder image. */
+int zsg_bn_apply_bf16(const float* x, const float* scale, const float* shift, const float* r, const float* rscale,
+                      const float* rshift, int relu, float* y, uint16_t* y_bf16, int64_t rows, int c, zsg_stream_t stream);
 /* backward reduce: dz = dy * mask ; sums[0:c] = sum dz, sums[c:2c] = sum dz*xhat.
  * mask_mode 0: none; 1: relu mask from (x*scale+shift) > 0; 2: relu mask from act_out > 0 (dz is also
  * written to dz_out when non-null, for the shortcut path). */
@@ -175,6 +188,12 @@ int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const f
                      const float* scale, const float* shift, const float* act_out, int mask_mode,
                      const double* sums, float* dx, float* dx_lo, float* dgamma, float* dbeta, int64_t rows, int c,
                      zsg_stream_t stream);
+
+/* zsg_bn_bwd_apply that writes the bf16 image of dx (dx_bf16, required) instead of a TF32 remainder image. */
+int zsg_bn_bwd_apply_bf16(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                          const float* scale, const float* shift, const float* act_out, int mask_mode,
+                          const double* sums, float* dx, uint16_t* dx_bf16, float* dgamma, float* dbeta, int64_t rows,
+                          int c, zsg_stream_t stream);
 
 /* ------------------------------ pooling / resampling glue -------------------------------- */
 /* stem: y = maxpool3x3/2,p1( relu(x*scale+shift) )  (mdl.py:150-152).  argmax (optional, same shape as y, one

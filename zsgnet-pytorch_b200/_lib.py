@@ -25,14 +25,16 @@ class ConvParams(C.Structure):
                 ("m", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
                 ("in_div", C.c_int32), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
-                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32), ("stats", C.c_void_p)]
+                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32), ("stats", C.c_void_p),
+                ("x_bf16", C.c_void_p), ("w_bf16", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p), ("rows", C.c_void_p),
                 ("m", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
                 ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32), ("split_k", C.c_int32),
-                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int32), ("dil", C.c_int32)]
+                ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int32), ("dil", C.c_int32),
+                ("x_bf16", C.c_void_p), ("dy_bf16", C.c_void_p)]
 
 
 _P, _I, _L, _F, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
@@ -50,6 +52,9 @@ SIGNATURES = {
     "zsg_pad_channels": [_P, _P, _L, _I, _I, _P],
     "zsg_split_tf32": [_P, _P, _P, _L, _P],
     "zsg_split_act": [_P, _P, _P, _I, _P, _P, _L, _I, _P],
+    "zsg_cast_bf16": [_P, _P, _P, _I, _P, _L, _I, _P],
+    "zsg_bn_apply_bf16": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
+    "zsg_bn_bwd_apply_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P],
     "zsg_nchw_to_nhwc4": [_P, _P, _I, _I, _I, _P],
     "zsg_colsum": [_P, _P, _L, _I, _I, _I, _P],
     "zsg_gather_rows": [_P, _P, _P, _L, _I, _I, _P],

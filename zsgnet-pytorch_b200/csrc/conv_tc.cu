@@ -181,13 +181,21 @@ constexpr int DRAIN_WARP0 = 8;
 constexpr int MMA_WARP = 16;           // issuer warps: 16 and 17 (TMEM is allocated / freed by 16)
 constexpr int NTHREADS2 = 18 * 32;
 
-template <int BN>
+// BF16 = the bf16 operand path (BASELINE configs 3-5): ONE image per operand (the bf16 copy), 64 elements per
+// 128-byte swizzle row, one kind::f16 MMA per product instead of three kind::tf32 ones.  A stage is then half the
+// bytes for twice the K extent, so the ring is deeper.
+template <int BN, bool BF16 = false>
 struct Smem {
+  static constexpr int BN_ = BN;
+  static constexpr bool BF16_ = BF16;
+  static constexpr int NIMG = BF16 ? 1 : 2;                 // operand images per tile (bf16 copy | TF32 hi + lo)
+  static constexpr int KBE = BF16 ? 64 : 32;                // K elements per stage (one 128-byte swizzle row)
+  static constexpr int ES = BF16 ? 2 : 4;                   // operand element size in bytes
   static constexpr int B_TILE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  static constexpr int STAGE_BYTES = NIMG * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int STAGES = BF16 ? 6 : (BN >= 128 ? 3 : 4);
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int ROWS_OFF = TILES_BYTES;              // TM row entries (fwd) / 2 groups x 2 x 32 (wgrad)
+  static constexpr int ROWS_OFF = TILES_BYTES;              // TM row entries (fwd) / 2 groups x 2 x 32|64 (wgrad)
   static constexpr int BAR_OFF = ROWS_OFF + NGROUP * TM * 16;
   static constexpr int EPI_OFF = BAR_OFF + 256;             // epilogue staging: 8 warps x 32 rows x 20 floats
   static constexpr int EPI_WARP_BYTES = 32 * 20 * 4;
@@ -195,14 +203,16 @@ struct Smem {
   static constexpr int TMEM_COLS = 4 * BN;                  // (chunk parity) x (issuer) accumulators
 };
 
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_SLOT_OFF = 192;     // byte offset of the TMEM base-address word inside the barrier block
 struct PipeBars {                      // mbarrier addresses are computed, never indexed from memory
   uint32_t bar0;
   __device__ __forceinline__ uint32_t full(int s) const { return bar0 + 8 * s; }
-  __device__ __forceinline__ uint32_t empty(int s) const { return bar0 + 32 + 8 * s; }
-  __device__ __forceinline__ uint32_t acc_full(int a) const { return bar0 + 64 + 8 * a; }
-  __device__ __forceinline__ uint32_t acc_empty(int a) const { return bar0 + 96 + 8 * a; }
-  __device__ __forceinline__ uint32_t tmem_slot() const { return bar0 + 128; }
-  __device__ __forceinline__ uint32_t token(uint32_t w) const { return bar0 + 136 + 8 * w; }
+  __device__ __forceinline__ uint32_t empty(int s) const { return bar0 + 64 + 8 * s; }
+  __device__ __forceinline__ uint32_t acc_full(int a) const { return bar0 + 128 + 8 * a; }
+  __device__ __forceinline__ uint32_t acc_empty(int a) const { return bar0 + 160 + 8 * a; }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return bar0 + TMEM_SLOT_OFF; }
+  __device__ __forceinline__ uint32_t token(uint32_t w) const { return bar0 + 200 + 8 * w; }
 };
 
 // Diagnostics (tools/trace_conv.py): when a trace buffer is registered, CTA 0 records clock timestamps of the
@@ -215,9 +225,10 @@ __device__ __forceinline__ void trace(int gk, int ev) {
 #endif
 }
 
-template <int BN>
+template <int BN, bool BF16 = false>
 __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int lane, int full_count = NPROD) {
-  using S = Smem<BN>;
+  using S = Smem<BN, BF16>;
+  static_assert(S::STAGES <= MAX_STAGES, "barrier block holds MAX_STAGES full/empty pairs");
   PipeBars pb;
   pb.bar0 = smem_u32(sm + S::BAR_OFF);
   if (warp == MMA_WARP) {
@@ -307,24 +318,66 @@ __device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_hi_lo, 
       : "memory");
 }
 
-template <int BN>
+// kind::f16 with bf16 operands, fp32 accumulate, M = 128 (instruction-descriptor fields as in kind::tf32: bits 4-5 D format
+// 1 = f32, 7-9 / 10-12 A / B format 1 = bf16, 15 / 16 A / B MN-major, 17-22 N >> 3, 24-28 M >> 4).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TM >> 4) << 24);
+}
+// bf16 K block = 64 K elements = four MMAs of K = 16.  K-major tiles (forward / data gradient): an MMA consumes 32 bytes
+// of every 128-byte swizzle row, start address += 2 (x 16 B).  MN-major tiles (weight gradient; [channel atom of 64]
+// [pixel][128 B], plain 128-byte swizzle = what TMA SWIZZLE_128B and the cp.async producers write): an MMA consumes 16
+// pixels = 2048 B, start address += 128.
+template <int BN, bool MN_MAJOR>
+__device__ __forceinline__ void issue_kblock_bf16(uint32_t tmem_d, uint32_t a_lo32, uint32_t desc_hi, uint32_t acc_first) {
+  constexpr uint32_t idesc = umma_idesc_bf16(BN, MN_MAJOR);
+  constexpr uint32_t A16 = A_TILE_BYTES >> 4, KSTEP = MN_MAJOR ? 128u : 2u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b32 a0, b0;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b32 a0, %1;\n\t"
+      "add.u32 b0, a0, %5;\n\t"
+      "mov.b64 da, {a0, %2};\n\tmov.b64 db, {b0, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "add.u32 a0, a0, %6;\n\tadd.u32 b0, b0, %6;\n\t"
+      "mov.b64 da, {a0, %2};\n\tmov.b64 db, {b0, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 a0, a0, %6;\n\tadd.u32 b0, b0, %6;\n\t"
+      "mov.b64 da, {a0, %2};\n\tmov.b64 db, {b0, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 a0, a0, %6;\n\tadd.u32 b0, b0, %6;\n\t"
+      "mov.b64 da, {a0, %2};\n\tmov.b64 db, {b0, %2};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(a_lo32), "r"(desc_hi), "r"(acc_first), "n"(idesc), "n"(A16), "n"(KSTEP)
+      : "memory");
+}
+
+template <int BN, bool BF16 = false>
 __device__ __forceinline__ Issuer issuer_init(uint32_t w) {
   Issuer is;
   is.w = w;
-  is.stage = w % Smem<BN>::STAGES;
+  is.stage = w % Smem<BN, BF16>::STAGES;
   is.phase = 0;
   return is;
 }
 
 // Executed by the elected thread of issuer warp `is.w` for the K blocks of one tile (both issuers walk all K blocks
 // to keep the chunk bookkeeping, each acts on its own).  A chunk never spans two tiles.
-template <int BN, bool MN_MAJOR = false>
+template <int BN, bool MN_MAJOR = false, bool BF16 = false>
 __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb, Issuer& is,
                                          bool swap_lbo_sbo = false, int ablate = 0) {
-  using S = Smem<BN>;
-  const uint32_t lbo = MN_MAJOR ? (swap_lbo_sbo ? 32u : 256u) : 1u;
-  const uint32_t sbo = MN_MAJOR ? (swap_lbo_sbo ? 256u : 32u) : 64u;
-  const uint32_t desc_hi = sbo | (1u << 14) | ((MN_MAJOR ? 1u : 2u) << 29);          // bits 32..63 of the descriptor
+  using S = Smem<BN, BF16>;
+  // MN-major strides (x 16 B).  tf32: atoms of 4 pixels x 128 B, 4096 B between channel atoms (SWIZZLE_128B_BASE32B).
+  // bf16: atoms of 8 pixels x 128 B (64 channels) = 1024 B (SBO), 64 pixels x 128 B = 8192 B between channel atoms (LBO),
+  // plain SWIZZLE_128B (layout type 2), as in the canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) uint128 layout.
+  const uint32_t lbo = MN_MAJOR ? (BF16 ? 512u : (swap_lbo_sbo ? 32u : 256u)) : 1u;
+  const uint32_t sbo = MN_MAJOR ? (BF16 ? 64u : (swap_lbo_sbo ? 256u : 32u)) : 64u;
+  const uint32_t desc_hi = sbo | (1u << 14) | (((MN_MAJOR && !BF16) ? 1u : 2u) << 29);   // bits 32..63 of the descriptor
   const uint32_t lo0 = ((smem_u32(sm) >> 4) & 0x3FFFu) | (lbo << 16);                // a_hi tile of stage 0
   uint32_t mine = 0;                                        // my K blocks so far in the current chunk
   for (int kb = 0; kb < nkb; ++kb, ++is.g) {
@@ -338,8 +391,12 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
       if (is.g > 0 && !(ablate & 8)) { mbar_wait(pb.token(is.w), is.tokens & 1u, 4000 + is.g); ++is.tokens; }      // my turn
       trace(is.g, 10);
       tc_fence_after();
-      issue_kblock<BN, MN_MAJOR>(tmem_base + acc * BN, lo0 + is.stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi,
-                                 mine == 0 ? 0u : 1u);
+      if (BF16)
+        issue_kblock_bf16<BN, MN_MAJOR>(tmem_base + acc * BN, lo0 + is.stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi,
+                                        mine == 0 ? 0u : 1u);
+      else
+        issue_kblock<BN, MN_MAJOR>(tmem_base + acc * BN, lo0 + is.stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi,
+                                   mine == 0 ? 0u : 1u);
       if (!(ablate & 8)) {
         tc_fence_before();
         mbar_arrive(pb.token(is.w ^ 1u));                   // the other issuer may go
@@ -413,10 +470,10 @@ __device__ __noinline__ void epilogue_store_ragged(float* y, const float* out_ma
 }
 
 // drain + epilogue warps of the forward / data-gradient kernels
-template <int BN>
+template <int BN, bool BF16 = false>
 __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t* sm, const PipeBars& pb, uint32_t tmem_base,
                                               int warp, int lane, int nkb, int tiles_n, int total_tiles, int ablate = 0) {
-  using S = Smem<BN>;
+  using S = Smem<BN, BF16>;
   // ------------------------------ drain + epilogue ------------------------------
   const int dw = warp - DRAIN_WARP0;
   const int quadrant = dw & 3, half = dw >> 2;
@@ -580,7 +637,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_generic_kernel(const zsg
   const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
 
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane, TMA_W ? NPROD + 1 : NPROD);   // contains __syncthreads
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
 
   if (warp >= MMA_WARP) {
     if (elect_one()) {
@@ -785,7 +842,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
 
   const int ablate = p.impl >= 8 ? p.impl - 8 : 0;     // diagnostics (tools/ablate_conv.py): 1 = no producers, 2 = no TMEM drain, 8 = issuers without token
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane, FULL_COUNT_TMA);   // contains __syncthreads
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
 
   if (warp >= MMA_WARP) {
     if (elect_one()) {
@@ -926,33 +983,38 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_kernel(const zsg_conv_pa
 // before this existed: the register-path producers (gather, affine, split, 16 STS.128 per thread and K block) took
 // 1000-2700 cycles per K block and group against a 768-cycle MMA floor.
 // ============================================================================================
-__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src, uint32_t src_bytes) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-template <int BN>
+// BF16 (p.x_bf16 / p.w_bf16): the same kernel over the bf16 images -- one image per operand, 64 channels per K block,
+// 8 cp.async per producer thread and K block, one TMA weight tile, four kind::f16 MMAs (issue_kblock_bf16).
+template <int BN, bool BF16>
 __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_conv_params p,
                                                                      const __grid_constant__ CUtensorMap tm_hi,
                                                                      const __grid_constant__ CUtensorMap tm_lo) {
-  using S = Smem<BN>;
+  using S = Smem<BN, BF16>;
+  constexpr int KBE = S::KBE;              // K elements per stage
+  constexpr int CE = 16 / S::ES;           // elements per 16-byte chunk
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.r * p.s * p.cin;
-  const int nkb = (K + KB - 1) / KB;
+  const int nkb = (K + KBE - 1) / KBE;
   const int tiles_n = (p.cout + BN - 1) / BN;
   const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
   const int ablate = p.impl >= 8 ? p.impl - 8 : 0;
-  PipeBars pb = setup_pipeline<BN>(sm, warp, lane, NPROD + 1);   // 128 cp.async completions + the expect_tx arrive
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+  PipeBars pb = setup_pipeline<BN, BF16>(sm, warp, lane, NPROD + 1);   // 128 cp.async completions + the expect_tx arrive
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
 
   if (warp >= MMA_WARP) {
     if (elect_one()) {
-      Issuer is = issuer_init<BN>(warp - MMA_WARP);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) mma_loop<BN>(sm, pb, tmem_base, nkb, is, false, ablate);
+      Issuer is = issuer_init<BN, BF16>(warp - MMA_WARP);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+        mma_loop<BN, false, BF16>(sm, pb, tmem_base, nkb, is, false, ablate);
     }
     __syncwarp();
   } else if (warp < DRAIN_WARP0) {
@@ -968,6 +1030,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
     const int cin = p.cin;
     int4* rows_g = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * TM;      // this group's copy of the row table
     const uint32_t tiles0 = smem_u32(sm);
+    const uint8_t* xbase = BF16 ? reinterpret_cast<const uint8_t*>(p.x_bf16) : reinterpret_cast<const uint8_t*>(p.x);
+    const uint8_t* xlbase = reinterpret_cast<const uint8_t*>(p.x_lo);
     int gkb0 = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, gkb0 += nkb) {
       const int n0 = (tile % tiles_n) * BN;
@@ -983,7 +1047,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
       }
       if (t == 0) trace(gkb0 + ((group - gkb0) & 1), 6);  // row table of the tile is in shared memory
       const int kb_first = (group - gkb0) & 1;            // K blocks with (gkb0 + kb) % NGROUP == group
-      int c = chunk * 4 + kb_first * KB, tap = 0, tr = 0, ts = 0;
+      int c = chunk * CE + kb_first * KBE, tap = 0, tr = 0, ts = 0;
       while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
       int cached_tap = -1;
       int off[8];                                         // element offset of the tap's pixel, -1 = padding
@@ -1004,43 +1068,43 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
             off[it] = ok ? e.x + (yy * win + xx) * cin : -1;
           }
         }
-        const float* xh = p.x + c;
-        const float* xl = p.x_lo + c;
+        const uint8_t* xh = xbase + (int64_t)c * S::ES;
+        const uint8_t* xl = BF16 ? xh : xlbase + (int64_t)c * S::ES;
         asm("" : "+l"(xh));
         asm("" : "+l"(xl));
         if (t == 0) trace(gk, 0);
         mbar_wait(pb.empty(s), ((gk / S::STAGES) & 1) ^ 1, 3000 + gk);
         if (t == 0) trace(gk, 1);
         const uint32_t a_hi = tiles0 + s * S::STAGE_BYTES;
-        if ((t >> 5) == 0) {                               // weights: two TMA tiles
+        if ((t >> 5) == 0) {                               // weights: one TMA tile per image
           if (elect_one()) {
-            mbar_arrive_expect_tx(pb.full(s), 2 * S::B_TILE_BYTES);
-            tma_load_2d(a_hi + 2 * A_TILE_BYTES, &tm_hi, kb * KB, n0, pb.full(s));
-            tma_load_2d(a_hi + 2 * A_TILE_BYTES + S::B_TILE_BYTES, &tm_lo, kb * KB, n0, pb.full(s));
+            mbar_arrive_expect_tx(pb.full(s), S::NIMG * S::B_TILE_BYTES);
+            tma_load_2d(a_hi + S::NIMG * A_TILE_BYTES, &tm_hi, kb * KBE, n0, pb.full(s));
+            if (!BF16) tma_load_2d(a_hi + 2 * A_TILE_BYTES + S::B_TILE_BYTES, &tm_lo, kb * KBE, n0, pb.full(s));
           }
           __syncwarp();
         }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const bool ok = off[it] >= 0;
-          const int o = ok ? off[it] : 0;
+          const int64_t o = ok ? (int64_t)off[it] * S::ES : 0;
           const uint32_t nbytes = ok ? 16u : 0u;           // 0 source bytes = 16 bytes of zeros (padding)
           const uint32_t dst = a_hi + soff + it * 2048;
           cp_async16(dst, xh + o, nbytes);
-          cp_async16(dst + A_TILE_BYTES, xl + o, nbytes);
+          if (!BF16) cp_async16(dst + A_TILE_BYTES, xl + o, nbytes);
         }
         // arrive on `full` when this thread's copies have landed; the thread itself moves on to its next K block.
         // (The copies are generic-proxy writes: the issuer runs fence.proxy.async after its wait on `full`.)
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
         if (t == 0) trace(gk, 3);
-        c += NGROUP * KB;
+        c += NGROUP * KBE;
         while (c >= cin) { c -= cin; ++tap; if (++ts == p.s) { ts = 0; ++tr; } }
       }
     }
     }
   } else if (warp >= DRAIN_WARP0) {
     regs_take_drain();
-    conv_epilogue<BN>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
+    conv_epilogue<BN, BF16>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
   }
   tc_fence_before();
   __syncthreads();
@@ -1068,7 +1132,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_kernel(const zsg_wgrad_
   const int nkb = kb_end - kb_begin;                        // >= 1 by construction of the grid
 
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane);
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
 
   if (warp >= MMA_WARP) {
     if (elect_one()) {
@@ -1218,7 +1282,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
   const int nkb = kb_end - kb_begin;                        // >= 1 by construction of the grid
 
   PipeBars pb = setup_pipeline<BN>(sm, warp, lane, TMA_DY ? NPROD + 1 : NPROD);
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + 128);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
 
   if (warp >= MMA_WARP) {
     if (elect_one()) {
@@ -1333,6 +1397,124 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
       if (has_next) {
         if (t < 32) ent[((it + 1) & 1) * 32 + t] = e_next;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      }
+    }
+  } else {
+    // drain + epilogue: lanes own consecutive j => coalesced reductions into dw[n][j]
+    regs_take_drain();
+    const int dw = warp - DRAIN_WARP0;
+    const int quadrant = dw & 3, half = dw >> 2;
+    float acc[BN / 2];
+    int gchunk = 0;
+    drain_loop<BN>(pb, tmem_base, nkb, 0, quadrant, half, acc, gchunk);
+    const int j = j0 + quadrant * 32 + lane;
+    if (j < Kt) {
+#pragma unroll
+      for (int q = 0; q < BN / 2; ++q) {
+        const int nn = n0 + half * (BN / 2) + q;
+        if (nn < p.cout) atomicAdd(p.dw + (int64_t)nn * Kt + j, acc[q]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ============================================================================================
+// weight-gradient kernel, bf16 operand images (p.x_bf16, p.dy_bf16; BASELINE configs 3-5).  Same roles, barriers and
+// drain as wgrad_tc_async_kernel; a K block is 64 pixels = four kind::f16 MMAs of K = 16.  Both operands are MN-major
+// (channels contiguous per pixel, as they lie in memory): tile = [atom of 64 channels][64 pixels][128 B] with the plain
+// 128-byte swizzle (16-byte chunk index ^= pixel & 7).  dy arrives by TMA (CU_TENSOR_MAP_SWIZZLE_128B writes exactly
+// this layout, one 64 x 64 box per atom), the gathered x by cp.async (8 x 16 B per producer thread and K block).
+// ============================================================================================
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgrad_params p, int kb_per_split,
+                                                                  const __grid_constant__ CUtensorMap tm_dy) {
+  using S = Smem<BN, true>;
+  constexpr int KBP = 64;                                   // pixels per K block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN;
+  const int j0 = blockIdx.y * TM;
+  const int Kt = p.r * p.s * p.cin;                         // rows of D
+  const int nkb_total = (p.m + KBP - 1) / KBP;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  int kb_end = kb_begin + kb_per_split;
+  if (kb_end > nkb_total) kb_end = nkb_total;
+  const int nkb = kb_end - kb_begin;                        // >= 1 by construction of the grid
+
+  PipeBars pb = setup_pipeline<BN, true>(sm, warp, lane, NPROD + 1);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
+
+  if (warp >= MMA_WARP) {
+    if (elect_one()) {
+      Issuer is = issuer_init<BN, true>(warp - MMA_WARP);
+      mma_loop<BN, true, true>(sm, pb, tmem_base, nkb, is);
+    }
+    __syncwarp();
+  } else if (warp < DRAIN_WARP0) {
+    regs_release_producer();
+    const int group = warp >> 2;
+    const int t = tid & 127;
+    const int mc = t & 15;                                  // 16-byte chunk (8 channels) of the 128-channel tile row
+    const int ps = t >> 4;                                  // pixel sub-index 0..7 (= pixel & 7: the swizzle key)
+    const uint32_t toff = (mc >> 3) * 8192 + ps * 128 + (((mc & 7) ^ ps) << 4);   // + q * 1024 (8 pixels x 128 B)
+    // A side: this thread's 8 channels j..j+7 of D's row index = (tap, c)
+    const int j = j0 + mc * 8;
+    const bool jvalid = j < Kt;
+    int tap = 0, c = 0, tr = 0, ts = 0;
+    if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
+    const uint16_t* xb = p.x_bf16 + c;
+    const int4* rows = reinterpret_cast<const int4*>(p.rows);
+    int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 128;      // [2][64] entries per group
+    const uint32_t tiles0 = smem_u32(sm);
+    // prologue: entries of this group's first K block
+    if (group < nkb) {
+      if (t < KBP) {
+        int4 e = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
+        const int pix = (kb_begin + group) * KBP + t;
+        if (pix < p.m) e = __ldg(rows + pix);
+        ent[t] = e;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+    }
+    int it = 0;
+    for (int i = group; i < nkb; i += NGROUP, ++it) {
+      const int s = i % S::STAGES;
+      const int4* eb = ent + (it & 1) * KBP;
+      int4 e_next = make_int4(0, 0, 0, 0);                   // entries of my next K block: in flight during this one
+      const bool has_next = i + NGROUP < nkb;
+      if (has_next && t < KBP) {
+        const int pix = (kb_begin + i + NGROUP) * KBP + t;
+        if (pix < p.m) e_next = __ldg(rows + pix);
+      }
+      mbar_wait(pb.empty(s), ((i / S::STAGES) & 1) ^ 1, 5000 + i);
+      const uint32_t a_tile = tiles0 + s * S::STAGE_BYTES;
+      const uint32_t b_tile = a_tile + A_TILE_BYTES;
+      if ((t >> 5) == 0) {
+        if (elect_one()) {
+          const int pix0 = (kb_begin + i) * KBP;
+          mbar_arrive_expect_tx(pb.full(s), S::B_TILE_BYTES);
+#pragma unroll
+          for (int atom = 0; atom < BN / 64; ++atom) tma_load_2d(b_tile + atom * 8192, &tm_dy, n0 + atom * 64, pix0, pb.full(s));
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int4 e = eb[q * 8 + ps];                       // pixel q * 8 + ps of the K block
+        const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
+        const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+        const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+        const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
+        cp_async16(a_tile + toff + q * 1024, xb + ao, oka ? 16u : 0u);
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
+      if (has_next) {
+        if (t < KBP) ent[((it + 1) & 1) * KBP + t] = e_next;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
       }
     }
@@ -1486,7 +1668,7 @@ template <int BN>
 static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
     if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
   }
@@ -1496,8 +1678,44 @@ static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
   if (int rc = make_weight_map(&tm_lo, p.w_lo, p.cout, K, BN)) return rc;
   const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_async_kernel<BN><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
+  conv_tc_async_kernel<BN, false><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
   return check_launch("zsg_conv_fwd");
+}
+
+// bf16 matrices for TMA: [rows][inner] bf16, inner contiguous; box = 64 inner elements (128 B, swizzle 128B) x box_rows.
+// Weights [cout][K] (K-major B operand of the forward kernel) and dy [m][pitch] (MN-major B operand of the weight
+// gradient) use the same encoding; out-of-range reads give 0.
+static int make_bf16_map(CUtensorMap* map, const uint16_t* base, int rows, int inner, int box_rows, const char* what) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ZSG_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * sizeof(uint16_t)};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for bf16 %s rows=%d inner=%d", (int)r, what, rows, inner); return ZSG_ECUDA; }
+  return ZSG_OK;
+}
+
+template <int BN>
+static int launch_conv_bf16(const zsg_conv_params& p, cudaStream_t st) {
+  using S = Smem<BN, true>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) { set_error("conv(bf16): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+    attr_done = true;
+  }
+  CUtensorMap tm_w, tm_unused;
+  memset(&tm_unused, 0, sizeof(tm_unused));
+  const int K = p.r * p.s * p.cin;
+  if (int rc = make_bf16_map(&tm_w, p.w_bf16, p.cout, K, BN, "weights")) return rc;
+  const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
+  conv_tc_async_kernel<BN, true><<<grid, NTHREADS2, S::TOTAL, st>>>(p, tm_w, tm_unused);
+  return check_launch("zsg_conv_fwd(bf16)");
 }
 
 template <int BN>
@@ -1525,6 +1743,23 @@ static int make_dy_map(CUtensorMap* map, const float* dy, int m, int pitch) {
   return ZSG_OK;
 }
 
+// split-K factor shared by the weight-gradient launchers: minimise (waves of CTAs) x (K blocks per CTA + fixed per-CTA
+// cost), so that the grid fills whole waves of the SMs while every CTA keeps at least 8 K blocks
+static int choose_split_k(int tiles, int nkb, int fixed) {
+  const int sms = num_sms();
+  const int max_split = nkb >= 16 ? nkb / 8 : 1;
+  long best_cost = -1;
+  int split = 1;
+  for (int sk = 1; sk <= max_split && sk <= 256; ++sk) {
+    const int per_cta = (nkb + sk - 1) / sk;
+    const int ctas = tiles * ((nkb + per_cta - 1) / per_cta);
+    const long waves = (ctas + sms - 1) / sms;
+    const long cost = waves * (per_cta + fixed);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; split = sk; }
+  }
+  return split;
+}
+
 template <int BN, int MODE>          // MODE 0 = register path, 1 = cp.async operands, 2 = cp.async x + TMA dy
 static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
   static bool attr_done = false;
@@ -1545,23 +1780,7 @@ static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
   const int Kt = p.r * p.s * p.cin;
   const int tiles = ((p.cout + BN - 1) / BN) * ((Kt + TM - 1) / TM);
   const int nkb = (p.m + KB - 1) / KB;
-  int split = p.split_k;
-  if (split <= 0) {
-    // split-K factor: minimise (waves of CTAs) x (K blocks per CTA + fixed per-CTA cost), so that the grid fills whole
-    // waves of the SMs (a 2.2-wave grid costs 3 waves) while every CTA keeps at least 8 K blocks
-    const int sms = num_sms();
-    const int max_split = nkb >= 16 ? nkb / 8 : 1;
-    const int fixed = 24;                                   // pipeline fill + atomic epilogue, in K-block times
-    long best_cost = -1;
-    split = 1;
-    for (int sk = 1; sk <= max_split && sk <= 256; ++sk) {
-      const int per_cta = (nkb + sk - 1) / sk;
-      const int ctas = tiles * ((nkb + per_cta - 1) / per_cta);
-      const long waves = (ctas + sms - 1) / sms;
-      const long cost = waves * (per_cta + fixed);
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; split = sk; }
-    }
-  }
+  int split = p.split_k > 0 ? p.split_k : choose_split_k(tiles, nkb, 24);   // fixed = pipeline fill + atomic epilogue, in K-block times
   if (split > nkb) split = nkb;
   const int per = (nkb + split - 1) / split;
   split = (nkb + per - 1) / per;                            // no empty splits
@@ -1570,6 +1789,30 @@ static int launch_wgrad(const zsg_wgrad_params& p, cudaStream_t st) {
   else if (MODE == 1) wgrad_tc_async_kernel<BN, false><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per, tm_dy, tm_dy_lo);
   else wgrad_tc_async_kernel<BN, true><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, per, tm_dy, tm_dy_lo);
   return check_launch("zsg_conv_wgrad");
+}
+
+template <int BN>
+static int launch_wgrad_bf16(const zsg_wgrad_params& p, cudaStream_t st) {
+  using S = Smem<BN, true>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) { set_error("wgrad(bf16): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+    attr_done = true;
+  }
+  CUtensorMap tm_dy;
+  if (int rc = make_bf16_map(&tm_dy, p.dy_bf16, p.m, p.dy_pitch, 64, "dy")) return rc;
+  const int Kt = p.r * p.s * p.cin;
+  const int tiles = ((p.cout + BN - 1) / BN) * ((Kt + TM - 1) / TM);
+  const int nkb = (p.m + 63) / 64;
+  int split = p.split_k > 0 ? p.split_k : choose_split_k(tiles, nkb, 40);   // a bf16 K block is a third of the MMA time of a
+                                                                            // tf32 one: the fixed cost weighs more
+  if (split > nkb) split = nkb;
+  const int per = (nkb + split - 1) / split;
+  split = (nkb + per - 1) / per;                            // no empty splits
+  dim3 grid((p.cout + BN - 1) / BN, (Kt + TM - 1) / TM, split);
+  wgrad_bf16_kernel<BN><<<grid, NTHREADS2, S::TOTAL, st>>>(p, per, tm_dy);
+  return check_launch("zsg_conv_wgrad(bf16)");
 }
 
 }  // namespace zsg
@@ -1588,11 +1831,12 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   zsg_conv_params p = *pp;
   ZSG_REQUIRE(p.dil >= 0 && p.dil <= 64, "zsg_conv_fwd: dil=%d out of range", p.dil);
   if (p.dil == 0) p.dil = 1;
-  ZSG_REQUIRE(p.x && p.w && p.y && p.rows, "zsg_conv_fwd: null pointer");
+  ZSG_REQUIRE(((p.x && p.w) || (p.x_bf16 && p.w_bf16)) && p.y && p.rows, "zsg_conv_fwd: null pointer");
   ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.r > 0 && p.s > 0, "zsg_conv_fwd: empty problem");
   ZSG_REQUIRE(p.cin > 0 && p.cin % 4 == 0, "zsg_conv_fwd: cin=%d must be a multiple of 4", p.cin);
   ZSG_REQUIRE(p.in_div == 1 || p.in_div == 2, "zsg_conv_fwd: in_div must be 1 or 2");
   ZSG_REQUIRE((((uintptr_t)p.x | (uintptr_t)p.w) & 15) == 0, "zsg_conv_fwd: x and w must be 16-byte aligned");
+  ZSG_REQUIRE(p.impl != 1 || (p.x && p.w), "zsg_conv_fwd: the SIMT check kernel reads the fp32 operands");
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_fwd: in_scale without in_shift");
   ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.accumulate && p.impl != 1),
               "zsg_conv_fwd: stats needs a plain output (no bias / ReLU / mask / residual / accumulate) on the tcgen05 path");
@@ -1603,6 +1847,13 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
     return check_launch("zsg_conv_fwd(simt)");
   }
   if (!zsg_device_supported()) { set_error("zsg_conv_fwd: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
+  if (p.x_bf16 || p.w_bf16) {
+    ZSG_REQUIRE(p.x_bf16 && p.w_bf16, "zsg_conv_fwd: x_bf16 and w_bf16 go together");
+    ZSG_REQUIRE(p.cin % 8 == 0, "zsg_conv_fwd: the bf16 path needs cin=%d to be a multiple of 8", p.cin);
+    ZSG_REQUIRE(!p.in_scale && !p.in_relu, "zsg_conv_fwd: bf16 images exclude the on-load affine / ReLU (apply them in zsg_cast_bf16)");
+    ZSG_REQUIRE((((uintptr_t)p.x_bf16 | (uintptr_t)p.w_bf16) & 15) == 0, "zsg_conv_fwd: x_bf16 and w_bf16 must be 16-byte aligned");
+    return p.cout <= 64 ? launch_conv_bf16<64>(p, st) : launch_conv_bf16<128>(p, st);
+  }
   if (p.x_lo) {
     ZSG_REQUIRE(p.w_lo, "zsg_conv_fwd: x_lo needs pre-split weights (w_lo)");
     ZSG_REQUIRE(!p.in_scale && !p.in_relu, "zsg_conv_fwd: x_lo excludes the on-load affine / ReLU (apply them in zsg_split_act)");
@@ -1621,7 +1872,8 @@ extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
   zsg_wgrad_params p = *pp;
   ZSG_REQUIRE(p.dil >= 0 && p.dil <= 64, "zsg_conv_wgrad: dil=%d out of range", p.dil);
   if (p.dil == 0) p.dil = 1;
-  ZSG_REQUIRE(p.x && p.dy && p.dw && p.rows, "zsg_conv_wgrad: null pointer");
+  ZSG_REQUIRE(((p.x && p.dy) || (p.x_bf16 && p.dy_bf16)) && p.dw && p.rows, "zsg_conv_wgrad: null pointer");
+  ZSG_REQUIRE(p.impl != 1 || (p.x && p.dy), "zsg_conv_wgrad: the SIMT check kernel reads the fp32 operands");
   ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.cin > 0 && p.r > 0 && p.s > 0, "zsg_conv_wgrad: empty problem");
   ZSG_REQUIRE(p.impl == 1 || p.cin % 4 == 0, "zsg_conv_wgrad: cin=%d must be a multiple of 4", p.cin);
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_wgrad: in_scale without in_shift");
@@ -1632,6 +1884,15 @@ extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
     return check_launch("zsg_conv_wgrad(simt)");
   }
   if (!zsg_device_supported()) { set_error("zsg_conv_wgrad: tcgen05 path needs an sm_100 device"); return ZSG_EARCH; }
+  if (p.x_bf16 || p.dy_bf16) {
+    ZSG_REQUIRE(p.x_bf16 && p.dy_bf16, "zsg_conv_wgrad: x_bf16 and dy_bf16 go together");
+    ZSG_REQUIRE(p.cin % 8 == 0, "zsg_conv_wgrad: the bf16 path needs cin=%d to be a multiple of 8", p.cin);
+    ZSG_REQUIRE(!p.in_scale && !p.in_relu, "zsg_conv_wgrad: bf16 images exclude the on-load affine / ReLU");
+    ZSG_REQUIRE(p.dy_pitch >= p.cout && p.dy_pitch % 8 == 0,
+                "zsg_conv_wgrad: the bf16 path needs dy as a plain [m, dy_pitch] matrix, dy_pitch >= cout and a multiple of 8");
+    ZSG_REQUIRE((((uintptr_t)p.x_bf16 | (uintptr_t)p.dy_bf16) & 15) == 0, "zsg_conv_wgrad: bf16 operands must be 16-byte aligned");
+    return p.cout <= 64 ? launch_wgrad_bf16<64>(p, st) : launch_wgrad_bf16<128>(p, st);
+  }
   if (p.x_lo || p.dy_lo) {
     ZSG_REQUIRE(p.x_lo && p.dy_lo, "zsg_conv_wgrad: x_lo and dy_lo go together");
     ZSG_REQUIRE(!p.in_scale && !p.in_relu, "zsg_conv_wgrad: pre-split operands exclude the on-load affine / ReLU");

@@ -2,6 +2,7 @@
 // stem max-pool, FPN nearest upsample + add, global average pool, language/grid tiling,
 // bias-gradient column sums, layout helpers and Adam.  All tensors NHWC float32, channel
 // counts multiples of 4 so that every access is a 16-byte vector, channels fastest => coalesced.
+#include <cuda_bf16.h>
 #include <math.h>
 #include "common.cuh"
 
@@ -30,6 +31,20 @@ __device__ __forceinline__ float4 tf32_lo4(float4 v) {          // remainder aft
   l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
   l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
   return l;
+}
+
+// bf16 operand image (the bf16 GEMM path of configs 3-5): round-to-nearest-even, 4 values = one 8-byte store
+__device__ __forceinline__ void st4_bf16(uint16_t* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+// operand image of a value the kernel has in registers: TF32 remainder (float) or bf16 copy, whichever the caller passed
+__device__ __forceinline__ void st_image(float* lo, uint16_t* b16, int64_t i4, float4 v) {
+  if (lo) st4(lo + i4, tf32_lo4(v));
+  if (b16) st4_bf16(b16 + i4, v);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -174,8 +189,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ shift, const float* __restrict__ r,
                                                        const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, int relu,
-                                                       float* __restrict__ y, float* __restrict__ y_lo, int64_t n4,
-                                                       int c4) {
+                                                       float* __restrict__ y, float* __restrict__ y_lo,
+                                                       uint16_t* __restrict__ y_b16, int64_t n4, int c4) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
     float4 v = fma4(ld4(x + i * 4), ld4(scale + c), ld4(shift + c));
@@ -186,14 +201,15 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     }
     if (relu) v = relu4(v);
     st4(y + i * 4, v);
-    if (y_lo) st4(y_lo + i * 4, tf32_lo4(v));
+    st_image(y_lo, y_b16, i * 4, v);
   }
 }
 
 // operand preparation for the cp.async GEMM paths: z = relu?(x * scale + shift), lo = z - trunc_tf32(z)
 __global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int relu, float* __restrict__ z,
-                                                        float* __restrict__ lo, int64_t n4, int c4) {
+                                                        float* __restrict__ lo, uint16_t* __restrict__ b16, int64_t n4,
+                                                        int c4) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = ld4(x + i * 4);
     if (scale) {
@@ -202,7 +218,7 @@ __global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict_
     }
     if (relu) v = relu4(v);
     if (z) st4(z + i * 4, v);
-    st4(lo + i * 4, tf32_lo4(v));
+    st_image(lo, b16, i * 4, v);
   }
 }
 
@@ -210,8 +226,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ act_out, int mask_mode,
-    const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dx_lo, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, int64_t rows, int C) {
+    const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dx_lo, uint16_t* __restrict__ dx_b16,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C) {
   const int c4 = C / 4;
   const int64_t n4 = rows * c4;
   const float inv_n = 1.0f / (float)rows;
@@ -260,7 +276,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       o.z = ga.z * is.z * (gg.z - s1[2] - (v[u].z - mu.z) * is.z * s2[2]);
       o.w = ga.w * is.w * (gg.w - s1[3] - (v[u].w - mu.w) * is.w * s2[3]);
       st4(dx + i * 4, o);
-      if (dx_lo) st4(dx_lo + i * 4, tf32_lo4(o));
+      st_image(dx_lo, dx_b16, i * 4, o);
     }
   }
 }
@@ -869,8 +885,29 @@ extern "C" int zsg_bn_apply(const float* x, const float* scale, const float* shi
   ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_bn_apply: bad arguments");
   int64_t n4 = rows * (c / 4);
   bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, y_lo,
-                                                                     n4, c / 4);
+                                                                     nullptr, n4, c / 4);
   return check_launch("zsg_bn_apply");
+}
+
+extern "C" int zsg_bn_apply_bf16(const float* x, const float* scale, const float* shift, const float* r,
+                                 const float* rscale, const float* rshift, int relu, float* y, uint16_t* y_bf16,
+                                 int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && scale && shift && y && y_bf16 && c % 4 == 0, "zsg_bn_apply_bf16: bad arguments");
+  int64_t n4 = rows * (c / 4);
+  bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, nullptr,
+                                                                     y_bf16, n4, c / 4);
+  return check_launch("zsg_bn_apply_bf16");
+}
+
+extern "C" int zsg_cast_bf16(const float* x, const float* scale, const float* shift, int relu, uint16_t* out,
+                             int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && out && c > 0 && c % 4 == 0, "zsg_cast_bf16: bad arguments");
+  ZSG_REQUIRE(!scale == !shift, "zsg_cast_bf16: scale and shift go together");
+  ZSG_REQUIRE((((uintptr_t)x & 15) | ((uintptr_t)out & 7)) == 0, "zsg_cast_bf16: x must be 16-byte and out 8-byte aligned");
+  if (rows <= 0) return ZSG_OK;
+  const int64_t n4 = rows * (c / 4);
+  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, nullptr, nullptr, out, n4, c / 4);
+  return check_launch("zsg_cast_bf16");
 }
 
 extern "C" int zsg_split_act(const float* x, const float* scale, const float* shift, int relu, float* z, float* lo,
@@ -880,7 +917,7 @@ extern "C" int zsg_split_act(const float* x, const float* scale, const float* sh
   ZSG_REQUIRE(z || (!scale && !relu), "zsg_split_act: a prologue needs an output tensor z");
   if (rows <= 0) return ZSG_OK;
   const int64_t n4 = rows * (c / 4);
-  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, z, lo, n4, c / 4);
+  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, z, lo, nullptr, n4, c / 4);
   return check_launch("zsg_split_act");
 }
 
@@ -900,8 +937,18 @@ extern "C" int zsg_bn_bwd_apply(const float* dy, const float* x, const float* me
                                 float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
   ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx && c % 4 == 0, "zsg_bn_bwd_apply: bad arguments");
   bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
-      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dx_lo, dgamma, dbeta, rows, c);
+      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dx_lo, nullptr, dgamma, dbeta, rows, c);
   return check_launch("zsg_bn_bwd_apply");
+}
+
+extern "C" int zsg_bn_bwd_apply_bf16(const float* dy, const float* x, const float* mean, const float* invstd,
+                                     const float* gamma, const float* scale, const float* shift, const float* act_out,
+                                     int mask_mode, const double* sums, float* dx, uint16_t* dx_bf16, float* dgamma,
+                                     float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx && dx_bf16 && c % 4 == 0, "zsg_bn_bwd_apply_bf16: bad arguments");
+  bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
+      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, nullptr, dx_bf16, dgamma, dbeta, rows, c);
+  return check_launch("zsg_bn_bwd_apply_bf16");
 }
 
 extern "C" int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const float* shift, float* y,

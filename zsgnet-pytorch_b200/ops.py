@@ -35,9 +35,8 @@ class LaunchProfiler:
         return out
 
 
-def _f32c(t):
-    assert t.dtype == torch.float32 and t.is_cuda, (t.dtype, t.device)
-    return t
+def _is_bf16(t):
+    return t is not None and t.dtype == torch.bfloat16
 
 
 class ConvOp:
@@ -48,12 +47,20 @@ class ConvOp:
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
                  x_lo=None, dil=1, stats=None):
         self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats)
+        # operand images: float32 x_lo / w_lo = TF32 remainders (3xTF32 path); bfloat16 x_lo / w_lo = the bf16 copies of the
+        # operands (bf16 path of BASELINE configs 3-5; goes into the x_bf16 / w_bf16 fields of the parameter block)
+        self.bf16 = _is_bf16(x_lo)
+        assert self.bf16 == _is_bf16(w_lo), "conv operand images must both be bf16 or both fp32"
+        xb, wb = (x_lo, w_lo) if self.bf16 else (None, None)
+        if self.bf16:
+            x_lo = w_lo = None
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl, ptr(x_lo), dil, ptr(stats))
+                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
-        self.kernel = "conv_tc_async_kernel" if x_lo is not None else ("conv_tc_kernel" if w_lo is not None else "conv_tc_generic_kernel")
+        self.kernel = ("conv_bf16_kernel" if self.bf16 else "conv_tc_async_kernel" if x_lo is not None else
+                       "conv_tc_kernel" if w_lo is not None else "conv_tc_generic_kernel")
 
     def __call__(self):
         if PROFILER is not None:
@@ -66,11 +73,16 @@ class WgradOp:
                  impl=IMPL_TC, x_lo=None, dy_lo=None, dy_pitch=0, dil=1):
         self.keep = (x, dy, dw, rows, in_scale, in_shift, x_lo, dy_lo)
         self.dw = dw
+        self.bf16 = _is_bf16(x_lo)                           # bf16 images (see ConvOp)
+        assert self.bf16 == _is_bf16(dy_lo), "wgrad operand images must both be bf16 or both fp32"
+        xb, dyb = (x_lo, dy_lo) if self.bf16 else (None, None)
+        if self.bf16:
+            x_lo = dy_lo = None
         self.p = WgradParams(ptr(x), ptr(dy), ptr(dw), ptr(rows), m, cin, cout, r, s, ptr(in_scale), ptr(in_shift),
-                             int(in_relu), split_k, impl, ptr(x_lo), ptr(dy_lo), dy_pitch, dil)
+                             int(in_relu), split_k, impl, ptr(x_lo), ptr(dy_lo), dy_pitch, dil, ptr(xb), ptr(dyb))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin
-        self.kernel = "wgrad_tc_async_kernel" if x_lo is not None else "wgrad_tc_kernel"
+        self.kernel = "wgrad_bf16_kernel" if self.bf16 else "wgrad_tc_async_kernel" if x_lo is not None else "wgrad_tc_kernel"
 
     def __call__(self):
         if PROFILER is not None:
@@ -101,8 +113,17 @@ def weight_transpose_flip_batched(src_base, dst_base, table, n, total):
 
 
 def split_act(x, lo, rows, c, scale=None, shift=None, relu=False, z=None):
-    """lo = remainder of (z or x) after TF32 truncation; z = relu?(x * scale + shift) when a prologue is given."""
+    """Operand image of relu?(x * scale + shift).  float32 `lo`: the TF32 remainder (and z = the activated tensor when a
+    prologue is given); bfloat16 `lo`: the bf16 copy (z is not needed by the bf16 GEMMs and is not written)."""
+    if _is_bf16(lo):
+        call("zsg_cast_bf16", ptr(x), ptr(scale), ptr(shift), int(relu), ptr(lo), rows, c, stream())
+        return
     call("zsg_split_act", ptr(x), ptr(scale), ptr(shift), int(relu), ptr(z), ptr(lo), rows, c, stream())
+
+
+def cast_bf16(x, out, n):
+    """out[i] = bf16(x[i]) over a flat array (weights); n % 4 == 0."""
+    call("zsg_cast_bf16", ptr(x), None, None, 0, ptr(out), n // 4, 4, stream())
 
 
 def split_tf32(w, hi, lo, n):
@@ -150,8 +171,8 @@ def bn_eval_affine(rm, rv, gamma, beta, eps, c, scale, shift):
 
 
 def bn_apply(x, scale, shift, y, rows, c, relu, r=None, rscale=None, rshift=None, y_lo=None):
-    call("zsg_bn_apply", ptr(x), ptr(scale), ptr(shift), ptr(r), ptr(rscale), ptr(rshift), int(relu), ptr(y), ptr(y_lo),
-         rows, c, stream())
+    call("zsg_bn_apply_bf16" if _is_bf16(y_lo) else "zsg_bn_apply", ptr(x), ptr(scale), ptr(shift), ptr(r), ptr(rscale),
+         ptr(rshift), int(relu), ptr(y), ptr(y_lo), rows, c, stream())
 
 
 def bn_bwd_reduce(dy, x, mean, invstd, sums, rows, c, mask_mode=0, scale=None, shift=None, act_out=None, dz_out=None):
@@ -161,8 +182,9 @@ def bn_bwd_reduce(dy, x, mean, invstd, sums, rows, c, mask_mode=0, scale=None, s
 
 def bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, rows, c, mask_mode=0, scale=None, shift=None,
                  act_out=None, dx_lo=None):
-    call("zsg_bn_bwd_apply", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(scale), ptr(shift), ptr(act_out),
-         mask_mode, ptr(sums), ptr(dx), ptr(dx_lo), ptr(dgamma), ptr(dbeta), rows, c, stream())
+    call("zsg_bn_bwd_apply_bf16" if _is_bf16(dx_lo) else "zsg_bn_bwd_apply", ptr(dy), ptr(x), ptr(mean), ptr(invstd),
+         ptr(gamma), ptr(scale), ptr(shift), ptr(act_out), mask_mode, ptr(sums), ptr(dx), ptr(dx_lo), ptr(dgamma), ptr(dbeta),
+         rows, c, stream())
 
 
 def maxpool_bn_relu_fwd(x, scale, shift, y, argmax, b, h, w, c, ho, wo):
