@@ -268,7 +268,10 @@ int zsg_lstm_rev_step_bwd(const float* dlang, const float* gates /*[B,512]*/, co
  * strict > thr, first-index argmax (bit-exact `pos`/`top1`).  att/reg may be strided views of one packed
  * [B,A,5] buffer: *_stride are element strides per anchor.
  * losses[0..2] = loss, cls_ls, box_ls (double); d_att/d_reg are gradients of `loss` (lamb_reg applied).
- * workspace: zsg_match_loss_workspace_bytes(B).                                                        */
+ * NaN follows torch.max: a NaN IoU row / NaN scores select the first NaN index, never an out-of-range one; a NaN
+ * loss is replaced by the constants of loss.py:128-133 and the gradients are zeroed.
+ * workspace: zsg_match_loss_workspace_bytes(B) bytes, 16-byte aligned, ALL ZERO before the first call; every call
+ * leaves it all zero again (no memset on the stream between steps).  Two kernel launches.               */
 size_t zsg_match_loss_workspace_bytes(int b);
 int zsg_match_loss(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride, const float* annot,
                    const double* anchors, int b, int a, double match_thr, float alpha, float gamma, double lamb_reg,
@@ -279,9 +282,13 @@ int zsg_match_loss(const float* att, int64_t att_stride, const float* reg, int64
 /* -------------------------- evaluator (evaluator.py:48-117) ------------------------------
  * best_ids = argmax sigmoid(att) (first index); Acc/MaxPos flags from the decoded box of that / the
  * IoU-argmax anchor; pred_boxes in pixel x1y1x2y2 (double); metrics[0]=Acc, [1]=MaxPos (float).       */
+size_t zsg_eval_workspace_bytes(int b);
+/* metrics holds 2 + 2*B floats (the per-sample flags follow the two means); workspace as for zsg_match_loss
+ * (zsg_eval_workspace_bytes(B), all zero before the first call, left zero).  One kernel launch. */
 int zsg_eval(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride, const float* annot,
              const double* anchors, const float* img_size /*[B,2] (h,w)*/, int b, int a, double iou_thr,
-             int64_t* best_ids, float* pred_scores, double* pred_boxes, float* metrics, zsg_stream_t stream);
+             int64_t* best_ids, float* pred_scores, double* pred_boxes, float* metrics, void* workspace,
+             size_t ws_bytes, zsg_stream_t stream);
 
 /* ------------------------------ Adam (main_dist.py:50) ----------------------------------- */
 int zsg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -40,8 +40,9 @@ def _worker(rank, world, port, out_q, model="retina"):
         red.on_bucket(lo_, hi_)
     red.finish()
     other = torch.randn(store.used, generator=torch.Generator().manual_seed(100 + (1 - rank)))
-    expect = (mine + other) * red.grad_scale
-    got = store.grad_arena * red.grad_scale
+    expect = (mine + other) / world               # the reducer leaves the MEAN in the arena (what DDP leaves in .grad)
+    got = store.grad_arena
+    assert red.grad_scale == 1.0
     ok = torch.allclose(got, expect, rtol=1e-6, atol=1e-6)
     a, b = ddp.shard_range(128, rank, world)
     out_q.put((rank, ok, red.calls, red.bytes_reduced, (a, b)))

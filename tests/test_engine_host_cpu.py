@@ -69,7 +69,43 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     assert seen[0][0] == 0 and seen[-1][1] == store.used
     for (a, b), (c, d) in zip(seen, seen[1:]):
         assert b == c and a < b
-    assert len(seen) == 16 + 4
+    # 20 backward stages (head, lstm, fpn, 16 blocks, stem) coalesced into buckets of >= 4 Mi elements: one graph
+    # segment + one all-reduce each
+    assert len(eng.bucket_marks) == 16 + 4 and len(seen) == len(eng.segments) == 6
+    assert all(b - a >= eng.bucket_elems for a, b in seen[:-1])
+    assert [s[0] for s in eng.segments] == [0] + [s[1] for s in eng.segments[:-1]] and eng.segments[-1][1] == len(eng.bwd)
+
+
+def test_bf16_engine_program_on_host(recorded):
+    """dtype='bf16' (BASELINE configs[2..4]): every contraction with cin % 8 == 0 reads bf16 images; the 3-channel stem
+    and the 300-wide LSTM projection keep the fp32 (3xTF32) path; BatchNorm passes write bf16 images directly."""
+    calls, engine, spec, ops = recorded
+    B, T = 2, 5
+    store = engine.ParamStore(torch.device("cpu"))
+    bufs = {}
+    for name, shp in spec.buffer_specs():
+        bufs[name] = torch.zeros(shp if len(shp) else (), dtype=torch.float32 if len(shp) else torch.long)
+    eng = engine.Engine(store, bufs, B, T, torch.device("cpu"), dtype="bf16")
+    f32 = engine.Engine(store, bufs, B, T, torch.device("cpu"))
+    kinds = collections.Counter(it[1].kernel for it in eng.fwd if it[0] == "op")
+    assert kinds == {"conv_bf16_kernel": 52 + 8 + 6, "conv_tc_async_kernel": 2}      # stem + LSTM projection stay fp32
+    bk = collections.Counter(op.kernel for op in eng.bwd if isinstance(op, (ops.ConvOp, ops.WgradOp)))
+    assert bk["wgrad_bf16_kernel"] == 52 + 8 + 6 and bk["wgrad_tc_async_kernel"] == 1 and bk["wgrad_tc_kernel"] == 4
+    assert bk["conv_bf16_kernel"] == 52 + 8 + 6 + 5 * 3 and "conv_tc_async_kernel" not in bk
+    # no materialised BN-ReLU tensors and half-size images: the activation-side buffers shrink (at B = 2 the weight
+    # images dominate both engines, so compare without them)
+    wimg = lambda e: 4 * (2 * store.total + 3 * e.pool_n) + (2 * (store.total + e.pool_n) if e.bf16 else 0)
+    assert eng.nbytes - wimg(eng) < 0.85 * (f32.nbytes - wimg(f32))
+    eng.set_inputs(torch.rand(B, 3, 300, 300), torch.randn(B, 4, 300), torch.tensor([4.0, 2.0]), torch.tensor([0, 1]),
+                   torch.randn(2, B, 128), torch.randn(2, B, 128))
+    del calls[:]
+    eng.forward(training=True)
+    fwd = collections.Counter(calls)
+    assert fwd["zsg_cast_bf16"] == 2 + 32 + 1 + 4 + 6 and fwd["zsg_split_act"] == 2 and fwd["zsg_bn_apply_bf16"] == 16
+    del calls[:]
+    eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5))
+    bwd = collections.Counter(calls)
+    assert bwd["zsg_bn_bwd_apply_bf16"] == 52 and bwd["zsg_bn_bwd_apply"] == 1 and bwd["zsg_split_tf32"] == 0
 
 
 def test_ssd_vgg_program_builds_and_runs_on_host(recorded):
@@ -100,7 +136,8 @@ def test_ssd_vgg_program_builds_and_runs_on_host(recorded):
     assert seen[0][0] == 0 and seen[-1][1] == store.used
     for (a, b), (c, d) in zip(seen, seen[1:]):
         assert b == c and a < b
-    assert len(seen) == 6 + 2 + 2                                              # VGG segments, extras, fproj, lstm, head
+    assert len(eng.bucket_marks) == 6 + 2 + 2                                   # VGG segments, extras, fproj, lstm, head
+    assert 2 <= len(seen) == len(eng.segments) <= 6                             # coalesced to >= 4 Mi elements each
 
 
 def test_param_store_views_follow_reference_shapes(recorded):

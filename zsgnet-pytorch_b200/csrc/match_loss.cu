@@ -1,7 +1,7 @@
 // Anchor matching + focal / smooth-L1 loss + gradient, and the Acc@0.5 evaluator.
 //
-// Replaces loss.py:73-135 (≈25 ATen launches, a 1.22 GB torch.eye and 3 host syncs) and
-// evaluator.py:74-99 by three launches each.  IoU follows anchors.py:90-116 operation by
+// Replaces loss.py:73-135 (≈25 ATen launches, a 1.22 GB torch.eye and 3 host syncs) by two launches and
+// evaluator.py:74-99 by one (round 1: memset + four, and two; the match pass ran one CTA per sample).  IoU follows anchors.py:90-116 operation by
 // operation in float64 with explicit round-to-nearest intrinsics so that nvcc cannot contract
 // a*b+c into an FMA: the positive mask and both argmaxes are bit-exact with the CPU reference.
 //
@@ -46,11 +46,17 @@ __device__ __forceinline__ double iou_box_gt(const Box4& bx, float g0, float g1,
   return __ddiv_rn(inter, __dadd_rn(uni, 1e-8));
 }
 
+// torch.max semantics for the row argmax (anchors.py / loss.py:77, evaluator.py:74): the largest value wins, NaN counts as
+// the largest of all, ties (and several NaNs) go to the LOWEST index.  A diverged network (all-NaN scores) or a NaN
+// annotation therefore still yields a valid index, like the reference, instead of an out-of-range one.
 struct ArgMaxD { double v; int i; };
-__device__ __forceinline__ ArgMaxD better(ArgMaxD a, ArgMaxD b) {   // larger value, then lower index
-  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+__device__ __forceinline__ ArgMaxD better(ArgMaxD a, ArgMaxD b) {
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  const bool gt = bn ? !an : (!an && b.v > a.v);
+  const bool eq = (an && bn) || b.v == a.v;
+  return (gt || (eq && b.i < a.i)) ? b : a;
 }
-__device__ __forceinline__ ArgMaxD block_argmax(ArgMaxD x, ArgMaxD* sm) {
+__device__ __forceinline__ ArgMaxD warp_argmax(ArgMaxD x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ArgMaxD y;
@@ -58,18 +64,16 @@ __device__ __forceinline__ ArgMaxD block_argmax(ArgMaxD x, ArgMaxD* sm) {
     y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
     x = better(x, y);
   }
+  return x;
+}
+constexpr double ARG_NONE = -1.0;       // below every IoU / score; paired with index INT_MAX, replaced by the first candidate
+__device__ __forceinline__ ArgMaxD block_argmax(ArgMaxD x, ArgMaxD* sm) {
+  x = warp_argmax(x);
   int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
   if (l == 0) sm[w] = x;
   __syncthreads();
   if (w == 0) {
-    x = (l < nw) ? sm[l] : ArgMaxD{-1.0, 0x7fffffff};
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ArgMaxD y;
-      y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
-      y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
-      x = better(x, y);
-    }
+    x = warp_argmax((l < nw) ? sm[l] : ArgMaxD{ARG_NONE, 0x7fffffff});
     if (l == 0) sm[0] = x;
   }
   __syncthreads();
@@ -78,31 +82,68 @@ __device__ __forceinline__ ArgMaxD block_argmax(ArgMaxD x, ArgMaxD* sm) {
   return r;
 }
 
-struct LossWs {                      // device workspace header (doubles first for alignment)
+// Device workspace.  Contract: all zero before the first call; every call leaves it all zero again (the last block
+// of the loss kernel clears what the call used), so no memset sits on the stream between steps.
+constexpr int MATCH_MAX_CHUNKS = 32;
+struct LossWs {
   double cls_sum;
   unsigned long long npos_total;
   int nan_flag;
-  int pad;
-  // followed by double box_row[B]; int npos_row[B]
+  unsigned int loss_ticket;
+  // followed by: double box_row[B]; int npos_row[B]; unsigned row_ticket[B]; MatchPart part[B][MATCH_MAX_CHUNKS]
 };
+struct MatchPart { double v; int i; int cnt; };
 
-// ---- pass 1: one CTA per sample: IoU row, first-index argmax, positives ---------------------
-__global__ void __launch_bounds__(1024) match_rows_kernel(const float* __restrict__ annot,
-                                                          const double* __restrict__ anchors, int A,
-                                                          double thr, int use_multi, uint8_t* __restrict__ pos,
-                                                          int64_t* __restrict__ top1, LossWs* ws,
-                                                          int* __restrict__ npos_row) {
+__host__ __device__ inline size_t ws_box_off() { return sizeof(LossWs); }
+__host__ __device__ inline size_t ws_npos_off(int B) { return ws_box_off() + (size_t)B * sizeof(double); }
+__host__ __device__ inline size_t ws_ticket_off(int B) { return ws_npos_off(B) + (size_t)B * sizeof(int); }
+__host__ __device__ inline size_t ws_part_off(int B) { return (ws_ticket_off(B) + (size_t)B * sizeof(unsigned) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t ws_total(int B) { return ws_part_off(B) + (size_t)B * MATCH_MAX_CHUNKS * sizeof(MatchPart); }
+
+// IoU of the match pass: exactly iou_gt_anchor, but the division is skipped where the boxes do not intersect
+// (inter == 0 gives 0 / (positive) == +0.0 in the reference too; most of the 17460 anchors of a row are such).
+__device__ __forceinline__ double iou_match(float g0, float g1, float g2, float g3, const Box4& an, bool row_nan) {
+  const double tl0 = fmax((double)g0, an.y1), tl1 = fmax((double)g1, an.x1);
+  const double br0 = fmin((double)g2, an.y2), br1 = fmin((double)g3, an.x2);
+  const double s0 = fmax(__dsub_rn(br0, tl0), 0.0), s1 = fmax(__dsub_rn(br1, tl1), 0.0);
+  const double inter = __dmul_rn(s0, s1);
+  double v = 0.0;
+  if (inter != 0.0) {
+    const float gh = __fsub_rn(g2, g0), gw = __fsub_rn(g3, g1);
+    const double gt_area = (double)__fmul_rn(gh, gw);                // float32 product, then promoted
+    const double an_area = __dmul_rn(__dsub_rn(an.y2, an.y1), __dsub_rn(an.x2, an.x1));
+    const double uni = __dsub_rn(__dadd_rn(gt_area, an_area), inter);
+    v = __ddiv_rn(inter, __dadd_rn(uni, 1e-8));
+  }
+  // torch.max / torch.min propagate NaN (CUDA's fmax / fmin drop it): a NaN annotation makes the whole IoU row NaN
+  return row_nan ? __longlong_as_double(0x7ff8000000000000LL) : v;
+}
+
+// ---- pass 1: grid (chunks, B): IoU of a chunk of one row, positives, partial first-index argmax; the last chunk of a
+// row to finish (ticket) reduces the partials: top-1 anchor, positives per row and in total.  With one CTA per sample
+// (round 1) 64 CTAs ran on 148 SMs and the pass took as long as the loss pass itself.
+__global__ void __launch_bounds__(256) match_rows_kernel(const float* __restrict__ annot,
+                                                         const double* __restrict__ anchors, int A, int per_chunk,
+                                                         double thr, int use_multi, uint8_t* __restrict__ pos,
+                                                         int64_t* __restrict__ top1, uint8_t* __restrict__ wsb, int B) {
   __shared__ ArgMaxD sm[32];
-  __shared__ int cnt_sm[32];
-  const int b = blockIdx.x;
+  __shared__ int cnt_sm[8];
+  __shared__ bool last;
+  LossWs* ws = reinterpret_cast<LossWs*>(wsb);
+  int* npos_row = reinterpret_cast<int*>(wsb + ws_npos_off(B));
+  unsigned* row_ticket = reinterpret_cast<unsigned*>(wsb + ws_ticket_off(B));
+  MatchPart* part = reinterpret_cast<MatchPart*>(wsb + ws_part_off(B));
+  const int b = blockIdx.y, ch = blockIdx.x, nch = gridDim.x;
   const float g0 = annot[4 * b], g1 = annot[4 * b + 1], g2 = annot[4 * b + 2], g3 = annot[4 * b + 3];
-  ArgMaxD best{-1.0, 0x7fffffff};
+  const bool row_nan = (g0 != g0) || (g1 != g1) || (g2 != g2) || (g3 != g3);
+  ArgMaxD best{ARG_NONE, 0x7fffffff};
   int cnt = 0;
   uint8_t* prow = pos + (size_t)b * A;
-  for (int a = threadIdx.x; a < A; a += blockDim.x) {
-    double v = iou_gt_anchor(g0, g1, g2, g3, load_anchor(anchors, a));
+  const int a_end = min(A, (ch + 1) * per_chunk);
+  for (int a = ch * per_chunk + threadIdx.x; a < a_end; a += blockDim.x) {
+    const double v = iou_match(g0, g1, g2, g3, load_anchor(anchors, a), row_nan);
     best = better(best, ArgMaxD{v, a});
-    int p = (use_multi && v > thr) ? 1 : 0;
+    const int p = (use_multi && v > thr) ? 1 : 0;
     cnt += p;
     prow[a] = (uint8_t)p;
   }
@@ -113,73 +154,147 @@ __global__ void __launch_bounds__(1024) match_rows_kernel(const float* __restric
   if (threadIdx.x == 0) {
     int total = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += cnt_sm[w];
-    if (!(use_multi && best.v > thr)) total += 1;                   // the top-1 anchor is always positive
-    prow[best.i] = 1;
-    top1[b] = best.i;
-    npos_row[b] = total;
-    atomicAdd(&ws->npos_total, (unsigned long long)total);
+    part[b * MATCH_MAX_CHUNKS + ch] = MatchPart{best.v, best.i, total};
+    __threadfence();                                                // partial and this chunk's pos bytes before the ticket
+    last = atomicAdd(&row_ticket[b], 1u) == (unsigned)nch - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x < 32) {
+    __threadfence();
+    ArgMaxD x{ARG_NONE, 0x7fffffff};
+    int c = 0;
+    if ((int)threadIdx.x < nch) {
+      const volatile MatchPart* q = part + b * MATCH_MAX_CHUNKS + threadIdx.x;
+      x = ArgMaxD{q->v, q->i};
+      c = q->cnt;
+    }
+    x = warp_argmax(x);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (threadIdx.x == 0) {
+      const int idx = min(max(x.i, 0), A - 1);
+      if (!(use_multi && x.v > thr)) c += 1;                        // the top-1 anchor is always positive
+      prow[idx] = 1;
+      top1[b] = idx;
+      npos_row[b] = c;
+      atomicAdd(&ws->npos_total, (unsigned long long)c);
+      row_ticket[b] = 0;                                            // leave the workspace clean
+    }
   }
 }
 
-// ---- pass 2: per (sample, anchor) loss terms and gradients ----------------------------------
+// ---- pass 2: per (sample, anchor) loss terms and gradients; the last block (ticket) turns the sums into the three
+// loss scalars, applies the reference's NaN guard and clears the workspace.  PACKED: att / reg and d_att / d_reg are the
+// [..., 4] / [..., :4] views of [B, A, 5] buffers (what the head writes, mdl.py:381-382): the block's 256 anchors are
+// 5120 contiguous bytes, moved with 128-bit accesses through shared memory instead of five stride-5 scalar loads and
+// stores per thread.
+struct LossTerms { float d_att; float4 d_reg; double cls_l, box_l; };
+
+__device__ __forceinline__ LossTerms loss_terms(float x, const float r[4], bool t, int b, int a, int B,
+                                                const float* __restrict__ annot, const double* __restrict__ anchors,
+                                                float alpha, float gamma, double lamb_reg, float inv_np, int npos_b) {
+  LossTerms o;
+  // loss.py:103-125 in float32, like the reference
+  const float p = 1.0f / (1.0f + expf(-x));
+  float w = t ? (1.0f - p) : p;
+  w = (gamma == 2.0f) ? w * w : powf(w, gamma);
+  w *= t ? (1.0f - alpha) : alpha;                                  // alpha weights the negatives
+  const float tf = t ? 1.0f : 0.0f;
+  const float bce = fmaxf(x, 0.0f) - x * tf + log1pf(expf(-fabsf(x)));
+  o.cls_l = (double)(w * bce);
+  o.d_att = w * (p - tf) * inv_np;
+  o.d_reg = make_float4(0.f, 0.f, 0.f, 0.f);
+  o.box_l = 0.0;
+  if (t) {                                                          // few per row: divergence is cheap
+    const float g0 = annot[4 * b], g1 = annot[4 * b + 1], g2 = annot[4 * b + 2], g3 = annot[4 * b + 3];
+    const Box4 an = load_anchor(anchors, a);
+    // anchors.py:168-179: GT centre/size in float32, anchors in float64
+    const float gc0 = __fdiv_rn(__fadd_rn(g0, g2), 2.0f), gc1 = __fdiv_rn(__fadd_rn(g1, g3), 2.0f);
+    const float gh = __fsub_rn(g2, g0), gw = __fsub_rn(g3, g1);
+    const double ac0 = __ddiv_rn(__dadd_rn(an.y1, an.y2), 2.0), ac1 = __ddiv_rn(__dadd_rn(an.x1, an.x2), 2.0);
+    const double ah = __dadd_rn(__dsub_rn(an.y2, an.y1), 1e-8), aw = __dadd_rn(__dsub_rn(an.x2, an.x1), 1e-8);
+    double tg[4];
+    tg[0] = ((double)gc0 - ac0) / ah;
+    tg[1] = ((double)gc1 - ac1) / aw;
+    tg[2] = log((double)gh / ah);
+    tg[3] = log((double)gw / aw);
+    const double gscale = lamb_reg / ((double)B * (double)npos_b);
+    float dv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double d = (double)r[k] - tg[k];
+      const double ad = fabs(d);
+      o.box_l += (ad < 1.0) ? 0.5 * d * d : ad - 0.5;              // SmoothL1, beta = 1 (loss.py:41,91)
+      dv[k] = (float)(gscale * fmin(fmax(d, -1.0), 1.0));
+    }
+    o.d_reg = make_float4(dv[0], dv[1], dv[2], dv[3]);
+  }
+  return o;
+}
+
+template <bool PACKED>
 __global__ void __launch_bounds__(256) loss_grad_kernel(
     const float* __restrict__ att, int64_t att_stride, const float* __restrict__ reg, int64_t reg_stride,
     const float* __restrict__ annot, const double* __restrict__ anchors, const uint8_t* __restrict__ pos, int B, int A,
     float alpha, float gamma, double lamb_reg, float* __restrict__ d_att, int64_t d_att_stride,
-    float* __restrict__ d_reg, int64_t d_reg_stride, LossWs* ws, double* __restrict__ box_row,
-    const int* __restrict__ npos_row) {
+    float* __restrict__ d_reg, int64_t d_reg_stride, uint8_t* __restrict__ wsb, double* __restrict__ losses) {
+  __shared__ __align__(16) float tile[PACKED ? 256 * 5 : 4];
+  LossWs* ws = reinterpret_cast<LossWs*>(wsb);
+  double* box_row = reinterpret_cast<double*>(wsb + ws_box_off());
+  int* npos_row = reinterpret_cast<int*>(wsb + ws_npos_off(B));
   const int b = blockIdx.y;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a0 = blockIdx.x * 256;
+  const int a = a0 + threadIdx.x;
+  const int na = min(256, A - a0);                                  // anchors of this block
   double cls_l = 0.0, box_l = 0.0;
-  if (a < A) {
-    const size_t e = (size_t)b * A + a;
-    const float x = att[e * att_stride];
-    const bool t = pos[e] != 0;
-    // loss.py:103-125 in float32, like the reference
-    const float p = 1.0f / (1.0f + expf(-x));
-    float w = t ? (1.0f - p) : p;
-    w = (gamma == 2.0f) ? w * w : powf(w, gamma);
-    w *= t ? (1.0f - alpha) : alpha;                                  // alpha weights the negatives
-    const float tf = t ? 1.0f : 0.0f;
-    const float bce = fmaxf(x, 0.0f) - x * tf + log1pf(expf(-fabsf(x)));
-    cls_l = (double)(w * bce);
-    const float inv_np = 1.0f / (float)ws->npos_total;
-    d_att[e * d_att_stride] = w * (p - tf) * inv_np;
-    float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t) {                                                          // few per row: divergence is cheap
-      const float g0 = annot[4 * b], g1 = annot[4 * b + 1], g2 = annot[4 * b + 2], g3 = annot[4 * b + 3];
-      const Box4 an = load_anchor(anchors, a);
-      // anchors.py:168-179: GT centre/size in float32, anchors in float64
-      const float gc0 = __fdiv_rn(__fadd_rn(g0, g2), 2.0f), gc1 = __fdiv_rn(__fadd_rn(g1, g3), 2.0f);
-      const float gh = __fsub_rn(g2, g0), gw = __fsub_rn(g3, g1);
-      const double ac0 = __ddiv_rn(__dadd_rn(an.y1, an.y2), 2.0), ac1 = __ddiv_rn(__dadd_rn(an.x1, an.x2), 2.0);
-      const double ah = __dadd_rn(__dsub_rn(an.y2, an.y1), 1e-8), aw = __dadd_rn(__dsub_rn(an.x2, an.x1), 1e-8);
-      double tg[4];
-      tg[0] = ((double)gc0 - ac0) / ah;
-      tg[1] = ((double)gc1 - ac1) / aw;
-      tg[2] = log((double)gh / ah);
-      tg[3] = log((double)gw / aw);
-      const float* r = reg + e * reg_stride;
-      const double gscale = lamb_reg / ((double)B * (double)npos_row[b]);
-      float dv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double d = (double)r[k] - tg[k];
-        const double ad = fabs(d);
-        box_l += (ad < 1.0) ? 0.5 * d * d : ad - 0.5;                // SmoothL1, beta = 1 (loss.py:41,91)
-        dv[k] = (float)(gscale * fmin(fmax(d, -1.0), 1.0));
-      }
-      dr = make_float4(dv[0], dv[1], dv[2], dv[3]);
+  const float inv_np = 1.0f / (float)ws->npos_total;
+  if (PACKED) {
+    // reg points at element [0, 0, 0] of the packed buffer, d_reg likewise; rows start 16-byte aligned (A * 5 % 4 == 0)
+    const float* src = reg + ((size_t)b * A + a0) * 5;
+    float* dst = d_reg + ((size_t)b * A + a0) * 5;
+    const int nf = na * 5;                                          // floats of this block; a0 * 5 % 4 == 0
+    for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
+      if (i + 3 < nf) *reinterpret_cast<float4*>(tile + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+      else for (int k = i; k < nf; ++k) tile[k] = __ldg(src + k);
     }
+    __syncthreads();
+    LossTerms o;
+    if (a < A) {
+      const float r[4] = {tile[threadIdx.x * 5], tile[threadIdx.x * 5 + 1], tile[threadIdx.x * 5 + 2], tile[threadIdx.x * 5 + 3]};
+      const float x = tile[threadIdx.x * 5 + 4];
+      o = loss_terms(x, r, pos[(size_t)b * A + a] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg, inv_np, npos_row[b]);
+      cls_l = o.cls_l;
+      box_l = o.box_l;
+    }
+    __syncthreads();
+    if (a < A) {
+      float* q = tile + threadIdx.x * 5;
+      q[0] = o.d_reg.x; q[1] = o.d_reg.y; q[2] = o.d_reg.z; q[3] = o.d_reg.w; q[4] = o.d_att;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
+      if (i + 3 < nf) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(tile + i);
+      else for (int k = i; k < nf; ++k) dst[k] = tile[k];
+    }
+  } else if (a < A) {
+    const size_t e = (size_t)b * A + a;
+    const float* rp = reg + e * reg_stride;
+    const float r[4] = {rp[0], rp[1], rp[2], rp[3]};
+    const LossTerms o = loss_terms(att[e * att_stride], r, pos[e] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg,
+                                   inv_np, npos_row[b]);
+    cls_l = o.cls_l;
+    box_l = o.box_l;
+    d_att[e * d_att_stride] = o.d_att;
     float* dp = d_reg + e * d_reg_stride;
     if (d_reg_stride == 4) {
-      *reinterpret_cast<float4*>(dp) = dr;
+      *reinterpret_cast<float4*>(dp) = o.d_reg;
     } else {
-      dp[0] = dr.x; dp[1] = dr.y; dp[2] = dr.z; dp[3] = dr.w;
+      dp[0] = o.d_reg.x; dp[1] = o.d_reg.y; dp[2] = o.d_reg.z; dp[3] = o.d_reg.w;
     }
   }
   // block reduction -> one atomic per block and quantity
   __shared__ double red[2][8];
+  __shared__ bool last;
   cls_l = warp_sum(cls_l);
   box_l = warp_sum(box_l);
   const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
@@ -190,37 +305,58 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { c += red[0][i]; bx += red[1][i]; }
     atomicAdd(&ws->cls_sum, c);
     if (bx != 0.0) atomicAdd(&box_row[b], bx);
+    __threadfence();                                                // sums and this block's gradients before the ticket
+    last = atomicAdd(&ws->loss_ticket, 1u) == gridDim.x * gridDim.y - 1;
   }
-}
-
-__global__ void loss_finalize_kernel(LossWs* ws, const double* __restrict__ box_row, const int* __restrict__ npos_row,
-                                     int B, double lamb_reg, double* __restrict__ losses) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double box = 0.0;
-  for (int b = 0; b < B; ++b) box += box_row[b] / (double)(float)npos_row[b];
-  box /= (double)B;
-  float cls = (float)ws->cls_sum / (float)ws->npos_total;           // f32 / count, like loss.py:125
-  int bad = (box != box) || (cls != cls);
-  if (bad) { box = 0.01; cls = 1.0f; }                               // loss.py:128-133
-  ws->nan_flag = bad;
-  losses[0] = lamb_reg * box + (double)cls;
-  losses[1] = (double)cls;
-  losses[2] = box;
-}
-
-// loss.py:128-133: a NaN step carries no gradient.  Returns immediately in the normal case.
-__global__ void zero_if_nan_kernel(const LossWs* ws, float* d_att, int64_t sa, float* d_reg, int64_t sr, size_t n) {
-  if (!ws->nan_flag) return;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-    d_att[e * sa] = 0.f;
-    for (int k = 0; k < 4; ++k) d_reg[e * sr + k] = 0.f;
+  __syncthreads();
+  if (!last) return;
+  // ---- finalize (loss.py:91-143), one block ----
+  __shared__ int bad_s;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    double box = 0.0;
+    for (int i = 0; i < B; ++i) box += __ldcg(box_row + i) / (double)(float)npos_row[i];
+    box /= (double)B;
+    float cls = (float)__ldcg(&ws->cls_sum) / (float)ws->npos_total;   // f32 / count, like loss.py:125
+    const int bad = (box != box) || (cls != cls);
+    if (bad) { box = 0.01; cls = 1.0f; }                             // loss.py:128-133
+    losses[0] = lamb_reg * box + (double)cls;
+    losses[1] = (double)cls;
+    losses[2] = box;
+    bad_s = bad;
   }
+  __syncthreads();
+  if (bad_s) {
+    // loss.py:128-133: a NaN step carries no gradient (the constants above have none).  Every other block has finished
+    // (ticket), so this one may overwrite their output; rare, hence not parallelised further.
+    const size_t n = (size_t)B * A;
+    for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
+      d_att[e * d_att_stride] = 0.f;
+      for (int k = 0; k < 4; ++k) d_reg[e * d_reg_stride + k] = 0.f;
+    }
+  }
+  // leave the workspace all zero for the next call
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { box_row[i] = 0.0; npos_row[i] = 0; }
+  if (threadIdx.x == 0) { ws->cls_sum = 0.0; ws->npos_total = 0ull; ws->nan_flag = 0; ws->loss_ticket = 0u; }
 }
 
 // ---- evaluator ------------------------------------------------------------------------------
 struct ArgMaxF { float v; int i; };
-__device__ __forceinline__ ArgMaxF betterf(ArgMaxF a, ArgMaxF b) {
-  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+__device__ __forceinline__ ArgMaxF betterf(ArgMaxF a, ArgMaxF b) {   // torch.max semantics, see better()
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  const bool gt = bn ? !an : (!an && b.v > a.v);
+  const bool eq = (an && bn) || b.v == a.v;
+  return (gt || (eq && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ArgMaxF warp_argmaxf(ArgMaxF x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMaxF y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    x = betterf(x, y);
+  }
+  return x;
 }
 
 __device__ __forceinline__ Box4 decode_box(const Box4& an, const float* r) {   // anchors.py:182-197
@@ -232,65 +368,89 @@ __device__ __forceinline__ Box4 decode_box(const Box4& an, const float* r) {   /
   return {__dsub_rn(c0, hh), __dsub_rn(c1, hw), __dadd_rn(c0, hh), __dadd_rn(c1, hw)};
 }
 
-__global__ void __launch_bounds__(1024) eval_rows_kernel(const float* __restrict__ att, int64_t att_stride,
-                                                         const float* __restrict__ reg, int64_t reg_stride,
-                                                         const float* __restrict__ annot,
-                                                         const double* __restrict__ anchors,
-                                                         const float* __restrict__ img_size, int A, double thr,
-                                                         int64_t* __restrict__ best_ids, float* __restrict__ scores,
-                                                         double* __restrict__ pred_boxes, float* __restrict__ flags) {
+// grid (chunks, B) like the match pass: partial argmaxes of the IoU row and of the scores; the last chunk of a row
+// decodes the two selected boxes; the last row to finish (second ticket) averages the flags into Acc / MaxPos.
+// scratch (behind the flags in `metrics`, see zsg_eval): EvalPart[B][chunks], unsigned row_ticket[B], unsigned done.
+struct EvalPart { double iv; int ii; float sv; int si; int pad; };
+constexpr int EVAL_CHUNKS = 8;
+
+__global__ void __launch_bounds__(256) eval_rows_kernel(const float* __restrict__ att, int64_t att_stride,
+                                                        const float* __restrict__ reg, int64_t reg_stride,
+                                                        const float* __restrict__ annot,
+                                                        const double* __restrict__ anchors,
+                                                        const float* __restrict__ img_size, int A, int per_chunk,
+                                                        double thr, int64_t* __restrict__ best_ids,
+                                                        float* __restrict__ scores, double* __restrict__ pred_boxes,
+                                                        float* __restrict__ metrics, EvalPart* __restrict__ part,
+                                                        unsigned* __restrict__ tickets) {
   __shared__ ArgMaxD smd[32];
-  __shared__ ArgMaxF smf[32];
-  const int b = blockIdx.x;
+  __shared__ ArgMaxF smf[8];
+  __shared__ int last;
+  const int b = blockIdx.y, ch = blockIdx.x, nch = gridDim.x, B = gridDim.y;
+  float* flags = metrics + 2;
   const float g0 = annot[4 * b], g1 = annot[4 * b + 1], g2 = annot[4 * b + 2], g3 = annot[4 * b + 3];
-  ArgMaxD bi{-1.0, 0x7fffffff};
+  const bool row_nan = (g0 != g0) || (g1 != g1) || (g2 != g2) || (g3 != g3);
+  ArgMaxD bi{ARG_NONE, 0x7fffffff};
   ArgMaxF bs{-1.0f, 0x7fffffff};
-  for (int a = threadIdx.x; a < A; a += blockDim.x) {
-    bi = better(bi, ArgMaxD{iou_gt_anchor(g0, g1, g2, g3, load_anchor(anchors, a)), a});
+  const int a_end = min(A, (ch + 1) * per_chunk);
+  for (int a = ch * per_chunk + threadIdx.x; a < a_end; a += blockDim.x) {
+    bi = better(bi, ArgMaxD{iou_match(g0, g1, g2, g3, load_anchor(anchors, a), row_nan), a});
     const float x = att[((size_t)b * A + a) * att_stride];
     bs = betterf(bs, ArgMaxF{1.0f / (1.0f + expf(-x)), a});          // evaluator.py:74-75
   }
   bi = block_argmax(bi, smd);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ArgMaxF y;
-    y.v = __shfl_xor_sync(0xffffffffu, bs.v, o);
-    y.i = __shfl_xor_sync(0xffffffffu, bs.i, o);
-    bs = betterf(bs, y);
-  }
+  bs = warp_argmaxf(bs);
   if ((threadIdx.x & 31) == 0) smf[threadIdx.x >> 5] = bs;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) bs = betterf(bs, smf[w]);
-    const Box4 bx = decode_box(load_anchor(anchors, bs.i), reg + ((size_t)b * A + bs.i) * reg_stride);
-    const Box4 mx = decode_box(load_anchor(anchors, bi.i), reg + ((size_t)b * A + bi.i) * reg_stride);
-    flags[b] = iou_box_gt(bx, g0, g1, g2, g3) >= thr ? 1.f : 0.f;
-    flags[gridDim.x + b] = iou_box_gt(mx, g0, g1, g2, g3) >= thr ? 1.f : 0.f;
-    best_ids[b] = bs.i;
-    scores[b] = bs.v;
-    // evaluator.py:96-97: ((box+1)/2) * (h,w), then y1x1y2x2 -> x1y1x2y2
-    const double h = (double)img_size[2 * b], w = (double)img_size[2 * b + 1];
-    const double py1 = __dmul_rn(h, __ddiv_rn(__dadd_rn(bx.y1, 1.0), 2.0)), px1 = __dmul_rn(w, __ddiv_rn(__dadd_rn(bx.x1, 1.0), 2.0));
-    const double py2 = __dmul_rn(h, __ddiv_rn(__dadd_rn(bx.y2, 1.0), 2.0)), px2 = __dmul_rn(w, __ddiv_rn(__dadd_rn(bx.x2, 1.0), 2.0));
-    double* o = pred_boxes + 4 * b;
-    o[0] = px1; o[1] = py1; o[2] = px2; o[3] = py2;
+    part[b * EVAL_CHUNKS + ch] = EvalPart{bi.v, bi.i, bs.v, bs.i, 0};
+    __threadfence();
+    last = atomicAdd(&tickets[b], 1u) == (unsigned)nch - 1;
+    if (last) {
+      __threadfence();
+      const volatile EvalPart* q = part + b * EVAL_CHUNKS;
+      bi = ArgMaxD{ARG_NONE, 0x7fffffff};
+      bs = ArgMaxF{-1.0f, 0x7fffffff};
+      for (int c = 0; c < nch; ++c) {
+        bi = better(bi, ArgMaxD{q[c].iv, q[c].ii});
+        bs = betterf(bs, ArgMaxF{q[c].sv, q[c].si});
+      }
+      const int si = min(max(bs.i, 0), A - 1), ii = min(max(bi.i, 0), A - 1);
+      const Box4 bx = decode_box(load_anchor(anchors, si), reg + ((size_t)b * A + si) * reg_stride);
+      const Box4 mx = decode_box(load_anchor(anchors, ii), reg + ((size_t)b * A + ii) * reg_stride);
+      flags[b] = iou_box_gt(bx, g0, g1, g2, g3) >= thr ? 1.f : 0.f;
+      flags[B + b] = iou_box_gt(mx, g0, g1, g2, g3) >= thr ? 1.f : 0.f;
+      best_ids[b] = si;
+      scores[b] = bs.v;
+      // evaluator.py:96-97: ((box+1)/2) * (h,w), then y1x1y2x2 -> x1y1x2y2
+      const double h = (double)img_size[2 * b], w = (double)img_size[2 * b + 1];
+      const double py1 = __dmul_rn(h, __ddiv_rn(__dadd_rn(bx.y1, 1.0), 2.0)), px1 = __dmul_rn(w, __ddiv_rn(__dadd_rn(bx.x1, 1.0), 2.0));
+      const double py2 = __dmul_rn(h, __ddiv_rn(__dadd_rn(bx.y2, 1.0), 2.0)), px2 = __dmul_rn(w, __ddiv_rn(__dadd_rn(bx.x2, 1.0), 2.0));
+      double* o = pred_boxes + 4 * b;
+      o[0] = px1; o[1] = py1; o[2] = px2; o[3] = py2;
+      tickets[b] = 0;
+      __threadfence();
+      if (atomicAdd(&tickets[B], 1u) == (unsigned)B - 1) {           // last row: the two means (evaluator.py:108-117)
+        __threadfence();
+        float acc = 0.f, mp = 0.f;
+        for (int i = 0; i < B; ++i) { acc += __ldcg(flags + i); mp += __ldcg(flags + B + i); }
+        metrics[0] = acc / (float)B;
+        metrics[1] = mp / (float)B;
+        tickets[B] = 0;
+      }
+    }
   }
-}
-
-__global__ void eval_finalize_kernel(const float* __restrict__ flags, int B, float* __restrict__ metrics) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float a = 0.f, m = 0.f;
-  for (int b = 0; b < B; ++b) { a += flags[b]; m += flags[B + b]; }
-  metrics[0] = a / (float)B;
-  metrics[1] = m / (float)B;
 }
 
 }  // namespace zsg
 
 using namespace zsg;
 
-extern "C" size_t zsg_match_loss_workspace_bytes(int b) {
-  return sizeof(LossWs) + (size_t)b * (sizeof(double) + sizeof(int)) + 16;
+extern "C" size_t zsg_match_loss_workspace_bytes(int b) { return ws_total(b < 1 ? 1 : b); }
+
+extern "C" size_t zsg_eval_workspace_bytes(int b) {
+  return (size_t)(b < 1 ? 1 : b) * EVAL_CHUNKS * sizeof(EvalPart) + ((size_t)b + 1) * sizeof(unsigned) + 16;
 }
 
 extern "C" int zsg_match_loss(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride,
@@ -301,35 +461,52 @@ extern "C" int zsg_match_loss(const float* att, int64_t att_stride, const float*
   ZSG_REQUIRE(att && reg && annot && anchors && losses && d_att && d_reg && top1 && pos && workspace,
               "zsg_match_loss: null pointer");
   ZSG_REQUIRE(b > 0 && a > 0, "zsg_match_loss: empty batch (b=%d a=%d)", b, a);
+  ZSG_REQUIRE(b <= 65535, "zsg_match_loss: batch %d exceeds the grid limit", b);
   ZSG_REQUIRE(ws_bytes >= zsg_match_loss_workspace_bytes(b), "zsg_match_loss: workspace too small");
+  ZSG_REQUIRE(((uintptr_t)workspace & 15) == 0, "zsg_match_loss: workspace must be 16-byte aligned");
   ZSG_REQUIRE(((uintptr_t)anchors & 15) == 0, "zsg_match_loss: anchors must be 16-byte aligned");
   ZSG_REQUIRE(d_reg_stride != 4 || ((uintptr_t)d_reg & 15) == 0, "zsg_match_loss: d_reg must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
-  LossWs* ws = reinterpret_cast<LossWs*>(workspace);
-  double* box_row = reinterpret_cast<double*>(ws + 1);
-  int* npos_row = reinterpret_cast<int*>(box_row + b);
-  cudaMemsetAsync(workspace, 0, zsg_match_loss_workspace_bytes(b), st);
-  match_rows_kernel<<<b, 1024, 0, st>>>(annot, anchors, a, match_thr, use_multi, pos, top1, ws, npos_row);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+  // chunks per row: enough CTAs for ~4 per SM, at most MATCH_MAX_CHUNKS, at least 256 anchors each
+  int nch = (num_sms() * 4 + b - 1) / b;
+  if (nch > MATCH_MAX_CHUNKS) nch = MATCH_MAX_CHUNKS;
+  if (nch > (a + 255) / 256) nch = (a + 255) / 256;
+  if (nch < 1) nch = 1;
+  const int per_chunk = (a + nch - 1) / nch;
+  nch = (a + per_chunk - 1) / per_chunk;
+  match_rows_kernel<<<dim3(nch, b), 256, 0, st>>>(annot, anchors, a, per_chunk, match_thr, use_multi, pos, top1, wsb, b);
   dim3 grid((a + 255) / 256, b);
-  loss_grad_kernel<<<grid, 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma,
-                                         lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, ws, box_row, npos_row);
-  loss_finalize_kernel<<<1, 32, 0, st>>>(ws, box_row, npos_row, b, lamb_reg, losses);
-  zero_if_nan_kernel<<<num_sms(), 256, 0, st>>>(ws, d_att, d_att_stride, d_reg, d_reg_stride, (size_t)b * a);
+  const bool packed = att_stride == 5 && reg_stride == 5 && d_att_stride == 5 && d_reg_stride == 5 && att == reg + 4 &&
+                      d_att == d_reg + 4 && ((((uintptr_t)reg | (uintptr_t)d_reg) & 15) == 0) && (a % 4 == 0);
+  if (packed)
+    loss_grad_kernel<true><<<grid, 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma,
+                                                 lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb, losses);
+  else
+    loss_grad_kernel<false><<<grid, 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma,
+                                                  lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb, losses);
   return check_launch("zsg_match_loss");
 }
 
 extern "C" int zsg_eval(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride,
                         const float* annot, const double* anchors, const float* img_size, int b, int a,
                         double iou_thr, int64_t* best_ids, float* pred_scores, double* pred_boxes, float* metrics,
-                        zsg_stream_t stream) {
-  ZSG_REQUIRE(att && reg && annot && anchors && img_size && best_ids && pred_scores && pred_boxes && metrics,
+                        void* workspace, size_t ws_bytes, zsg_stream_t stream) {
+  ZSG_REQUIRE(att && reg && annot && anchors && img_size && best_ids && pred_scores && pred_boxes && metrics && workspace,
               "zsg_eval: null pointer");
-  ZSG_REQUIRE(b > 0 && a > 0, "zsg_eval: empty batch");
+  ZSG_REQUIRE(b > 0 && a > 0 && b <= 65535, "zsg_eval: bad batch");
+  ZSG_REQUIRE(ws_bytes >= zsg_eval_workspace_bytes(b) && ((uintptr_t)workspace & 15) == 0, "zsg_eval: workspace too small or misaligned");
   cudaStream_t st = as_stream(stream);
+  int nch = (num_sms() * 2 + b - 1) / b;
+  if (nch > EVAL_CHUNKS) nch = EVAL_CHUNKS;
+  if (nch > (a + 255) / 256) nch = (a + 255) / 256;
+  if (nch < 1) nch = 1;
+  const int per_chunk = (a + nch - 1) / nch;
+  nch = (a + per_chunk - 1) / per_chunk;
+  EvalPart* part = reinterpret_cast<EvalPart*>(workspace);
+  unsigned* tickets = reinterpret_cast<unsigned*>(part + (size_t)b * EVAL_CHUNKS);
   // flags live behind the two metrics: metrics must hold 2 + 2*b floats
-  float* flags = metrics + 2;
-  eval_rows_kernel<<<b, 1024, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, img_size, a, iou_thr,
-                                       best_ids, pred_scores, pred_boxes, flags);
-  eval_finalize_kernel<<<1, 32, 0, st>>>(flags, b, metrics);
+  eval_rows_kernel<<<dim3(nch, b), 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, img_size, a, per_chunk,
+                                                 iou_thr, best_ids, pred_scores, pred_boxes, metrics, part, tickets);
   return check_launch("zsg_eval");
 }

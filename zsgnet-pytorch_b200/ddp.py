@@ -2,9 +2,12 @@
 
 One process per GPU.  Parameters and gradients live in flat arenas ordered by backward completion,
 so a gradient bucket is a contiguous slice: as soon as the engine reports a slice final, it is
-all-reduced with NCCL (NVLink 5 / NVSwitch) on a side stream while the backward continues.  The 1/N
-averaging is folded into the Adam kernel (grad_scale), so no extra pass touches the gradients.
-BatchNorm statistics stay per rank, like the reference's non-synchronised BatchNorm."""
+all-reduced with NCCL (NVLink 5 / NVSwitch) on a side stream while the backward continues.  The
+reduction is an AVERAGE (NCCL's ReduceOp.AVG: the 1/N is applied inside the collective, no extra pass
+touches the gradients), exactly what DistributedDataParallel leaves in param.grad (main_dist.py:36-40),
+so any optimiser -- this repo's FusedAdam or a stock torch.optim.Adam over the arena views -- sees the
+same gradients as under the reference.  BatchNorm statistics stay per rank, like the reference's
+non-synchronised BatchNorm."""
 import torch
 import torch.distributed as dist
 
@@ -22,7 +25,8 @@ class GradReducer:
 
     @property
     def grad_scale(self):
-        return 1.0 / self.world
+        """Factor the optimiser still has to apply to the arena gradients: none, the collective averages."""
+        return 1.0
 
     def on_bucket(self, lo, hi):
         """Engine callback: grad_arena[lo:hi] is final (called in increasing arena order)."""
@@ -38,14 +42,14 @@ class GradReducer:
         buf = self.store.grad_arena[lo:hi]
         self.bytes_reduced += buf.numel() * 4
         self.calls += 1
-        if self.comm_stream is None:                      # gloo / CPU tests
-            self._works.append(dist.all_reduce(buf, group=self.group, async_op=True))
+        if self.comm_stream is None:                      # gloo / CPU tests: no AVG there, divide after the wait
+            self._works.append((dist.all_reduce(buf, group=self.group, async_op=True), buf))
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(buf, group=self.group)        # NCCL: enqueued on comm_stream, overlaps the backward
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)   # NCCL: enqueued on comm_stream, overlaps the backward
 
     def finish(self):
         """Make the compute stream wait for every outstanding all-reduce (call before the optimiser)."""
@@ -54,8 +58,9 @@ class GradReducer:
         if self._lo is not None:
             self._launch(self._lo, self.store.used)
             self._lo = None
-        for w in self._works:
+        for w, buf in self._works:
             w.wait()
+            buf.div_(self.world)
         self._works = []
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)

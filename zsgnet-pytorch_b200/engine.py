@@ -7,6 +7,8 @@ and their gradients live in two flat arenas (ParamStore) laid out in backward-co
 so gradient buckets for the NCCL all-reduce are contiguous slices that become final one after
 the other while the backward is still running.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -85,8 +87,14 @@ class _BN:
 
 
 class Engine:
-    def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC):
+    def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC, dtype="fp32"):
         self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
+        assert dtype in ("fp32", "bf16"), dtype
+        # dtype = arithmetic of the dense contractions.  "fp32": 3xTF32 (BASELINE configs[1], the reference's fp32 results to
+        # 1e-4).  "bf16": bf16 operand images, one kind::f16 MMA per product, fp32 accumulation (configs[2..4], "bf16
+        # tensor-core convs"); tensors stay fp32 in HBM, only the GEMM operand images are bf16.  Contractions whose channel
+        # count is not a multiple of 8 (the 3-channel stem, the 300-wide LSTM projection) keep the fp32 path.
+        self.dtype, self.bf16 = dtype, dtype == "bf16"
         self.model = store.model
         self._rows_cache = {}
         self._operand_cache, self._bwd_lo = {}, {}
@@ -104,17 +112,38 @@ class Engine:
         self.arena_hi, self.arena_lo = self.buf(store.total), self.buf(store.total)
         self.pool_n = 44 << 20
         self.pool, self.pool_hi, self.pool_lo = self.buf(self.pool_n), self.buf(self.pool_n), self.buf(self.pool_n)
+        self.arena_b16 = self.img(store.total) if self.bf16 else None      # bf16 images of the same weights
+        self.pool_b16 = self.img(self.pool_n) if self.bf16 else None
         self._pool_used, self._pool_f_end = 0, None
         self._wtf = []
         self._bn_tickets = torch.zeros(64, dtype=torch.int32, device=device)
         self.prep_fwd = []
+        # CUDA graphs: the program is a fixed list of launches over static buffers, so the forward pass and each backward
+        # segment (the ops between two gradient buckets) are captured once and replayed as ONE launch each: ~700 ctypes
+        # calls and ~190 ATen ops per step issued from one Python thread become a handful (the step was
+        # host-bound at 8 ranks).  ZSG_GRAPHS=0 runs every launch eagerly (debugging, per-launch profiling).
+        self.use_graphs = self._side_stream is not None and os.environ.get("ZSG_GRAPHS", "1") != "0"
+        self._graphs = {}
+        self.bucket_elems = 4 << 20                      # gradient buckets are coalesced to at least this many elements
         self._build()
+        self._plan_segments()
 
     # ------------------------------------------------------------------ allocation helpers
     def buf(self, *shape, zero=False):
         t = (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device=self.device)
         self.nbytes += t.numel() * 4
         return t
+
+    def img(self, *shape, b16=True):
+        """Storage of a GEMM operand image: bfloat16 copy (bf16 path) or float32 TF32 remainder."""
+        if not b16:
+            return self.buf(*shape)
+        t = torch.empty(*shape, dtype=torch.bfloat16, device=self.device)
+        self.nbytes += t.numel() * 2
+        return t
+
+    def use_b16(self, cin):
+        return self.bf16 and cin % 8 == 0 and self.impl == ops.IMPL_TC
 
     def f32(self, n):
         return torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -126,46 +155,58 @@ class Engine:
         return self._f64_pool[o:o + n]
 
     def pool_alloc(self, n):
-        """(w, hi, lo) views of n floats from the transformed-weight pool."""
+        """(w, hi, lo, b16) views of n elements from the transformed-weight pool (b16 is None on the fp32 engine)."""
         o = self._pool_used
         self._pool_used += _align(n)
         assert self._pool_used <= self.pool_n, "transformed-weight pool too small"
-        return self.pool[o:o + n], self.pool_hi[o:o + n], self.pool_lo[o:o + n]
+        return (self.pool[o:o + n], self.pool_hi[o:o + n], self.pool_lo[o:o + n],
+                self.pool_b16[o:o + n] if self.bf16 else None)
 
     def arena_split_views(self, wname):
         o, n = self.store.offsets[wname], self.store.numel(wname)
         return self.arena_hi[o:o + n], self.arena_lo[o:o + n]
+
+    def weight_operand(self, w, b16):
+        """(w, w_lo) arguments of a ConvOp: TF32 (hi, lo) images, or (fp32 weights, bf16 image) on the bf16 path.
+        w = parameter name, or a pool_alloc() tuple."""
+        if isinstance(w, str):
+            if b16:
+                o, n = self.store.offsets[w], self.store.numel(w)
+                return self.store.flat(w), self.arena_b16[o:o + n]
+            return self.arena_split_views(w)
+        return (w[0], w[3]) if b16 else (w[1], w[2])
 
     # ------------------------------------------------------------------ GEMM operand images
     # Every tensor that feeds an implicit GEMM is given its TF32 remainder image (`lo`) by one elementwise pass
     # (zsg_split_act); when the consumer needs a BatchNorm affine / ReLU on load, the same pass materialises
     # z = relu(x * scale + shift).  The GEMM kernels then move (z, lo) global -> shared with cp.async, no register
     # pass (csrc/conv_tc.cu: conv_tc_async_kernel, wgrad_tc_async_kernel).
-    def fwd_operand(self, x, nrows, c, pro=None, relu=False):
-        """(z, lo) of a forward conv input; the split launch is appended to the forward program once per tensor."""
-        key = (x.data_ptr(), nrows, c, id(pro), bool(relu))
+    def fwd_operand(self, x, nrows, c, pro=None, relu=False, b16=False):
+        """(z, image) of a forward conv input; the split / cast launch is appended to the forward program once per
+        tensor.  b16: the image is the bf16 copy of relu?(bn(x)) and z is not materialised (z = x, unused by the GEMMs)."""
+        key = (x.data_ptr(), nrows, c, id(pro), bool(relu), bool(b16))
         if key not in self._operand_cache:
-            need_z = pro is not None or relu
+            need_z = (pro is not None or relu) and not b16
             z = self.buf(nrows, c) if need_z else x
-            lo = self.buf(nrows, c)
+            lo = self.img(nrows, c, b16=b16)
             sc, sh = (pro.scale, pro.shift) if pro is not None else (None, None)
             self.fwd.append(("fn", lambda: ops.split_act(x, lo, nrows, c, scale=sc, shift=sh, relu=relu,
                                                          z=z if need_z else None)))
             self._operand_cache[key] = (z, lo)
         return self._operand_cache[key]
 
-    def bwd_lo_buffer(self, dy, nrows, c):
-        """Storage for the lo image of a gradient tensor (one per scratch buffer, sized for its largest user)."""
+    def bwd_lo_buffer(self, dy, nrows, c, b16=False):
+        """Storage for the operand image of a gradient tensor (one per scratch buffer, sized for its largest user)."""
         n = nrows * c
-        key = dy.data_ptr()
+        key = (dy.data_ptr(), bool(b16))
         if key not in self._bwd_lo or self._bwd_lo[key].numel() < n:
-            self._bwd_lo[key] = self.buf(n)
+            self._bwd_lo[key] = self.img(n, b16=b16)
         return self._bwd_lo[key][:n]
 
-    def bwd_operand(self, dy, nrows, c):
-        """lo image of a gradient tensor; appends the split launch to the backward program (call it right after
-        the kernel that produced dy -- scratch buffers are reused, so nothing is cached across calls)."""
-        lo = self.bwd_lo_buffer(dy, nrows, c)
+    def bwd_operand(self, dy, nrows, c, b16=False):
+        """operand image of a gradient tensor; appends the split / cast launch to the backward program (call it right
+        after the kernel that produced dy -- scratch buffers are reused, so nothing is cached across calls)."""
+        lo = self.bwd_lo_buffer(dy, nrows, c, b16)
         self.bwd.append(lambda: ops.split_act(dy, lo, nrows, c))
         return lo
 
@@ -207,12 +248,10 @@ class Engine:
         span = dil * (k - 1) + 1
         hout, wout = (hin + 2 * pad - span) // stride + 1, (win + 2 * pad - span) // stride + 1
         rows = self.rows("fwd", hin, win, cin, hout, wout, cout, stride, pad)
-        if w is None:
-            w = self.store.flat(wname)
-            w_hi, w_lo = self.arena_split_views(wname)
-        else:
-            w, w_hi, w_lo = w                                # a (w, hi, lo) triple from the pool
-        xz, x_lo = self.fwd_operand(x, self.B * hin * win, cin, pro=pro, relu=in_relu)
+        b16 = self.use_b16(cin)
+        w_hi, w_lo = self.weight_operand(wname if w is None else w, b16)
+        w = self.store.flat(wname) if w is None else w[0]     # fp32 weights (dgrad prep)
+        xz, x_lo = self.fwd_operand(x, self.B * hin * win, cin, pro=pro, relu=in_relu, b16=b16)
         part = None
         if stats:                                            # BatchNorm statistics as a by-product of the epilogue
             parts = (self.B * hout * wout + 127) // 128 * 4
@@ -222,7 +261,7 @@ class Engine:
                     w_lo=w_lo, x_lo=x_lo, dil=dil, stats=part[0] if part else None)
         self.fwd.append(("op", op))
         return dict(stats=part, wname=wname, x=x, xz=xz, x_lo=x_lo, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
-                    hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w, dil=dil)   # w: fp32 weights (dgrad prep)
+                    hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w, dil=dil, b16=b16)
 
     def conv_wgrad(self, L, dy, dy_lo, dw=None):
         dw = self.store.grad_flat(L["wname"]) if dw is None else dw
@@ -230,12 +269,16 @@ class Engine:
                                 L["k"], impl=self.impl, x_lo=L["x_lo"], dy_lo=dy_lo, dy_pitch=L["cout"], dil=L["dil"]))
 
     def grad_operand(self, L, dy):
-        """lo image of the output gradient of conv L (shared by its wgrad and dgrad)."""
-        return self.bwd_operand(dy, self.B * L["hout"] * L["wout"], L["cout"])
+        """operand image of the output gradient of conv L (shared by its wgrad and dgrad; bf16 iff the conv is)."""
+        return self.bwd_operand(dy, self.B * L["hout"] * L["wout"], L["cout"], b16=L["b16"])
 
     def conv_dgrad(self, L, dy, dy_lo, dx, out_mask=None, residual=None, accumulate=False):
         k, cin, cout, stride = L["k"], L["cin"], L["cout"], L["stride"]
-        wt, wt_hi, wt_lo = self.pool_alloc(cin * k * k * cout)
+        b16 = L["b16"]
+        assert not b16 or cout % 8 == 0, "bf16 data gradient needs cout % 8 == 0"
+        wt_t = self.pool_alloc(cin * k * k * cout)
+        wt = wt_t[0]
+        wt_hi, wt_lo = self.weight_operand(wt_t, b16)
         w = L["w"]
         self.queue_transpose(w, wt, cout, k, cin)
         epi = dict(out_mask=out_mask, residual=residual, accumulate=accumulate, impl=self.impl)
@@ -247,7 +290,9 @@ class Engine:
                 for ex in (0, 1):
                     sr, sc_ = (slice(1, 2), slice(0, 3, 2))[ey], (slice(1, 2), slice(0, 3, 2))[ex]
                     kr, ks = 1 + ey, 1 + ex
-                    wc, wc_hi, wc_lo = self.pool_alloc(cin * kr * ks * cout)
+                    wc_t = self.pool_alloc(cin * kr * ks * cout)
+                    wc = wc_t[0]
+                    wc_hi, wc_lo = self.weight_operand(wc_t, b16)
                     self.prep_bwd.append(lambda wc=wc, sr=sr, sc_=sc_, kr=kr, ks=ks:
                                          wc.view(cin, kr, ks, cout).copy_(wt4[:, sr, sc_, :]))
                     key = ("dgrad_s2", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, ey, ex)
@@ -280,9 +325,9 @@ class Engine:
         else:
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w, wt, cout, k, k, cin))
 
-    def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True):
-        """BatchNorm backward; returns the lo image of dx (written by the same kernel) for the GEMMs that follow."""
-        dx_lo = self.bwd_lo_buffer(dx, bn.rows, bn.c) if want_lo else None
+    def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True, b16=False):
+        """BatchNorm backward; returns the operand image of dx (written by the same kernel) for the GEMMs that follow."""
+        dx_lo = self.bwd_lo_buffer(dx, bn.rows, bn.c, b16) if want_lo else None
 
         def run():
             ops.bn_bwd_reduce(dy, x, bn.mean, bn.invstd, bn.bsums, bn.rows, bn.c, mask_mode=mask_mode, scale=bn.scale,
@@ -346,7 +391,7 @@ class Engine:
         # ---------------- stem: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2 (mdl.py:149-152)
         img4 = self.buf(B, 300, 300, 4)
         w1p_t = self.pool_alloc(64 * 49 * 4)
-        w1p, dw1p = w1p_t[0], self.buf(64 * 49 * 4)
+        w1p, dw1p = w1p_t[0], self.buf(64 * 49 * 4)           # (cin = 4: this conv keeps the fp32 path on the bf16 engine)
         c1 = self.buf(B * 150 * 150, 64)
         x0 = self.buf(B * 75 * 75, 64)
         w1 = st.flat(e + "conv1.weight")
@@ -365,7 +410,7 @@ class Engine:
 
         def stem_bwd():
             self.bwd.append(lambda: ops.maxpool_bn_relu_bwd(pool_arg, g_x0, da_stem, B, 150, 150, 64, 75, 75))
-            lo_stem = self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1)
+            lo_stem = self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1, b16=Lstem["b16"])
             self.bwd.append(lambda: dw1p.zero_())
             self.conv_wgrad(Lstem, da_stem, lo_stem, dw=dw1p)
             self.bwd.append(lambda: ops.pad_channels(dw1p, g1, 64 * 49, 4, 3))
@@ -399,8 +444,9 @@ class Engine:
                     bnD = self.add_bn(p + "downsample.1", 4 * width, ro)
                     self.bn_forward(bnD, rd, Ld)
 
-                out_lo = self.buf(ro, 4 * width)              # operand image of the block output, written by the tail
-                self._operand_cache[(out.data_ptr(), ro, 4 * width, id(None), False)] = (out, out_lo)
+                ob16 = self.use_b16(4 * width)
+                out_lo = self.img(ro, 4 * width, b16=ob16)    # operand image of the block output, written by the tail
+                self._operand_cache[(out.data_ptr(), ro, 4 * width, id(None), False, ob16)] = (out, out_lo)
 
                 def tail(r3=r3, bnC=bnC, rd=rd, bnD=bnD, inp=inp, out=out, ro=ro, c=4 * width, out_lo=out_lo):
                     if rd is not None:
@@ -422,17 +468,18 @@ class Engine:
                 L = blocks[k]
                 ro, ri, w4, w = L["ro"], L["ri"], 4 * L["width"], L["width"]
                 dz, dr3, da2, da1 = sA[:ro * w4], sB[:ro * w4], sC[:ro * w], sD[:ri * w]
-                lo3 = self.bn_backward(L["bnC"], L["g_out"], L["r3"], dr3, mask_mode=2, act_out=L["out"], dz_out=dz)
+                lo3 = self.bn_backward(L["bnC"], L["g_out"], L["r3"], dr3, mask_mode=2, act_out=L["out"], dz_out=dz,
+                                       b16=L["Lc"]["b16"])
                 self.conv_wgrad(L["Lc"], dr3, lo3)
                 self.conv_dgrad(L["Lc"], dr3, lo3, da2)
-                lo2 = self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1)
+                lo2 = self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1, b16=L["Lb"]["b16"])
                 self.conv_wgrad(L["Lb"], da2, lo2)
                 self.conv_dgrad(L["Lb"], da2, lo2, da1)
-                lo1 = self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1)
+                lo1 = self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1, b16=L["La"]["b16"])
                 self.conv_wgrad(L["La"], da1, lo1)
                 if L["Ld"] is not None:
                     drd = sB[:ro * w4]
-                    lod = self.bn_backward(L["bnD"], dz, L["rd"], drd, mask_mode=0)
+                    lod = self.bn_backward(L["bnD"], dz, L["rd"], drd, mask_mode=0, b16=L["Ld"]["b16"])
                     self.conv_wgrad(L["Ld"], drd, lod)
                     self.conv_dgrad(L["La"], da1, lo1, L["g_in"], accumulate=L["acc_in"])      # writes every pixel
                     self.conv_dgrad(L["Ld"], drd, lod, L["g_in"], accumulate=True)            # stride 2: even pixels only
@@ -702,18 +749,20 @@ class Engine:
         rows_f520, rows_f256 = head_rows("fwd", CP, 256), head_rows("fwd", 256, 256)
         rows_last, rows_f48 = head_rows("fwd", 256, 45, scatter=True), head_rows("fwd", 256, 48)
         rows_d520, rows_d256, rows_d48 = head_rows("dgrad", CP, 256), head_rows("dgrad", 256, 256), head_rows("dgrad", 256, 48)
-        _, fused_lo = self.fwd_operand(fused, M, CP)
-        self.fwd.append(("op", ConvOp(fused, w0p_t[1], hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
-                                      impl=self.impl, w_lo=w0p_t[2], x_lo=fused_lo)))
+        hb16 = self.use_b16(256)                             # every head contraction has channel counts % 8 == 0
+        _, fused_lo = self.fwd_operand(fused, M, CP, b16=hb16)
+        w0h, w0l = self.weight_operand(w0p_t, hb16)
+        self.fwd.append(("op", ConvOp(fused, w0h, hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
+                                      impl=self.impl, w_lo=w0l, x_lo=fused_lo)))
         hs_lo = []
         for i in range(1, 5):
-            wh, wl = self.arena_split_views(f"att_reg_box.{i}.0.weight")
-            hs_lo.append(self.fwd_operand(hs[i - 1], M, 256)[1])
+            wh, wl = self.weight_operand(f"att_reg_box.{i}.0.weight", hb16)
+            hs_lo.append(self.fwd_operand(hs[i - 1], M, 256, b16=hb16)[1])
             self.fwd.append(("op", ConvOp(hs[i - 1], wh, hs[i], rows_f256, M, 256, 256, 3, 3, bias=hb(i), out_relu=True,
                                           impl=self.impl, w_lo=wl, x_lo=hs_lo[-1])))
-        hs_lo.append(self.fwd_operand(hs[4], M, 256)[1])
+        hs_lo.append(self.fwd_operand(hs[4], M, 256, b16=hb16)[1])
         w5 = st.flat("att_reg_box.5.weight")
-        w5h, w5l = self.arena_split_views("att_reg_box.5.weight")
+        w5h, w5l = self.weight_operand("att_reg_box.5.weight", hb16)
         self.fwd.append(("op", ConvOp(hs[4], w5h, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
                                       impl=self.impl, w_lo=w5l, x_lo=hs_lo[4])))
         self.d_out = self.buf(B, A, 5)
@@ -733,31 +782,34 @@ class Engine:
             self.bwd.append(lambda: ops.gather_rows(d_out, rows_last, dy5, M, 45, 48))
             self.bwd.append(lambda: ops.colsum(dy5, tmp48, M, 48))
             self.bwd.append(lambda: st.grad_flat("att_reg_box.5.bias").copy_(tmp48[:45]))
-            dy5_lo = self.bwd_operand(dy5, M, 48)
+            dy5_lo = self.bwd_operand(dy5, M, 48, b16=hb16)
             self.bwd.append(WgradOp(hs[4], dy5, st.grad_flat("att_reg_box.5.weight"), rows_f48, M, 256, 45, 3, 3,
                                     impl=self.impl, x_lo=hs_lo[4], dy_lo=dy5_lo, dy_pitch=48))
-            self.bwd.append(ConvOp(dy5, wt5p_t[1], dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl,
-                                   w_lo=wt5p_t[2], x_lo=dy5_lo))
+            wt5h, wt5l = self.weight_operand(wt5p_t, hb16)
+            self.bwd.append(ConvOp(dy5, wt5h, dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl,
+                                   w_lo=wt5l, x_lo=dy5_lo))
             for i in range(4, 0, -1):
                 wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i][0]
                 self.queue_transpose(wi, wti, 256, 3, 256)
                 gb = st.grad_flat(f"att_reg_box.{i}.0.bias")
                 self.bwd.append(lambda i=i, gb=gb: ops.colsum(dhs[i], gb, M, 256))
-                dlo = self.bwd_operand(dhs[i], M, 256)
+                dlo = self.bwd_operand(dhs[i], M, 256, b16=hb16)
                 self.bwd.append(WgradOp(hs[i - 1], dhs[i], st.grad_flat(f"att_reg_box.{i}.0.weight"), rows_f256, M, 256,
                                         256, 3, 3, impl=self.impl, x_lo=hs_lo[i - 1], dy_lo=dlo, dy_pitch=256))
-                self.bwd.append(ConvOp(dhs[i], wts[i][1], dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
-                                       impl=self.impl, w_lo=wts[i][2], x_lo=dlo))
+                wth, wtl = self.weight_operand(wts[i], hb16)
+                self.bwd.append(ConvOp(dhs[i], wth, dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
+                                       impl=self.impl, w_lo=wtl, x_lo=dlo))
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
             gb0 = st.grad_flat("att_reg_box.0.0.bias")
             self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
             self.bwd.append(lambda: dw0p.zero_())
-            d0lo = self.bwd_operand(dhs[0], M, 256)
+            d0lo = self.bwd_operand(dhs[0], M, 256, b16=hb16)
             self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl, x_lo=fused_lo, dy_lo=d0lo,
                                     dy_pitch=256))
             g0 = st.grad_flat("att_reg_box.0.0.weight")
             self.bwd.append(lambda: ops.pad_channels(dw0p, g0, 256 * 9, CP, spec.FUSED_C))
-            self.bwd.append(ConvOp(dhs[0], wt0_t[1], dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0_t[2],
+            wt0h, wt0l = self.weight_operand(wt0_t, hb16)
+            self.bwd.append(ConvOp(dhs[0], wt0h, dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0l,
                                    x_lo=d0lo))
             self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
         bwd_stages.append(head_bwd)
@@ -787,7 +839,28 @@ class Engine:
         hc = torch.stack([h0[0][inv_perm_cpu], c0[0][inv_perm_cpu], h0[1][inv_perm_cpu], c0[1][inv_perm_cpu]])
         self.h0c0.copy_(hc, non_blocking=True)
 
+    def _graphed(self, key, fn):
+        """Run fn() -- a fixed sequence of launches over static buffers -- as a CUDA graph: the first call runs eagerly (one-time
+        initialisation inside the library: function attributes), the second captures, every later one replays."""
+        if not self.use_graphs or ops.PROFILER is not None:
+            return fn()
+        key = key + (self.overlap_wgrad, self.overlap_lstm)
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs[key] = "warm"
+            return fn()
+        if g == "warm":
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                fn()
+            self._graphs[key] = g
+        g.replay()
+
     def forward(self, training=True):
+        self._graphed(("fwd", bool(training)), lambda: self._forward_eager(training))
+        return self.out                                   # num_batches_tracked is bumped by the caller (one op for all)
+
+    def _forward_eager(self, training=True):
         if training:
             self._f64_pool[:self._f64_used].zero_()
             self._bn_tickets.zero_()                      # self-resetting, but a step aborted mid-kernel must not poison the next
@@ -796,6 +869,9 @@ class Engine:
         ops.split_tf32(self.store.param_arena, self.arena_hi, self.arena_lo, self.store.total)
         fe = self._pool_f_end
         ops.split_tf32(self.pool, self.pool_hi, self.pool_lo, fe)
+        if self.bf16:
+            ops.cast_bf16(self.store.param_arena, self.arena_b16, self.store.total)
+            ops.cast_bf16(self.pool, self.pool_b16, fe)
         def run(item):
             if item[0] == "bn":
                 (item[1] if training else item[2])()
@@ -822,32 +898,41 @@ class Engine:
             if i == hi and side is not None:
                 main.wait_event(done)
             run(item)
-        return self.out                                   # num_batches_tracked is bumped by the caller (one op for all)
 
-    def backward(self, d_out=None, on_bucket=None):
-        """d_out: [B,A,5] gradient of the packed head output (copied into the static buffer unless it already
-        is self.d_out).  on_bucket(lo, hi) is called as soon as grad_arena[lo:hi] is final."""
-        if d_out is not None and d_out.data_ptr() != self.d_out.data_ptr():
-            self.d_out.copy_(d_out)
+    def _plan_segments(self):
+        """Backward segments: [start, end) ranges of self.bwd, each ending where a coalesced gradient bucket
+        grad_arena[lo:hi] becomes final (at least bucket_elems elements, or the end of the arena)."""
+        self.segments, start, lo0 = [], 0, None
+        for idx, lo, hi in self.bucket_marks:
+            lo0 = lo if lo0 is None else min(lo0, lo)
+            if hi - lo0 >= self.bucket_elems or idx == len(self.bwd):
+                self.segments.append((start, idx, lo0, hi))
+                start, lo0 = idx, None
+        assert self.segments and self.segments[-1][1] == len(self.bwd) and lo0 is None
+
+    def _backward_prologue(self):
         self.store.grad_arena.zero_()
         for fn in self.prep_bwd:
             fn()
         fe, pu = self._pool_f_end, self._pool_used
-        ops.split_tf32(self.pool[fe:pu], self.pool_hi[fe:pu], self.pool_lo[fe:pu], pu - fe)
-        marks = {m[0]: m for m in self.bucket_marks}
-        # Weight gradients run on a side stream next to the data gradient(s) that follow them: the two only share
-        # read-only inputs, and the tail of one persistent kernel (partial last wave) is filled by the other.
-        # Any other launch first waits for the outstanding weight gradient (its dy scratch may be overwritten).
+        if self.bf16:                                     # every data gradient of the bf16 engine reads the bf16 image
+            ops.cast_bf16(self.pool[fe:pu], self.pool_b16[fe:pu], pu - fe)
+        else:
+            ops.split_tf32(self.pool[fe:pu], self.pool_hi[fe:pu], self.pool_lo[fe:pu], pu - fe)
+
+    def _run_bwd_ops(self, start, end):
+        """self.bwd[start:end] on the current stream.  Weight gradients run on a side stream next to the data gradient(s)
+        that follow them: the two only share read-only inputs, and the tail of one persistent kernel (partial last wave)
+        is filled by the other.  Any other launch first waits for the outstanding weight gradient (its dy scratch may be
+        overwritten); the side stream has always joined when the range ends."""
         if not self.overlap_wgrad:
-            for i, op in enumerate(self.bwd, start=1):
+            for op in self.bwd[start:end]:
                 op()
-                if on_bucket is not None and i in marks:
-                    on_bucket(marks[i][1], marks[i][2])
             return
         main = torch.cuda.current_stream()
         side = self._side_stream
         pending = None
-        for i, op in enumerate(self.bwd, start=1):
+        for op in self.bwd[start:end]:
             if isinstance(op, WgradOp):
                 ready = torch.cuda.Event()
                 ready.record(main)
@@ -861,11 +946,24 @@ class Engine:
                     main.wait_event(pending)
                     pending = None
                 op()
-            if i in marks:
-                if pending is not None:
-                    main.wait_event(pending)
-                    pending = None
-                if on_bucket is not None:
-                    on_bucket(marks[i][1], marks[i][2])
         if pending is not None:
             main.wait_event(pending)
+
+    def backward(self, d_out=None, on_bucket=None):
+        """d_out: [B,A,5] gradient of the packed head output (copied into the static buffer unless it already
+        is self.d_out).  on_bucket(lo, hi) is called as soon as grad_arena[lo:hi] is final (coalesced buckets)."""
+        if d_out is not None and d_out.data_ptr() != self.d_out.data_ptr():
+            self.d_out.copy_(d_out)
+        if on_bucket is None:                             # one graph for the whole backward
+            def whole():
+                self._backward_prologue()
+                self._run_bwd_ops(0, len(self.bwd))
+            self._graphed(("bwd",), whole)
+            return
+        for k, (start, end, lo, hi) in enumerate(self.segments):
+            def seg(k=k, start=start, end=end):
+                if k == 0:
+                    self._backward_prologue()
+                self._run_bwd_ops(start, end)
+            self._graphed(("bwd", k, len(self.segments)), seg)
+            on_bucket(lo, hi)

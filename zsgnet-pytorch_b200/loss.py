@@ -39,7 +39,9 @@ class _MatchLossFn(torch.autograd.Function):
         losses = torch.empty(3, dtype=torch.float64, device=dev)
         top1 = torch.empty(B, dtype=torch.int64, device=dev)
         pos = torch.empty(B, A, dtype=torch.uint8, device=dev)
-        ws = ops.match_loss_workspace(B, dev)
+        ws = mod._ws.get((dev, B))                      # zeroed once; the kernels leave it zero after every call
+        if ws is None:
+            ws = mod._ws[(dev, B)] = ops.match_loss_workspace(B, dev)
         ops.match_loss(att, sa, bbx, sr, annot, mod.anchs, B, A, float(mod.match_thr), float(mod.alpha),
                        float(mod.gamma), float(mod.lamb_reg), bool(mod.use_multi), losses, d_att, sa, d_reg, sr, top1,
                        pos, ws)
@@ -75,6 +77,7 @@ class ZSGLoss(nn.Module):
         self.loss_keys = ["loss", "cls_ls", "box_ls"]
         self.anchs = None
         self.last_top1 = self.last_pos = None
+        self._ws = {}
 
     def get_anchors(self, feat_sizes, device):
         sizes = [(int(h), int(w)) for h, w in feat_sizes.tolist()]

@@ -35,6 +35,17 @@ def _attach(root, dotted, tensor, is_param):
         node.register_buffer(parts[-1], tensor)
 
 
+def check_qlens(qlens_cpu, t_avail):
+    """Host-side validation of the query lengths (the reference fails in pack_padded_sequence for both cases, mdl.py:315-316;
+    here an unchecked 0 or too long length would read outside the query buffer).  Returns max_qlen."""
+    lo, hi = int(qlens_cpu.min().item()), int(qlens_cpu.max().item())
+    if lo < 1:
+        raise ValueError(f"zsg_b200: qlens must be >= 1 (got {lo}): an empty query cannot be encoded")
+    if hi > t_avail:
+        raise ValueError(f"zsg_b200: qlens up to {hi} but qvec holds only {t_avail} tokens per query")
+    return hi
+
+
 class _ZSGNetFn(torch.autograd.Function):
     """One autograd node for the whole network: forward = engine.forward, backward = engine.backward."""
 
@@ -54,8 +65,14 @@ class _ZSGNetFn(torch.autograd.Function):
                                "(one backward per forward; retain_graph is not supported)")
         eng.pending_backward = False
         eng.backward(d_out.contiguous(), on_bucket=net._on_bucket)
-        grads = tuple(net.store.grad_view(n) for n in net.param_names)
-        return (None,) * 8 + grads
+        if net.direct_grads:
+            # the gradients are already where the optimiser reads them: param.grad IS the arena view (no AccumulateGrad
+            # clone of 161 strided tensors per step).  Overwrites instead of accumulating: zero_grad() every step, as
+            # the reference loop does (utils.py:410).
+            for p, g in zip(net._param_list, net._grad_views):
+                p.grad = g
+            return (None,) * 9
+        return (None,) * 8 + tuple(net._grad_views)
 
 
 class ZSGNet(nn.Module):
@@ -92,12 +109,16 @@ class ZSGNet(nn.Module):
             raise NotImplementedError("zsg_b200 hot path does not cover: " + "; ".join(unsupported))
         self.cfg = cfg
         self.n_anchors = n_anchors
+        # arithmetic of the dense contractions: "fp32" (3xTF32, the reference's fp32 results; BASELINE configs[1]) or "bf16"
+        # (bf16 tensor-core convs with fp32 accumulation; configs[2..4]).  cfg key `zsg_dtype`, or set_compute_dtype().
+        self.compute_dtype = "fp32"
+        self.set_compute_dtype(get("zsg_dtype", "fp32"))
         dev = torch.device(device if device is not None else "cuda")
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.store = ParamStore(dev, self.model)
         self.param_names = [n for n, _, _ in spec.trainable_specs(self.model)]
-        for n in self.param_names + [u[0] for u in spec.unused_specs(self.model)]:
+        for n in spec.reference_param_order(self.model):        # the reference's registration order (optimizer state_dict)
             _attach(self, n, nn.Parameter(self.store.view(n)), True)
         # BatchNorm buffers: float stats in one tensor, counters in another (views keep the reference names)
         bspecs = spec.buffer_specs(self.model)
@@ -118,6 +139,13 @@ class ZSGNet(nn.Module):
             _attach(self, name, t, False)
         self._engines = {}
         self._on_bucket = None
+        self._param_list = [self.get_parameter(n) for n in self.param_names]
+        self._grad_views = [self.store.grad_view(n) for n in self.param_names]
+        # cfg key `zsg_direct_grads` (or the attribute): hand gradients to the optimiser by pointing param.grad at the
+        # gradient arena instead of returning 161 tensors through autograd.  Off by default: torch's
+        # DistributedDataParallel needs the AccumulateGrad hooks of the ordinary path.
+        self.direct_grads = bool(get("zsg_direct_grads", False))
+        self._anchor = torch.zeros((), device=dev, requires_grad=True)
         self.reset_parameters()
 
     # ------------------------------------------------------------------ init / state
@@ -159,16 +187,30 @@ class ZSGNet(nn.Module):
                                "supported (build it with device=...)")
         return self
 
+    def set_compute_dtype(self, dtype):
+        if dtype not in ("fp32", "bf16"):
+            raise ValueError(f"zsg_b200: compute dtype {dtype!r} (choose 'fp32' or 'bf16')")
+        self.compute_dtype = dtype
+        return self
+
     # ------------------------------------------------------------------ forward
-    def engine_for(self, B, T):
-        key = (B, T)
-        if key not in self._engines:
-            if len(self._engines) >= 2:                           # bound memory: keep two shapes (train / last batch)
-                self._engines.pop(next(iter(self._engines)))
+    T_BUCKET = 50            # dat_loader pads / truncates queries to 50 tokens (dat_loader.py:74, 'phrase_len')
+
+    def engine_for(self, B, T=None):
+        """The static launch program for batch size B.  Query length is NOT part of the shape: the LSTM buffers are sized
+        for T_BUCKET tokens (the loader's maximum; longer batches round up to the next multiple) and the recurrences run
+        to each sample's own length, so batches of any max_qlen share one engine and nothing is rebuilt per step."""
+        Ta = max(1, -(-max(int(T or 1), 1) // self.T_BUCKET)) * self.T_BUCKET
+        key = (B, Ta, self.compute_dtype)
+        eng = self._engines.pop(key, None)
+        if eng is None:
+            while len(self._engines) >= 2:                        # bound memory: two programs (train batch / ragged last batch)
+                self._engines.pop(next(iter(self._engines)))      # least recently used first
                 torch.cuda.empty_cache()
             bufs = {k: v for k, v in self.bn_buffers.items()}
-            self._engines[key] = Engine(self.store, bufs, B, T, self.store.device)
-        return self._engines[key]
+            eng = Engine(self.store, bufs, B, Ta, self.store.device, dtype=self.compute_dtype)
+        self._engines[key] = eng                                  # most recently used last
+        return eng
 
     def forward(self, inp: Dict[str, Any]):
         img, qvec, qlens = inp["img"], inp["qvec"], inp["qlens"]
@@ -178,7 +220,7 @@ class ZSGNet(nn.Module):
         B = img.shape[0]
         # mdl.py:357: the reference synchronises here too (qlens.max().item())
         qlens_cpu = qlens.detach().cpu()
-        max_qlen = int(qlens_cpu.max().item())
+        max_qlen = check_qlens(qlens_cpu, qvec.shape[1])
         qvec = qvec[:, :max_qlen, :]
         # mdl.py:279-294, 307: h0 then c0 from the global CPU RNG, consumed in sorted-row order (309-319)
         h0 = torch.randn(2, B, 128)
@@ -187,7 +229,7 @@ class ZSGNet(nn.Module):
         inv = torch.empty_like(perm)
         inv[perm] = torch.arange(B)
         eng = self.engine_for(B, max(max_qlen, 1))
-        params = [self.get_parameter(n) for n in self.param_names]
+        params = [self._anchor] if self.direct_grads else self._param_list
         out = _ZSGNetFn.apply(self, eng, img.contiguous().float(), qvec.float(), qlens_cpu, inv, h0, c0, *params)
         if self.training:
             self._bn_n.add_(1)                                    # num_batches_tracked

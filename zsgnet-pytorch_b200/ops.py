@@ -277,8 +277,14 @@ def lstm_rev_step_bwd(dlang, gates, c0, b, dgates):
 
 
 def match_loss_workspace(b, device):
+    """Zeroed once here; zsg_match_loss leaves it zero after every call (include/zsg_b200.h)."""
     n = _lib.load().zsg_match_loss_workspace_bytes(b)
-    return torch.empty((n + 7) // 8, dtype=torch.float64, device=device)
+    return torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+def eval_workspace(b, device):
+    n = _lib.load().zsg_eval_workspace_bytes(b)
+    return torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)
 
 
 def match_loss(att, att_stride, reg, reg_stride, annot, anchors, b, a, thr, alpha, gamma, lamb, use_multi, losses,
@@ -288,9 +294,18 @@ def match_loss(att, att_stride, reg, reg_stride, annot, anchors, b, a, thr, alph
          ptr(pos), ptr(ws), ws.numel() * 8, stream())
 
 
-def evaluate(att, att_stride, reg, reg_stride, annot, anchors, img_size, b, a, thr, best_ids, scores, boxes, metrics):
+_EVAL_WS = {}
+
+
+def evaluate(att, att_stride, reg, reg_stride, annot, anchors, img_size, b, a, thr, best_ids, scores, boxes, metrics,
+             ws=None):
+    if ws is None:                                       # one cached scratch per (device, batch): calls on a stream serialise
+        key = (att.device, b)
+        if key not in _EVAL_WS:
+            _EVAL_WS[key] = eval_workspace(b, att.device)
+        ws = _EVAL_WS[key]
     call("zsg_eval", ptr(att), att_stride, ptr(reg), reg_stride, ptr(annot), ptr(anchors), ptr(img_size), b, a, thr,
-         ptr(best_ids), ptr(scores), ptr(boxes), ptr(metrics), stream())
+         ptr(best_ids), ptr(scores), ptr(boxes), ptr(metrics), ptr(ws), ws.numel() * 8, stream())
 
 
 def adam(p, g, m, v, n, lr, b1, b2, eps, step, grad_scale=1.0):

@@ -151,3 +151,24 @@ def buffer_specs(model="retina"):
             if b == 0:
                 out += bn_buffers(p + "downsample.1", width * 4)
     return out
+
+
+def reference_param_order(model="retina"):
+    """Parameter names in the REFERENCE module's registration order (named_parameters()): torch.optim.Adam's state_dict
+    indexes parameters by it (utils.py:479-497 saves optimizer.state_dict()), so the drop-in registers its parameters in
+    this order.  retina: encoder incl. the unused fc (torchvision resnet50), fpn as P7_2, P6, P5_1 .. P3_2
+    (fpn_resnet.py:113-152), att_reg_box, lstm (mdl.py:208-228).  ssd_vgg: vgg, fproj1-3, extras, loc, conf
+    (ssd_vgg.py:31-52), att_reg_box, lstm.  Pinned against the real reference by tests/golden/param_order.json."""
+    names = [n for n, _, _ in trainable_specs(model) + unused_specs(model)]
+    e = "backbone.encoder."
+
+    def take(prefixes):
+        return [n for pre in prefixes for n in names if n.startswith(pre)]
+    if model == "ssd_vgg":
+        order = take([e + "vgg.", e + "fproj1.", e + "fproj2.", e + "fproj3.", e + "extras.", e + "loc.", e + "conf."])
+    else:
+        order = [n for n in names if n.startswith(e) and not n.startswith(e + "fc.")] + take([e + "fc."])
+        order += take(["backbone.fpn." + k + "." for k in ("P7_2", "P6", "P5_1", "P5_2", "P4_1", "P4_2", "P3_1", "P3_2")])
+    order += take(["att_reg_box.", "lstm."])
+    assert sorted(order) == sorted(names) and len(set(order)) == len(order)
+    return order

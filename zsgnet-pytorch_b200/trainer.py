@@ -8,6 +8,7 @@ import torch
 from . import ops, spec
 from .anchors import create_anchors
 from .ddp import GradReducer
+from .mdl import check_qlens
 from .optim import FusedAdam
 
 
@@ -38,7 +39,7 @@ class FusedStep:
         img, qvec, qlens = batch["img"], batch["qvec"], batch["qlens"]
         B, A = img.shape[0], spec.NUM_ANCHORS
         qlens_cpu = batch["qlens_cpu"] if "qlens_cpu" in batch else qlens.cpu()
-        max_qlen = int(qlens_cpu.max().item())
+        max_qlen = check_qlens(qlens_cpu, qvec.shape[1])
         if h0 is None:
             h0, c0 = torch.randn(2, B, 128), torch.randn(2, B, 128)      # mdl.py:279-294
         _, perm = qlens_cpu.sort(0, descending=True)
@@ -53,7 +54,7 @@ class FusedStep:
         ops.match_loss(flat[4:], 5, out, 5, batch["annot"], self.anchs, B, A, float(cfg["matching_threshold"]),
                        float(cfg["alpha"]), float(cfg["gamma"]), float(cfg["lamb_reg"]), bool(cfg["use_multi"]),
                        b["losses"], dflat[4:], 5, eng.d_out, 5, b["top1"], b["pos"], b["ws"])
-        eng.backward(None, on_bucket=self.reducer.on_bucket)
+        eng.backward(None, on_bucket=self.reducer.on_bucket if self.reducer.world > 1 else None)
         if do_opt:
             self.opt.step()
         else:
