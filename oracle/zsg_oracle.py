@@ -26,6 +26,60 @@ import torch.nn.functional as F
 from . import synth
 
 # --------------------------------------------------------------------------------------
+# convolution arithmetic
+# --------------------------------------------------------------------------------------
+# "fp32": F.conv2d as the reference executes it (BASELINE configs 1-2).
+# "bf16": what BASELINE configs 3-5 call "bf16 tensor-core convs", restated as the arithmetic the product computes: both
+#   operands of every contraction rounded to bfloat16 (round-to-nearest-even), products exact, accumulation and output
+#   in fp32 -- forward (x, w), data gradient (dy, w) and weight gradient (x, dy) alike; bias gradients from the unrounded
+#   dy.  The 3-channel stem convolution (and the LSTM, which is not a convolution) stay fp32, as in the product.
+#   The reference has no bf16 mode of its own; the closest thing it offers, torch.autocast(bfloat16) around the same
+#   modules, additionally rounds every conv OUTPUT to bf16 (tests/test_bf16_network_gpu.py measures both against fp32).
+CONV_MODE = ["fp32"]
+
+
+class conv_mode:
+    def __init__(self, mode):
+        assert mode in ("fp32", "bf16"), mode
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev, CONV_MODE[0] = CONV_MODE[0], self.mode
+
+    def __exit__(self, *a):
+        CONV_MODE[0] = self.prev
+
+
+def _rb(t):
+    return t.bfloat16().to(t.dtype)
+
+
+class _Bf16OperandConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding, dilation):
+        xr, wr = _rb(x), _rb(w)
+        ctx.save_for_backward(xr, wr)
+        ctx.conf = (stride, padding, dilation, bias is not None, x.shape, w.shape)
+        return F.conv2d(xr, wr, bias, stride, padding, dilation)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, wr = ctx.saved_tensors
+        stride, padding, dilation, has_bias, xs, ws = ctx.conf
+        dyr = _rb(dy)
+        gx = torch.nn.grad.conv2d_input(xs, wr, dyr, stride, padding, dilation) if ctx.needs_input_grad[0] else None
+        gw = torch.nn.grad.conv2d_weight(xr, ws, dyr, stride, padding, dilation) if ctx.needs_input_grad[1] else None
+        gb = dy.sum((0, 2, 3)) if has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None, None
+
+
+def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1):
+    if CONV_MODE[0] == "bf16" and x.shape[1] >= 8:          # all but the 3-channel stem (the 514-channel fused input is padded to 520)
+        return _Bf16OperandConv.apply(x, w, bias, stride, padding, dilation)
+    return F.conv2d(x, w, bias, stride=stride, padding=padding, dilation=dilation)
+
+
+# --------------------------------------------------------------------------------------
 # anchors.py
 # --------------------------------------------------------------------------------------
 
@@ -157,6 +211,9 @@ def zsg_loss(att_out, bbx_out, annot, anchs, cfg=None):
     w = (w.pow(cfg["gamma"]) * al).detach()
     cls = F.binary_cross_entropy_with_logits(x, posf, weight=w, reduction="none")
     cls_loss = cls.sum() / pos.sum()
+    if torch.isnan(box_loss) or torch.isnan(cls_loss):                       # loss.py:128-133: constants without gradient
+        box_loss = (box_loss.new_ones(box_loss.shape) * 0.01).requires_grad_(True)
+        cls_loss = cls_loss.new_ones(cls_loss.shape).requires_grad_(True)
     loss = cfg["lamb_reg"] * box_loss + cls_loss
     return {"loss": loss, "cls_ls": cls_loss, "box_ls": box_loss, "pos": pos, "top1": top1}
 
@@ -206,26 +263,34 @@ class BNState:
                             training=self.training, momentum=0.1, eps=1e-5)
 
 
-def resnet50_c3c4c5(sd, img, bn):
-    """mdl.py:148-156 over torchvision's ResNet-50 v1.5: stem conv7x7/2 -> BN -> ReLU ->
-    maxpool3x3/2 -> 4 stages of bottlenecks (1x1 -> 3x3(stride) -> 1x1(x4), BN after each,
-    identity or 1x1/s+BN shortcut, ReLU after the add).  Returns C3, C4, C5."""
+def stem(sd, img, bn):
+    """mdl.py:149-152: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2."""
     e = "backbone.encoder."
-    x = F.conv2d(img, sd[e + "conv1.weight"], None, stride=2, padding=3)
+    x = conv2d(img, sd[e + "conv1.weight"], None, stride=2, padding=3)
     x = F.relu(bn(x, e + "bn1"))
-    x = F.max_pool2d(x, 3, 2, 1)
+    return F.max_pool2d(x, 3, 2, 1)
+
+
+def bottleneck(sd, x, p, s, bn):
+    """torchvision Bottleneck (v1.5: the stride sits on the 3x3): 1x1 -> BN, ReLU -> 3x3(stride s) -> BN, ReLU -> 1x1 (x4) -> BN
+    -> + identity (or 1x1/s conv + BN when the block has a `downsample`) -> ReLU.  p = 'backbone.encoder.layerL.B.'."""
+    idt = x
+    y = F.relu(bn(conv2d(x, sd[p + "conv1.weight"]), p + "bn1"))
+    y = F.relu(bn(conv2d(y, sd[p + "conv2.weight"], None, stride=s, padding=1), p + "bn2"))
+    y = bn(conv2d(y, sd[p + "conv3.weight"]), p + "bn3")
+    if p + "downsample.0.weight" in sd:
+        idt = bn(conv2d(x, sd[p + "downsample.0.weight"], None, stride=s), p + "downsample.1")
+    return F.relu(y + idt)
+
+
+def resnet50_c3c4c5(sd, img, bn):
+    """mdl.py:148-156 over torchvision's ResNet-50 v1.5: stem -> 4 stages of bottlenecks.  Returns C3, C4, C5."""
+    e = "backbone.encoder."
+    x = stem(sd, img, bn)
     feats = []
     for li, (nblk, width, stride) in enumerate(synth.RESNET_LAYERS, start=1):
         for b in range(nblk):
-            p = f"{e}layer{li}.{b}."
-            s = stride if b == 0 else 1
-            idt = x
-            y = F.relu(bn(F.conv2d(x, sd[p + "conv1.weight"]), p + "bn1"))
-            y = F.relu(bn(F.conv2d(y, sd[p + "conv2.weight"], None, stride=s, padding=1), p + "bn2"))
-            y = bn(F.conv2d(y, sd[p + "conv3.weight"]), p + "bn3")
-            if b == 0:
-                idt = bn(F.conv2d(x, sd[p + "downsample.0.weight"], None, stride=s), p + "downsample.1")
-            x = F.relu(y + idt)
+            x = bottleneck(sd, x, f"{e}layer{li}.{b}.", stride if b == 0 else 1, bn)
         feats.append(x)
     return feats[1], feats[2], feats[3]
 
@@ -235,7 +300,7 @@ def fpn(sd, c3, c4, c5):
     f = "backbone.fpn."
 
     def cv(name, x, stride=1, pad=0):
-        return F.conv2d(x, sd[f + name + ".weight"], sd[f + name + ".bias"], stride=stride, padding=pad)
+        return conv2d(x, sd[f + name + ".weight"], sd[f + name + ".bias"], stride=stride, padding=pad)
 
     p51 = cv("P5_1", c5)
     p5 = cv("P5_2", p51, pad=1)
@@ -262,7 +327,7 @@ def ssd_vgg_feats(sd, img):
             if not lo <= i < hi:
                 continue
             if L[0] == "conv":
-                x = F.conv2d(x, sd[f"{e}vgg.{i}.weight"], sd[f"{e}vgg.{i}.bias"], padding=L[4], dilation=L[5])
+                x = conv2d(x, sd[f"{e}vgg.{i}.weight"], sd[f"{e}vgg.{i}.bias"], padding=L[4], dilation=L[5])
             elif L[0] == "relu":
                 x = F.relu(x)
             else:
@@ -273,10 +338,10 @@ def ssd_vgg_feats(sd, img):
     x = run(x, 23, len(synth.vgg_layers()))
     sources.append(x)
     for i, (_, _, _, stride, pad) in enumerate(synth.VGG_EXTRAS):
-        x = F.relu(F.conv2d(x, sd[f"{e}extras.{i}.weight"], sd[f"{e}extras.{i}.bias"], stride=stride, padding=pad))
+        x = F.relu(conv2d(x, sd[f"{e}extras.{i}.weight"], sd[f"{e}extras.{i}.bias"], stride=stride, padding=pad))
         if i % 2 == 1:
             sources.append(x)
-    proj = [F.conv2d(sources[j], sd[f"{e}fproj{j + 1}.weight"], sd[f"{e}fproj{j + 1}.bias"]) for j in range(3)]
+    proj = [conv2d(sources[j], sd[f"{e}fproj{j + 1}.weight"], sd[f"{e}fproj{j + 1}.bias"]) for j in range(3)]
     return proj + sources[3:]
 
 
@@ -351,8 +416,8 @@ def fuse_and_head(sd, feats, lang):
         we = lang.view(B, -1, 1, 1).expand(B, lang.shape[1], H, W)
         y = torch.cat([x, we, grid], dim=1)
         for i in range(5):
-            y = F.relu(F.conv2d(y, sd[f"att_reg_box.{i}.0.weight"], sd[f"att_reg_box.{i}.0.bias"], padding=1))
-        y = F.conv2d(y, sd["att_reg_box.5.weight"], sd["att_reg_box.5.bias"], padding=1)
+            y = F.relu(conv2d(y, sd[f"att_reg_box.{i}.0.weight"], sd[f"att_reg_box.{i}.0.bias"], padding=1))
+        y = conv2d(y, sd["att_reg_box.5.weight"], sd["att_reg_box.5.bias"], padding=1)
         outs.append(y.permute(0, 2, 3, 1).reshape(B, -1, 5))
     out = torch.cat(outs, dim=1)
     return out[..., 4:5], out[..., :4]

@@ -1,0 +1,167 @@
+"""Network-level parity of the bf16 operand path (BASELINE configs[2..4]: "bf16 tensor-core convs") and of the CUDA-graph
+replay of the launch program.
+
+Checker for bf16: the CPU oracle with its convolutions switched to the SAME arithmetic the product computes
+(oracle/zsg_oracle.py conv_mode('bf16'): operands rounded to bfloat16, exact products, fp32 accumulation and outputs, for the
+forward, data-gradient and weight-gradient contractions).  What remains between the two is fp32 summation order, amplified
+where a value sits on a bf16 rounding boundary and rounds the other way (one bf16 ulp = 0.4 % on a ~1e-4 fraction of the
+elements of each layer).  Tolerances (measured): losses 2e-3 relative, head outputs 5e-3 rms;
+anchor indices / positives / Acc are bit-exact (they come from the fp64 match kernel, which the dtype does not touch).
+Against the reference's only bf16 offer -- torch.autocast(bfloat16), which also rounds every conv OUTPUT -- the test shows
+the product is closer to the fp32 result than autocast is."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def to_dev(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+def rms_rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean() / max((b ** 2).mean(), 1e-60)))
+
+
+@pytest.fixture(scope="module")
+def bf16_stack():
+    assert torch.cuda.is_available()
+    import zsg_b200  # noqa: F401
+    from zsg_b200 import mdl, loss, evaluator
+    from oracle import synth
+    cfg = synth.default_cfg()
+    cfg["device"] = "cuda"
+    cfg["zsg_dtype"] = "bf16"
+    ratios, scales = synth.ratios_scales(cfg)
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    assert net.compute_dtype == "bf16"
+    return net, loss.get_default_loss(ratios, scales, cfg), evaluator.get_default_eval(ratios, scales, cfg), synth
+
+
+def zsg_step(net, crit, ev, synth, batch, seed):
+    net.load_state_dict(synth.make_state_dict(0), strict=True)
+    net.train()
+    net.zero_grad()
+    dbatch = to_dev(batch)
+    torch.manual_seed(seed)
+    out = net(dbatch)
+    ls = crit(out, dbatch)
+    ls["loss"].mean().backward()
+    met = ev(out, dbatch)
+    torch.cuda.synchronize()
+    return out, ls, met
+
+
+def test_bf16_engine_uses_bf16_kernels(bf16_stack):
+    net, crit, ev, synth = bf16_stack
+    from zsg_b200 import ops
+    eng = net.engine_for(2, 20)
+    kinds = [it[1].kernel for it in eng.fwd if it[0] == "op"]
+    assert kinds.count("conv_bf16_kernel") == 66 and kinds.count("conv_tc_async_kernel") == 2
+    assert sum(1 for o in eng.bwd if isinstance(o, ops.WgradOp) and o.kernel == "wgrad_bf16_kernel") == 66
+
+
+@pytest.mark.parametrize("B,seed,var_len", [(2, 21, False), (3, 22, True)])
+def test_bf16_train_step_vs_bf16_oracle(bf16_stack, B, seed, var_len):
+    net, crit, ev, synth = bf16_stack
+    from oracle import zsg_oracle as zo
+    batch = synth.make_batch(B, seed=seed, var_len=var_len)
+    out, ls, met = zsg_step(net, crit, ev, synth, batch, seed)
+    with zo.conv_mode("bf16"):
+        ols, omet, ograds, oout, _ = zo.train_step(synth.make_state_dict(0), batch, seed=seed, do_adam=False)
+    fls, fmet, fgrads, fout, _ = zo.train_step(synth.make_state_dict(0), batch, seed=seed, do_adam=False)      # fp32 reference
+    # index work: bit-exact (fp64 matching is independent of the conv arithmetic)
+    assert torch.equal(crit.last_top1.cpu(), ols["top1"]) and torch.equal(crit.last_pos.cpu().bool(), ols["pos"])
+    for k in ("loss", "cls_ls", "box_ls"):
+        assert ls[k].item() == pytest.approx(ols[k].item(), rel=2e-3), k
+    att, oatt = out["att_out"].detach().cpu().numpy(), oout["att_out"].detach().numpy()
+    bbx, obbx = out["bbx_out"].detach().cpu().numpy(), oout["bbx_out"].detach().numpy()
+    e_att, e_bbx = rms_rel(att, oatt), rms_rel(bbx, obbx)
+    # distance of the bf16 arithmetic itself from the fp32 reference, for scale
+    d_att, d_bbx = rms_rel(oatt, fout["att_out"].detach().numpy()), rms_rel(obbx, fout["bbx_out"].detach().numpy())
+    print(f"bf16 B={B}: zsg vs bf16-oracle att {e_att:.2e} bbx {e_bbx:.2e}; bf16-oracle vs fp32-oracle att {d_att:.2e} bbx {d_bbx:.2e}; "
+          f"loss zsg {ls['loss'].item():.6f} bf16-oracle {ols['loss'].item():.6f} fp32 {fls['loss'].item():.6f}")
+    assert e_att < 5e-3 and e_bbx < 5e-3
+    assert e_att < 0.5 * d_att + 1e-3 and e_bbx < 0.5 * d_bbx + 1e-3      # far closer to its own oracle than bf16 is to fp32
+    assert ls["loss"].item() == pytest.approx(fls["loss"].item(), rel=2e-2)   # and bf16 training sees (almost) the fp32 loss
+    # predicted box of the best anchor (Evaluator): equal ids unless two scores are within the bf16 noise
+    same = (met["best_ids"].cpu() == omet["idxs_best"]).float().mean().item()
+    assert same >= 0.5
+    # gradients: language path and head are BatchNorm-free -> tight; the trunk within the chaotic band of the fp32 test
+    errs = {}
+    for k, g in ograds.items():
+        if g is None:
+            assert net.get_parameter(k).grad is None, k
+            continue
+        r = g.double()
+        errs[k] = float((net.get_parameter(k).grad.cpu().double() - r).norm() / r.norm().clamp_min(1e-30))
+    head = [v for k, v in errs.items() if k.startswith(("att_reg_box.", "lstm."))]
+    print(f"bf16 gradient error vs bf16-oracle: head/lstm median {np.median(head):.2e} max {max(head):.2e}; all median "
+          f"{np.median(list(errs.values())):.2e} max {max(errs.values()):.2e}")
+    assert np.median(head) < 2e-2 and np.median(list(errs.values())) < 0.15
+
+
+def test_bf16_closer_to_fp32_than_autocast(bf16_stack):
+    """The reference's own bf16 option is torch.autocast(bfloat16) around its modules; it rounds conv outputs as well as
+    operands.  Head outputs of the product's bf16 path must be at least as close to the fp32 reference as autocast's."""
+    net, crit, ev, synth = bf16_stack
+    from oracle import zsg_oracle as zo
+    B, seed = 2, 41
+    batch = synth.make_batch(B, seed=seed)
+    out, ls, met = zsg_step(net, crit, ev, synth, batch, seed)
+    sd = synth.make_state_dict(0)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        ref = zo.zsgnet_forward(dict(sd), batch, training=True)
+        torch.manual_seed(seed)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            auto = zo.zsgnet_forward(dict(sd), batch, training=True)
+    mine = rms_rel(out["att_out"].detach().cpu().numpy(), ref["att_out"].numpy())
+    theirs = rms_rel(auto["att_out"].float().numpy(), ref["att_out"].numpy())
+    print(f"att_out error vs fp32: zsg bf16 {mine:.2e}, torch.autocast(bfloat16) {theirs:.2e}")
+    assert mine <= 1.2 * theirs + 1e-3
+
+
+def test_graph_replay_matches_eager_launches():
+    """The forward pass and the backward are replayed as CUDA graphs from their second run on; results must be those of
+    launching every kernel eagerly: forward bit for bit, gradients up to the order of the split-K atomics."""
+    import zsg_b200  # noqa: F401
+    from zsg_b200 import mdl, loss, evaluator
+    from oracle import synth
+    cfg = synth.default_cfg()
+    cfg["device"] = "cuda"
+    ratios, scales = synth.ratios_scales(cfg)
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    crit = loss.get_default_loss(ratios, scales, cfg)
+    B = 2
+    batches = [synth.make_batch(B, seed=60 + i) for i in range(3)]
+
+    def run(use_graphs):
+        net.load_state_dict(synth.make_state_dict(0), strict=True)
+        net.train()
+        eng = net.engine_for(B, 20)
+        eng.use_graphs = use_graphs
+        res = []
+        for i in list(range(3)) + [0]:                       # eager warm-up, capture, replay, replay on the first batch again
+            net.zero_grad()
+            torch.manual_seed(i)
+            out = net(to_dev(batches[i]))
+            ls = crit(out, to_dev(batches[i]))
+            ls["loss"].mean().backward()
+            torch.cuda.synchronize()
+            res.append((out["att_out"].detach().clone(), ls["loss"].item(),
+                        net.get_parameter("att_reg_box.5.weight").grad.clone(), net.get_parameter("backbone.encoder.conv1.weight").grad.clone()))
+        return res, eng
+
+    eager, eng = run(False)
+    graphed, eng = run(True)
+    assert any(isinstance(g, torch.cuda.CUDAGraph) for g in eng._graphs.values())
+    for i, (e, g) in enumerate(zip(eager, graphed)):
+        assert torch.equal(e[0], g[0]), f"forward of step {i} differs between graph replay and eager launches"
+        assert e[1] == pytest.approx(g[1], rel=1e-12)
+        for j in (2, 3):
+            assert float((e[j] - g[j]).norm() / e[j].norm()) < 1e-4, (i, j)
+    # BatchNorm running statistics were updated by every replay (4 training steps)
+    assert int(net.state_dict()["backbone.encoder.bn1.num_batches_tracked"]) == 4

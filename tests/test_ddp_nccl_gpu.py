@@ -1,0 +1,106 @@
+"""N > 1 on hardware: two ranks over NCCL, one process per GPU, each with its own shard
+of the global batch.  After k steps the parameters must be bit-identical on both ranks (same averaged gradients, same
+Adam), rank r's loss must equal the oracle's on shard r (BatchNorm statistics and loss normalisers stay per rank, like the
+reference's non-synchronised BatchNorm under DistributedDataParallel, main_dist.py:36-40), and the gradients the optimiser
+sees must be the MEAN of the per-shard gradients.  Skipped on boxes with fewer than two GPUs (`gpurun --gpus 2`)."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+B, STEPS = 2, 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, dtype, out_q):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import zsg_b200  # noqa: F401
+    from zsg_b200 import ddp, mdl
+    from zsg_b200.trainer import FusedStep
+    from oracle import synth, zsg_oracle as zo
+    cfg = synth.default_cfg()
+    cfg["device"], cfg["zsg_dtype"] = f"cuda:{rank}", dtype
+    ratios, scales = synth.ratios_scales(cfg)
+    torch.manual_seed(100 + rank)                                      # DIFFERENT initial weights per rank ...
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    if rank == 0:
+        net.load_state_dict(synth.make_state_dict(0), strict=True)
+    net.train()
+    red = ddp.GradReducer(net.store)
+    red.broadcast_state(net)                                           # ... made equal to rank 0's, like DDP's constructor
+    fused = FusedStep(net, ratios, scales, cfg, lr=1e-4, reducer=red)
+    glob = [synth.make_batch(world * B, seed=500 + i) for i in range(STEPS)]      # the global batches; rank r owns [rB, (r+1)B)
+    lo, hi = ddp.shard_range(world * B, rank, world)
+    losses, grads0 = [], None
+    for i, g in enumerate(glob):
+        shard = {k: v[lo:hi].contiguous().cuda() for k, v in g.items()}
+        torch.manual_seed(1000 * rank + i)
+        res = fused.step(shard, do_opt=(i > 0))                       # step 0: reduce only, so the averaged gradients can be read
+        torch.cuda.synchronize()
+        losses.append(float(res["loss"].item()))
+        if i == 0:
+            grads0 = net.store.grad_arena.clone()
+            fused.opt.step()
+    torch.cuda.synchronize()
+    # (1) parameters bit-identical across ranks after STEPS optimiser steps
+    mine = net.store.param_arena[: net.store.used].clone()
+    other = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(other, mine)
+    same = all(torch.equal(other[0], o) for o in other)
+    gsame_t = [torch.empty_like(grads0) for _ in range(world)]
+    dist.all_gather(gsame_t, grads0)
+    gsame = all(torch.equal(gsame_t[0], o) for o in gsame_t)
+    # (2) loss of step 0 on this rank's shard vs the oracle on the same shard (fp32 engine: 1e-4; bf16: its own oracle, 2e-3)
+    shard0 = {k: v[lo:hi].contiguous() for k, v in glob[0].items()}
+    with zo.conv_mode(dtype):
+        ols, _, og, _, _ = zo.train_step(synth.make_state_dict(0), shard0, seed=1000 * rank, do_adam=False)
+    # (3) averaged gradients = mean over ranks of the per-shard oracle gradients (BatchNorm-free parameters: tight)
+    keys = ["att_reg_box.5.bias", "att_reg_box.5.weight", "att_reg_box.4.0.bias", "lstm.bias_ih_l0"]
+    mean_err = {}
+    for k in keys:
+        t = og[k].detach().cuda().contiguous()
+        dist.all_reduce(t)
+        t /= world
+        got = net.store.view(k, grads0)
+        mean_err[k] = float((got.double() - t.double()).norm() / t.double().norm().clamp_min(1e-30))
+    out_q.put(dict(rank=rank, same=same, gsame=gsame, loss=losses[0], oloss=float(ols["loss"].item()), mean_err=mean_err,
+                   calls=red.calls, world=red.world))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_two_ranks_nccl_parameters_identical_and_losses_per_shard(dtype):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, dtype, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda d: d["rank"])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    print(res)
+    for d in res:
+        assert d["world"] == 2 and d["calls"] >= 2 * STEPS             # bucketed all-reduces actually ran
+        assert d["same"], "parameters differ between ranks after training steps"
+        assert d["gsame"], "averaged gradients differ between ranks"
+        assert d["loss"] == pytest.approx(d["oloss"], rel=1e-4 if dtype == "fp32" else 2e-3), d
+        assert max(d["mean_err"].values()) < (1e-3 if dtype == "fp32" else 2e-2), d["mean_err"]
+    assert res[0]["loss"] != res[1]["loss"]                            # different shards: per-rank losses, not a global one

@@ -878,3 +878,115 @@ def test_batched_weight_transpose_flip(zsg):
     ops.weight_transpose_flip_batched(src, dst, tab, len(entries), total)
     torch.cuda.synchronize()
     assert torch.equal(dst[:off], want[:off]) and torch.isnan(dst[off:]).all()
+
+
+# ------------------------------------------------------------------------------- NaN handling, anchors (ADVICE)
+def test_match_loss_nan_guard_and_workspace_left_clean(zsg):
+    """loss.py:128-133: a NaN box or class loss is replaced by the constants 0.01 / 1.0, which carry no gradient.  A diverged
+    network (NaN score) must neither poison the step's gradients nor leave the device workspace dirty."""
+    ops, _ = zsg
+    from oracle import synth, zsg_oracle as zo
+    B, A = 4, synth.NUM_ANCHORS
+    g = torch.Generator().manual_seed(3)
+    batch = synth.make_batch(B, seed=3)
+    att = (torch.randn(B, A, 1, generator=g) * 1.5 - 3.0)
+    bbx = torch.randn(B, A, 4, generator=g) * 0.7
+    anchs = zo.default_anchors()
+    for packed in (False, True):
+        bad = att.clone()
+        bad[1, 777, 0] = float("nan")
+        d = att.device
+        ws = ops.match_loss_workspace(B, "cuda")
+        losses = torch.empty(3, dtype=torch.float64, device="cuda")
+        top1, pos = torch.empty(B, dtype=torch.int64, device="cuda"), torch.empty(B, A, dtype=torch.uint8, device="cuda")
+
+        def call(a):
+            if packed:
+                buf = torch.cat([bbx, a], dim=2).cuda().contiguous()
+                dbuf = torch.full_like(buf, 7.0)
+                ops.match_loss(buf.view(-1)[4:], 5, buf, 5, dev(batch["annot"]), dev(anchs), B, A, 0.6, 0.25, 2.0, 1.0, True,
+                               losses, dbuf.view(-1)[4:], 5, dbuf, 5, top1, pos, ws)
+                torch.cuda.synchronize()
+                return dbuf[..., 4].cpu(), dbuf[..., :4].cpu()
+            datt, dreg = torch.full((B, A), 7.0, device="cuda"), torch.full((B, A, 4), 7.0, device="cuda")
+            ops.match_loss(dev(a), 1, dev(bbx), 4, dev(batch["annot"]), dev(anchs), B, A, 0.6, 0.25, 2.0, 1.0, True,
+                           losses, datt, 1, dreg, 4, top1, pos, ws)
+            torch.cuda.synchronize()
+            return datt.cpu(), dreg.cpu()
+        datt, dreg = call(bad)
+        assert losses.cpu().tolist() == [1.0 * 0.01 + 1.0, 1.0, 0.01]
+        assert float(datt.abs().sum()) == 0.0 and float(dreg.abs().sum()) == 0.0
+        assert int(ws.view(torch.int64).abs().sum()) == 0                  # self-cleaning workspace
+        # the same buffers right afterwards with finite scores: the normal result (nothing stuck from the NaN call)
+        ref = zo.zsg_loss(att.clone().requires_grad_(True), bbx.clone().requires_grad_(True), batch["annot"], anchs)
+        datt, dreg = call(att)
+        assert losses[0].item() == pytest.approx(ref["loss"].item(), rel=RTOL)
+        assert torch.equal(top1.cpu(), ref["top1"]) and float(datt.abs().sum()) > 0
+        assert int(ws.view(torch.int64).abs().sum()) == 0
+
+
+def test_nan_rows_select_a_valid_anchor_like_torch_max(zsg):
+    """torch.max treats NaN as the maximum and returns the first such index (loss.py:77, evaluator.py:74).  A NaN annotation
+    (whole IoU row NaN) or all-NaN scores must give index 0, never an out-of-range index (the round-1 kernels
+    kept INT_MAX and read the anchor table out of bounds)."""
+    ops, _ = zsg
+    from oracle import synth, zsg_oracle as zo
+    B, A = 3, synth.NUM_ANCHORS
+    batch = synth.make_batch(B, seed=9)
+    annot = batch["annot"].clone()
+    annot[1, 2] = float("nan")
+    g = torch.Generator().manual_seed(9)
+    att = torch.randn(B, A, 1, generator=g)
+    att[2] = float("nan")
+    bbx = torch.randn(B, A, 4, generator=g) * 0.3
+    anchs = zo.default_anchors()
+    losses, datt, dreg, top1, pos = run_loss(ops, dev(att), dev(bbx), dev(annot), dev(anchs))
+    iou = zo.iou_gt_vs_anchors(annot, anchs)
+    assert torch.isnan(iou[1]).all()
+    want_top1 = iou.max(1)[1]                                            # CPU torch.max: first NaN = index 0
+    assert want_top1[1].item() == 0 and torch.equal(top1, want_top1)
+    assert pos[1].sum().item() == 1 and pos[1, 0]                        # nothing exceeds the threshold, only the top-1
+    assert losses.tolist() == [1.01, 1.0, 0.01]                          # NaN loss -> guard constants
+    best = torch.empty(B, dtype=torch.int64, device="cuda")
+    scores, boxes = torch.empty(B, device="cuda"), torch.empty(B, 4, dtype=torch.float64, device="cuda")
+    metrics = torch.empty(2 + 2 * B, device="cuda")
+    ops.evaluate(dev(att), 1, dev(bbx), 4, dev(annot), dev(anchs), dev(batch["img_size"]), B, A, 0.5, best, scores, boxes,
+                 metrics)
+    torch.cuda.synchronize()
+    want_best = torch.sigmoid(att).squeeze(-1).max(1)[1]
+    assert want_best[2].item() == 0 and torch.equal(best.cpu(), want_best)
+    assert torch.isnan(scores[2]).item() and 0.0 <= metrics[0].item() <= 1.0
+
+
+def test_product_anchor_table_equals_reference_golden(zsg):
+    """anchors.create_anchors of the PRODUCT package (what the loss / evaluator kernels read) bit-equal to the table the real
+    reference produced (tests/golden/anchors.npz): fp64, with the fp32-rounded 2/h factor of anchors.py:66-87."""
+    from zsg_b200.anchors import create_anchors
+    from oracle import synth
+    ratios, scales = synth.ratios_scales()
+    a = create_anchors([(s, s) for s in synth.LEVEL_SIZES], ratios, scales, flatten=True, device="cuda")
+    z = load_npz("anchors")
+    assert a.dtype == torch.float64 and tuple(a.shape) == (synth.NUM_ANCHORS, 4)
+    assert np.array_equal(a.cpu().numpy(), z["anchs"])
+
+
+def test_zero_area_box_takes_the_nan_guard_like_reference(zsg):
+    """a-13: a zero-area ground-truth box has log(0) regression targets.  The reference multiplies the box loss of every anchor
+    by the positive mask (loss.py:92), so inf * 0 = NaN reaches the guard of loss.py:128-133: constants, no gradient.  (The
+    golden dump tests/golden/loss_zero_area.npz holds what the real reference returned.)"""
+    ops, _ = zsg
+    from oracle import synth, zsg_oracle as zo
+    B, A = 2, synth.NUM_ANCHORS
+    batch = synth.make_batch(B, seed=4)
+    annot = batch["annot"].clone()
+    annot[0] = torch.tensor([0.1, 0.1, 0.1, 0.4])                         # zero height
+    g = torch.Generator().manual_seed(4)
+    att, bbx = torch.randn(B, A, 1, generator=g) - 3.0, torch.randn(B, A, 4, generator=g) * 0.3
+    anchs = zo.default_anchors()
+    losses, datt, dreg, top1, pos = run_loss(ops, dev(att), dev(bbx), dev(annot), dev(anchs))
+    ref = zo.zsg_loss(att, bbx, annot, anchs)
+    z = load_npz("loss_zero_area")
+    assert [ref["loss"].item(), ref["cls_ls"].item(), ref["box_ls"].item()] == [1.01, 1.0, 0.01] == z["losses"].tolist()
+    assert losses.tolist() == [1.01, 1.0, 0.01]
+    assert torch.equal(top1, ref["top1"]) and torch.equal(pos, ref["pos"]) and np.array_equal(top1.numpy(), z["top1"])
+    assert float(datt.abs().sum()) == 0.0 and float(dreg.abs().sum()) == 0.0

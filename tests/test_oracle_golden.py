@@ -118,3 +118,35 @@ def test_upsample_index_table(golden_meta):
         i, o = (int(v) for v in key.split("->"))
         mine = [min(int(np.floor(np.float32(d) * np.float32(i / o))), i - 1) for d in range(o)]
         assert mine == ref
+
+
+def test_oracle_nan_guard_matches_reference_on_zero_area_box():
+    """loss.py:128-133 through loss.py:92 (inf * 0): the dump of the real reference (tests/golden/make_golden_extra.py)."""
+    import numpy as np
+    from oracle import synth, zsg_oracle as zo
+    z = load_npz("loss_zero_area")
+    B, A = 2, synth.NUM_ANCHORS
+    batch = synth.make_batch(B, seed=4)
+    batch["annot"][0] = torch.tensor([0.1, 0.1, 0.1, 0.4])
+    g = torch.Generator().manual_seed(4)
+    att = (torch.randn(B, A, 1, generator=g) - 3.0).requires_grad_(True)
+    bbx = (torch.randn(B, A, 4, generator=g) * 0.3).requires_grad_(True)
+    ls = zo.zsg_loss(att, bbx, batch["annot"], zo.default_anchors())
+    assert [ls["loss"].item(), ls["cls_ls"].item(), ls["box_ls"].item()] == z["losses"].tolist() == [1.01, 1.0, 0.01]
+    assert np.array_equal(ls["top1"].numpy(), z["top1"])
+    ls["loss"].backward()
+    assert att.grad is None and bbx.grad is None and float(z["datt_abs_sum"]) == 0.0
+
+
+def test_reference_parameter_registration_order():
+    """spec.reference_param_order (the order ZSGNet registers its parameters in, hence torch.optim.Adam's state indices)
+    against named_parameters() of the real reference modules (tests/golden/make_param_order.py)."""
+    import json
+    import os
+    from zsg_b200 import spec
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "param_order.json")) as f:
+        gold = json.load(f)
+    for model in ("retina", "ssd_vgg"):
+        assert spec.reference_param_order(model) == [n for n, _ in gold[model]]
+        shapes = {n: tuple(s) for n, s, _ in spec.trainable_specs(model) + spec.unused_specs(model)}
+        assert all(shapes[n] == tuple(s) for n, s in gold[model])

@@ -382,8 +382,13 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
   uint32_t mine = 0;                                        // my K blocks so far in the current chunk
   for (int kb = 0; kb < nkb; ++kb, ++is.g) {
     const uint32_t acc = (is.chunk & 1u) * 2u + is.w;
+    // Opening a chunk: my accumulator of this parity must have been drained (two chunks ago).  BOTH issuers wait, whether or
+    // not they own a K block of the chunk: each commits acc_full for its accumulator at the end of every chunk, and an
+    // issuer with nothing to do in a run of chunks (single-K-block tiles: it owns every other tile, always with the same
+    // accumulator) would otherwise complete acc_full phases faster than the drain warps consume them -- their parity wait
+    // then misses a phase and hangs (seen on the bf16 path, where K = 64 is ONE K block per tile).
+    if (kb % CHUNK_KB == 0) mbar_wait(pb.acc_empty(acc), ((is.chunk >> 1) & 1u) ^ 1u, 100 + is.g);
     if ((is.g & 1u) == is.w) {
-      if (mine == 0) mbar_wait(pb.acc_empty(acc), ((is.chunk >> 1) & 1u) ^ 1u, 100 + is.g);      // drained two chunks ago
       trace(is.g, 8);
       if (!(ablate & 1)) mbar_wait(pb.full(is.stage), is.phase, 1000 + is.g);     // ablate bit 0 (diagnostics): producers are off
       trace(is.g, 9);

@@ -318,8 +318,11 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
     for (int i = 0; i < B; ++i) box += __ldcg(box_row + i) / (double)(float)npos_row[i];
     box /= (double)B;
     float cls = (float)__ldcg(&ws->cls_sum) / (float)ws->npos_total;   // f32 / count, like loss.py:125
-    const int bad = (box != box) || (cls != cls);
-    if (bad) { box = 0.01; cls = 1.0f; }                             // loss.py:128-133
+    // loss.py:128-133.  The reference multiplies the per-anchor box loss of ALL anchors by the mask (loss.py:92): a zero-area
+    // or inverted box (log(0) / log(<0) targets) gives inf * 0 = NaN there, while only positives are evaluated here (inf):
+    // an infinite box loss is the same condition.
+    const int bad = (box != box) || (cls != cls) || isinf(box);
+    if (bad) { box = 0.01; cls = 1.0f; }
     losses[0] = lamb_reg * box + (double)cls;
     losses[1] = (double)cls;
     losses[2] = box;

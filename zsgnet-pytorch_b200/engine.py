@@ -104,6 +104,7 @@ class Engine:
         self._f64_pool, self._f64_used = torch.zeros(1 << 18, dtype=torch.float64, device=device), 0
         self.bns = []
         self.fwd_train, self.fwd_eval_bn, self.fwd, self.bwd, self.prep_bwd = [], [], [], [], []
+        self.fwd_marks = {}                                   # stage label -> [start, end) in self.fwd (stage-wise tests)
         self.inp = {}
         self.nbytes = 0
         # TF32 hi/lo images of the weights (the kernels fetch them by TMA): the whole parameter arena is split by
@@ -362,8 +363,11 @@ class Engine:
         # backward = stages in reverse forward order; gradient-ready marks for the bucketed all-reduce
         self.bucket_marks = []                            # (index into self.bwd after which arena[lo:hi] is final)
         assert len(stage_names) == len(bwd_stages)
+        self.bwd_marks = {}                               # stage label -> [start, end) in self.bwd (stage-wise tests)
         for stage, names in zip(reversed(bwd_stages), reversed(stage_names)):
+            b0 = len(self.bwd)
             stage()
+            self.bwd_marks[getattr(stage, "label", f"stage{len(self.bwd_marks)}")] = (b0, len(self.bwd))
             lo = min(st.offsets[n] for n in names)
             hi = max(st.offsets[n] + _align(st.numel(n)) for n in names)
             self.bucket_marks.append((len(self.bwd), lo, hi))
@@ -395,15 +399,17 @@ class Engine:
         c1 = self.buf(B * 150 * 150, 64)
         x0 = self.buf(B * 75 * 75, 64)
         w1 = st.flat(e + "conv1.weight")
-        self.fwd.append(("fn", lambda: ops.nchw_to_nhwc4(self.inp["img"], img4)))
+        self._img4 = img4                                     # filled by set_inputs (NCHW -> NHWC4), outside the replayed graph
         self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, 4))
         self._alloc_head_w0p()                                # region F (forward-time transformed weights) ends here
+        f0 = len(self.fwd)
         Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p_t, stats=True)
         bn1 = self.add_bn(e + "bn1", 64, B * 150 * 150)
         self.bn_forward(bn1, c1, Lstem)
         pool_arg = torch.empty(B * 75 * 75 * 64, dtype=torch.uint8, device=dev)
         self.fwd.append(("fn", lambda: ops.maxpool_bn_relu_fwd(c1, bn1.scale, bn1.shift, x0, pool_arg, B, 150, 150, 64, 75,
                                                                75)))
+        self.fwd_marks["stem"] = (f0, len(self.fwd))
         g_x0 = self.buf(B * 75 * 75, 64)
         da_stem = self.buf(B * 150 * 150, 64)
         g1 = st.grad_flat(e + "conv1.weight")
@@ -414,6 +420,7 @@ class Engine:
             self.bwd.append(lambda: dw1p.zero_())
             self.conv_wgrad(Lstem, da_stem, lo_stem, dw=dw1p)
             self.bwd.append(lambda: ops.pad_channels(dw1p, g1, 64 * 49, 4, 3))
+        stem_bwd.label = "stem"
         bwd_stages.append(stem_bwd)
 
         # ---------------- bottleneck stages (torchvision resnet50 v1.5)
@@ -428,6 +435,7 @@ class Engine:
                 ri, ro = B * h * h, B * ho * ho
                 r1, r2, r3 = self.buf(ri, width), self.buf(ro, width), self.buf(ro, 4 * width)
                 out, g_out = self.buf(ro, 4 * width), self.buf(ro, 4 * width)
+                f0 = len(self.fwd)
                 La = self.conv(p + "conv1.weight", inp, h, h, cin, width, 1, 1, 0, r1, stats=True)
                 bnA = self.add_bn(p + "bn1", width, ri)
                 self.bn_forward(bnA, r1, La)
@@ -455,7 +463,8 @@ class Engine:
                     else:
                         ops.bn_apply(r3, bnC.scale, bnC.shift, out, ro, c, True, r=inp, y_lo=out_lo)
                 self.fwd.append(("fn", tail))
-                blocks.append(dict(La=La, Lb=Lb, Lc=Lc, Ld=Ld, bnA=bnA, bnB=bnB, bnC=bnC, bnD=bnD, r1=r1, r2=r2, r3=r3,
+                self.fwd_marks[f"layer{li}.{b}"] = (f0, len(self.fwd))
+                blocks.append(dict(label=f"layer{li}.{b}", inp=inp, out_lo=out_lo, h=h, ho=ho, cin=cin, La=La, Lb=Lb, Lc=Lc, Ld=Ld, bnA=bnA, bnB=bnB, bnC=bnC, bnD=bnD, r1=r1, r2=r2, r3=r3,
                                    rd=rd, out=out, g_out=g_out, g_in=g_in, ri=ri, ro=ro, width=width,
                                    acc_in=(b == 0 and li in (3, 4))))   # c3 / c4 also receive FPN gradients
                 max_o4, max_ow, max_iw = max(max_o4, ro * 4 * width), max(max_ow, ro * width), max(max_iw, ri * width)
@@ -487,7 +496,9 @@ class Engine:
                     self.conv_dgrad(L["La"], da1, lo1, L["g_in"], residual=dz, accumulate=L["acc_in"])
             return emit
         for k in range(len(blocks)):
-            bwd_stages.append(block_bwd(k))
+            fn = block_bwd(k)
+            fn.label = blocks[k]["label"]
+            bwd_stages.append(fn)
 
         # ---------------- FPN (fpn_resnet.py:154-178)
         c3, g_c3, _, _ = stage_out[2]
@@ -501,6 +512,7 @@ class Engine:
         for (i, o) in ((10, 19), (19, 38)):
             idx = [min(int(np.floor(np.float32(d) * np.float32(i / o))), i - 1) for d in range(o)]   # F.interpolate nearest
             up[(i, o)] = torch.tensor(idx, dtype=torch.int32, device=dev)
+        f0 = len(self.fwd)
         L51 = self.conv(f + "P5_1.weight", c5, 10, 10, 2048, 256, 1, 1, 0, p51, bias=bias("P5_1"))
         L52 = self.conv(f + "P5_2.weight", p51, 10, 10, 256, 256, 3, 1, 1, fl[2], bias=bias("P5_2"))
         L41 = self.conv(f + "P4_1.weight", c4, 19, 19, 1024, 256, 1, 1, 0, p41, bias=bias("P4_1"))
@@ -512,6 +524,7 @@ class Engine:
         L6 = self.conv(f + "P6.weight", c5, 10, 10, 2048, 256, 3, 2, 1, fl[3], bias=bias("P6"))
         L7 = self.conv(f + "P7_2.weight", fl[3], 5, 5, 256, 256, 3, 2, 1, fl[4], in_relu=True, bias=bias("P7_2"))
         self.fwd.append(("fn", lambda: ops.avgpool_fwd(fl[4], fl[5], B, 9, 256)))
+        self.fwd_marks["fpn"] = (f0, len(self.fwd))
 
         def gbias(n, dy, rows):
             gb = st.grad_flat(f + n + ".bias")
@@ -534,9 +547,10 @@ class Engine:
             layer("P5_2", L52, dfl[2], B * 100, dp51)
             self.bwd.append(lambda: ops.upsample_add_bwd(dp41, dp51, up[(10, 19)], up[(10, 19)], B, 19, 19, 10, 10, 256))
             layer("P5_1", L51, dp51, B * 100, g_c5, accumulate=True)
+        fpn_bwd.label = "fpn"
         bwd_stages.append(fpn_bwd)
         stage_names += self._stage_param_names(len(blocks))
-        return dict(x0=x0, c1=c1, c3=c3, c4=c4, c5=c5, blocks=blocks)
+        return dict(x0=x0, g_x0=g_x0, c1=c1, c3=c3, c4=c4, c5=c5, g_c3=g_c3, g_c4=g_c4, g_c5=g_c5, blocks=blocks, fl=fl, dfl=dfl)
 
     def _build_ssd_vgg(self, bwd_stages, stage_names, fl, dfl):
         """mdl_to_use='ssd_vgg' (config 5): SSDBackBone.encode_feats (mdl.py:162-168) = SSD.forward (ssd_vgg.py:54-102).
@@ -568,7 +582,7 @@ class Engine:
         img4 = self.buf(B, 300, 300, 4)
         w1 = st.flat(e + "vgg.0.weight")
         w1p_t = self.pool_alloc(64 * 9 * 4)
-        self.fwd.append(("fn", lambda: ops.nchw_to_nhwc4(self.inp["img"], img4)))
+        self._img4 = img4
         self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p_t[0], 64 * 9, 3, 4))
         self._alloc_head_w0p()
         x, gx, h, cin, x_is_relu = img4, None, 300, 4, False
@@ -697,6 +711,8 @@ class Engine:
                                                          P("bias_ih_l0_reverse"), P("bias_hh_l0_reverse"), h0c0[2],
                                                          h0c0[3], lens, B, T, E, xlast, rgates, lang)))
         self._lstm_items = (lstm_first, len(self.fwd))
+        self.fwd_marks["lstm"] = self._lstm_items
+        head_first = len(self.fwd)
         Gd = lambda n: st.grad_flat("lstm." + n)
 
         def lstm_bwd():
@@ -711,6 +727,7 @@ class Engine:
                                     impl=self.impl))
             self.bwd.append(lambda: ops.colsum(drgates, Gd("bias_ih_l0_reverse"), B, G))
             self.bwd.append(lambda: Gd("bias_hh_l0_reverse").copy_(Gd("bias_ih_l0_reverse")))
+        lstm_bwd.label = "lstm"
         bwd_stages.append(lstm_bwd)
 
         # ---------------- fusion + shared six-level head (mdl.py:69-104, 235-254, 379-382)
@@ -765,8 +782,9 @@ class Engine:
         w5h, w5l = self.weight_operand("att_reg_box.5.weight", hb16)
         self.fwd.append(("op", ConvOp(hs[4], w5h, out, rows_last, M, 256, 45, 3, 3, bias=st.flat("att_reg_box.5.bias"),
                                       impl=self.impl, w_lo=w5l, x_lo=hs_lo[4])))
+        self.fwd_marks["head"] = (head_first, len(self.fwd))
         self.d_out = self.buf(B, A, 5)
-        self.dbg = dict(feat=feat, lang=lang, hs=hs, fused=fused, lvl_off=lvl_off, **dbg)
+        self.dbg = dict(feat=feat, dfeat=dfeat, lang=lang, dlang=dlang, hs=hs, fused=fused, lvl_off=lvl_off, **dbg)
         wt5 = self.buf(256 * 9 * 45)
         wt5p_t = self.pool_alloc(256 * 9 * 48)
         wt5p = wt5p_t[0]
@@ -812,6 +830,7 @@ class Engine:
             self.bwd.append(ConvOp(dhs[0], wt0h, dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0l,
                                    x_lo=d0lo))
             self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
+        head_bwd.label = "head"
         bwd_stages.append(head_bwd)
 
     def _stage_param_names(self, nblocks):
@@ -832,7 +851,9 @@ class Engine:
         the host in SORTED-row order (mdl.py:307-319), re-ordered here to per-sample order."""
         B, T = self.B, self.T
         assert img.shape == (B, 3, 300, 300) and img.is_contiguous(), img.shape
-        self.inp["img"] = img
+        # every input lands in a static buffer here: the forward pass is a replayed CUDA graph and must not depend on the
+        # address of this step's batch tensors
+        ops.nchw_to_nhwc4(img, self._img4)
         Tq = qvec.shape[1]
         self.qv.view(B, T, 300)[:, :Tq].copy_(qvec)
         self.lens.copy_(lens_cpu.to(torch.int32), non_blocking=True)
