@@ -6,6 +6,13 @@ to the 1e-4 bar of BASELINE.json on its own (2e-5 where the stage has no BatchNo
 The engine is one static program; a stage is run by overwriting its input buffers (and their GEMM operand images) with the
 oracle's activations and launching only the stage's slice of the program (Engine.fwd_marks / bwd_marks).
 
+ReLU decisions.  Where a pre-activation lies within fp32 rounding noise of zero, two correct forward passes disagree on
+relu'(x); with the random +-1-sized output gradients used here, a handful of such flips among the 5.8 M activations of a
+layer1 block already moves a bias gradient by 1e-3 (measured: forward 1e-6, backward 1e-6 in blocks without a flip, 2e-3 in
+blocks with one).  The backward comparison therefore runs the oracle with the ENGINE's ReLU masks (oracle relu_masks): same
+function on both sides, every kernel of the backward still checked end to end.  The number of disagreeing decisions is
+printed.
+
 dtype 'bf16' runs the same stages on the bf16 operand path against the oracle in conv_mode('bf16') (same arithmetic, see
 oracle/zsg_oracle.py): what is left is summation order plus values that sit on a bf16 rounding boundary and round the other
 way (one bf16 ulp = 0.4 %, on a ~1e-4 fraction of a layer's elements), hence 2e-3 instead of 1e-4."""
@@ -20,6 +27,16 @@ B = 4
 
 def nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous().view(-1, t.shape[1])
+
+
+def rows_to_nchw(buf, h, w):
+    """engine buffer [B*h*w, C] (NHWC rows) -> CPU NCHW"""
+    return buf.view(B, h, w, -1).permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def bn_relu_mask(x, bn, h, w):
+    """the engine's decision relu'(x * scale + shift) of a BatchNorm + ReLU on load (sign of the fused multiply-add)"""
+    return rows_to_nchw((x.double() * bn.scale.double() + bn.shift.double()) > 0, h, w)
 
 
 def err(a, b):
@@ -109,12 +126,12 @@ def test_stem_stage(st):
     e = "backbone.encoder."
     keys = [e + "conv1.weight", e + "bn1.weight", e + "bn1.bias"]
     sd = st.sdg(keys)
-    with zo.conv_mode(st.dtype):
+    st.ops.nchw_to_nhwc4(st.batch["img"].cuda(), eng._img4)
+    st.fwd("stem")
+    with zo.conv_mode(st.dtype), zo.relu_masks([bn_relu_mask(eng.dbg["c1"], eng.bns[0], 150, 150)]):
         y = zo.stem(sd, st.batch["img"], zo.BNState(sd, True))
         G = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
         (y * G).sum().backward()
-    st.ops.nchw_to_nhwc4(st.batch["img"].cuda(), eng._img4)
-    st.fwd("stem")
     assert err(eng.dbg["x0"], nhwc(y)) < st.tol_bn
     st.bwd("stem", lambda: st.put(eng.dbg["g_x0"], G))
     for k in keys:
@@ -133,12 +150,17 @@ def test_bottleneck_stage(st, label):
     sd = st.sdg(keys)
     x = st.acts[label].clone().requires_grad_(True)
     stride = 2 if (label.endswith(".0") and not label.startswith("layer1")) else 1
-    with zo.conv_mode(st.dtype):
+    st.put(blk["inp"], x)
+    st.fwd(label)
+    h, ho = blk["h"], blk["ho"]
+    masks = [bn_relu_mask(blk["r1"], blk["bnA"], h, h), bn_relu_mask(blk["r2"], blk["bnB"], ho, ho),
+             rows_to_nchw(blk["out"] > 0, ho, ho)]
+    with zo.conv_mode(st.dtype), zo.relu_masks(masks):
         y = zo.bottleneck(sd, x, p, stride, zo.BNState(sd, True))
         G = torch.randn(y.shape, generator=torch.Generator().manual_seed(2))
         (y * G).sum().backward()
-    st.put(blk["inp"], x)
-    st.fwd(label)
+    print(f"{st.dtype} {label}: forward {err(blk['out'], nhwc(y)):.2e}; {int(((y > 0) != masks[2]).sum())} of {y.numel()} final "
+          "ReLU decisions differ between engine and oracle")
     assert err(blk["out"], nhwc(y)) < st.tol_bn
 
     def fill():
@@ -156,14 +178,14 @@ def test_fpn_stage(st):
     keys = [k for k in st.sd if k.startswith("backbone.fpn.")]
     sd = st.sdg(keys)
     cs = [st.inter[k].clone().requires_grad_(True) for k in ("c3", "c4", "c5")]
-    with zo.conv_mode(st.dtype):
+    for name, c in zip(("c3", "c4", "c5"), cs):
+        st.put(eng.dbg[name], c)
+    st.fwd("fpn")
+    with zo.conv_mode(st.dtype), zo.relu_masks([rows_to_nchw(eng.dbg["fl"][3] > 0, 5, 5)]):      # relu(p6) in front of P7_2
         feats = zo.fpn(sd, *cs)
         gen = torch.Generator().manual_seed(3)
         Gs = [torch.randn(f.shape, generator=gen) for f in feats]
         sum((f * g).sum() for f, g in zip(feats, Gs)).backward()
-    for name, c in zip(("c3", "c4", "c5"), cs):
-        st.put(eng.dbg[name], c)
-    st.fwd("fpn")
     for i, f in enumerate(feats):
         assert err(eng.dbg["fl"][i], nhwc(f)) < st.tol, i
     st.bwd("fpn", lambda: [st.put(eng.dbg["dfl"][i], g) for i, g in enumerate(Gs)])
@@ -181,15 +203,18 @@ def test_fusion_head_stage(st):
     sd = st.sdg(keys)
     feats = [f.clone().requires_grad_(True) for f in st.inter["feats"]]
     lang = st.inter["lang"].clone().requires_grad_(True)
-    with zo.conv_mode(st.dtype):
-        att, bbx = zo.fuse_and_head(sd, feats, lang)
-        packed = torch.cat([bbx, att], dim=2)
-        G = torch.randn(packed.shape, generator=torch.Generator().manual_seed(4))
-        (packed * G).sum().backward()
     for i, f in enumerate(feats):
         st.put(eng.dbg["fl"][i], f)
     eng.lang.copy_(lang.detach().cuda())
     st.fwd("head")
+    lvl_off, sizes = eng.dbg["lvl_off"], st.synth.LEVEL_SIZES
+    masks = [rows_to_nchw(eng.dbg["hs"][i][lvl_off[lv]:lvl_off[lv + 1]] > 0, s, s)          # oracle order: level-major, 5 ReLUs each
+             for lv, s in enumerate(sizes) for i in range(5)]
+    with zo.conv_mode(st.dtype), zo.relu_masks(masks):
+        att, bbx = zo.fuse_and_head(sd, feats, lang)
+        packed = torch.cat([bbx, att], dim=2)
+        G = torch.randn(packed.shape, generator=torch.Generator().manual_seed(4))
+        (packed * G).sum().backward()
     assert err(eng.out, packed) < st.tol
     st.bwd("head", lambda: eng.d_out.copy_(G.cuda()))
     for i, f in enumerate(feats):
