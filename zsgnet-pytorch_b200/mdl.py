@@ -218,8 +218,9 @@ class ZSGNet(nn.Module):
         if img.device != dev:
             raise RuntimeError(f"zsg_b200: inputs must be on {dev} (got {img.device}); no CPU path exists")
         B = img.shape[0]
-        # mdl.py:357: the reference synchronises here too (qlens.max().item())
-        qlens_cpu = qlens.detach().cpu()
+        # mdl.py:357: the reference synchronises here (qlens.max().item()); a host copy that came with the batch
+        # (dat_loader.DevicePrefetcher adds `qlens_cpu`) avoids the read-back
+        qlens_cpu = inp["qlens_cpu"] if "qlens_cpu" in inp else qlens.detach().cpu()
         max_qlen = check_qlens(qlens_cpu, qvec.shape[1])
         qvec = qvec[:, :max_qlen, :]
         # mdl.py:279-294, 307: h0 then c0 from the global CPU RNG, consumed in sorted-row order (309-319)
