@@ -328,13 +328,13 @@ def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=Tr
             for i in range(n):
                 yield host[i % nres]
 
-        for batch in dat_loader.DevicePrefetcher(host_batches(3), dev):             # warm-up
+        for batch in dat_loader.DevicePrefetcher(host_batches(3), dev, lstm_state=True):             # warm-up
             e2e_step(batch)
         barrier()
         t0 = time.perf_counter()
         # every step's batch is copied host -> device inside the timed region (utils.py:405-406), one step ahead on a
         # copy stream; every step ends with the device -> host read of its loss and metric (utils.py:426 formats the loss)
-        for batch in dat_loader.DevicePrefetcher(host_batches(steps), dev):
+        for batch in dat_loader.DevicePrefetcher(host_batches(steps), dev, lstm_state=True):
             lt, at = e2e_step(batch)
             lv, av = float(lt.item()), float(at.item())
         torch.cuda.synchronize()

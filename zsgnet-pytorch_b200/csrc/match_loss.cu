@@ -232,6 +232,23 @@ __device__ __forceinline__ LossTerms loss_terms(float x, const float r[4], bool 
   return o;
 }
 
+// block-wide sum of a double (all threads call; result valid in thread 0); `red` holds 8 doubles
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();                                                  // previous use of `red` is over
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+// Persistent blocks over tiles of 256 anchors (a contiguous tile range per block, so a block changes row at most a few
+// times): the class-loss sum is carried in registers across tiles and the per-row box sums are flushed when the row
+// changes, which leaves ~3 same-address atomics per BLOCK.  One block per tile (4416 blocks at B = 64, each with an
+// atomicAdd on cls_sum and on the ticket) was bound by exactly those: same-address atomics retire one every ~5 ns, 44 us
+// for a kernel that moves 45 MB.
 template <bool PACKED>
 __global__ void __launch_bounds__(256) loss_grad_kernel(
     const float* __restrict__ att, int64_t att_stride, const float* __restrict__ reg, int64_t reg_stride,
@@ -239,74 +256,86 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
     float alpha, float gamma, double lamb_reg, float* __restrict__ d_att, int64_t d_att_stride,
     float* __restrict__ d_reg, int64_t d_reg_stride, uint8_t* __restrict__ wsb, double* __restrict__ losses) {
   __shared__ __align__(16) float tile[PACKED ? 256 * 5 : 4];
+  __shared__ double red[8];
+  __shared__ bool last;
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
   double* box_row = reinterpret_cast<double*>(wsb + ws_box_off());
   int* npos_row = reinterpret_cast<int*>(wsb + ws_npos_off(B));
-  const int b = blockIdx.y;
-  const int a0 = blockIdx.x * 256;
-  const int a = a0 + threadIdx.x;
-  const int na = min(256, A - a0);                                  // anchors of this block
-  double cls_l = 0.0, box_l = 0.0;
+  const int tiles_per_row = (A + 255) / 256;
+  const int total_tiles = tiles_per_row * B;
+  const int t0 = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int t1 = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
   const float inv_np = 1.0f / (float)ws->npos_total;
-  if (PACKED) {
-    // reg points at element [0, 0, 0] of the packed buffer, d_reg likewise; rows start 16-byte aligned (A * 5 % 4 == 0)
-    const float* src = reg + ((size_t)b * A + a0) * 5;
-    float* dst = d_reg + ((size_t)b * A + a0) * 5;
-    const int nf = na * 5;                                          // floats of this block; a0 * 5 % 4 == 0
-    for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
-      if (i + 3 < nf) *reinterpret_cast<float4*>(tile + i) = __ldg(reinterpret_cast<const float4*>(src + i));
-      else for (int k = i; k < nf; ++k) tile[k] = __ldg(src + k);
+  double cls_acc = 0.0, box_acc = 0.0;
+  int cur_b = -1;
+  for (int t = t0; t < t1; ++t) {
+    const int b = t / tiles_per_row;
+    const int a0 = (t - b * tiles_per_row) * 256;
+    if (b != cur_b) {                                               // block-uniform
+      if (cur_b >= 0) {
+        const double bx = block_sum(box_acc, red);
+        if (threadIdx.x == 0 && bx != 0.0) atomicAdd(&box_row[cur_b], bx);
+      }
+      box_acc = 0.0;
+      cur_b = b;
     }
-    __syncthreads();
-    LossTerms o;
-    if (a < A) {
-      const float r[4] = {tile[threadIdx.x * 5], tile[threadIdx.x * 5 + 1], tile[threadIdx.x * 5 + 2], tile[threadIdx.x * 5 + 3]};
-      const float x = tile[threadIdx.x * 5 + 4];
-      o = loss_terms(x, r, pos[(size_t)b * A + a] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg, inv_np, npos_row[b]);
-      cls_l = o.cls_l;
-      box_l = o.box_l;
-    }
-    __syncthreads();
-    if (a < A) {
-      float* q = tile + threadIdx.x * 5;
-      q[0] = o.d_reg.x; q[1] = o.d_reg.y; q[2] = o.d_reg.z; q[3] = o.d_reg.w; q[4] = o.d_att;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
-      if (i + 3 < nf) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(tile + i);
-      else for (int k = i; k < nf; ++k) dst[k] = tile[k];
-    }
-  } else if (a < A) {
-    const size_t e = (size_t)b * A + a;
-    const float* rp = reg + e * reg_stride;
-    const float r[4] = {rp[0], rp[1], rp[2], rp[3]};
-    const LossTerms o = loss_terms(att[e * att_stride], r, pos[e] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg,
-                                   inv_np, npos_row[b]);
-    cls_l = o.cls_l;
-    box_l = o.box_l;
-    d_att[e * d_att_stride] = o.d_att;
-    float* dp = d_reg + e * d_reg_stride;
-    if (d_reg_stride == 4) {
-      *reinterpret_cast<float4*>(dp) = o.d_reg;
-    } else {
-      dp[0] = o.d_reg.x; dp[1] = o.d_reg.y; dp[2] = o.d_reg.z; dp[3] = o.d_reg.w;
+    const int a = a0 + threadIdx.x;
+    const int na = min(256, A - a0);                                // anchors of this tile
+    if (PACKED) {
+      // reg points at element [0, 0, 0] of the packed buffer, d_reg likewise; rows start 16-byte aligned (A * 5 % 4 == 0)
+      const float* src = reg + ((size_t)b * A + a0) * 5;
+      float* dst = d_reg + ((size_t)b * A + a0) * 5;
+      const int nf = na * 5;                                        // floats of this tile; a0 * 5 % 4 == 0
+      for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
+        if (i + 3 < nf) *reinterpret_cast<float4*>(tile + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+        else for (int k = i; k < nf; ++k) tile[k] = __ldg(src + k);
+      }
+      __syncthreads();
+      LossTerms o;
+      if (a < A) {
+        const float r[4] = {tile[threadIdx.x * 5], tile[threadIdx.x * 5 + 1], tile[threadIdx.x * 5 + 2], tile[threadIdx.x * 5 + 3]};
+        const float x = tile[threadIdx.x * 5 + 4];
+        o = loss_terms(x, r, pos[(size_t)b * A + a] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg, inv_np, npos_row[b]);
+        cls_acc += o.cls_l;
+        box_acc += o.box_l;
+      }
+      __syncthreads();
+      if (a < A) {
+        float* q = tile + threadIdx.x * 5;
+        q[0] = o.d_reg.x; q[1] = o.d_reg.y; q[2] = o.d_reg.z; q[3] = o.d_reg.w; q[4] = o.d_att;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
+        if (i + 3 < nf) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(tile + i);
+        else for (int k = i; k < nf; ++k) dst[k] = tile[k];
+      }
+      __syncthreads();                                              // the tile buffer is reused by the next tile
+    } else if (a < A) {
+      const size_t e = (size_t)b * A + a;
+      const float* rp = reg + e * reg_stride;
+      const float r[4] = {rp[0], rp[1], rp[2], rp[3]};
+      const LossTerms o = loss_terms(att[e * att_stride], r, pos[e] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg,
+                                     inv_np, npos_row[b]);
+      cls_acc += o.cls_l;
+      box_acc += o.box_l;
+      d_att[e * d_att_stride] = o.d_att;
+      float* dp = d_reg + e * d_reg_stride;
+      if (d_reg_stride == 4) {
+        *reinterpret_cast<float4*>(dp) = o.d_reg;
+      } else {
+        dp[0] = o.d_reg.x; dp[1] = o.d_reg.y; dp[2] = o.d_reg.z; dp[3] = o.d_reg.w;
+      }
     }
   }
-  // block reduction -> one atomic per block and quantity
-  __shared__ double red[2][8];
-  __shared__ bool last;
-  cls_l = warp_sum(cls_l);
-  box_l = warp_sum(box_l);
-  const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
-  if (l_ == 0) { red[0][w_] = cls_l; red[1][w_] = box_l; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double c = 0.0, bx = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { c += red[0][i]; bx += red[1][i]; }
-    atomicAdd(&ws->cls_sum, c);
-    if (bx != 0.0) atomicAdd(&box_row[b], bx);
-    __threadfence();                                                // sums and this block's gradients before the ticket
-    last = atomicAdd(&ws->loss_ticket, 1u) == gridDim.x * gridDim.y - 1;
+  {
+    const double bx = block_sum(box_acc, red);
+    const double c = block_sum(cls_acc, red);
+    if (threadIdx.x == 0) {
+      if (cur_b >= 0 && bx != 0.0) atomicAdd(&box_row[cur_b], bx);
+      atomicAdd(&ws->cls_sum, c);
+      __threadfence();                                              // sums and this block's gradients before the ticket
+      last = atomicAdd(&ws->loss_ticket, 1u) == gridDim.x - 1;
+    }
   }
   __syncthreads();
   if (!last) return;
@@ -479,7 +508,8 @@ extern "C" int zsg_match_loss(const float* att, int64_t att_stride, const float*
   const int per_chunk = (a + nch - 1) / nch;
   nch = (a + per_chunk - 1) / per_chunk;
   match_rows_kernel<<<dim3(nch, b), 256, 0, st>>>(annot, anchors, a, per_chunk, match_thr, use_multi, pos, top1, wsb, b);
-  dim3 grid((a + 255) / 256, b);
+  const int total_tiles = ((a + 255) / 256) * b;
+  const int grid = total_tiles < num_sms() * 4 ? total_tiles : num_sms() * 4;     // persistent: ~4 blocks per SM
   const bool packed = att_stride == 5 && reg_stride == 5 && d_att_stride == 5 && d_reg_stride == 5 && att == reg + 4 &&
                       d_att == d_reg + 4 && ((((uintptr_t)reg | (uintptr_t)d_reg) & 15) == 0) && (a % 4 == 0);
   if (packed)

@@ -174,11 +174,16 @@ class DevicePrefetcher:
     in order, and the step that is starting has a few tiny host-to-device copies of its own (query lengths, LSTM initial
     states) -- behind one monolithic image copy of the NEXT batch they, and the whole forward pass with them, waited
     for it (measured: the end-to-end step was slower than the device-resident one by exactly the image copy time).
-    `qlens_cpu` (the host copy of the query lengths) rides along so that the model does not read them back."""
+    `qlens_cpu` (the host copy of the query lengths) rides along so that the model does not read them back.
+
+    lstm_state=True also stages what the model would otherwise copy at the start of its forward pass: the int32 query
+    lengths and the two torch.randn(2, B, 128) draws of mdl.py:279-294 (made here, when the batch is fetched, from the
+    same global CPU RNG and in batch order -- the values a forward pass would draw if nothing else consumed the RNG in
+    between).  The step then starts without any host-to-device copy queued behind the next batch's image."""
     CHUNK_BYTES = 4 << 20
 
-    def __init__(self, batches, device):
-        self.it, self.device = iter(batches), torch.device(device)
+    def __init__(self, batches, device, lstm_state=False):
+        self.it, self.device, self.lstm_state = iter(batches), torch.device(device), lstm_state
         self.stream = torch.cuda.Stream(device=self.device)
         self.next = self._fetch()
 
@@ -198,8 +203,15 @@ class DevicePrefetcher:
             host = next(self.it)
         except StopIteration:
             return None
+        extra = {}
+        if self.lstm_state and "qlens" in host:
+            from .engine import Engine
+            from .mdl import draw_lstm_state
+            h0, c0, inv = draw_lstm_state(host["qlens"])
+            extra["_zsg_h0c0"] = Engine.lstm_state_per_sample(h0, c0, inv).pin_memory()
+            extra["_zsg_lens"] = host["qlens"].to(torch.int32).pin_memory()
         with torch.cuda.stream(self.stream):
-            dev = {k: self._to_device(v) for k, v in host.items()}
+            dev = {k: self._to_device(v) for k, v in list(host.items()) + list(extra.items())}
             ev = torch.cuda.Event()
             ev.record(self.stream)
         if "qlens" in host and "qlens_cpu" not in host:

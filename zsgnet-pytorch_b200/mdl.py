@@ -46,12 +46,25 @@ def check_qlens(qlens_cpu, t_avail):
     return hi
 
 
+def draw_lstm_state(qlens_cpu):
+    """mdl.py:279-294: h0 then c0 ~ torch.randn(2, B, 128) from the global CPU RNG, assigned to the rows of the
+    length-sorted batch (mdl.py:307-319).  Returns (h0, c0, inverse permutation)."""
+    B = qlens_cpu.shape[0]
+    h0 = torch.randn(2, B, 128)
+    c0 = torch.randn(2, B, 128)
+    _, perm = qlens_cpu.sort(0, descending=True)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(B)
+    return h0, c0, inv
+
+
 class _ZSGNetFn(torch.autograd.Function):
     """One autograd node for the whole network: forward = engine.forward, backward = engine.backward."""
 
     @staticmethod
     def forward(ctx, net, eng, img, qvec, lens_cpu, inv_perm, h0, c0, *params):
-        eng.set_inputs(img, qvec, lens_cpu, inv_perm, h0, c0)
+        eng.set_inputs(img, qvec, lens_cpu, inv_perm, h0, c0, staged=net._staged)
+        net._staged = None
         out = eng.forward(training=net.training)
         ctx.net, ctx.eng = net, eng
         eng.pending_backward = net.training
@@ -139,6 +152,7 @@ class ZSGNet(nn.Module):
             _attach(self, name, t, False)
         self._engines = {}
         self._on_bucket = None
+        self._staged = None
         self._param_list = [self.get_parameter(n) for n in self.param_names]
         self._grad_views = [self.store.grad_view(n) for n in self.param_names]
         # cfg key `zsg_direct_grads` (or the attribute): hand gradients to the optimiser by pointing param.grad at the
@@ -146,6 +160,8 @@ class ZSGNet(nn.Module):
         # DistributedDataParallel needs the AccumulateGrad hooks of the ordinary path.
         self.direct_grads = bool(get("zsg_direct_grads", False))
         self._anchor = torch.zeros((), device=dev, requires_grad=True)
+        self._feat_sizes = torch.tensor([[s, s] for s in spec.LEVEL_SIZES], device=dev)
+        self._num_f_out = torch.tensor([len(spec.LEVEL_SIZES)], device=dev)
         self.reset_parameters()
 
     # ------------------------------------------------------------------ init / state
@@ -223,20 +239,25 @@ class ZSGNet(nn.Module):
         qlens_cpu = inp["qlens_cpu"] if "qlens_cpu" in inp else qlens.detach().cpu()
         max_qlen = check_qlens(qlens_cpu, qvec.shape[1])
         qvec = qvec[:, :max_qlen, :]
-        # mdl.py:279-294, 307: h0 then c0 from the global CPU RNG, consumed in sorted-row order (309-319)
-        h0 = torch.randn(2, B, 128)
-        c0 = torch.randn(2, B, 128)
-        _, perm = qlens_cpu.sort(0, descending=True)
-        inv = torch.empty_like(perm)
-        inv[perm] = torch.arange(B)
+        # mdl.py:279-294, 307: h0 then c0 from the global CPU RNG, consumed in sorted-row order (309-319).  A batch that
+        # comes from dat_loader.DevicePrefetcher(lstm_state=True) carries both draws (made when the batch was fetched, in
+        # batch order) and the int32 lengths on the device already.
+        self._staged = None
+        h0 = c0 = inv = None
+        if "_zsg_h0c0" in inp and "_zsg_lens" in inp:
+            self._staged = (inp["_zsg_lens"], inp["_zsg_h0c0"])
+        else:
+            h0, c0, inv = draw_lstm_state(qlens_cpu)
         eng = self.engine_for(B, max(max_qlen, 1))
         params = [self._anchor] if self.direct_grads else self._param_list
         out = _ZSGNetFn.apply(self, eng, img.contiguous().float(), qvec.float(), qlens_cpu, inv, h0, c0, *params)
         if self.training:
             self._bn_n.add_(1)                                    # num_batches_tracked
-        feat_sizes = torch.tensor([[s, s] for s in spec.LEVEL_SIZES], device=dev)
-        return {"att_out": out[..., 4:], "bbx_out": out[..., :4], "feat_sizes": feat_sizes,
-                "num_f_out": torch.tensor([len(spec.LEVEL_SIZES)], device=dev)}
+        # constants of the output dict (mdl.py:391-395 builds them per forward with two small host-to-device copies; here
+        # they are made once: a per-step copy on this stream would queue behind the prefetch of the next batch's image on
+        # the DMA engine and hold up everything launched after it)
+        return {"att_out": out[..., 4:], "bbx_out": out[..., :4], "feat_sizes": self._feat_sizes.clone(),
+                "num_f_out": self._num_f_out.clone()}
 
 
 def get_default_net(num_anchors=1, cfg=None):
