@@ -295,17 +295,26 @@ def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=Tr
                        bufs["losses"], dflat[4:], 5, eng.d_out, 5, bufs["top1"], bufs["pos"], bufs["ws"])
     loss_pass()
     torch.cuda.synchronize()
+    # `reps` back-to-back calls captured in one CUDA graph and replayed: launched one by one from Python the two ~10 us
+    # kernels of a call are issued more slowly (~50 us of ctypes + launch overhead per call) than they execute, and the
+    # events would time the host
+    lg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(lg, capture_error_mode="thread_local"):
+        for _ in range(reps):
+            loss_pass()
+    lg.replay()
+    torch.cuda.synchronize()
     a0.record()
-    for _ in range(reps):
-        loss_pass()
+    lg.replay()
     a1.record()
     torch.cuda.synchronize()
     loss_ms = a0.elapsed_time(a1) / reps
     loss_gbs = B * A * LOSS_BYTES_PER_ANCHOR / (loss_ms / 1e3) / 1e9
     roof_hbm = {"kernel": "zsg_match_loss (match_rows_kernel + loss_grad_kernel)", "bound": "hbm", "achieved": loss_gbs,
                 "peak": pk["hbm"], "unit": "GB/s", "frac": loss_gbs / pk["hbm"], "traffic": None, "ms": loss_ms,
-                "note": f"{B * A * LOSS_BYTES_PER_ANCHOR / 1e6:.0f} MB algorithmic per call (40 B per anchor), two launches, "
-                        f"{reps} back-to-back calls on the same buffers (L2-resident at this size, as in the step)"}
+                "note": f"{B * A * LOSS_BYTES_PER_ANCHOR / 1e6:.0f} MB algorithmic per call (40 B per anchor), two launches per call; "
+                        f"{reps} back-to-back calls on the same buffers replayed as one CUDA graph (L2-resident at this size, as in "
+                        "the step, where the head has just written the scores)"}
 
     # ---------------------------------------------------------------- e2e: public module API, host buffers
     e2e = None
@@ -334,17 +343,20 @@ def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=Tr
         t0 = time.perf_counter()
         # every step's batch is copied host -> device inside the timed region (utils.py:405-406), one step ahead on a
         # copy stream; every step ends with the device -> host read of its loss and metric (utils.py:426 formats the loss)
+        marks = [t0]
         for batch in dat_loader.DevicePrefetcher(host_batches(steps), dev, lstm_state=True):
             lt, at = e2e_step(batch)
             lv, av = float(lt.item()), float(at.item())
+            marks.append(time.perf_counter())
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
+        step_ms = [round((b - a) * 1e3, 2) for a, b in zip(marks, marks[1:])]
         h2d = sum(v.numel() * v.element_size() for v in host[0].values())
         e2e = {"value": B * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                "ms_per_step": dt / steps * 1e3, "api": "mdl.get_default_net(cfg)(batch) -> loss.get_default_loss -> "
                ".backward() -> optim.FusedAdam.step -> evaluator.get_default_eval (cfg zsg_direct_grads: param.grad are views of the "
                "gradient arena); dat_loader.DevicePrefetcher copies every step's pinned host batch to the device one step ahead "
-               "on a copy stream", "last_loss": lv, "last_acc": av}
+               "on a copy stream", "last_loss": lv, "last_acc": av, "step_ms": step_ms}
         net._on_bucket = None
 
     nsteps_total = warmup + steps + 1 + psteps + ((steps + 3) if want_e2e else 0)

@@ -143,6 +143,8 @@ int zsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, zsg_stream_t
 int zsg_pad_channels(const float* src, float* dst, int64_t n, int csrc, int cdst, zsg_stream_t stream);
 /* NCHW image -> NHWC with 4 channels (4th = 0) for the stem (mdl.py:149). */
 int zsg_nchw_to_nhwc4(const float* img, float* out, int b, int h, int w, zsg_stream_t stream);
+/* bf16 operand path: NCHW image -> NHWC with 8 bfloat16 channels (r, g, b, 0 x 5): padded image and GEMM operand image in one. */
+int zsg_nchw_to_nhwc8_bf16(const float* img, uint16_t* out, int b, int h, int w, zsg_stream_t stream);
 /* column sums: out[c] (+)= sum_rows x[row*ld + c]   (bias gradients of FPN/head convs and LSTM). */
 int zsg_colsum(const float* x, float* out, int64_t rows, int c, int ld, int accumulate, zsg_stream_t stream);
 /* dst[i][0:cdst] = src[rows[i].out + 0:csrc] (zero padded): turns the packed [B,A,5] head gradient

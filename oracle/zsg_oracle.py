@@ -32,7 +32,7 @@ from . import synth
 # "bf16": what BASELINE configs 3-5 call "bf16 tensor-core convs", restated as the arithmetic the product computes: both
 #   operands of every contraction rounded to bfloat16 (round-to-nearest-even), products exact, accumulation and output
 #   in fp32 -- forward (x, w), data gradient (dy, w) and weight gradient (x, dy) alike; bias gradients from the unrounded
-#   dy.  The 3-channel stem convolution (and the LSTM, which is not a convolution) stay fp32, as in the product.
+#   dy.  The LSTM (not a convolution) stays fp32, as in the product.
 #   The reference has no bf16 mode of its own; the closest thing it offers, torch.autocast(bfloat16) around the same
 #   modules, additionally rounds every conv OUTPUT to bf16 (tests/test_bf16_network_gpu.py measures both against fp32).
 CONV_MODE = ["fp32"]
@@ -114,7 +114,7 @@ def relu(x):
 
 
 def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1):
-    if CONV_MODE[0] == "bf16" and x.shape[1] >= 8:          # all but the 3-channel stem (the 514-channel fused input is padded to 520)
+    if CONV_MODE[0] == "bf16":                              # every convolution (the LSTM is not one and stays fp32)
         return _Bf16OperandConv.apply(x, w, bias, stride, padding, dilation)
     return F.conv2d(x, w, bias, stride=stride, padding=padding, dilation=dilation)
 

@@ -60,8 +60,8 @@ def test_bf16_engine_uses_bf16_kernels(bf16_stack):
     from zsg_b200 import ops
     eng = net.engine_for(2, 20)
     kinds = [it[1].kernel for it in eng.fwd if it[0] == "op"]
-    assert kinds.count("conv_bf16_kernel") == 66 and kinds.count("conv_tc_async_kernel") == 2
-    assert sum(1 for o in eng.bwd if isinstance(o, ops.WgradOp) and o.kernel == "wgrad_bf16_kernel") == 66
+    assert kinds.count("conv_bf16_kernel") == 67 and kinds.count("conv_tc_async_kernel") == 1     # fp32: LSTM projection only
+    assert sum(1 for o in eng.bwd if isinstance(o, ops.WgradOp) and o.kernel == "wgrad_bf16_kernel") == 67
 
 
 @pytest.mark.parametrize("B,seed,var_len", [(2, 21, False), (3, 22, True)])
@@ -162,3 +162,44 @@ def test_graph_replay_matches_eager_launches():
             assert float((e[j] - g[j]).norm() / e[j].norm()) < 1e-4, (i, j)
     # BatchNorm running statistics were updated by every replay (4 training steps)
     assert int(net.state_dict()["backbone.encoder.bn1.num_batches_tracked"]) == 4
+
+
+def test_bf16_ssd_vgg_train_step_vs_bf16_oracle():
+    """BASELINE configs[4]: SSD-VGG trunk with bf16 tensor-core convs.  No BatchNorm in this model, so the whole network is
+    comparable end to end against the oracle in the same arithmetic (conv_mode('bf16')): losses 2e-3, head outputs 5e-3 rms
+    (five max-pools and 26 ReLUs: ties at the bf16 noise level move a few windows), index work bit-exact."""
+    import zsg_b200  # noqa: F401
+    from zsg_b200 import mdl, loss, evaluator
+    from oracle import synth, zsg_oracle as zo
+    cfg = synth.default_cfg("ssd_vgg")
+    cfg["device"], cfg["zsg_dtype"] = "cuda", "bf16"
+    ratios, scales = synth.ratios_scales(cfg)
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    crit, ev = loss.get_default_loss(ratios, scales, cfg), evaluator.get_default_eval(ratios, scales, cfg)
+    B, seed = 2, 31
+    batch = synth.make_batch(B, seed=seed)
+    net.load_state_dict(synth.make_state_dict(0, "ssd_vgg"), strict=True)
+    net.train()
+    dbatch = to_dev(batch)
+    torch.manual_seed(seed)
+    out = net(dbatch)
+    ls = crit(out, dbatch)
+    ls["loss"].mean().backward()
+    torch.cuda.synchronize()
+    eng = net.engine_for(B, 20)
+    assert all(it[1].kernel in ("conv_bf16_kernel", "conv_tc_async_kernel") for it in eng.fwd if it[0] == "op")
+    assert sum(1 for it in eng.fwd if it[0] == "op" and it[1].kernel == "conv_tc_async_kernel") == 1      # LSTM projection
+    with zo.conv_mode("bf16"):
+        ols, omet, ograds, oout, _ = zo.train_step(synth.make_state_dict(0, "ssd_vgg"), batch, seed=seed, do_adam=False)
+    assert torch.equal(crit.last_top1.cpu(), ols["top1"]) and torch.equal(crit.last_pos.cpu().bool(), ols["pos"])
+    for k in ("loss", "cls_ls", "box_ls"):
+        assert ls[k].item() == pytest.approx(ols[k].item(), rel=2e-3), k
+    e_att = rms_rel(out["att_out"].detach().cpu().numpy(), oout["att_out"].detach().numpy())
+    e_bbx = rms_rel(out["bbx_out"].detach().cpu().numpy(), oout["bbx_out"].detach().numpy())
+    g = {k: float((net.get_parameter(k).grad.cpu().double() - v.double()).norm() / v.double().norm().clamp_min(1e-30))
+         for k, v in ograds.items() if v is not None}
+    head = [v for k, v in g.items() if k.startswith(("att_reg_box.", "lstm."))]
+    print(f"ssd_vgg bf16: att {e_att:.2e} bbx {e_bbx:.2e}; gradient error head/lstm median {np.median(head):.2e} max {max(head):.2e}, "
+          f"all median {np.median(list(g.values())):.2e} max {max(g.values()):.2e}")
+    assert e_att < 5e-3 and e_bbx < 5e-3
+    assert np.median(head) < 2e-2 and np.median(list(g.values())) < 5e-2

@@ -56,6 +56,7 @@ SIGNATURES = {
     "zsg_bn_apply_bf16": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
     "zsg_bn_bwd_apply_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P],
     "zsg_nchw_to_nhwc4": [_P, _P, _I, _I, _I, _P],
+    "zsg_nchw_to_nhwc8_bf16": [_P, _P, _I, _I, _I, _P],
     "zsg_colsum": [_P, _P, _L, _I, _I, _I, _P],
     "zsg_gather_rows": [_P, _P, _P, _L, _I, _I, _P],
     "zsg_bn_stats": [_P, _P, _L, _I, _P],

@@ -779,6 +779,21 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc4_kernel(const float* __restr
   }
 }
 
+// the same for the bf16 operand path: 8 bf16 channels per pixel (r, g, b, 0 x 5) = one 16-byte store, which is at once the
+// padded NHWC image and its GEMM operand image (no fp32 copy, no cast pass)
+__global__ void __launch_bounds__(256) nchw_to_nhwc8_bf16_kernel(const float* __restrict__ img, uint16_t* __restrict__ out,
+                                                                 int B, int H, int W) {
+  const int64_t n = (int64_t)B * H * W;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / plane, p = i % plane;
+    const float* s = img + b * 3 * plane + p;
+    const __nv_bfloat162 rg = __floats2bfloat162_rn(s[0], s[plane]), b0 = __floats2bfloat162_rn(s[2 * plane], 0.f);
+    uint4 u = make_uint4(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&b0), 0u, 0u);
+    *reinterpret_cast<uint4*>(out + i * 8) = u;
+  }
+}
+
 // out[c] (+)= sum_rows x[row][c]; block = 32 x 8, each block owns 32 channels and a row slab
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows,
                                                      int C, int ld) {
@@ -1116,6 +1131,12 @@ extern "C" int zsg_nchw_to_nhwc4(const float* img, float* out, int b, int h, int
   ZSG_REQUIRE(img && out, "zsg_nchw_to_nhwc4: null pointer");
   nchw_to_nhwc4_kernel<<<grid_for((int64_t)b * h * w, 256), 256, 0, as_stream(stream)>>>(img, out, b, h, w);
   return check_launch("zsg_nchw_to_nhwc4");
+}
+
+extern "C" int zsg_nchw_to_nhwc8_bf16(const float* img, uint16_t* out, int b, int h, int w, zsg_stream_t stream) {
+  ZSG_REQUIRE(img && out && b > 0 && h > 0 && w > 0 && ((uintptr_t)out & 15) == 0, "zsg_nchw_to_nhwc8_bf16: bad arguments");
+  nchw_to_nhwc8_bf16_kernel<<<grid_for((int64_t)b * h * w, 256), 256, 0, as_stream(stream)>>>(img, out, b, h, w);
+  return check_launch("zsg_nchw_to_nhwc8_bf16");
 }
 
 extern "C" int zsg_gather_rows(const float* src, const zsg_row_t* rows, float* dst, int64_t m, int csrc, int cdst,

@@ -143,6 +143,20 @@ class Engine:
         self.nbytes += t.numel() * 2
         return t
 
+    def stem_input(self, cp):
+        """The network input as the first conv reads it, filled by set_inputs (outside the replayed graph): fp32 NHWC4, or
+        on the bf16 engine NHWC8 bfloat16, which is registered as its own operand image (no cast pass).  Returns the tensor
+        handed to conv() as `x`."""
+        B = self.B
+        if cp == 8:
+            self._img4 = torch.zeros(B, 300, 300, 8, dtype=torch.bfloat16, device=self.device)
+            self.nbytes += self._img4.numel() * 2
+            x = torch.zeros(4, dtype=torch.float32, device=self.device)     # placeholder: the bf16 kernels never read `x`
+            self._operand_cache[(x.data_ptr(), B * 300 * 300, 8, id(None), False, True)] = (x, self._img4)
+            return x
+        self._img4 = self.buf(B, 300, 300, 4)
+        return self._img4
+
     def use_b16(self, cin):
         return self.bf16 and cin % 8 == 0 and self.impl == ops.IMPL_TC
 
@@ -393,17 +407,17 @@ class Engine:
                                                nparts(B * 361) * 1024, nparts(B * 100) * 2048))
 
         # ---------------- stem: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2 (mdl.py:149-152)
-        img4 = self.buf(B, 300, 300, 4)
-        w1p_t = self.pool_alloc(64 * 49 * 4)
-        w1p, dw1p = w1p_t[0], self.buf(64 * 49 * 4)           # (cin = 4: this conv keeps the fp32 path on the bf16 engine)
+        cp = 8 if self.bf16 and self.impl == ops.IMPL_TC else 4      # padded input channels (bf16: 8 = one 16-byte chunk)
+        img4 = self.stem_input(cp)
+        w1p_t = self.pool_alloc(64 * 49 * cp)
+        w1p, dw1p = w1p_t[0], self.buf(64 * 49 * cp)
         c1 = self.buf(B * 150 * 150, 64)
         x0 = self.buf(B * 75 * 75, 64)
         w1 = st.flat(e + "conv1.weight")
-        self._img4 = img4                                     # filled by set_inputs (NCHW -> NHWC4), outside the replayed graph
-        self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, 4))
+        self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, cp))
         self._alloc_head_w0p()                                # region F (forward-time transformed weights) ends here
         f0 = len(self.fwd)
-        Lstem = self.conv(e + "conv1.weight", img4, 300, 300, 4, 64, 7, 2, 3, c1, w=w1p_t, stats=True)
+        Lstem = self.conv(e + "conv1.weight", img4, 300, 300, cp, 64, 7, 2, 3, c1, w=w1p_t, stats=True)
         bn1 = self.add_bn(e + "bn1", 64, B * 150 * 150)
         self.bn_forward(bn1, c1, Lstem)
         pool_arg = torch.empty(B * 75 * 75 * 64, dtype=torch.uint8, device=dev)
@@ -419,7 +433,7 @@ class Engine:
             lo_stem = self.bn_backward(bn1, da_stem, c1, da_stem, mask_mode=1, b16=Lstem["b16"])
             self.bwd.append(lambda: dw1p.zero_())
             self.conv_wgrad(Lstem, da_stem, lo_stem, dw=dw1p)
-            self.bwd.append(lambda: ops.pad_channels(dw1p, g1, 64 * 49, 4, 3))
+            self.bwd.append(lambda: ops.pad_channels(dw1p, g1, 64 * 49, cp, 3))
         stem_bwd.label = "stem"
         bwd_stages.append(stem_bwd)
 
@@ -572,20 +586,20 @@ class Engine:
                 dwp, gw = rec["dw"], st.grad_flat(rec["name"] + ".weight")
                 self.bwd.append(lambda: dwp.zero_())
                 self.conv_wgrad(L, g, lo, dw=dwp)
-                self.bwd.append(lambda: ops.pad_channels(dwp, gw, L["cout"] * L["k"] * L["k"], 4, 3))
+                self.bwd.append(lambda: ops.pad_channels(dwp, gw, L["cout"] * L["k"] * L["k"], L["cin"], 3))
             else:
                 self.conv_wgrad(L, g, lo)
             if rec["dx"] is not None:
                 self.conv_dgrad(L, g, lo, rec["dx"], out_mask=rec["dx_mask"], accumulate=rec.get("dx_acc", False))
 
         # ---------------- VGG-16 with pool5 / dilated conv6 / conv7 (ssd_vgg.py:76-85, 111-133)
-        img4 = self.buf(B, 300, 300, 4)
+        cp = 8 if self.bf16 and self.impl == ops.IMPL_TC else 4
+        img4 = self.stem_input(cp)
         w1 = st.flat(e + "vgg.0.weight")
-        w1p_t = self.pool_alloc(64 * 9 * 4)
-        self._img4 = img4
-        self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p_t[0], 64 * 9, 3, 4))
+        w1p_t = self.pool_alloc(64 * 9 * cp)
+        self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p_t[0], 64 * 9, 3, cp))
         self._alloc_head_w0p()
-        x, gx, h, cin, x_is_relu = img4, None, 300, 4, False
+        x, gx, h, cin, x_is_relu = img4, None, 300, cp, False
         segments, seg = [], []
         src = {}
         for i, Lr in enumerate(spec.vgg_layers()):
@@ -597,7 +611,7 @@ class Engine:
                               w=w1p_t if i == 0 else None)
                 assert L["hout"] == h
                 seg.append(("conv", dict(L=L, name=name, g=gy, rows=B * h * h, dx=gx, dx_mask=x if x_is_relu else None,
-                                         dw=self.buf(64 * 9 * 4) if i == 0 else None)))
+                                         dw=self.buf(64 * 9 * cp) if i == 0 else None)))
                 x, gx, cin, x_is_relu = y, gy, co, True
                 if i == 21:                                   # relu(conv4_3): source 0 = x / ||x||_2 -> fproj1 (ssd_vgg.py:80, 97)
                     n38 = B * h * h

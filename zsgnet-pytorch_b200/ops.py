@@ -135,8 +135,9 @@ def pad_channels(src, dst, n, csrc, cdst):
 
 
 def nchw_to_nhwc4(img, out):
+    """out float32 [B,H,W,4] (fp32 path) or bfloat16 [B,H,W,8] (bf16 path: padded image = operand image)."""
     b, _, h, w = img.shape
-    call("zsg_nchw_to_nhwc4", ptr(img), ptr(out), b, h, w, stream())
+    call("zsg_nchw_to_nhwc8_bf16" if _is_bf16(out) else "zsg_nchw_to_nhwc4", ptr(img), ptr(out), b, h, w, stream())
 
 
 def colsum(x, out, rows, c, accumulate=False, ld=None):
