@@ -337,7 +337,7 @@ def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=Tr
             for i in range(n):
                 yield host[i % nres]
 
-        for batch in dat_loader.DevicePrefetcher(host_batches(3), dev, lstm_state=True):             # warm-up
+        for batch in dat_loader.DevicePrefetcher(host_batches(5), dev, lstm_state=True):             # warm-up (allocator caches)
             e2e_step(batch)
         barrier()
         t0 = time.perf_counter()
@@ -359,7 +359,7 @@ def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=Tr
                "on a copy stream", "last_loss": lv, "last_acc": av, "step_ms": step_ms}
         net._on_bucket = None
 
-    nsteps_total = warmup + steps + 1 + psteps + ((steps + 3) if want_e2e else 0)
+    nsteps_total = warmup + steps + 1 + psteps + ((steps + 5) if want_e2e else 0)
     res = {"value": value, "ms_per_step": ms_step, "gpu_launches": launches, "gpu_launches_per_step": per_step_launches,
            "cuda_graphs": bool(eng.use_graphs), "graph_launches_per_step": (1 + len(eng.segments) if world > 1 else 2) if eng.use_graphs else 0,
            "roofline": roof, "roofline_hbm": roof_hbm, "kernels": kernels,

@@ -916,7 +916,7 @@ def test_match_loss_nan_guard_and_workspace_left_clean(zsg):
         datt, dreg = call(bad)
         assert losses.cpu().tolist() == [1.0 * 0.01 + 1.0, 1.0, 0.01]
         assert float(datt.abs().sum()) == 0.0 and float(dreg.abs().sum()) == 0.0
-        head = (32 + B * 16) // 8                                          # header, box_row[B], npos_row[B], row_ticket[B]
+        head = (16 + 28 * B) // 8                                          # header + the per-row sums, counts and tickets
         assert int(ws[:head].view(torch.int64).abs().sum()) == 0           # self-cleaning (the partials behind need no zeroing)
         # the same buffers right afterwards with finite scores: the normal result (nothing stuck from the NaN call)
         ref = zo.zsg_loss(att.clone().requires_grad_(True), bbx.clone().requires_grad_(True), batch["annot"], anchs)

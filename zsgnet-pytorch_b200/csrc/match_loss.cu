@@ -82,23 +82,30 @@ __device__ __forceinline__ ArgMaxD block_argmax(ArgMaxD x, ArgMaxD* sm) {
   return r;
 }
 
-// Device workspace.  Contract: all zero before the first call; every call leaves it all zero again (the last block
-// of the loss kernel clears what the call used), so no memset sits on the stream between steps.
+// Device workspace.  Contract: all zero before the first call; every call leaves the counters zero again (the last
+// block of the loss kernel clears what the call used), so no memset sits on the stream between steps.  Partial sums are
+// written to per-tile slots and added up in a fixed order by "last block done" tickets: no floating-point atomics, so the
+// three loss scalars are bit-reproducible from run to run.
 constexpr int MATCH_MAX_CHUNKS = 32;
+constexpr int LOSS_MAX_TILES = 128;          // tiles of 256 anchors per row: A <= 32768
 struct LossWs {
-  double cls_sum;
   unsigned long long npos_total;
+  unsigned int rows_done;
   int nan_flag;
-  unsigned int loss_ticket;
-  // followed by: double box_row[B]; int npos_row[B]; unsigned row_ticket[B]; MatchPart part[B][MATCH_MAX_CHUNKS]
+  // followed by the arrays of ws_*_off() below
 };
 struct MatchPart { double v; int i; int cnt; };
 
-__host__ __device__ inline size_t ws_box_off() { return sizeof(LossWs); }
-__host__ __device__ inline size_t ws_npos_off(int B) { return ws_box_off() + (size_t)B * sizeof(double); }
-__host__ __device__ inline size_t ws_ticket_off(int B) { return ws_npos_off(B) + (size_t)B * sizeof(int); }
-__host__ __device__ inline size_t ws_part_off(int B) { return (ws_ticket_off(B) + (size_t)B * sizeof(unsigned) + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t ws_total(int B) { return ws_part_off(B) + (size_t)B * MATCH_MAX_CHUNKS * sizeof(MatchPart); }
+__host__ __device__ inline size_t ws_al(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t ws_rowcls_off() { return ws_al(sizeof(LossWs)); }                              // double row_cls[B]
+__host__ __device__ inline size_t ws_box_off(int B) { return ws_rowcls_off() + (size_t)B * sizeof(double); }     // double row_box[B]
+__host__ __device__ inline size_t ws_npos_off(int B) { return ws_box_off(B) + (size_t)B * sizeof(double); }      // int npos_row[B]
+__host__ __device__ inline size_t ws_ticket_off(int B) { return ws_npos_off(B) + (size_t)B * sizeof(int); }      // unsigned match_ticket[B]
+__host__ __device__ inline size_t ws_lticket_off(int B) { return ws_ticket_off(B) + (size_t)B * sizeof(unsigned); }   // unsigned loss_ticket[B]
+__host__ __device__ inline size_t ws_clean_end(int B) { return ws_lticket_off(B) + (size_t)B * sizeof(unsigned); }    // [0, here) is left zero
+__host__ __device__ inline size_t ws_part_off(int B) { return ws_al(ws_clean_end(B)); }                          // MatchPart part[B][MATCH_MAX_CHUNKS]
+__host__ __device__ inline size_t ws_tile_off(int B) { return ws_part_off(B) + (size_t)B * MATCH_MAX_CHUNKS * sizeof(MatchPart); }   // double2 tile[B][LOSS_MAX_TILES]
+__host__ __device__ inline size_t ws_total(int B) { return ws_tile_off(B) + (size_t)B * LOSS_MAX_TILES * sizeof(double2); }
 
 // IoU of the match pass: exactly iou_gt_anchor, but the division is skipped where the boxes do not intersect
 // (inter == 0 gives 0 / (positive) == +0.0 in the reference too; most of the 17460 anchors of a row are such).
@@ -244,11 +251,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
-// Persistent blocks over tiles of 256 anchors (a contiguous tile range per block, so a block changes row at most a few
-// times): the class-loss sum is carried in registers across tiles and the per-row box sums are flushed when the row
-// changes, which leaves ~3 same-address atomics per BLOCK.  One block per tile (4416 blocks at B = 64, each with an
-// atomicAdd on cls_sum and on the ticket) was bound by exactly those: same-address atomics retire one every ~5 ns, 44 us
-// for a kernel that moves 45 MB.
+// grid (tiles of 256 anchors, B).  Every block leaves its two partial sums in its own slot; the last block of a row
+// (ticket) adds the row's slots in tile order, the last row to finish adds the rows in row order and finalizes
+// (loss.py:91-143).  Earlier versions added the partials with atomicAdd on one address per quantity: same-address atomics
+// retire one every ~2.5-5 ns, and 4416 blocks x 2 of them WERE the kernel's duration (22 us in round 1, 44 us with a
+// ticket on a second single address) -- besides making the loss differ in the last bits from run to run.
 template <bool PACKED>
 __global__ void __launch_bounds__(256) loss_grad_kernel(
     const float* __restrict__ att, int64_t att_stride, const float* __restrict__ reg, int64_t reg_stride,
@@ -257,96 +264,93 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
     float* __restrict__ d_reg, int64_t d_reg_stride, uint8_t* __restrict__ wsb, double* __restrict__ losses) {
   __shared__ __align__(16) float tile[PACKED ? 256 * 5 : 4];
   __shared__ double red[8];
-  __shared__ bool last;
+  __shared__ int stage;                                             // 0: done, 1: last block of its row, 2: last block overall
   LossWs* ws = reinterpret_cast<LossWs*>(wsb);
-  double* box_row = reinterpret_cast<double*>(wsb + ws_box_off());
+  double* row_cls = reinterpret_cast<double*>(wsb + ws_rowcls_off());
+  double* row_box = reinterpret_cast<double*>(wsb + ws_box_off(B));
   int* npos_row = reinterpret_cast<int*>(wsb + ws_npos_off(B));
-  const int tiles_per_row = (A + 255) / 256;
-  const int total_tiles = tiles_per_row * B;
-  const int t0 = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
-  const int t1 = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+  unsigned* loss_ticket = reinterpret_cast<unsigned*>(wsb + ws_lticket_off(B));
+  double2* tiles = reinterpret_cast<double2*>(wsb + ws_tile_off(B));
+  const int b = blockIdx.y;
+  const int a0 = blockIdx.x * 256;
+  const int a = a0 + threadIdx.x;
+  const int na = min(256, A - a0);                                  // anchors of this block
   const float inv_np = 1.0f / (float)ws->npos_total;
-  double cls_acc = 0.0, box_acc = 0.0;
-  int cur_b = -1;
-  for (int t = t0; t < t1; ++t) {
-    const int b = t / tiles_per_row;
-    const int a0 = (t - b * tiles_per_row) * 256;
-    if (b != cur_b) {                                               // block-uniform
-      if (cur_b >= 0) {
-        const double bx = block_sum(box_acc, red);
-        if (threadIdx.x == 0 && bx != 0.0) atomicAdd(&box_row[cur_b], bx);
-      }
-      box_acc = 0.0;
-      cur_b = b;
+  double cls_l = 0.0, box_l = 0.0;
+  if (PACKED) {
+    // reg points at element [0, 0, 0] of the packed buffer, d_reg likewise; rows start 16-byte aligned (A * 5 % 4 == 0)
+    const float* src = reg + ((size_t)b * A + a0) * 5;
+    float* dst = d_reg + ((size_t)b * A + a0) * 5;
+    const int nf = na * 5;                                          // floats of this block; a0 * 5 % 4 == 0
+    for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
+      if (i + 3 < nf) *reinterpret_cast<float4*>(tile + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+      else for (int k = i; k < nf; ++k) tile[k] = __ldg(src + k);
     }
-    const int a = a0 + threadIdx.x;
-    const int na = min(256, A - a0);                                // anchors of this tile
-    if (PACKED) {
-      // reg points at element [0, 0, 0] of the packed buffer, d_reg likewise; rows start 16-byte aligned (A * 5 % 4 == 0)
-      const float* src = reg + ((size_t)b * A + a0) * 5;
-      float* dst = d_reg + ((size_t)b * A + a0) * 5;
-      const int nf = na * 5;                                        // floats of this tile; a0 * 5 % 4 == 0
-      for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
-        if (i + 3 < nf) *reinterpret_cast<float4*>(tile + i) = __ldg(reinterpret_cast<const float4*>(src + i));
-        else for (int k = i; k < nf; ++k) tile[k] = __ldg(src + k);
-      }
-      __syncthreads();
-      LossTerms o;
-      if (a < A) {
-        const float r[4] = {tile[threadIdx.x * 5], tile[threadIdx.x * 5 + 1], tile[threadIdx.x * 5 + 2], tile[threadIdx.x * 5 + 3]};
-        const float x = tile[threadIdx.x * 5 + 4];
-        o = loss_terms(x, r, pos[(size_t)b * A + a] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg, inv_np, npos_row[b]);
-        cls_acc += o.cls_l;
-        box_acc += o.box_l;
-      }
-      __syncthreads();
-      if (a < A) {
-        float* q = tile + threadIdx.x * 5;
-        q[0] = o.d_reg.x; q[1] = o.d_reg.y; q[2] = o.d_reg.z; q[3] = o.d_reg.w; q[4] = o.d_att;
-      }
-      __syncthreads();
-      for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
-        if (i + 3 < nf) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(tile + i);
-        else for (int k = i; k < nf; ++k) dst[k] = tile[k];
-      }
-      __syncthreads();                                              // the tile buffer is reused by the next tile
-    } else if (a < A) {
-      const size_t e = (size_t)b * A + a;
-      const float* rp = reg + e * reg_stride;
-      const float r[4] = {rp[0], rp[1], rp[2], rp[3]};
-      const LossTerms o = loss_terms(att[e * att_stride], r, pos[e] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg,
-                                     inv_np, npos_row[b]);
-      cls_acc += o.cls_l;
-      box_acc += o.box_l;
-      d_att[e * d_att_stride] = o.d_att;
-      float* dp = d_reg + e * d_reg_stride;
-      if (d_reg_stride == 4) {
-        *reinterpret_cast<float4*>(dp) = o.d_reg;
-      } else {
-        dp[0] = o.d_reg.x; dp[1] = o.d_reg.y; dp[2] = o.d_reg.z; dp[3] = o.d_reg.w;
-      }
+    __syncthreads();
+    LossTerms o;
+    if (a < A) {
+      const float r[4] = {tile[threadIdx.x * 5], tile[threadIdx.x * 5 + 1], tile[threadIdx.x * 5 + 2], tile[threadIdx.x * 5 + 3]};
+      const float x = tile[threadIdx.x * 5 + 4];
+      o = loss_terms(x, r, pos[(size_t)b * A + a] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg, inv_np, npos_row[b]);
+      cls_l = o.cls_l;
+      box_l = o.box_l;
+    }
+    __syncthreads();
+    if (a < A) {
+      float* q = tile + threadIdx.x * 5;
+      q[0] = o.d_reg.x; q[1] = o.d_reg.y; q[2] = o.d_reg.z; q[3] = o.d_reg.w; q[4] = o.d_att;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x * 4; i < nf; i += 256 * 4) {
+      if (i + 3 < nf) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(tile + i);
+      else for (int k = i; k < nf; ++k) dst[k] = tile[k];
+    }
+  } else if (a < A) {
+    const size_t e = (size_t)b * A + a;
+    const float* rp = reg + e * reg_stride;
+    const float r[4] = {rp[0], rp[1], rp[2], rp[3]};
+    const LossTerms o = loss_terms(att[e * att_stride], r, pos[e] != 0, b, a, B, annot, anchors, alpha, gamma, lamb_reg,
+                                   inv_np, npos_row[b]);
+    cls_l = o.cls_l;
+    box_l = o.box_l;
+    d_att[e * d_att_stride] = o.d_att;
+    float* dp = d_reg + e * d_reg_stride;
+    if (d_reg_stride == 4) {
+      *reinterpret_cast<float4*>(dp) = o.d_reg;
+    } else {
+      dp[0] = o.d_reg.x; dp[1] = o.d_reg.y; dp[2] = o.d_reg.z; dp[3] = o.d_reg.w;
     }
   }
-  {
-    const double bx = block_sum(box_acc, red);
-    const double c = block_sum(cls_acc, red);
-    if (threadIdx.x == 0) {
-      if (cur_b >= 0 && bx != 0.0) atomicAdd(&box_row[cur_b], bx);
-      atomicAdd(&ws->cls_sum, c);
-      __threadfence();                                              // sums and this block's gradients before the ticket
-      last = atomicAdd(&ws->loss_ticket, 1u) == gridDim.x - 1;
-    }
+  const double c = block_sum(cls_l, red), bx = block_sum(box_l, red);
+  if (threadIdx.x == 0) {
+    tiles[(size_t)b * LOSS_MAX_TILES + blockIdx.x] = make_double2(c, bx);
+    __threadfence();                                                // the slot and this block's gradients before the ticket
+    stage = atomicAdd(&loss_ticket[b], 1u) == gridDim.x - 1 ? 1 : 0;
   }
   __syncthreads();
-  if (!last) return;
-  // ---- finalize (loss.py:91-143), one block ----
+  if (stage == 0) return;
+  // ---- last block of row b: the row's sums, tiles in order ----
+  if (threadIdx.x == 0) {
+    __threadfence();
+    double rc = 0.0, rb = 0.0;
+    const volatile double2* t = tiles + (size_t)b * LOSS_MAX_TILES;
+    for (int i = 0; i < (int)gridDim.x; ++i) { rc += t[i].x; rb += t[i].y; }
+    row_cls[b] = rc;
+    row_box[b] = rb / (double)(float)npos_row[b];                   // loss.py:93: row sum / positives of the row (float count)
+    loss_ticket[b] = 0;
+    __threadfence();
+    stage = atomicAdd(&ws->rows_done, 1u) == (unsigned)B - 1 ? 2 : 0;
+  }
+  __syncthreads();
+  if (stage != 2) return;
+  // ---- last block overall: finalize (loss.py:94-143) ----
   __shared__ int bad_s;
   if (threadIdx.x == 0) {
     __threadfence();
-    double box = 0.0;
-    for (int i = 0; i < B; ++i) box += __ldcg(box_row + i) / (double)(float)npos_row[i];
+    double box = 0.0, clsd = 0.0;
+    for (int i = 0; i < B; ++i) { box += __ldcg(row_box + i); clsd += __ldcg(row_cls + i); }
     box /= (double)B;
-    float cls = (float)__ldcg(&ws->cls_sum) / (float)ws->npos_total;   // f32 / count, like loss.py:125
+    float cls = (float)clsd / (float)ws->npos_total;                // f32 / count, like loss.py:125
     // loss.py:128-133.  The reference multiplies the per-anchor box loss of ALL anchors by the mask (loss.py:92): a zero-area
     // or inverted box (log(0) / log(<0) targets) gives inf * 0 = NaN there, while only positives are evaluated here (inf):
     // an infinite box loss is the same condition.
@@ -360,16 +364,16 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
   __syncthreads();
   if (bad_s) {
     // loss.py:128-133: a NaN step carries no gradient (the constants above have none).  Every other block has finished
-    // (ticket), so this one may overwrite their output; rare, hence not parallelised further.
+    // (tickets), so this one may overwrite their output; rare, hence not parallelised further.
     const size_t n = (size_t)B * A;
     for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
       d_att[e * d_att_stride] = 0.f;
       for (int k = 0; k < 4; ++k) d_reg[e * d_reg_stride + k] = 0.f;
     }
   }
-  // leave the workspace all zero for the next call
-  for (int i = threadIdx.x; i < B; i += blockDim.x) { box_row[i] = 0.0; npos_row[i] = 0; }
-  if (threadIdx.x == 0) { ws->cls_sum = 0.0; ws->npos_total = 0ull; ws->nan_flag = 0; ws->loss_ticket = 0u; }
+  // leave the counters zero for the next call
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { row_cls[i] = 0.0; row_box[i] = 0.0; npos_row[i] = 0; }
+  if (threadIdx.x == 0) { ws->npos_total = 0ull; ws->rows_done = 0u; ws->nan_flag = 0; }
 }
 
 // ---- evaluator ------------------------------------------------------------------------------
@@ -508,8 +512,8 @@ extern "C" int zsg_match_loss(const float* att, int64_t att_stride, const float*
   const int per_chunk = (a + nch - 1) / nch;
   nch = (a + per_chunk - 1) / per_chunk;
   match_rows_kernel<<<dim3(nch, b), 256, 0, st>>>(annot, anchors, a, per_chunk, match_thr, use_multi, pos, top1, wsb, b);
-  const int total_tiles = ((a + 255) / 256) * b;
-  const int grid = total_tiles < num_sms() * 4 ? total_tiles : num_sms() * 4;     // persistent: ~4 blocks per SM
+  ZSG_REQUIRE((a + 255) / 256 <= LOSS_MAX_TILES, "zsg_match_loss: a=%d exceeds %d anchors per row", a, LOSS_MAX_TILES * 256);
+  dim3 grid((a + 255) / 256, b);
   const bool packed = att_stride == 5 && reg_stride == 5 && d_att_stride == 5 && d_reg_stride == 5 && att == reg + 4 &&
                       d_att == d_reg + 4 && ((((uintptr_t)reg | (uintptr_t)d_reg) & 15) == 0) && (a % 4 == 0);
   if (packed)
