@@ -292,6 +292,31 @@ int zsg_eval(const float* att, int64_t att_stride, const float* reg, int64_t reg
              int64_t* best_ids, float* pred_scores, double* pred_boxes, float* metrics, void* workspace,
              size_t ws_bytes, zsg_stream_t stream);
 
+/* ---------------------- data path (dat_loader.py:98-146) -----------------
+ * What a CPU worker of the reference does per sample after JPEG decoding, for a whole batch on the device:
+ * `img.resize((300, 300))` (Pillow ImagingResample on 8-bit RGB: BICUBIC, the default since Pillow 7.0, or NEAREST,
+ * the default of the pinned pillow 6.1), `pil2tensor(img).float().div_(255)` (dat_loader.py:136), and the word-vector
+ * lookup (dat_loader.py:115).  Bit-identical to Pillow: fixed-point coefficient tables are built on the host exactly like
+ * Resample.c precompute_coeffs (zsg_b200/gpu_data.py) and passed in `tables`.
+ *   src      packed decoded images, uint8 [h][w][3] each, image i at src_off
+ *   tables   int32: per image and output column xx: {xmin, xmax, k[hksize]} from hk_off, per output row yy: {ymin - y_first,
+ *            ymax, k[vksize]} from vk_off (NEAREST: xtab[out_w] at hk_off, ytab[out_h] at vk_off)
+ *   workspace  bytes for the horizontal pass: n_rows * out_w * 3 per image at tmp_off (unused for NEAREST)
+ *   out      float32 [n_images][3][out_h][out_w] in [0, 1]                                                        */
+typedef struct {
+  int64_t src_off, tmp_off;
+  int32_t h, w;
+  int32_t y_first, n_rows;   /* source rows the vertical pass reads: [y_first, y_first + n_rows) (Pillow: ybox_first / ybox_last) */
+  int32_t hk_off, vk_off;    /* offsets into `tables` (in int32) */
+  int32_t hksize, vksize;
+} zsg_resize_desc;
+int zsg_resize_rgb8(const uint8_t* src, const zsg_resize_desc* descs /*device*/, const int32_t* tables /*device*/,
+                    int n_images, int out_h, int out_w, int max_rows /*max n_rows over the batch*/, int nearest,
+                    uint8_t* workspace, float* out, zsg_stream_t stream);
+/* out[i][0:dim] = table[tokens[i]][0:dim], zeros where tokens[i] < 0; dim % 4 == 0. */
+int zsg_embed_gather(const int32_t* tokens, const float* table, float* out, int64_t n_tokens, int dim,
+                     zsg_stream_t stream);
+
 /* ------------------------------ Adam (main_dist.py:50) ----------------------------------- */
 int zsg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
              float eps, int step, float grad_scale, zsg_stream_t stream);

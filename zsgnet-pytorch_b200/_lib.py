@@ -91,6 +91,8 @@ SIGNATURES = {
     "zsg_eval_workspace_bytes": [_I],
     "zsg_eval": [_P, _L, _P, _L, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P, _Z, _P],
     "zsg_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
+    "zsg_resize_rgb8": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "zsg_embed_gather": [_P, _P, _P, _L, _I, _P],
 }
 _RET = {"zsg_last_error_string": C.c_char_p, "zsg_match_loss_workspace_bytes": C.c_size_t,
         "zsg_eval_workspace_bytes": C.c_size_t}
@@ -125,7 +127,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (memsets not counted); used for bench.py's gpu_launches claim
-KERNELS_PER_CALL = {"zsg_match_loss": 2, "zsg_unfuse_lang_grid": 2}
+KERNELS_PER_CALL = {"zsg_match_loss": 2, "zsg_unfuse_lang_grid": 2, "zsg_resize_rgb8": 2}
 LAUNCH_COUNT = [0]
 
 

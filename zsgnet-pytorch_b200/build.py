@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzsg_b200.so")
 TRACE_LIB = os.path.join(HERE, "libzsg_b200_trace.so")
-SOURCES = ["api.cu", "match_loss.cu", "elementwise.cu", "lstm.cu", "conv_tc.cu"]
+SOURCES = ["api.cu", "match_loss.cu", "elementwise.cu", "lstm.cu", "data.cu", "conv_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

@@ -78,12 +78,17 @@ class ImgQuDataset(Dataset):
     std normalisation, 89-90), the phrase padded with ' PD' tokens to 50 vectors (107-114), the box turned from pixel
     x1y1x2y2 into y1x1y2x2 in [-1,1] (119-128).  Keys and dtypes are the reference's (136-144)."""
 
-    def __init__(self, cfg, csv_file, ds_name, split_type="train", embed=None):
+    def __init__(self, cfg, csv_file, ds_name, split_type="train", embed=None, raw=False, tokenize=None):
+        """raw=True (device-side data path, gpu_data.GpuBatchStage): an item carries the DECODED image as it is (`img_raw`,
+        uint8 [h, w, 3]) instead of the resized float tensor -- the resize and /255 run on the GPU -- and, when `tokenize`
+        (text -> list of vocabulary ids) is given, `tokens` (int32, -1 padded to 50) instead of `qvec`: the embedding
+        lookup runs on the GPU as well.  Workers then only decode and tokenise."""
         self.cfg, self.ann_file, self.ds_name, self.split_type = cfg, csv_file, ds_name, split_type
         self.image_data = self._read_annotations(csv_file)
         self.img_dir = Path(cfg["ds_info"][ds_name]["img_dir"])
         self.phrase_len = 50
-        self.embed = embed if embed is not None else _spacy_embedder()
+        self.raw, self.tokenize = raw, tokenize
+        self.embed = embed if embed is not None else (None if (raw and tokenize is not None) else _spacy_embedder())
 
     def __len__(self):
         return len(self.image_data)
@@ -111,16 +116,29 @@ class ImgQuDataset(Dataset):
         img = PIL.Image.open(img_file).convert("RGB")
         h, w = img.height, img.width
         q = q.strip()
-        qlen = len(self.embed(q))
+        t = np.array([annot[1] / h, annot[0] / w, annot[3] / h, annot[2] / w])
+        item = {"idxs": torch.tensor(idx).long(), "annot": torch.from_numpy(2 * t - 1).float(),
+                "orig_annot": torch.tensor(annot).float(), "img_size": torch.tensor([h, w])}
+        if self.raw and self.tokenize is not None:
+            ids = list(self.tokenize(q))
+            qlen = len(ids)
+            ids = ids + list(self.tokenize(" PD" * (self.phrase_len - qlen)))       # the ' PD' padding tokens (dat_loader.py:110)
+            tok = torch.full((self.phrase_len,), -1, dtype=torch.int32)
+            tok[:min(len(ids), self.phrase_len)] = torch.tensor(ids[: self.phrase_len], dtype=torch.int32)
+            item["tokens"] = tok
+        else:
+            qlen = len(self.embed(q))
+            vecs = np.asarray(self.embed(q + " PD" * (self.phrase_len - qlen)), dtype=np.float32)[: self.phrase_len]
+            item["qvec"] = torch.from_numpy(vecs)
         if qlen == 0:
             raise NotImplementedError("empty query")                 # dat_loader.py:103-105
-        vecs = np.asarray(self.embed(q + " PD" * (self.phrase_len - qlen)), dtype=np.float32)[: self.phrase_len]
+        item["qlens"] = torch.tensor(qlen)
+        if self.raw:
+            item["img_raw"] = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy())
+            return item
         img = img.resize((self.cfg["resize_img"][0], self.cfg["resize_img"][1]))
-        t = np.array([annot[1] / h, annot[0] / w, annot[3] / h, annot[2] / w])
-        px = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255)
-        return {"img": px, "idxs": torch.tensor(idx).long(), "qvec": torch.from_numpy(vecs), "qlens": torch.tensor(qlen),
-                "annot": torch.from_numpy(2 * t - 1).float(), "orig_annot": torch.tensor(annot).float(),
-                "img_size": torch.tensor([h, w])}
+        item["img"] = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255)
+        return item
 
 
 def _spacy_embedder():
@@ -243,23 +261,37 @@ def collater(batch):
     return out
 
 
+def raw_collater(batch):
+    """Collate for the device-side data path: images stay a list (their sizes differ), everything else is stacked as in
+    collater(); gpu_data.GpuBatchStage turns the result into the reference's batch dict on the device."""
+    out = {k: torch.stack([b[k] for b in batch]) for k in batch[0] if k != "img_raw"}
+    out["img_raw"] = [b["img_raw"] for b in batch]
+    return out
+
+
 def get_dataloader(cfg, dataset, is_train):
+    """dat_loader.py:209-227: per-GPU batch under DDP, `cfg.nw` worker processes (the synthetic datasets need none)."""
     dist = bool(cfg["do_dist"]) if "do_dist" in cfg else False
     bs = cfg["bs"] if dist else cfg["bs"] * max(1, int(cfg["num_gpus"]) if "num_gpus" in cfg else 1)
     if dist:
         sampler = NewDistributedSampler(dataset, shuffle=True)
     else:
         sampler = (torch.utils.data.RandomSampler if is_train else torch.utils.data.SequentialSampler)(dataset)
-    return DataLoader(dataset, batch_size=bs, sampler=sampler, drop_last=is_train, num_workers=0, collate_fn=collater)
+    nw = int(cfg["nw"]) if ("nw" in cfg and isinstance(dataset, ImgQuDataset)) else 0
+    collate = raw_collater if getattr(dataset, "raw", False) else collater
+    return DataLoader(dataset, batch_size=bs, sampler=sampler, drop_last=is_train, num_workers=nw, collate_fn=collate,
+                      pin_memory=not getattr(dataset, "raw", False) and torch.cuda.is_available())
 
 
-def get_data(cfg, embed=None):
+def get_data(cfg, embed=None, raw=False, tokenize=None):
     """Same signature as dat_loader.py:230-253.  With cfg.ds_to_use / cfg.ds_info set, the reference's CSV datasets
-    (train / valid / test); otherwise synthetic data of the BASELINE shape."""
+    (train / valid / test); otherwise synthetic data of the BASELINE shape.  raw / tokenize: the device-side data path
+    (ImgQuDataset raw mode; wrap the loaders' batches with gpu_data.GpuBatchStage)."""
     if "ds_to_use" in cfg and "ds_info" in cfg and cfg["ds_to_use"] in cfg["ds_info"]:
         name = cfg["ds_to_use"]
         info = cfg["ds_info"][name]
-        ds = {k: ImgQuDataset(cfg, info[f"{k}_csv_file"], name, split_type="train" if k == "trn" else "valid", embed=embed)
+        ds = {k: ImgQuDataset(cfg, info[f"{k}_csv_file"], name, split_type="train" if k == "trn" else "valid", embed=embed,
+                              raw=raw, tokenize=tokenize)
               for k in ("trn", "val", "test")}
         return DataWrap(path=cfg["tmp_path"] if "tmp_path" in cfg else "./tmp",
                         train_dl=get_dataloader(cfg, ds["trn"], True), valid_dl=get_dataloader(cfg, ds["val"], False),
