@@ -272,9 +272,20 @@ int zsg_lstm_rev_step_bwd(const float* dlang, const float* gates /*[B,512]*/, co
  * losses[0..2] = loss, cls_ls, box_ls (double); d_att/d_reg are gradients of `loss` (lamb_reg applied).
  * NaN follows torch.max: a NaN IoU row / NaN scores select the first NaN index, never an out-of-range one; a NaN
  * loss is replaced by the constants of loss.py:128-133 and the gradients are zeroed.
- * workspace: zsg_match_loss_workspace_bytes(B) bytes, 16-byte aligned, ALL ZERO before the first call; every call
- * leaves it all zero again (no memset on the stream between steps).  Two kernel launches.               */
+ * workspace: zsg_match_loss_workspace_bytes(B) bytes, 16-byte aligned; carries the positives' counts from the match
+ * to the loss pass and nothing between calls.  a <= 32768.
+ * Two halves, callable separately (the match only needs the annotations, so a training step runs it on a side stream
+ * under the forward pass) or as one call:
+ *   zsg_match      anchors.py:153-165 + loss.py:76-87: pos [B,A] (uint8), top1 [B], counts into the workspace.  fp64 ALU work.
+ *   zsg_loss_grad  loss.py:88-143 and its gradient: the HBM-bound pass, 40 B per (sample, anchor); partial sums in fixed
+ *                  order (bit-reproducible losses).  Must follow a zsg_match on the same workspace.                */
 size_t zsg_match_loss_workspace_bytes(int b);
+int zsg_match(const float* annot, const double* anchors, int b, int a, double match_thr, int use_multi, int64_t* top1,
+              uint8_t* pos, void* workspace, size_t ws_bytes, zsg_stream_t stream);
+int zsg_loss_grad(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride, const float* annot,
+                  const double* anchors, const uint8_t* pos, int b, int a, float alpha, float gamma, double lamb_reg,
+                  double* losses, float* d_att, int64_t d_att_stride, float* d_reg, int64_t d_reg_stride,
+                  void* workspace, size_t ws_bytes, zsg_stream_t stream);
 int zsg_match_loss(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride, const float* annot,
                    const double* anchors, int b, int a, double match_thr, float alpha, float gamma, double lamb_reg,
                    int use_multi, double* losses, float* d_att, int64_t d_att_stride, float* d_reg,

@@ -88,6 +88,8 @@ SIGNATURES = {
     "zsg_lstm_rev_step_bwd": [_P, _P, _P, _I, _P, _P],
     "zsg_match_loss_workspace_bytes": [_I],
     "zsg_match_loss": [_P, _L, _P, _L, _P, _P, _I, _I, _D, _F, _F, _D, _I, _P, _P, _L, _P, _L, _P, _P, _P, _Z, _P],
+    "zsg_match": [_P, _P, _I, _I, _D, _I, _P, _P, _P, _Z, _P],
+    "zsg_loss_grad": [_P, _L, _P, _L, _P, _P, _P, _I, _I, _F, _F, _D, _P, _P, _L, _P, _L, _P, _Z, _P],
     "zsg_eval_workspace_bytes": [_I],
     "zsg_eval": [_P, _L, _P, _L, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P, _Z, _P],
     "zsg_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
@@ -127,7 +129,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (memsets not counted); used for bench.py's gpu_launches claim
-KERNELS_PER_CALL = {"zsg_match_loss": 2, "zsg_unfuse_lang_grid": 2, "zsg_resize_rgb8": 2}
+KERNELS_PER_CALL = {"zsg_match_loss": 3, "zsg_loss_grad": 2, "zsg_unfuse_lang_grid": 2, "zsg_resize_rgb8": 2}
 LAUNCH_COUNT = [0]
 
 

@@ -82,10 +82,9 @@ __device__ __forceinline__ ArgMaxD block_argmax(ArgMaxD x, ArgMaxD* sm) {
   return r;
 }
 
-// Device workspace.  Contract: all zero before the first call; every call leaves the counters zero again (the last
-// block of the loss kernel clears what the call used), so no memset sits on the stream between steps.  Partial sums are
-// written to per-tile slots and added up in a fixed order by "last block done" tickets: no floating-point atomics, so the
-// three loss scalars are bit-reproducible from run to run.
+// Device workspace (no state between calls: zsg_match clears the counters it uses).  Partial sums of the loss are written
+// to per-tile slots and added up in a fixed order by a one-block finalize kernel: no floating-point atomics, so the three
+// loss scalars are bit-reproducible from run to run.
 constexpr int MATCH_MAX_CHUNKS = 32;
 constexpr int LOSS_MAX_TILES = 128;          // tiles of 256 anchors per row: A <= 32768
 struct LossWs {
@@ -251,25 +250,20 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
-// grid (tiles of 256 anchors, B).  Every block leaves its two partial sums in its own slot; the last block of a row
-// (ticket) adds the row's slots in tile order, the last row to finish adds the rows in row order and finalizes
-// (loss.py:91-143).  Earlier versions added the partials with atomicAdd on one address per quantity: same-address atomics
-// retire one every ~2.5-5 ns, and 4416 blocks x 2 of them WERE the kernel's duration (22 us in round 1, 44 us with a
-// ticket on a second single address) -- besides making the loss differ in the last bits from run to run.
+// grid (tiles of 256 anchors, B).  Every block leaves its two partial sums in its own slot and is done: no atomics, no
+// fence, nothing serial at the end of a block (with ~30 waves of blocks per SM, a fence + ticket per block was most of the
+// kernel's duration; same-address atomicAdds on the sums, round 1, retire one every ~2.5-5 ns: 22 us for 4416 blocks).
+// loss_finalize_kernel adds the slots up.
 template <bool PACKED>
 __global__ void __launch_bounds__(256) loss_grad_kernel(
     const float* __restrict__ att, int64_t att_stride, const float* __restrict__ reg, int64_t reg_stride,
     const float* __restrict__ annot, const double* __restrict__ anchors, const uint8_t* __restrict__ pos, int B, int A,
     float alpha, float gamma, double lamb_reg, float* __restrict__ d_att, int64_t d_att_stride,
-    float* __restrict__ d_reg, int64_t d_reg_stride, uint8_t* __restrict__ wsb, double* __restrict__ losses) {
+    float* __restrict__ d_reg, int64_t d_reg_stride, uint8_t* __restrict__ wsb) {
   __shared__ __align__(16) float tile[PACKED ? 256 * 5 : 4];
   __shared__ double red[8];
-  __shared__ int stage;                                             // 0: done, 1: last block of its row, 2: last block overall
-  LossWs* ws = reinterpret_cast<LossWs*>(wsb);
-  double* row_cls = reinterpret_cast<double*>(wsb + ws_rowcls_off());
-  double* row_box = reinterpret_cast<double*>(wsb + ws_box_off(B));
-  int* npos_row = reinterpret_cast<int*>(wsb + ws_npos_off(B));
-  unsigned* loss_ticket = reinterpret_cast<unsigned*>(wsb + ws_lticket_off(B));
+  const LossWs* ws = reinterpret_cast<const LossWs*>(wsb);
+  const int* npos_row = reinterpret_cast<const int*>(wsb + ws_npos_off(B));
   double2* tiles = reinterpret_cast<double2*>(wsb + ws_tile_off(B));
   const int b = blockIdx.y;
   const int a0 = blockIdx.x * 256;
@@ -322,33 +316,31 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
     }
   }
   const double c = block_sum(cls_l, red), bx = block_sum(box_l, red);
-  if (threadIdx.x == 0) {
-    tiles[(size_t)b * LOSS_MAX_TILES + blockIdx.x] = make_double2(c, bx);
-    __threadfence();                                                // the slot and this block's gradients before the ticket
-    stage = atomicAdd(&loss_ticket[b], 1u) == gridDim.x - 1 ? 1 : 0;
-  }
-  __syncthreads();
-  if (stage == 0) return;
-  // ---- last block of row b: the row's sums, tiles in order ----
-  if (threadIdx.x == 0) {
-    __threadfence();
+  if (threadIdx.x == 0) tiles[(size_t)b * LOSS_MAX_TILES + blockIdx.x] = make_double2(c, bx);
+}
+
+// one block: rows in parallel (each adds its tiles in tile order), then the rows in row order (loss.py:91-143)
+__global__ void __launch_bounds__(256) loss_finalize_kernel(uint8_t* __restrict__ wsb, int B, int A, int ntiles, double lamb_reg,
+                                                            double* __restrict__ losses, float* __restrict__ d_att,
+                                                            int64_t d_att_stride, float* __restrict__ d_reg,
+                                                            int64_t d_reg_stride) {
+  LossWs* ws = reinterpret_cast<LossWs*>(wsb);
+  double* row_cls = reinterpret_cast<double*>(wsb + ws_rowcls_off());
+  double* row_box = reinterpret_cast<double*>(wsb + ws_box_off(B));
+  const int* npos_row = reinterpret_cast<const int*>(wsb + ws_npos_off(B));
+  const double2* tiles = reinterpret_cast<const double2*>(wsb + ws_tile_off(B));
+  __shared__ int bad_s;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double2* t = tiles + (size_t)b * LOSS_MAX_TILES;
     double rc = 0.0, rb = 0.0;
-    const volatile double2* t = tiles + (size_t)b * LOSS_MAX_TILES;
-    for (int i = 0; i < (int)gridDim.x; ++i) { rc += t[i].x; rb += t[i].y; }
+    for (int i = 0; i < ntiles; ++i) { rc += t[i].x; rb += t[i].y; }
     row_cls[b] = rc;
     row_box[b] = rb / (double)(float)npos_row[b];                   // loss.py:93: row sum / positives of the row (float count)
-    loss_ticket[b] = 0;
-    __threadfence();
-    stage = atomicAdd(&ws->rows_done, 1u) == (unsigned)B - 1 ? 2 : 0;
   }
   __syncthreads();
-  if (stage != 2) return;
-  // ---- last block overall: finalize (loss.py:94-143) ----
-  __shared__ int bad_s;
   if (threadIdx.x == 0) {
-    __threadfence();
     double box = 0.0, clsd = 0.0;
-    for (int i = 0; i < B; ++i) { box += __ldcg(row_box + i); clsd += __ldcg(row_cls + i); }
+    for (int i = 0; i < B; ++i) { box += row_box[i]; clsd += row_cls[i]; }
     box /= (double)B;
     float cls = (float)clsd / (float)ws->npos_total;                // f32 / count, like loss.py:125
     // loss.py:128-133.  The reference multiplies the per-anchor box loss of ALL anchors by the mask (loss.py:92): a zero-area
@@ -359,21 +351,18 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
     losses[0] = lamb_reg * box + (double)cls;
     losses[1] = (double)cls;
     losses[2] = box;
+    ws->nan_flag = bad;
     bad_s = bad;
   }
   __syncthreads();
   if (bad_s) {
-    // loss.py:128-133: a NaN step carries no gradient (the constants above have none).  Every other block has finished
-    // (tickets), so this one may overwrite their output; rare, hence not parallelised further.
+    // a NaN step carries no gradient (the constants above have none); rare, hence one block
     const size_t n = (size_t)B * A;
     for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
       d_att[e * d_att_stride] = 0.f;
       for (int k = 0; k < 4; ++k) d_reg[e * d_reg_stride + k] = 0.f;
     }
   }
-  // leave the counters zero for the next call
-  for (int i = threadIdx.x; i < B; i += blockDim.x) { row_cls[i] = 0.0; row_box[i] = 0.0; npos_row[i] = 0; }
-  if (threadIdx.x == 0) { ws->npos_total = 0ull; ws->rows_done = 0u; ws->nan_flag = 0; }
 }
 
 // ---- evaluator ------------------------------------------------------------------------------
@@ -489,21 +478,23 @@ extern "C" size_t zsg_eval_workspace_bytes(int b) {
   return (size_t)(b < 1 ? 1 : b) * EVAL_CHUNKS * sizeof(EvalPart) + ((size_t)b + 1) * sizeof(unsigned) + 16;
 }
 
-extern "C" int zsg_match_loss(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride,
-                              const float* annot, const double* anchors, int b, int a, double match_thr, float alpha,
-                              float gamma, double lamb_reg, int use_multi, double* losses, float* d_att,
-                              int64_t d_att_stride, float* d_reg, int64_t d_reg_stride, int64_t* top1, uint8_t* pos,
-                              void* workspace, size_t ws_bytes, zsg_stream_t stream) {
-  ZSG_REQUIRE(att && reg && annot && anchors && losses && d_att && d_reg && top1 && pos && workspace,
-              "zsg_match_loss: null pointer");
-  ZSG_REQUIRE(b > 0 && a > 0, "zsg_match_loss: empty batch (b=%d a=%d)", b, a);
-  ZSG_REQUIRE(b <= 65535, "zsg_match_loss: batch %d exceeds the grid limit", b);
-  ZSG_REQUIRE(ws_bytes >= zsg_match_loss_workspace_bytes(b), "zsg_match_loss: workspace too small");
-  ZSG_REQUIRE(((uintptr_t)workspace & 15) == 0, "zsg_match_loss: workspace must be 16-byte aligned");
-  ZSG_REQUIRE(((uintptr_t)anchors & 15) == 0, "zsg_match_loss: anchors must be 16-byte aligned");
-  ZSG_REQUIRE(d_reg_stride != 4 || ((uintptr_t)d_reg & 15) == 0, "zsg_match_loss: d_reg must be 16-byte aligned");
+static int check_ws(const char* who, void* workspace, size_t ws_bytes, int b, int a) {
+  ZSG_REQUIRE(workspace, "%s: null workspace", who);
+  ZSG_REQUIRE(b > 0 && a > 0 && b <= 65535, "%s: bad batch (b=%d a=%d)", who, b, a);
+  ZSG_REQUIRE(ws_bytes >= zsg_match_loss_workspace_bytes(b), "%s: workspace too small", who);
+  ZSG_REQUIRE(((uintptr_t)workspace & 15) == 0, "%s: workspace must be 16-byte aligned", who);
+  ZSG_REQUIRE((a + 255) / 256 <= LOSS_MAX_TILES, "%s: a=%d exceeds %d anchors per row", who, a, LOSS_MAX_TILES * 256);
+  return ZSG_OK;
+}
+
+extern "C" int zsg_match(const float* annot, const double* anchors, int b, int a, double match_thr, int use_multi,
+                         int64_t* top1, uint8_t* pos, void* workspace, size_t ws_bytes, zsg_stream_t stream) {
+  ZSG_REQUIRE(annot && anchors && top1 && pos, "zsg_match: null pointer");
+  if (int rc = check_ws("zsg_match", workspace, ws_bytes, b, a)) return rc;
+  ZSG_REQUIRE(((uintptr_t)anchors & 15) == 0, "zsg_match: anchors must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+  cudaMemsetAsync(wsb, 0, ws_clean_end(b), st);                     // counters and tickets of this call
   // chunks per row: enough CTAs for ~4 per SM, at most MATCH_MAX_CHUNKS, at least 256 anchors each
   int nch = (num_sms() * 4 + b - 1) / b;
   if (nch > MATCH_MAX_CHUNKS) nch = MATCH_MAX_CHUNKS;
@@ -512,17 +503,41 @@ extern "C" int zsg_match_loss(const float* att, int64_t att_stride, const float*
   const int per_chunk = (a + nch - 1) / nch;
   nch = (a + per_chunk - 1) / per_chunk;
   match_rows_kernel<<<dim3(nch, b), 256, 0, st>>>(annot, anchors, a, per_chunk, match_thr, use_multi, pos, top1, wsb, b);
-  ZSG_REQUIRE((a + 255) / 256 <= LOSS_MAX_TILES, "zsg_match_loss: a=%d exceeds %d anchors per row", a, LOSS_MAX_TILES * 256);
-  dim3 grid((a + 255) / 256, b);
+  return check_launch("zsg_match");
+}
+
+extern "C" int zsg_loss_grad(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride, const float* annot,
+                             const double* anchors, const uint8_t* pos, int b, int a, float alpha, float gamma,
+                             double lamb_reg, double* losses, float* d_att, int64_t d_att_stride, float* d_reg,
+                             int64_t d_reg_stride, void* workspace, size_t ws_bytes, zsg_stream_t stream) {
+  ZSG_REQUIRE(att && reg && annot && anchors && pos && losses && d_att && d_reg, "zsg_loss_grad: null pointer");
+  if (int rc = check_ws("zsg_loss_grad", workspace, ws_bytes, b, a)) return rc;
+  ZSG_REQUIRE(((uintptr_t)anchors & 15) == 0, "zsg_loss_grad: anchors must be 16-byte aligned");
+  ZSG_REQUIRE(d_reg_stride != 4 || ((uintptr_t)d_reg & 15) == 0, "zsg_loss_grad: d_reg must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+  const int ntiles = (a + 255) / 256;
+  dim3 grid(ntiles, b);
   const bool packed = att_stride == 5 && reg_stride == 5 && d_att_stride == 5 && d_reg_stride == 5 && att == reg + 4 &&
                       d_att == d_reg + 4 && ((((uintptr_t)reg | (uintptr_t)d_reg) & 15) == 0) && (a % 4 == 0);
   if (packed)
     loss_grad_kernel<true><<<grid, 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma,
-                                                 lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb, losses);
+                                                 lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb);
   else
     loss_grad_kernel<false><<<grid, 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma,
-                                                  lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb, losses);
-  return check_launch("zsg_match_loss");
+                                                  lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb);
+  loss_finalize_kernel<<<1, 256, 0, st>>>(wsb, b, a, ntiles, lamb_reg, losses, d_att, d_att_stride, d_reg, d_reg_stride);
+  return check_launch("zsg_loss_grad");
+}
+
+extern "C" int zsg_match_loss(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride,
+                              const float* annot, const double* anchors, int b, int a, double match_thr, float alpha,
+                              float gamma, double lamb_reg, int use_multi, double* losses, float* d_att,
+                              int64_t d_att_stride, float* d_reg, int64_t d_reg_stride, int64_t* top1, uint8_t* pos,
+                              void* workspace, size_t ws_bytes, zsg_stream_t stream) {
+  if (int rc = zsg_match(annot, anchors, b, a, match_thr, use_multi, top1, pos, workspace, ws_bytes, stream)) return rc;
+  return zsg_loss_grad(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma, lamb_reg, losses, d_att,
+                       d_att_stride, d_reg, d_reg_stride, workspace, ws_bytes, stream);
 }
 
 extern "C" int zsg_eval(const float* att, int64_t att_stride, const float* reg, int64_t reg_stride,

@@ -277,8 +277,18 @@ def lstm_rev_step_bwd(dlang, gates, c0, b, dgates):
     call("zsg_lstm_rev_step_bwd", ptr(dlang), ptr(gates), ptr(c0), b, ptr(dgates), stream())
 
 
+def match(annot, anchors, b, a, thr, use_multi, top1, pos, ws):
+    call("zsg_match", ptr(annot), ptr(anchors), b, a, thr, int(use_multi), ptr(top1), ptr(pos), ptr(ws), ws.numel() * 8, stream())
+
+
+def loss_grad(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma, lamb, losses, d_att, d_att_stride,
+              d_reg, d_reg_stride, ws):
+    call("zsg_loss_grad", ptr(att), att_stride, ptr(reg), reg_stride, ptr(annot), ptr(anchors), ptr(pos), b, a, alpha, gamma,
+         lamb, ptr(losses), ptr(d_att), d_att_stride, ptr(d_reg), d_reg_stride, ptr(ws), ws.numel() * 8, stream())
+
+
 def match_loss_workspace(b, device):
-    """Zeroed once here; zsg_match_loss leaves it zero after every call (include/zsg_b200.h)."""
+    """Scratch that carries the positives' counts from the match to the loss pass (include/zsg_b200.h)."""
     n = _lib.load().zsg_match_loss_workspace_bytes(b)
     return torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)
 

@@ -21,6 +21,8 @@ class FusedStep:
         self.reducer = reducer if reducer is not None else GradReducer(net.store)
         self.opt = FusedAdam(net.parameters(), lr=lr, betas=(0.9, 0.99), net=net, reducer=self.reducer)
         self._per_b = {}
+        # the anchor match needs only the annotations: it runs on this stream under the forward pass
+        self._match_stream = torch.cuda.Stream(device=dev)
 
     def _bufs(self, B):
         if B not in self._per_b:
@@ -47,13 +49,18 @@ class FusedStep:
         inv[perm] = torch.arange(B)
         eng = net.engine_for(B, max(max_qlen, 1))
         eng.set_inputs(img, qvec[:, :max_qlen], qlens_cpu, inv, h0, c0)
+        b = self._bufs(B)
+        main = torch.cuda.current_stream()
+        self._match_stream.wait_stream(main)                  # previous step's loss pass has read pos / the workspace
+        with torch.cuda.stream(self._match_stream):
+            ops.match(batch["annot"], self.anchs, B, A, float(cfg["matching_threshold"]), bool(cfg["use_multi"]), b["top1"],
+                      b["pos"], b["ws"])
         out = eng.forward(training=True)
         net._bn_n.add_(1)
-        b = self._bufs(B)
         flat, dflat = out.view(-1), eng.d_out.view(-1)
-        ops.match_loss(flat[4:], 5, out, 5, batch["annot"], self.anchs, B, A, float(cfg["matching_threshold"]),
-                       float(cfg["alpha"]), float(cfg["gamma"]), float(cfg["lamb_reg"]), bool(cfg["use_multi"]),
-                       b["losses"], dflat[4:], 5, eng.d_out, 5, b["top1"], b["pos"], b["ws"])
+        main.wait_stream(self._match_stream)
+        ops.loss_grad(flat[4:], 5, out, 5, batch["annot"], self.anchs, b["pos"], B, A, float(cfg["alpha"]), float(cfg["gamma"]),
+                      float(cfg["lamb_reg"]), b["losses"], dflat[4:], 5, eng.d_out, 5, b["ws"])
         eng.backward(None, on_bucket=self.reducer.on_bucket if self.reducer.world > 1 else None)
         if do_opt:
             self.opt.step()
