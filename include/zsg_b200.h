@@ -191,7 +191,8 @@ int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const f
                      const double* sums, float* dx, float* dx_lo, float* dgamma, float* dbeta, int64_t rows, int c,
                      zsg_stream_t stream);
 
-/* zsg_bn_bwd_apply that writes the bf16 image of dx (dx_bf16, required) instead of a TF32 remainder image. */
+/* zsg_bn_bwd_apply that writes the bf16 image of dx (dx_bf16, required) instead of a TF32 remainder image; dx may be NULL
+ * (the fp32 gradient is not stored when only the two GEMMs that follow, which read the image, consume it). */
 int zsg_bn_bwd_apply_bf16(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                           const float* scale, const float* shift, const float* act_out, int mask_mode,
                           const double* sums, float* dx, uint16_t* dx_bf16, float* dgamma, float* dbeta, int64_t rows,

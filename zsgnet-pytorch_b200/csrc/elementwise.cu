@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       o.y = ga.y * is.y * (gg.y - s1[1] - (v[u].y - mu.y) * is.y * s2[1]);
       o.z = ga.z * is.z * (gg.z - s1[2] - (v[u].z - mu.z) * is.z * s2[2]);
       o.w = ga.w * is.w * (gg.w - s1[3] - (v[u].w - mu.w) * is.w * s2[3]);
-      st4(dx + i * 4, o);
+      if (dx) st4(dx + i * 4, o);                         // bf16 path: only the image is consumed (by the two GEMMs that follow)
       st_image(dx_lo, dx_b16, i * 4, o);
     }
   }
@@ -960,7 +960,7 @@ extern "C" int zsg_bn_bwd_apply_bf16(const float* dy, const float* x, const floa
                                      const float* gamma, const float* scale, const float* shift, const float* act_out,
                                      int mask_mode, const double* sums, float* dx, uint16_t* dx_bf16, float* dgamma,
                                      float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
-  ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx && dx_bf16 && c % 4 == 0, "zsg_bn_bwd_apply_bf16: bad arguments");
+  ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx_bf16 && c % 4 == 0, "zsg_bn_bwd_apply_bf16: bad arguments");
   bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
       dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, nullptr, dx_bf16, dgamma, dbeta, rows, c);
   return check_launch("zsg_bn_bwd_apply_bf16");

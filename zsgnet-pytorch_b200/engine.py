@@ -349,8 +349,10 @@ class Engine:
                               shift=bn.shift, act_out=act_out, dz_out=dz_out)
             src = dz_out if dz_out is not None else dy
             mm = 0 if dz_out is not None else mask_mode
-            ops.bn_bwd_apply(src, x, bn.mean, bn.invstd, bn.gamma, bn.bsums, dx, bn.dgamma, bn.dbeta, bn.rows, bn.c,
-                             mask_mode=mm, scale=bn.scale, shift=bn.shift, act_out=act_out, dx_lo=dx_lo)
+            # bf16 engine: the gradient w.r.t. the conv output is only read by that conv's two backward GEMMs, through the
+            # bf16 image -- the fp32 copy is not stored (4 of the pass's 14 bytes per element)
+            ops.bn_bwd_apply(src, x, bn.mean, bn.invstd, bn.gamma, bn.bsums, None if (b16 and want_lo) else dx, bn.dgamma,
+                             bn.dbeta, bn.rows, bn.c, mask_mode=mm, scale=bn.scale, shift=bn.shift, act_out=act_out, dx_lo=dx_lo)
         self.bwd.append(run)
         return dx_lo
 
