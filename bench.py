@@ -164,7 +164,7 @@ def net_cfg(model, dtype, local_rank):
             "use_focal": True, "use_softmax": False, "alpha": 0.25, "gamma": 2, "emb_dim": 300,
             "matching_threshold": 0.6, "use_bidirectional": True, "lstm_dim": 128, "lamb_reg": 1,
             "acc_iou_threshold": 0.5, "use_lang": True, "use_img": True, "device": f"cuda:{local_rank}",
-            "zsg_dtype": dtype, "zsg_direct_grads": True}
+            "zsg_dtype": dtype, "zsg_direct_grads": True, "zsg_quiet": True}
 
 
 def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=True, sampler=None):

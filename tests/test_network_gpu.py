@@ -408,3 +408,25 @@ def test_inputs_are_validated_not_silently_accepted(stack):
     bad["img"] = bad["img"][:, :, :256, :256].contiguous()
     with pytest.raises((AssertionError, RuntimeError, NotImplementedError)):
         net(bad)                                          # only 300x300 is built (resize_img)
+
+
+def test_pretrained_trunk_weights_load_like_the_reference(tmp_path):
+    """mdl.py:411 starts from torchvision's resnet50 weights: a torchvision state_dict (random here: no network) loads into
+    backbone.encoder through cfg['zsg_pretrained']; without it get_default_net warns that the trunk is randomly initialised."""
+    import torchvision
+    import zsg_b200  # noqa: F401
+    from zsg_b200 import mdl
+    from oracle import synth
+    torch.manual_seed(3)
+    tv = torchvision.models.resnet50(weights=None)
+    path = tmp_path / "resnet50.pth"
+    torch.save(tv.state_dict(), path)
+    cfg = synth.default_cfg()
+    cfg["device"] = "cuda"
+    with pytest.warns(UserWarning, match="randomly initialised"):
+        mdl.get_default_net(num_anchors=9, cfg=cfg)
+    cfg["zsg_pretrained"] = str(path)
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    sd = net.state_dict()
+    for k, v in tv.state_dict().items():
+        assert torch.equal(sd["backbone.encoder." + k].cpu(), v), k

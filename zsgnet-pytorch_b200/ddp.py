@@ -65,6 +65,15 @@ class GradReducer:
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
+    def broadcast_buffers(self, net):
+        """Rank 0's BatchNorm running statistics to every rank, on the compute stream: what DistributedDataParallel(
+        broadcast_buffers=True) does at the start of EVERY forward (main_dist.py:37-40).  Statistics are still computed per
+        rank; this only decides whose running averages eval mode and the checkpoint see (rank 0's, as in the reference)."""
+        if self.world == 1 or net._bn_f.numel() == 0:
+            return
+        dist.broadcast(net._bn_f, 0, group=self.group)
+        dist.broadcast(net._bn_n, 0, group=self.group)
+
     def broadcast_state(self, net):
         """Rank 0's parameters and BatchNorm buffers to every rank (DDP does this at construction)."""
         if self.world == 1:

@@ -260,9 +260,36 @@ class ZSGNet(nn.Module):
                 "num_f_out": self._num_f_out.clone()}
 
 
+def load_pretrained_encoder(net, path):
+    """Pretrained trunk weights into backbone.encoder: a torchvision resnet50 state_dict for 'retina' (the reference builds
+    tvm.resnet50(True), mdl.py:411) or vgg16_reducedfc.pth for 'ssd_vgg' (mdl.py:415-416: ssd_net.vgg.load_state_dict)."""
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    prefix = "backbone.encoder.vgg." if net.model == "ssd_vgg" else "backbone.encoder."
+    own = net.state_dict()
+    hit = {prefix + k: v for k, v in sd.items() if prefix + k in own and tuple(own[prefix + k].shape) == tuple(v.shape)}
+    if not hit:
+        raise ValueError(f"zsg_b200: {path} holds no tensor that fits {prefix}*")
+    net.load_state_dict(hit, strict=False)
+    return sorted(hit)
+
+
 def get_default_net(num_anchors=1, cfg=None):
-    """Same signature as mdl.py:406-422."""
+    """Same signature as mdl.py:406-422.  The reference starts from pretrained trunks (ImageNet resnet50 downloaded by
+    torchvision, mdl.py:411; ./weights/vgg16_reducedfc.pth, mdl.py:415-416).  There is no network here: cfg['zsg_pretrained']
+    (a state_dict file) or, for ssd_vgg, the reference's own path is loaded when present; otherwise the trunk keeps its
+    random initialisation and a warning says so (accuracy of a from-scratch run is not the reference's)."""
+    import os
+    import warnings
     dev = None
     if cfg is not None and "device" in cfg and str(cfg["device"]).startswith("cuda"):
         dev = cfg["device"]
-    return ZSGNet(None, num_anchors, cfg=cfg, device=dev)
+    net = ZSGNet(None, num_anchors, cfg=cfg, device=dev)
+    path = cfg["zsg_pretrained"] if (cfg is not None and "zsg_pretrained" in cfg) else None
+    if path is None and net.model == "ssd_vgg" and os.path.exists("./weights/vgg16_reducedfc.pth"):
+        path = "./weights/vgg16_reducedfc.pth"
+    if path:
+        load_pretrained_encoder(net, path)
+    elif not (cfg is not None and "zsg_quiet" in cfg and cfg["zsg_quiet"]):
+        warnings.warn("zsg_b200.get_default_net: no pretrained trunk weights (cfg['zsg_pretrained'] not set; the reference "
+                      "starts from ImageNet / vgg16_reducedfc weights): the encoder is randomly initialised", stacklevel=2)
+    return net

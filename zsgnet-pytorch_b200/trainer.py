@@ -13,8 +13,8 @@ from .optim import FusedAdam
 
 
 class FusedStep:
-    def __init__(self, net, ratios, scales, cfg, lr=1e-4, reducer=None):
-        self.net, self.cfg = net, cfg
+    def __init__(self, net, ratios, scales, cfg, lr=1e-4, reducer=None, broadcast_buffers=True):
+        self.net, self.cfg, self.broadcast_buffers = net, cfg, broadcast_buffers
         dev = net.store.device
         sizes = [(s, s) for s in spec.LEVEL_SIZES]
         self.anchs = create_anchors(sizes, ratios, scales, flatten=True, device=dev)
@@ -49,6 +49,8 @@ class FusedStep:
         inv[perm] = torch.arange(B)
         eng = net.engine_for(B, max(max_qlen, 1))
         eng.set_inputs(img, qvec[:, :max_qlen], qlens_cpu, inv, h0, c0)
+        if self.broadcast_buffers:
+            self.reducer.broadcast_buffers(net)                # DDP broadcast_buffers=True (main_dist.py:39); no-op on one rank
         b = self._bufs(B)
         main = torch.cuda.current_stream()
         self._match_stream.wait_stream(main)                  # previous step's loss pass has read pos / the workspace
