@@ -8,10 +8,11 @@ import numpy as np
 from zsg_b200.trainer import FusedStep
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+DT = sys.argv[2] if len(sys.argv) > 2 else "fp32"
 cfg = {"do_norm": False, "use_same_atb": True, "mdl_to_use": "retina", "resize_img": [300, 300], "use_multi": True,
        "use_focal": True, "use_softmax": False, "alpha": 0.25, "gamma": 2, "emb_dim": 300, "matching_threshold": 0.6,
        "use_bidirectional": True, "lstm_dim": 128, "lamb_reg": 1, "acc_iou_threshold": 0.5, "use_lang": True,
-       "use_img": True, "device": "cuda:0"}
+       "use_img": True, "device": "cuda:0", "zsg_dtype": DT, "zsg_quiet": True}
 torch.manual_seed(0)
 net = mdl.get_default_net(9, cfg); net.train()
 fs = FusedStep(net, [0.5, 1, 2], 4 * np.array([1, 2 ** (1 / 3), 2 ** (2 / 3)]), cfg)
@@ -42,7 +43,7 @@ for ms, kind, m, cin, cout, r, div, tf in rows:
     key = (kind, m, cin, cout, r, div)
     agg[key][0] += ms; agg[key][1] += tf * ms; agg[key][2] += 1
 print(f"{'ms':>8s} {'n':>3s} {'TF/s':>7s}  kind   M       cin  cout  k div")
-for key, (ms, tfms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+for key, (ms, tfms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:70]:
     kind, m, cin, cout, r, div = key
     print(f"{ms:8.2f} {n:3d} {tfms/ms:7.1f}  {kind:6s} {m:7d} {cin:5d} {cout:5d} {r:2d} {div}")
 for kind in ("fwd", "dgrad", "wgrad"):
