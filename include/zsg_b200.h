@@ -86,6 +86,14 @@ typedef struct {
   const uint16_t* w_bf16;  /* (indexed like x, zsg_cast_bf16) and of the weights [cout][r][s][cin].  Selects the bf16 operand  */
                            /* path of BASELINE configs 3-5 ("bf16 tensor-core convs"): one kind::f16 MMA per product, fp32      */
                            /* accumulation, fp32 epilogue and output; x / w / x_lo / w_lo are not read then (may be NULL)      */
+  int32_t x_plain;         /* 1: the gather is the identity -- r = s = 1, in_div = 1 and row i reads x[i * cin .. (i+1) * cin) (every  */
+                           /* 1x1 stride-1 conv of the path and its data gradient; the caller built the table, so it knows).  With */
+                           /* operand images (x_lo or x_bf16) the A tiles are then fetched by TMA like the weights: no per-thread */
+                           /* address work, no row-table reads on the producer side.  0: unknown (always correct)                 */
+  uint16_t* y_bf16;        /* optional ("bf16 storage" of the bf16 engine's trunk): the output is stored as bfloat16 (round to      */
+                           /* nearest even), indexed like y, INSTEAD of y (y may then be NULL).  Plain outputs only: no bias /     */
+                           /* ReLU / mask / residual / accumulate, cout % 4 == 0, row offsets % 4 == 0; `stats` still come from    */
+                           /* the fp32 accumulators                                                                                */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
@@ -190,6 +198,28 @@ int zsg_bn_bwd_apply(const float* dy, const float* x, const float* mean, const f
                      const float* scale, const float* shift, const float* act_out, int mask_mode,
                      const double* sums, float* dx, float* dx_lo, float* dgamma, float* dbeta, int64_t rows, int c,
                      zsg_stream_t stream);
+
+/* ---- bf16 storage: trunk activations of the bf16 engine (conv outputs x, BatchNorm+ReLU images, block outputs) live in HBM as
+ * bfloat16 ONLY; the same kernels with bfloat16 loads / stores, arithmetic in fp32 (sums in fp64) as above.
+ * Under torch.autocast(bfloat16) the reference stores exactly these tensors in bfloat16 (mdl.py:149-156 trunk). ---- */
+/* out = bf16( relu?(x * scale[c] + shift[c]) ), x bfloat16 [rows, c] (zsg_cast_bf16 with a bfloat16 source). */
+int zsg_act_b16(const uint16_t* x, const float* scale, const float* shift, int relu, uint16_t* out, int64_t rows, int c,
+                zsg_stream_t stream);
+/* zsg_bn_apply over bfloat16 tensors: y = bf16( relu?( x*scale+shift [+ r*rscale+rshift | + r] ) ). */
+int zsg_bn_apply_b16(const uint16_t* x, const float* scale, const float* shift, const uint16_t* r, const float* rscale,
+                     const float* rshift, int relu, uint16_t* y, int64_t rows, int c, zsg_stream_t stream);
+/* zsg_bn_bwd_reduce with x / act_out in bfloat16; dy and dz_out are float32 or bfloat16 (flags). */
+int zsg_bn_bwd_reduce_b16(const void* dy, int dy_is_b16, const uint16_t* x, const float* mean, const float* invstd,
+                          const float* scale, const float* shift, const uint16_t* act_out, int mask_mode, void* dz_out,
+                          int dz_is_b16, double* sums, int64_t rows, int c, zsg_stream_t stream);
+/* zsg_bn_bwd_apply_bf16 with x / act_out in bfloat16; dy float32 or bfloat16; writes only the bfloat16 dx. */
+int zsg_bn_bwd_apply_b16(const void* dy, int dy_is_b16, const uint16_t* x, const float* mean, const float* invstd,
+                         const float* gamma, const float* scale, const float* shift, const uint16_t* act_out, int mask_mode,
+                         const double* sums, uint16_t* dx_bf16, float* dgamma, float* dbeta, int64_t rows, int c,
+                         zsg_stream_t stream);
+/* zsg_maxpool_bn_relu_fwd with a bfloat16 source and a bfloat16 result. */
+int zsg_maxpool_bn_relu_fwd_b16(const uint16_t* x, const float* scale, const float* shift, uint16_t* y, uint8_t* argmax,
+                                int b, int h, int w, int c, int ho, int wo, zsg_stream_t stream);
 
 /* zsg_bn_bwd_apply that writes the bf16 image of dx (dx_bf16, required) instead of a TF32 remainder image; dx may be NULL
  * (the fp32 gradient is not stored when only the two GEMMs that follow, which read the image, consume it). */

@@ -33,6 +33,9 @@ from . import synth
 #   operands of every contraction rounded to bfloat16 (round-to-nearest-even), products exact, accumulation and output
 #   in fp32 -- forward (x, w), data gradient (dy, w) and weight gradient (x, dy) alike; bias gradients from the unrounded
 #   dy.  The LSTM (not a convolution) stays fp32, as in the product.
+#   ResNet-50 trunk ("bf16 storage", what torch.autocast(bfloat16) also does to these tensors): every conv output (the
+#   tensor a BatchNorm reads), the stem's pooled output and every block output is rounded to bfloat16 where it is stored
+#   (store_act); gradients pass those points unrounded.
 #   The reference has no bf16 mode of its own; the closest thing it offers, torch.autocast(bfloat16) around the same
 #   modules, additionally rounds every conv OUTPUT to bf16 (tests/test_bf16_network_gpu.py measures both against fp32).
 CONV_MODE = ["fp32"]
@@ -52,6 +55,21 @@ class conv_mode:
 
 def _rb(t):
     return t.bfloat16().to(t.dtype)
+
+
+class _StoreBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _rb(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def store_act(x):
+    """A trunk activation as the bf16 engine keeps it in HBM (bfloat16 only); identity in fp32 mode."""
+    return _StoreBf16.apply(x) if CONV_MODE[0] == "bf16" else x
 
 
 class _Bf16OperandConv(torch.autograd.Function):
@@ -306,21 +324,21 @@ class BNState:
 def stem(sd, img, bn):
     """mdl.py:149-152: conv7x7/2 -> BN -> ReLU -> maxpool3x3/2."""
     e = "backbone.encoder."
-    x = conv2d(img, sd[e + "conv1.weight"], None, stride=2, padding=3)
+    x = store_act(conv2d(img, sd[e + "conv1.weight"], None, stride=2, padding=3))
     x = relu(bn(x, e + "bn1"))
-    return F.max_pool2d(x, 3, 2, 1)
+    return store_act(F.max_pool2d(x, 3, 2, 1))
 
 
 def bottleneck(sd, x, p, s, bn):
     """torchvision Bottleneck (v1.5: the stride sits on the 3x3): 1x1 -> BN, ReLU -> 3x3(stride s) -> BN, ReLU -> 1x1 (x4) -> BN
     -> + identity (or 1x1/s conv + BN when the block has a `downsample`) -> ReLU.  p = 'backbone.encoder.layerL.B.'."""
     idt = x
-    y = relu(bn(conv2d(x, sd[p + "conv1.weight"]), p + "bn1"))
-    y = relu(bn(conv2d(y, sd[p + "conv2.weight"], None, stride=s, padding=1), p + "bn2"))
-    y = bn(conv2d(y, sd[p + "conv3.weight"]), p + "bn3")
+    y = relu(bn(store_act(conv2d(x, sd[p + "conv1.weight"])), p + "bn1"))
+    y = relu(bn(store_act(conv2d(y, sd[p + "conv2.weight"], None, stride=s, padding=1)), p + "bn2"))
+    y = bn(store_act(conv2d(y, sd[p + "conv3.weight"])), p + "bn3")
     if p + "downsample.0.weight" in sd:
-        idt = bn(conv2d(x, sd[p + "downsample.0.weight"], None, stride=s), p + "downsample.1")
-    return relu(y + idt)
+        idt = bn(store_act(conv2d(x, sd[p + "downsample.0.weight"], None, stride=s)), p + "downsample.1")
+    return store_act(relu(y + idt))
 
 
 def resnet50_c3c4c5(sd, img, bn):

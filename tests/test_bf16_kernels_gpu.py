@@ -244,3 +244,100 @@ def test_bn_kernels_write_bf16_images(zsg):
     ops.bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx2, dgam, dbet, rows, c)
     torch.cuda.synchronize()
     assert torch.equal(dx, dx2) and torch.equal(dxb.view(torch.int16), dx.bfloat16().view(torch.int16))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# bf16 storage: trunk activations of the bf16 engine are bfloat16 tensors (their own GEMM operand images)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(2, 64, 19, 19, 64, 1, 1, 0), (3, 128, 20, 18, 128, 3, 2, 1), (4, 64, 75, 75, 256, 1, 1, 0)])
+def test_conv_bf16_output_storage(zsg, case):
+    """zsg_conv_params.y_bf16: the same accumulators stored as bfloat16 (round to nearest even) instead of fp32; the
+    BatchNorm statistics still come from the fp32 accumulators (identical to the fp32-output launch)."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(31)
+    x = nhwc(torch.randn(B, cin, H, W, generator=g)).cuda()
+    w = khwc(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    m = B * Ho * Wo
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    xi, wi = image(ops, x), image(ops, w)
+    nst = (m + 127) // 128 * 4 * 2 * cout
+    y32, st32 = torch.empty(m, cout, device="cuda"), torch.zeros(nst, device="cuda")
+    y16, st16 = torch.full((m, cout), 7.0, dtype=torch.bfloat16, device="cuda"), torch.zeros(nst, device="cuda")
+    plain = k == 1 and stride == 1
+    ops.ConvOp(x, w, y32, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, stats=st32, x_plain=plain)()
+    ops.ConvOp(x, w, y16, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, stats=st16, x_plain=plain)()
+    torch.cuda.synchronize()
+    assert torch.equal(y16, y32.bfloat16()) and torch.equal(st16, st32)
+
+
+@pytest.mark.parametrize("rows,c", [(1000, 64), (333, 256), (77, 2048), (129, 4)])
+def test_bf16_storage_batchnorm_passes(zsg, rows, c):
+    """zsg_act_b16 / zsg_bn_apply_b16 / zsg_bn_bwd_reduce_b16 / zsg_bn_bwd_apply_b16 against the fp32 kernels run on the same
+    (bfloat16-representable) values: bit-equal images, sums to fp32 rounding.  c = 4 takes the 4-channel fallback."""
+    ops, _ = zsg
+    g = torch.Generator().manual_seed(rows + c)
+    R = lambda *s: torch.randn(*s, generator=g).cuda()
+    xb, rb_ = R(rows, c).bfloat16(), R(rows, c).bfloat16()
+    x, r = xb.float(), rb_.float()
+    sc, sh, rsc, rsh = R(c).abs() + 0.5, R(c) * 0.3, R(c).abs() + 0.5, R(c) * 0.3
+    # BatchNorm + ReLU image
+    z16, z32 = torch.empty_like(xb), torch.empty_like(xb)
+    ops.act_b16(xb, z16, rows, c, scale=sc, shift=sh, relu=True)
+    ops.split_act(x, z32, rows, c, scale=sc, shift=sh, relu=True)
+    assert torch.equal(z16, z32)
+    # bottleneck tail, both shortcut kinds
+    for kw16, kw32 in ((dict(r=rb_), dict(r=r)), (dict(r=rb_, rscale=rsc, rshift=rsh), dict(r=r, rscale=rsc, rshift=rsh))):
+        y16, y32, i32 = torch.empty_like(xb), torch.empty_like(x), torch.empty_like(xb)
+        ops.bn_apply(xb, sc, sh, y16, rows, c, True, **kw16)
+        ops.bn_apply(x, sc, sh, y32, rows, c, True, y_lo=i32, **kw32)
+        assert torch.equal(y16, i32)
+    # backward: reduce + apply, every mask mode, fp32 and bfloat16 gradients
+    mean, invstd, gamma = x.mean(0), 1.0 / (x.var(0, unbiased=False) + 1e-5).sqrt(), R(c).abs() + 0.5
+    act16 = y16
+    for mode in (0, 1, 2):
+        for gdt in (torch.float32, torch.bfloat16):
+            dy = R(rows, c).to(gdt)
+            s16, s32 = torch.zeros(2 * c, dtype=torch.float64, device="cuda"), torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+            for zdt in ((torch.float32, torch.bfloat16) if mode == 2 else (None,)):
+                s16.zero_()
+                dz16 = torch.empty(rows, c, dtype=zdt, device="cuda") if zdt is not None else None
+                ops.bn_bwd_reduce(dy, xb, mean, invstd, s16, rows, c, mask_mode=mode, scale=sc, shift=sh,
+                                  act_out=act16 if mode == 2 else None, dz_out=dz16)
+                dz32 = torch.empty(rows, c, device="cuda") if mode == 2 else None
+                s32.zero_()
+                ops.bn_bwd_reduce(dy.float(), x, mean, invstd, s32, rows, c, mask_mode=mode, scale=sc, shift=sh,
+                                  act_out=act16.float() if mode == 2 else None, dz_out=dz32)
+                torch.cuda.synchronize()
+                scale_ = s32.abs().max().item() + 1.0
+                assert float((s16 - s32).abs().max()) < 2e-5 * scale_ * max(1.0, float(mean.abs().max())), (mode, gdt, zdt)
+                if mode == 2:
+                    assert torch.equal(dz16.float(), dz32.to(zdt).float())
+            dx16, dx32, dxi = torch.empty_like(xb), torch.empty_like(x), torch.empty_like(xb)
+            dga, dbe, dga2, dbe2 = (torch.empty(c, device="cuda") for _ in range(4))
+            ops.bn_bwd_apply(dy, xb, mean, invstd, gamma, s32, None, dga, dbe, rows, c, mask_mode=mode, scale=sc, shift=sh,
+                             act_out=act16 if mode == 2 else None, dx_lo=dx16)
+            ops.bn_bwd_apply(dy.float(), x, mean, invstd, gamma, s32, dx32, dga2, dbe2, rows, c, mask_mode=mode, scale=sc,
+                             shift=sh, act_out=act16.float() if mode == 2 else None, dx_lo=dxi)
+            torch.cuda.synchronize()
+            assert torch.equal(dga, dga2) and torch.equal(dbe, dbe2)
+            # same formula, different association (A*dz + B*x + C): a few fp32 ulps before the bf16 rounding
+            d = (dx16.float() - dx32).abs()
+            assert float(d.max()) <= 2 ** -7 * float(dx32.abs().max()), (mode, gdt)
+            assert float((d > 2 ** -8 * dx32.abs().clamp_min(1e-3)).float().mean()) < 1e-3
+
+
+def test_bf16_storage_stem_pool(zsg):
+    ops, _ = zsg
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C = 2, 30, 26, 64
+    xb = torch.randn(B, H, W, C, generator=g).cuda().bfloat16()
+    sc, sh = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda() * 0.2
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    y16, a16 = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device="cuda"), torch.empty(B * Ho * Wo * C, dtype=torch.uint8, device="cuda")
+    y32, a32 = torch.empty(B, Ho, Wo, C, device="cuda"), torch.empty_like(a16)
+    ops.maxpool_bn_relu_fwd(xb, sc, sh, y16, a16, B, H, W, C, Ho, Wo)
+    ops.maxpool_bn_relu_fwd(xb.float(), sc, sh, y32, a32, B, H, W, C, Ho, Wo)
+    torch.cuda.synchronize()
+    assert torch.equal(y16, y32.bfloat16()) and torch.equal(a16, a32)

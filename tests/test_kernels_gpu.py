@@ -1015,3 +1015,47 @@ def test_loss_scalars_are_bit_reproducible_and_split_api_equals_composite(zsg):
     ops.loss_grad(att, 1, bbx, 4, annot, anchs, pos, B, A, 0.25, 2.0, 1.0, losses, datt, 1, dreg, 4, ws)
     torch.cuda.synchronize()
     assert torch.equal(losses.cpu(), runs[0][0]) and torch.equal(datt.cpu(), runs[0][1]) and torch.equal(top1.cpu(), runs[0][3])
+
+
+@pytest.mark.parametrize("case", [(3, 64, 13, 11, 256), (2, 256, 20, 19, 64), (5, 300, 1, 4, 512), (2, 2048, 10, 10, 256),
+                                  (1, 64, 75, 75, 64), (2, 128, 16, 16, 40)])
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("epi", ["plain", "stats", "full"])
+def test_conv_plain_matrix_tma_equals_gather_path(zsg, case, bf16, epi):
+    """x_plain (zsg_conv_params): 1x1 stride-1 convs fetch their A tiles by TMA from the plain [m, cin] matrix.  Same smem
+    image, same MMAs, same epilogue as the cp.async gather path => bit-identical results (ragged last M tile, K that is
+    not a multiple of the K block, every epilogue option)."""
+    ops, geo = zsg
+    B, cin, H, W, cout = case
+    if bf16 and cin % 8:
+        pytest.skip("bf16 images need cin % 8 == 0")
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    m = B * H * W
+    x = torch.randn(m, cin, generator=g).cuda()
+    w = (torch.randn(cout, cin, generator=g) / cin ** 0.5).cuda()
+    rows = geo.conv_rows(B, H, W, cin, H, W, cout, 1, 0).cuda()
+    kw = {}
+    if epi == "full":
+        kw = dict(bias=torch.randn(cout, generator=g).cuda(), out_mask=torch.randn(m, cout, generator=g).cuda(),
+                  residual=torch.randn(m, cout, generator=g).cuda(), accumulate=True)
+    if bf16:
+        xi, wi = x.to(torch.bfloat16), w.to(torch.bfloat16)
+        wa = w
+    else:
+        xi, wa, wi = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+        ops.split_act(x, xi, m, cin)
+        ops.split_tf32(w, wa, wi, w.numel())
+    ys, sts = [], []
+    for plain in (False, True):
+        y = torch.full((m, cout), 0.25, device="cuda")
+        st = torch.zeros((m + 127) // 128 * 4 * 2 * cout, device="cuda") if epi == "stats" else None
+        ops.ConvOp(x, wa, y, rows, m, cin, cout, 1, 1, w_lo=wi, x_lo=xi, stats=st, x_plain=plain, **kw)()
+        ys.append(y)
+        sts.append(st)
+    torch.cuda.synchronize()
+    assert torch.equal(ys[0], ys[1])
+    if epi == "stats":
+        assert torch.equal(sts[0], sts[1])
+    if epi != "full":
+        ref = (x.to(torch.bfloat16).float() @ w.to(torch.bfloat16).float().t()) if bf16 else x @ w.t()
+        assert rel_err(ys[1], ref) < (2e-5 if not bf16 else 1e-5)

@@ -75,9 +75,14 @@ class Stage:
             torch.manual_seed(7)
             out = zo.zsgnet_forward(dict(self.sd), self.batch, training=True, return_inter=True)
             self.inter = out["_inter"]
-        self.tol_bn = 1e-4 if dtype == "fp32" else 2e-3
+        # bf16: one bfloat16 ulp is 2^-8 = 3.9e-3 relative.  With bf16 storage of the trunk (block outputs and conv outputs are
+        # bfloat16 tensors) values that sit on a rounding boundary round the other way on either side, and the engine's
+        # BatchNorm statistics come from the fp32 accumulators while the oracle's come from the stored (rounded) tensor:
+        # measured 2.2e-3 .. 3.0e-3 rms per block forward and up to 4.1e-3 on a weight gradient (layer1.0.conv1), i.e. about
+        # one ulp
+        self.tol_bn = 1e-4 if dtype == "fp32" else 4e-3
         self.tol = 2e-5 if dtype == "fp32" else 2e-3
-        self.tol_g = 1e-4 if dtype == "fp32" else 3e-3
+        self.tol_g = 1e-4 if dtype == "fp32" else 6e-3
 
     def sdg(self, keys):
         """leaf copies of the oracle weights that take part in a stage"""
@@ -90,7 +95,7 @@ class Stage:
         """oracle tensor (NCHW) -> engine buffer (NHWC rows); regenerates the GEMM operand image of the buffer if it has one"""
         buf.view(-1)[: t.numel()].copy_(nhwc(t).cuda().view(-1))
         for key, (z, img) in self.eng._operand_cache.items():
-            if key[0] == buf.data_ptr() and key[3] == id(None) and not key[4]:
+            if key[0] == buf.data_ptr() and key[3] == id(None) and not key[4] and img is not buf:   # bf16 storage: own image
                 self.ops.split_act(buf, img, key[1], key[2])
 
     def fwd(self, label):

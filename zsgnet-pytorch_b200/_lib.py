@@ -26,7 +26,7 @@ class ConvParams(C.Structure):
                 ("in_div", C.c_int32), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
                 ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32), ("stats", C.c_void_p),
-                ("x_bf16", C.c_void_p), ("w_bf16", C.c_void_p)]
+                ("x_bf16", C.c_void_p), ("w_bf16", C.c_void_p), ("x_plain", C.c_int32), ("y_bf16", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
@@ -53,6 +53,11 @@ SIGNATURES = {
     "zsg_split_tf32": [_P, _P, _P, _L, _P],
     "zsg_split_act": [_P, _P, _P, _I, _P, _P, _L, _I, _P],
     "zsg_cast_bf16": [_P, _P, _P, _I, _P, _L, _I, _P],
+    "zsg_act_b16": [_P, _P, _P, _I, _P, _L, _I, _P],
+    "zsg_bn_apply_b16": [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P],
+    "zsg_bn_bwd_reduce_b16": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _L, _I, _P],
+    "zsg_bn_bwd_apply_b16": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _I, _P],
+    "zsg_maxpool_bn_relu_fwd_b16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "zsg_bn_apply_bf16": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
     "zsg_bn_bwd_apply_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P],
     "zsg_nchw_to_nhwc4": [_P, _P, _I, _I, _I, _P],

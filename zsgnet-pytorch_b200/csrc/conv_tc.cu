@@ -24,6 +24,7 @@
 // empty[s] and acc_full[a] (tcgen05.commit), acc_empty[a] (256 drain arrivals), token[w] (issuer hand-over).
 // Warp roles and the chunked-promotion scheme are described above setup_pipeline().
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -551,12 +552,22 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
           p.stats[((int64_t)((m0 / TM) * 4 + quadrant) * 2 + hsel) * p.cout + ncol] = hsel ? s2 : s1;
       }
       const int n = n0 + half * (BN / 2) + slab * 16 + c4;
+      if (p.y_bf16 && !use_plain) {                         // zsg_conv_fwd checked the epilogue options; only the offsets are left
+        if (lane == 0 && slab == 0) printf("zsg conv: y_bf16 needs row offsets that are multiples of 4\n");
+        __trap();
+      }
       if (use_plain) {
         if (n < p.cout) {                                   // cout % 4 == 0: the whole float4 is inside
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 v = *reinterpret_cast<const float4*>(stg + (i * 8 + rsel) * 20 + c4);
-            if (pk[i]) *reinterpret_cast<float4*>(p.y + po[i] + slab * 16) = v;
+            if (p.y_bf16) {                                 // bf16 storage: 4 values = one 8-byte store, no fp32 copy
+              const __nv_bfloat162 b0 = __floats2bfloat162_rn(v.x, v.y), b1 = __floats2bfloat162_rn(v.z, v.w);
+              uint2 u;
+              u.x = *reinterpret_cast<const uint32_t*>(&b0);
+              u.y = *reinterpret_cast<const uint32_t*>(&b1);
+              if (pk[i]) *reinterpret_cast<uint2*>(p.y_bf16 + po[i] + slab * 16) = u;
+            } else if (pk[i]) *reinterpret_cast<float4*>(p.y + po[i] + slab * 16) = v;
           }
         }
         continue;
@@ -1000,7 +1011,9 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 template <int BN, bool BF16>
 __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_conv_params p,
                                                                      const __grid_constant__ CUtensorMap tm_hi,
-                                                                     const __grid_constant__ CUtensorMap tm_lo) {
+                                                                     const __grid_constant__ CUtensorMap tm_lo,
+                                                                     const __grid_constant__ CUtensorMap tm_a,
+                                                                     const __grid_constant__ CUtensorMap tm_a_lo) {
   using S = Smem<BN, BF16>;
   constexpr int KBE = S::KBE;              // K elements per stage
   constexpr int CE = 16 / S::ES;           // elements per 16-byte chunk
@@ -1012,7 +1025,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
   const int tiles_n = (p.cout + BN - 1) / BN;
   const int total_tiles = tiles_n * ((p.m + TM - 1) / TM);
   const int ablate = p.impl >= 8 ? p.impl - 8 : 0;
-  PipeBars pb = setup_pipeline<BN, BF16>(sm, warp, lane, NPROD + 1);   // 128 cp.async completions + the expect_tx arrive
+  // x_plain (1x1 stride-1 convs and their data gradients: A is a plain [m, cin] matrix): the A tiles come by TMA like the
+  // weights, `full` then counts only the expect_tx arrive.  Otherwise: 128 cp.async completions + the expect_tx arrive.
+  const bool plain_a = p.x_plain != 0;
+  PipeBars pb = setup_pipeline<BN, BF16>(sm, warp, lane, plain_a ? 1 : NPROD + 1);
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
 
   if (warp >= MMA_WARP) {
@@ -1025,7 +1041,32 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
   } else if (warp < DRAIN_WARP0) {
     // ------------------------------ producers ------------------------------
     regs_release_producer();
-    if (!(ablate & 1)) {
+    if (plain_a) {
+      // One thread feeds the whole ring: per K block one expect_tx and 2 (bf16) or 4 (hi + lo images) TMA tiles.  The
+      // per-tile chain of the gather path (row entries -> group barriers -> tap offsets -> 8-16 cp.async per thread) took
+      // ~7 k cycles per tile on the 1-2-K-block tiles of the 64-channel layers against 0.25-1.5 k cycles of MMA time.
+      if (warp == 0 && !(ablate & 1)) {
+        if (elect_one()) {
+          const uint32_t tiles0 = smem_u32(sm);
+          uint32_t stage = 0, phase = 0;
+          for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n0 = (tile % tiles_n) * BN;
+            const int m0 = (tile / tiles_n) * TM;
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(pb.empty(stage), phase ^ 1u, 3000 + kb);
+              const uint32_t a_hi = tiles0 + stage * S::STAGE_BYTES;
+              mbar_arrive_expect_tx(pb.full(stage), S::NIMG * (A_TILE_BYTES + S::B_TILE_BYTES));
+              tma_load_2d(a_hi, &tm_a, kb * KBE, m0, pb.full(stage));
+              if (!BF16) tma_load_2d(a_hi + A_TILE_BYTES, &tm_a_lo, kb * KBE, m0, pb.full(stage));
+              tma_load_2d(a_hi + S::NIMG * A_TILE_BYTES, &tm_hi, kb * KBE, n0, pb.full(stage));
+              if (!BF16) tma_load_2d(a_hi + 2 * A_TILE_BYTES + S::B_TILE_BYTES, &tm_lo, kb * KBE, n0, pb.full(stage));
+              if (++stage == (uint32_t)S::STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    } else if (!(ablate & 1)) {
     const int group = warp >> 2;
     const int t = tid & 127;
     const int chunk = t & 7;
@@ -1677,13 +1718,19 @@ static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
   }
-  CUtensorMap tm_hi, tm_lo;
+  CUtensorMap tm_hi, tm_lo, tm_a, tm_a_lo;
   const int K = p.r * p.s * p.cin;
   if (int rc = make_weight_map(&tm_hi, p.w, p.cout, K, BN)) return rc;
   if (int rc = make_weight_map(&tm_lo, p.w_lo, p.cout, K, BN)) return rc;
+  memset(&tm_a, 0, sizeof(tm_a));
+  memset(&tm_a_lo, 0, sizeof(tm_a_lo));
+  if (p.x_plain) {                                          // A = x as a plain [m, cin] matrix: box of 32 channels x 128 rows
+    if (int rc = make_weight_map(&tm_a, p.x, p.m, p.cin, TM)) return rc;
+    if (int rc = make_weight_map(&tm_a_lo, p.x_lo, p.m, p.cin, TM)) return rc;
+  }
   const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_async_kernel<BN, false><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo);
+  conv_tc_async_kernel<BN, false><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo, tm_a, tm_a_lo);
   return check_launch("zsg_conv_fwd");
 }
 
@@ -1717,9 +1764,13 @@ static int launch_conv_bf16(const zsg_conv_params& p, cudaStream_t st) {
   memset(&tm_unused, 0, sizeof(tm_unused));
   const int K = p.r * p.s * p.cin;
   if (int rc = make_bf16_map(&tm_w, p.w_bf16, p.cout, K, BN, "weights")) return rc;
+  CUtensorMap tm_a;
+  memset(&tm_a, 0, sizeof(tm_a));
+  if (p.x_plain)                                            // A = x_bf16 as a plain [m, cin] matrix: 64 channels x 128 rows
+    if (int rc = make_bf16_map(&tm_a, p.x_bf16, p.m, p.cin, TM, "x")) return rc;
   const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_async_kernel<BN, true><<<grid, NTHREADS2, S::TOTAL, st>>>(p, tm_w, tm_unused);
+  conv_tc_async_kernel<BN, true><<<grid, NTHREADS2, S::TOTAL, st>>>(p, tm_w, tm_unused, tm_a, tm_unused);
   return check_launch("zsg_conv_fwd(bf16)");
 }
 
@@ -1836,13 +1887,18 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   zsg_conv_params p = *pp;
   ZSG_REQUIRE(p.dil >= 0 && p.dil <= 64, "zsg_conv_fwd: dil=%d out of range", p.dil);
   if (p.dil == 0) p.dil = 1;
-  ZSG_REQUIRE(((p.x && p.w) || (p.x_bf16 && p.w_bf16)) && p.y && p.rows, "zsg_conv_fwd: null pointer");
+  ZSG_REQUIRE(((p.x && p.w) || (p.x_bf16 && p.w_bf16)) && (p.y || p.y_bf16) && p.rows, "zsg_conv_fwd: null pointer");
+  ZSG_REQUIRE(!p.y_bf16 || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.accumulate && p.cout % 4 == 0 &&
+                            p.impl != 1 && (p.x_lo || p.x_bf16) && ((uintptr_t)p.y_bf16 & 7) == 0),
+              "zsg_conv_fwd: y_bf16 needs a plain output (no bias / ReLU / mask / residual / accumulate), cout %% 4 == 0, an "
+              "operand-image input and the tcgen05 path");
   ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.r > 0 && p.s > 0, "zsg_conv_fwd: empty problem");
   ZSG_REQUIRE(p.cin > 0 && p.cin % 4 == 0, "zsg_conv_fwd: cin=%d must be a multiple of 4", p.cin);
   ZSG_REQUIRE(p.in_div == 1 || p.in_div == 2, "zsg_conv_fwd: in_div must be 1 or 2");
   ZSG_REQUIRE((((uintptr_t)p.x | (uintptr_t)p.w) & 15) == 0, "zsg_conv_fwd: x and w must be 16-byte aligned");
   ZSG_REQUIRE(p.impl != 1 || (p.x && p.w), "zsg_conv_fwd: the SIMT check kernel reads the fp32 operands");
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_fwd: in_scale without in_shift");
+  ZSG_REQUIRE(!p.x_plain || (p.r == 1 && p.s == 1 && p.in_div == 1), "zsg_conv_fwd: x_plain needs r = s = 1 and in_div = 1");
   ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.accumulate && p.impl != 1),
               "zsg_conv_fwd: stats needs a plain output (no bias / ReLU / mask / residual / accumulate) on the tcgen05 path");
   cudaStream_t st = as_stream(stream);

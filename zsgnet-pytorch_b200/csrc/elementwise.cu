@@ -41,6 +41,24 @@ __device__ __forceinline__ void st4_bf16(uint16_t* p, float4 v) {
   u.y = *reinterpret_cast<const uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
 }
+// Activation tensors are float32, or -- trunk activations of the bf16 engine (conv outputs, block outputs: "bf16 storage")
+// -- bfloat16.  Kernels take them as const void* plus a flag word; e = element index (a multiple of 4).
+enum { TF_ACT = 1,    // x / r / act_out (forward activations) are bfloat16
+       TF_DY = 2,     // dy is bfloat16
+       TF_DZ = 4,     // dz_out is bfloat16
+       TF_Y = 8 };    // y (the kernel's forward output) is bfloat16
+__device__ __forceinline__ float4 ldx4(const void* p, bool b16, size_t e) {
+  if (b16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + e);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xFFFF0000u));
+  }
+  return ld4(reinterpret_cast<const float*>(p) + e);
+}
+__device__ __forceinline__ void stx4(void* p, bool b16, size_t e, float4 v) {
+  if (b16) st4_bf16(reinterpret_cast<uint16_t*>(p) + e, v);
+  else st4(reinterpret_cast<float*>(p) + e, v);
+}
 // operand image of a value the kernel has in registers: TF32 remainder (float) or bf16 copy, whichever the caller passed
 __device__ __forceinline__ void st_image(float* lo, uint16_t* b16, int64_t i4, float4 v) {
   if (lo) st4(lo + i4, tf32_lo4(v));
@@ -54,10 +72,11 @@ __device__ __forceinline__ void st_image(float* lo, uint16_t* b16, int64_t i4, f
 // ------------------------------------------------------------------------------------------
 template <int MODE>   // 0: stats (sum x, sum x^2); 1: bn backward (sum dz, sum dz*xhat)
 __global__ void __launch_bounds__(256) channel_reduce_kernel(
-    const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ act_out,
+    const void* __restrict__ x, const void* __restrict__ dy, const void* __restrict__ act_out,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
-    const float* __restrict__ shift, int mask_mode, float* __restrict__ dz_out, double* __restrict__ sums,
-    int64_t rows, int C, int cols) {
+    const float* __restrict__ shift, int mask_mode, void* __restrict__ dz_out, double* __restrict__ sums,
+    int64_t rows, int C, int cols, int tf) {
+  const bool xb = tf & TF_ACT, gb = tf & TF_DY, zb = tf & TF_DZ;
   const int lane_c = threadIdx.x % cols;
   const int lane_r = threadIdx.x / cols;
   const int rpb = 256 / cols;
@@ -81,10 +100,10 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
       const int64_t rr = r + u * stride;
       ok[u] = rr < rows;
       const size_t off = (size_t)(ok[u] ? rr : r) * C + c;
-      v[u] = ld4(x + off);
+      v[u] = ldx4(x, xb, off);
       if (MODE == 1) {
-        g[u] = ld4(dy + off);
-        if (mask_mode == 2) a[u] = ld4(act_out + off);
+        g[u] = ldx4(dy, gb, off);
+        if (mask_mode == 2) a[u] = ldx4(act_out, xb, off);
       }
     }
     float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
@@ -104,7 +123,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
         } else if (mask_mode == 2) {
           gg.x = a[u].x > 0.f ? gg.x : 0.f; gg.y = a[u].y > 0.f ? gg.y : 0.f;
           gg.z = a[u].z > 0.f ? gg.z : 0.f; gg.w = a[u].w > 0.f ? gg.w : 0.f;
-          if (dz_out) st4(dz_out + (size_t)(r + u * stride) * C + c, gg);
+          if (dz_out) stx4(dz_out, zb, (size_t)(r + u * stride) * C + c, gg);
         }
         f1[0] += gg.x; f1[1] += gg.y; f1[2] += gg.z; f1[3] += gg.w;
         f2[0] = fmaf(gg.x, (v[u].x - mu.x) * is.x, f2[0]); f2[1] = fmaf(gg.y, (v[u].y - mu.y) * is.y, f2[1]);
@@ -131,9 +150,9 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
   }
 }
 
-static int launch_channel_reduce(int mode, const float* x, const float* dy, const float* act_out, const float* mean,
+static int launch_channel_reduce(int mode, const void* x, const void* dy, const void* act_out, const float* mean,
                                  const float* invstd, const float* scale, const float* shift, int mask_mode,
-                                 float* dz_out, double* sums, int64_t rows, int C, cudaStream_t st) {
+                                 void* dz_out, double* sums, int64_t rows, int C, cudaStream_t st, int tf = 0) {
   ZSG_REQUIRE(C % 4 == 0 && C >= 4, "channel reduce: C=%d must be a multiple of 4", C);
   int c4 = C / 4;
   int cols = c4 >= 256 ? 256 : c4;
@@ -146,10 +165,10 @@ static int launch_channel_reduce(int mode, const float* x, const float* dy, cons
   dim3 grid(gx, gy);
   if (mode == 0)
     channel_reduce_kernel<0><<<grid, 256, 0, st>>>(x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out,
-                                                   sums, rows, C, cols);
+                                                   sums, rows, C, cols, tf);
   else
     channel_reduce_kernel<1><<<grid, 256, 0, st>>>(x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out,
-                                                   sums, rows, C, cols);
+                                                   sums, rows, C, cols, tf);
   return check_launch("channel_reduce");
 }
 
@@ -185,33 +204,35 @@ __global__ void bn_eval_affine_kernel(const float* rm, const float* rv, const fl
   shift[c] = beta[c] - rm[c] * sc;
 }
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, const float* __restrict__ r,
+__global__ void __launch_bounds__(256) bn_apply_kernel(const void* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const void* __restrict__ r,
                                                        const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, int relu,
                                                        float* __restrict__ y, float* __restrict__ y_lo,
-                                                       uint16_t* __restrict__ y_b16, int64_t n4, int c4) {
+                                                       uint16_t* __restrict__ y_b16, int64_t n4, int c4, int tf) {
+  const bool xb = tf & TF_ACT;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
-    float4 v = fma4(ld4(x + i * 4), ld4(scale + c), ld4(shift + c));
+    float4 v = fma4(ldx4(x, xb, i * 4), ld4(scale + c), ld4(shift + c));
     if (r) {
-      float4 q = ld4(r + i * 4);
+      float4 q = ldx4(r, xb, i * 4);
       if (rscale) q = fma4(q, ld4(rscale + c), ld4(rshift + c));
       v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
     if (relu) v = relu4(v);
-    st4(y + i * 4, v);
+    if (y) st4(y + i * 4, v);                              // bf16 storage: the bfloat16 tensor (y_b16) is the only copy
     st_image(y_lo, y_b16, i * 4, v);
   }
 }
 
 // operand preparation for the cp.async GEMM paths: z = relu?(x * scale + shift), lo = z - trunc_tf32(z)
-__global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256) split_act_kernel(const void* __restrict__ x, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int relu, float* __restrict__ z,
                                                         float* __restrict__ lo, uint16_t* __restrict__ b16, int64_t n4,
-                                                        int c4) {
+                                                        int c4, int tf) {
+  const bool xb = tf & TF_ACT;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = ld4(x + i * 4);
+    float4 v = ldx4(x, xb, i * 4);
     if (scale) {
       const int c = (int)(i % c4) * 4;
       v = fma4(v, ld4(scale + c), ld4(shift + c));
@@ -223,11 +244,12 @@ __global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
-    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+    const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
-    const float* __restrict__ shift, const float* __restrict__ act_out, int mask_mode,
+    const float* __restrict__ shift, const void* __restrict__ act_out, int mask_mode,
     const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dx_lo, uint16_t* __restrict__ dx_b16,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C, int tf) {
+  const bool xb = tf & TF_ACT, gb = tf & TF_DY;
   const int c4 = C / 4;
   const int64_t n4 = rows * c4;
   const float inv_n = 1.0f / (float)rows;
@@ -246,9 +268,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * nthreads;
       if (i < n4) {
-        g[u] = ld4(dy + i * 4);
-        v[u] = ld4(x + i * 4);
-        if (mask_mode == 2) a[u] = ld4(act_out + i * 4);
+        g[u] = ldx4(dy, gb, i * 4);
+        v[u] = ldx4(x, xb, i * 4);
+        if (mask_mode == 2) a[u] = ldx4(act_out, xb, i * 4);
       }
     }
 #pragma unroll
@@ -338,13 +360,274 @@ __global__ void __launch_bounds__(256) bn_partials_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 storage kernels: EIGHT channels per thread, so that a bfloat16 tensor is read / written with 16-byte accesses
+// like the fp32 kernels above (with 4 channels = 8 bytes per access these passes are bound by the number of memory
+// requests in flight, not by bytes: halving the bytes alone changed nothing, measured).  x / r / act_out / y are
+// bfloat16; dy and dz_out are float32 or bfloat16 (template flags).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool B16>
+__device__ __forceinline__ void ldraw8(const void* p, size_t e, uint4& a, uint4& b) {
+  if (B16) {
+    a = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + e);
+  } else {
+    a = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p) + e);
+    b = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p) + e + 4);
+  }
+}
+template <bool B16>
+__device__ __forceinline__ void unpack8(const uint4& a, const uint4& b, float (&f)[8]) {
+  if (B16) {
+    f[0] = __uint_as_float(a.x << 16); f[1] = __uint_as_float(a.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(a.y << 16); f[3] = __uint_as_float(a.y & 0xFFFF0000u);
+    f[4] = __uint_as_float(a.z << 16); f[5] = __uint_as_float(a.z & 0xFFFF0000u);
+    f[6] = __uint_as_float(a.w << 16); f[7] = __uint_as_float(a.w & 0xFFFF0000u);
+  } else {
+    f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+    f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <bool B16>
+__device__ __forceinline__ void st8(void* p, size_t e, const float (&f)[8]) {
+  if (B16) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p) + e) = u;
+  } else {
+    st4(reinterpret_cast<float*>(p) + e, make_float4(f[0], f[1], f[2], f[3]));
+    st4(reinterpret_cast<float*>(p) + e + 4, make_float4(f[4], f[5], f[6], f[7]));
+  }
+}
+__device__ __forceinline__ void ldc8(const float* p, int c, float (&f)[8]) {       // per-channel parameters (L1 / L2 resident)
+  const float4 a = ld4(p + c), b = ld4(p + c + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Thread layout of the kernels below: a thread owns the SAME 8 channels for the whole launch (column lane_c of `cols`
+// = min(C / 8, 256) columns per block, grid.y walks column groups) and strides over rows, so every per-channel
+// coefficient is loaded once into registers and the row loop is loads + a few FMAs + one 16-byte store.
+struct Cols8 {
+  int c, lane_r, rpb;
+  __device__ __forceinline__ Cols8(int cols) {
+    c = (blockIdx.y * cols + threadIdx.x % cols) * 8;
+    lane_r = threadIdx.x / cols;
+    rpb = 256 / cols;
+  }
+};
+static inline bool cols8_geometry(int C, int64_t rows, int rows_per_iter, int& cols, dim3& grid) {
+  if (C % 8) return false;
+  const int c8 = C / 8;
+  cols = c8 >= 256 ? 256 : c8;
+  if ((cols & (cols - 1)) != 0 || c8 % cols != 0) return false;
+  const int rpb = 256 / cols, gy = c8 / cols;
+  const int64_t want = (rows + (int64_t)rpb * rows_per_iter - 1) / ((int64_t)rpb * rows_per_iter);
+  const int64_t cap = (int64_t)num_sms() * 8 / gy;
+  grid = dim3((unsigned)(want < 1 ? 1 : (want > cap ? cap : want)), gy);
+  return true;
+}
+
+// y = bf16(relu?(x * scale + shift [+ r * rscale + rshift | + r])): BatchNorm+ReLU image of a conv output (r = NULL) and
+// the bottleneck tail
+__global__ void __launch_bounds__(256) bn_apply8_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, const uint16_t* __restrict__ r,
+                                                        const float* __restrict__ rscale, const float* __restrict__ rshift,
+                                                        int relu, uint16_t* __restrict__ y, int64_t rows, int C, int cols) {
+  const Cols8 t(cols);
+  float sc[8], sh[8], rs[8], rh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = 1.f; sh[k] = 0.f; rs[k] = 1.f; rh[k] = 0.f; }
+  if (scale) { ldc8(scale, t.c, sc); ldc8(shift, t.c, sh); }
+  if (rscale) { ldc8(rscale, t.c, rs); ldc8(rshift, t.c, rh); }
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * t.rpb;
+  for (int64_t r0 = (int64_t)blockIdx.x * t.rpb + t.lane_r; r0 < rows; r0 += U * stride) {
+    uint4 xr[U], rr[U], dummy;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = r0 + u * stride;
+      if (row < rows) {
+        ldraw8<true>(x, (size_t)row * C + t.c, xr[u], dummy);
+        if (r) ldraw8<true>(r, (size_t)row * C + t.c, rr[u], dummy);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = r0 + u * stride;
+      if (row >= rows) break;
+      float v[8], q[8];
+      unpack8<true>(xr[u], dummy, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+      if (r) {
+        unpack8<true>(rr[u], dummy, q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += fmaf(q[k], rs[k], rh[k]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+      st8<true>(y, (size_t)row * C + t.c, v);
+    }
+  }
+}
+
+// BatchNorm backward reduce over bfloat16 activations: sums[0:C] = sum dz, sums[C:2C] = sum dz * xhat with
+// dz = dy * relu-mask.  Accumulates sum dz and sum dz * x (fp32 over a few rows, then fp64) and centres once at the end:
+// sum dz * xhat = invstd * (sum dz * x - mean * sum dz), in fp64.
+template <bool GB, bool ZB>
+__global__ void __launch_bounds__(256) bn_bwd_reduce8_kernel(
+    const uint16_t* __restrict__ x, const void* __restrict__ dy, const uint16_t* __restrict__ act_out,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
+    const float* __restrict__ shift, int mask_mode, void* __restrict__ dz_out, double* __restrict__ sums, int64_t rows,
+    int C, int cols) {
+  const Cols8 t(cols);
+  const int c = t.c;
+  double a1[8], a2[8];
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a1[k] = 0.0; a2[k] = 0.0; sc[k] = 0.f; sh[k] = 0.f; }
+  if (mask_mode == 1) { ldc8(scale, c, sc); ldc8(shift, c, sh); }
+  const int64_t stride = (int64_t)gridDim.x * t.rpb;
+  constexpr int U = GB ? 4 : 2;
+  for (int64_t r = (int64_t)blockIdx.x * t.rpb + t.lane_r; r < rows; r += U * stride) {
+    uint4 xr[U], ga[U], gb2[U], ar[U], dummy;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * stride;
+      if (rr < rows) {
+        const size_t off = (size_t)rr * C + c;
+        ldraw8<true>(x, off, xr[u], dummy);
+        ldraw8<GB>(dy, off, ga[u], gb2[u]);
+        if (mask_mode == 2) ldraw8<true>(act_out, off, ar[u], dummy);
+      }
+    }
+    float f1[8], f2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u * stride >= rows) break;
+      float v[8], g[8];
+      unpack8<true>(xr[u], dummy, v);
+      unpack8<GB>(ga[u], gb2[u], g);
+      if (mask_mode == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = fmaf(v[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+      } else if (mask_mode == 2) {
+        float a[8];
+        unpack8<true>(ar[u], dummy, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = a[k] > 0.f ? g[k] : 0.f;
+        if (dz_out) st8<ZB>(dz_out, (size_t)(r + u * stride) * C + c, g);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        f1[k] += g[k];
+        f2[k] = fmaf(g[k], v[k], f2[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a1[k] += (double)f1[k]; a2[k] += (double)f2[k]; }
+  }
+  __shared__ double sm[2][256][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sm[0][threadIdx.x][k] = a1[k]; sm[1][threadIdx.x][k] = a2[k]; }
+  __syncthreads();
+  if (t.lane_r == 0) {
+    const int lane_c = threadIdx.x % cols;
+    for (int j = 1; j < t.rpb; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a1[k] += sm[0][j * cols + lane_c][k]; a2[k] += sm[1][j * cols + lane_c][k]; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sums[c + k], a1[k]);
+      atomicAdd(&sums[C + c + k], ((double)invstd[c + k]) * (a2[k] - (double)mean[c + k] * a1[k]));
+    }
+  }
+}
+
+// dx = gamma * invstd * (dz - s1/n - xhat * s2/n) = A * dz + Bc * x + Cc with per-channel A, Bc, Cc (registers)
+template <bool GB>
+__global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(
+    const void* __restrict__ dy, const uint16_t* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
+    const float* __restrict__ shift, const uint16_t* __restrict__ act_out, int mask_mode,
+    const double* __restrict__ sums, uint16_t* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    int64_t rows, int C, int cols) {
+  const Cols8 t(cols);
+  const int c = t.c;
+  if (blockIdx.x == 0 && t.lane_r == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (dbeta) dbeta[c + k] = (float)sums[c + k];
+      if (dgamma) dgamma[c + k] = (float)sums[C + c + k];
+    }
+  }
+  float A[8], Bc[8], Cc[8], sc[8], sh[8];
+  {
+    const float inv_n = 1.0f / (float)rows;
+    float mu[8], is[8], gam[8];
+    ldc8(mean, c, mu); ldc8(invstd, c, is); ldc8(gamma, c, gam);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float s1 = (float)sums[c + k] * inv_n, s2 = (float)sums[C + c + k] * inv_n;
+      A[k] = gam[k] * is[k];
+      Bc[k] = -A[k] * is[k] * s2;
+      Cc[k] = -A[k] * s1 - Bc[k] * mu[k];
+      sc[k] = 0.f; sh[k] = 0.f;
+    }
+    if (mask_mode == 1) { ldc8(scale, c, sc); ldc8(shift, c, sh); }
+  }
+  constexpr int U = GB ? 4 : 2;
+  const int64_t stride = (int64_t)gridDim.x * t.rpb;
+  for (int64_t r = (int64_t)blockIdx.x * t.rpb + t.lane_r; r < rows; r += U * stride) {
+    uint4 xr[U], ga[U], gb2[U], ar[U], dummy;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * stride;
+      if (rr < rows) {
+        const size_t off = (size_t)rr * C + c;
+        ldraw8<GB>(dy, off, ga[u], gb2[u]);
+        ldraw8<true>(x, off, xr[u], dummy);
+        if (mask_mode == 2) ldraw8<true>(act_out, off, ar[u], dummy);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * stride;
+      if (rr >= rows) break;
+      float v[8], g[8], o[8];
+      unpack8<true>(xr[u], dummy, v);
+      unpack8<GB>(ga[u], gb2[u], g);
+      if (mask_mode == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = fmaf(v[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+      } else if (mask_mode == 2) {
+        float a[8];
+        unpack8<true>(ar[u], dummy, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = a[k] > 0.f ? g[k] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], g[k], fmaf(Bc[k], v[k], Cc[k]));
+      st8<true>(dx, (size_t)rr * C + c, o);
+    }
+  }
+}
+
 // ------------------------------------- stem max-pool ----------------------------------------
 // forward also records, per output element, which tap of the 3x3 window won (first maximum in row-major scan
 // order over the valid taps, like ATen's max_pool2d): code = dy*3 + dx.  Backward is then a pure gather.
-__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, float* __restrict__ y,
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const void* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, void* __restrict__ y,
                                                           uint8_t* __restrict__ argmax, int B, int H, int W, int C,
-                                                          int Ho, int Wo) {
+                                                          int Ho, int Wo, int tf) {
+  const bool xb = tf & TF_ACT, yb = tf & TF_Y;
   const int c4 = C / 4;
   const int64_t n = (int64_t)B * Ho * Wo * c4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -362,7 +645,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
       for (int dx = 0; dx < 3; ++dx) {
         const int xx = 2 * q - 1 + dx;
         if (xx < 0 || xx >= W) continue;
-        const float4 v = relu4(fma4(ld4(x + (((size_t)b * H + yy) * W + xx) * C + c), sc, sh));
+        const float4 v = relu4(fma4(ldx4(x, xb, (((size_t)b * H + yy) * W + xx) * C + c), sc, sh));
         const unsigned char k = (unsigned char)(dy * 3 + dx);
         if (v.x > m.x) { m.x = v.x; code.x = k; }
         if (v.y > m.y) { m.y = v.y; code.y = k; }
@@ -370,7 +653,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
         if (v.w > m.w) { m.w = v.w; code.w = k; }
       }
     }
-    st4(y + i * 4, m);
+    stx4(y, yb, i * 4, m);
     if (argmax) *reinterpret_cast<uchar4*>(argmax + i * 4) = code;
   }
 }
@@ -900,7 +1183,7 @@ extern "C" int zsg_bn_apply(const float* x, const float* scale, const float* shi
   ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_bn_apply: bad arguments");
   int64_t n4 = rows * (c / 4);
   bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, y_lo,
-                                                                     nullptr, n4, c / 4);
+                                                                     nullptr, n4, c / 4, 0);
   return check_launch("zsg_bn_apply");
 }
 
@@ -910,7 +1193,7 @@ extern "C" int zsg_bn_apply_bf16(const float* x, const float* scale, const float
   ZSG_REQUIRE(x && scale && shift && y && y_bf16 && c % 4 == 0, "zsg_bn_apply_bf16: bad arguments");
   int64_t n4 = rows * (c / 4);
   bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, nullptr,
-                                                                     y_bf16, n4, c / 4);
+                                                                     y_bf16, n4, c / 4, 0);
   return check_launch("zsg_bn_apply_bf16");
 }
 
@@ -921,7 +1204,7 @@ extern "C" int zsg_cast_bf16(const float* x, const float* scale, const float* sh
   ZSG_REQUIRE((((uintptr_t)x & 15) | ((uintptr_t)out & 7)) == 0, "zsg_cast_bf16: x must be 16-byte and out 8-byte aligned");
   if (rows <= 0) return ZSG_OK;
   const int64_t n4 = rows * (c / 4);
-  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, nullptr, nullptr, out, n4, c / 4);
+  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, nullptr, nullptr, out, n4, c / 4, 0);
   return check_launch("zsg_cast_bf16");
 }
 
@@ -932,7 +1215,7 @@ extern "C" int zsg_split_act(const float* x, const float* scale, const float* sh
   ZSG_REQUIRE(z || (!scale && !relu), "zsg_split_act: a prologue needs an output tensor z");
   if (rows <= 0) return ZSG_OK;
   const int64_t n4 = rows * (c / 4);
-  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, z, lo, nullptr, n4, c / 4);
+  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, z, lo, nullptr, n4, c / 4, 0);
   return check_launch("zsg_split_act");
 }
 
@@ -952,7 +1235,7 @@ extern "C" int zsg_bn_bwd_apply(const float* dy, const float* x, const float* me
                                 float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
   ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx && c % 4 == 0, "zsg_bn_bwd_apply: bad arguments");
   bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
-      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dx_lo, nullptr, dgamma, dbeta, rows, c);
+      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dx_lo, nullptr, dgamma, dbeta, rows, c, 0);
   return check_launch("zsg_bn_bwd_apply");
 }
 
@@ -962,7 +1245,7 @@ extern "C" int zsg_bn_bwd_apply_bf16(const float* dy, const float* x, const floa
                                      float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
   ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx_bf16 && c % 4 == 0, "zsg_bn_bwd_apply_bf16: bad arguments");
   bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
-      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, nullptr, dx_bf16, dgamma, dbeta, rows, c);
+      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, nullptr, dx_bf16, dgamma, dbeta, rows, c, 0);
   return check_launch("zsg_bn_bwd_apply_bf16");
 }
 
@@ -971,8 +1254,102 @@ extern "C" int zsg_maxpool_bn_relu_fwd(const float* x, const float* scale, const
                                        zsg_stream_t stream) {
   ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_maxpool_bn_relu_fwd: bad arguments");
   maxpool_fwd_kernel<<<grid_for((int64_t)b * ho * wo * (c / 4), 256), 256, 0, as_stream(stream)>>>(
-      x, scale, shift, y, argmax, b, h, w, c, ho, wo);
+      x, scale, shift, y, argmax, b, h, w, c, ho, wo, 0);
   return check_launch("zsg_maxpool_bn_relu_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 storage (trunk of the bf16 engine): conv outputs, BatchNorm+ReLU images and block outputs live in HBM as
+// bfloat16 only.  Same kernels, bfloat16 loads / stores; statistics, affine and reductions stay fp32 / fp64.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int zsg_act_b16(const uint16_t* x, const float* scale, const float* shift, int relu, uint16_t* out,
+                           int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(x && out && c > 0 && c % 4 == 0, "zsg_act_b16: bad arguments");
+  ZSG_REQUIRE(!scale == !shift, "zsg_act_b16: scale and shift go together");
+  ZSG_REQUIRE((((uintptr_t)x | (uintptr_t)out) & 7) == 0, "zsg_act_b16: x and out must be 8-byte aligned");
+  if (rows <= 0) return ZSG_OK;
+  int cols;
+  dim3 grid;
+  if ((((uintptr_t)x | (uintptr_t)out) & 15) == 0 && cols8_geometry(c, rows, 8, cols, grid)) {
+    bn_apply8_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, nullptr, nullptr, nullptr, relu, out, rows, c, cols);
+    return check_launch("zsg_act_b16");
+  }
+  const int64_t n4 = rows * (c / 4);
+  split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, nullptr, nullptr, out, n4, c / 4,
+                                                                      TF_ACT);
+  return check_launch("zsg_act_b16");
+}
+
+extern "C" int zsg_bn_apply_b16(const uint16_t* x, const float* scale, const float* shift, const uint16_t* r,
+                                const float* rscale, const float* rshift, int relu, uint16_t* y, int64_t rows, int c,
+                                zsg_stream_t stream) {
+  ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_bn_apply_b16: bad arguments");
+  int cols;
+  dim3 grid;
+  if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)r) & 15) == 0 && cols8_geometry(c, rows, 8, cols, grid)) {
+    bn_apply8_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, rows, c, cols);
+    return check_launch("zsg_bn_apply_b16");
+  }
+  int64_t n4 = rows * (c / 4);
+  bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, nullptr,
+                                                                     nullptr, y, n4, c / 4, TF_ACT);
+  return check_launch("zsg_bn_apply_b16");
+}
+
+extern "C" int zsg_bn_bwd_reduce_b16(const void* dy, int dy_is_b16, const uint16_t* x, const float* mean,
+                                     const float* invstd, const float* scale, const float* shift, const uint16_t* act_out,
+                                     int mask_mode, void* dz_out, int dz_is_b16, double* sums, int64_t rows, int c,
+                                     zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && x && mean && invstd && sums, "zsg_bn_bwd_reduce_b16: null pointer");
+  ZSG_REQUIRE(mask_mode != 1 || (scale && shift), "zsg_bn_bwd_reduce_b16: mask_mode 1 needs scale/shift");
+  ZSG_REQUIRE(mask_mode != 2 || act_out, "zsg_bn_bwd_reduce_b16: mask_mode 2 needs act_out");
+  int cols;
+  dim3 grid;
+  if ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)act_out | (uintptr_t)dz_out) & 15) == 0 &&
+      cols8_geometry(c, rows, 8, cols, grid)) {
+    cudaStream_t st = as_stream(stream);
+#define ZSG_RED8(GB, ZB)                                                                                                  \
+  bn_bwd_reduce8_kernel<GB, ZB><<<grid, 256, 0, st>>>(x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out, sums, \
+                                                      rows, c, cols)
+    if (dy_is_b16) { if (dz_is_b16) ZSG_RED8(true, true); else ZSG_RED8(true, false); }
+    else { if (dz_is_b16) ZSG_RED8(false, true); else ZSG_RED8(false, false); }
+#undef ZSG_RED8
+    return check_launch("zsg_bn_bwd_reduce_b16");
+  }
+  return launch_channel_reduce(1, x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out, sums, rows, c,
+                               as_stream(stream), TF_ACT | (dy_is_b16 ? TF_DY : 0) | (dz_is_b16 ? TF_DZ : 0));
+}
+
+extern "C" int zsg_bn_bwd_apply_b16(const void* dy, int dy_is_b16, const uint16_t* x, const float* mean,
+                                    const float* invstd, const float* gamma, const float* scale, const float* shift,
+                                    const uint16_t* act_out, int mask_mode, const double* sums, uint16_t* dx_bf16,
+                                    float* dgamma, float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx_bf16 && c % 4 == 0, "zsg_bn_bwd_apply_b16: bad arguments");
+  int cols;
+  dim3 grid;
+  if ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)act_out | (uintptr_t)dx_bf16) & 15) == 0 &&
+      cols8_geometry(c, rows, 8, cols, grid)) {
+    if (dy_is_b16)
+      bn_bwd_apply8_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode,
+                                                                       sums, dx_bf16, dgamma, dbeta, rows, c, cols);
+    else
+      bn_bwd_apply8_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(dy, x, mean, invstd, gamma, scale, shift, act_out,
+                                                                        mask_mode, sums, dx_bf16, dgamma, dbeta, rows, c, cols);
+    return check_launch("zsg_bn_bwd_apply_b16");
+  }
+  bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
+      dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, nullptr, nullptr, dx_bf16, dgamma, dbeta, rows, c,
+      TF_ACT | (dy_is_b16 ? TF_DY : 0));
+  return check_launch("zsg_bn_bwd_apply_b16");
+}
+
+extern "C" int zsg_maxpool_bn_relu_fwd_b16(const uint16_t* x, const float* scale, const float* shift, uint16_t* y,
+                                           uint8_t* argmax, int b, int h, int w, int c, int ho, int wo,
+                                           zsg_stream_t stream) {
+  ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_maxpool_bn_relu_fwd_b16: bad arguments");
+  maxpool_fwd_kernel<<<grid_for((int64_t)b * ho * wo * (c / 4), 256), 256, 0, as_stream(stream)>>>(
+      x, scale, shift, y, argmax, b, h, w, c, ho, wo, TF_ACT | TF_Y);
+  return check_launch("zsg_maxpool_bn_relu_fwd_b16");
 }
 
 extern "C" int zsg_maxpool_bn_relu_bwd(const uint8_t* argmax, const float* dy, float* da, int b, int h, int w, int c,

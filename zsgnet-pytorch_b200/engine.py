@@ -96,6 +96,12 @@ class Engine:
         # count is not a multiple of 8 (the 3-channel stem, the 300-wide LSTM projection) keep the fp32 path.
         self.dtype, self.bf16 = dtype, dtype == "bf16"
         self.model = store.model
+        # bf16 storage: on the bf16 engine the ResNet trunk's activations (conv outputs, BatchNorm+ReLU images, block
+        # outputs) live in HBM as bfloat16 ONLY -- the tensor is its own GEMM operand image, every elementwise pass moves
+        # half the bytes, and the conv epilogues store half.  Statistics, affine parameters, the gradient stream between
+        # blocks and all accumulation stay fp32.  (torch.autocast(bfloat16) stores the same tensors in bfloat16.)
+        self.b16act = (self.bf16 and self.model == "retina" and impl == ops.IMPL_TC
+                       and os.environ.get("ZSG_B16_ACT", "1") != "0")
         self._rows_cache = {}
         self._operand_cache, self._bwd_lo = {}, {}
         self._side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
@@ -142,6 +148,10 @@ class Engine:
         t = torch.empty(*shape, dtype=torch.bfloat16, device=self.device)
         self.nbytes += t.numel() * 2
         return t
+
+    def act(self, *shape):
+        """Storage of a trunk activation: bfloat16 under bf16 storage, else float32."""
+        return self.img(*shape) if self.b16act else self.buf(*shape)
 
     def stem_input(self, cp):
         """The network input as the first conv reads it, filled by set_inputs (outside the replayed graph): fp32 NHWC4, or
@@ -200,6 +210,16 @@ class Engine:
         """(z, image) of a forward conv input; the split / cast launch is appended to the forward program once per
         tensor.  b16: the image is the bf16 copy of relu?(bn(x)) and z is not materialised (z = x, unused by the GEMMs)."""
         key = (x.data_ptr(), nrows, c, id(pro), bool(relu), bool(b16))
+        if key not in self._operand_cache and x.dtype == torch.bfloat16:
+            # bf16 storage: the tensor is its own operand image; a BatchNorm / ReLU on load is one bfloat16 -> bfloat16 pass
+            assert b16
+            if pro is None and not relu:
+                self._operand_cache[key] = (x, x)
+            else:
+                z = self.img(nrows, c)
+                sc, sh = (pro.scale, pro.shift) if pro is not None else (None, None)
+                self.fwd.append(("fn", lambda: ops.act_b16(x, z, nrows, c, scale=sc, shift=sh, relu=relu)))
+                self._operand_cache[key] = (x, z)
         if key not in self._operand_cache:
             need_z = (pro is not None or relu) and not b16
             z = self.buf(nrows, c) if need_z else x
@@ -273,7 +293,8 @@ class Engine:
             assert parts * 2 * cout <= self._stats_scratch.numel()
             part = (self._stats_scratch, parts)
         op = ConvOp(xz, w_hi, y, rows, self.B * hout * wout, cin, cout, k, k, bias=bias, out_relu=out_relu, impl=self.impl,
-                    w_lo=w_lo, x_lo=x_lo, dil=dil, stats=part[0] if part else None)
+                    w_lo=w_lo, x_lo=x_lo, dil=dil, stats=part[0] if part else None,
+                    x_plain=(k == 1 and stride == 1 and pad == 0))     # identity gather: A tiles by TMA
         self.fwd.append(("op", op))
         return dict(stats=part, wname=wname, x=x, xz=xz, x_lo=x_lo, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
                     hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w, dil=dil, b16=b16)
@@ -328,7 +349,7 @@ class Engine:
             return
         rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, stride, L["pad"], L["dil"])
         self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=stride,
-                               w_lo=wt_lo, x_lo=dy_lo, dil=L["dil"], **epi))
+                               w_lo=wt_lo, x_lo=dy_lo, dil=L["dil"], x_plain=(k == 1 and stride == 1 and L["pad"] == 0), **epi))
 
     def queue_transpose(self, w, wt, cout, k, cin):
         """Flipped-transposed copy of a conv weight for its data gradient.  Copies from the parameter arena into the
@@ -413,8 +434,8 @@ class Engine:
         img4 = self.stem_input(cp)
         w1p_t = self.pool_alloc(64 * 49 * cp)
         w1p, dw1p = w1p_t[0], self.buf(64 * 49 * cp)
-        c1 = self.buf(B * 150 * 150, 64)
-        x0 = self.buf(B * 75 * 75, 64)
+        c1 = self.act(B * 150 * 150, 64)
+        x0 = self.act(B * 75 * 75, 64)
         w1 = st.flat(e + "conv1.weight")
         self.prep_fwd.append(lambda: ops.pad_channels(w1, w1p, 64 * 49, 3, cp))
         self._alloc_head_w0p()                                # region F (forward-time transformed weights) ends here
@@ -449,8 +470,8 @@ class Engine:
                 ho = (h + 2 - 3) // s + 1
                 p = f"{e}layer{li}.{b}."
                 ri, ro = B * h * h, B * ho * ho
-                r1, r2, r3 = self.buf(ri, width), self.buf(ro, width), self.buf(ro, 4 * width)
-                out, g_out = self.buf(ro, 4 * width), self.buf(ro, 4 * width)
+                r1, r2, r3 = self.act(ri, width), self.act(ro, width), self.act(ro, 4 * width)
+                out, g_out = self.act(ro, 4 * width), self.buf(ro, 4 * width)
                 f0 = len(self.fwd)
                 La = self.conv(p + "conv1.weight", inp, h, h, cin, width, 1, 1, 0, r1, stats=True)
                 bnA = self.add_bn(p + "bn1", width, ri)
@@ -463,14 +484,15 @@ class Engine:
                 self.bn_forward(bnC, r3, Lc)
                 Ld = bnD = rd = None
                 if b == 0:
-                    rd = self.buf(ro, 4 * width)
+                    rd = self.act(ro, 4 * width)
                     Ld = self.conv(p + "downsample.0.weight", inp, h, h, cin, 4 * width, 1, s, 0, rd, stats=True)
                     bnD = self.add_bn(p + "downsample.1", 4 * width, ro)
                     self.bn_forward(bnD, rd, Ld)
 
                 ob16 = self.use_b16(4 * width)
-                out_lo = self.img(ro, 4 * width, b16=ob16)    # operand image of the block output, written by the tail
-                self._operand_cache[(out.data_ptr(), ro, 4 * width, id(None), False, ob16)] = (out, out_lo)
+                # operand image of the block output, written by the tail (bf16 storage: the output itself)
+                out_lo = None if self.b16act else self.img(ro, 4 * width, b16=ob16)
+                self._operand_cache[(out.data_ptr(), ro, 4 * width, id(None), False, ob16)] = (out, out if self.b16act else out_lo)
 
                 def tail(r3=r3, bnC=bnC, rd=rd, bnD=bnD, inp=inp, out=out, ro=ro, c=4 * width, out_lo=out_lo):
                     if rd is not None:
@@ -719,7 +741,8 @@ class Engine:
         wih_hi, wih_lo = self.arena_split_views("lstm.weight_ih_l0")
         lstm_first = len(self.fwd)                           # forward items [lstm_first, lstm_end) = the query encoder
         _, qv_lo = self.fwd_operand(qv, B * T, E)
-        self.fwd.append(("op", ConvOp(qv, wih_hi, gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl, w_lo=wih_lo, x_lo=qv_lo)))
+        self.fwd.append(("op", ConvOp(qv, wih_hi, gx, rows_ih, B * T, E, G, 1, 1, impl=self.impl, w_lo=wih_lo, x_lo=qv_lo,
+                                      x_plain=True)))
         self.fwd.append(("fn", lambda: ops.weight_transpose_flip(P("weight_hh_l0"), whh_t, G, 1, 1, Hh)))
         self.fwd.append(("fn", lambda: ops.lstm_fwd_dir(gx, whh_t, P("bias_ih_l0"), P("bias_hh_l0"), h0c0[0], h0c0[1],
                                                         lens, B, T, gates, cs, hprev, lang)))

@@ -45,8 +45,11 @@ class ConvOp:
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
-                 x_lo=None, dil=1, stats=None):
+                 x_lo=None, dil=1, stats=None, x_plain=False):
         self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats)
+        yb = None
+        if _is_bf16(y):                                      # bf16 storage: the output tensor itself is bfloat16
+            y, yb = None, y
         # operand images: float32 x_lo / w_lo = TF32 remainders (3xTF32 path); bfloat16 x_lo / w_lo = the bf16 copies of the
         # operands (bf16 path of BASELINE configs 3-5; goes into the x_bf16 / w_bf16 fields of the parameter block)
         self.bf16 = _is_bf16(x_lo)
@@ -56,7 +59,7 @@ class ConvOp:
             x_lo = w_lo = None
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb))
+                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
         self.kernel = ("conv_bf16_kernel" if self.bf16 else "conv_tc_async_kernel" if x_lo is not None else
@@ -172,23 +175,52 @@ def bn_eval_affine(rm, rv, gamma, beta, eps, c, scale, shift):
 
 
 def bn_apply(x, scale, shift, y, rows, c, relu, r=None, rscale=None, rshift=None, y_lo=None):
+    if _is_bf16(x):                                          # bf16 storage: bfloat16 in, bfloat16 out (y is the only copy)
+        assert _is_bf16(y) and y_lo is None and (r is None or _is_bf16(r))
+        call("zsg_bn_apply_b16", ptr(x), ptr(scale), ptr(shift), ptr(r), ptr(rscale), ptr(rshift), int(relu), ptr(y), rows, c,
+             stream())
+        return
     call("zsg_bn_apply_bf16" if _is_bf16(y_lo) else "zsg_bn_apply", ptr(x), ptr(scale), ptr(shift), ptr(r), ptr(rscale),
          ptr(rshift), int(relu), ptr(y), ptr(y_lo), rows, c, stream())
 
 
+def act_b16(x, out, rows, c, scale=None, shift=None, relu=False):
+    """bf16 storage: out = bf16(relu?(x * scale + shift)) over a bfloat16 tensor."""
+    assert _is_bf16(x) and _is_bf16(out)
+    call("zsg_act_b16", ptr(x), ptr(scale), ptr(shift), int(relu), ptr(out), rows, c, stream())
+
+
 def bn_bwd_reduce(dy, x, mean, invstd, sums, rows, c, mask_mode=0, scale=None, shift=None, act_out=None, dz_out=None):
+    if _is_bf16(x):                                          # bf16 storage
+        assert act_out is None or _is_bf16(act_out)
+        call("zsg_bn_bwd_reduce_b16", ptr(dy), int(_is_bf16(dy)), ptr(x), ptr(mean), ptr(invstd), ptr(scale), ptr(shift),
+             ptr(act_out), mask_mode, ptr(dz_out), int(_is_bf16(dz_out)), ptr(sums), rows, c, stream())
+        return
+    _bn_bwd_reduce_f32(dy, x, mean, invstd, sums, rows, c, mask_mode, scale, shift, act_out, dz_out)
+
+
+def _bn_bwd_reduce_f32(dy, x, mean, invstd, sums, rows, c, mask_mode=0, scale=None, shift=None, act_out=None, dz_out=None):
     call("zsg_bn_bwd_reduce", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(scale), ptr(shift), ptr(act_out), mask_mode,
          ptr(dz_out), ptr(sums), rows, c, stream())
 
 
 def bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, rows, c, mask_mode=0, scale=None, shift=None,
                  act_out=None, dx_lo=None):
+    if _is_bf16(x):                                          # bf16 storage: only the bfloat16 dx is written
+        assert dx is None and _is_bf16(dx_lo) and (act_out is None or _is_bf16(act_out))
+        call("zsg_bn_bwd_apply_b16", ptr(dy), int(_is_bf16(dy)), ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(scale),
+             ptr(shift), ptr(act_out), mask_mode, ptr(sums), ptr(dx_lo), ptr(dgamma), ptr(dbeta), rows, c, stream())
+        return
     call("zsg_bn_bwd_apply_bf16" if _is_bf16(dx_lo) else "zsg_bn_bwd_apply", ptr(dy), ptr(x), ptr(mean), ptr(invstd),
          ptr(gamma), ptr(scale), ptr(shift), ptr(act_out), mask_mode, ptr(sums), ptr(dx), ptr(dx_lo), ptr(dgamma), ptr(dbeta),
          rows, c, stream())
 
 
 def maxpool_bn_relu_fwd(x, scale, shift, y, argmax, b, h, w, c, ho, wo):
+    if _is_bf16(x):
+        assert _is_bf16(y)
+        call("zsg_maxpool_bn_relu_fwd_b16", ptr(x), ptr(scale), ptr(shift), ptr(y), ptr(argmax), b, h, w, c, ho, wo, stream())
+        return
     call("zsg_maxpool_bn_relu_fwd", ptr(x), ptr(scale), ptr(shift), ptr(y), ptr(argmax), b, h, w, c, ho, wo, stream())
 
 
