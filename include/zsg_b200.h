@@ -94,6 +94,8 @@ typedef struct {
                            /* nearest even), indexed like y, INSTEAD of y (y may then be NULL).  Plain outputs only: no bias /     */
                            /* ReLU / mask / residual / accumulate, cout % 4 == 0, row offsets % 4 == 0; `stats` still come from    */
                            /* the fp32 accumulators                                                                                */
+  const uint16_t* residual_bf16; /* optional, instead of `residual`: the same addend read from a bfloat16 tensor indexed like y    */
+                           /* (bf16 storage: the shortcut gradient of a bottleneck block); cout % 4 == 0, row offsets % 4 == 0     */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`

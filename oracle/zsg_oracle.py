@@ -35,7 +35,9 @@ from . import synth
 #   dy.  The LSTM (not a convolution) stays fp32, as in the product.
 #   ResNet-50 trunk ("bf16 storage", what torch.autocast(bfloat16) also does to these tensors): every conv output (the
 #   tensor a BatchNorm reads), the stem's pooled output and every block output is rounded to bfloat16 where it is stored
-#   (store_act); gradients pass those points unrounded.
+#   (store_act); gradients pass those points unrounded.  The block-internal gradients the engine stores are bfloat16 as
+#   well (store_grad): the gradient behind the block's final ReLU (= the shortcut gradient) and the gradients of the two
+#   inner BatchNorm+ReLU images; the gradient stream between blocks stays fp32.
 #   The reference has no bf16 mode of its own; the closest thing it offers, torch.autocast(bfloat16) around the same
 #   modules, additionally rounds every conv OUTPUT to bf16 (tests/test_bf16_network_gpu.py measures both against fp32).
 CONV_MODE = ["fp32"]
@@ -65,6 +67,21 @@ class _StoreBf16(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return g
+
+
+class _StoreGradBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _rb(g)
+
+
+def store_grad(x):
+    """Identity whose GRADIENT is kept in bfloat16 by the bf16 engine; identity in fp32 mode."""
+    return _StoreGradBf16.apply(x) if CONV_MODE[0] == "bf16" else x
 
 
 def store_act(x):
@@ -333,12 +350,12 @@ def bottleneck(sd, x, p, s, bn):
     """torchvision Bottleneck (v1.5: the stride sits on the 3x3): 1x1 -> BN, ReLU -> 3x3(stride s) -> BN, ReLU -> 1x1 (x4) -> BN
     -> + identity (or 1x1/s conv + BN when the block has a `downsample`) -> ReLU.  p = 'backbone.encoder.layerL.B.'."""
     idt = x
-    y = relu(bn(store_act(conv2d(x, sd[p + "conv1.weight"])), p + "bn1"))
-    y = relu(bn(store_act(conv2d(y, sd[p + "conv2.weight"], None, stride=s, padding=1)), p + "bn2"))
+    y = store_grad(relu(bn(store_act(conv2d(x, sd[p + "conv1.weight"])), p + "bn1")))
+    y = store_grad(relu(bn(store_act(conv2d(y, sd[p + "conv2.weight"], None, stride=s, padding=1)), p + "bn2")))
     y = bn(store_act(conv2d(y, sd[p + "conv3.weight"])), p + "bn3")
     if p + "downsample.0.weight" in sd:
         idt = bn(store_act(conv2d(x, sd[p + "downsample.0.weight"], None, stride=s)), p + "downsample.1")
-    return store_act(relu(y + idt))
+    return store_act(relu(store_grad(y + idt)))
 
 
 def resnet50_c3c4c5(sd, img, bn):

@@ -508,7 +508,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
     // instructions per pass of the generic path below (653 per warp and tile in the ncu source view).  Worth 1 % of
     // the training step; the store-heavy 1x1 64->256 conv itself did not move (0.172 -> 0.168 ms), so its limit is
     // not the epilogue's instruction count.
-    const bool plain = !p.bias && !p.out_mask && !p.residual && !p.accumulate && !p.out_relu && (p.cout & 3) == 0 &&
+    const bool plain = !p.bias && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && !p.out_relu && (p.cout & 3) == 0 &&
                        !(ablate & 16);
     int64_t po[4];
     bool pk[4];
@@ -607,6 +607,15 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
             if (k0) { v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w; }
             if (k1) { v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w; }
           }
+          if (p.residual_bf16) {                           // bf16 storage: the shortcut gradient is a bfloat16 tensor
+            uint2 u0 = make_uint2(0u, 0u), u1 = make_uint2(0u, 0u);
+            if (k0) u0 = *reinterpret_cast<const uint2*>(p.residual_bf16 + a0);
+            if (k1) u1 = *reinterpret_cast<const uint2*>(p.residual_bf16 + a1);
+            v0.x += __uint_as_float(u0.x << 16); v0.y += __uint_as_float(u0.x & 0xFFFF0000u);
+            v0.z += __uint_as_float(u0.y << 16); v0.w += __uint_as_float(u0.y & 0xFFFF0000u);
+            v1.x += __uint_as_float(u1.x << 16); v1.y += __uint_as_float(u1.x & 0xFFFF0000u);
+            v1.z += __uint_as_float(u1.y << 16); v1.w += __uint_as_float(u1.y & 0xFFFF0000u);
+          }
           if (p.accumulate) {
             if (k0) q0 = *reinterpret_cast<const float4*>(p.y + a0);
             if (k1) q1 = *reinterpret_cast<const float4*>(p.y + a1);
@@ -622,6 +631,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
             if (k1) *reinterpret_cast<float4*>(p.y + a1) = v1;
           }
         } else {
+          if (p.residual_bf16) __trap();                    // checked on the host: cout % 4 == 0; only unaligned row offsets get here
           if (k0) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o0, n, v0);
           if (k1) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o1, n, v1);
         }
@@ -1888,7 +1898,9 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(p.dil >= 0 && p.dil <= 64, "zsg_conv_fwd: dil=%d out of range", p.dil);
   if (p.dil == 0) p.dil = 1;
   ZSG_REQUIRE(((p.x && p.w) || (p.x_bf16 && p.w_bf16)) && (p.y || p.y_bf16) && p.rows, "zsg_conv_fwd: null pointer");
-  ZSG_REQUIRE(!p.y_bf16 || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.accumulate && p.cout % 4 == 0 &&
+  ZSG_REQUIRE(!p.residual_bf16 || (!p.residual && p.cout % 4 == 0 && p.impl != 1 && ((uintptr_t)p.residual_bf16 & 7) == 0),
+              "zsg_conv_fwd: residual_bf16 excludes residual, needs cout %% 4 == 0 (and row offsets %% 4 == 0) and the tcgen05 path");
+  ZSG_REQUIRE(!p.y_bf16 || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && p.cout % 4 == 0 &&
                             p.impl != 1 && (p.x_lo || p.x_bf16) && ((uintptr_t)p.y_bf16 & 7) == 0),
               "zsg_conv_fwd: y_bf16 needs a plain output (no bias / ReLU / mask / residual / accumulate), cout %% 4 == 0, an "
               "operand-image input and the tcgen05 path");
@@ -1899,7 +1911,7 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(p.impl != 1 || (p.x && p.w), "zsg_conv_fwd: the SIMT check kernel reads the fp32 operands");
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_fwd: in_scale without in_shift");
   ZSG_REQUIRE(!p.x_plain || (p.r == 1 && p.s == 1 && p.in_div == 1), "zsg_conv_fwd: x_plain needs r = s = 1 and in_div = 1");
-  ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.accumulate && p.impl != 1),
+  ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && p.impl != 1),
               "zsg_conv_fwd: stats needs a plain output (no bias / ReLU / mask / residual / accumulate) on the tcgen05 path");
   cudaStream_t st = as_stream(stream);
   if (p.impl == 1) {

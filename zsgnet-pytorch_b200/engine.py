@@ -508,7 +508,13 @@ class Engine:
                 max_o4, max_ow, max_iw = max(max_o4, ro * 4 * width), max(max_ow, ro * width), max(max_iw, ri * width)
                 inp, g_in, cin, h = out, g_out, 4 * width, ho
             stage_out[li] = (inp, g_in, h, cin)
-        sA, sB, sC, sD = self.buf(max_o4), self.buf(max_o4), self.buf(max_ow), self.buf(max_iw)
+        if self.b16act:
+            # bf16 storage of the block-internal gradients too: dz (gradient behind the final ReLU = shortcut gradient), da2 / da1
+            # (gradients of the two inner BatchNorm+ReLU images) are bfloat16; dr3 / drd only ever exist as operand images.
+            # The gradient stream between blocks (g_out / g_in, where contributions accumulate) stays fp32.
+            sA, sB, sC, sD = self.img(max_o4), self.buf(4), self.img(max_ow), self.img(max_iw)
+        else:
+            sA, sB, sC, sD = self.buf(max_o4), self.buf(max_o4), self.buf(max_ow), self.buf(max_iw)
 
         def block_bwd(k):
             def emit():

@@ -50,6 +50,9 @@ class ConvOp:
         yb = None
         if _is_bf16(y):                                      # bf16 storage: the output tensor itself is bfloat16
             y, yb = None, y
+        rb = None
+        if _is_bf16(residual):
+            residual, rb = None, residual
         # operand images: float32 x_lo / w_lo = TF32 remainders (3xTF32 path); bfloat16 x_lo / w_lo = the bf16 copies of the
         # operands (bf16 path of BASELINE configs 3-5; goes into the x_bf16 / w_bf16 fields of the parameter block)
         self.bf16 = _is_bf16(x_lo)
@@ -59,7 +62,7 @@ class ConvOp:
             x_lo = w_lo = None
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb))
+                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb), ptr(rb))
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
         self.kernel = ("conv_bf16_kernel" if self.bf16 else "conv_tc_async_kernel" if x_lo is not None else
