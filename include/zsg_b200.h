@@ -92,7 +92,7 @@ typedef struct {
                            /* address work, no row-table reads on the producer side.  0: unknown (always correct)                 */
   uint16_t* y_bf16;        /* optional ("bf16 storage" of the bf16 engine's trunk): the output is stored as bfloat16 (round to      */
                            /* nearest even), indexed like y, INSTEAD of y (y may then be NULL).  Plain outputs only: no bias /     */
-                           /* ReLU / mask / residual / accumulate, cout % 4 == 0, row offsets % 4 == 0; `stats` still come from    */
+                           /* ReLU / mask / residual / accumulate, cout % 8 == 0, row offsets % 8 == 0; `stats` still come from    */
                            /* the fp32 accumulators                                                                                */
   const uint16_t* residual_bf16; /* optional, instead of `residual`: the same addend read from a bfloat16 tensor indexed like y    */
                            /* (bf16 storage: the shortcut gradient of a bottleneck block); cout % 4 == 0, row offsets % 4 == 0     */

@@ -243,7 +243,10 @@ def test_bn_kernels_write_bf16_images(zsg):
     dx2 = torch.empty_like(dx)
     ops.bn_bwd_apply(dy, x, mean, invstd, gamma, sums, dx2, dgam, dbet, rows, c)
     torch.cuda.synchronize()
-    assert torch.equal(dx, dx2) and torch.equal(dxb.view(torch.int16), dx.bfloat16().view(torch.int16))
+    # the image is the rounding of the fp32 value the SAME launch wrote; the fp32-image launch runs the 8-channel kernel
+    # (centred form with per-channel coefficients in registers): same formula, last-ulp association differences
+    assert torch.equal(dxb.view(torch.int16), dx.bfloat16().view(torch.int16))
+    assert float((dx - dx2).abs().max()) <= 2e-6 * float(dx.abs().max())
 
 
 # ------------------------------------------------------------------------------------------------------------------

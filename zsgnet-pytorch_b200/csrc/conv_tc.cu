@@ -475,11 +475,30 @@ __device__ __noinline__ void epilogue_store_ragged(float* y, const float* out_ma
   }
 }
 
-// drain + epilogue warps of the forward / data-gradient kernels
-template <int BN, bool BF16 = false>
+// drain + epilogue warps of the forward / data-gradient kernels.
+//
+// EPI selects the epilogue at COMPILE time.  The slab loop is unrolled BN/32 times, so every option costs its code four
+// times over, and the three warp roles of this kernel already fill the instruction cache: with the bf16-storage and
+// bf16-residual options added as run-time branches the kernel grew from 3.3 k to 4.4 k SASS instructions and the big 3x3
+// layers, which use neither, lost 13 % (measured).  Each product kernel now carries one of
+//   EPI_PLAIN   y = acc (fp32), optional BatchNorm statistics            -- every conv that feeds a BatchNorm, plain data gradients
+//   EPI_B16     y_bf16 = bf16(acc), optional statistics                  -- the same under bf16 storage
+//   EPI_GENERIC bias / ReLU / mask / residual(_bf16) / accumulate / ragged cout
+// and the register-path kernels keep EPI_ANY (PLAIN or GENERIC decided at run time, as before).
+enum { EPI_PLAIN = 0, EPI_B16 = 1, EPI_GENERIC = 2, EPI_ANY = 3 };
+
+__host__ __device__ inline bool epilogue_is_plain(const zsg_conv_params& p) {
+  return !p.bias && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && !p.out_relu && (p.cout & 3) == 0;
+}
+
+template <int BN, bool BF16 = false, int EPI = EPI_ANY>
 __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t* sm, const PipeBars& pb, uint32_t tmem_base,
                                               int warp, int lane, int nkb, int tiles_n, int total_tiles, int ablate = 0) {
   using S = Smem<BN, BF16>;
+  constexpr bool HAS_PLAIN = EPI == EPI_PLAIN || EPI == EPI_ANY;
+  constexpr bool HAS_B16 = EPI == EPI_B16;
+  constexpr bool HAS_GENERIC = EPI == EPI_GENERIC || EPI == EPI_ANY;
+  constexpr bool HAS_STATS = EPI != EPI_GENERIC;
   // ------------------------------ drain + epilogue ------------------------------
   const int dw = warp - DRAIN_WARP0;
   const int quadrant = dw & 3, half = dw >> 2;
@@ -503,17 +522,13 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
     // with full 32-byte sectors, for the store and for the residual / mask / accumulate reads alike.
     float* stg = reinterpret_cast<float*>(sm + S::EPI_OFF + dw * S::EPI_WARP_BYTES);
     const int rsel = lane >> 2, c4 = (lane & 3) * 4;
-    // Plain stores (every conv that feeds a BatchNorm, the plain data gradients): the row offsets of the four rows
-    // this lane stores are fetched once per tile and the per-slab work is four LDS.128 + four STG.128, against ~100
-    // instructions per pass of the generic path below (653 per warp and tile in the ncu source view).  Worth 1 % of
-    // the training step; the store-heavy 1x1 64->256 conv itself did not move (0.172 -> 0.168 ms), so its limit is
-    // not the epilogue's instruction count.
-    const bool plain = !p.bias && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && !p.out_relu && (p.cout & 3) == 0 &&
-                       !(ablate & 16);
-    int64_t po[4];
-    bool pk[4];
-    bool use_plain = false;
-    if (plain) {
+    // Plain stores: the row offsets of the rows this lane stores are fetched once per tile and the per-slab work is four
+    // LDS.128 + four STG.128, against ~100 instructions per pass of the generic path.
+    const bool plain = EPI == EPI_PLAIN || (EPI == EPI_ANY && epilogue_is_plain(p) && !(ablate & 16));
+    int64_t po[4] = {0, 0, 0, 0};
+    bool pk[4] = {false, false, false, false};
+    bool use_plain = false;                                // vector stores: every row offset is 16-byte aligned
+    if (HAS_PLAIN && plain) {
       bool al = true;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -522,7 +537,23 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         po[i] = (int64_t)o + n0 + half * (BN / 2) + c4;
         al = al && (o & 3) == 0;
       }
-      use_plain = __all_sync(0xffffffffu, al);             // unaligned row offsets: leave the tile to the generic path
+      use_plain = __all_sync(0xffffffffu, al);
+    }
+    // bf16 storage (y_bf16): lane = (8-column half, row) -- two passes of 16 rows, 8 fp32 columns -> ONE 16-byte store,
+    // the two halves of a row's 32 bytes in the same instruction (full sectors); slab reads stay conflict-free
+    const int hb = lane >> 4, rb = lane & 15;
+    int64_t pob[2] = {0, 0};
+    bool pkb[2] = {false, false};
+    if (HAS_B16) {
+      bool al = true;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int o = __shfl_sync(0xffffffffu, out_off, rb + 16 * i);
+        pkb[i] = __shfl_sync(0xffffffffu, (int)row_ok, rb + 16 * i) != 0;
+        pob[i] = (int64_t)o + n0 + half * (BN / 2) + hb * 8;
+        al = al && (o & 7) == 0;
+      }
+      use_plain = __all_sync(0xffffffffu, al);
     }
 #pragma unroll
     for (int slab = 0; slab < BN / 32; ++slab) {
@@ -532,7 +563,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         *reinterpret_cast<float4*>(stg + lane * 20 + j) =
             make_float4(acc[slab * 16 + j], acc[slab * 16 + j + 1], acc[slab * 16 + j + 2], acc[slab * 16 + j + 3]);
       __syncwarp();
-      if (p.stats) {
+      if (HAS_STATS && p.stats) {
         // BatchNorm statistics of this warp's 32 rows x 16 columns while they sit in the slab: lane = (row half,
         // column); the two halves walk rows 20 (or 4) apart, which puts them on different banks (row stride 20 floats).
         // Rows past p.m hold zeros (their A rows were zero-filled), so they add nothing.
@@ -552,22 +583,49 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
           p.stats[((int64_t)((m0 / TM) * 4 + quadrant) * 2 + hsel) * p.cout + ncol] = hsel ? s2 : s1;
       }
       const int n = n0 + half * (BN / 2) + slab * 16 + c4;
-      if (p.y_bf16 && !use_plain) {                         // zsg_conv_fwd checked the epilogue options; only the offsets are left
-        if (lane == 0 && slab == 0) printf("zsg conv: y_bf16 needs row offsets that are multiples of 4\n");
-        __trap();
-      }
-      if (use_plain) {
+      if (HAS_B16) {
+        if (use_plain) {
+          if (n0 + half * (BN / 2) + slab * 16 + hb * 8 < p.cout) {      // cout % 8 == 0: the 8 columns are inside
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float* src = stg + (rb + 16 * i) * 20 + hb * 8;
+              const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+              const __nv_bfloat162 b0 = __floats2bfloat162_rn(v0.x, v0.y), b1 = __floats2bfloat162_rn(v0.z, v0.w);
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(v1.x, v1.y), b3 = __floats2bfloat162_rn(v1.z, v1.w);
+              uint4 u;
+              u.x = *reinterpret_cast<const uint32_t*>(&b0);
+              u.y = *reinterpret_cast<const uint32_t*>(&b1);
+              u.z = *reinterpret_cast<const uint32_t*>(&b2);
+              u.w = *reinterpret_cast<const uint32_t*>(&b3);
+              if (pkb[i]) *reinterpret_cast<uint4*>(p.y_bf16 + pob[i] + slab * 16) = u;
+            }
+          }
+          continue;
+        }
+      } else if (HAS_PLAIN && use_plain) {
         if (n < p.cout) {                                   // cout % 4 == 0: the whole float4 is inside
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 v = *reinterpret_cast<const float4*>(stg + (i * 8 + rsel) * 20 + c4);
-            if (p.y_bf16) {                                 // bf16 storage: 4 values = one 8-byte store, no fp32 copy
-              const __nv_bfloat162 b0 = __floats2bfloat162_rn(v.x, v.y), b1 = __floats2bfloat162_rn(v.z, v.w);
-              uint2 u;
-              u.x = *reinterpret_cast<const uint32_t*>(&b0);
-              u.y = *reinterpret_cast<const uint32_t*>(&b1);
-              if (pk[i]) *reinterpret_cast<uint2*>(p.y_bf16 + po[i] + slab * 16) = u;
-            } else if (pk[i]) *reinterpret_cast<float4*>(p.y + po[i] + slab * 16) = v;
+            if (pk[i]) *reinterpret_cast<float4*>(p.y + po[i] + slab * 16) = v;
+          }
+        }
+        continue;
+      }
+      if (!HAS_GENERIC) {
+        // EPI_PLAIN / EPI_B16 over a row table whose offsets are not 16-byte aligned (no table of the path is): scalar stores,
+        // not unrolled -- correct, compact, never on the hot path
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int r_ = i * 8 + rsel;
+          const int o = __shfl_sync(0xffffffffu, out_off, r_);
+          const bool ok = __shfl_sync(0xffffffffu, (int)row_ok, r_) != 0;
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            if (!ok || n + q >= p.cout) continue;
+            const float v = stg[r_ * 20 + c4 + q];
+            if (HAS_B16) reinterpret_cast<__nv_bfloat16*>(p.y_bf16)[(int64_t)o + n + q] = __float2bfloat16_rn(v);
+            else p.y[(int64_t)o + n + q] = v;
           }
         }
         continue;
@@ -607,7 +665,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
             if (k0) { v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w; }
             if (k1) { v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w; }
           }
-          if (p.residual_bf16) {                           // bf16 storage: the shortcut gradient is a bfloat16 tensor
+          if (EPI == EPI_GENERIC && p.residual_bf16) {      // bf16 storage: the shortcut gradient is a bfloat16 tensor
             uint2 u0 = make_uint2(0u, 0u), u1 = make_uint2(0u, 0u);
             if (k0) u0 = *reinterpret_cast<const uint2*>(p.residual_bf16 + a0);
             if (k1) u1 = *reinterpret_cast<const uint2*>(p.residual_bf16 + a1);
@@ -631,7 +689,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
             if (k1) *reinterpret_cast<float4*>(p.y + a1) = v1;
           }
         } else {
-          if (p.residual_bf16) __trap();                    // checked on the host: cout % 4 == 0; only unaligned row offsets get here
+          if (EPI == EPI_GENERIC && p.residual_bf16) __trap();   // checked on the host: cout % 4 == 0; only unaligned row offsets get here
           if (k0) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o0, n, v0);
           if (k1) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o1, n, v1);
         }
@@ -1018,7 +1076,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 
 // BF16 (p.x_bf16 / p.w_bf16): the same kernel over the bf16 images -- one image per operand, 64 channels per K block,
 // 8 cp.async per producer thread and K block, one TMA weight tile, four kind::f16 MMAs (issue_kblock_bf16).
-template <int BN, bool BF16>
+template <int BN, bool BF16, int EPI>
 __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_conv_params p,
                                                                      const __grid_constant__ CUtensorMap tm_hi,
                                                                      const __grid_constant__ CUtensorMap tm_lo,
@@ -1134,9 +1192,13 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
         const uint32_t a_hi = tiles0 + s * S::STAGE_BYTES;
         if ((t >> 5) == 0) {                               // weights: one TMA tile per image
           if (elect_one()) {
-            mbar_arrive_expect_tx(pb.full(s), S::NIMG * S::B_TILE_BYTES);
-            tma_load_2d(a_hi + S::NIMG * A_TILE_BYTES, &tm_hi, kb * KBE, n0, pb.full(s));
-            if (!BF16) tma_load_2d(a_hi + 2 * A_TILE_BYTES + S::B_TILE_BYTES, &tm_lo, kb * KBE, n0, pb.full(s));
+            if (ablate & 64) {                              // diagnostics: no weight loads
+              mbar_arrive(pb.full(s));
+            } else {
+              mbar_arrive_expect_tx(pb.full(s), S::NIMG * S::B_TILE_BYTES);
+              tma_load_2d(a_hi + S::NIMG * A_TILE_BYTES, &tm_hi, kb * KBE, n0, pb.full(s));
+              if (!BF16) tma_load_2d(a_hi + 2 * A_TILE_BYTES + S::B_TILE_BYTES, &tm_lo, kb * KBE, n0, pb.full(s));
+            }
           }
           __syncwarp();
         }
@@ -1146,6 +1208,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
           const int64_t o = ok ? (int64_t)off[it] * S::ES : 0;
           const uint32_t nbytes = ok ? 16u : 0u;           // 0 source bytes = 16 bytes of zeros (padding)
           const uint32_t dst = a_hi + soff + it * 2048;
+          if (ablate & 32) continue;                        // diagnostics: no input loads
           cp_async16(dst, xh + o, nbytes);
           if (!BF16) cp_async16(dst + A_TILE_BYTES, xl + o, nbytes);
         }
@@ -1160,7 +1223,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
     }
   } else if (warp >= DRAIN_WARP0) {
     regs_take_drain();
-    conv_epilogue<BN, BF16>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
+    conv_epilogue<BN, BF16, EPI>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
   }
   tc_fence_before();
   __syncthreads();
@@ -1720,11 +1783,18 @@ static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
   return check_launch("zsg_conv_fwd");
 }
 
-template <int BN>
-static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
+// the stores can be switched off for timing ablations (impl = 8 + 16) only in the generic epilogue
+static inline int pick_epilogue(const zsg_conv_params& p) {
+  if (p.y_bf16) return EPI_B16;
+  const int ablate = p.impl >= 8 ? p.impl - 8 : 0;
+  return (epilogue_is_plain(p) && !(ablate & 16)) ? EPI_PLAIN : EPI_GENERIC;
+}
+
+template <int BN, int EPI>
+static int launch_conv_async_epi(const zsg_conv_params& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN, false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL);
     if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
   }
@@ -1740,8 +1810,16 @@ static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
   }
   const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_async_kernel<BN, false><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo, tm_a, tm_a_lo);
+  conv_tc_async_kernel<BN, false, EPI><<<grid, NTHREADS2, Smem<BN>::TOTAL, st>>>(p, tm_hi, tm_lo, tm_a, tm_a_lo);
   return check_launch("zsg_conv_fwd");
+}
+template <int BN>
+static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
+  switch (pick_epilogue(p)) {
+    case EPI_PLAIN: return launch_conv_async_epi<BN, EPI_PLAIN>(p, st);
+    case EPI_B16: return launch_conv_async_epi<BN, EPI_B16>(p, st);
+    default: return launch_conv_async_epi<BN, EPI_GENERIC>(p, st);
+  }
 }
 
 // bf16 matrices for TMA: [rows][inner] bf16, inner contiguous; box = 64 inner elements (128 B, swizzle 128B) x box_rows.
@@ -1761,12 +1839,12 @@ static int make_bf16_map(CUtensorMap* map, const uint16_t* base, int rows, int i
   return ZSG_OK;
 }
 
-template <int BN>
-static int launch_conv_bf16(const zsg_conv_params& p, cudaStream_t st) {
+template <int BN, int EPI>
+static int launch_conv_bf16_epi(const zsg_conv_params& p, cudaStream_t st) {
   using S = Smem<BN, true>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_async_kernel<BN, true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) { set_error("conv(bf16): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
     attr_done = true;
   }
@@ -1780,8 +1858,16 @@ static int launch_conv_bf16(const zsg_conv_params& p, cudaStream_t st) {
     if (int rc = make_bf16_map(&tm_a, p.x_bf16, p.m, p.cin, TM, "x")) return rc;
   const int total_tiles = ((p.cout + BN - 1) / BN) * ((p.m + TM - 1) / TM);
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();      // persistent: one CTA per SM
-  conv_tc_async_kernel<BN, true><<<grid, NTHREADS2, S::TOTAL, st>>>(p, tm_w, tm_unused, tm_a, tm_unused);
+  conv_tc_async_kernel<BN, true, EPI><<<grid, NTHREADS2, S::TOTAL, st>>>(p, tm_w, tm_unused, tm_a, tm_unused);
   return check_launch("zsg_conv_fwd(bf16)");
+}
+template <int BN>
+static int launch_conv_bf16(const zsg_conv_params& p, cudaStream_t st) {
+  switch (pick_epilogue(p)) {
+    case EPI_PLAIN: return launch_conv_bf16_epi<BN, EPI_PLAIN>(p, st);
+    case EPI_B16: return launch_conv_bf16_epi<BN, EPI_B16>(p, st);
+    default: return launch_conv_bf16_epi<BN, EPI_GENERIC>(p, st);
+  }
 }
 
 template <int BN>
@@ -1900,9 +1986,9 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(((p.x && p.w) || (p.x_bf16 && p.w_bf16)) && (p.y || p.y_bf16) && p.rows, "zsg_conv_fwd: null pointer");
   ZSG_REQUIRE(!p.residual_bf16 || (!p.residual && p.cout % 4 == 0 && p.impl != 1 && ((uintptr_t)p.residual_bf16 & 7) == 0),
               "zsg_conv_fwd: residual_bf16 excludes residual, needs cout %% 4 == 0 (and row offsets %% 4 == 0) and the tcgen05 path");
-  ZSG_REQUIRE(!p.y_bf16 || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && p.cout % 4 == 0 &&
-                            p.impl != 1 && (p.x_lo || p.x_bf16) && ((uintptr_t)p.y_bf16 & 7) == 0),
-              "zsg_conv_fwd: y_bf16 needs a plain output (no bias / ReLU / mask / residual / accumulate), cout %% 4 == 0, an "
+  ZSG_REQUIRE(!p.y_bf16 || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && p.cout % 8 == 0 &&
+                            p.impl != 1 && (p.x_lo || p.x_bf16) && ((uintptr_t)p.y_bf16 & 15) == 0),
+              "zsg_conv_fwd: y_bf16 needs a plain output (no bias / ReLU / mask / residual / accumulate), cout %% 8 == 0, an "
               "operand-image input and the tcgen05 path");
   ZSG_REQUIRE(p.m > 0 && p.cout > 0 && p.r > 0 && p.s > 0, "zsg_conv_fwd: empty problem");
   ZSG_REQUIRE(p.cin > 0 && p.cin % 4 == 0, "zsg_conv_fwd: cin=%d must be a multiple of 4", p.cin);

@@ -418,40 +418,59 @@ struct Cols8 {
     rpb = 256 / cols;
   }
 };
-static inline bool cols8_geometry(int C, int64_t rows, int rows_per_iter, int& cols, dim3& grid) {
+static inline bool cols8_geometry(int C, int64_t rows, int rows_per_iter, int& cols, dim3& grid, int waves = 8) {
   if (C % 8) return false;
   const int c8 = C / 8;
   cols = c8 >= 256 ? 256 : c8;
   if ((cols & (cols - 1)) != 0 || c8 % cols != 0) return false;
   const int rpb = 256 / cols, gy = c8 / cols;
   const int64_t want = (rows + (int64_t)rpb * rows_per_iter - 1) / ((int64_t)rpb * rows_per_iter);
-  const int64_t cap = (int64_t)num_sms() * 8 / gy;
+  int64_t cap = (int64_t)num_sms() * waves / gy;
+  if (cap < 1) cap = 1;
   grid = dim3((unsigned)(want < 1 ? 1 : (want > cap ? cap : want)), gy);
   return true;
 }
 
-// y = bf16(relu?(x * scale + shift [+ r * rscale + rshift | + r])): BatchNorm+ReLU image of a conv output (r = NULL) and
-// the bottleneck tail
-__global__ void __launch_bounds__(256) bn_apply8_kernel(const uint16_t* __restrict__ x, const float* __restrict__ scale,
-                                                        const float* __restrict__ shift, const uint16_t* __restrict__ r,
+// XB = storage of the forward activations (x, r, act_out and the kernel's own output): true = bfloat16 ("bf16 storage",
+// the tensor is its own GEMM operand image), false = float32 (fp32 engine: the output is the fp32 tensor `y` and / or its
+// TF32 remainder image `y_lo`).
+template <bool XB>
+__device__ __forceinline__ void st_act8(void* y, float* y_lo, size_t e, const float (&v)[8]) {
+  if (XB) {
+    st8<true>(y, e, v);
+  } else {
+    if (y) st8<false>(y, e, v);
+    if (y_lo) {
+      st4(y_lo + e, tf32_lo4(make_float4(v[0], v[1], v[2], v[3])));
+      st4(y_lo + e + 4, tf32_lo4(make_float4(v[4], v[5], v[6], v[7])));
+    }
+  }
+}
+
+// y = relu?(x * scale + shift [+ r * rscale + rshift | + r]): BatchNorm+ReLU image of a conv output (r = NULL) and the
+// bottleneck tail
+template <bool XB>
+__global__ void __launch_bounds__(256) bn_apply8_kernel(const void* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, const void* __restrict__ r,
                                                         const float* __restrict__ rscale, const float* __restrict__ rshift,
-                                                        int relu, uint16_t* __restrict__ y, int64_t rows, int C, int cols) {
+                                                        int relu, void* __restrict__ y, float* __restrict__ y_lo,
+                                                        int64_t rows, int C, int cols) {
   const Cols8 t(cols);
   float sc[8], sh[8], rs[8], rh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sc[k] = 1.f; sh[k] = 0.f; rs[k] = 1.f; rh[k] = 0.f; }
   if (scale) { ldc8(scale, t.c, sc); ldc8(shift, t.c, sh); }
   if (rscale) { ldc8(rscale, t.c, rs); ldc8(rshift, t.c, rh); }
-  constexpr int U = 4;
+  constexpr int U = XB ? 4 : 2;
   const int64_t stride = (int64_t)gridDim.x * t.rpb;
   for (int64_t r0 = (int64_t)blockIdx.x * t.rpb + t.lane_r; r0 < rows; r0 += U * stride) {
-    uint4 xr[U], rr[U], dummy;
+    uint4 xa[U], xb2[U], ra[U], rb2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t row = r0 + u * stride;
       if (row < rows) {
-        ldraw8<true>(x, (size_t)row * C + t.c, xr[u], dummy);
-        if (r) ldraw8<true>(r, (size_t)row * C + t.c, rr[u], dummy);
+        ldraw8<XB>(x, (size_t)row * C + t.c, xa[u], xb2[u]);
+        if (r) ldraw8<XB>(r, (size_t)row * C + t.c, ra[u], rb2[u]);
       }
     }
 #pragma unroll
@@ -459,51 +478,58 @@ __global__ void __launch_bounds__(256) bn_apply8_kernel(const uint16_t* __restri
       const int64_t row = r0 + u * stride;
       if (row >= rows) break;
       float v[8], q[8];
-      unpack8<true>(xr[u], dummy, v);
+      unpack8<XB>(xa[u], xb2[u], v);
+      if (scale) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+      }
       if (r) {
-        unpack8<true>(rr[u], dummy, q);
+        unpack8<XB>(ra[u], rb2[u], q);
+        if (rscale) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] += fmaf(q[k], rs[k], rh[k]);
+          for (int k = 0; k < 8; ++k) q[k] = fmaf(q[k], rs[k], rh[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += q[k];
       }
       if (relu) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
       }
-      st8<true>(y, (size_t)row * C + t.c, v);
+      st_act8<XB>(y, y_lo, (size_t)row * C + t.c, v);
     }
   }
 }
 
-// BatchNorm backward reduce over bfloat16 activations: sums[0:C] = sum dz, sums[C:2C] = sum dz * xhat with
-// dz = dy * relu-mask.  Accumulates sum dz and sum dz * x (fp32 over a few rows, then fp64) and centres once at the end:
-// sum dz * xhat = invstd * (sum dz * x - mean * sum dz), in fp64.
-template <bool GB, bool ZB>
+// BatchNorm backward reduce: sums[0:C] = sum dz, sums[C:2C] = sum dz * xhat with dz = dy * relu-mask.
+// fp32 tensors: xhat = (x - mean) * invstd per element, as the 4-channel kernel.  bf16 storage: accumulates sum dz * x and
+// centres once at the end, sum dz * xhat = invstd * (sum dz * x - mean * sum dz), in fp64.
+template <bool XB, bool GB, bool ZB>
 __global__ void __launch_bounds__(256) bn_bwd_reduce8_kernel(
-    const uint16_t* __restrict__ x, const void* __restrict__ dy, const uint16_t* __restrict__ act_out,
+    const void* __restrict__ x, const void* __restrict__ dy, const void* __restrict__ act_out,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
     const float* __restrict__ shift, int mask_mode, void* __restrict__ dz_out, double* __restrict__ sums, int64_t rows,
     int C, int cols) {
   const Cols8 t(cols);
   const int c = t.c;
   double a1[8], a2[8];
-  float sc[8], sh[8];
+  float sc[8], sh[8], mu[8], is[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { a1[k] = 0.0; a2[k] = 0.0; sc[k] = 0.f; sh[k] = 0.f; }
+  for (int k = 0; k < 8; ++k) { a1[k] = 0.0; a2[k] = 0.0; sc[k] = 0.f; sh[k] = 0.f; mu[k] = 0.f; is[k] = 1.f; }
   if (mask_mode == 1) { ldc8(scale, c, sc); ldc8(shift, c, sh); }
+  if (!XB) { ldc8(mean, c, mu); ldc8(invstd, c, is); }
   const int64_t stride = (int64_t)gridDim.x * t.rpb;
-  constexpr int U = GB ? 4 : 2;
+  constexpr int U = (XB && GB) ? 4 : 2;
   for (int64_t r = (int64_t)blockIdx.x * t.rpb + t.lane_r; r < rows; r += U * stride) {
-    uint4 xr[U], ga[U], gb2[U], ar[U], dummy;
+    uint4 xa[U], xb2[U], ga[U], gb2[U], aa[U], ab2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * stride;
       if (rr < rows) {
         const size_t off = (size_t)rr * C + c;
-        ldraw8<true>(x, off, xr[u], dummy);
+        ldraw8<XB>(x, off, xa[u], xb2[u]);
         ldraw8<GB>(dy, off, ga[u], gb2[u]);
-        if (mask_mode == 2) ldraw8<true>(act_out, off, ar[u], dummy);
+        if (mask_mode == 2) ldraw8<XB>(act_out, off, aa[u], ab2[u]);
       }
     }
     float f1[8], f2[8];
@@ -513,14 +539,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce8_kernel(
     for (int u = 0; u < U; ++u) {
       if (r + u * stride >= rows) break;
       float v[8], g[8];
-      unpack8<true>(xr[u], dummy, v);
+      unpack8<XB>(xa[u], xb2[u], v);
       unpack8<GB>(ga[u], gb2[u], g);
       if (mask_mode == 1) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = fmaf(v[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
       } else if (mask_mode == 2) {
         float a[8];
-        unpack8<true>(ar[u], dummy, a);
+        unpack8<XB>(aa[u], ab2[u], a);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = a[k] > 0.f ? g[k] : 0.f;
         if (dz_out) st8<ZB>(dz_out, (size_t)(r + u * stride) * C + c, g);
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce8_kernel(
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         f1[k] += g[k];
-        f2[k] = fmaf(g[k], v[k], f2[k]);
+        f2[k] = XB ? fmaf(g[k], v[k], f2[k]) : fmaf(g[k], (v[k] - mu[k]) * is[k], f2[k]);
       }
     }
 #pragma unroll
@@ -546,19 +572,20 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce8_kernel(
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       atomicAdd(&sums[c + k], a1[k]);
-      atomicAdd(&sums[C + c + k], ((double)invstd[c + k]) * (a2[k] - (double)mean[c + k] * a1[k]));
+      atomicAdd(&sums[C + c + k], XB ? ((double)invstd[c + k]) * (a2[k] - (double)mean[c + k] * a1[k]) : a2[k]);
     }
   }
 }
 
-// dx = gamma * invstd * (dz - s1/n - xhat * s2/n) = A * dz + Bc * x + Cc with per-channel A, Bc, Cc (registers)
-template <bool GB>
+// dx = gamma * invstd * (dz - s1/n - xhat * s2/n) = A * (dz - s1/n) + Bc * (x - mean), per-channel A, Bc in registers
+// (bf16 storage: folded further into A * dz + Bc * x + Cc)
+template <bool XB, bool GB>
 __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(
-    const void* __restrict__ dy, const uint16_t* __restrict__ x, const float* __restrict__ mean,
+    const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
-    const float* __restrict__ shift, const uint16_t* __restrict__ act_out, int mask_mode,
-    const double* __restrict__ sums, uint16_t* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    int64_t rows, int C, int cols) {
+    const float* __restrict__ shift, const void* __restrict__ act_out, int mask_mode,
+    const double* __restrict__ sums, void* __restrict__ dx, float* __restrict__ dx_lo, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, int64_t rows, int C, int cols) {
   const Cols8 t(cols);
   const int c = t.c;
   if (blockIdx.x == 0 && t.lane_r == 0) {
@@ -568,33 +595,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(
       if (dgamma) dgamma[c + k] = (float)sums[C + c + k];
     }
   }
-  float A[8], Bc[8], Cc[8], sc[8], sh[8];
+  float A[8], Bc[8], Cc[8], mu[8], sc[8], sh[8];
   {
     const float inv_n = 1.0f / (float)rows;
-    float mu[8], is[8], gam[8];
+    float is[8], gam[8];
     ldc8(mean, c, mu); ldc8(invstd, c, is); ldc8(gamma, c, gam);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float s1 = (float)sums[c + k] * inv_n, s2 = (float)sums[C + c + k] * inv_n;
       A[k] = gam[k] * is[k];
       Bc[k] = -A[k] * is[k] * s2;
-      Cc[k] = -A[k] * s1 - Bc[k] * mu[k];
+      Cc[k] = XB ? -A[k] * s1 - Bc[k] * mu[k] : s1;          // fp32: Cc holds s1, the centred form is kept
       sc[k] = 0.f; sh[k] = 0.f;
     }
     if (mask_mode == 1) { ldc8(scale, c, sc); ldc8(shift, c, sh); }
   }
-  constexpr int U = GB ? 4 : 2;
+  constexpr int U = (XB && GB) ? 4 : 2;
   const int64_t stride = (int64_t)gridDim.x * t.rpb;
   for (int64_t r = (int64_t)blockIdx.x * t.rpb + t.lane_r; r < rows; r += U * stride) {
-    uint4 xr[U], ga[U], gb2[U], ar[U], dummy;
+    uint4 xa[U], xb2[U], ga[U], gb2[U], aa[U], ab2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * stride;
       if (rr < rows) {
         const size_t off = (size_t)rr * C + c;
         ldraw8<GB>(dy, off, ga[u], gb2[u]);
-        ldraw8<true>(x, off, xr[u], dummy);
-        if (mask_mode == 2) ldraw8<true>(act_out, off, ar[u], dummy);
+        ldraw8<XB>(x, off, xa[u], xb2[u]);
+        if (mask_mode == 2) ldraw8<XB>(act_out, off, aa[u], ab2[u]);
       }
     }
 #pragma unroll
@@ -602,20 +629,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply8_kernel(
       const int64_t rr = r + u * stride;
       if (rr >= rows) break;
       float v[8], g[8], o[8];
-      unpack8<true>(xr[u], dummy, v);
+      unpack8<XB>(xa[u], xb2[u], v);
       unpack8<GB>(ga[u], gb2[u], g);
       if (mask_mode == 1) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = fmaf(v[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
       } else if (mask_mode == 2) {
         float a[8];
-        unpack8<true>(ar[u], dummy, a);
+        unpack8<XB>(aa[u], ab2[u], a);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = a[k] > 0.f ? g[k] : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], g[k], fmaf(Bc[k], v[k], Cc[k]));
-      st8<true>(dx, (size_t)rr * C + c, o);
+      for (int k = 0; k < 8; ++k)
+        o[k] = XB ? fmaf(A[k], g[k], fmaf(Bc[k], v[k], Cc[k])) : fmaf(Bc[k], v[k] - mu[k], A[k] * (g[k] - Cc[k]));
+      st_act8<XB>(dx, dx_lo, (size_t)rr * C + c, o);
     }
   }
 }
@@ -1181,6 +1209,15 @@ extern "C" int zsg_bn_apply(const float* x, const float* scale, const float* shi
                             const float* rscale, const float* rshift, int relu, float* y, float* y_lo, int64_t rows,
                             int c, zsg_stream_t stream) {
   ZSG_REQUIRE(x && scale && shift && y && c % 4 == 0, "zsg_bn_apply: bad arguments");
+  {
+    int cols;
+    dim3 grid;
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)r | (uintptr_t)y_lo) & 15) == 0 && cols8_geometry(c, rows, 4, cols, grid)) {
+      bn_apply8_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, y_lo, rows, c,
+                                                                   cols);
+      return check_launch("zsg_bn_apply");
+    }
+  }
   int64_t n4 = rows * (c / 4);
   bn_apply_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, y_lo,
                                                                      nullptr, n4, c / 4, 0);
@@ -1214,6 +1251,15 @@ extern "C" int zsg_split_act(const float* x, const float* scale, const float* sh
   ZSG_REQUIRE(!scale == !shift, "zsg_split_act: scale and shift go together");
   ZSG_REQUIRE(z || (!scale && !relu), "zsg_split_act: a prologue needs an output tensor z");
   if (rows <= 0) return ZSG_OK;
+  {
+    int cols;
+    dim3 grid;
+    if ((((uintptr_t)x | (uintptr_t)z | (uintptr_t)lo) & 15) == 0 && cols8_geometry(c, rows, 4, cols, grid)) {
+      bn_apply8_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, nullptr, nullptr, nullptr, relu, z, lo, rows, c,
+                                                                   cols);
+      return check_launch("zsg_split_act");
+    }
+  }
   const int64_t n4 = rows * (c / 4);
   split_act_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(x, scale, shift, relu, z, lo, nullptr, n4, c / 4, 0);
   return check_launch("zsg_split_act");
@@ -1225,6 +1271,16 @@ extern "C" int zsg_bn_bwd_reduce(const float* dy, const float* x, const float* m
   ZSG_REQUIRE(dy && x && mean && invstd && sums, "zsg_bn_bwd_reduce: null pointer");
   ZSG_REQUIRE(mask_mode != 1 || (scale && shift), "zsg_bn_bwd_reduce: mask_mode 1 needs scale/shift");
   ZSG_REQUIRE(mask_mode != 2 || act_out, "zsg_bn_bwd_reduce: mask_mode 2 needs act_out");
+  {
+    int cols;
+    dim3 grid;
+    if ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)act_out | (uintptr_t)dz_out) & 15) == 0 &&
+        cols8_geometry(c, rows, 4, cols, grid, 2)) {
+      bn_bwd_reduce8_kernel<false, false, false><<<grid, 256, 0, as_stream(stream)>>>(x, dy, act_out, mean, invstd, scale, shift,
+                                                                                      mask_mode, dz_out, sums, rows, c, cols);
+      return check_launch("zsg_bn_bwd_reduce");
+    }
+  }
   return launch_channel_reduce(1, x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out, sums, rows, c,
                                as_stream(stream));
 }
@@ -1234,6 +1290,17 @@ extern "C" int zsg_bn_bwd_apply(const float* dy, const float* x, const float* me
                                 int mask_mode, const double* sums, float* dx, float* dx_lo, float* dgamma,
                                 float* dbeta, int64_t rows, int c, zsg_stream_t stream) {
   ZSG_REQUIRE(dy && x && mean && invstd && gamma && sums && dx && c % 4 == 0, "zsg_bn_bwd_apply: bad arguments");
+  {
+    int cols;
+    dim3 grid;
+    if ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)act_out | (uintptr_t)dx | (uintptr_t)dx_lo) & 15) == 0 &&
+        cols8_geometry(c, rows, 4, cols, grid)) {
+      bn_bwd_apply8_kernel<false, false><<<grid, 256, 0, as_stream(stream)>>>(dy, x, mean, invstd, gamma, scale, shift, act_out,
+                                                                              mask_mode, sums, dx, dx_lo, dgamma, dbeta, rows, c,
+                                                                              cols);
+      return check_launch("zsg_bn_bwd_apply");
+    }
+  }
   bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
       dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode, sums, dx, dx_lo, nullptr, dgamma, dbeta, rows, c, 0);
   return check_launch("zsg_bn_bwd_apply");
@@ -1271,7 +1338,8 @@ extern "C" int zsg_act_b16(const uint16_t* x, const float* scale, const float* s
   int cols;
   dim3 grid;
   if ((((uintptr_t)x | (uintptr_t)out) & 15) == 0 && cols8_geometry(c, rows, 8, cols, grid)) {
-    bn_apply8_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, nullptr, nullptr, nullptr, relu, out, rows, c, cols);
+    bn_apply8_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, nullptr, nullptr, nullptr, relu, out, nullptr,
+                                                                rows, c, cols);
     return check_launch("zsg_act_b16");
   }
   const int64_t n4 = rows * (c / 4);
@@ -1287,7 +1355,8 @@ extern "C" int zsg_bn_apply_b16(const uint16_t* x, const float* scale, const flo
   int cols;
   dim3 grid;
   if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)r) & 15) == 0 && cols8_geometry(c, rows, 8, cols, grid)) {
-    bn_apply8_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, rows, c, cols);
+    bn_apply8_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, scale, shift, r, rscale, rshift, relu, y, nullptr, rows, c,
+                                                                cols);
     return check_launch("zsg_bn_apply_b16");
   }
   int64_t n4 = rows * (c / 4);
@@ -1306,11 +1375,11 @@ extern "C" int zsg_bn_bwd_reduce_b16(const void* dy, int dy_is_b16, const uint16
   int cols;
   dim3 grid;
   if ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)act_out | (uintptr_t)dz_out) & 15) == 0 &&
-      cols8_geometry(c, rows, 8, cols, grid)) {
+      cols8_geometry(c, rows, 8, cols, grid, 2)) {
     cudaStream_t st = as_stream(stream);
-#define ZSG_RED8(GB, ZB)                                                                                                  \
-  bn_bwd_reduce8_kernel<GB, ZB><<<grid, 256, 0, st>>>(x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out, sums, \
-                                                      rows, c, cols)
+#define ZSG_RED8(GB, ZB)                                                                                                        \
+  bn_bwd_reduce8_kernel<true, GB, ZB><<<grid, 256, 0, st>>>(x, dy, act_out, mean, invstd, scale, shift, mask_mode, dz_out, sums, \
+                                                            rows, c, cols)
     if (dy_is_b16) { if (dz_is_b16) ZSG_RED8(true, true); else ZSG_RED8(true, false); }
     else { if (dz_is_b16) ZSG_RED8(false, true); else ZSG_RED8(false, false); }
 #undef ZSG_RED8
@@ -1330,11 +1399,13 @@ extern "C" int zsg_bn_bwd_apply_b16(const void* dy, int dy_is_b16, const uint16_
   if ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)act_out | (uintptr_t)dx_bf16) & 15) == 0 &&
       cols8_geometry(c, rows, 8, cols, grid)) {
     if (dy_is_b16)
-      bn_bwd_apply8_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(dy, x, mean, invstd, gamma, scale, shift, act_out, mask_mode,
-                                                                       sums, dx_bf16, dgamma, dbeta, rows, c, cols);
+      bn_bwd_apply8_kernel<true, true><<<grid, 256, 0, as_stream(stream)>>>(dy, x, mean, invstd, gamma, scale, shift, act_out,
+                                                                             mask_mode, sums, dx_bf16, nullptr, dgamma, dbeta, rows,
+                                                                             c, cols);
     else
-      bn_bwd_apply8_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(dy, x, mean, invstd, gamma, scale, shift, act_out,
-                                                                        mask_mode, sums, dx_bf16, dgamma, dbeta, rows, c, cols);
+      bn_bwd_apply8_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(dy, x, mean, invstd, gamma, scale, shift, act_out,
+                                                                              mask_mode, sums, dx_bf16, nullptr, dgamma, dbeta, rows,
+                                                                              c, cols);
     return check_launch("zsg_bn_bwd_apply_b16");
   }
   bn_bwd_apply_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, as_stream(stream)>>>(
