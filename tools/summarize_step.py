@@ -52,9 +52,15 @@ with open(out_md, "w") as f:
         f.write(f"| `{k}` | {n} | {ns / 1e3:.1f} | {100 * ns / tot_ns:.1f}% | {ns / n / 1e3:.1f} | {b / n / 1e6:.1f} | {b / max(ns, 1):.0f} |\n")
 if traffic_json:
     d = json.load(open(traffic_json)) if os.path.exists(traffic_json) else {}
+    suffix = "@" + tag
+    for key in [k for k in d if k.endswith(suffix)]:     # a re-run replaces this tag's entries
+        del d[key]
     for k, (n, ns, b) in agg.items():
         base = re.sub(r"<.*", "", k)
-        key = f"{ {'conv_tc_async_kernel': 'conv_bf16_kernel'}.get(base, base) if (tag.startswith('bf16') and 'true' in k) else base}@{tag.replace('@bs', '@bs')}"
+        m = re.match(r"conv_tc_async_kernel<\d+, (\w+)", k)
+        if m and m.group(1) in ("1", "true"):              # second template argument: the bf16 operand path
+            base = "conv_bf16_kernel"
+        key = f"{base}{suffix}"
         e = d.setdefault(key, dict(launches=0, dram_bytes=0.0, ns=0.0))
         e["launches"] += n
         e["dram_bytes"] += b
