@@ -96,6 +96,9 @@ typedef struct {
                            /* the fp32 accumulators                                                                                */
   const uint16_t* residual_bf16; /* optional, instead of `residual`: the same addend read from a bfloat16 tensor indexed like y    */
                            /* (bf16 storage: the shortcut gradient of a bottleneck block); cout % 4 == 0, row offsets % 4 == 0     */
+  int32_t y_pitch;         /* > 0: rows[i].out == i * y_pitch for every row (the output is a plain [m, y_pitch] matrix, true for  */
+                           /* every forward table of the path but the [B,A,5] scatter): the epilogue then computes the offsets     */
+                           /* instead of reading the table.  0: unknown (always correct)                                           */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`

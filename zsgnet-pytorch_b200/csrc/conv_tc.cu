@@ -509,7 +509,9 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
     const int m0 = (tile / tiles_n) * TM;
     int out_off = 0;
     const bool row_ok = m0 + row < p.m;
-    if (row_ok) out_off = __ldg(&p.rows[m0 + row].out);          // prefetched under the drain
+    // y_pitch: the output is a plain [m, y_pitch] matrix -- no table read (on 1-2-K-block tiles the drain has nothing to
+    // wait for and the ~700-cycle load was exposed once per tile)
+    if (row_ok) out_off = p.y_pitch > 0 ? (m0 + row) * p.y_pitch : __ldg(&p.rows[m0 + row].out);
     float acc[BN / 2];
     if (dw == 0 && lane == 0) trace(gkb0, 12);
     drain_loop<BN>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
@@ -563,19 +565,23 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         *reinterpret_cast<float4*>(stg + lane * 20 + j) =
             make_float4(acc[slab * 16 + j], acc[slab * 16 + j + 1], acc[slab * 16 + j + 2], acc[slab * 16 + j + 3]);
       __syncwarp();
-      if (HAS_STATS && p.stats) {
+      if (HAS_STATS && p.stats && !(ablate & 128)) {
         // BatchNorm statistics of this warp's 32 rows x 16 columns while they sit in the slab: lane = (row half,
         // column); the two halves walk rows 20 (or 4) apart, which puts them on different banks (row stride 20 floats).
         // Rows past p.m hold zeros (their A rows were zero-filled), so they add nothing.
         const int col = lane & 15, hsel = lane >> 4;
-        float s1 = 0.f, s2 = 0.f;
+        float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;        // two chains each: the 16-deep dependent add was exposed
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int rr = hsel ? 16 + ((r + 4) & 15) : r;
-          const float v = stg[rr * 20 + col];
+        for (int r = 0; r < 16; r += 2) {
+          const int ra = hsel ? 16 + ((r + 4) & 15) : r, rb2 = hsel ? 16 + ((r + 5) & 15) : r + 1;
+          const float v = stg[ra * 20 + col], u = stg[rb2 * 20 + col];
           s1 += v;
           s2 = fmaf(v, v, s2);
+          t1 += u;
+          t2 = fmaf(u, u, t2);
         }
+        s1 += t1;
+        s2 += t2;
         s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
         s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
         const int ncol = n0 + half * (BN / 2) + slab * 16 + col;
@@ -597,7 +603,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
               u.y = *reinterpret_cast<const uint32_t*>(&b1);
               u.z = *reinterpret_cast<const uint32_t*>(&b2);
               u.w = *reinterpret_cast<const uint32_t*>(&b3);
-              if (pkb[i]) *reinterpret_cast<uint4*>(p.y_bf16 + pob[i] + slab * 16) = u;
+              if (pkb[i] && !(ablate & 16)) *reinterpret_cast<uint4*>(p.y_bf16 + pob[i] + slab * 16) = u;
             }
           }
           continue;
@@ -607,7 +613,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 v = *reinterpret_cast<const float4*>(stg + (i * 8 + rsel) * 20 + c4);
-            if (pk[i]) *reinterpret_cast<float4*>(p.y + po[i] + slab * 16) = v;
+            if (pk[i] && !(ablate & 16)) *reinterpret_cast<float4*>(p.y + po[i] + slab * 16) = v;
           }
         }
         continue;
@@ -1783,11 +1789,9 @@ static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
   return check_launch("zsg_conv_fwd");
 }
 
-// the stores can be switched off for timing ablations (impl = 8 + 16) only in the generic epilogue
 static inline int pick_epilogue(const zsg_conv_params& p) {
   if (p.y_bf16) return EPI_B16;
-  const int ablate = p.impl >= 8 ? p.impl - 8 : 0;
-  return (epilogue_is_plain(p) && !(ablate & 16)) ? EPI_PLAIN : EPI_GENERIC;
+  return epilogue_is_plain(p) ? EPI_PLAIN : EPI_GENERIC;
 }
 
 template <int BN, int EPI>
@@ -1997,6 +2001,7 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(p.impl != 1 || (p.x && p.w), "zsg_conv_fwd: the SIMT check kernel reads the fp32 operands");
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_fwd: in_scale without in_shift");
   ZSG_REQUIRE(!p.x_plain || (p.r == 1 && p.s == 1 && p.in_div == 1), "zsg_conv_fwd: x_plain needs r = s = 1 and in_div = 1");
+  ZSG_REQUIRE(p.y_pitch == 0 || p.y_pitch >= p.cout, "zsg_conv_fwd: y_pitch=%d must be 0 or >= cout", p.y_pitch);
   ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && p.impl != 1),
               "zsg_conv_fwd: stats needs a plain output (no bias / ReLU / mask / residual / accumulate) on the tcgen05 path");
   cudaStream_t st = as_stream(stream);

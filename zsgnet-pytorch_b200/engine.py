@@ -294,7 +294,8 @@ class Engine:
             part = (self._stats_scratch, parts)
         op = ConvOp(xz, w_hi, y, rows, self.B * hout * wout, cin, cout, k, k, bias=bias, out_relu=out_relu, impl=self.impl,
                     w_lo=w_lo, x_lo=x_lo, dil=dil, stats=part[0] if part else None,
-                    x_plain=(k == 1 and stride == 1 and pad == 0))     # identity gather: A tiles by TMA
+                    x_plain=(k == 1 and stride == 1 and pad == 0),     # identity gather: A tiles by TMA
+                    y_pitch=cout)                                      # conv_rows: out = i * cout
         self.fwd.append(("op", op))
         return dict(stats=part, wname=wname, x=x, xz=xz, x_lo=x_lo, hin=hin, win=win, cin=cin, cout=cout, k=k, stride=stride, pad=pad,
                     hout=hout, wout=wout, rows=rows, pro=pro, in_relu=in_relu, w=w, dil=dil, b16=b16)
@@ -349,7 +350,8 @@ class Engine:
             return
         rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, stride, L["pad"], L["dil"])
         self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=stride,
-                               w_lo=wt_lo, x_lo=dy_lo, dil=L["dil"], x_plain=(k == 1 and stride == 1 and L["pad"] == 0), **epi))
+                               w_lo=wt_lo, x_lo=dy_lo, dil=L["dil"], x_plain=(k == 1 and stride == 1 and L["pad"] == 0),
+                               y_pitch=cin, **epi))                    # dgrad_rows: one row per input pixel, out = i * cin
 
     def queue_transpose(self, w, wt, cout, k, cin):
         """Flipped-transposed copy of a conv weight for its data gradient.  Copies from the parameter arena into the
@@ -815,13 +817,13 @@ class Engine:
         _, fused_lo = self.fwd_operand(fused, M, CP, b16=hb16)
         w0h, w0l = self.weight_operand(w0p_t, hb16)
         self.fwd.append(("op", ConvOp(fused, w0h, hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
-                                      impl=self.impl, w_lo=w0l, x_lo=fused_lo)))
+                                      impl=self.impl, w_lo=w0l, x_lo=fused_lo, y_pitch=256)))
         hs_lo = []
         for i in range(1, 5):
             wh, wl = self.weight_operand(f"att_reg_box.{i}.0.weight", hb16)
             hs_lo.append(self.fwd_operand(hs[i - 1], M, 256, b16=hb16)[1])
             self.fwd.append(("op", ConvOp(hs[i - 1], wh, hs[i], rows_f256, M, 256, 256, 3, 3, bias=hb(i), out_relu=True,
-                                          impl=self.impl, w_lo=wl, x_lo=hs_lo[-1])))
+                                          impl=self.impl, w_lo=wl, x_lo=hs_lo[-1], y_pitch=256)))
         hs_lo.append(self.fwd_operand(hs[4], M, 256, b16=hb16)[1])
         w5 = st.flat("att_reg_box.5.weight")
         w5h, w5l = self.weight_operand("att_reg_box.5.weight", hb16)
@@ -850,7 +852,7 @@ class Engine:
                                     impl=self.impl, x_lo=hs_lo[4], dy_lo=dy5_lo, dy_pitch=48))
             wt5h, wt5l = self.weight_operand(wt5p_t, hb16)
             self.bwd.append(ConvOp(dy5, wt5h, dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl,
-                                   w_lo=wt5l, x_lo=dy5_lo))
+                                   w_lo=wt5l, x_lo=dy5_lo, y_pitch=256))
             for i in range(4, 0, -1):
                 wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i][0]
                 self.queue_transpose(wi, wti, 256, 3, 256)
@@ -861,7 +863,7 @@ class Engine:
                                         256, 3, 3, impl=self.impl, x_lo=hs_lo[i - 1], dy_lo=dlo, dy_pitch=256))
                 wth, wtl = self.weight_operand(wts[i], hb16)
                 self.bwd.append(ConvOp(dhs[i], wth, dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
-                                       impl=self.impl, w_lo=wtl, x_lo=dlo))
+                                       impl=self.impl, w_lo=wtl, x_lo=dlo, y_pitch=256))
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
             gb0 = st.grad_flat("att_reg_box.0.0.bias")
             self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
@@ -873,7 +875,7 @@ class Engine:
             self.bwd.append(lambda: ops.pad_channels(dw0p, g0, 256 * 9, CP, spec.FUSED_C))
             wt0h, wt0l = self.weight_operand(wt0_t, hb16)
             self.bwd.append(ConvOp(dhs[0], wt0h, dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0l,
-                                   x_lo=d0lo))
+                                   x_lo=d0lo, y_pitch=CP))
             self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
         head_bwd.label = "head"
         bwd_stages.append(head_bwd)

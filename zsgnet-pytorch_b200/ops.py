@@ -45,7 +45,7 @@ class ConvOp:
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
-                 x_lo=None, dil=1, stats=None, x_plain=False):
+                 x_lo=None, dil=1, stats=None, x_plain=False, y_pitch=0):
         self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats)
         yb = None
         if _is_bf16(y):                                      # bf16 storage: the output tensor itself is bfloat16
@@ -62,7 +62,10 @@ class ConvOp:
             x_lo = w_lo = None
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb), ptr(rb))
+                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb), ptr(rb), int(y_pitch))
+        if y_pitch and rows.is_cuda:                         # the claim is checked once, when the launch is described
+            out = rows.view(torch.int32).view(-1, 4)[:m, 3].to(torch.int64)
+            assert bool((out == torch.arange(m, device=rows.device) * y_pitch).all()), "y_pitch does not describe this row table"
         self.ref = C.byref(self.p)
         self.flops = 2.0 * m * cout * r * s * cin / (in_div * in_div)     # algorithmic (valid taps only)
         self.kernel = ("conv_bf16_kernel" if self.bf16 else "conv_tc_async_kernel" if x_lo is not None else
