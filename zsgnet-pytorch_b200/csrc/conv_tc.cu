@@ -70,6 +70,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     }
   }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -512,6 +513,26 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
     // y_pitch: the output is a plain [m, y_pitch] matrix -- no table read (on 1-2-K-block tiles the drain has nothing to
     // wait for and the ~700-cycle load was exposed once per tile)
     if (row_ok) out_off = p.y_pitch > 0 ? (m0 + row) * p.y_pitch : __ldg(&p.rows[m0 + row].out);
+    if (HAS_GENERIC && p.y_pitch > 0 && (p.residual || p.residual_bf16 || p.accumulate || p.out_mask)) {
+      // The epilogue's read operands (shortcut gradient, ReLU mask, the tensor it accumulates into) are streamed once from
+      // HBM and consumed two 16-byte loads at a time: on the short-K data gradients that was ~9 k of 11 k cycles per tile
+      // (tools/ablate_epilogue.py).  Each thread asks L2 for its row of the NEXT tile (one to four 128-byte lines) now;
+      // by the time the loads are issued they are L2 hits.
+      const int nt = tile + gridDim.x;
+      if (nt < total_tiles) {
+        const int nn0 = (nt % tiles_n) * BN + half * (BN / 2), nm = (nt / tiles_n) * TM + row;
+        if (nm < p.m && nn0 < p.cout) {
+          const int64_t e = (int64_t)nm * p.y_pitch + nn0;
+          const int cols = (p.cout - nn0 < BN / 2) ? p.cout - nn0 : BN / 2;
+          if (p.residual_bf16) prefetch_l2(p.residual_bf16 + e);
+          for (int c = 0; c < cols; c += 32) {
+            if (p.residual) prefetch_l2(p.residual + e + c);
+            if (p.out_mask) prefetch_l2(p.out_mask + e + c);
+            if (p.accumulate) prefetch_l2(p.y + e + c);
+          }
+        }
+      }
+    }
     float acc[BN / 2];
     if (dw == 0 && lane == 0) trace(gkb0, 12);
     drain_loop<BN>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
