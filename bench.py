@@ -325,7 +325,7 @@ def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=Tr
     torch.cuda.synchronize()
     loss_ms = a0.elapsed_time(a1) / reps
     loss_gbs = B * A * LOSS_BYTES_PER_ANCHOR / (loss_ms / 1e3) / 1e9
-    roof_hbm = {"kernel": "zsg_loss_grad (loss_grad_kernel + loss_finalize_kernel)", "bound": "hbm", "achieved": loss_gbs,
+    roof_hbm = {"kernel": "zsg_loss_grad (loss_grad_packed_kernel + loss_finalize_kernel)", "bound": "hbm", "achieved": loss_gbs,
                 "peak": pk["hbm"], "unit": "GB/s", "frac": loss_gbs / pk["hbm"], "traffic": None, "ms": loss_ms,
                 "match_ms": match_ms,
                 "note": f"{B * A * LOSS_BYTES_PER_ANCHOR / 1e6:.0f} MB algorithmic per call (40 B per anchor: scores + boxes read, both "

@@ -8,6 +8,7 @@
 // HBM roofline: 40 B per (sample, anchor): read att 4 + reg 16, write d_att 4 + d_reg 16
 //  + 1 B mask; the 559 KB float64 anchor table stays in L2.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace zsg {
@@ -196,6 +197,38 @@ __global__ void __launch_bounds__(256) match_rows_kernel(const float* __restrict
 // stores per thread.
 struct LossTerms { float d_att; float4 d_reg; double cls_l, box_l; };
 
+// box term of a POSITIVE anchor (a few per row of 17460): fp64 targets, smooth-L1 and its gradient.  (Measured out of
+// line: 48 instead of 76 registers, 5 instead of 3 blocks per SM -- and 21-24 us instead of 18 us per pass at B = 64.)
+__device__ __forceinline__ void box_terms(const float* __restrict__ annot, const double* __restrict__ anchors, int b, int a, int B,
+                                       float r0, float r1, float r2, float r3, double lamb_reg, int npos_b, float4* d_reg,
+                                       double* box_l) {
+  const float r[4] = {r0, r1, r2, r3};
+  const float g0 = annot[4 * b], g1 = annot[4 * b + 1], g2 = annot[4 * b + 2], g3 = annot[4 * b + 3];
+  const Box4 an = load_anchor(anchors, a);
+  // anchors.py:168-179: GT centre/size in float32, anchors in float64
+  const float gc0 = __fdiv_rn(__fadd_rn(g0, g2), 2.0f), gc1 = __fdiv_rn(__fadd_rn(g1, g3), 2.0f);
+  const float gh = __fsub_rn(g2, g0), gw = __fsub_rn(g3, g1);
+  const double ac0 = __ddiv_rn(__dadd_rn(an.y1, an.y2), 2.0), ac1 = __ddiv_rn(__dadd_rn(an.x1, an.x2), 2.0);
+  const double ah = __dadd_rn(__dsub_rn(an.y2, an.y1), 1e-8), aw = __dadd_rn(__dsub_rn(an.x2, an.x1), 1e-8);
+  double tg[4];
+  tg[0] = ((double)gc0 - ac0) / ah;
+  tg[1] = ((double)gc1 - ac1) / aw;
+  tg[2] = log((double)gh / ah);
+  tg[3] = log((double)gw / aw);
+  const double gscale = lamb_reg / ((double)B * (double)npos_b);
+  float dv[4];
+  double bl = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double d = (double)r[k] - tg[k];
+    const double ad = fabs(d);
+    bl += (ad < 1.0) ? 0.5 * d * d : ad - 0.5;                      // SmoothL1, beta = 1 (loss.py:41,91)
+    dv[k] = (float)(gscale * fmin(fmax(d, -1.0), 1.0));
+  }
+  *d_reg = make_float4(dv[0], dv[1], dv[2], dv[3]);
+  *box_l = bl;
+}
+
 __device__ __forceinline__ LossTerms loss_terms(float x, const float r[4], bool t, int b, int a, int B,
                                                 const float* __restrict__ annot, const double* __restrict__ anchors,
                                                 float alpha, float gamma, double lamb_reg, float inv_np, int npos_b) {
@@ -211,30 +244,8 @@ __device__ __forceinline__ LossTerms loss_terms(float x, const float r[4], bool 
   o.d_att = w * (p - tf) * inv_np;
   o.d_reg = make_float4(0.f, 0.f, 0.f, 0.f);
   o.box_l = 0.0;
-  if (t) {                                                          // few per row: divergence is cheap
-    const float g0 = annot[4 * b], g1 = annot[4 * b + 1], g2 = annot[4 * b + 2], g3 = annot[4 * b + 3];
-    const Box4 an = load_anchor(anchors, a);
-    // anchors.py:168-179: GT centre/size in float32, anchors in float64
-    const float gc0 = __fdiv_rn(__fadd_rn(g0, g2), 2.0f), gc1 = __fdiv_rn(__fadd_rn(g1, g3), 2.0f);
-    const float gh = __fsub_rn(g2, g0), gw = __fsub_rn(g3, g1);
-    const double ac0 = __ddiv_rn(__dadd_rn(an.y1, an.y2), 2.0), ac1 = __ddiv_rn(__dadd_rn(an.x1, an.x2), 2.0);
-    const double ah = __dadd_rn(__dsub_rn(an.y2, an.y1), 1e-8), aw = __dadd_rn(__dsub_rn(an.x2, an.x1), 1e-8);
-    double tg[4];
-    tg[0] = ((double)gc0 - ac0) / ah;
-    tg[1] = ((double)gc1 - ac1) / aw;
-    tg[2] = log((double)gh / ah);
-    tg[3] = log((double)gw / aw);
-    const double gscale = lamb_reg / ((double)B * (double)npos_b);
-    float dv[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double d = (double)r[k] - tg[k];
-      const double ad = fabs(d);
-      o.box_l += (ad < 1.0) ? 0.5 * d * d : ad - 0.5;              // SmoothL1, beta = 1 (loss.py:41,91)
-      dv[k] = (float)(gscale * fmin(fmax(d, -1.0), 1.0));
-    }
-    o.d_reg = make_float4(dv[0], dv[1], dv[2], dv[3]);
-  }
+  if (t)                                                            // few per row: divergence is cheap
+    box_terms(annot, anchors, b, a, B, r[0], r[1], r[2], r[3], lamb_reg, npos_b, &o.d_reg, &o.box_l);
   return o;
 }
 
@@ -319,6 +330,78 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(
   if (threadIdx.x == 0) tiles[(size_t)b * LOSS_MAX_TILES + blockIdx.x] = make_double2(c, bx);
 }
 
+// The product path (packed [B, A, 5] buffers, what the head writes): a block walks `tpb` consecutive tiles of 256 anchors of
+// one row and leaves ONE pair of partial sums.  Nothing in the tile loop is block-wide: a warp owns 32 anchors = 160
+// contiguous floats, moves them with 128-bit accesses through its own 640-byte slab of shared memory (__syncwarp only) and
+// has the next tile's loads in flight while it computes.  With one tile per block (above) the pass was a chain of ~10
+// block-wide phases for 256 anchors -- 4416 blocks of ~7 us lifetime at B = 64 -- and sat at a quarter of the HBM roof.
+__global__ void __launch_bounds__(256) loss_grad_packed_kernel(
+    const float* __restrict__ reg, const float* __restrict__ annot, const double* __restrict__ anchors,
+    const uint8_t* __restrict__ pos, int B, int A, int tpb, float alpha, float gamma, double lamb_reg,
+    float* __restrict__ d_reg, uint8_t* __restrict__ wsb) {
+  __shared__ __align__(16) float slab[8][160];
+  __shared__ double red[8];
+  const LossWs* ws = reinterpret_cast<const LossWs*>(wsb);
+  const int* npos_row = reinterpret_cast<const int*>(wsb + ws_npos_off(B));
+  double2* tiles = reinterpret_cast<double2*>(wsb + ws_tile_off(B));
+  const int b = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_np = 1.0f / (float)ws->npos_total;
+  const int npos_b = npos_row[b];
+  float* my = slab[w];
+  const int t0 = blockIdx.x * tpb;
+  double cls_l = 0.0, box_l = 0.0;
+  // the warp's 32 anchors of tile t: floats [0, nf) of src / dst below; nf % 4 == 0 because A % 4 == 0
+  auto first = [&](int t) { return t * 256 + w * 32; };
+  float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+  uint8_t cp = 0;
+  {
+    const int a0 = first(t0), nf = max(0, min(32, A - a0)) * 5;
+    const float* src = reg + ((size_t)b * A + a0) * 5;
+    if (lane * 4 < nf) c0 = __ldg(reinterpret_cast<const float4*>(src) + lane);
+    if (128 + lane * 4 < nf) c1 = __ldg(reinterpret_cast<const float4*>(src) + 32 + lane);
+    if (a0 + lane < A) cp = pos[(size_t)b * A + a0 + lane];
+  }
+  for (int t = t0; t < t0 + tpb; ++t) {
+    const int a0 = first(t);
+    if (a0 >= A) break;                                             // warp-uniform
+    const int nf = min(32, A - a0) * 5;
+    // next tile's loads first: they are in flight while this one is computed
+    float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
+    uint8_t np_ = 0;
+    if (t + 1 < t0 + tpb) {
+      const int a1 = first(t + 1), nf1 = max(0, min(32, A - a1)) * 5;
+      const float* src = reg + ((size_t)b * A + a1) * 5;
+      if (lane * 4 < nf1) n0 = __ldg(reinterpret_cast<const float4*>(src) + lane);
+      if (128 + lane * 4 < nf1) n1 = __ldg(reinterpret_cast<const float4*>(src) + 32 + lane);
+      if (a1 + lane < A) np_ = pos[(size_t)b * A + a1 + lane];
+    }
+    if (lane * 4 < nf) *reinterpret_cast<float4*>(my + lane * 4) = c0;
+    if (128 + lane * 4 < nf) *reinterpret_cast<float4*>(my + 128 + lane * 4) = c1;
+    __syncwarp();
+    const bool live = a0 + lane < A;
+    LossTerms o;
+    if (live) {
+      const float r[4] = {my[lane * 5], my[lane * 5 + 1], my[lane * 5 + 2], my[lane * 5 + 3]};
+      o = loss_terms(my[lane * 5 + 4], r, cp != 0, b, a0 + lane, B, annot, anchors, alpha, gamma, lamb_reg, inv_np, npos_b);
+      cls_l += o.cls_l;
+      box_l += o.box_l;
+    }
+    __syncwarp();
+    if (live) {
+      float* q = my + lane * 5;
+      q[0] = o.d_reg.x; q[1] = o.d_reg.y; q[2] = o.d_reg.z; q[3] = o.d_reg.w; q[4] = o.d_att;
+    }
+    __syncwarp();
+    float* dst = d_reg + ((size_t)b * A + a0) * 5;
+    if (lane * 4 < nf) *reinterpret_cast<float4*>(dst + lane * 4) = *reinterpret_cast<const float4*>(my + lane * 4);
+    if (128 + lane * 4 < nf) *reinterpret_cast<float4*>(dst + 128 + lane * 4) = *reinterpret_cast<const float4*>(my + 128 + lane * 4);
+    __syncwarp();
+    c0 = n0; c1 = n1; cp = np_;
+  }
+  const double c = block_sum(cls_l, red), bx = block_sum(box_l, red);
+  if (threadIdx.x == 0) tiles[(size_t)b * LOSS_MAX_TILES + blockIdx.x] = make_double2(c, bx);
+}
+
 // one block: rows in parallel (each adds its tiles in tile order), then the rows in row order (loss.py:91-143)
 __global__ void __launch_bounds__(256) loss_finalize_kernel(uint8_t* __restrict__ wsb, int B, int A, int ntiles, double lamb_reg,
                                                             double* __restrict__ losses, float* __restrict__ d_att,
@@ -330,17 +413,24 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(uint8_t* __restrict_
   const int* npos_row = reinterpret_cast<const int*>(wsb + ws_npos_off(B));
   const double2* tiles = reinterpret_cast<const double2*>(wsb + ws_tile_off(B));
   __shared__ int bad_s;
+  constexpr int SROWS = 1024;                                       // rows kept in shared memory for the serial row-order sum
+  __shared__ double s_cls[SROWS], s_box[SROWS];
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const double2* t = tiles + (size_t)b * LOSS_MAX_TILES;
     double rc = 0.0, rb = 0.0;
     for (int i = 0; i < ntiles; ++i) { rc += t[i].x; rb += t[i].y; }
+    rb = rb / (double)(float)npos_row[b];                           // loss.py:93: row sum / positives of the row (float count)
     row_cls[b] = rc;
-    row_box[b] = rb / (double)(float)npos_row[b];                   // loss.py:93: row sum / positives of the row (float count)
+    row_box[b] = rb;
+    if (b < SROWS) { s_cls[b] = rc; s_box[b] = rb; }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double box = 0.0, clsd = 0.0;
-    for (int i = 0; i < B; ++i) { box += row_box[i]; clsd += row_cls[i]; }
+    for (int i = 0; i < B; ++i) {
+      box += i < SROWS ? s_box[i] : row_box[i];
+      clsd += i < SROWS ? s_cls[i] : row_cls[i];
+    }
     box /= (double)B;
     float cls = (float)clsd / (float)ws->npos_total;                // f32 / count, like loss.py:125
     // loss.py:128-133.  The reference multiplies the per-anchor box loss of ALL anchors by the mask (loss.py:92): a zero-area
@@ -516,14 +606,20 @@ extern "C" int zsg_loss_grad(const float* att, int64_t att_stride, const float* 
   ZSG_REQUIRE(d_reg_stride != 4 || ((uintptr_t)d_reg & 15) == 0, "zsg_loss_grad: d_reg must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
-  const int ntiles = (a + 255) / 256;
+  int ntiles = (a + 255) / 256;
   dim3 grid(ntiles, b);
   const bool packed = att_stride == 5 && reg_stride == 5 && d_att_stride == 5 && d_reg_stride == 5 && att == reg + 4 &&
                       d_att == d_reg + 4 && ((((uintptr_t)reg | (uintptr_t)d_reg) & 15) == 0) && (a % 4 == 0);
-  if (packed)
-    loss_grad_kernel<true><<<grid, 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma,
-                                                 lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb);
-  else
+  if (packed) {
+    // tiles per block (measured sweep, tools/time_loss.py: 1 -> 29.9 us, 2 -> 23.8, 4 -> 18.0 at B = 64): about one wave of
+    // 8 blocks per SM
+    int tpb = (int)(((int64_t)b * ntiles + (int64_t)num_sms() * 8 - 1) / ((int64_t)num_sms() * 8));
+    tpb = tpb < 1 ? 1 : (tpb > 16 ? 16 : tpb);
+    if (const char* e = getenv("ZSG_LOSS_TPB")) tpb = atoi(e) > 0 ? atoi(e) : tpb;      // diagnostics
+    ntiles = (ntiles + tpb - 1) / tpb;                      // slots per row the finalize kernel adds up
+    loss_grad_packed_kernel<<<dim3(ntiles, b), 256, 0, st>>>(reg, annot, anchors, pos, b, a, tpb, alpha, gamma, lamb_reg, d_reg,
+                                                              wsb);
+  } else
     loss_grad_kernel<false><<<grid, 256, 0, st>>>(att, att_stride, reg, reg_stride, annot, anchors, pos, b, a, alpha, gamma,
                                                   lamb_reg, d_att, d_att_stride, d_reg, d_reg_stride, wsb);
   loss_finalize_kernel<<<1, 256, 0, st>>>(wsb, b, a, ntiles, lamb_reg, losses, d_att, d_att_stride, d_reg, d_reg_stride);
