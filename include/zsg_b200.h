@@ -99,6 +99,9 @@ typedef struct {
   int32_t y_pitch;         /* > 0: rows[i].out == i * y_pitch for every row (the output is a plain [m, y_pitch] matrix, true for  */
                            /* every forward table of the path but the [B,A,5] scatter): the epilogue then computes the offsets     */
                            /* instead of reading the table.  0: unknown (always correct)                                           */
+  const float* row_add;    /* optional pair: result[row][n] += row_add[row_add_idx[2*row] + n] + row_add[row_add_idx[2*row+1] + n]  */
+  const int32_t* row_add_idx; /* after the bias, before the ReLU (the language and grid terms of the first head conv); cout % 4  */
+                           /* == 0, offsets % 4 == 0                                                                              */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
@@ -271,6 +274,26 @@ int zsg_axpy(const float* x, float* y, float a, int64_t n, zsg_stream_t stream);
 /* x[i*stride + 0:width] *= (float)*scale, scale a DEVICE double: applies the incoming autograd gradient
  * of the scalar loss (utils.py:410-412) without a host synchronisation. */
 int zsg_scale_dev(float* x, int64_t rows, int width, int64_t stride, const double* scale, zsg_stream_t stream);
+
+/* ---- the first head conv without the concatenated tensor (mdl.py:69-104 tiles the language vector and a coordinate grid over
+ * every feature map, concatenates [feat | lang | grid] (514 channels) and convolves it; mdl.py:235-244).  Linear in its three
+ * parts: conv(W, fused) = conv(W_f, feat) + L[b, border class of the cell] + G[cell], see csrc/elementwise.cu.  The 514-channel
+ * tensor, its gradient and the K = 520 contractions over them never exist (a-6 at 0 bytes). ---- */
+/* dst[row][0:c] = src[row][0:c], row pitches src_ld / dst_ld: the channel slices W_f / W_l / W_g of the [256][9][514] weight and
+ * of its gradient. */
+int zsg_copy_cols(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int c, zsg_stream_t stream);
+/* forward terms: v [b][n*9] = lang x W_l^T (from zsg_conv_fwd), wg [n*9][2], gridpatch [total_cells][9][2] (grid value of the
+ * neighbour cell under each tap, 0 outside the level) -> lang_cls [b][16][n] (sum of v over the taps valid for a border
+ * class), grid_term [total_cells][n].  zsg_conv_params.row_add adds both per output row. */
+int zsg_head0_lang_grid_terms(const float* v, const float* wg, const float* gridpatch, float* lang_cls, float* grid_term,
+                              int b, int total_cells, int n, zsg_stream_t stream);
+/* backward sums over dh [sum_l b*cells_l][n] (row of (sample, cell) = cell_base[cell] + sample * cell_stride[cell]):
+ * tap_sums [b][n*9] = sum over the cells where the tap is valid (-> d lang and dW_l by two small GEMMs), and
+ * dwg[(n*9+t) * dwg_ld + g] = dW_g (written into the [.., 514] gradient at column 512).  scratch: b * 8 * 34 * n floats.
+ * Partial sums are added in a fixed order: deterministic. */
+int zsg_head0_backward_sums(const float* dh, const int32_t* cell_base, const int32_t* cell_stride, const int32_t* cell_cls,
+                            const float* gridpatch, int b, int total_cells, int n, float* scratch, size_t scratch_floats,
+                            float* tap_sums, float* dwg, int64_t dwg_ld, zsg_stream_t stream);
 
 /* -------------------- language/grid tiling fusion (mdl.py:69-104) ------------------------
  * fused[b][cell][0:256]=feat, [256:512]=lang[b], [512]=grid_y, [513]=grid_x, [514:cpad]=0, for the six

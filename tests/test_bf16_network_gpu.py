@@ -60,7 +60,7 @@ def test_bf16_engine_uses_bf16_kernels(bf16_stack):
     from zsg_b200 import ops
     eng = net.engine_for(2, 20)
     kinds = [it[1].kernel for it in eng.fwd if it[0] == "op"]
-    assert kinds.count("conv_bf16_kernel") == 67 and kinds.count("conv_tc_async_kernel") == 1     # fp32: LSTM projection only
+    assert kinds.count("conv_bf16_kernel") == 68 and kinds.count("conv_tc_async_kernel") == 1     # fp32: LSTM projection only
     assert sum(1 for o in eng.bwd if isinstance(o, ops.WgradOp) and o.kernel == "wgrad_bf16_kernel") == 67
 
 

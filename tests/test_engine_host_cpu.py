@@ -40,13 +40,16 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     out = eng.forward(training=True)
     assert out.shape == (B, spec.NUM_ANCHORS, 5)
     fwd = collections.Counter(calls)
-    # 53 trunk convs + 8 FPN + 6 head + 1 LSTM projection
-    assert fwd["zsg_conv_fwd"] == 53 + 8 + 6 + 1
+    # 53 trunk convs + 8 FPN + 6 head + 1 LSTM projection + the language GEMM of the split first head conv (lang x W_l)
+    assert fwd["zsg_conv_fwd"] == 53 + 8 + 6 + 1 + 1
     # BatchNorm statistics come out of the conv epilogues (per-row-group partials), not from a pass over the activations
     assert fwd["zsg_bn_stats"] == 0 and fwd["zsg_bn_finalize_partials"] == 53
     assert fwd["zsg_bn_finalize"] == 0 and fwd["zsg_bn_apply"] == 16
-    assert fwd["zsg_split_tf32"] == 2 and fwd["zsg_pad_channels"] == 2
-    assert fwd["zsg_lstm_fwd_dir"] == 1 and fwd["zsg_lstm_rev_step"] == 1 and fwd["zsg_fuse_lang_grid"] == 1
+    # a-6: the [feat | lang | grid] tensor is never built: three channel slices of the 514-channel weight, border-class sums
+    # of lang x W_l and the grid term, added per row in the conv epilogue (zsg_conv_params.row_add)
+    assert fwd["zsg_split_tf32"] == 2 and fwd["zsg_pad_channels"] == 1 and fwd["zsg_copy_cols"] == 3
+    assert fwd["zsg_fuse_lang_grid"] == 0 and fwd["zsg_head0_lang_grid_terms"] == 1
+    assert fwd["zsg_lstm_fwd_dir"] == 1 and fwd["zsg_lstm_rev_step"] == 1
     del calls[:]
     eng.forward(training=False)
     ev = collections.Counter(calls)
@@ -56,14 +59,15 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5), on_bucket=lambda lo, hi: seen.append((lo, hi)))
     bwd = collections.Counter(calls)
     # every conv has a wgrad (+5 LSTM weight gradients... 4 LSTM matrices), every conv but the stem a dgrad
-    assert bwd["zsg_conv_wgrad"] == 53 + 8 + 6 + 4
+    assert bwd["zsg_conv_wgrad"] == 53 + 8 + 6 + 4 + 1                 # + dW_l of the split first head conv
+    assert bwd["zsg_unfuse_lang_grid"] == 0 and bwd["zsg_head0_backward_sums"] == 1 and bwd["zsg_copy_cols"] == 2
     # data gradients run through the forward kernel; the five 3x3 / stride-2 convs (layer2-4.0.conv2, P6, P7_2) take
     # one launch per input-pixel parity class (4) instead of one zero-stuffed launch
-    assert bwd["zsg_conv_fwd"] == 52 + 8 + 6 + 5 * 3
+    assert bwd["zsg_conv_fwd"] == 52 + 8 + 6 + 5 * 3 + 1               # + d lang = tap sums x W_l
     assert bwd["zsg_bn_bwd_reduce"] == 53 and bwd["zsg_bn_bwd_apply"] == 53
-    # 64 of the 66 transposed-flipped weight copies (all that go arena -> pool) are one batched launch; the two padded
-    # head weights (first and last head conv) keep their own
-    assert bwd["zsg_weight_transpose_flip_batched"] == 1 and bwd["zsg_weight_transpose_flip"] == 2
+    # 64 of the transposed-flipped weight copies (all that go arena -> pool) are one batched launch; the padded last head
+    # weight and the two slices of the first one (W_f for d feat, W_l for d lang) keep their own
+    assert bwd["zsg_weight_transpose_flip_batched"] == 1 and bwd["zsg_weight_transpose_flip"] == 3
     assert len(eng._wtf) == 52 + 8 + 4 and bwd["zsg_split_tf32"] == 1
     # buckets: contiguous, ordered, covering the used arena exactly once
     assert seen[0][0] == 0 and seen[-1][1] == store.used
@@ -88,10 +92,10 @@ def test_bf16_engine_program_on_host(recorded):
     eng = engine.Engine(store, bufs, B, T, torch.device("cpu"), dtype="bf16")
     f32 = engine.Engine(store, bufs, B, T, torch.device("cpu"))
     kinds = collections.Counter(it[1].kernel for it in eng.fwd if it[0] == "op")
-    assert kinds == {"conv_bf16_kernel": 53 + 8 + 6, "conv_tc_async_kernel": 1}      # the LSTM projection stays fp32
+    assert kinds == {"conv_bf16_kernel": 53 + 8 + 6 + 1, "conv_tc_async_kernel": 1}  # + lang x W_l; the LSTM projection stays fp32
     bk = collections.Counter(op.kernel for op in eng.bwd if isinstance(op, (ops.ConvOp, ops.WgradOp)))
-    assert bk["wgrad_bf16_kernel"] == 53 + 8 + 6 and bk["wgrad_tc_async_kernel"] == 0 and bk["wgrad_tc_kernel"] == 4
-    assert bk["conv_bf16_kernel"] == 52 + 8 + 6 + 5 * 3 and "conv_tc_async_kernel" not in bk
+    assert bk["wgrad_bf16_kernel"] == 53 + 8 + 6 and bk["wgrad_tc_async_kernel"] == 0 and bk["wgrad_tc_kernel"] == 4 + 1   # + dW_l
+    assert bk["conv_bf16_kernel"] == 52 + 8 + 6 + 5 * 3 + 1 and "conv_tc_async_kernel" not in bk                          # + d lang
     # no materialised BN-ReLU tensors and half-size images: the activation-side buffers shrink (at B = 2 the weight
     # images dominate both engines, so compare without them)
     wimg = lambda e: 4 * (2 * store.total + 3 * e.pool_n) + (2 * (store.total + e.pool_n) if e.bf16 else 0)
@@ -103,9 +107,9 @@ def test_bf16_engine_program_on_host(recorded):
     fwd = collections.Counter(calls)
     # bf16 storage of the trunk: conv outputs / block outputs are bfloat16 tensors (their own operand images): the 32
     # BatchNorm+ReLU-on-load passes are bfloat16 -> bfloat16, the stem pool output needs no cast at all; fp32 tensors that
-    # feed a GEMM (2 weight arenas, 4 FPN inner maps incl. relu(P6), 6 head inputs) are still cast
+    # feed a GEMM (2 weight arenas, 4 FPN inner maps incl. relu(P6), 7 head inputs: feat, lang, 5 hidden maps) are still cast
     assert eng.b16act and eng.dbg["c5"].dtype == torch.bfloat16 and eng.dbg["blocks"][0]["r1"].dtype == torch.bfloat16
-    assert fwd["zsg_act_b16"] == 32 and fwd["zsg_cast_bf16"] == 2 + 4 + 6 and fwd["zsg_split_act"] == 1
+    assert fwd["zsg_act_b16"] == 32 and fwd["zsg_cast_bf16"] == 2 + 4 + 7 and fwd["zsg_split_act"] == 1
     assert fwd["zsg_bn_apply_b16"] == 16 and fwd["zsg_bn_apply_bf16"] == 0 and fwd["zsg_maxpool_bn_relu_fwd_b16"] == 1
     del calls[:]
     eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5))
@@ -128,16 +132,16 @@ def test_ssd_vgg_program_builds_and_runs_on_host(recorded):
     out = eng.forward(training=True)
     assert out.shape == (B, spec.NUM_ANCHORS, 5)
     fwd = collections.Counter(calls)
-    # 15 VGG convs + 8 extras + 3 fproj + 6 head + 1 LSTM projection
-    assert fwd["zsg_conv_fwd"] == 15 + 8 + 3 + 6 + 1
+    # 15 VGG convs + 8 extras + 3 fproj + 6 head + 1 LSTM projection + lang x W_l of the split first head conv
+    assert fwd["zsg_conv_fwd"] == 15 + 8 + 3 + 6 + 1 + 1
     assert fwd["zsg_maxpool_fwd"] == 5 and fwd["zsg_l2norm_fwd"] == 1 and fwd["zsg_bn_stats"] == 0
     del calls[:]
     seen = []
     eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5), on_bucket=lambda lo, hi: seen.append((lo, hi)))
     bwd = collections.Counter(calls)
-    assert bwd["zsg_conv_wgrad"] == 15 + 8 + 3 + 6 + 4
+    assert bwd["zsg_conv_wgrad"] == 15 + 8 + 3 + 6 + 4 + 1
     # every conv but vgg.0 has a data gradient; extras.1 / extras.3 (3x3, stride 2) take 4 parity-class launches each
-    assert bwd["zsg_conv_fwd"] == 14 + 8 + 3 + 6 + 2 * 3
+    assert bwd["zsg_conv_fwd"] == 14 + 8 + 3 + 6 + 2 * 3 + 1
     assert bwd["zsg_maxpool_bwd"] == 5 and bwd["zsg_l2norm_bwd"] == 1 and bwd["zsg_relu_bwd"] == 3
     assert seen[0][0] == 0 and seen[-1][1] == store.used
     for (a, b), (c, d) in zip(seen, seen[1:]):

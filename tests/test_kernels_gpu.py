@@ -1059,3 +1059,75 @@ def test_conv_plain_matrix_tma_equals_gather_path(zsg, case, bf16, epi):
     if epi != "full":
         ref = (x.to(torch.bfloat16).float() @ w.to(torch.bfloat16).float().t()) if bf16 else x @ w.t()
         assert rel_err(ys[1], ref) < (2e-5 if not bf16 else 1e-5)
+
+
+def test_split_first_head_conv_equals_the_materialised_convolution(zsg):
+    """a-6: conv(W, [feat | lang tiled | grid]) (mdl.py:69-104, 235-244) = conv(W_f, feat) + L[b, border class] + G[cell].
+    Forward through zsg_conv_fwd with row_add against F.conv2d over the concatenated tensor, level by level; backward sums
+    (per-tap column sums, dW_g) against autograd of the same."""
+    ops, geo = zsg
+    from zsg_b200 import spec
+    from zsg_b200.anchors import cell_grid
+    B, N, FC = 3, 256, 514
+    sizes = spec.LEVEL_SIZES
+    g = torch.Generator().manual_seed(11)
+    feats = [torch.randn(B, 256, s, s, generator=g) for s in sizes]
+    lang = torch.randn(B, 256, generator=g)
+    W = (torch.randn(N, FC, 3, 3, generator=g) / (FC * 9) ** 0.5).requires_grad_(True)
+    bias = torch.randn(N, generator=g)
+    grids = [cell_grid(s, s) for s in sizes]                                   # [s, s, 2]
+    outs = []
+    for f, gr in zip(feats, grids):
+        s = f.shape[-1]
+        fused = torch.cat([f, lang.view(B, 256, 1, 1).expand(B, 256, s, s), gr.permute(2, 0, 1).unsqueeze(0).expand(B, 2, s, s)], 1)
+        outs.append(F.relu(F.conv2d(fused, W, bias, padding=1)))
+    G_ = [torch.randn(o.shape, generator=g) for o in outs]
+    lang_r = lang.clone().requires_grad_(True)
+    outs_r = []
+    for f, gr in zip(feats, grids):
+        s = f.shape[-1]
+        fused = torch.cat([f, lang_r.view(B, 256, 1, 1).expand(B, 256, s, s), gr.permute(2, 0, 1).unsqueeze(0).expand(B, 2, s, s)], 1)
+        outs_r.append(F.conv2d(fused, W, bias, padding=1))
+    sum((o * gg).sum() for o, gg in zip(outs_r, G_)).backward()
+
+    # ---- device side: level-major rows
+    tot = spec.TOTAL_CELLS
+    lvl_off = np.concatenate([[0], np.cumsum([B * s * s for s in sizes])]).tolist()
+    M = B * tot
+    rows_level_major = lambda ts: torch.cat([nhwc(t).reshape(-1, t.shape[1]) for t in ts]).cuda().contiguous()
+    feat = rows_level_major(feats)
+    grid = torch.cat([gr.reshape(-1, 2) for gr in grids])
+    tabs = geo.head0_tables(B, sizes, grid)
+    Wk = W.detach().permute(0, 2, 3, 1).contiguous().cuda().view(-1)           # [n][t][514]
+    wf, wl, wg = torch.empty(N * 9 * 256, device="cuda"), torch.empty(2304 * 256, device="cuda"), torch.empty(2304 * 2, device="cuda")
+    ops.copy_cols(Wk, FC, wf, 256, 2304, 256)
+    ops.copy_cols(Wk[256:], FC, wl, 256, 2304, 256)
+    ops.copy_cols(Wk[512:], FC, wg, 2, 2304, 2)
+    V = (lang.cuda() @ wl.view(2304, 256).t()).contiguous()                    # the GEMM itself is tested elsewhere
+    radd = torch.empty(B * 16 * N + tot * N, device="cuda")
+    ops.head0_lang_grid_terms(V, wg, tabs["gridpatch"].cuda(), radd[:B * 16 * N], radd[B * 16 * N:], B, tot, N)
+    tabs_f = []
+    for li, s in enumerate(sizes):
+        tabs_f.append(geo.conv_rows(B, s, s, 256, s, s, N, 1, 1, in_off=lvl_off[li] * 256, out_off=lvl_off[li] * N))
+    rows = torch.cat(tabs_f).contiguous().cuda()
+    hi, lo, flo = torch.empty_like(wf), torch.empty_like(wf), torch.empty_like(feat)
+    ops.split_tf32(wf, hi, lo, wf.numel())
+    ops.split_act(feat, flo, M, 256)
+    y = torch.empty(M, N, device="cuda")
+    ops.ConvOp(feat, hi, y, rows, M, 256, N, 3, 3, bias=bias.cuda(), out_relu=True, w_lo=lo, x_lo=flo, y_pitch=N, row_add=radd,
+               row_add_idx=tabs["row_add_idx"].cuda())()
+    torch.cuda.synchronize()
+    assert rel_err(y, rows_level_major(outs)) < 2e-5
+    # ---- backward sums
+    dh = rows_level_major(G_)
+    scr = torch.empty(B * 8 * 34 * N, device="cuda")
+    St = torch.empty(B, 2304, device="cuda")
+    g0 = torch.full((2304 * FC,), 7.0, device="cuda")
+    ops.head0_backward_sums(dh, tabs["cell_base"].cuda(), tabs["cell_stride"].cuda(), tabs["cell_cls"].cuda(),
+                            tabs["gridpatch"].cuda(), B, tot, N, scr, St, g0[512:], FC)
+    torch.cuda.synchronize()
+    gW = W.grad.permute(0, 2, 3, 1).reshape(2304, FC)                          # [(n,t)][514]
+    assert rel_err(g0.view(2304, FC)[:, 512:], gW[:, 512:]) < 2e-5
+    assert bool((g0.view(2304, FC)[:, :512] == 7.0).all())                      # only the two grid columns are written
+    assert rel_err(St.t() @ lang.cuda(), gW[:, 256:512]) < 2e-5                # dW_l = St^T x lang
+    assert rel_err(St @ wl.view(2304, 256), lang_r.grad) < 2e-5                # d lang = St x W_l

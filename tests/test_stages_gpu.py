@@ -208,8 +208,8 @@ def test_fusion_head_stage(st):
     sd = st.sdg(keys)
     feats = [f.clone().requires_grad_(True) for f in st.inter["feats"]]
     lang = st.inter["lang"].clone().requires_grad_(True)
-    for i, f in enumerate(feats):
-        st.put(eng.dbg["fl"][i], f)
+    for i, f in reversed(list(enumerate(feats))):          # level 0 last: its put() regenerates the operand image of the whole
+        st.put(eng.dbg["fl"][i], f)                        # level-major matrix the split first head conv reads
     eng.lang.copy_(lang.detach().cuda())
     st.fwd("head")
     lvl_off, sizes = eng.dbg["lvl_off"], st.synth.LEVEL_SIZES

@@ -26,7 +26,8 @@ class ConvParams(C.Structure):
                 ("in_div", C.c_int32), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
                 ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32), ("stats", C.c_void_p),
-                ("x_bf16", C.c_void_p), ("w_bf16", C.c_void_p), ("x_plain", C.c_int32), ("y_bf16", C.c_void_p), ("residual_bf16", C.c_void_p), ("y_pitch", C.c_int32)]
+                ("x_bf16", C.c_void_p), ("w_bf16", C.c_void_p), ("x_plain", C.c_int32), ("y_bf16", C.c_void_p), ("residual_bf16", C.c_void_p), ("y_pitch", C.c_int32), ("row_add", C.c_void_p),
+                ("row_add_idx", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
@@ -85,6 +86,9 @@ SIGNATURES = {
     "zsg_relu_bwd": [_P, _P, _P, _L, _I, _P],
     "zsg_axpy": [_P, _P, _F, _L, _P],
     "zsg_scale_dev": [_P, _L, _I, _L, _P, _P],
+    "zsg_copy_cols": [_P, _L, _P, _L, _L, _I, _P],
+    "zsg_head0_lang_grid_terms": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "zsg_head0_backward_sums": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P, _P, _L, _P],
     "zsg_fuse_lang_grid": [_P, _P, _P, _P, _I, _I, C.POINTER(C.c_int32), _I, _I, _I, _I, _P],
     "zsg_unfuse_lang_grid": [_P, _P, _P, _I, _I, C.POINTER(C.c_int32), _I, _I, _I, _I, _P],
     "zsg_lstm_fwd_dir": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
@@ -134,7 +138,8 @@ def stream():
 
 
 # kernels launched per C-ABI call (memsets not counted); used for bench.py's gpu_launches claim
-KERNELS_PER_CALL = {"zsg_match_loss": 3, "zsg_loss_grad": 2, "zsg_unfuse_lang_grid": 2, "zsg_resize_rgb8": 2}
+KERNELS_PER_CALL = {"zsg_match_loss": 3, "zsg_loss_grad": 2, "zsg_unfuse_lang_grid": 2, "zsg_resize_rgb8": 2,
+                    "zsg_head0_lang_grid_terms": 2, "zsg_head0_backward_sums": 2}
 LAUNCH_COUNT = [0]
 
 

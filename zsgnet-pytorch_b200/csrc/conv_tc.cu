@@ -489,7 +489,8 @@ __device__ __noinline__ void epilogue_store_ragged(float* y, const float* out_ma
 enum { EPI_PLAIN = 0, EPI_B16 = 1, EPI_GENERIC = 2, EPI_ANY = 3 };
 
 __host__ __device__ inline bool epilogue_is_plain(const zsg_conv_params& p) {
-  return !p.bias && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && !p.out_relu && (p.cout & 3) == 0;
+  return !p.bias && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && !p.out_relu && !p.row_add &&
+         (p.cout & 3) == 0;
 }
 
 template <int BN, bool BF16 = false, int EPI = EPI_ANY>
@@ -532,6 +533,12 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
           }
         }
       }
+    }
+    int ra0 = 0, ra1 = 0;                                  // row_add: offsets of this row's two addend rows
+    if (HAS_GENERIC && p.row_add && row_ok) {
+      const int2 ra = __ldg(reinterpret_cast<const int2*>(p.row_add_idx) + m0 + row);
+      ra0 = ra.x;
+      ra1 = ra.y;
     }
     float acc[BN / 2];
     if (dw == 0 && lane == 0) trace(gkb0, 12);
@@ -680,6 +687,20 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         if (vec) {
           const int64_t a0 = (int64_t)o0 + n, a1 = (int64_t)o1 + n;
           float4 q0, q1;
+          if (p.row_add) {                                  // language + grid terms of the first head conv (L2-resident tables)
+            const int i00 = __shfl_sync(0xffffffffu, ra0, r0), i01 = __shfl_sync(0xffffffffu, ra1, r0);
+            const int i10 = __shfl_sync(0xffffffffu, ra0, r1), i11 = __shfl_sync(0xffffffffu, ra1, r1);
+            if (k0) {
+              q0 = __ldg(reinterpret_cast<const float4*>(p.row_add + i00 + n));
+              q1 = __ldg(reinterpret_cast<const float4*>(p.row_add + i01 + n));
+              v0.x += q0.x + q1.x; v0.y += q0.y + q1.y; v0.z += q0.z + q1.z; v0.w += q0.w + q1.w;
+            }
+            if (k1) {
+              q0 = __ldg(reinterpret_cast<const float4*>(p.row_add + i10 + n));
+              q1 = __ldg(reinterpret_cast<const float4*>(p.row_add + i11 + n));
+              v1.x += q0.x + q1.x; v1.y += q0.y + q1.y; v1.z += q0.z + q1.z; v1.w += q0.w + q1.w;
+            }
+          }
           if (p.out_mask) {
             if (k0) q0 = __ldg(reinterpret_cast<const float4*>(p.out_mask + a0));
             if (k1) q1 = __ldg(reinterpret_cast<const float4*>(p.out_mask + a1));
@@ -716,7 +737,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
             if (k1) *reinterpret_cast<float4*>(p.y + a1) = v1;
           }
         } else {
-          if (EPI == EPI_GENERIC && p.residual_bf16) __trap();   // checked on the host: cout % 4 == 0; only unaligned row offsets get here
+          if (p.row_add || (EPI == EPI_GENERIC && p.residual_bf16)) __trap();   // checked on the host: cout % 4 == 0; only unaligned row offsets get here
           if (k0) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o0, n, v0);
           if (k1) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o1, n, v1);
         }
@@ -2023,6 +2044,10 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(!p.in_scale || p.in_shift, "zsg_conv_fwd: in_scale without in_shift");
   ZSG_REQUIRE(!p.x_plain || (p.r == 1 && p.s == 1 && p.in_div == 1), "zsg_conv_fwd: x_plain needs r = s = 1 and in_div = 1");
   ZSG_REQUIRE(p.y_pitch == 0 || p.y_pitch >= p.cout, "zsg_conv_fwd: y_pitch=%d must be 0 or >= cout", p.y_pitch);
+  ZSG_REQUIRE(!p.row_add == !p.row_add_idx, "zsg_conv_fwd: row_add and row_add_idx go together");
+  ZSG_REQUIRE(!p.row_add || (p.cout % 4 == 0 && (p.x_lo || p.x_bf16) && p.impl != 1 && !p.y_bf16 && !p.stats &&
+                             (((uintptr_t)p.row_add & 15) | ((uintptr_t)p.row_add_idx & 7)) == 0),
+              "zsg_conv_fwd: row_add needs cout %% 4 == 0, an operand-image input, the tcgen05 path and aligned tables");
   ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && p.impl != 1),
               "zsg_conv_fwd: stats needs a plain output (no bias / ReLU / mask / residual / accumulate) on the tcgen05 path");
   cudaStream_t st = as_stream(stream);

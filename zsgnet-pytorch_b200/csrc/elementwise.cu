@@ -1023,6 +1023,143 @@ __global__ void __launch_bounds__(256) unfuse_lang_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// First head conv WITHOUT the concatenated tensor (mdl.py:69-104 builds [feat | lang tiled | grid] and convolves it).
+// conv(W, [feat|lang|grid]) = conv(W_f, feat) + L[b, class(cell)] + G[cell]:
+//   V[b, (n,t)]   = sum_c W_l[n,t,c] * lang[b,c]                       a [B,256] x [256,2304] GEMM (zsg_conv_fwd)
+//   L[b, cls, n]  = sum over the taps t that fall inside the level at a cell of border class cls of V[b,(n,t)]
+//   G[cell, n]    = sum_t sum_g W_g[n,t,g] * gridpatch[cell, t, g]     batch independent
+// and the conv over feat adds L + G per output row in its epilogue (zsg_conv_params.row_add).  Border class of a cell
+// (y, x) of an S x S level: ry = (y == 0) | (y == S-1) << 1, rx likewise, cls = ry * 4 + rx; tap (r, s) is valid iff
+// !(r == 0 && ry & 1) && !(r == 2 && ry & 2) and the same in x.  gridpatch[cell][t][g] = grid value g of the neighbour
+// cell under tap t, 0 outside the level (host-built table, like the row tables).
+// Backward: S_t[b,(n,t)] = sum over the cells where t is valid of dh0[b,cell,n] gives d lang = S_t x W_l (GEMM) and
+// dW_l = S_t^T x lang (weight-gradient GEMM); dW_g[n,t,g] = sum_{b,cell} dh0[b,cell,n] * gridpatch[cell,t,g].
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tap_valid(int cls, int t) {
+  const int r = t / 3, q = t % 3, ry = cls >> 2, rx = cls & 3;
+  return !(r == 0 && (ry & 1)) && !(r == 2 && (ry & 2)) && !(q == 0 && (rx & 1)) && !(q == 2 && (rx & 2));
+}
+
+// dst[row][0:c] = src[row][0:c] with separate row pitches (channel slices of [.., 514] weights and their gradients)
+__global__ void __launch_bounds__(256) copy_cols_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ dst,
+                                                        int64_t dst_ld, int64_t rows, int c) {
+  const int64_t n = rows * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c;
+    const int k = (int)(i % c);
+    dst[r * dst_ld + k] = src[r * src_ld + k];
+  }
+}
+
+// L[b][cls][n] from V[b][n * 9 + t]; grid (B, 16), 256 threads = n
+__global__ void __launch_bounds__(256) lang_class_kernel(const float* __restrict__ V, float* __restrict__ L, int N) {
+  const int b = blockIdx.x, cls = blockIdx.y;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* v = V + ((size_t)b * N + n) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      if (tap_valid(cls, t)) acc += v[t];
+    L[((size_t)b * 16 + cls) * N + n] = acc;
+  }
+}
+
+// G[cell][n] = sum_{t,g} Wg[(n * 9 + t) * 2 + g] * gp[cell][t * 2 + g]; one block per cell
+__global__ void __launch_bounds__(256) grid_term_kernel(const float* __restrict__ Wg, const float* __restrict__ gp,
+                                                        float* __restrict__ G, int N) {
+  const int cell = blockIdx.x;
+  float p[18];
+#pragma unroll
+  for (int k = 0; k < 18; ++k) p[k] = gp[(size_t)cell * 18 + k];
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* w = Wg + (size_t)n * 18;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 18; ++k) acc = fmaf(w[k], p[k], acc);
+    G[(size_t)cell * N + n] = acc;
+  }
+}
+
+// Backward reduce over the rows of dh0 (level-major [sum_l B * cells_l, N], N = 256 = blockDim.x): block (b, chunk) walks
+// the cells chunk, chunk + nch, ... of sample b; per border class the column sums (shared memory, a thread only ever
+// touches its own column) and per (tap, grid channel) the sums weighted with the grid patch (registers).
+//   Sp[b][chunk][16][N], Wp[b][chunk][N][18]   partial sums, added up in fixed order by head0_finish_kernel
+__global__ void __launch_bounds__(256) head0_reduce_kernel(const float* __restrict__ dh, const int32_t* __restrict__ cell_base,
+                                                           const int32_t* __restrict__ cell_stride,
+                                                           const int32_t* __restrict__ cell_cls, const float* __restrict__ gp,
+                                                           int total_cells, int N, float* __restrict__ Sp,
+                                                           float* __restrict__ Wp) {
+  __shared__ float s[16][256];
+  const int b = blockIdx.x, ch = blockIdx.y, nch = gridDim.y, n = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s[k][n] = 0.f;
+  float wg[18];
+#pragma unroll
+  for (int k = 0; k < 18; ++k) wg[k] = 0.f;
+  constexpr int U = 4;
+  for (int c0 = ch; c0 < total_cells; c0 += nch * U) {
+    float v[U];
+    int cl[U], ce[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ce[u] = c0 + u * nch;
+      v[u] = 0.f;
+      cl[u] = 0;
+      if (ce[u] < total_cells) {
+        cl[u] = cell_cls[ce[u]];
+        v[u] = dh[((size_t)cell_base[ce[u]] + (size_t)b * cell_stride[ce[u]]) * N + n];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ce[u] >= total_cells) break;
+      s[cl[u]][n] += v[u];
+      const float* g = gp + (size_t)ce[u] * 18;
+#pragma unroll
+      for (int k = 0; k < 18; ++k) wg[k] = fmaf(v[u], g[k], wg[k]);
+    }
+  }
+  float* sp = Sp + ((size_t)b * nch + ch) * 16 * N;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) sp[(size_t)k * N + n] = s[k][n];
+  float* wp = Wp + (((size_t)b * nch + ch) * N + n) * 18;
+#pragma unroll
+  for (int k = 0; k < 18; ++k) wp[k] = wg[k];
+}
+
+// St[b][n * 9 + t] = sum_chunk sum_{cls: t valid} Sp ; dWg (row pitch ld, starting at column 0 of dwg) = sum_b sum_chunk Wp
+__global__ void __launch_bounds__(256) head0_finish_kernel(const float* __restrict__ Sp, const float* __restrict__ Wp, int B,
+                                                           int nch, int N, float* __restrict__ St, float* __restrict__ dwg,
+                                                           int64_t dwg_ld) {
+  const int n = threadIdx.x;
+  if ((int)blockIdx.x < B) {
+    const int b = blockIdx.x;
+    float cls_sum[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a = 0.f;
+      for (int c = 0; c < nch; ++c) a += Sp[(((size_t)b * nch + c) * 16 + k) * N + n];
+      cls_sum[k] = a;
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (tap_valid(k, t)) a += cls_sum[k];
+      St[((size_t)b * N + n) * 9 + t] = a;
+    }
+  } else {
+    // blocks B .. B + 17: one (tap, grid channel) each
+    const int k = blockIdx.x - B;
+    float a = 0.f;
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < nch; ++c) a += Wp[(((size_t)b * nch + c) * N + n) * 18 + k];
+    dwg[((size_t)n * 9 + k / 2) * dwg_ld + (k & 1)] = a;
+  }
+}
+
 // ------------------------------------ layout helpers -----------------------------------------
 __global__ void __launch_bounds__(256) weight_transpose_flip_kernel(const float* __restrict__ w, float* __restrict__ wt,
                                                                     int Cout, int R, int S, int Cin) {
@@ -1546,6 +1683,40 @@ extern "C" int zsg_unfuse_lang_grid(const float* dfused, float* dfeat, float* dl
   unfuse_lang_kernel<<<dim3(b, nlvl, (max_cells + UNFUSE_CHUNK - 1) / UNFUSE_CHUNK), 256, 0, st>>>(dfused, dlang, b, lv, cfeat,
                                                                                                   clang, cpad);
   return check_launch("zsg_unfuse_lang_grid");
+}
+
+extern "C" int zsg_copy_cols(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int c,
+                             zsg_stream_t stream) {
+  ZSG_REQUIRE(src && dst && rows > 0 && c > 0 && src_ld >= c && dst_ld >= c, "zsg_copy_cols: bad arguments");
+  copy_cols_kernel<<<grid_for(rows * c, 256), 256, 0, as_stream(stream)>>>(src, src_ld, dst, dst_ld, rows, c);
+  return check_launch("zsg_copy_cols");
+}
+
+extern "C" int zsg_head0_lang_grid_terms(const float* v, const float* wg, const float* gridpatch, float* lang_cls,
+                                         float* grid_term, int b, int total_cells, int n, zsg_stream_t stream) {
+  ZSG_REQUIRE(v && wg && gridpatch && lang_cls && grid_term && b > 0 && total_cells > 0 && n > 0,
+              "zsg_head0_lang_grid_terms: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  lang_class_kernel<<<dim3(b, 16), 256, 0, st>>>(v, lang_cls, n);
+  grid_term_kernel<<<total_cells, 256, 0, st>>>(wg, gridpatch, grid_term, n);
+  return check_launch("zsg_head0_lang_grid_terms");
+}
+
+extern "C" int zsg_head0_backward_sums(const float* dh, const int32_t* cell_base, const int32_t* cell_stride,
+                                       const int32_t* cell_cls, const float* gridpatch, int b, int total_cells, int n,
+                                       float* scratch, size_t scratch_floats, float* tap_sums, float* dwg, int64_t dwg_ld,
+                                       zsg_stream_t stream) {
+  ZSG_REQUIRE(dh && cell_base && cell_stride && cell_cls && gridpatch && scratch && tap_sums && dwg,
+              "zsg_head0_backward_sums: null pointer");
+  ZSG_REQUIRE(n == 256, "zsg_head0_backward_sums: n=%d (the head width of the path is 256)", n);
+  const int nch = 8;
+  ZSG_REQUIRE(scratch_floats >= (size_t)b * nch * (16 + 18) * n, "zsg_head0_backward_sums: scratch too small");
+  float* Sp = scratch;
+  float* Wp = scratch + (size_t)b * nch * 16 * n;
+  cudaStream_t st = as_stream(stream);
+  head0_reduce_kernel<<<dim3(b, nch), 256, 0, st>>>(dh, cell_base, cell_stride, cell_cls, gridpatch, total_cells, n, Sp, Wp);
+  head0_finish_kernel<<<b + 18, 256, 0, st>>>(Sp, Wp, b, nch, n, tap_sums, dwg, dwg_ld);
+  return check_launch("zsg_head0_backward_sums");
 }
 
 extern "C" int zsg_weight_transpose_flip(const float* w, float* wt, int cout, int rs_r, int rs_s, int cin,

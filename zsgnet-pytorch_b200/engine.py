@@ -102,6 +102,9 @@ class Engine:
         # blocks and all accumulation stay fp32.  (torch.autocast(bfloat16) stores the same tensors in bfloat16.)
         self.b16act = (self.bf16 and self.model == "retina" and impl == ops.IMPL_TC
                        and os.environ.get("ZSG_B16_ACT", "1") != "0")
+        # The first head conv without the concatenated [feat | lang | grid] tensor (a-6 at 0 bytes): a K = 2304 GEMM over feat
+        # whose epilogue adds per-row language / grid terms; ZSG_SPLIT_HEAD0=0 keeps the materialised K = 520 x 9 formulation
+        self.split_head0 = impl == ops.IMPL_TC and os.environ.get("ZSG_SPLIT_HEAD0", "1") != "0"
         self._rows_cache = {}
         self._operand_cache, self._bwd_lo = {}, {}
         self._side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
@@ -117,7 +120,7 @@ class Engine:
         # one launch per forward; transformed weights (padded / transposed-flipped) live in one pool that is split
         # by one launch per forward (region F) and one per backward (region B)
         self.arena_hi, self.arena_lo = self.buf(store.total), self.buf(store.total)
-        self.pool_n = 44 << 20
+        self.pool_n = 48 << 20
         self.pool, self.pool_hi, self.pool_lo = self.buf(self.pool_n), self.buf(self.pool_n), self.buf(self.pool_n)
         self.arena_b16 = self.img(store.total) if self.bf16 else None      # bf16 images of the same weights
         self.pool_b16 = self.img(self.pool_n) if self.bf16 else None
@@ -418,6 +421,8 @@ class Engine:
     def _alloc_head_w0p(self):
         """Padded first head weight: the last forward-time entry of the transformed-weight pool (region F)."""
         self._w0p_t = self.pool_alloc(256 * 9 * spec.FUSED_CP)
+        # channel slices of the same weight for the split formulation: W_f [256][9][256], W_l [(n,t) = 2304][256], W_g [2304][2]
+        self._w0_split = (self.pool_alloc(256 * 9 * 256), self.pool_alloc(2304 * 256), self.pool_alloc(2304 * 2))
         self._pool_f_end = self._pool_used
 
     def _build_resnet_fpn(self, bwd_stages, stage_names, fl, dfl):
@@ -789,8 +794,25 @@ class Engine:
         self.out = out
         w0, w0p, dw0p = st.flat("att_reg_box.0.0.weight"), w0p_t[0], self.buf(256 * 9 * CP)
         cells = list(spec.CELLS)
-        self.fwd.append(("fn", lambda: ops.fuse_lang_grid(feat, lang, grid, fused, B, spec.TOTAL_CELLS, cells, 256, 256, CP)))
-        self.prep_fwd.append(lambda: ops.pad_channels(w0, w0p, 256 * 9, spec.FUSED_C, CP))
+        split = self.split_head0
+        if not split:
+            self.fwd.append(("fn", lambda: ops.fuse_lang_grid(feat, lang, grid, fused, B, spec.TOTAL_CELLS, cells, 256, 256, CP)))
+            self.prep_fwd.append(lambda: ops.pad_channels(w0, w0p, 256 * 9, spec.FUSED_C, CP))
+        else:
+            FC, TC = spec.FUSED_C, spec.TOTAL_CELLS
+            h0wf_t, h0wl_t, h0wg_t = self._w0_split
+            h0wf, h0wl, h0wg = h0wf_t[0], h0wl_t[0], h0wg_t[0]
+            self.prep_fwd.append(lambda: ops.copy_cols(w0, FC, h0wf, 256, 2304, 256))
+            self.prep_fwd.append(lambda: ops.copy_cols(w0[256:], FC, h0wl, 256, 2304, 256))
+            self.prep_fwd.append(lambda: ops.copy_cols(w0[512:], FC, h0wg, 2, 2304, 2))
+            tabs = geometry.head0_tables(B, spec.LEVEL_SIZES, grid.cpu())
+            gp, cell_cls = tabs["gridpatch"].to(dev), tabs["cell_cls"].to(dev)
+            cell_base, cell_stride, ridx = tabs["cell_base"].to(dev), tabs["cell_stride"].to(dev), tabs["row_add_idx"].to(dev)
+            radd = self.buf(B * 16 * 256 + TC * 256)          # L [B][16][256] followed by G [cells][256]
+            Lt, Gt = radd[:B * 16 * 256], radd[B * 16 * 256:]
+            V, St = self.buf(B, 2304), self.buf(B, 2304)
+            rows_l = geometry.conv_rows(B, 1, 1, 256, 1, 1, 2304, 1, 0).to(dev)
+            rows_lt = geometry.conv_rows(B, 1, 1, 2304, 1, 1, 256, 1, 0).to(dev)
 
         def head_rows(kind, cin, cout, scatter=False):
             tabs, a_off = [], 0
@@ -814,10 +836,22 @@ class Engine:
         rows_last, rows_f48 = head_rows("fwd", 256, 45, scatter=True), head_rows("fwd", 256, 48)
         rows_d520, rows_d256, rows_d48 = head_rows("dgrad", CP, 256), head_rows("dgrad", 256, 256), head_rows("dgrad", 256, 48)
         hb16 = self.use_b16(256)                             # every head contraction has channel counts % 8 == 0
-        _, fused_lo = self.fwd_operand(fused, M, CP, b16=hb16)
-        w0h, w0l = self.weight_operand(w0p_t, hb16)
-        self.fwd.append(("op", ConvOp(fused, w0h, hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
-                                      impl=self.impl, w_lo=w0l, x_lo=fused_lo, y_pitch=256)))
+        if not split:
+            _, fused_lo = self.fwd_operand(fused, M, CP, b16=hb16)
+            w0h, w0l = self.weight_operand(w0p_t, hb16)
+            self.fwd.append(("op", ConvOp(fused, w0h, hs[0], rows_f520, M, CP, 256, 3, 3, bias=hb(0), out_relu=True,
+                                          impl=self.impl, w_lo=w0l, x_lo=fused_lo, y_pitch=256)))
+        else:
+            # V = lang x W_l^T, its border-class sums and the grid term, then the conv over feat alone adds them per row
+            _, lang_lo = self.fwd_operand(lang, B, 256, b16=hb16)
+            wlh, wll = self.weight_operand(h0wl_t, hb16)
+            self.fwd.append(("op", ConvOp(lang, wlh, V, rows_l, B, 256, 2304, 1, 1, impl=self.impl, w_lo=wll, x_lo=lang_lo,
+                                          x_plain=True, y_pitch=2304)))
+            self.fwd.append(("fn", lambda: ops.head0_lang_grid_terms(V, h0wg, gp, Lt, Gt, B, TC, 256)))
+            _, feat_lo = self.fwd_operand(feat, M, 256, b16=hb16)
+            wfh, wfl = self.weight_operand(h0wf_t, hb16)
+            self.fwd.append(("op", ConvOp(feat, wfh, hs[0], rows_f256, M, 256, 256, 3, 3, bias=hb(0), out_relu=True,
+                                          impl=self.impl, w_lo=wfl, x_lo=feat_lo, y_pitch=256, row_add=radd, row_add_idx=ridx)))
         hs_lo = []
         for i in range(1, 5):
             wh, wl = self.weight_operand(f"att_reg_box.{i}.0.weight", hb16)
@@ -832,6 +866,8 @@ class Engine:
         self.fwd_marks["head"] = (head_first, len(self.fwd))
         self.d_out = self.buf(B, A, 5)
         self.dbg = dict(feat=feat, dfeat=dfeat, lang=lang, dlang=dlang, hs=hs, fused=fused, lvl_off=lvl_off, **dbg)
+        if split:
+            self.dbg["head0"] = dict(V=V, St=St, radd=radd, wf=h0wf, wl=h0wl, wg=h0wg, gridpatch=gp, row_add_idx=ridx)
         wt5 = self.buf(256 * 9 * 45)
         wt5p_t = self.pool_alloc(256 * 9 * 48)
         wt5p = wt5p_t[0]
@@ -839,6 +875,10 @@ class Engine:
         wt0_t = self.pool_alloc(CP * 9 * 256)
         wt0 = wt0_t[0]
         tmp48 = self.buf(48)
+        if split:
+            dwf, dwl = self.buf(256 * 9 * 256), self.buf(2304 * 256)
+            scr = self.buf(B * 8 * 34 * 256)
+            wlT_t, wfT_t = self.pool_alloc(256 * 2304), self.pool_alloc(256 * 9 * 256)
 
         def head_bwd():
             d_out = self.d_out
@@ -864,14 +904,36 @@ class Engine:
                 wth, wtl = self.weight_operand(wts[i], hb16)
                 self.bwd.append(ConvOp(dhs[i], wth, dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
                                        impl=self.impl, w_lo=wtl, x_lo=dlo, y_pitch=256))
-            self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
             gb0 = st.grad_flat("att_reg_box.0.0.bias")
             self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
-            self.bwd.append(lambda: dw0p.zero_())
             d0lo = self.bwd_operand(dhs[0], M, 256, b16=hb16)
+            g0 = st.grad_flat("att_reg_box.0.0.weight")
+            if split:
+                # dW_f: weight gradient over feat; dW_l, d lang: two small GEMMs over the per-tap column sums; dW_g from the same
+                # pass over dh0; d feat: the data gradient with W_f alone, straight into the level buffer
+                self.bwd.append(lambda: dwf.zero_())
+                self.bwd.append(WgradOp(feat, dhs[0], dwf, rows_f256, M, 256, 256, 3, 3, impl=self.impl, x_lo=feat_lo, dy_lo=d0lo,
+                                        dy_pitch=256))
+                self.bwd.append(lambda: ops.copy_cols(dwf, 256, g0, FC, 2304, 256))
+                self.bwd.append(lambda: ops.head0_backward_sums(dhs[0], cell_base, cell_stride, cell_cls, gp, B, TC, 256, scr, St,
+                                                                g0[512:], FC))
+                self.bwd.append(lambda: dwl.zero_())
+                self.bwd.append(WgradOp(lang, St, dwl, rows_l, B, 256, 2304, 1, 1, impl=self.impl))
+                self.bwd.append(lambda: ops.copy_cols(dwl, 256, g0[256:], FC, 2304, 256))
+                self.prep_bwd.append(lambda: ops.weight_transpose_flip(h0wl, wlT_t[0], 2304, 1, 1, 256))
+                self.prep_bwd.append(lambda: ops.weight_transpose_flip(h0wf, wfT_t[0], 256, 3, 3, 256))
+                st_lo = self.bwd_operand(St, B, 2304, b16=hb16)
+                wlth, wltl = self.weight_operand(wlT_t, hb16)
+                self.bwd.append(ConvOp(St, wlth, dlang, rows_lt, B, 2304, 256, 1, 1, impl=self.impl, w_lo=wltl, x_lo=st_lo,
+                                       x_plain=True, y_pitch=256))
+                wfth, wftl = self.weight_operand(wfT_t, hb16)
+                self.bwd.append(ConvOp(dhs[0], wfth, dfeat, rows_d256, M, 256, 256, 3, 3, impl=self.impl, w_lo=wftl, x_lo=d0lo,
+                                       y_pitch=256))
+                return
+            self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
+            self.bwd.append(lambda: dw0p.zero_())
             self.bwd.append(WgradOp(fused, dhs[0], dw0p, rows_f520, M, CP, 256, 3, 3, impl=self.impl, x_lo=fused_lo, dy_lo=d0lo,
                                     dy_pitch=256))
-            g0 = st.grad_flat("att_reg_box.0.0.weight")
             self.bwd.append(lambda: ops.pad_channels(dw0p, g0, 256 * 9, CP, spec.FUSED_C))
             wt0h, wt0l = self.weight_operand(wt0_t, hb16)
             self.bwd.append(ConvOp(dhs[0], wt0h, dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0l,

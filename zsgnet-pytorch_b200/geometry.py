@@ -67,3 +67,39 @@ def dgrad_rows_1x1_s2(B, hin, win, cin, hout, wout, cout, dy_off=0, dx_off=0):
 
 def concat_rows(tables):
     return torch.cat(tables, dim=0).contiguous()
+
+
+def head0_tables(B, level_sizes, grid_yx):
+    """Host tables of the split first head conv (engine.py, csrc/elementwise.cu): per cell (all levels, level-major) the border
+    class, the grid values under the nine taps (0 outside the level), the row of (sample 0, cell) and the row stride between
+    samples in the level-major [sum_l B * cells_l, C] matrices; per output row the two offsets zsg_conv_params.row_add adds
+    (language class sums L [B][16][256], then the grid term G [cells][256] in the same buffer).  grid_yx: [cells, 2] as
+    mdl.py:77-104 tiles it (anchors.cell_grid per level)."""
+    grid_yx = np.asarray(grid_yx, dtype=np.float32).reshape(-1, 2)
+    total = sum(s * s for s in level_sizes)
+    gp = np.zeros((total, 9, 2), dtype=np.float32)
+    cls = np.zeros(total, dtype=np.int32)
+    base = np.zeros(total, dtype=np.int32)
+    stride = np.zeros(total, dtype=np.int32)
+    ridx = []
+    cb, row_off = 0, 0
+    for S in level_sizes:
+        ys, xs = np.divmod(np.arange(S * S), S)
+        ry = (ys == 0).astype(np.int32) | ((ys == S - 1).astype(np.int32) << 1)
+        rx = (xs == 0).astype(np.int32) | ((xs == S - 1).astype(np.int32) << 1)
+        cls[cb:cb + S * S] = ry * 4 + rx
+        for t in range(9):
+            ny, nx = ys + t // 3 - 1, xs + t % 3 - 1
+            ok = (ny >= 0) & (ny < S) & (nx >= 0) & (nx < S)
+            nb = cb + np.clip(ny, 0, S - 1) * S + np.clip(nx, 0, S - 1)
+            gp[cb:cb + S * S, t, :] = np.where(ok[:, None], grid_yx[nb], 0.0)
+        base[cb:cb + S * S] = row_off + np.arange(S * S)
+        stride[cb:cb + S * S] = S * S
+        b = np.repeat(np.arange(B), S * S)
+        local = np.tile(np.arange(S * S), B)
+        ridx.append(np.stack([(b * 16 + cls[cb + local]) * 256, B * 16 * 256 + (cb + local) * 256], axis=1))
+        cb += S * S
+        row_off += B * S * S
+    return dict(gridpatch=torch.from_numpy(gp.reshape(total, 18)), cell_cls=torch.from_numpy(cls),
+                cell_base=torch.from_numpy(base), cell_stride=torch.from_numpy(stride),
+                row_add_idx=torch.from_numpy(np.concatenate(ridx).astype(np.int32)).contiguous())

@@ -45,8 +45,8 @@ class ConvOp:
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
-                 x_lo=None, dil=1, stats=None, x_plain=False, y_pitch=0):
-        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats)
+                 x_lo=None, dil=1, stats=None, x_plain=False, y_pitch=0, row_add=None, row_add_idx=None):
+        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats, row_add, row_add_idx)
         yb = None
         if _is_bf16(y):                                      # bf16 storage: the output tensor itself is bfloat16
             y, yb = None, y
@@ -62,7 +62,8 @@ class ConvOp:
             x_lo = w_lo = None
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
-                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb), ptr(rb), int(y_pitch))
+                            impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb), ptr(rb), int(y_pitch),
+                            ptr(row_add), ptr(row_add_idx))
         if y_pitch and rows.is_cuda:                         # the claim is checked once, when the launch is described
             out = rows.view(torch.int32).view(-1, 4)[:m, 3].to(torch.int64)
             assert bool((out == torch.arange(m, device=rows.device) * y_pitch).all()), "y_pitch does not describe this row table"
@@ -97,6 +98,19 @@ class WgradOp:
         if PROFILER is not None:
             return PROFILER.timed(self, "zsg_conv_wgrad")
         call("zsg_conv_wgrad", self.ref, stream())
+
+
+def copy_cols(src, src_ld, dst, dst_ld, rows, c):
+    call("zsg_copy_cols", ptr(src), src_ld, ptr(dst), dst_ld, rows, c, stream())
+
+
+def head0_lang_grid_terms(v, wg, gridpatch, lang_cls, grid_term, b, total_cells, n):
+    call("zsg_head0_lang_grid_terms", ptr(v), ptr(wg), ptr(gridpatch), ptr(lang_cls), ptr(grid_term), b, total_cells, n, stream())
+
+
+def head0_backward_sums(dh, cell_base, cell_stride, cell_cls, gridpatch, b, total_cells, n, scratch, tap_sums, dwg, dwg_ld):
+    call("zsg_head0_backward_sums", ptr(dh), ptr(cell_base), ptr(cell_stride), ptr(cell_cls), ptr(gridpatch), b, total_cells, n,
+         ptr(scratch), scratch.numel(), ptr(tap_sums), ptr(dwg), dwg_ld, stream())
 
 
 def weight_transpose_flip(w, wt, cout, r, s, cin):
