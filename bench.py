@@ -424,6 +424,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"              # the version banner goes to stdout, where the ONE JSON line belongs
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import zsg_b200  # noqa: F401
 
