@@ -461,7 +461,10 @@ __global__ void __launch_bounds__(256) bn_apply8_kernel(const void* __restrict__
   for (int k = 0; k < 8; ++k) { sc[k] = 1.f; sh[k] = 0.f; rs[k] = 1.f; rh[k] = 0.f; }
   if (scale) { ldc8(scale, t.c, sc); ldc8(shift, t.c, sh); }
   if (rscale) { ldc8(rscale, t.c, rs); ldc8(rshift, t.c, rh); }
-  constexpr int U = XB ? 4 : 2;
+#ifndef ZSG_APPLY_U
+#define ZSG_APPLY_U 2      // measured (tools/time_bn.py): 4 rows in flight help the 369 MB tensors (6.3 vs 6.0 TB/s), 2 the smaller ones
+#endif
+  constexpr int U = XB ? 4 : ZSG_APPLY_U;
   const int64_t stride = (int64_t)gridDim.x * t.rpb;
   for (int64_t r0 = (int64_t)blockIdx.x * t.rpb + t.lane_r; r0 < rows; r0 += U * stride) {
     uint4 xa[U], xb2[U], ra[U], rb2[U];
@@ -1115,9 +1118,13 @@ __global__ void __launch_bounds__(256) head0_reduce_kernel(const float* __restri
     for (int u = 0; u < U; ++u) {
       if (ce[u] >= total_cells) break;
       s[cl[u]][n] += v[u];
-      const float* g = gp + (size_t)ce[u] * 18;
+      const float2* g = reinterpret_cast<const float2*>(gp + (size_t)ce[u] * 18);     // 72-byte rows: 8-byte aligned
 #pragma unroll
-      for (int k = 0; k < 18; ++k) wg[k] = fmaf(v[u], g[k], wg[k]);
+      for (int k = 0; k < 9; ++k) {
+        const float2 gk = __ldg(g + k);
+        wg[2 * k] = fmaf(v[u], gk.x, wg[2 * k]);
+        wg[2 * k + 1] = fmaf(v[u], gk.y, wg[2 * k + 1]);
+      }
     }
   }
   float* sp = Sp + ((size_t)b * nch + ch) * 16 * N;
@@ -1710,7 +1717,8 @@ extern "C" int zsg_head0_backward_sums(const float* dh, const int32_t* cell_base
               "zsg_head0_backward_sums: null pointer");
   ZSG_REQUIRE(n == 256, "zsg_head0_backward_sums: n=%d (the head width of the path is 256)", n);
   const int nch = 8;
-  ZSG_REQUIRE(scratch_floats >= (size_t)b * nch * (16 + 18) * n, "zsg_head0_backward_sums: scratch too small");
+  ZSG_REQUIRE(scratch_floats >= (size_t)b * nch * (16 + 18) * n && ((uintptr_t)gridpatch & 7) == 0,
+              "zsg_head0_backward_sums: scratch too small or gridpatch not 8-byte aligned");
   float* Sp = scratch;
   float* Wp = scratch + (size_t)b * nch * 16 * n;
   cudaStream_t st = as_stream(stream);
