@@ -144,6 +144,10 @@ typedef struct {
 } zsg_wtf_desc;
 int zsg_weight_transpose_flip_batched(const float* src_base, float* dst_base, const zsg_wtf_desc* descs, int n,
                                       int64_t total, zsg_stream_t stream);
+/* The same for tables in which EVERY cin and cout is a multiple of 32 (all of the path's): 32 x 32 tiles through shared memory,
+ * coalesced on both sides. */
+int zsg_weight_transpose_flip_batched32(const float* src_base, float* dst_base, const zsg_wtf_desc* descs, int n,
+                                        int64_t total, zsg_stream_t stream);
 /* Operand preparation for the cp.async GEMM paths: z = relu?(x * scale[c] + shift[c]) (z may be NULL when there is
  * no affine / ReLU: the tensor is its own high part) and lo = z - trunc_tf32(z).  x is [rows, c], c % 4 == 0.
  * Replaces the on-the-fly split inside the conv kernels for every conv of the path (mdl.py / fpn_resnet.py). */

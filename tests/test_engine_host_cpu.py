@@ -67,7 +67,7 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     assert bwd["zsg_bn_bwd_reduce"] == 53 and bwd["zsg_bn_bwd_apply"] == 53
     # 64 of the transposed-flipped weight copies (all that go arena -> pool) are one batched launch; the padded last head
     # weight and the two slices of the first one (W_f for d feat, W_l for d lang) keep their own
-    assert bwd["zsg_weight_transpose_flip_batched"] == 1 and bwd["zsg_weight_transpose_flip"] == 3
+    assert bwd["zsg_weight_transpose_flip_batched32"] == 1 and bwd["zsg_weight_transpose_flip"] == 3   # tiled: all dims % 32 == 0
     assert len(eng._wtf) == 52 + 8 + 4 and bwd["zsg_split_tf32"] == 1
     # buckets: contiguous, ordered, covering the used arena exactly once
     assert seen[0][0] == 0 and seen[-1][1] == store.used

@@ -878,6 +878,21 @@ def test_batched_weight_transpose_flip(zsg):
     ops.weight_transpose_flip_batched(src, dst, tab, len(entries), total)
     torch.cuda.synchronize()
     assert torch.equal(dst[:off], want[:off]) and torch.isnan(dst[off:]).all()
+    # the tiled variant (every cin / cout a multiple of 32, as in the engine's table)
+    shapes = [(64, 1, 64), (256, 3, 128), (64, 3, 64), (2048, 1, 512), (256, 3, 256)]
+    src = torch.randn(sum(co * k * k * ci for co, k, ci in shapes), generator=g).cuda()
+    dst, want = torch.full_like(src, float("nan")), torch.full_like(src, float("nan"))
+    entries, off = [], 0
+    for co, k, ci in shapes:
+        n = co * k * k * ci
+        entries.append((off, off, co, k, k, ci))
+        ops.weight_transpose_flip(src[off:off + n], want[off:off + n], co, k, k, ci)
+        off += n
+    assert ops.wtf_table_is_tiled(entries)
+    tab, total = ops.wtf_table(entries, "cuda")
+    ops.weight_transpose_flip_batched(src, dst, tab, len(entries), total, tiled=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, want)
 
 
 # ------------------------------------------------------------------------------- NaN handling, anchors (ADVICE)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "zsg_debug_set_conv_trace": [_P, _I],
     "zsg_weight_transpose_flip": [_P, _P, _I, _I, _I, _I, _P],
     "zsg_weight_transpose_flip_batched": [_P, _P, _P, _I, _L, _P],
+    "zsg_weight_transpose_flip_batched32": [_P, _P, _P, _I, _L, _P],
     "zsg_pad_channels": [_P, _P, _L, _I, _I, _P],
     "zsg_split_tf32": [_P, _P, _P, _L, _P],
     "zsg_split_act": [_P, _P, _P, _I, _P, _P, _L, _I, _P],

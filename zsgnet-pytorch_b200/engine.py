@@ -416,7 +416,8 @@ class Engine:
         if self._wtf:                                     # first: the stride-2 class slices are cut from these copies
             tab, total = ops.wtf_table(self._wtf, dev)
             n, arena, pool = len(self._wtf), st.param_arena, self.pool
-            self.prep_bwd.insert(0, lambda: ops.weight_transpose_flip_batched(arena, pool, tab, n, total))
+            tiled = ops.wtf_table_is_tiled(self._wtf)
+            self.prep_bwd.insert(0, lambda: ops.weight_transpose_flip_batched(arena, pool, tab, n, total, tiled=tiled))
 
     def _alloc_head_w0p(self):
         """Padded first head weight: the last forward-time entry of the transformed-weight pool (region F)."""

@@ -131,8 +131,14 @@ def wtf_table(entries, device):
     return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(device), begin
 
 
-def weight_transpose_flip_batched(src_base, dst_base, table, n, total):
-    call("zsg_weight_transpose_flip_batched", ptr(src_base), ptr(dst_base), ptr(table), n, total, stream())
+def weight_transpose_flip_batched(src_base, dst_base, table, n, total, tiled=False):
+    """tiled: every cin / cout of the table is a multiple of 32 (wtf_table_is_tiled)."""
+    call("zsg_weight_transpose_flip_batched32" if tiled else "zsg_weight_transpose_flip_batched", ptr(src_base), ptr(dst_base),
+         ptr(table), n, total, stream())
+
+
+def wtf_table_is_tiled(entries):
+    return all(cout % 32 == 0 and cin % 32 == 0 for _, _, cout, _, _, cin in entries)
 
 
 def split_act(x, lo, rows, c, scale=None, shift=None, relu=False, z=None):
