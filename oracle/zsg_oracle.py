@@ -505,8 +505,9 @@ def draw_h0c0(B):
     return h0, c0
 
 
-def zsgnet_forward(sd, batch, training=True, h0c0=None, batched_lstm=True, return_inter=False):
-    """mdl.py:338-403.  The trunk is chosen by the keys present: SSD-VGG (mdl.py:413-418) or ResNet-50+FPN."""
+def zsgnet_forward(sd, batch, training=True, h0c0=None, batched_lstm=True, return_inter=False, do_norm=False):
+    """mdl.py:338-403.  The trunk is chosen by the keys present: SSD-VGG (mdl.py:413-418) or ResNet-50+FPN.
+    do_norm: cfg do_norm (mdl.py:118-130): every feature pixel and the language vector are L2-normalised before the fusion."""
     img, qvec, qlens = batch["img"], batch["qvec"], batch["qlens"]
     max_qlen = int(qlens.max().item())
     qvec = qvec[:, :max_qlen].contiguous()
@@ -520,12 +521,16 @@ def zsgnet_forward(sd, batch, training=True, h0c0=None, batched_lstm=True, retur
         bn = BNState(sd, training)
         c3, c4, c5 = resnet50_c3c4c5(sd, img, bn)
         feats = fpn(sd, c3, c4, c5)
+    lang_raw, feats_raw = lang, feats
+    if do_norm:                                              # mdl.py:118-123 and 128-130
+        feats = [f / f.norm(dim=1).unsqueeze(1).expand(*f.shape) for f in feats]
+        lang = lang / lang.norm(dim=1).unsqueeze(1).expand(*lang.shape)
     att, bbx = fuse_and_head(sd, feats, lang)
     out = {"att_out": att, "bbx_out": bbx,
            "feat_sizes": torch.tensor([[f.shape[2], f.shape[3]] for f in feats]),
            "num_f_out": torch.tensor([len(feats)])}
     if return_inter:
-        out["_inter"] = {"lang": lang, "c3": c3, "c4": c4, "c5": c5, "feats": feats}
+        out["_inter"] = {"lang": lang_raw, "c3": c3, "c4": c4, "c5": c5, "feats": feats_raw}
     return out
 
 
@@ -543,7 +548,7 @@ def trainable_keys(sd):
     return [k for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k]
 
 
-def train_step(sd, batch, opt_state=None, lr=1e-4, seed=None, do_adam=True):
+def train_step(sd, batch, opt_state=None, lr=1e-4, seed=None, do_adam=True, do_norm=False):
     """One iteration of utils.py:405-414: forward, loss, backward, Adam(betas 0.9,0.99), metric.
     `sd` is updated in place.  Returns losses, metric and the gradients."""
     if seed is not None:
@@ -551,7 +556,7 @@ def train_step(sd, batch, opt_state=None, lr=1e-4, seed=None, do_adam=True):
     keys = trainable_keys(sd)
     for k in keys:
         sd[k] = sd[k].detach().requires_grad_(True)
-    out = zsgnet_forward(sd, batch, training=True)
+    out = zsgnet_forward(sd, batch, training=True, do_norm=do_norm)
     anchs = default_anchors().to(batch["img"].device)
     ls = zsg_loss(out["att_out"], out["bbx_out"], batch["annot"], anchs)
     ls["loss"].mean().backward()

@@ -430,3 +430,50 @@ def test_pretrained_trunk_weights_load_like_the_reference(tmp_path):
     sd = net.state_dict()
     for k, v in tv.state_dict().items():
         assert torch.equal(sd["backbone.encoder." + k].cpu(), v), k
+
+
+# ------------------------------------------------------------------------------- ablation config: do_norm (mdl.py:118-130)
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_do_norm_train_step_vs_live_oracle(split, monkeypatch):
+    """cfg do_norm: every feature pixel and the language vector are L2-normalised in front of the fusion.  The oracle's
+    do_norm is pinned against the unmodified reference in tests/test_ablation_cfg_cpu.py.  Both formulations of the first
+    head conv (split / materialised)."""
+    monkeypatch.setenv("ZSG_SPLIT_HEAD0", split)
+    import zsg_b200  # noqa: F401
+    from zsg_b200 import mdl, loss, evaluator
+    from oracle import synth, zsg_oracle as zo
+    cfg = synth.default_cfg()
+    cfg["device"], cfg["do_norm"], cfg["zsg_quiet"] = "cuda", True, True
+    ratios, scales = synth.ratios_scales(cfg)
+    net = mdl.get_default_net(num_anchors=9, cfg=cfg)
+    crit, ev = loss.get_default_loss(ratios, scales, cfg), evaluator.get_default_eval(ratios, scales, cfg)
+    B, seed = 3, 41
+    batch, out, ls, met = run_step(net, crit, ev, synth, B, seed, True)
+    assert net.engine_for(B, 20).do_norm
+    ols, omet, ograds, oout, _ = zo.train_step(synth.make_state_dict(0), synth.make_batch(B, seed=seed, var_len=True), seed=seed,
+                                               do_adam=False, do_norm=True)
+    plain, _, _, _, _ = zo.train_step(synth.make_state_dict(0), synth.make_batch(B, seed=seed, var_len=True), seed=seed, do_adam=False)
+    assert abs(plain["loss"].item() - ols["loss"].item()) > 1e-3 * abs(ols["loss"].item())      # the flag changes the function
+    for k in ("loss", "cls_ls", "box_ls"):
+        assert ls[k].item() == pytest.approx(ols[k].item(), rel=RTOL), k
+    assert torch.equal(crit.last_top1.cpu(), ols["top1"]) and torch.equal(crit.last_pos.cpu().bool(), ols["pos"])
+    assert rms_rel(out["att_out"].detach().cpu().numpy(), oout["att_out"].detach().numpy()) < 3e-4
+    # gradients: against the noise floor of this network (the same oracle functions executed by PyTorch on CUDA in fp32, TF32
+    # off), like test_train_step_vs_live_oracle_b4
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdg = {k: v.cuda() for k, v in synth.make_state_dict(0).items()}
+    _, _, cgrads, _, _ = zo.train_step(sdg, batch, seed=seed, do_adam=False, do_norm=True)
+    mine_e, cuda_e = [], []
+    for k, g in ograds.items():
+        if g is None:
+            continue
+        r = g.double()
+        n = r.norm().clamp_min(1e-30)
+        mine_e.append(float((net.get_parameter(k).grad.cpu().double() - r).norm() / n))
+        cuda_e.append(float((cgrads[k].cpu().double() - r).norm() / n))
+    mine_e, cuda_e = np.array(mine_e), np.array(cuda_e)
+    print(f"do_norm gradient error vs CPU fp32: zsg_b200 median {np.median(mine_e):.3e} max {mine_e.max():.3e}; torch CUDA fp32 "
+          f"median {np.median(cuda_e):.3e} max {cuda_e.max():.3e}")
+    assert np.median(mine_e) < 2.0 * np.median(cuda_e) + 1e-3
+    assert mine_e.max() < 3.0 * cuda_e.max() + 1e-3

@@ -87,8 +87,9 @@ class _BN:
 
 
 class Engine:
-    def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC, dtype="fp32"):
+    def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC, dtype="fp32", do_norm=False):
         self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
+        self.do_norm = bool(do_norm)                      # cfg do_norm (mdl.py:118-130): L2-normalised feature pixels / language vector
         assert dtype in ("fp32", "bf16"), dtype
         # dtype = arithmetic of the dense contractions.  "fp32": 3xTF32 (BASELINE configs[1], the reference's fp32 results to
         # 1e-4).  "bf16": bf16 operand images, one kind::f16 MMA per product, fp32 accumulation (configs[2..4], "bf16
@@ -796,8 +797,17 @@ class Engine:
         w0, w0p, dw0p = st.flat("att_reg_box.0.0.weight"), w0p_t[0], self.buf(256 * 9 * CP)
         cells = list(spec.CELLS)
         split = self.split_head0
+        # cfg do_norm (mdl.py:118-130): the head sees feat / ||feat||_2 per pixel (over channels) and lang / ||lang||_2; the
+        # backward maps the gradients back through zsg_l2norm_bwd at the end of the head stage.  (New names, not rebinding:
+        # the LSTM launches above are closures over `lang` / `dlang`.)
+        hfeat, hlang, hdfeat, hdlang = feat, lang, dfeat, dlang
+        if self.do_norm:
+            hfeat, hlang, hdfeat, hdlang = self.buf(M, 256), self.buf(B, 256), self.buf(M, 256), self.buf(B, 256)
+            fnorm, lnorm = self.buf(M), self.buf(B)
+            self.fwd.append(("fn", lambda: ops.l2norm_fwd(feat, hfeat, fnorm, M, 256)))
+            self.fwd.append(("fn", lambda: ops.l2norm_fwd(lang, hlang, lnorm, B, 256)))
         if not split:
-            self.fwd.append(("fn", lambda: ops.fuse_lang_grid(feat, lang, grid, fused, B, spec.TOTAL_CELLS, cells, 256, 256, CP)))
+            self.fwd.append(("fn", lambda: ops.fuse_lang_grid(hfeat, hlang, grid, fused, B, spec.TOTAL_CELLS, cells, 256, 256, CP)))
             self.prep_fwd.append(lambda: ops.pad_channels(w0, w0p, 256 * 9, spec.FUSED_C, CP))
         else:
             FC, TC = spec.FUSED_C, spec.TOTAL_CELLS
@@ -844,14 +854,14 @@ class Engine:
                                           impl=self.impl, w_lo=w0l, x_lo=fused_lo, y_pitch=256)))
         else:
             # V = lang x W_l^T, its border-class sums and the grid term, then the conv over feat alone adds them per row
-            _, lang_lo = self.fwd_operand(lang, B, 256, b16=hb16)
+            _, lang_lo = self.fwd_operand(hlang, B, 256, b16=hb16)
             wlh, wll = self.weight_operand(h0wl_t, hb16)
-            self.fwd.append(("op", ConvOp(lang, wlh, V, rows_l, B, 256, 2304, 1, 1, impl=self.impl, w_lo=wll, x_lo=lang_lo,
+            self.fwd.append(("op", ConvOp(hlang, wlh, V, rows_l, B, 256, 2304, 1, 1, impl=self.impl, w_lo=wll, x_lo=lang_lo,
                                           x_plain=True, y_pitch=2304)))
             self.fwd.append(("fn", lambda: ops.head0_lang_grid_terms(V, h0wg, gp, Lt, Gt, B, TC, 256)))
-            _, feat_lo = self.fwd_operand(feat, M, 256, b16=hb16)
+            _, feat_lo = self.fwd_operand(hfeat, M, 256, b16=hb16)
             wfh, wfl = self.weight_operand(h0wf_t, hb16)
-            self.fwd.append(("op", ConvOp(feat, wfh, hs[0], rows_f256, M, 256, 256, 3, 3, bias=hb(0), out_relu=True,
+            self.fwd.append(("op", ConvOp(hfeat, wfh, hs[0], rows_f256, M, 256, 256, 3, 3, bias=hb(0), out_relu=True,
                                           impl=self.impl, w_lo=wfl, x_lo=feat_lo, y_pitch=256, row_add=radd, row_add_idx=ridx)))
         hs_lo = []
         for i in range(1, 5):
@@ -880,6 +890,11 @@ class Engine:
             dwf, dwl = self.buf(256 * 9 * 256), self.buf(2304 * 256)
             scr = self.buf(B * 8 * 34 * 256)
             wlT_t, wfT_t = self.pool_alloc(256 * 2304), self.pool_alloc(256 * 9 * 256)
+
+        def norm_bwd():
+            if self.do_norm:
+                self.bwd.append(lambda: ops.l2norm_bwd(hdfeat, feat, fnorm, dfeat, M, 256))
+                self.bwd.append(lambda: ops.l2norm_bwd(hdlang, lang, lnorm, dlang, B, 256))
 
         def head_bwd():
             d_out = self.d_out
@@ -913,23 +928,24 @@ class Engine:
                 # dW_f: weight gradient over feat; dW_l, d lang: two small GEMMs over the per-tap column sums; dW_g from the same
                 # pass over dh0; d feat: the data gradient with W_f alone, straight into the level buffer
                 self.bwd.append(lambda: dwf.zero_())
-                self.bwd.append(WgradOp(feat, dhs[0], dwf, rows_f256, M, 256, 256, 3, 3, impl=self.impl, x_lo=feat_lo, dy_lo=d0lo,
+                self.bwd.append(WgradOp(hfeat, dhs[0], dwf, rows_f256, M, 256, 256, 3, 3, impl=self.impl, x_lo=feat_lo, dy_lo=d0lo,
                                         dy_pitch=256))
                 self.bwd.append(lambda: ops.copy_cols(dwf, 256, g0, FC, 2304, 256))
                 self.bwd.append(lambda: ops.head0_backward_sums(dhs[0], cell_base, cell_stride, cell_cls, gp, B, TC, 256, scr, St,
                                                                 g0[512:], FC))
                 self.bwd.append(lambda: dwl.zero_())
-                self.bwd.append(WgradOp(lang, St, dwl, rows_l, B, 256, 2304, 1, 1, impl=self.impl))
+                self.bwd.append(WgradOp(hlang, St, dwl, rows_l, B, 256, 2304, 1, 1, impl=self.impl))
                 self.bwd.append(lambda: ops.copy_cols(dwl, 256, g0[256:], FC, 2304, 256))
                 self.prep_bwd.append(lambda: ops.weight_transpose_flip(h0wl, wlT_t[0], 2304, 1, 1, 256))
                 self.prep_bwd.append(lambda: ops.weight_transpose_flip(h0wf, wfT_t[0], 256, 3, 3, 256))
                 st_lo = self.bwd_operand(St, B, 2304, b16=hb16)
                 wlth, wltl = self.weight_operand(wlT_t, hb16)
-                self.bwd.append(ConvOp(St, wlth, dlang, rows_lt, B, 2304, 256, 1, 1, impl=self.impl, w_lo=wltl, x_lo=st_lo,
+                self.bwd.append(ConvOp(St, wlth, hdlang, rows_lt, B, 2304, 256, 1, 1, impl=self.impl, w_lo=wltl, x_lo=st_lo,
                                        x_plain=True, y_pitch=256))
                 wfth, wftl = self.weight_operand(wfT_t, hb16)
-                self.bwd.append(ConvOp(dhs[0], wfth, dfeat, rows_d256, M, 256, 256, 3, 3, impl=self.impl, w_lo=wftl, x_lo=d0lo,
+                self.bwd.append(ConvOp(dhs[0], wfth, hdfeat, rows_d256, M, 256, 256, 3, 3, impl=self.impl, w_lo=wftl, x_lo=d0lo,
                                        y_pitch=256))
+                norm_bwd()
                 return
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w0p, wt0, 256, 3, 3, CP))
             self.bwd.append(lambda: dw0p.zero_())
@@ -939,7 +955,8 @@ class Engine:
             wt0h, wt0l = self.weight_operand(wt0_t, hb16)
             self.bwd.append(ConvOp(dhs[0], wt0h, dfused, rows_d520, M, 256, CP, 3, 3, impl=self.impl, w_lo=wt0l,
                                    x_lo=d0lo, y_pitch=CP))
-            self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, dfeat, dlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
+            self.bwd.append(lambda: ops.unfuse_lang_grid(dfused, hdfeat, hdlang, B, spec.TOTAL_CELLS, cells, 256, 256, CP))
+            norm_bwd()
         head_bwd.label = "head"
         bwd_stages.append(head_bwd)
 

@@ -108,8 +108,7 @@ class ZSGNet(nn.Module):
             unsupported.append("mdl_to_use=%r (built: 'retina' = ResNet-50+FPN, 'ssd_vgg' = SSD-VGG16)" % self.model)
         if list(get("resize_img", [300, 300])) != [300, 300]:
             unsupported.append("resize_img != [300, 300]")
-        if get("do_norm", False):
-            unsupported.append("do_norm=true")
+        self.do_norm = bool(get("do_norm", False))          # mdl.py:118-130, built (zsg_l2norm_fwd / bwd in front of the head)
         if not (get("use_lang", True) and get("use_img", True)):
             unsupported.append("language-/image-blind ablations")
         if not get("use_same_atb", True):
@@ -224,7 +223,7 @@ class ZSGNet(nn.Module):
                 self._engines.pop(next(iter(self._engines)))      # least recently used first
                 torch.cuda.empty_cache()
             bufs = {k: v for k, v in self.bn_buffers.items()}
-            eng = Engine(self.store, bufs, B, Ta, self.store.device, dtype=self.compute_dtype)
+            eng = Engine(self.store, bufs, B, Ta, self.store.device, dtype=self.compute_dtype, do_norm=self.do_norm)
         self._engines[key] = eng                                  # most recently used last
         return eng
 
