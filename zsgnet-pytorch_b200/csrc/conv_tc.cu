@@ -284,10 +284,24 @@ __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int la
 // results do not depend on how the pipe interleaves the tail of one K block with the head of the next (with a
 // shared accumulator that made the fp32 sums differ from run to run).  They still take turns through a token
 // (mbarrier) so that only one thread issues at a time: issuing from both concurrently hung the pipe now and then.
+// Issuer w owns the K blocks g with (g / G) % 2 == w.  G = 1: strict alternation.  Measured (tools/time_big.py, bf16, where a K
+// block is only 4 MMAs = 256 cycles): G = 1, 2 and 4 give the same 670 / 530 TFLOP/s on the 3x3 256->256 forward / weight
+// gradient -- the hand-over between the two issuing threads is not what limits the bf16 kernels.
+#ifndef ZSG_ISSUE_GROUP_BF16
+#define ZSG_ISSUE_GROUP_BF16 1
+#endif
+template <bool BF16> struct IssueGroup { static constexpr uint32_t G = BF16 ? ZSG_ISSUE_GROUP_BF16 : 1; };
+template <bool BF16>
+__device__ __forceinline__ int issuer_count(int g0, int n, int w) {     // K blocks g0 .. g0 + n - 1 owned by issuer w
+  constexpr int G = (int)IssueGroup<BF16>::G;
+  int c = 0;
+  for (int k = 0; k < n; ++k) c += (((g0 + k) / G) & 1) == w;
+  return c;
+}
 struct Issuer {
   uint32_t w;                // 0 / 1
-  uint32_t stage;            // ring position of my next K block
-  uint32_t phase;            // parity of full[stage] for my next K block
+  uint32_t stage;            // ring position of K block g
+  uint32_t phase;            // parity of full[stage] for K block g
   uint32_t tokens = 0;       // tokens consumed so far (parity of my token barrier)
   uint32_t g = 0;            // global K-block index over all tiles of this CTA
   uint32_t chunk = 0;        // global chunk index (selects the accumulator pair and its parity)
@@ -375,7 +389,7 @@ template <int BN, bool BF16 = false>
 __device__ __forceinline__ Issuer issuer_init(uint32_t w) {
   Issuer is;
   is.w = w;
-  is.stage = w % Smem<BN, BF16>::STAGES;
+  is.stage = 0;
   is.phase = 0;
   return is;
 }
@@ -402,12 +416,16 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
     // accumulator) would otherwise complete acc_full phases faster than the drain warps consume them -- their parity wait
     // then misses a phase and hangs (seen on the bf16 path, where K = 64 is ONE K block per tile).
     if (kb % CHUNK_KB == 0) mbar_wait(pb.acc_empty(acc), ((is.chunk >> 1) & 1u) ^ 1u, 100 + is.g);
-    if ((is.g & 1u) == is.w) {
+    constexpr uint32_t G = IssueGroup<BF16>::G;
+    if (((is.g / G) & 1u) == is.w) {
       trace(is.g, 8);
       if (!(ablate & 1)) mbar_wait(pb.full(is.stage), is.phase, 1000 + is.g);     // ablate bit 0 (diagnostics): producers are off
       trace(is.g, 9);
       fence_proxy_async();                                  // cp.async-filled tiles (generic proxy) -> tensor core (async proxy)
-      if (is.g > 0 && !(ablate & 8)) { mbar_wait(pb.token(is.w), is.tokens & 1u, 4000 + is.g); ++is.tokens; }      // my turn
+      if (is.g > 0 && is.g % G == 0 && !(ablate & 8)) {    // first K block of my group: my turn
+        mbar_wait(pb.token(is.w), is.tokens & 1u, 4000 + is.g);
+        ++is.tokens;
+      }
       trace(is.g, 10);
       tc_fence_after();
       if (BF16)
@@ -416,16 +434,15 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
       else
         issue_kblock<BN, MN_MAJOR>(tmem_base + acc * BN, lo0 + is.stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi,
                                    mine == 0 ? 0u : 1u);
-      if (!(ablate & 8)) {
+      if (is.g % G == G - 1 && !(ablate & 8)) {             // last K block of my group: the other issuer may go
         tc_fence_before();
-        mbar_arrive(pb.token(is.w ^ 1u));                   // the other issuer may go
+        mbar_arrive(pb.token(is.w ^ 1u));
       }
       umma_commit(pb.empty(is.stage));                      // frees the stage once the MMAs above have read it
       trace(is.g, 11);
       ++mine;
-      is.stage += 2;
-      if (is.stage >= (uint32_t)S::STAGES) { is.stage -= S::STAGES; is.phase ^= 1u; }
     }
+    if (++is.stage == (uint32_t)S::STAGES) { is.stage = 0; is.phase ^= 1u; }
     if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) {   // chunk closed: my part of it (possibly empty) is complete
       umma_commit(pb.acc_full(acc));
       ++is.chunk;
@@ -436,7 +453,7 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
 
 // drain warps: promote every finished TMEM chunk into fp32 registers (round-to-nearest adds), issuer 0's part first.
 // gkb0 = global index of the tile's first K block (decides which issuer owns which K block of the chunk).
-template <int BN>
+template <int BN, bool BF16 = false>
 __device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_base, int nkb, int gkb0, int quadrant, int half,
                                            float (&acc)[BN / 2], int& gchunk, int ablate = 0) {
   // The first accumulator of a tile that holds anything is loaded straight into `acc` (all of its x16 loads in flight, one
@@ -447,11 +464,10 @@ __device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_bas
     const int c = gchunk;
     const int k0 = cc * CHUNK_KB;
     const int n = (nkb - k0 < CHUNK_KB) ? nkb - k0 : CHUNK_KB;
-    const int first_owner = (gkb0 + k0) & 1;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       const int a = (c & 1) * 2 + w;
-      const int count = (w == first_owner) ? (n + 1) / 2 : n / 2;      // K blocks issuer w put into its accumulator
+      const int count = issuer_count<BF16>(gkb0 + k0, n, w);           // K blocks issuer w put into its accumulator
       mbar_wait(pb.acc_full(a), (c >> 1) & 1, 2000 + c * 2 + w);
       tc_fence_after();
       if (count > 0 && !(ablate & 2)) {
@@ -520,7 +536,7 @@ __device__ __forceinline__ void tmem_ld_frag<4>(uint32_t taddr, float* r) {
 }
 
 // drain_loop in the fragment layout: acc[h * 4U + 4u + 2hh + c]
-template <int BN>
+template <int BN, bool BF16 = false>
 __device__ __forceinline__ void drain_loop_frag(const PipeBars& pb, uint32_t tmem_base, int nkb, int gkb0, int quadrant, int half,
                                                 float (&acc)[BN / 2], int& gchunk, int ablate = 0) {
   constexpr int U = BN / 16;                                // 8-column units of the warp's BN / 2 columns
@@ -530,11 +546,10 @@ __device__ __forceinline__ void drain_loop_frag(const PipeBars& pb, uint32_t tme
     const int c = gchunk;
     const int k0 = cc * CHUNK_KB;
     const int n = (nkb - k0 < CHUNK_KB) ? nkb - k0 : CHUNK_KB;
-    const int first_owner = (gkb0 + k0) & 1;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       const int a = (c & 1) * 2 + w;
-      const int count = (w == first_owner) ? (n + 1) / 2 : n / 2;
+      const int count = issuer_count<BF16>(gkb0 + k0, n, w);
       mbar_wait(pb.acc_full(a), (c >> 1) & 1, 2000 + c * 2 + w);
       tc_fence_after();
       if (count > 0 && !(ablate & 2)) {
@@ -706,7 +721,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
       const int m0 = (tile / tiles_n) * TM;
       float acc[BN / 2];
       if (dw == 0 && lane == 0) trace(gkb0, 12);
-      drain_loop_frag<BN>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
+      drain_loop_frag<BN, BF16>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
       if (dw == 0 && lane == 0) trace(gkb0, 13);
       epilogue_frag<BN, EPI == EPI_B16>(p, acc, m0, n0, quadrant, half, lane, ablate);
       if (dw == 0 && lane == 0) trace(gkb0, 14);
@@ -750,7 +765,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
     }
     float acc[BN / 2];
     if (dw == 0 && lane == 0) trace(gkb0, 12);
-    drain_loop<BN>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
+    drain_loop<BN, BF16>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
     if (dw == 0 && lane == 0) trace(gkb0, 13);
     const int gkb_tile = gkb0;
     gkb0 += nkb;
@@ -1900,7 +1915,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
     const int quadrant = dw & 3, half = dw >> 2;
     float acc[BN / 2];
     int gchunk = 0;
-    drain_loop<BN>(pb, tmem_base, nkb, 0, quadrant, half, acc, gchunk);
+    drain_loop<BN, true>(pb, tmem_base, nkb, 0, quadrant, half, acc, gchunk);
     const int j = j0 + quadrant * 32 + lane;
     if (j < Kt) {
 #pragma unroll
