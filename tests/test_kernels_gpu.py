@@ -1076,6 +1076,56 @@ def test_conv_plain_matrix_tma_equals_gather_path(zsg, case, bf16, epi):
         assert rel_err(ys[1], ref) < (2e-5 if not bf16 else 1e-5)
 
 
+@pytest.mark.parametrize("case", [(2, 64, 20, 19, 256, 1), (1, 256, 30, 30, 64, 1), (2, 128, 9, 9, 136, 3), (3, 72, 7, 5, 24, 3),
+                                  (1, 256, 38, 38, 256, 3)])
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("opts", ["bias_relu", "mask", "residual_acc", "residual_bf16", "full", "row_add"])
+def test_conv_fragment_epilogue_equals_slab_epilogue(zsg, case, bf16, opts):
+    """EPI_FRAGX (conv_tc.cu epilogue_fragx: bias / row_add / ReLU mask / residual / residual_bf16 / accumulate / ReLU from the
+    fragment registers, chosen for plain [m, y_pitch] outputs with cout % 8 == 0) against the slab epilogue (y_pitch = 0):
+    same accumulators, same order of operations => bit-identical outputs; ragged last M tile, cout not a multiple of the tile."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k = case
+    g = torch.Generator().manual_seed(cin * 5 + cout + k)
+    m = B * H * W
+    x = torch.randn(B, H, W, cin, generator=g).cuda()
+    w = (torch.randn(cout, k, k, cin, generator=g) / (cin * k * k) ** 0.5).cuda()
+    rows = geo.conv_rows(B, H, W, cin, H, W, cout, 1, k // 2).cuda()
+    kw = {}
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    if opts == "bias_relu":
+        kw = dict(bias=r(cout), out_relu=True)
+    elif opts == "mask":
+        kw = dict(out_mask=r(m, cout))
+    elif opts == "residual_acc":
+        kw = dict(residual=r(m, cout), accumulate=True)
+    elif opts == "residual_bf16":
+        kw = dict(residual=r(m, cout).to(torch.bfloat16), accumulate=True)
+    elif opts == "full":
+        kw = dict(bias=r(cout), out_mask=r(m, cout), residual=r(m, cout), accumulate=True, out_relu=True)
+    elif opts == "row_add":
+        tab = r(37, cout)
+        idx = (torch.randint(0, 37, (m, 2), generator=g, dtype=torch.int32) * cout).cuda()
+        kw = dict(bias=r(cout), out_relu=True, row_add=tab, row_add_idx=idx)
+    if bf16:
+        xi, wi, wa = x.to(torch.bfloat16), w.to(torch.bfloat16), w
+    else:
+        xi, wa, wi = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+        ops.split_act(x, xi, m, cin)
+        ops.split_tf32(w, wa, wi, w.numel())
+    ys = []
+    for pitch in (0, cout):
+        y = torch.full((m, cout), 0.25, device="cuda")
+        ops.ConvOp(x, wa, y, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, y_pitch=pitch, **kw)()
+        ys.append(y)
+    torch.cuda.synchronize()
+    assert torch.equal(ys[0], ys[1])
+    if opts == "bias_relu":
+        xr, wr = (x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()) if bf16 else (x, w)
+        ref = torch.relu(torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(0, 3, 1, 2), kw["bias"], padding=k // 2))
+        assert rel_err(ys[1], ref.permute(0, 2, 3, 1).reshape(m, cout)) < 2e-5
+
+
 def test_split_first_head_conv_equals_the_materialised_convolution(zsg):
     """a-6: conv(W, [feat | lang tiled | grid]) (mdl.py:69-104, 235-244) = conv(W_f, feat) + L[b, border class] + G[cell].
     Forward through zsg_conv_fwd with row_add against F.conv2d over the concatenated tensor, level by level; backward sums

@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace zsg {
@@ -666,6 +667,142 @@ __device__ __forceinline__ void epilogue_frag(const zsg_conv_params& p, const fl
     }
 }
 
+// EPI_FRAGX: the options of the generic epilogue (bias, row_add, ReLU mask, residual / residual_bf16, accumulate, ReLU; same
+// order of operations, bit-identical results) straight from the fragment registers, for plain [m, y_pitch] outputs with cout % 8 == 0.
+// The slab epilogue consumed its read operands two 16-byte loads at a time per lane (8 KB in flight per SM): the short-K data
+// gradients that add into the gradient stream between blocks (y += ..., or + residual) ran at half of what HBM allows
+// (10.2 k cycles per 128x128 tile against 5.3 k for its 128 KB).  Here a lane owns two rows x U column pairs per pass and
+// issues all 2U loads of an operand before using any: 16 x 8 B x 32 lanes x 8 warps = 32 KB in flight.
+template <int BN>
+__device__ __forceinline__ void epilogue_fragx(const zsg_conv_params& p, float (&acc)[BN / 2], int m0, int n0, int quadrant,
+                                               int half, int lane, int ablate) {
+  constexpr int U = BN / 16;
+  const int q = lane & 3, g = lane >> 2;
+  const int nbase = n0 + half * (BN / 2) + 2 * q;
+  if (ablate & 16) return;
+#define VX(hh, u) acc[h * 4 * U + 4 * (u) + 2 * (hh)]
+#define VY(hh, u) acc[h * 4 * U + 4 * (u) + 2 * (hh) + 1]
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int64_t off[2];                                         // y_pitch > 0 and even (pick_epilogue): every access is 8-byte aligned
+    bool ok[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int r = m0 + quadrant * 32 + 16 * h + 8 * hh + g;
+      ok[hh] = r < p.m;
+      off[hh] = (int64_t)r * p.y_pitch + nbase;
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (nbase + 8 * u >= p.cout) break;
+        const float2 b = __ldg(reinterpret_cast<const float2*>(p.bias + nbase + 8 * u));
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) { VX(hh, u) += b.x; VY(hh, u) += b.y; }
+      }
+    }
+    if (p.row_add) {                                        // language + grid terms of the first head conv (L2-resident tables)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (!ok[hh]) continue;
+        const int2 ra = __ldg(reinterpret_cast<const int2*>(p.row_add_idx) + (m0 + quadrant * 32 + 16 * h + 8 * hh + g));
+        float2 t0[U], t1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (nbase + 8 * u >= p.cout) break;
+          t0[u] = __ldg(reinterpret_cast<const float2*>(p.row_add + ra.x + nbase + 8 * u));
+          t1[u] = __ldg(reinterpret_cast<const float2*>(p.row_add + ra.y + nbase + 8 * u));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (nbase + 8 * u >= p.cout) break;
+          VX(hh, u) += t0[u].x + t1[u].x;
+          VY(hh, u) += t0[u].y + t1[u].y;
+        }
+      }
+    }
+    if (p.out_mask) {
+      float2 t[2][U];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          t[hh][u] = make_float2(1.f, 1.f);
+          if (ok[hh] && nbase + 8 * u < p.cout) t[hh][u] = __ldg(reinterpret_cast<const float2*>(p.out_mask + off[hh] + 8 * u));
+        }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!(t[hh][u].x > 0.f)) VX(hh, u) = 0.f;
+          if (!(t[hh][u].y > 0.f)) VY(hh, u) = 0.f;
+        }
+    }
+    if (p.residual) {
+      float2 t[2][U];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          t[hh][u] = make_float2(0.f, 0.f);
+          if (ok[hh] && nbase + 8 * u < p.cout) t[hh][u] = *reinterpret_cast<const float2*>(p.residual + off[hh] + 8 * u);
+        }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) { VX(hh, u) += t[hh][u].x; VY(hh, u) += t[hh][u].y; }
+    }
+    if (p.residual_bf16) {                                  // bf16 storage: the shortcut gradient is a bfloat16 tensor
+      uint32_t t[2][U];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          t[hh][u] = 0u;
+          if (ok[hh] && nbase + 8 * u < p.cout) t[hh][u] = *reinterpret_cast<const uint32_t*>(p.residual_bf16 + off[hh] + 8 * u);
+        }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          VX(hh, u) += __uint_as_float(t[hh][u] << 16);
+          VY(hh, u) += __uint_as_float(t[hh][u] & 0xFFFF0000u);
+        }
+    }
+    if (p.accumulate) {
+      float2 t[2][U];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          t[hh][u] = make_float2(0.f, 0.f);
+          if (ok[hh] && nbase + 8 * u < p.cout) t[hh][u] = *reinterpret_cast<const float2*>(p.y + off[hh] + 8 * u);
+        }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) { VX(hh, u) += t[hh][u].x; VY(hh, u) += t[hh][u].y; }
+    }
+    if (p.out_relu) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) { VX(hh, u) = fmaxf(VX(hh, u), 0.f); VY(hh, u) = fmaxf(VY(hh, u), 0.f); }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (!ok[hh]) continue;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (nbase + 8 * u >= p.cout) break;
+        *reinterpret_cast<float2*>(p.y + off[hh] + 8 * u) = make_float2(VX(hh, u), VY(hh, u));
+      }
+    }
+  }
+#undef VX
+#undef VY
+}
+
 // ragged rows (channel count or row offset not a multiple of 4: the [B, A, 5] head output): scalar, out of line.
 // (Arguments by value: a reference to the kernel parameter block forces a local-memory copy of it, and with ~6 KB of
 // L1 left every read of that copy is an L2 round trip.)
@@ -693,9 +830,10 @@ __device__ __noinline__ void epilogue_store_ragged(float* y, const float* out_ma
 // layers, which use neither, lost 13 % (measured).  Each product kernel now carries one of
 //   EPI_PLAIN   y = acc (fp32), optional BatchNorm statistics            -- every conv that feeds a BatchNorm, plain data gradients
 //   EPI_B16     y_bf16 = bf16(acc), optional statistics                  -- the same under bf16 storage
-//   EPI_GENERIC bias / ReLU / mask / residual(_bf16) / accumulate / ragged cout
+//   EPI_GENERIC bias / ReLU / mask / residual(_bf16) / accumulate / ragged cout (slab epilogue)
+//   EPI_FRAGX   the same options for cout % 8 == 0, from the fragment registers (epilogue_fragx)
 // and the register-path kernels keep EPI_ANY (PLAIN or GENERIC decided at run time, as before).
-enum { EPI_PLAIN = 0, EPI_B16 = 1, EPI_GENERIC = 2, EPI_ANY = 3 };
+enum { EPI_PLAIN = 0, EPI_B16 = 1, EPI_GENERIC = 2, EPI_ANY = 3, EPI_FRAGX = 4 };
 
 __host__ __device__ inline bool epilogue_is_plain(const zsg_conv_params& p) {
   return !p.bias && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && !p.out_relu && !p.row_add &&
@@ -715,15 +853,34 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
   const int quadrant = dw & 3, half = dw >> 2;
   const int row = quadrant * 32 + lane;
   int gchunk = 0, gkb0 = 0;
-  if (EPI == EPI_PLAIN || EPI == EPI_B16) {                 // register epilogue: no shared-memory transposition
+  if (EPI == EPI_PLAIN || EPI == EPI_B16 || EPI == EPI_FRAGX) {   // register epilogue: no shared-memory transposition
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n0 = (tile % tiles_n) * BN;
       const int m0 = (tile / tiles_n) * TM;
+      if (EPI == EPI_FRAGX && p.y_pitch > 0 && (p.residual || p.residual_bf16 || p.accumulate || p.out_mask)) {
+        // the epilogue's read operands of the NEXT tile are asked for now (one to four 128-byte lines per thread and
+        // operand), so that they are L2 hits when the loads are issued
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles) {
+          const int nn0 = (nt % tiles_n) * BN + half * (BN / 2), nm = (nt / tiles_n) * TM + row;
+          if (nm < p.m && nn0 < p.cout) {
+            const int64_t e = (int64_t)nm * p.y_pitch + nn0;
+            const int cols = (p.cout - nn0 < BN / 2) ? p.cout - nn0 : BN / 2;
+            if (p.residual_bf16) prefetch_l2(p.residual_bf16 + e);
+            for (int c = 0; c < cols; c += 32) {
+              if (p.residual) prefetch_l2(p.residual + e + c);
+              if (p.out_mask) prefetch_l2(p.out_mask + e + c);
+              if (p.accumulate) prefetch_l2(p.y + e + c);
+            }
+          }
+        }
+      }
       float acc[BN / 2];
       if (dw == 0 && lane == 0) trace(gkb0, 12);
       drain_loop_frag<BN, BF16>(pb, tmem_base, nkb, gkb0, quadrant, half, acc, gchunk, ablate);
       if (dw == 0 && lane == 0) trace(gkb0, 13);
-      epilogue_frag<BN, EPI == EPI_B16>(p, acc, m0, n0, quadrant, half, lane, ablate);
+      if (EPI == EPI_FRAGX) epilogue_fragx<BN>(p, acc, m0, n0, quadrant, half, lane, ablate);
+      else epilogue_frag<BN, EPI == EPI_B16>(p, acc, m0, n0, quadrant, half, lane, ablate);
       if (dw == 0 && lane == 0) trace(gkb0, 14);
       gkb0 += nkb;
     }
@@ -907,12 +1064,15 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
         v0.x += bias4.x; v0.y += bias4.y; v0.z += bias4.z; v0.w += bias4.w;
         v1.x += bias4.x; v1.y += bias4.y; v1.z += bias4.z; v1.w += bias4.w;
         const bool vec = ((p.cout & 3) == 0) && (((o0 | o1) & 3) == 0) && (n + 3 < p.cout);
+        int i00 = 0, i01 = 0, i10 = 0, i11 = 0;             // row_add offsets: shuffled by ALL lanes (`vec` may diverge on a ragged cout)
+        if (p.row_add) {
+          i00 = __shfl_sync(0xffffffffu, ra0, r0); i01 = __shfl_sync(0xffffffffu, ra1, r0);
+          i10 = __shfl_sync(0xffffffffu, ra0, r1); i11 = __shfl_sync(0xffffffffu, ra1, r1);
+        }
         if (vec) {
           const int64_t a0 = (int64_t)o0 + n, a1 = (int64_t)o1 + n;
           float4 q0, q1;
           if (p.row_add) {                                  // language + grid terms of the first head conv (L2-resident tables)
-            const int i00 = __shfl_sync(0xffffffffu, ra0, r0), i01 = __shfl_sync(0xffffffffu, ra1, r0);
-            const int i10 = __shfl_sync(0xffffffffu, ra0, r1), i11 = __shfl_sync(0xffffffffu, ra1, r1);
             if (k0) {
               q0 = __ldg(reinterpret_cast<const float4*>(p.row_add + i00 + n));
               q1 = __ldg(reinterpret_cast<const float4*>(p.row_add + i01 + n));
@@ -960,7 +1120,7 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
             if (k1) *reinterpret_cast<float4*>(p.y + a1) = v1;
           }
         } else {
-          if (p.row_add || (EPI == EPI_GENERIC && p.residual_bf16)) __trap();   // checked on the host: cout % 4 == 0; only unaligned row offsets get here
+          if ((k0 || k1) && (p.row_add || (EPI == EPI_GENERIC && p.residual_bf16))) __trap();   // checked on the host: cout % 4 == 0; only unaligned row offsets get here
           if (k0) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o0, n, v0);
           if (k1) epilogue_store_ragged(p.y, p.out_mask, p.residual, p.accumulate, p.out_relu, p.cout, o1, n, v1);
         }
@@ -2055,8 +2215,12 @@ static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
 }
 
 static inline int pick_epilogue(const zsg_conv_params& p) {
+  static const bool fragx = [] { const char* e = getenv("ZSG_EPI_FRAGX"); return !(e && e[0] == '0'); }();   // 0: slab epilogue (A/B runs)
   if (p.y_bf16) return EPI_B16;
-  return epilogue_is_plain(p) ? EPI_PLAIN : EPI_GENERIC;
+  if (epilogue_is_plain(p)) return EPI_PLAIN;
+  const uintptr_t ptrs = (uintptr_t)p.y | (uintptr_t)p.bias | (uintptr_t)p.out_mask | (uintptr_t)p.residual | (uintptr_t)p.row_add;
+  return (fragx && p.cout % 8 == 0 && p.y_pitch > 0 && p.y_pitch % 2 == 0 && (ptrs & 7) == 0 && ((uintptr_t)p.residual_bf16 & 3) == 0)
+             ? EPI_FRAGX : EPI_GENERIC;
 }
 
 template <int BN, int EPI>
@@ -2087,6 +2251,7 @@ static int launch_conv_async(const zsg_conv_params& p, cudaStream_t st) {
   switch (pick_epilogue(p)) {
     case EPI_PLAIN: return launch_conv_async_epi<BN, EPI_PLAIN>(p, st);
     case EPI_B16: return launch_conv_async_epi<BN, EPI_B16>(p, st);
+    case EPI_FRAGX: return launch_conv_async_epi<BN, EPI_FRAGX>(p, st);
     default: return launch_conv_async_epi<BN, EPI_GENERIC>(p, st);
   }
 }
@@ -2135,6 +2300,7 @@ static int launch_conv_bf16(const zsg_conv_params& p, cudaStream_t st) {
   switch (pick_epilogue(p)) {
     case EPI_PLAIN: return launch_conv_bf16_epi<BN, EPI_PLAIN>(p, st);
     case EPI_B16: return launch_conv_bf16_epi<BN, EPI_B16>(p, st);
+    case EPI_FRAGX: return launch_conv_bf16_epi<BN, EPI_FRAGX>(p, st);
     default: return launch_conv_bf16_epi<BN, EPI_GENERIC>(p, st);
   }
 }
