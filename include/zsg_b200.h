@@ -71,7 +71,8 @@ typedef struct {
                               applied after the bias and before residual / accumulate            */
   const float* residual;   /* optional, indexed like y                                      */
   int32_t accumulate;      /* y += result instead of y = result                             */
-  int32_t impl;            /* 0 = tcgen05 (product path), 1 = SIMT check kernel (tests only) */
+  int32_t impl;            /* 0 = tcgen05 (product path), 1 = SIMT check kernel (tests only); bf16 operand path: 2 / 3 force
+                              128- / 256-column tiles (tests; 0 chooses by layer size) */
   const float* x_lo;       /* optional (needs w_lo, no in_scale / in_relu): fp32 remainders of x after TF32 truncation
                               (zsg_split_act), same indexing as x.  The input operand then goes global -> shared by
                               cp.async with no register pass: the tensor core reads x itself as the TF32 high part */

@@ -123,6 +123,79 @@ def test_conv_bf16_statistics_and_run_to_run_bits(zsg):
     np.testing.assert_allclose(stats[:, 1].sum(0).cpu().numpy(), (y * y).sum(0).cpu().numpy(), rtol=1e-4)
 
 
+# B, cin, H, W, cout, k, stride, pad
+WIDE_CASES = [
+    (2, 256, 38, 38, 256, 3, 1, 1),                 # 36 K blocks, 23 tiles
+    (4, 64, 75, 75, 256, 1, 1, 0),                  # 176 tiles on 148 CTAs: 1 K block each, both accumulators, x_plain
+    (2, 256, 19, 19, 1024, 1, 1, 0),                # four column tiles
+    (2, 2048, 10, 10, 512, 3, 2, 1),                # K = 18432: whole-K accumulation in TMEM
+    (3, 128, 21, 17, 512, 3, 1, 1),                 # ragged last M tile
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES)
+@pytest.mark.parametrize("epi", ["plain_stats", "b16_stats", "bias_relu", "mask_residual_acc", "residual_bf16"])
+def test_conv_bf16_wide_tiles(zsg, case, epi):
+    """256-column tiles of the bf16 path (conv_tc.cu mma_loop_wide / conv_epilogue_wide; zsg_conv_params.impl = 3 forces
+    them, 2 forces 128 columns): against the fp32 convolution over the bf16-rounded operands, against the 128-column kernel
+    (same products, other accumulation order), BatchNorm statistics, every fragment-epilogue option, run-to-run bits."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case) + len(epi))
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    ref = nhwc(F.conv2d(rb(x), rb(w), None, stride=stride, padding=pad))
+    Ho, Wo = ref.shape[1], ref.shape[2]
+    m = B * Ho * Wo
+    ref = ref.reshape(m, cout)
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    xn, wk = nhwc(x), khwc(w)
+    xb, wb = image(ops, xn), image(ops, wk)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    kw, y0 = {}, float("nan")
+    if epi == "bias_relu":
+        kw = dict(bias=r(cout), out_relu=True)
+        ref = F.relu(ref + kw["bias"])
+    elif epi == "mask_residual_acc":
+        kw = dict(out_mask=r(m, cout), residual=r(m, cout), accumulate=True)
+        y0 = 0.25
+        ref = torch.where(kw["out_mask"] > 0, ref, torch.zeros_like(ref)) + kw["residual"] + y0
+    elif epi == "residual_bf16":
+        kw = dict(residual=r(m, cout).bfloat16())
+        ref = ref + kw["residual"].float()
+    parts = (m + 127) // 128 * 4
+    outs = []
+    for impl in (2, 3, 3):
+        if epi == "b16_stats":
+            y = torch.zeros(m, cout, dtype=torch.bfloat16, device="cuda")
+        else:
+            y = torch.full((m, cout), y0, device="cuda")
+        st = torch.zeros(parts, 2, cout, device="cuda") if epi.endswith("stats") else None
+        ops.ConvOp(xn, wk, y, rows, m, cin, cout, k, k, x_lo=xb, w_lo=wb, stats=st, y_pitch=cout, impl=impl,
+                   x_plain=(k == 1 and stride == 1), **kw)()
+        torch.cuda.synchronize()
+        outs.append((y, st))
+    assert torch.equal(outs[1][0], outs[2][0])                                   # run to run
+    if epi == "b16_stats":
+        d = (outs[1][0].float() - rb(ref)).abs().max() / ref.abs().max()
+        assert float(d) < 2.0 ** -7                                               # one bfloat16 ulp at the largest value
+        # vs the 128-column kernel: fp32 sums differing in the last bits round to the neighbouring bfloat16 now and then
+        a16, b16 = outs[0][0].float(), outs[1][0].float()
+        assert (a16 != b16).float().mean() < 2e-2 and bool(((a16 - b16).abs() <= 2.0 ** -7 * torch.maximum(a16.abs(), b16.abs()) + 1e-4).all())
+    else:
+        # whole-K accumulation in TMEM: the tensor core adds into the fp32 accumulator with truncation, a bias that grows
+        # with K (the 128-column kernel promotes every 8 K blocks into registers); K = 18432 is not a layer the product
+        # heuristic gives to this kernel
+        tol = TOL if cin * k * k <= 8192 else 5e-5
+        assert rel_err(outs[1][0], ref) < tol
+        assert rel_err(outs[1][0], outs[0][0]) < tol
+    if st is not None:
+        assert torch.equal(outs[1][1], outs[2][1])
+        np.testing.assert_allclose(outs[1][1][:, 0].sum(0).cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-4, atol=2e-3)
+        np.testing.assert_allclose(outs[1][1][:, 1].sum(0).cpu().numpy(), (ref * ref).sum(0).cpu().numpy(), rtol=1e-4)
+        np.testing.assert_allclose(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy(), rtol=1e-3, atol=1e-3)
+
+
 DGRAD_CASES = [(2, 64, 19, 19, 256, 3, 1, 1), (3, 128, 20, 18, 128, 3, 2, 1), (2, 256, 10, 10, 512, 1, 2, 0),
                (2, 2048, 10, 10, 256, 3, 2, 1), (2, 256, 5, 5, 45, 3, 1, 1), (2, 64, 8, 8, 64, 1, 1, 0)]
 

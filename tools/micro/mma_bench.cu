@@ -144,7 +144,22 @@ void run(const char* name, int sts_warps, int sts_per_iter, int iters = 6000, in
   cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {                                           // N = 128 vs 256, kind::f16 and kind::tf32, with concurrent store traffic
+    run<3, 128>("f16 SS", 0, 0);
+    run<3, 256>("f16 SS", 0, 0);
+    run<3, 128>("f16 SS + STS", 4, 0);
+    run<3, 256>("f16 SS + STS", 4, 0);
+    run<3, 128>("f16 SS + paced STS", 4, 40);
+    run<3, 256>("f16 SS + paced STS", 4, 40);
+    run<0, 128>("tf32 SS", 0, 0);
+    run<0, 256>("tf32 SS", 0, 0);
+    run<0, 128>("tf32 SS + STS", 4, 0);
+    run<0, 256>("tf32 SS + STS", 4, 0);
+    run<0, 128>("tf32 SS + paced STS", 4, 40);
+    run<0, 256>("tf32 SS + paced STS", 4, 40);
+    return 0;
+  }
   run<0, 128>("plain", 0, 0, 6000, 0);
   run<0, 128>("+commit per 12", 0, 0, 6000, 1);
   run<0, 128>("+fence+elect", 0, 0, 6000, 2);

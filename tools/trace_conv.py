@@ -10,7 +10,7 @@ import zsg_b200
 from zsg_b200 import ops, geometry, _lib
 _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libzsg_b200_trace.so")   # python zsgnet-pytorch_b200/build.py --trace
 
-def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False, impl=0):
+def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False, impl=0, bf16=False):
     x = torch.randn(B, H, H, cin, device="cuda")
     w = torch.randn(cout, k, k, cin, device="cuda") * 0.05
     hi, lo = torch.empty_like(w), torch.empty_like(w)
@@ -20,7 +20,9 @@ def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False, impl=0)
     M = B * H * H
     sc = torch.rand(cin, device="cuda") + 0.5 if pro else None
     sh = torch.randn(cin, device="cuda") if pro else None
-    if use_async:
+    if bf16:
+        op = ops.ConvOp(x, w, y, rows, M, cin, cout, k, k, w_lo=w.bfloat16(), x_lo=x.bfloat16(), impl=impl)
+    elif use_async:
         x_lo = torch.empty_like(x)
         ops.split_act(x, x_lo, M, cin)
         op = ops.ConvOp(x, hi, y, rows, M, cin, cout, k, k, w_lo=lo, x_lo=x_lo, impl=impl)
@@ -60,7 +62,9 @@ def run(B, cin, H, cout, k, label, nblk=120, pro=False, use_async=False, impl=0)
     per = (t[100, 11] - t[20, 11]) / 80.0
     print(f"average issue period over K blocks 20..100: {per:.0f} cycles (floor 768)")
 
-if "small" in sys.argv:
+if "bf16" in sys.argv:
+    run(128, 256, 44, 256, 3, "bf16 3x3 256->256", bf16=True, impl=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+elif "small" in sys.argv:
     run(64, 64, 75, 256, 1, "1x1 64->256 M=360000 cp.async path", use_async=True, impl=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 elif "async" in sys.argv:
     run(64, 256, 44, 256, 3, "3x3 256->256 cp.async path", use_async=True)

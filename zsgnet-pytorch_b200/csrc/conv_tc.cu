@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 #include <string.h>
 #include <stdlib.h>
+#include <math.h>
 #include "common.cuh"
 
 namespace zsg {
@@ -191,6 +192,10 @@ __device__ __forceinline__ void store_split(uint8_t* tile_hi, uint8_t* tile_lo, 
 constexpr int NGROUP = 2;            // producer groups
 constexpr int CHUNK_KB = 8;          // K-blocks per chunk: each of the two issuers accumulates its (up to) 4 in its own TMEM
                                      // accumulator before the drain warps promote both into fp32 registers
+#ifndef ZSG_CHUNK_KB_BF16
+#define ZSG_CHUNK_KB_BF16 8
+#endif
+template <bool BF16> struct ChunkKB { static constexpr int V = BF16 ? ZSG_CHUNK_KB_BF16 : CHUNK_KB; };
 constexpr int NDRAIN = 256;          // drain / epilogue threads
 constexpr int DRAIN_WARP0 = 8;
 constexpr int MMA_WARP = 16;           // issuer warps: 16 and 17 (TMEM is allocated / freed by 16)
@@ -208,14 +213,14 @@ struct Smem {
   static constexpr int ES = BF16 ? 2 : 4;                   // operand element size in bytes
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = NIMG * (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int STAGES = BF16 ? 6 : (BN >= 128 ? 3 : 4);
+  static constexpr int STAGES = BF16 ? (BN > 128 ? 4 : 6) : (BN >= 128 ? 3 : 4);
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
   static constexpr int ROWS_OFF = TILES_BYTES;              // TM row entries (fwd) / 2 groups x 2 x 32|64 (wgrad)
   static constexpr int BAR_OFF = ROWS_OFF + NGROUP * TM * 16;
   static constexpr int EPI_OFF = BAR_OFF + 256;             // epilogue staging: 8 warps x 32 rows x 20 floats
   static constexpr int EPI_WARP_BYTES = 32 * 20 * 4;
   static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_BYTES + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = 4 * BN;                  // (chunk parity) x (issuer) accumulators
+  static constexpr int TMEM_COLS = BN > 128 ? 512 : 4 * BN;   // (chunk parity) x (issuer) accumulators; BN = 256: two, by tile parity
 };
 
 constexpr int MAX_STAGES = 8;
@@ -416,7 +421,7 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
     // issuer with nothing to do in a run of chunks (single-K-block tiles: it owns every other tile, always with the same
     // accumulator) would otherwise complete acc_full phases faster than the drain warps consume them -- their parity wait
     // then misses a phase and hangs (seen on the bf16 path, where K = 64 is ONE K block per tile).
-    if (kb % CHUNK_KB == 0) mbar_wait(pb.acc_empty(acc), ((is.chunk >> 1) & 1u) ^ 1u, 100 + is.g);
+    if (kb % ChunkKB<BF16>::V == 0) mbar_wait(pb.acc_empty(acc), ((is.chunk >> 1) & 1u) ^ 1u, 100 + is.g);
     constexpr uint32_t G = IssueGroup<BF16>::G;
     if (((is.g / G) & 1u) == is.w) {
       trace(is.g, 8);
@@ -444,7 +449,7 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
       ++mine;
     }
     if (++is.stage == (uint32_t)S::STAGES) { is.stage = 0; is.phase ^= 1u; }
-    if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) {   // chunk closed: my part of it (possibly empty) is complete
+    if (kb % ChunkKB<BF16>::V == ChunkKB<BF16>::V - 1 || kb == nkb - 1) {   // chunk closed: my part of it (possibly empty) is complete
       umma_commit(pb.acc_full(acc));
       ++is.chunk;
       mine = 0;
@@ -460,11 +465,11 @@ __device__ __forceinline__ void drain_loop(const PipeBars& pb, uint32_t tmem_bas
   // The first accumulator of a tile that holds anything is loaded straight into `acc` (all of its x16 loads in flight, one
   // wait); later ones go through 16 temporaries, one load at a time.
   bool fresh = true;
-  const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+  const int nchunks = (nkb + ChunkKB<BF16>::V - 1) / ChunkKB<BF16>::V;
   for (int cc = 0; cc < nchunks; ++cc, ++gchunk) {
     const int c = gchunk;
-    const int k0 = cc * CHUNK_KB;
-    const int n = (nkb - k0 < CHUNK_KB) ? nkb - k0 : CHUNK_KB;
+    const int k0 = cc * ChunkKB<BF16>::V;
+    const int n = (nkb - k0 < ChunkKB<BF16>::V) ? nkb - k0 : ChunkKB<BF16>::V;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       const int a = (c & 1) * 2 + w;
@@ -542,11 +547,11 @@ __device__ __forceinline__ void drain_loop_frag(const PipeBars& pb, uint32_t tme
                                                 float (&acc)[BN / 2], int& gchunk, int ablate = 0) {
   constexpr int U = BN / 16;                                // 8-column units of the warp's BN / 2 columns
   bool fresh = true;
-  const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+  const int nchunks = (nkb + ChunkKB<BF16>::V - 1) / ChunkKB<BF16>::V;
   for (int cc = 0; cc < nchunks; ++cc, ++gchunk) {
     const int c = gchunk;
-    const int k0 = cc * CHUNK_KB;
-    const int n = (nkb - k0 < CHUNK_KB) ? nkb - k0 : CHUNK_KB;
+    const int k0 = cc * ChunkKB<BF16>::V;
+    const int n = (nkb - k0 < ChunkKB<BF16>::V) ? nkb - k0 : ChunkKB<BF16>::V;
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       const int a = (c & 1) * 2 + w;
@@ -838,6 +843,91 @@ enum { EPI_PLAIN = 0, EPI_B16 = 1, EPI_GENERIC = 2, EPI_ANY = 3, EPI_FRAGX = 4 }
 __host__ __device__ inline bool epilogue_is_plain(const zsg_conv_params& p) {
   return !p.bias && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && !p.out_relu && !p.row_add &&
          (p.cout & 3) == 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BN = 256 tiles of the bf16 path ("wide" kernel).  Measured on B200 (tools/micro/mma_bench.cu, tools/trace_conv.py): a
+// 128x128x16 kind::f16 MMA issues every 75.6 cycles (85 % of the pipe), a 128x256x16 one every 128.0 (100 %); and in the
+// 128-column kernel the PRODUCERS bound the big bf16 layers -- a producer group needs ~1.8 k cycles per K block (950 per K
+// block over the two groups) against 300 cycles of MMA.  A 256-column tile does twice the MMA work per gathered A tile.
+// Pipeline: ONE issuing thread (a K block is 4 x 128 cycles, the ~50 instructions between K blocks hide behind the two MMAs
+// the pipe queues), the whole K extent accumulates in TMEM (no chunked promotion: its truncation bias, 1e-5 at K = 2304, is
+// far below a bfloat16 ulp), two 256-column accumulators taken by tile parity, and the drain warps run the fragment
+// epilogues of the 128-column kernel over their 128 columns in two passes of 64 straight out of TMEM.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void mma_loop_wide(uint8_t* sm, const PipeBars& pb, uint32_t tmem_base, int nkb, int total_tiles,
+                                              int ablate) {
+  using S = Smem<BN, true>;
+  const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);   // K-major, SBO = 1024 B, 128-byte swizzle
+  const uint32_t lo0 = ((smem_u32(sm) >> 4) & 0x3FFFu) | (1u << 16);
+  uint32_t stage = 0, phase = 0, nt = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++nt) {
+    const uint32_t a = nt & 1u;
+    mbar_wait(pb.acc_empty(a), ((nt >> 1) & 1u) ^ 1u, 100 + nt);      // drained two tiles ago
+    tc_fence_after();
+    for (int kb = 0; kb < nkb; ++kb) {
+      if (!(ablate & 1)) mbar_wait(pb.full(stage), phase, 1000 + kb);
+      fence_proxy_async();
+      tc_fence_after();
+      issue_kblock_bf16<BN, false>(tmem_base + a * BN, lo0 + stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi, kb == 0 ? 0u : 1u);
+      umma_commit(pb.empty(stage));
+      if (++stage == (uint32_t)S::STAGES) { stage = 0; phase ^= 1u; }
+    }
+    umma_commit(pb.acc_full(a));
+  }
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void conv_epilogue_wide(const zsg_conv_params& p, const PipeBars& pb, uint32_t tmem_base, int warp,
+                                                   int lane, int tiles_n, int total_tiles, int ablate) {
+  static_assert(BN == 256 && (EPI == EPI_PLAIN || EPI == EPI_B16 || EPI == EPI_FRAGX), "wide kernel: fragment epilogues only");
+  const int dw = warp - DRAIN_WARP0;
+  const int quadrant = dw & 3, half = dw >> 2;              // TMEM lanes, 128-column half of the tile
+  const int row = quadrant * 32 + lane;
+  uint32_t nt = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++nt) {
+    const int n0 = (tile % tiles_n) * BN + half * 128;
+    const int m0 = (tile / tiles_n) * TM;
+    if (EPI == EPI_FRAGX && (p.residual || p.residual_bf16 || p.accumulate || p.out_mask)) {
+      const int ntile = tile + gridDim.x;                   // L2 prefetch of the next tile's read operands (see conv_epilogue)
+      if (ntile < total_tiles) {
+        const int nn0 = (ntile % tiles_n) * BN + half * 128, nm = (ntile / tiles_n) * TM + row;
+        if (nm < p.m && nn0 < p.cout) {
+          const int64_t e = (int64_t)nm * p.y_pitch + nn0;
+          const int cols = (p.cout - nn0 < 128) ? p.cout - nn0 : 128;
+          for (int c = 0; c < cols; c += 32) {
+            if (p.residual_bf16 && (c & 63) == 0) prefetch_l2(p.residual_bf16 + e + c);
+            if (p.residual) prefetch_l2(p.residual + e + c);
+            if (p.out_mask) prefetch_l2(p.out_mask + e + c);
+            if (p.accumulate) prefetch_l2(p.y + e + c);
+          }
+        }
+      }
+    }
+    const uint32_t a = nt & 1u;
+    mbar_wait(pb.acc_full(a), (nt >> 1) & 1u, 2000 + nt);
+    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float acc[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quadrant * 32) << 16) + a * BN + (uint32_t)(half * 128 + j * 64);
+      if (!(ablate & 2)) {
+        tmem_ld_frag<8>(taddr, acc);
+        tmem_ld_frag<8>(taddr + (16u << 16), acc + 32);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      }
+      if (j == 1) {                                         // every TMEM read of this tile is done: the accumulator may be reused
+        tc_fence_before();
+        mbar_arrive(pb.acc_empty(a));
+      }
+      if (EPI == EPI_FRAGX) epilogue_fragx<128>(p, acc, m0, n0, quadrant, j, lane, ablate);
+      else epilogue_frag<128, EPI == EPI_B16>(p, acc, m0, n0, quadrant, j, lane, ablate);
+    }
+  }
 }
 
 template <int BN, bool BF16 = false, int EPI = EPI_ANY>
@@ -1530,8 +1620,11 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
   PipeBars pb = setup_pipeline<BN, BF16>(sm, warp, lane, plain_a ? 1 : NPROD + 1);
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
 
+  static_assert(BN <= 128 || (BF16 && EPI != EPI_GENERIC), "256-column tiles: bf16 path, fragment epilogues");
   if (warp >= MMA_WARP) {
-    if (elect_one()) {
+    if (BN > 128) {                                         // wide kernel: one issuing thread (warp 17 idles)
+      if (warp == MMA_WARP && elect_one()) mma_loop_wide<BN>(sm, pb, tmem_base, nkb, total_tiles, ablate);
+    } else if (elect_one()) {
       Issuer is = issuer_init<BN, BF16>(warp - MMA_WARP);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
         mma_loop<BN, false, BF16>(sm, pb, tmem_base, nkb, is, false, ablate);
@@ -1654,7 +1747,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
     }
   } else if (warp >= DRAIN_WARP0) {
     regs_take_drain();
-    conv_epilogue<BN, BF16, EPI>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
+    if constexpr (BN > 128) conv_epilogue_wide<BN, EPI>(p, pb, tmem_base, warp, lane, tiles_n, total_tiles, ablate);
+    else conv_epilogue<BN, BF16, EPI>(p, sm, pb, tmem_base, warp, lane, nkb, tiles_n, total_tiles, ablate);
   }
   tc_fence_before();
   __syncthreads();
@@ -2295,8 +2389,34 @@ static int launch_conv_bf16_epi(const zsg_conv_params& p, cudaStream_t st) {
   conv_tc_async_kernel<BN, true, EPI><<<grid, NTHREADS2, S::TOTAL, st>>>(p, tm_w, tm_unused, tm_a, tm_unused);
   return check_launch("zsg_conv_fwd(bf16)");
 }
+// 256-column tiles when the layer has them and they pay: twice the MMA work per gathered A tile and the full issue rate, but
+// half as many tiles -- the partial last wave of the persistent grid weighs more.  wide_gain = measured speed ratio of the two
+// kernels on full waves (tools/time_big.py).
+static bool use_wide_bf16(const zsg_conv_params& p, int epi) {
+  static const int mode = [] { const char* e = getenv("ZSG_WIDE_BF16"); return e ? atoi(e) : 1; }();   // 0 off, 1 heuristic, 2 whenever legal
+  if (epi == EPI_GENERIC || p.cout % 256 != 0 || p.impl == 2) return false;      // impl 2 / 3 (tests): 128- / 256-column tiles
+  if (p.impl == 3) return true;
+  if (mode == 0) return false;
+  if (mode == 2) return true;
+  const double tm = (p.m + TM - 1) / TM, sms = num_sms();
+  const double t128 = tm * (p.cout / 128), t256 = tm * (p.cout / 256);
+  const double eff128 = t128 / (ceil(t128 / sms) * sms), eff256 = t256 / (ceil(t256 / sms) * sms);
+  const double wide_gain = (p.r * p.s > 1) ? 1.4 : 1.1;    // gather-fed 3x3 layers 1.3-1.5x, TMA-fed 1x1 layers 1.0-1.1x (epilogue-bound)
+  return eff256 * wide_gain > eff128;
+}
+
 template <int BN>
 static int launch_conv_bf16(const zsg_conv_params& p, cudaStream_t st) {
+  if constexpr (BN == 128) {
+    const int epi = pick_epilogue(p);
+    if (use_wide_bf16(p, epi)) {
+      switch (epi) {
+        case EPI_PLAIN: return launch_conv_bf16_epi<256, EPI_PLAIN>(p, st);
+        case EPI_B16: return launch_conv_bf16_epi<256, EPI_B16>(p, st);
+        default: return launch_conv_bf16_epi<256, EPI_FRAGX>(p, st);
+      }
+    }
+  }
   switch (pick_epilogue(p)) {
     case EPI_PLAIN: return launch_conv_bf16_epi<BN, EPI_PLAIN>(p, st);
     case EPI_B16: return launch_conv_bf16_epi<BN, EPI_B16>(p, st);
