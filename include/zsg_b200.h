@@ -122,7 +122,7 @@ typedef struct {
   const float* in_shift;
   int32_t in_relu;
   int32_t split_k;         /* 0 = choose automatically                                       */
-  int32_t impl;
+  int32_t impl;            /* as in zsg_conv_params (bf16 path: 2 / 3 force 128- / 256-column tiles) */
   const float* x_lo;       /* optional pair (both or none; no in_scale / in_relu): TF32 remainders of x and dy      */
   const float* dy_lo;      /* (zsg_split_act); operands then go global -> shared by cp.async                         */
   int32_t dy_pitch;        /* > 0: rows[i].out == i * dy_pitch for every row (dy is a plain [m, dy_pitch] matrix, true for

@@ -292,6 +292,38 @@ def test_conv_wgrad_bf16_vs_torch(zsg, case, split_k):
     assert rel_err(dw, khwc(w.grad)) < 3e-5
 
 
+WIDE_WGRAD_CASES = [(2, 64, 19, 19, 256, 3, 1, 1), (4, 1024, 19, 19, 256, 1, 1, 0), (2, 520, 10, 10, 256, 3, 1, 1),
+                    (1, 256, 3, 3, 256, 3, 1, 1), (6, 256, 44, 44, 256, 3, 1, 1), (3, 128, 40, 36, 512, 3, 2, 1),
+                    (70, 64, 10, 10, 256, 1, 1, 0)]
+
+
+@pytest.mark.parametrize("case", WIDE_WGRAD_CASES)
+def test_conv_wgrad_bf16_wide_tiles(zsg, case):
+    """wgrad_bf16_wide_kernel (256-column tiles, persistent over units of <= 64 K blocks; zsg_wgrad_params.impl = 3 forces
+    it): against autograd over the bf16-rounded operands and against the 128-column kernel; several units per CTA, a unit
+    of one K block, ragged last K block, row tiles past Kt."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda().requires_grad_(True)
+    y = F.conv2d(rb(x), w, None, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(rb(dy))
+    Ho, Wo = y.shape[2], y.shape[3]
+    rows = geo.conv_rows(B, H, W, cin, Ho, Wo, cout, stride, pad).cuda()
+    xn, dyn = nhwc(x), nhwc(dy)
+    xb, dyb = image(ops, xn), image(ops, dyn)
+    outs = []
+    for impl in (2, 3):
+        dw = torch.zeros(cout, k, k, cin, device="cuda")
+        ops.WgradOp(xn, dyn, dw, rows, B * Ho * Wo, cin, cout, k, k, x_lo=xb, dy_lo=dyb, dy_pitch=cout, impl=impl)()
+        torch.cuda.synchronize()
+        outs.append(dw)
+    assert rel_err(outs[1], khwc(w.grad)) < 3e-5
+    assert rel_err(outs[1], outs[0]) < 3e-5
+
+
 def test_bn_kernels_write_bf16_images(zsg):
     """bn_apply / bn_bwd_apply write the bf16 image of their output next to the fp32 tensor."""
     ops, _ = zsg

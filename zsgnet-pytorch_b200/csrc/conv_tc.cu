@@ -2185,6 +2185,164 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
 }
 
 // ============================================================================================
+// bf16 weight gradient over 256-column tiles ("wide", see mma_loop_wide): the gathered x tile -- the side that costs
+// producer time -- feeds twice the MMA work.  Persistent over work units (column tile, row tile, pixel split); a unit is at
+// most WG_UNIT_KB K blocks, accumulated in TMEM without promotion (256 MMAs: the truncation bias stays at a few 1e-6), one
+// issuing thread, two accumulators by unit parity, and the drain warps reduce a finished unit into dw (fp32 red.add, lanes
+// along j) while the MMAs of the next unit run.
+// ============================================================================================
+constexpr int WG_UNIT_KB = 64;
+__global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_wide_kernel(const zsg_wgrad_params p, int kb_per_split, int splits,
+                                                                       const __grid_constant__ CUtensorMap tm_dy) {
+  constexpr int BN = 256;
+  using S = Smem<BN, true>;
+  constexpr int KBP = 64;                                   // pixels per K block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Kt = p.r * p.s * p.cin;                         // rows of D
+  const int tiles_n = (p.cout + BN - 1) / BN, tiles_j = (Kt + TM - 1) / TM;
+  const int nkb_total = (p.m + KBP - 1) / KBP;
+  const int units = tiles_n * tiles_j * splits;             // unit u: split fastest (neighbouring CTAs share the x / dy pixels' tile rows in L2)
+  PipeBars pb = setup_pipeline<BN, true>(sm, warp, lane, NPROD + 1);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sm + S::BAR_OFF + TMEM_SLOT_OFF);
+#define WG_UNIT(u)                                                                         \
+  const int sp = (u) % splits, tj = ((u) / splits) % tiles_j, tn = (u) / (splits * tiles_j); \
+  const int kb_begin = sp * kb_per_split;                                                  \
+  const int nkb = (kb_begin + kb_per_split > nkb_total ? nkb_total : kb_begin + kb_per_split) - kb_begin; \
+  const int n0 = tn * BN, j0 = tj * TM;
+
+  if (warp >= MMA_WARP) {
+    if (warp == MMA_WARP && elect_one()) {
+      const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);                  // MN-major: SBO = 1024 B, 128-byte swizzle
+      const uint32_t lo0 = ((smem_u32(sm) >> 4) & 0x3FFFu) | (512u << 16);     // LBO = 8192 B between channel atoms
+      uint32_t stage = 0, phase = 0, nu = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++nu) {
+        WG_UNIT(u)
+        (void)n0; (void)j0;
+        const uint32_t a = nu & 1u;
+        mbar_wait(pb.acc_empty(a), ((nu >> 1) & 1u) ^ 1u, 100 + nu);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(pb.full(stage), phase, 1000 + kb);
+          fence_proxy_async();
+          tc_fence_after();
+          issue_kblock_bf16<BN, true>(tmem_base + a * BN, lo0 + stage * (uint32_t)(S::STAGE_BYTES >> 4), desc_hi, kb == 0 ? 0u : 1u);
+          umma_commit(pb.empty(stage));
+          if (++stage == (uint32_t)S::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(pb.acc_full(a));
+      }
+    }
+    __syncwarp();
+  } else if (warp < DRAIN_WARP0) {
+    regs_release_producer();
+    const int group = warp >> 2;
+    const int t = tid & 127;
+    const int mc = t & 15;                                  // 16-byte chunk (8 channels) of the 128-channel tile row
+    const int ps = t >> 4;                                  // pixel sub-index 0..7 (= pixel & 7: the swizzle key)
+    const uint32_t toff = (mc >> 3) * 8192 + ps * 128 + (((mc & 7) ^ ps) << 4);   // + q * 1024 (8 pixels x 128 B)
+    const int4* rows = reinterpret_cast<const int4*>(p.rows);
+    int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 128;      // [2][64] entries per group
+    const uint32_t tiles0 = smem_u32(sm);
+    int g0 = 0;                                             // K blocks of this CTA before the current unit (ring position)
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      WG_UNIT(u)
+      const int j = j0 + mc * 8;                            // this thread's 8 channels j..j+7 of D's row index = (tap, c)
+      const bool jvalid = j < Kt;
+      int tap = 0, c = 0, tr = 0, ts = 0;
+      if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
+      const uint16_t* xb = p.x_bf16 + c;
+      const int first = (group - g0) & 1;                   // K blocks with (g0 + i) % NGROUP == group
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");   // the previous unit's entries have been read
+      if (first < nkb && t < KBP) {
+        int4 e = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
+        const int pix = (kb_begin + first) * KBP + t;
+        if (pix < p.m) e = __ldg(rows + pix);
+        ent[t] = e;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      int it = 0;
+      for (int i = first; i < nkb; i += NGROUP, ++it) {
+        const int g = g0 + i;
+        const int s = g % S::STAGES;
+        const int4* eb = ent + (it & 1) * KBP;
+        int4 e_next = make_int4(0, 0, 0, 0);                 // entries of my next K block: in flight during this one
+        const bool has_next = i + NGROUP < nkb;
+        if (has_next && t < KBP) {
+          const int pix = (kb_begin + i + NGROUP) * KBP + t;
+          if (pix < p.m) e_next = __ldg(rows + pix);
+        }
+        mbar_wait(pb.empty(s), ((g / S::STAGES) & 1) ^ 1, 5000 + i);
+        const uint32_t a_tile = tiles0 + s * S::STAGE_BYTES;
+        const uint32_t b_tile = a_tile + A_TILE_BYTES;
+        if ((t >> 5) == 0) {
+          if (elect_one()) {
+            const int pix0 = (kb_begin + i) * KBP;
+            mbar_arrive_expect_tx(pb.full(s), S::B_TILE_BYTES);
+#pragma unroll
+            for (int atom = 0; atom < BN / 64; ++atom) tma_load_2d(b_tile + atom * 8192, &tm_dy, n0 + atom * 64, pix0, pb.full(s));
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int4 e = eb[q * 8 + ps];                     // pixel q * 8 + ps of the K block
+          const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
+          const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+          const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
+          cp_async16(a_tile + toff + q * 1024, xb + ao, oka ? 16u : 0u);
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
+        if (has_next) {
+          if (t < KBP) ent[((it + 1) & 1) * KBP + t] = e_next;
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+        }
+      }
+      g0 += nkb;
+    }
+  } else {
+    // drain + epilogue: lanes own consecutive j => coalesced reductions into dw[n][j]
+    regs_take_drain();
+    const int dw = warp - DRAIN_WARP0;
+    const int quadrant = dw & 3, half = dw >> 2;
+    uint32_t nu = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++nu) {
+      WG_UNIT(u)
+      (void)nkb;
+      const uint32_t a = nu & 1u;
+      mbar_wait(pb.acc_full(a), (nu >> 1) & 1u, 2000 + nu);
+      tc_fence_after();
+      const int j = j0 + quadrant * 32 + lane;
+#pragma unroll
+      for (int jp = 0; jp < 2; ++jp) {
+        float acc[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quadrant * 32) << 16) + a * BN + (uint32_t)(half * 128 + jp * 64);
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) tmem_ld16_nowait(taddr + cb * 16, acc + cb * 16);
+        tmem_ld_wait();
+        if (jp == 1) {
+          tc_fence_before();
+          mbar_arrive(pb.acc_empty(a));
+        }
+        if (j < Kt) {
+#pragma unroll
+          for (int q = 0; q < 64; ++q) {
+            const int nn = n0 + half * 128 + jp * 64 + q;
+            if (nn < p.cout) atomicAdd(p.dw + (int64_t)nn * Kt + j, acc[q]);
+          }
+        }
+      }
+    }
+  }
+#undef WG_UNIT
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ============================================================================================
 // SIMT check kernels (tests only): the same gather semantics in plain fp32 FMAs, one thread
 // per output element.  Independent of every tcgen05 / smem-layout assumption above.
 // ============================================================================================
@@ -2522,6 +2680,47 @@ static int launch_wgrad_bf16(const zsg_wgrad_params& p, cudaStream_t st) {
   return check_launch("zsg_conv_wgrad(bf16)");
 }
 
+// 256-column tiles for the bf16 weight gradient (wgrad_bf16_wide_kernel) when the layer has them: units of at most
+// WG_UNIT_KB K blocks, the unit length chosen so that the persistent grid ends on a full wave.
+static int launch_wgrad_bf16_wide(const zsg_wgrad_params& p, cudaStream_t st) {
+  using S = Smem<256, true>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) { set_error("wgrad(bf16 wide): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ZSG_ECUDA; }
+    attr_done = true;
+  }
+  CUtensorMap tm_dy;
+  if (int rc = make_bf16_map(&tm_dy, p.dy_bf16, p.m, p.dy_pitch, 64, "dy")) return rc;
+  const int Kt = p.r * p.s * p.cin;
+  const int tiles = (p.cout / 256) * ((Kt + TM - 1) / TM);
+  const int nkb = (p.m + 63) / 64;
+  const int sms = num_sms();
+  int best_per = WG_UNIT_KB;
+  double best_cost = -1.0;
+  for (int per = WG_UNIT_KB; per >= 24 && per >= 1; --per) {
+    const int splits = (nkb + per - 1) / per;
+    const double units = (double)tiles * splits, waves = ceil(units / sms);
+    const double cost = waves * (per + 6);                  // + per-unit overhead in K-block times
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_per = per; }
+  }
+  int per = nkb < best_per ? nkb : best_per;
+  const int splits = (nkb + per - 1) / per;
+  const int units = tiles * splits;
+  const int grid = units < sms ? units : sms;
+  wgrad_bf16_wide_kernel<<<grid, NTHREADS2, S::TOTAL, st>>>(p, per, splits, tm_dy);
+  return check_launch("zsg_conv_wgrad(bf16 wide)");
+}
+static bool use_wide_wgrad_bf16(const zsg_wgrad_params& p) {
+  static const int mode = [] { const char* e = getenv("ZSG_WIDE_WGRAD_BF16"); return e ? atoi(e) : 1; }();   // 0 off, 1 heuristic, 2 whenever legal
+  if (p.cout % 256 != 0 || p.impl == 2 || p.split_k > 0 || p.dy_pitch <= 0) return false;
+  if (p.impl == 3 || mode == 2) return true;
+  if (mode == 0) return false;
+  const int Kt = p.r * p.s * p.cin;
+  const double units = (double)(p.cout / 256) * ((Kt + TM - 1) / TM) * (((p.m + 63) / 64 + WG_UNIT_KB - 1) / WG_UNIT_KB);
+  return units >= 32.0;                                     // measured (tools/step_time.py): wide wherever legal beats a two-wave threshold by 1 ms / step
+}
+
 }  // namespace zsg
 
 using namespace zsg;
@@ -2610,6 +2809,7 @@ extern "C" int zsg_conv_wgrad(const zsg_wgrad_params* pp, zsg_stream_t stream) {
     ZSG_REQUIRE(p.dy_pitch >= p.cout && p.dy_pitch % 8 == 0,
                 "zsg_conv_wgrad: the bf16 path needs dy as a plain [m, dy_pitch] matrix, dy_pitch >= cout and a multiple of 8");
     ZSG_REQUIRE((((uintptr_t)p.x_bf16 | (uintptr_t)p.dy_bf16) & 15) == 0, "zsg_conv_wgrad: bf16 operands must be 16-byte aligned");
+    if (use_wide_wgrad_bf16(p)) return launch_wgrad_bf16_wide(p, st);
     return p.cout <= 64 ? launch_wgrad_bf16<64>(p, st) : launch_wgrad_bf16<128>(p, st);
   }
   if (p.x_lo || p.dy_lo) {
