@@ -266,11 +266,14 @@ def measure(model, dtype, B, steps, warmup, rank, world, local_rank, want_e2e=Tr
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(f"{dom}@{dtype}@bs{B}", {}).get("dram_bytes_per_launch")
-    note = ("fp32 path = 3xTF32: 3 kind::tf32 MMAs per algorithmic product; a 128x128x8 kind::tf32 MMA takes 64 cycles = 4096 "
-            "FLOP/cycle/SM (tools/micro/mma_bench.cu), so the ceiling of this arithmetic is 148 x 4096 x clock / 3 = 373 "
-            "TFLOP/s at 1.845 GHz = 0.27 of the bf16 peak used here" if dtype == "fp32" else
-            "bf16 path: one kind::f16 MMA per product (8192 FLOP/cycle/SM), fp32 accumulation in TMEM; operands are the bf16 "
-            "images of fp32 tensors")
+    note = ("fp32 path = 3xTF32: 3 kind::tf32 MMAs per algorithmic product, 128-column tiles (the fp32 running sums of the "
+            "chunked promotion fill the drain warps' registers at 128 columns).  Measured (tools/micro/mma_bench.cu): a "
+            "128x128x8 kind::tf32 MMA issues every 75.6 cycles = 3468 FLOP/cycle/SM (a 128x256x8 one every 128.0 = 4096), so "
+            "the ceiling of this arithmetic and tile is 148 x 3468 x clock / 3 = 316 TFLOP/s at 1.845 GHz = 0.23 of the bf16 "
+            "peak used here (373 = 0.27 with 256-column tiles)" if dtype == "fp32" else
+            "bf16 path: one kind::f16 MMA per product, fp32 accumulation in TMEM; 256-column tiles (8192 FLOP/cycle/SM, one "
+            "issuing thread, whole-K accumulation) where the layer has a multiple of 256 output channels, 128-column tiles "
+            "(6936 FLOP/cycle/SM) elsewhere")
     roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": f"{pk['src']} bf16 sustained (MEASURED_PEAKS.json)",
             "launches_per_step": d["launches"] / psteps, "avg_launch_ms": d["ms"] / d["launches"],

@@ -296,7 +296,10 @@ __device__ __forceinline__ PipeBars setup_pipeline(uint8_t* sm, int warp, int la
 #ifndef ZSG_ISSUE_GROUP_BF16
 #define ZSG_ISSUE_GROUP_BF16 1
 #endif
-template <bool BF16> struct IssueGroup { static constexpr uint32_t G = BF16 ? ZSG_ISSUE_GROUP_BF16 : 1; };
+#ifndef ZSG_ISSUE_GROUP_FP32
+#define ZSG_ISSUE_GROUP_FP32 1
+#endif
+template <bool BF16> struct IssueGroup { static constexpr uint32_t G = BF16 ? ZSG_ISSUE_GROUP_BF16 : ZSG_ISSUE_GROUP_FP32; };
 template <bool BF16>
 __device__ __forceinline__ int issuer_count(int g0, int n, int w) {     // K blocks g0 .. g0 + n - 1 owned by issuer w
   constexpr int G = (int)IssueGroup<BF16>::G;
@@ -429,7 +432,11 @@ __device__ __forceinline__ void mma_loop(uint8_t* sm, const PipeBars& pb, uint32
       trace(is.g, 9);
       fence_proxy_async();                                  // cp.async-filled tiles (generic proxy) -> tensor core (async proxy)
       if (is.g > 0 && is.g % G == 0 && !(ablate & 8)) {    // first K block of my group: my turn
+#ifdef ZSG_TOKEN_SPIN
+        while (!mbar_try_wait(pb.token(is.w), is.tokens & 1u)) {}
+#else
         mbar_wait(pb.token(is.w), is.tokens & 1u, 4000 + is.g);
+#endif
         ++is.tokens;
       }
       trace(is.g, 10);
