@@ -103,6 +103,10 @@ typedef struct {
   const float* row_add;    /* optional pair: result[row][n] += row_add[row_add_idx[2*row] + n] + row_add[row_add_idx[2*row+1] + n]  */
   const int32_t* row_add_idx; /* after the bias, before the ReLU (the language and grid terms of the first head conv); cout % 4  */
                            /* == 0, offsets % 4 == 0                                                                              */
+  float* y_lo;             /* optional, one of the two: the GEMM operand image of the OUTPUT, written by the epilogue next to y     */
+  uint16_t* y_img_bf16;    /* (indexed like y): y_lo = TF32 remainders as zsg_split_act writes them, y_img_bf16 = the bfloat16 copy  */
+                           /* as zsg_cast_bf16.  The consumer of y (next conv, weight / data gradient) then needs no image pass.   */
+                           /* Plain [m, y_pitch] outputs with cout % 8 == 0 and y_pitch % 2 == 0 on the operand-image paths only   */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`

@@ -1126,6 +1126,43 @@ def test_conv_fragment_epilogue_equals_slab_epilogue(zsg, case, bf16, opts):
         assert rel_err(ys[1], ref.permute(0, 2, 3, 1).reshape(m, cout)) < 2e-5
 
 
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("case", [(2, 256, 19, 19, 256, 3), (3, 48, 9, 11, 256, 3), (2, 64, 20, 20, 72, 1)])
+def test_conv_epilogue_writes_the_output_operand_image(zsg, case, bf16):
+    """zsg_conv_params.y_lo / y_img_bf16: the fragment epilogue stores the GEMM operand image of its OUTPUT (TF32 remainders
+    / bfloat16 copy) next to y -- bit-identical to zsg_split_act / zsg_cast_bf16 over the finished tensor, y itself
+    unchanged; 128- and 256-column tiles."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k = case
+    g = torch.Generator().manual_seed(cin + cout)
+    m = B * H * W
+    x = torch.randn(B, H, W, cin, generator=g).cuda()
+    w = (torch.randn(cout, k, k, cin, generator=g) / (cin * k * k) ** 0.5).cuda()
+    rows = geo.conv_rows(B, H, W, cin, H, W, cout, 1, k // 2).cuda()
+    kw = dict(bias=torch.randn(cout, generator=g).cuda(), out_relu=True, out_mask=torch.randn(m, cout, generator=g).cuda())
+    if bf16:
+        xi, wi, wa = x.to(torch.bfloat16), w.to(torch.bfloat16), w
+    else:
+        xi, wa, wi = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+        ops.split_act(x, xi, m, cin)
+        ops.split_tf32(w, wa, wi, w.numel())
+    for impl in ((2, 3) if bf16 and cout % 256 == 0 else (0,)):
+        y0, y1 = torch.zeros(m, cout, device="cuda"), torch.zeros(m, cout, device="cuda")
+        img = torch.zeros(m, cout, device="cuda", dtype=torch.bfloat16 if bf16 else torch.float32)
+        ops.ConvOp(x, wa, y0, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, y_pitch=cout, impl=impl, **kw)()
+        ops.ConvOp(x, wa, y1, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, y_pitch=cout, impl=impl, y_img=img, **kw)()
+        want = torch.zeros_like(img)
+        if bf16:
+            ops.cast_bf16(y0, want, y0.numel())
+        else:
+            ops.split_act(y0, want, m, cout)
+        torch.cuda.synchronize()
+        assert torch.equal(y0, y1)
+        assert torch.equal(img.view(torch.int16 if bf16 else torch.int32), want.view(torch.int16 if bf16 else torch.int32))
+    with pytest.raises(Exception):                           # not a plain [m, y_pitch] output: refused, never silently skipped
+        ops.ConvOp(x, wa, y1, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, y_pitch=0, y_img=img, **kw)()
+
+
 def test_split_first_head_conv_equals_the_materialised_convolution(zsg):
     """a-6: conv(W, [feat | lang tiled | grid]) (mdl.py:69-104, 235-244) = conv(W_f, feat) + L[b, border class] + G[cell].
     Forward through zsg_conv_fwd with row_add against F.conv2d over the concatenated tensor, level by level; backward sums

@@ -27,7 +27,7 @@ class ConvParams(C.Structure):
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
                 ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32), ("stats", C.c_void_p),
                 ("x_bf16", C.c_void_p), ("w_bf16", C.c_void_p), ("x_plain", C.c_int32), ("y_bf16", C.c_void_p), ("residual_bf16", C.c_void_p), ("y_pitch", C.c_int32), ("row_add", C.c_void_p),
-                ("row_add_idx", C.c_void_p)]
+                ("row_add_idx", C.c_void_p), ("y_lo", C.c_void_p), ("y_img_bf16", C.c_void_p)]
 
 
 class WgradParams(C.Structure):

@@ -809,6 +809,23 @@ __device__ __forceinline__ void epilogue_fragx(const zsg_conv_params& p, float (
         if (nbase + 8 * u >= p.cout) break;
         *reinterpret_cast<float2*>(p.y + off[hh] + 8 * u) = make_float2(VX(hh, u), VY(hh, u));
       }
+      if (p.y_lo) {                                         // operand image of the output: TF32 remainders (as zsg_split_act)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (nbase + 8 * u >= p.cout) break;
+          float h0, l0, h1, l1;
+          split_tf32(VX(hh, u), h0, l0);
+          split_tf32(VY(hh, u), h1, l1);
+          *reinterpret_cast<float2*>(p.y_lo + off[hh] + 8 * u) = make_float2(l0, l1);
+        }
+      }
+      if (p.y_img_bf16) {                                   // ... or the bfloat16 copy (as zsg_cast_bf16)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (nbase + 8 * u >= p.cout) break;
+          *reinterpret_cast<__nv_bfloat162*>(p.y_img_bf16 + off[hh] + 8 * u) = __floats2bfloat162_rn(VX(hh, u), VY(hh, u));
+        }
+      }
     }
   }
 #undef VX
@@ -2479,9 +2496,10 @@ static int launch_conv(const zsg_conv_params& p, cudaStream_t st) {
 static inline int pick_epilogue(const zsg_conv_params& p) {
   static const bool fragx = [] { const char* e = getenv("ZSG_EPI_FRAGX"); return !(e && e[0] == '0'); }();   // 0: slab epilogue (A/B runs)
   if (p.y_bf16) return EPI_B16;
-  if (epilogue_is_plain(p)) return EPI_PLAIN;
-  const uintptr_t ptrs = (uintptr_t)p.y | (uintptr_t)p.bias | (uintptr_t)p.out_mask | (uintptr_t)p.residual | (uintptr_t)p.row_add;
-  return (fragx && p.cout % 8 == 0 && p.y_pitch > 0 && p.y_pitch % 2 == 0 && (ptrs & 7) == 0 && ((uintptr_t)p.residual_bf16 & 3) == 0)
+  if (epilogue_is_plain(p) && !p.y_lo && !p.y_img_bf16) return EPI_PLAIN;
+  const uintptr_t ptrs = (uintptr_t)p.y | (uintptr_t)p.bias | (uintptr_t)p.out_mask | (uintptr_t)p.residual | (uintptr_t)p.row_add |
+                         (uintptr_t)p.y_lo;
+  return (fragx && p.cout % 8 == 0 && p.y_pitch > 0 && p.y_pitch % 2 == 0 && (ptrs & 7) == 0 && (((uintptr_t)p.residual_bf16 | (uintptr_t)p.y_img_bf16) & 3) == 0)
              ? EPI_FRAGX : EPI_GENERIC;
 }
 
@@ -2763,6 +2781,12 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(!p.x_plain || (p.r == 1 && p.s == 1 && p.in_div == 1), "zsg_conv_fwd: x_plain needs r = s = 1 and in_div = 1");
   ZSG_REQUIRE(p.y_pitch == 0 || p.y_pitch >= p.cout, "zsg_conv_fwd: y_pitch=%d must be 0 or >= cout", p.y_pitch);
   ZSG_REQUIRE(!p.row_add == !p.row_add_idx, "zsg_conv_fwd: row_add and row_add_idx go together");
+  ZSG_REQUIRE((!p.y_lo && !p.y_img_bf16) ||
+                  (!(p.y_lo && p.y_img_bf16) && !p.y_bf16 && !p.stats && p.impl != 1 && (p.x_lo || p.x_bf16) && p.cout % 8 == 0 &&
+                   p.y_pitch > 0 && p.y_pitch % 2 == 0 && ((uintptr_t)p.y & 7) == 0 && ((uintptr_t)p.y_lo & 7) == 0 &&
+                   ((uintptr_t)p.y_img_bf16 & 3) == 0 && pick_epilogue(p) == EPI_FRAGX),
+              "zsg_conv_fwd: y_lo / y_img_bf16 (one of them) need a plain [m, y_pitch] fp32 output with cout %% 8 == 0 and an even "
+              "y_pitch on the operand-image tcgen05 paths (the fragment epilogue writes them)");
   ZSG_REQUIRE(!p.row_add || (p.cout % 4 == 0 && (p.x_lo || p.x_bf16) && p.impl != 1 && !p.y_bf16 && !p.stats &&
                              (((uintptr_t)p.row_add & 15) | ((uintptr_t)p.row_add_idx & 7)) == 0),
               "zsg_conv_fwd: row_add needs cout %% 4 == 0, an operand-image input, the tcgen05 path and aligned tables");

@@ -234,6 +234,14 @@ class Engine:
             self._operand_cache[key] = (z, lo)
         return self._operand_cache[key]
 
+    def out_image(self, y, nrows, c, b16=False):
+        """Operand image of a tensor that a conv epilogue writes next to it (zsg_conv_params.y_lo / y_img_bf16): registered
+        as the tensor's forward operand, so the consumer's fwd_operand() finds it and appends no split / cast pass."""
+        key = (y.data_ptr(), nrows, c, id(None), False, bool(b16))
+        if key not in self._operand_cache:
+            self._operand_cache[key] = (y, self.img(nrows, c, b16=b16))
+        return self._operand_cache[key][1]
+
     def bwd_lo_buffer(self, dy, nrows, c, b16=False):
         """Storage for the operand image of a gradient tensor (one per scratch buffer, sized for its largest user)."""
         n = nrows * c
@@ -847,6 +855,9 @@ class Engine:
         rows_last, rows_f48 = head_rows("fwd", 256, 45, scatter=True), head_rows("fwd", 256, 48)
         rows_d520, rows_d256, rows_d48 = head_rows("dgrad", CP, 256), head_rows("dgrad", 256, 256), head_rows("dgrad", 256, 48)
         hb16 = self.use_b16(256)                             # every head contraction has channel counts % 8 == 0
+        # operand images of the head activations / gradients straight from the producing conv's epilogue (no split / cast
+        # pass over the [M, 256] tensors: 10 passes of 254 MB at bs = 64); ZSG_EPI_IMAGES=0: the separate passes (A/B runs)
+        epi_img = os.environ.get("ZSG_EPI_IMAGES", "1") != "0" and self.impl == 0
         if not split:
             _, fused_lo = self.fwd_operand(fused, M, CP, b16=hb16)
             w0h, w0l = self.weight_operand(w0p_t, hb16)
@@ -862,13 +873,15 @@ class Engine:
             _, feat_lo = self.fwd_operand(hfeat, M, 256, b16=hb16)
             wfh, wfl = self.weight_operand(h0wf_t, hb16)
             self.fwd.append(("op", ConvOp(hfeat, wfh, hs[0], rows_f256, M, 256, 256, 3, 3, bias=hb(0), out_relu=True,
-                                          impl=self.impl, w_lo=wfl, x_lo=feat_lo, y_pitch=256, row_add=radd, row_add_idx=ridx)))
+                                          impl=self.impl, w_lo=wfl, x_lo=feat_lo, y_pitch=256, row_add=radd, row_add_idx=ridx,
+                                          y_img=self.out_image(hs[0], M, 256, b16=hb16) if epi_img else None)))
         hs_lo = []
         for i in range(1, 5):
             wh, wl = self.weight_operand(f"att_reg_box.{i}.0.weight", hb16)
             hs_lo.append(self.fwd_operand(hs[i - 1], M, 256, b16=hb16)[1])
             self.fwd.append(("op", ConvOp(hs[i - 1], wh, hs[i], rows_f256, M, 256, 256, 3, 3, bias=hb(i), out_relu=True,
-                                          impl=self.impl, w_lo=wl, x_lo=hs_lo[-1], y_pitch=256)))
+                                          impl=self.impl, w_lo=wl, x_lo=hs_lo[-1], y_pitch=256,
+                                          y_img=self.out_image(hs[i], M, 256, b16=hb16) if epi_img else None)))
         hs_lo.append(self.fwd_operand(hs[4], M, 256, b16=hb16)[1])
         w5 = st.flat("att_reg_box.5.weight")
         w5h, w5l = self.weight_operand("att_reg_box.5.weight", hb16)
@@ -907,22 +920,24 @@ class Engine:
             self.bwd.append(WgradOp(hs[4], dy5, st.grad_flat("att_reg_box.5.weight"), rows_f48, M, 256, 45, 3, 3,
                                     impl=self.impl, x_lo=hs_lo[4], dy_lo=dy5_lo, dy_pitch=48))
             wt5h, wt5l = self.weight_operand(wt5p_t, hb16)
+            # the image of every dhs[i] comes out of the data gradient that writes it (epi_img)
+            dimg = [self.bwd_lo_buffer(dhs[i], M, 256, hb16) if epi_img else None for i in range(5)]
             self.bwd.append(ConvOp(dy5, wt5h, dhs[4], rows_d48, M, 48, 256, 3, 3, out_mask=hs[4], impl=self.impl,
-                                   w_lo=wt5l, x_lo=dy5_lo, y_pitch=256))
+                                   w_lo=wt5l, x_lo=dy5_lo, y_pitch=256, y_img=dimg[4]))
             for i in range(4, 0, -1):
                 wi, wti = st.flat(f"att_reg_box.{i}.0.weight"), wts[i][0]
                 self.queue_transpose(wi, wti, 256, 3, 256)
                 gb = st.grad_flat(f"att_reg_box.{i}.0.bias")
                 self.bwd.append(lambda i=i, gb=gb: ops.colsum(dhs[i], gb, M, 256))
-                dlo = self.bwd_operand(dhs[i], M, 256, b16=hb16)
+                dlo = dimg[i] if epi_img else self.bwd_operand(dhs[i], M, 256, b16=hb16)
                 self.bwd.append(WgradOp(hs[i - 1], dhs[i], st.grad_flat(f"att_reg_box.{i}.0.weight"), rows_f256, M, 256,
                                         256, 3, 3, impl=self.impl, x_lo=hs_lo[i - 1], dy_lo=dlo, dy_pitch=256))
                 wth, wtl = self.weight_operand(wts[i], hb16)
                 self.bwd.append(ConvOp(dhs[i], wth, dhs[i - 1], rows_d256, M, 256, 256, 3, 3, out_mask=hs[i - 1],
-                                       impl=self.impl, w_lo=wtl, x_lo=dlo, y_pitch=256))
+                                       impl=self.impl, w_lo=wtl, x_lo=dlo, y_pitch=256, y_img=dimg[i - 1]))
             gb0 = st.grad_flat("att_reg_box.0.0.bias")
             self.bwd.append(lambda: ops.colsum(dhs[0], gb0, M, 256))
-            d0lo = self.bwd_operand(dhs[0], M, 256, b16=hb16)
+            d0lo = dimg[0] if epi_img else self.bwd_operand(dhs[0], M, 256, b16=hb16)
             g0 = st.grad_flat("att_reg_box.0.0.weight")
             if split:
                 # dW_f: weight gradient over feat; dW_l, d lang: two small GEMMs over the per-tap column sums; dW_g from the same

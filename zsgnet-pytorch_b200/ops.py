@@ -45,8 +45,8 @@ class ConvOp:
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
-                 x_lo=None, dil=1, stats=None, x_plain=False, y_pitch=0, row_add=None, row_add_idx=None):
-        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats, row_add, row_add_idx)
+                 x_lo=None, dil=1, stats=None, x_plain=False, y_pitch=0, row_add=None, row_add_idx=None, y_img=None):
+        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats, row_add, row_add_idx, y_img)
         yb = None
         if _is_bf16(y):                                      # bf16 storage: the output tensor itself is bfloat16
             y, yb = None, y
@@ -63,7 +63,9 @@ class ConvOp:
         self.p = ConvParams(ptr(x), ptr(w), ptr(w_lo), ptr(y), ptr(rows), m, cin, cout, r, s, in_div, ptr(in_scale),
                             ptr(in_shift), int(in_relu), ptr(bias), int(out_relu), ptr(out_mask), ptr(residual), int(accumulate),
                             impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb), ptr(rb), int(y_pitch),
-                            ptr(row_add), ptr(row_add_idx))
+                            ptr(row_add), ptr(row_add_idx),
+                            # y_img: the operand image of the output, written by the epilogue (fp32 = TF32 remainders, bf16 = copy)
+                            ptr(None if _is_bf16(y_img) else y_img), ptr(y_img if _is_bf16(y_img) else None))
         if y_pitch and rows.is_cuda:                         # the claim is checked once, when the launch is described
             out = rows.view(torch.int32).view(-1, 4)[:m, 3].to(torch.int64)
             assert bool((out == torch.arange(m, device=rows.device) * y_pitch).all()), "y_pitch does not describe this row table"
