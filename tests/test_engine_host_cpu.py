@@ -107,9 +107,11 @@ def test_bf16_engine_program_on_host(recorded):
     fwd = collections.Counter(calls)
     # bf16 storage of the trunk: conv outputs / block outputs are bfloat16 tensors (their own operand images): the 32
     # BatchNorm+ReLU-on-load passes are bfloat16 -> bfloat16, the stem pool output needs no cast at all; fp32 tensors that
-    # feed a GEMM (2 weight arenas, 4 FPN inner maps incl. relu(P6), 7 head inputs: feat, lang, 5 hidden maps) are still cast
+    # feed a GEMM (2 weight arenas, 4 FPN inner maps incl. relu(P6), 2 head inputs: feat, lang) are still cast; the images of
+    # the 5 hidden maps of the head come out of the producing conv's epilogue (zsg_conv_params.y_img_bf16)
     assert eng.b16act and eng.dbg["c5"].dtype == torch.bfloat16 and eng.dbg["blocks"][0]["r1"].dtype == torch.bfloat16
-    assert fwd["zsg_act_b16"] == 32 and fwd["zsg_cast_bf16"] == 2 + 4 + 7 and fwd["zsg_split_act"] == 1
+    assert fwd["zsg_act_b16"] == 32 and fwd["zsg_cast_bf16"] == 2 + 4 + 2 and fwd["zsg_split_act"] == 1
+    assert sum(1 for it in eng.fwd if it[0] == "op" and it[1].p.y_img_bf16) == 5
     assert fwd["zsg_bn_apply_b16"] == 16 and fwd["zsg_bn_apply_bf16"] == 0 and fwd["zsg_maxpool_bn_relu_fwd_b16"] == 1
     del calls[:]
     eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5))
