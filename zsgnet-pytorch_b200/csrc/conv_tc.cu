@@ -1750,15 +1750,20 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
           }
           __syncwarp();
         }
+        // One multiply-add per address: a padding tap (off = -1) points one element before the chunk and is never read (0
+        // source bytes = 16 bytes of zeros).  The select / add chain this replaces and a uniform branch inside the loop were
+        // 13 issue slots per copy; the producers are bound by issue slots (tools/trace_conv.py: ~95 cycles per copy).
+        if (!(ablate & 32)) {                               // diagnostics bit 5: no input loads
+          const int64_t lo_delta = xl - xh;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const bool ok = off[it] >= 0;
-          const int64_t o = ok ? (int64_t)off[it] * S::ES : 0;
-          const uint32_t nbytes = ok ? 16u : 0u;           // 0 source bytes = 16 bytes of zeros (padding)
-          const uint32_t dst = a_hi + soff + it * 2048;
-          if (ablate & 32) continue;                        // diagnostics: no input loads
-          cp_async16(dst, xh + o, nbytes);
-          if (!BF16) cp_async16(dst + A_TILE_BYTES, xl + o, nbytes);
+          for (int it = 0; it < 8; ++it) {
+            const int o = off[it];
+            const uint32_t nbytes = o >= 0 ? 16u : 0u;
+            const uint32_t dst = a_hi + soff + it * 2048;
+            const uint8_t* src = xh + (int64_t)o * S::ES;
+            cp_async16(dst, src, nbytes);
+            if (!BF16) cp_async16(dst + A_TILE_BYTES, src + lo_delta, nbytes);
+          }
         }
         // arrive on `full` when this thread's copies have landed; the thread itself moves on to its next K block.
         // (The copies are generic-proxy writes: the issuer runs fence.proxy.async after its wait on `full`.)
