@@ -1750,9 +1750,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
           }
           __syncwarp();
         }
-        // One multiply-add per address: a padding tap (off = -1) points one element before the chunk and is never read (0
-        // source bytes = 16 bytes of zeros).  The select / add chain this replaces and a uniform branch inside the loop were
-        // 13 issue slots per copy; the producers are bound by issue slots (tools/trace_conv.py: ~95 cycles per copy).
+        // One max + one multiply-add per address: a padding tap (off = -1) reads nothing (0 source bytes = 16 bytes of zeros)
+        // and is pointed at the chunk of pixel 0, a valid address.  The 64-bit select / add chain this replaces and a uniform
+        // branch inside the loop were 13 issue slots per copy; the producers are bound by issue slots (tools/trace_conv.py:
+        // ~95 cycles per copy).
         if (!(ablate & 32)) {                               // diagnostics bit 5: no input loads
           const int64_t lo_delta = xl - xh;
 #pragma unroll
@@ -1760,7 +1761,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv_tc_async_kernel(const zsg_c
             const int o = off[it];
             const uint32_t nbytes = o >= 0 ? 16u : 0u;
             const uint32_t dst = a_hi + soff + it * 2048;
-            const uint8_t* src = xh + (int64_t)o * S::ES;
+            const uint8_t* src = xh + (int64_t)max(o, 0) * S::ES;
             cp_async16(dst, src, nbytes);
             if (!BF16) cp_async16(dst + A_TILE_BYTES, src + lo_delta, nbytes);
           }
@@ -2039,8 +2040,9 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
           const int r4 = ps;                                 // pixel & 3
           const uint32_t off = atom_off + q * 512 + r4 * 128 + ((((cj >> 1) ^ r4) << 1) | (cj & 1)) * 16;
           (void)pixel;
-          cp_async16(a_hi + off, xh + (ao < 0 ? 0 : ao), ao < 0 ? 0u : 16u);
-          cp_async16(a_hi + A_TILE_BYTES + off, xl + (ao < 0 ? 0 : ao), ao < 0 ? 0u : 16u);
+          const float* src = xh + max(ao, 0);               // padding: nothing is read (0 source bytes), any valid address
+          cp_async16(a_hi + off, src, ao < 0 ? 0u : 16u);
+          cp_async16(a_hi + A_TILE_BYTES + off, src + (xl - xh), ao < 0 ? 0u : 16u);
           if (!TMA_DY && mc * 4 < BN) {
             cp_async16(b_hi + off, yh + (bo < 0 ? 0 : bo), bo < 0 ? 0u : bbytes);
             cp_async16(b_hi + S::B_TILE_BYTES + off, yl + (bo < 0 ? 0 : bo), bo < 0 ? 0u : bbytes);
