@@ -2143,6 +2143,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
     int tap = 0, c = 0, tr = 0, ts = 0;
     if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
     const uint16_t* xb = p.x_bf16 + c;
+    const int tap0 = __shfl_sync(0xffffffffu, tap, 0);        // (outside the &&: every lane must take part)
+    const bool warp_uniform = __all_sync(0xffffffffu, jvalid && tap == tap0) != 0;
     const int4* rows = reinterpret_cast<const int4*>(p.rows);
     int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 128;      // [2][64] entries per group
     const uint32_t tiles0 = smem_u32(sm);
@@ -2178,14 +2180,29 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
         }
         __syncwarp();
       }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int4 e = eb[q * 8 + ps];                       // pixel q * 8 + ps of the K block
+      if (warp_uniform) {
+        // one tap for the whole warp (cin >= 128): the warp's 16 (q, ps) pixels are decoded once, by lanes 0-15 (the upper half-warp
+        // repeats them), and the offsets are broadcast -- eight decodes per lane were most of the producers' issue slots
+        const int4 e = eb[(lane & 7) * 8 + 2 * (t >> 5) + ((lane >> 3) & 1)];
         const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
         const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-        const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
-        const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
-        cp_async16(a_tile + toff + q * 1024, xb + ao, oka ? 16u : 0u);
+        const bool oka = (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+        const int my_ao = oka ? e.x + (yy * win + xx) * p.cin : -1;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int ao = __shfl_sync(0xffffffffu, my_ao, q + ((lane >> 4) << 3));
+          cp_async16(a_tile + toff + q * 1024, xb + max(ao, 0), ao < 0 ? 0u : 16u);   // padding: 0 bytes from a valid address
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int4 e = eb[q * 8 + ps];                     // pixel q * 8 + ps of the K block
+          const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
+          const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+          const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
+          cp_async16(a_tile + toff + q * 1024, xb + ao, oka ? 16u : 0u);
+        }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
       if (has_next) {
@@ -2287,6 +2304,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_wide_kernel(const zsg
       int tap = 0, c = 0, tr = 0, ts = 0;
       if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
       const uint16_t* xb = p.x_bf16 + c;
+      const int tap0 = __shfl_sync(0xffffffffu, tap, 0);
+      const bool warp_uniform = __all_sync(0xffffffffu, jvalid && tap == tap0) != 0;
       const int first = (group - g0) & 1;                   // K blocks with (g0 + i) % NGROUP == group
       asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");   // the previous unit's entries have been read
       if (first < nkb && t < KBP) {
@@ -2319,14 +2338,29 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_wide_kernel(const zsg
           }
           __syncwarp();
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int4 e = eb[q * 8 + ps];                     // pixel q * 8 + ps of the K block
+        if (warp_uniform) {
+          // one tap for the whole warp (cin >= 128): the warp's 16 (q, ps) pixels are decoded once, by lanes 0-15 (the upper half-warp
+          // repeats them), and the offsets are broadcast -- eight decodes per lane were most of the producers' issue slots
+          const int4 e = eb[(lane & 7) * 8 + 2 * (t >> 5) + ((lane >> 3) & 1)];
           const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
           const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-          const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
-          const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
-          cp_async16(a_tile + toff + q * 1024, xb + ao, oka ? 16u : 0u);
+          const bool oka = (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          const int my_ao = oka ? e.x + (yy * win + xx) * p.cin : -1;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int ao = __shfl_sync(0xffffffffu, my_ao, q + ((lane >> 4) << 3));
+            cp_async16(a_tile + toff + q * 1024, xb + max(ao, 0), ao < 0 ? 0u : 16u);   // padding: 0 bytes from a valid address
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int4 e = eb[q * 8 + ps];                     // pixel q * 8 + ps of the K block
+            const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
+            const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
+            const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+            const int64_t ao = oka ? (int64_t)e.x + (int64_t)(yy * win + xx) * p.cin : 0;
+            cp_async16(a_tile + toff + q * 1024, xb + ao, oka ? 16u : 0u);
+          }
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
         if (has_next) {
