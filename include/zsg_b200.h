@@ -107,6 +107,13 @@ typedef struct {
   uint16_t* y_img_bf16;    /* (indexed like y): y_lo = TF32 remainders as zsg_split_act writes them, y_img_bf16 = the bfloat16 copy  */
                            /* as zsg_cast_bf16.  The consumer of y (next conv, weight / data gradient) then needs no image pass.   */
                            /* Plain [m, y_pitch] outputs with cout % 8 == 0 and y_pitch % 2 == 0 on the operand-image paths only   */
+  const void* bnb_x;       /* optional group (all four or none): this launch is the data gradient that writes dy of a BatchNorm+ReLU  */
+  const float* bnb_scale;  /* pair (mdl.py:149-156: bn1 / bn2 of a bottleneck) whose INPUT x (= output of the conv in front of it)   */
+  const float* bnb_shift;  /* is indexed like y: float32 with a float32 y, bfloat16 with y_bf16.  The epilogue then also writes, per */
+  float* bnb_partials;     /* 32-row group, sum dz and sum dz * x with dz = dy where x * scale + shift > 0 ([ceil(m/128)*4][2][cout],  */
+                           /* the layout of `stats`): zsg_bn_stats_partials + zsg_bn_bwd_center_sums turn them into the sums          */
+                           /* zsg_bn_bwd_apply reads, replacing zsg_bn_bwd_reduce (mask_mode 1) and its read of dy and x.  y is       */
+                           /* stored unmasked as without it.  Plain outputs, y_pitch > 0, cout % 8 == 0, no `stats`                   */
 } zsg_conv_params;
 int zsg_conv_fwd(const zsg_conv_params* p, zsg_stream_t stream);
 /* diagnostics only (tools/trace_conv.py): CTA 0 of the conv kernel writes clock stamps of its first `nblocks`
@@ -183,6 +190,9 @@ int zsg_gather_rows(const float* src, const zsg_row_t* rows, float* dst, int64_t
 int zsg_bn_stats(const float* x, double* sums, int64_t rows, int c, zsg_stream_t stream);
 /* the same sums from the per-row-group partials a conv wrote (zsg_conv_params.stats): parts = ceil(m/128)*4. */
 int zsg_bn_stats_partials(const float* partials, int64_t parts, int c, double* sums, zsg_stream_t stream);
+/* sums[c .. 2c) <- invstd * (sums[c .. 2c) - mean * sums[0 .. c)): turns (sum dz, sum dz * x) from a data gradient's epilogue
+ * (zsg_conv_params.bnb_partials, reduced by zsg_bn_stats_partials) into (sum dz, sum dz * xhat), what zsg_bn_bwd_apply reads. */
+int zsg_bn_bwd_center_sums(double* sums, const float* mean, const float* invstd, int c, zsg_stream_t stream);
 /* zsg_bn_stats_partials + zsg_bn_finalize in one launch: the last block of a channel group to finish (ticket counter)
  * finalizes it.  sums: 2c doubles, zeroed by the caller; tickets: 64 ints, zero before the first use, left zero. */
 int zsg_bn_finalize_partials(const float* partials, int64_t parts, int64_t rows, int c, const float* gamma,

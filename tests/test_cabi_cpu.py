@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/zsg_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert _lib.load().zsg_abi_version() == 7
+    assert _lib.load().zsg_abi_version() == 8
 
 
 def test_row_table_layout_matches_header():

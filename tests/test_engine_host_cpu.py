@@ -64,7 +64,11 @@ def test_engine_program_builds_and_runs_on_host(recorded):
     # data gradients run through the forward kernel; the five 3x3 / stride-2 convs (layer2-4.0.conv2, P6, P7_2) take
     # one launch per input-pixel parity class (4) instead of one zero-stuffed launch
     assert bwd["zsg_conv_fwd"] == 52 + 8 + 6 + 5 * 3 + 1               # + d lang = tap sums x W_l
-    assert bwd["zsg_bn_bwd_reduce"] == 53 and bwd["zsg_bn_bwd_apply"] == 53
+    # BatchNorm backward: the reduce pass of the 32 in-block BatchNorm+ReLU pairs (bn1 / bn2) comes out of the epilogue of the
+    # data gradient that writes their dy (zsg_conv_params.bnb_*), except behind the three stride-2 conv2 (parity-class launches)
+    assert bwd["zsg_bn_bwd_reduce"] == 53 - 29 and bwd["zsg_bn_bwd_apply"] == 53
+    assert bwd["zsg_bn_bwd_center_sums"] == 29 and bwd["zsg_bn_stats_partials"] == 29
+    assert sum(1 for op in eng.bwd if isinstance(op, ops.ConvOp) and op.p.bnb_partials) == 29
     # 64 of the transposed-flipped weight copies (all that go arena -> pool) are one batched launch; the padded last head
     # weight and the two slices of the first one (W_f for d feat, W_l for d lang) keep their own
     assert bwd["zsg_weight_transpose_flip_batched32"] == 1 and bwd["zsg_weight_transpose_flip"] == 3   # tiled: all dims % 32 == 0
@@ -116,7 +120,8 @@ def test_bf16_engine_program_on_host(recorded):
     del calls[:]
     eng.backward(torch.zeros(B, spec.NUM_ANCHORS, 5))
     bwd = collections.Counter(calls)
-    assert bwd["zsg_bn_bwd_apply_b16"] == 53 and bwd["zsg_bn_bwd_reduce_b16"] == 53
+    assert bwd["zsg_bn_bwd_apply_b16"] == 53 and bwd["zsg_bn_bwd_reduce_b16"] == 53 - 29      # 29 from data-gradient epilogues
+    assert bwd["zsg_bn_bwd_center_sums"] == 29
     assert bwd["zsg_bn_bwd_apply"] == 0 and bwd["zsg_bn_bwd_apply_bf16"] == 0 and bwd["zsg_split_tf32"] == 0
 
 

@@ -1163,6 +1163,57 @@ def test_conv_epilogue_writes_the_output_operand_image(zsg, case, bf16):
         ops.ConvOp(x, wa, y1, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, y_pitch=0, y_img=img, **kw)()
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16_store", "bf16_store_wide"])
+@pytest.mark.parametrize("case", [(2, 256, 19, 19, 64, 1), (3, 64, 21, 17, 64, 3), (2, 512, 10, 10, 256, 1), (2, 128, 20, 20, 128, 3)])
+def test_conv_epilogue_batchnorm_backward_sums(zsg, case, mode):
+    """zsg_conv_params.bnb_*: the data gradient that writes dy of a BatchNorm+ReLU also leaves sum dz / sum dz * x per 32-row
+    group (dz = dy where x * scale + shift > 0); zsg_bn_stats_partials + zsg_bn_bwd_center_sums turn them into the sums
+    zsg_bn_bwd_reduce (mask_mode 1) produces from dy and x -- compared with that kernel and with torch; y is unchanged."""
+    ops, geo = zsg
+    B, cin, H, W, cout, k = case
+    if mode == "bf16_store_wide" and cout % 256:
+        pytest.skip("256-column tiles need cout % 256 == 0")
+    bf16, store = mode != "fp32", mode.startswith("bf16_store")
+    g = torch.Generator().manual_seed(cin + 3 * cout + k)
+    m = B * H * W
+    x = torch.randn(B, H, W, cin, generator=g).cuda()
+    w = (torch.randn(cout, k, k, cin, generator=g) / (cin * k * k) ** 0.5).cuda()
+    rows = geo.conv_rows(B, H, W, cin, H, W, cout, 1, k // 2).cuda()
+    bx = (torch.randn(m, cout, generator=g) * 1.5 + 0.3).cuda()          # the BatchNorm's input at the output positions
+    mean, var = bx.mean(0), bx.var(0, unbiased=False)
+    invstd = (var + 1e-5).rsqrt()
+    gamma, beta = (torch.rand(cout, generator=g) + 0.5).cuda(), (torch.randn(cout, generator=g) * 0.2).cuda()
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    if store:
+        bx = bx.to(torch.bfloat16)
+    if bf16:
+        xi, wi, wa = x.to(torch.bfloat16), w.to(torch.bfloat16), w
+    else:
+        xi, wa, wi = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+        ops.split_act(x, xi, m, cin)
+        ops.split_tf32(w, wa, wi, w.numel())
+    parts = (m + 127) // 128 * 4
+    ydt = torch.bfloat16 if store else torch.float32
+    impl = 3 if mode == "bf16_store_wide" else (2 if bf16 else 0)
+    y0, y1 = torch.zeros(m, cout, device="cuda", dtype=ydt), torch.zeros(m, cout, device="cuda", dtype=ydt)
+    partials = torch.zeros(parts, 2, cout, device="cuda")
+    ops.ConvOp(x, wa, y0, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, y_pitch=cout, impl=impl)()
+    ops.ConvOp(x, wa, y1, rows, m, cin, cout, k, k, w_lo=wi, x_lo=xi, y_pitch=cout, impl=impl,
+               bnb=(bx, scale, shift, partials))()
+    sums = torch.zeros(2 * cout, device="cuda", dtype=torch.float64)
+    ops.bn_stats_partials(partials, parts, cout, sums)
+    ops.bn_bwd_center_sums(sums, mean, invstd, cout)
+    want = torch.zeros(2 * cout, device="cuda", dtype=torch.float64)
+    ops.bn_bwd_reduce(y0, bx, mean, invstd, want, m, cout, mask_mode=1, scale=scale, shift=shift)
+    torch.cuda.synchronize()
+    assert torch.equal(y0.view(torch.int16 if store else torch.int32), y1.view(torch.int16 if store else torch.int32))
+    dz = torch.where(bx.float() * scale + shift > 0, y0.float(), torch.zeros_like(y0, dtype=torch.float32)).double()
+    ref = torch.cat([dz.sum(0), (dz * ((bx.double() - mean.double()) * invstd.double())).sum(0)])
+    tol = 2e-5 * float(ref.abs().max())
+    assert float((sums - want).abs().max()) < tol and float((sums - ref).abs().max()) < tol
+
+
 def test_split_first_head_conv_equals_the_materialised_convolution(zsg):
     """a-6: conv(W, [feat | lang tiled | grid]) (mdl.py:69-104, 235-244) = conv(W_f, feat) + L[b, border class] + G[cell].
     Forward through zsg_conv_fwd with row_add against F.conv2d over the concatenated tensor, level by level; backward sums

@@ -27,7 +27,8 @@ class ConvParams(C.Structure):
                 ("bias", C.c_void_p), ("out_relu", C.c_int32), ("out_mask", C.c_void_p), ("residual", C.c_void_p), ("accumulate", C.c_int32),
                 ("impl", C.c_int32), ("x_lo", C.c_void_p), ("dil", C.c_int32), ("stats", C.c_void_p),
                 ("x_bf16", C.c_void_p), ("w_bf16", C.c_void_p), ("x_plain", C.c_int32), ("y_bf16", C.c_void_p), ("residual_bf16", C.c_void_p), ("y_pitch", C.c_int32), ("row_add", C.c_void_p),
-                ("row_add_idx", C.c_void_p), ("y_lo", C.c_void_p), ("y_img_bf16", C.c_void_p)]
+                ("row_add_idx", C.c_void_p), ("y_lo", C.c_void_p), ("y_img_bf16", C.c_void_p),
+                ("bnb_x", C.c_void_p), ("bnb_scale", C.c_void_p), ("bnb_shift", C.c_void_p), ("bnb_partials", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
@@ -68,6 +69,7 @@ SIGNATURES = {
     "zsg_gather_rows": [_P, _P, _P, _L, _I, _I, _P],
     "zsg_bn_stats": [_P, _P, _L, _I, _P],
     "zsg_bn_stats_partials": [_P, _L, _I, _P, _P],
+    "zsg_bn_bwd_center_sums": [_P, _P, _P, _I, _P],
     "zsg_bn_finalize_partials": [_P, _L, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "zsg_bn_finalize": [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "zsg_bn_eval_affine": [_P, _P, _P, _P, _F, _I, _P, _P, _P],

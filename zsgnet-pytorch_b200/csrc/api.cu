@@ -14,7 +14,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace zsg
 
 extern "C" const char* zsg_last_error_string(void) { return zsg::g_err; }
-extern "C" int zsg_abi_version(void) { return 7; }
+extern "C" int zsg_abi_version(void) { return 8; }
 extern "C" int zsg_device_supported(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

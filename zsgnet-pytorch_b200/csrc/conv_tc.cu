@@ -601,16 +601,68 @@ __device__ __forceinline__ void epilogue_frag(const zsg_conv_params& p, const fl
   const int q = lane & 3, g = lane >> 2;                    // column pair inside a unit, row inside an 8-row group
   const int nbase = n0 + half * (BN / 2) + 2 * q;           // column of (u = 0, c = 0)
   // ---- BatchNorm statistics of the warp's 32 rows (rows past p.m hold zeros: their A rows were zero-filled)
-  if (p.stats && !(ablate & 128)) {
+  //   forward (p.stats):        s1 = sum y,  s2 = sum y^2
+  //   backward (p.bnb_partials): this launch is the data gradient that produces dy of a BatchNorm+ReLU whose INPUT x lies at
+  //                             the output positions (p.bnb_x): s1 = sum dz, s2 = sum dz * x with dz = dy where
+  //                             x * scale + shift > 0 -- the reduce pass of that BatchNorm's backward (zsg_bn_bwd_reduce,
+  //                             mask_mode 1) as a by-product; y itself is stored unmasked, as without it
+  float* const stp = p.stats ? p.stats : p.bnb_partials;
+  if (stp && !(ablate & 128)) {
     float s1[2 * U], s2[2 * U];
+    if (p.stats) {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const float a0 = acc[4 * u + c], a1 = acc[4 * u + 2 + c], a2 = acc[4 * U + 4 * u + c], a3 = acc[4 * U + 4 * u + 2 + c];
-        s1[2 * u + c] = (a0 + a1) + (a2 + a3);
-        s2[2 * u + c] = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
+        for (int c = 0; c < 2; ++c) {
+          const float a0 = acc[4 * u + c], a1 = acc[4 * u + 2 + c], a2 = acc[4 * U + 4 * u + c], a3 = acc[4 * U + 4 * u + 2 + c];
+          s1[2 * u + c] = (a0 + a1) + (a2 + a3);
+          s2[2 * u + c] = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
+        }
+    } else {
+      // unit by unit: the unit's scale / shift pair once, its four rows' x pairs in flight together
+      int64_t roff[4];
+      bool rok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                         // i = 2h + hh
+        const int r = m0 + quadrant * 32 + 16 * (i >> 1) + 8 * (i & 1) + g;
+        rok[i] = r < p.m;                                   // (rows past m: zero accumulators, and nothing to read)
+        roff[i] = (int64_t)r * p.y_pitch + nbase;
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s1[2 * u] = s1[2 * u + 1] = s2[2 * u] = s2[2 * u + 1] = 0.f;
+        if (nbase + 8 * u >= p.cout) continue;
+        const float2 sc = __ldg(reinterpret_cast<const float2*>(p.bnb_scale + nbase + 8 * u));
+        const float2 sh = __ldg(reinterpret_cast<const float2*>(p.bnb_shift + nbase + 8 * u));
+        float2 xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xv[i] = make_float2(0.f, 0.f);
+          if (rok[i]) {
+            if (B16) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.bnb_x) + roff[i] + 8 * u);
+              xv[i] = make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+            } else {
+              xv[i] = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.bnb_x) + roff[i] + 8 * u);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v0 = acc[(i >> 1) * 4 * U + 4 * u + 2 * (i & 1)], v1 = acc[(i >> 1) * 4 * U + 4 * u + 2 * (i & 1) + 1];
+          if (B16) {                                        // the stored gradient is the bfloat16 rounding: sum what is stored
+            v0 = __bfloat162float(__float2bfloat16_rn(v0));
+            v1 = __bfloat162float(__float2bfloat16_rn(v1));
+          }
+          v0 = fmaf(xv[i].x, sc.x, sh.x) > 0.f ? v0 : 0.f;
+          v1 = fmaf(xv[i].y, sc.y, sh.y) > 0.f ? v1 : 0.f;
+          s1[2 * u] += v0;
+          s1[2 * u + 1] += v1;
+          s2[2 * u] = fmaf(v0, xv[i].x, s2[2 * u]);
+          s2[2 * u + 1] = fmaf(v1, xv[i].y, s2[2 * u + 1]);
+        }
+      }
+    }
     // halving butterfly over the 8 lanes of a column group: lane bit 4 keeps the upper / lower half of the values, ...
     int keep = 2 * U;                                       // number of values still held; they sit in s*[0 .. keep)
 #pragma unroll
@@ -634,7 +686,7 @@ __device__ __forceinline__ void epilogue_frag(const zsg_conv_params& p, const fl
       }
     }
     // values held now: k = kbase .. kbase + keep - 1 of the original 2U (k = 2u + c), kbase from the lane bits that chose halves
-    float* st1 = p.stats + ((int64_t)((m0 / TM) * 4 + quadrant) * 2) * p.cout;
+    float* st1 = stp + ((int64_t)((m0 / TM) * 4 + quadrant) * 2) * p.cout;
     float* st2 = st1 + p.cout;
     if (U == 8) {                                           // keep == 2: unit u = 4*b4 + 2*b3 + b2, both columns of the pair
       const int u = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -2831,6 +2883,13 @@ extern "C" int zsg_conv_fwd(const zsg_conv_params* pp, zsg_stream_t stream) {
   ZSG_REQUIRE(!p.row_add || (p.cout % 4 == 0 && (p.x_lo || p.x_bf16) && p.impl != 1 && !p.y_bf16 && !p.stats &&
                              (((uintptr_t)p.row_add & 15) | ((uintptr_t)p.row_add_idx & 7)) == 0),
               "zsg_conv_fwd: row_add needs cout %% 4 == 0, an operand-image input, the tcgen05 path and aligned tables");
+  ZSG_REQUIRE(!p.bnb_partials == !p.bnb_x && !p.bnb_partials == !p.bnb_scale && !p.bnb_partials == !p.bnb_shift,
+              "zsg_conv_fwd: bnb_x / bnb_scale / bnb_shift / bnb_partials go together");
+  ZSG_REQUIRE(!p.bnb_partials || (!p.stats && !p.y_lo && !p.y_img_bf16 && epilogue_is_plain(p) && p.impl != 1 && (p.x_lo || p.x_bf16) &&
+                                  p.cout % 8 == 0 && p.y_pitch > 0 && p.y_pitch % 2 == 0 &&
+                                  (((uintptr_t)p.bnb_x | (uintptr_t)p.bnb_scale | (uintptr_t)p.bnb_shift | (uintptr_t)p.bnb_partials) & 7) == 0),
+              "zsg_conv_fwd: bnb_* (BatchNorm backward sums from a data gradient's epilogue) need a plain [m, y_pitch] output "
+              "(fp32 y with fp32 bnb_x, or y_bf16 with bfloat16 bnb_x), cout %% 8 == 0, the operand-image tcgen05 paths");
   ZSG_REQUIRE(!p.stats || (!p.bias && !p.out_relu && !p.out_mask && !p.residual && !p.residual_bf16 && !p.accumulate && p.impl != 1),
               "zsg_conv_fwd: stats needs a plain output (no bias / ReLU / mask / residual / accumulate) on the tcgen05 path");
   cudaStream_t st = as_stream(stream);

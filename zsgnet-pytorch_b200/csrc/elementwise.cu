@@ -1363,6 +1363,18 @@ extern "C" int zsg_bn_stats_partials(const float* partials, int64_t parts, int c
   return check_launch("zsg_bn_stats_partials");
 }
 
+__global__ void bn_bwd_center_sums_kernel(double* __restrict__ sums, const float* __restrict__ mean,
+                                          const float* __restrict__ invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) sums[C + c] = (double)invstd[c] * (sums[C + c] - (double)mean[c] * sums[c]);
+}
+
+extern "C" int zsg_bn_bwd_center_sums(double* sums, const float* mean, const float* invstd, int c, zsg_stream_t stream) {
+  ZSG_REQUIRE(sums && mean && invstd && c > 0, "zsg_bn_bwd_center_sums: bad arguments");
+  bn_bwd_center_sums_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, mean, invstd, c);
+  return check_launch("zsg_bn_bwd_center_sums");
+}
+
 extern "C" int zsg_bn_finalize_partials(const float* partials, int64_t parts, int64_t rows, int c, const float* gamma,
                                         const float* beta, float eps, float momentum, float* running_mean,
                                         float* running_var, float* mean, float* invstd, float* scale, float* shift,

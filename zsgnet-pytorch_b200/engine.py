@@ -89,6 +89,8 @@ class _BN:
 class Engine:
     def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC, dtype="fp32", do_norm=False):
         self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
+        # BatchNorm backward sums from the producing data gradient's epilogue (ZSG_BNB_FUSE=0: the separate reduce pass)
+        self.fuse_bnb = os.environ.get("ZSG_BNB_FUSE", "1") != "0" and impl == ops.IMPL_TC
         self.do_norm = bool(do_norm)                      # cfg do_norm (mdl.py:118-130): L2-normalised feature pixels / language vector
         assert dtype in ("fp32", "bf16"), dtype
         # dtype = arithmetic of the dense contractions.  "fp32": 3xTF32 (BASELINE configs[1], the reference's fp32 results to
@@ -321,7 +323,7 @@ class Engine:
         """operand image of the output gradient of conv L (shared by its wgrad and dgrad; bf16 iff the conv is)."""
         return self.bwd_operand(dy, self.B * L["hout"] * L["wout"], L["cout"], b16=L["b16"])
 
-    def conv_dgrad(self, L, dy, dy_lo, dx, out_mask=None, residual=None, accumulate=False):
+    def conv_dgrad(self, L, dy, dy_lo, dx, out_mask=None, residual=None, accumulate=False, bnb=None):
         k, cin, cout, stride = L["k"], L["cin"], L["cout"], L["stride"]
         b16 = L["b16"]
         assert not b16 or cout % 8 == 0, "bf16 data gradient needs cout % 8 == 0"
@@ -361,9 +363,21 @@ class Engine:
             self.bwd.append(ConvOp(dy, wt_hi, dx, rows, rows.shape[0], cout, cin, 1, 1, w_lo=wt_lo, x_lo=dy_lo, **epi))
             return
         rows = self.rows("dgrad", L["hin"], L["win"], cin, L["hout"], L["wout"], cout, k, stride, L["pad"], L["dil"])
-        self.bwd.append(ConvOp(dy, wt_hi, dx, rows, self.B * L["hin"] * L["win"], cout, cin, k, k, in_div=stride,
+        m = self.B * L["hin"] * L["win"]
+        fused = None
+        if (bnb is not None and self.fuse_bnb and stride == 1 and cin % 8 == 0 and out_mask is None and residual is None
+                and not accumulate):
+            # BatchNorm backward sums of the BatchNorm+ReLU in front of this conv, from this launch's epilogue: returns the
+            # (partials, parts) the caller hands to bn_backward(); bnb = (bn, x) with x the BatchNorm's input [m, cin]
+            bn, xin = bnb
+            parts = (m + 127) // 128 * 4
+            assert parts * 2 * cin <= self._stats_scratch.numel() and bn.c == cin and bn.rows == m
+            fused = (self._stats_scratch, parts)
+            epi["bnb"] = (xin, bn.scale, bn.shift, self._stats_scratch)
+        self.bwd.append(ConvOp(dy, wt_hi, dx, rows, m, cout, cin, k, k, in_div=stride,
                                w_lo=wt_lo, x_lo=dy_lo, dil=L["dil"], x_plain=(k == 1 and stride == 1 and L["pad"] == 0),
                                y_pitch=cin, **epi))                    # dgrad_rows: one row per input pixel, out = i * cin
+        return fused
 
     def queue_transpose(self, w, wt, cout, k, cin):
         """Flipped-transposed copy of a conv weight for its data gradient.  Copies from the parameter arena into the
@@ -375,13 +389,20 @@ class Engine:
         else:
             self.prep_bwd.append(lambda: ops.weight_transpose_flip(w, wt, cout, k, k, cin))
 
-    def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True, b16=False):
-        """BatchNorm backward; returns the operand image of dx (written by the same kernel) for the GEMMs that follow."""
+    def bn_backward(self, bn, dy, x, dx, mask_mode, act_out=None, dz_out=None, want_lo=True, b16=False, partials=None):
+        """BatchNorm backward; returns the operand image of dx (written by the same kernel) for the GEMMs that follow.
+        partials = (buffer, parts) from conv_dgrad(..., bnb=...): the reduce pass already happened in the epilogue of the
+        data gradient that wrote dy (sum dz, sum dz * x per 32-row group); two small launches finish it."""
         dx_lo = self.bwd_lo_buffer(dx, bn.rows, bn.c, b16) if want_lo else None
+        assert partials is None or (mask_mode == 1 and dz_out is None)
 
         def run():
-            ops.bn_bwd_reduce(dy, x, bn.mean, bn.invstd, bn.bsums, bn.rows, bn.c, mask_mode=mask_mode, scale=bn.scale,
-                              shift=bn.shift, act_out=act_out, dz_out=dz_out)
+            if partials is not None:
+                ops.bn_stats_partials(partials[0], partials[1], bn.c, bn.bsums)
+                ops.bn_bwd_center_sums(bn.bsums, bn.mean, bn.invstd, bn.c)
+            else:
+                ops.bn_bwd_reduce(dy, x, bn.mean, bn.invstd, bn.bsums, bn.rows, bn.c, mask_mode=mask_mode, scale=bn.scale,
+                                  shift=bn.shift, act_out=act_out, dz_out=dz_out)
             src = dz_out if dz_out is not None else dy
             mm = 0 if dz_out is not None else mask_mode
             # bf16 engine: the gradient w.r.t. the conv output is only read by that conv's two backward GEMMs, through the
@@ -541,11 +562,11 @@ class Engine:
                 lo3 = self.bn_backward(L["bnC"], L["g_out"], L["r3"], dr3, mask_mode=2, act_out=L["out"], dz_out=dz,
                                        b16=L["Lc"]["b16"])
                 self.conv_wgrad(L["Lc"], dr3, lo3)
-                self.conv_dgrad(L["Lc"], dr3, lo3, da2)
-                lo2 = self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1, b16=L["Lb"]["b16"])
+                pB = self.conv_dgrad(L["Lc"], dr3, lo3, da2, bnb=(L["bnB"], L["r2"]))
+                lo2 = self.bn_backward(L["bnB"], da2, L["r2"], da2, mask_mode=1, b16=L["Lb"]["b16"], partials=pB)
                 self.conv_wgrad(L["Lb"], da2, lo2)
-                self.conv_dgrad(L["Lb"], da2, lo2, da1)
-                lo1 = self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1, b16=L["La"]["b16"])
+                pA = self.conv_dgrad(L["Lb"], da2, lo2, da1, bnb=(L["bnA"], L["r1"]))
+                lo1 = self.bn_backward(L["bnA"], da1, L["r1"], da1, mask_mode=1, b16=L["La"]["b16"], partials=pA)
                 self.conv_wgrad(L["La"], da1, lo1)
                 if L["Ld"] is not None:
                     drd = sB[:ro * w4]

@@ -45,8 +45,10 @@ class ConvOp:
 
     def __init__(self, x, w, y, rows, m, cin, cout, r, s, in_div=1, in_scale=None, in_shift=None, in_relu=False,
                  bias=None, out_relu=False, out_mask=None, residual=None, accumulate=False, impl=IMPL_TC, w_lo=None,
-                 x_lo=None, dil=1, stats=None, x_plain=False, y_pitch=0, row_add=None, row_add_idx=None, y_img=None):
-        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats, row_add, row_add_idx, y_img)
+                 x_lo=None, dil=1, stats=None, x_plain=False, y_pitch=0, row_add=None, row_add_idx=None, y_img=None, bnb=None):
+        # bnb = (x, scale, shift, partials): BatchNorm backward sums as a by-product of this data gradient (zsg_conv_params.bnb_*)
+        bnb = bnb if bnb is not None else (None, None, None, None)
+        self.keep = (x, w, w_lo, y, rows, in_scale, in_shift, bias, out_mask, residual, x_lo, stats, row_add, row_add_idx, y_img, bnb)
         yb = None
         if _is_bf16(y):                                      # bf16 storage: the output tensor itself is bfloat16
             y, yb = None, y
@@ -65,7 +67,8 @@ class ConvOp:
                             impl, ptr(x_lo), dil, ptr(stats), ptr(xb), ptr(wb), int(bool(x_plain)), ptr(yb), ptr(rb), int(y_pitch),
                             ptr(row_add), ptr(row_add_idx),
                             # y_img: the operand image of the output, written by the epilogue (fp32 = TF32 remainders, bf16 = copy)
-                            ptr(None if _is_bf16(y_img) else y_img), ptr(y_img if _is_bf16(y_img) else None))
+                            ptr(None if _is_bf16(y_img) else y_img), ptr(y_img if _is_bf16(y_img) else None),
+                            ptr(bnb[0]), ptr(bnb[1]), ptr(bnb[2]), ptr(bnb[3]))
         if y_pitch and rows.is_cuda:                         # the claim is checked once, when the launch is described
             out = rows.view(torch.int32).view(-1, 4)[:m, 3].to(torch.int64)
             assert bool((out == torch.arange(m, device=rows.device) * y_pitch).all()), "y_pitch does not describe this row table"
@@ -185,6 +188,10 @@ def bn_stats(x, sums, rows, c):
 
 def bn_stats_partials(partials, parts, c, sums):
     call("zsg_bn_stats_partials", ptr(partials), parts, c, ptr(sums), stream())
+
+
+def bn_bwd_center_sums(sums, mean, invstd, c):
+    call("zsg_bn_bwd_center_sums", ptr(sums), ptr(mean), ptr(invstd), c, stream())
 
 
 def bn_finalize_partials(partials, parts, rows, c, gamma, beta, eps, momentum, rm, rv, mean, invstd, scale, shift, sums,
