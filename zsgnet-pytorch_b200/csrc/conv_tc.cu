@@ -981,6 +981,20 @@ __device__ __forceinline__ void conv_epilogue_wide(const zsg_conv_params& p, con
         }
       }
     }
+    if (EPI != EPI_FRAGX && p.bnb_partials) {                // BatchNorm input rows of the next tile (backward sums)
+      const int ntile = tile + gridDim.x;
+      if (ntile < total_tiles) {
+        const int nn0 = (ntile % tiles_n) * BN + half * 128, nm = (ntile / tiles_n) * TM + row;
+        if (nm < p.m && nn0 < p.cout) {
+          const int64_t e = (int64_t)nm * p.y_pitch + nn0;
+          if (EPI == EPI_B16) {
+            for (int c = 0; c < 128; c += 64) prefetch_l2(reinterpret_cast<const uint16_t*>(p.bnb_x) + e + c);
+          } else {
+            for (int c = 0; c < 128; c += 32) prefetch_l2(reinterpret_cast<const float*>(p.bnb_x) + e + c);
+          }
+        }
+      }
+    }
     const uint32_t a = nt & 1u;
     mbar_wait(pb.acc_full(a), (nt >> 1) & 1u, 2000 + nt);
     tc_fence_after();
@@ -1037,6 +1051,20 @@ __device__ __forceinline__ void conv_epilogue(const zsg_conv_params& p, uint8_t*
               if (p.residual) prefetch_l2(p.residual + e + c);
               if (p.out_mask) prefetch_l2(p.out_mask + e + c);
               if (p.accumulate) prefetch_l2(p.y + e + c);
+            }
+          }
+        }
+      }
+      if (EPI != EPI_FRAGX && p.bnb_partials) {              // the BatchNorm input rows of the NEXT tile (backward sums): into L2 now
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles) {
+          const int nn0 = (nt % tiles_n) * BN + half * (BN / 2), nm = (nt / tiles_n) * TM + row;
+          if (nm < p.m && nn0 < p.cout) {
+            const int64_t e = (int64_t)nm * p.y_pitch + nn0;
+            if (EPI == EPI_B16) {
+              for (int c = 0; c < BN / 2; c += 64) prefetch_l2(reinterpret_cast<const uint16_t*>(p.bnb_x) + e + c);
+            } else {
+              for (int c = 0; c < BN / 2; c += 32) prefetch_l2(reinterpret_cast<const float*>(p.bnb_x) + e + c);
             }
           }
         }
