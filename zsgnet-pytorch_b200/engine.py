@@ -89,8 +89,11 @@ class _BN:
 class Engine:
     def __init__(self, store, buffers, B, T, device, impl=ops.IMPL_TC, dtype="fp32", do_norm=False):
         self.store, self.buffers, self.B, self.T, self.device, self.impl = store, buffers, B, T, device, impl
-        # BatchNorm backward sums from the producing data gradient's epilogue (ZSG_BNB_FUSE=0: the separate reduce pass)
-        self.fuse_bnb = os.environ.get("ZSG_BNB_FUSE", "1") != "0" and impl == ops.IMPL_TC
+        # BatchNorm backward sums from the producing data gradient's epilogue.  ZSG_BNB_FUSE = 0: the separate reduce pass,
+        # 1: fused, unset: fused on the fp32 engine only (measured: -0.35 ms per fp32 step; on the bf16 engine the step does not
+        # change -- the bf16 reduce passes hide next to the side-stream weight gradients -- and the data gradients get slower)
+        self._fuse_bnb_env = os.environ.get("ZSG_BNB_FUSE", "")
+        self.fuse_bnb = impl == ops.IMPL_TC and self._fuse_bnb_env != "0"
         self.do_norm = bool(do_norm)                      # cfg do_norm (mdl.py:118-130): L2-normalised feature pixels / language vector
         assert dtype in ("fp32", "bf16"), dtype
         # dtype = arithmetic of the dense contractions.  "fp32": 3xTF32 (BASELINE configs[1], the reference's fp32 results to
@@ -108,6 +111,8 @@ class Engine:
         # The first head conv without the concatenated [feat | lang | grid] tensor (a-6 at 0 bytes): a K = 2304 GEMM over feat
         # whose epilogue adds per-row language / grid terms; ZSG_SPLIT_HEAD0=0 keeps the materialised K = 520 x 9 formulation
         self.split_head0 = impl == ops.IMPL_TC and os.environ.get("ZSG_SPLIT_HEAD0", "1") != "0"
+        if self.bf16 and self._fuse_bnb_env != "1":          # (see fuse_bnb above: default off on the bf16 engine)
+            self.fuse_bnb = False
         self._rows_cache = {}
         self._operand_cache, self._bwd_lo = {}, {}
         self._side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
