@@ -2068,8 +2068,12 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
     const int4* rows = reinterpret_cast<const int4*>(p.rows);
     int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 64;       // [2][32] entries per group
     const uint32_t tiles0 = smem_u32(sm);
-    const int tap0 = __shfl_sync(0xffffffffu, tap, 0);        // (outside the &&: every lane must take part)
-    const bool warp_uniform = __all_sync(0xffffffffu, jvalid && tap == tap0) != 0;
+    // every group of 8 lanes (32 channels) lies inside one tap and is valid or not as a whole (cin % 32 == 0): each lane then
+    // decodes ONE pixel per K block for its group's tap and the group exchanges the offsets (the per-lane decode of all 8
+    // pixels was most of the producers' issue slots; with whole-warp uniformity only, the 64-channel layers fell back to it)
+    const int tap0 = __shfl_sync(0xffffffffu, tap, lane & 24);      // (outside the &&: every lane must take part)
+    const int jv0 = __shfl_sync(0xffffffffu, (int)jvalid, lane & 24);
+    const bool warp_uniform = __all_sync(0xffffffffu, tap == tap0 && (int)jvalid == jv0) != 0;
     // prologue: entries of this group's first K block
     if (group < nkb) {
       if (t < 32) {
@@ -2106,16 +2110,16 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
         __syncwarp();
       }
       if (warp_uniform) {
-        // one tap for the whole warp: lane q decodes pixel q * 4 + ps once, the offsets are broadcast
+        // lane (group, q) decodes pixel q * 4 + ps once for its group's tap, the group exchanges the offsets
         const int4 e = eb[(lane & 7) * 4 + ps];
         const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
         const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-        const bool oka = (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+        const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
         const int my_ao = oka ? e.x + (yy * win + xx) * p.cin : -1;
         const int my_bo = hin > 0 ? e.w : -1;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int ao = __shfl_sync(0xffffffffu, my_ao, q), bo = __shfl_sync(0xffffffffu, my_bo, q);
+          const int ao = __shfl_sync(0xffffffffu, my_ao, (lane & 24) + q), bo = __shfl_sync(0xffffffffu, my_bo, (lane & 24) + q);
           const int pixel = q * 4 + ps;
           const int r4 = ps;                                 // pixel & 3
           const uint32_t off = atom_off + q * 512 + r4 * 128 + ((((cj >> 1) ^ r4) << 1) | (cj & 1)) * 16;
@@ -2223,8 +2227,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
     int tap = 0, c = 0, tr = 0, ts = 0;
     if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
     const uint16_t* xb = p.x_bf16 + c;
-    const int tap0 = __shfl_sync(0xffffffffu, tap, 0);        // (outside the &&: every lane must take part)
-    const bool warp_uniform = __all_sync(0xffffffffu, jvalid && tap == tap0) != 0;
+    // every group of 8 lanes (64 channels) inside one tap, valid or not as a whole (cin % 64 == 0): see the fp32 kernel
+    const int tap0 = __shfl_sync(0xffffffffu, tap, lane & 24);      // (outside the &&: every lane must take part)
+    const int jv0 = __shfl_sync(0xffffffffu, (int)jvalid, lane & 24);
+    const bool warp_uniform = __all_sync(0xffffffffu, tap == tap0 && (int)jvalid == jv0) != 0;
     const int4* rows = reinterpret_cast<const int4*>(p.rows);
     int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 128;      // [2][64] entries per group
     const uint32_t tiles0 = smem_u32(sm);
@@ -2261,16 +2267,16 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
         __syncwarp();
       }
       if (warp_uniform) {
-        // one tap for the whole warp (cin >= 128): the warp's 16 (q, ps) pixels are decoded once, by lanes 0-15 (the upper half-warp
-        // repeats them), and the offsets are broadcast -- eight decodes per lane were most of the producers' issue slots
-        const int4 e = eb[(lane & 7) * 8 + 2 * (t >> 5) + ((lane >> 3) & 1)];
+        // each lane decodes ONE pixel (row q = lane & 7 of its own column ps) for its 8-lane group's tap and the group
+        // exchanges the offsets -- eight decodes per lane were most of the producers' issue slots
+        const int4 e = eb[(lane & 7) * 8 + ps];          // my group's tap, my pixel column ps, pixel row q = lane & 7
         const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
         const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-        const bool oka = (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+        const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
         const int my_ao = oka ? e.x + (yy * win + xx) * p.cin : -1;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int ao = __shfl_sync(0xffffffffu, my_ao, q + ((lane >> 4) << 3));
+          const int ao = __shfl_sync(0xffffffffu, my_ao, (lane & 24) + q);
           cp_async16(a_tile + toff + q * 1024, xb + max(ao, 0), ao < 0 ? 0u : 16u);   // padding: 0 bytes from a valid address
         }
       } else {
@@ -2384,8 +2390,9 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_wide_kernel(const zsg
       int tap = 0, c = 0, tr = 0, ts = 0;
       if (jvalid) { tap = j / p.cin; c = j - tap * p.cin; tr = tap / p.s; ts = tap - tr * p.s; }
       const uint16_t* xb = p.x_bf16 + c;
-      const int tap0 = __shfl_sync(0xffffffffu, tap, 0);
-      const bool warp_uniform = __all_sync(0xffffffffu, jvalid && tap == tap0) != 0;
+      const int tap0 = __shfl_sync(0xffffffffu, tap, lane & 24);     // groups of 8 lanes (64 channels): see the fp32 kernel
+      const int jv0 = __shfl_sync(0xffffffffu, (int)jvalid, lane & 24);
+      const bool warp_uniform = __all_sync(0xffffffffu, tap == tap0 && (int)jvalid == jv0) != 0;
       const int first = (group - g0) & 1;                   // K blocks with (g0 + i) % NGROUP == group
       asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");   // the previous unit's entries have been read
       if (first < nkb && t < KBP) {
@@ -2419,16 +2426,16 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_wide_kernel(const zsg
           __syncwarp();
         }
         if (warp_uniform) {
-          // one tap for the whole warp (cin >= 128): the warp's 16 (q, ps) pixels are decoded once, by lanes 0-15 (the upper half-warp
-          // repeats them), and the offsets are broadcast -- eight decodes per lane were most of the producers' issue slots
-          const int4 e = eb[(lane & 7) * 8 + 2 * (t >> 5) + ((lane >> 3) & 1)];
+          // each lane decodes ONE pixel (row q = lane & 7 of its own column ps) for its 8-lane group's tap and the group
+          // exchanges the offsets -- eight decodes per lane were most of the producers' issue slots
+          const int4 e = eb[(lane & 7) * 8 + ps];          // my group's tap, my pixel column ps, pixel row q = lane & 7
           const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
           const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
-          const bool oka = (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
+          const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
           const int my_ao = oka ? e.x + (yy * win + xx) * p.cin : -1;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int ao = __shfl_sync(0xffffffffu, my_ao, q + ((lane >> 4) << 3));
+            const int ao = __shfl_sync(0xffffffffu, my_ao, (lane & 24) + q);
             cp_async16(a_tile + toff + q * 1024, xb + max(ao, 0), ao < 0 ? 0u : 16u);   // padding: 0 bytes from a valid address
           }
         } else {
