@@ -415,14 +415,30 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(uint8_t* __restrict_
   __shared__ int bad_s;
   constexpr int SROWS = 1024;                                       // rows kept in shared memory for the serial row-order sum
   __shared__ double s_cls[SROWS], s_box[SROWS];
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const double2* t = tiles + (size_t)b * LOSS_MAX_TILES;
+  // LPR lanes per row (a power of two, 256 / B clamped to 1..32): lane `sub` adds the slots sub, sub + LPR, ... in order, a
+  // butterfly adds the lanes -- a fixed order, so the scalars stay bit-reproducible -- instead of one thread walking all of a
+  // row's slots through dependent L2 round trips (that chain was ~3 us of the 8 us this one-block kernel takes at B = 64)
+  int lpr = 1;
+  while (lpr < 32 && lpr * 2 * B <= (int)blockDim.x) lpr *= 2;
+  const int rows_per_pass = blockDim.x / lpr;
+  const int sub = threadIdx.x % lpr;
+  for (int b0 = 0; b0 < B; b0 += rows_per_pass) {                     // (uniform trip count: the shuffles below are warp-wide)
+    const int b = b0 + threadIdx.x / lpr;
     double rc = 0.0, rb = 0.0;
-    for (int i = 0; i < ntiles; ++i) { rc += t[i].x; rb += t[i].y; }
-    rb = rb / (double)(float)npos_row[b];                           // loss.py:93: row sum / positives of the row (float count)
-    row_cls[b] = rc;
-    row_box[b] = rb;
-    if (b < SROWS) { s_cls[b] = rc; s_box[b] = rb; }
+    if (b < B) {
+      const double2* t = tiles + (size_t)b * LOSS_MAX_TILES;
+      for (int i = sub; i < ntiles; i += lpr) { rc += t[i].x; rb += t[i].y; }
+    }
+    for (int off = lpr >> 1; off > 0; off >>= 1) {
+      rc += __shfl_xor_sync(0xffffffffu, rc, off);
+      rb += __shfl_xor_sync(0xffffffffu, rb, off);
+    }
+    if (b < B && sub == 0) {
+      rb = rb / (double)(float)npos_row[b];                         // loss.py:93: row sum / positives of the row (float count)
+      row_cls[b] = rc;
+      row_box[b] = rb;
+      if (b < SROWS) { s_cls[b] = rc; s_box[b] = rb; }
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
