@@ -158,6 +158,8 @@ int main(int argc, char** argv) {
     run<0, 256>("tf32 SS + STS", 4, 0);
     run<0, 128>("tf32 SS + paced STS", 4, 40);
     run<0, 256>("tf32 SS + paced STS", 4, 40);
+    run<2, 128>("tf32 SS MN-major (weight gradient)", 0, 0);
+    run<2, 128>("tf32 SS MN-major + STS", 4, 0);
     return 0;
   }
   run<0, 128>("plain", 0, 0, 6000, 0);
