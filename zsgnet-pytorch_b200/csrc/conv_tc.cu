@@ -2074,24 +2074,15 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
     const int tap0 = __shfl_sync(0xffffffffu, tap, lane & 24);      // (outside the &&: every lane must take part)
     const int jv0 = __shfl_sync(0xffffffffu, (int)jvalid, lane & 24);
     const bool warp_uniform = __all_sync(0xffffffffu, tap == tap0 && (int)jvalid == jv0) != 0;
-    // Row entries of a K block.  Shared-decode path (warp_uniform, the same for the four warps of a group): a lane needs ONE
-    // entry per K block, pixel (lane & 7) * 4 + ps; it fetches it itself one K block ahead into a register -- no staging in
-    // shared memory and no group barrier per K block.  Otherwise: the 32 entries of a K block are staged by the first warp.
-    const int my_pl = (lane & 7) * 4 + ps;
-    int4 e_cur = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
+    // prologue: entries of this group's first K block
     if (group < nkb) {
-      if (warp_uniform) {
-        const int pix = (kb_begin + group) * KB + my_pl;
-        if (pix < p.m) e_cur = __ldg(rows + pix);
-      } else {
-        if (t < 32) {
-          int4 e = make_int4(0, 0, 0, 0);
-          const int pix = (kb_begin + group) * KB + t;
-          if (pix < p.m) e = __ldg(rows + pix);
-          ent[t] = e;
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      if (t < 32) {
+        int4 e = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
+        const int pix = (kb_begin + group) * KB + t;
+        if (pix < p.m) e = __ldg(rows + pix);
+        ent[t] = e;
       }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
     }
     int it = 0;
     for (int i = group; i < nkb; i += NGROUP, ++it) {
@@ -2099,8 +2090,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
       const int4* eb = ent + (it & 1) * 32;
       int4 e_next = make_int4(0, 0, 0, 0);                   // entries of my next K block: in flight during this one
       const bool has_next = i + NGROUP < nkb;
-      if (has_next && (warp_uniform || t < 32)) {
-        const int pix = (kb_begin + i + NGROUP) * KB + (warp_uniform ? my_pl : t);
+      if (has_next && t < 32) {
+        const int pix = (kb_begin + i + NGROUP) * KB + t;
         if (pix < p.m) e_next = __ldg(rows + pix);
       }
       mbar_wait(pb.empty(s), ((i / S::STAGES) & 1) ^ 1, 5000 + i);
@@ -2119,8 +2110,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
         __syncwarp();
       }
       if (warp_uniform) {
-        // lane (group, q) decodes pixel q * 4 + ps once for its group's tap, the group exchanges the offsets
-        const int4 e = e_cur;
+        // lane (group, q) decodes pixel q * 4 + ps once for its group's tap, the group exchanges the offsets.  (The register
+        // prefetch of the entry that the bf16 kernels use instead of this shared-memory staging made this kernel spill at its 56
+        // producer registers and gained nothing: 213 TFLOP/s either way.)
+        const int4 e = eb[(lane & 7) * 4 + ps];
         const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
         const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
         const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
@@ -2163,9 +2156,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_tc_async_kernel(const zsg_
         }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
-      if (warp_uniform) {
-        e_cur = e_next;
-      } else if (has_next) {
+      if (has_next) {
         if (t < 32) ent[((it + 1) & 1) * 32 + t] = e_next;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
       }
@@ -2245,23 +2236,16 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
     const int4* rows = reinterpret_cast<const int4*>(p.rows);
     int4* ent = reinterpret_cast<int4*>(sm + S::ROWS_OFF) + group * 128;      // [2][64] entries per group
     const uint32_t tiles0 = smem_u32(sm);
-    // row entries of a K block: one per lane, fetched a K block ahead into a register on the shared-decode path (no staging, no
-    // group barrier per K block); staged through shared memory otherwise (see wgrad_tc_async_kernel)
-    const int my_pl = (lane & 7) * 8 + ps;
-    int4 e_cur = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
+    // prologue: entries of this group's first K block (staged through shared memory; the register prefetch of the wide kernel
+    // makes the 64-column instance of this one spill at its 56 producer registers)
     if (group < nkb) {
-      if (warp_uniform) {
-        const int pix = (kb_begin + group) * KBP + my_pl;
-        if (pix < p.m) e_cur = __ldg(rows + pix);
-      } else {
-        if (t < KBP) {
-          int4 e = make_int4(0, 0, 0, 0);
-          const int pix = (kb_begin + group) * KBP + t;
-          if (pix < p.m) e = __ldg(rows + pix);
-          ent[t] = e;
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
+      if (t < KBP) {
+        int4 e = make_int4(0, 0, 0, 0);                      // hin = 0 => masked (also past the last pixel)
+        const int pix = (kb_begin + group) * KBP + t;
+        if (pix < p.m) e = __ldg(rows + pix);
+        ent[t] = e;
       }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
     }
     int it = 0;
     for (int i = group; i < nkb; i += NGROUP, ++it) {
@@ -2269,8 +2253,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
       const int4* eb = ent + (it & 1) * KBP;
       int4 e_next = make_int4(0, 0, 0, 0);                   // entries of my next K block: in flight during this one
       const bool has_next = i + NGROUP < nkb;
-      if (has_next && (warp_uniform || t < KBP)) {
-        const int pix = (kb_begin + i + NGROUP) * KBP + (warp_uniform ? my_pl : t);
+      if (has_next && t < KBP) {
+        const int pix = (kb_begin + i + NGROUP) * KBP + t;
         if (pix < p.m) e_next = __ldg(rows + pix);
       }
       mbar_wait(pb.empty(s), ((i / S::STAGES) & 1) ^ 1, 5000 + i);
@@ -2288,7 +2272,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
       if (warp_uniform) {
         // each lane decodes ONE pixel (row q = lane & 7 of its own column ps) for its 8-lane group's tap and the group
         // exchanges the offsets -- eight decodes per lane were most of the producers' issue slots
-        const int4 e = e_cur;                            // my group's tap, my pixel column ps, pixel row q = lane & 7
+        const int4 e = eb[(lane & 7) * 8 + ps];          // my group's tap, my pixel column ps, pixel row q = lane & 7
         const int yy = (int)(short)(e.y & 0xFFFF) + tr * p.dil, xx = (e.y >> 16) + ts * p.dil;
         const int hin = (int)(short)(e.z & 0xFFFF), win = e.z >> 16;
         const bool oka = jvalid && (unsigned)yy < (unsigned)hin && (unsigned)xx < (unsigned)win;
@@ -2310,9 +2294,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) wgrad_bf16_kernel(const zsg_wgra
         }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pb.full(s)) : "memory");
-      if (warp_uniform) {
-        e_cur = e_next;
-      } else if (has_next) {
+      if (has_next) {
         if (t < KBP) ent[((it + 1) & 1) * KBP + t] = e_next;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(NPROD) : "memory");
       }
